@@ -1,0 +1,422 @@
+"""ORACLE bindings -- test infrastructure, not product code.
+
+Two CPU implementations of the reference hot path behind ONE numpy-facing API, so a test can run the
+same check against either:
+
+* ``load_ref(mt=False)``  -> oracle/_ref/liblimu_ref(.so|_mt.so): the reference's UNMODIFIED sources
+  (Oreoluwa-Se/Lidar-Imu-Slam env_ws/src/limu) compiled by oracle/Makefile against the vendored
+  Eigen/Sophus tarballs and the shims in oracle/shims. Prebuilt in the authoring container; travels to
+  the GPU box as a binary (``/root/reference`` does not exist there).
+* ``load_port()``        -> oracle/build/liblimu_oracle.so: the plain-C restatement (limu_oracle.c),
+  buildable anywhere gcc exists.
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's ``cpu_baseline`` / ``--impl reference`` legs may
+import this package. The product (``lidar-imu-slam_b200``) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "liblimu_ref.so")
+REF_MT_SO = os.path.join(HERE, "_ref", "liblimu_ref_mt.so")
+PORT_SO = os.path.join(HERE, "build", "liblimu_oracle.so")
+
+_dp = C.POINTER(C.c_double)
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int)
+_lp = C.POINTER(C.c_long)
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _f(a):
+    return a.ctypes.data_as(_fp) if a is not None else None
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip) if a is not None else None
+
+
+def _l(a):
+    return a.ctypes.data_as(_lp) if a is not None else None
+
+
+def _pts(x):
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)
+    return x
+
+
+def build_port(force: bool = False) -> str:
+    """Compile the C restatement (gcc only)."""
+    if force or not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < os.path.getmtime(os.path.join(HERE, "limu_oracle.c")):
+        subprocess.check_call(["make", "-s", "-C", HERE, "port"])
+    return PORT_SO
+
+
+def build_ref() -> bool:
+    """Compile the reference itself; only possible where /root/reference exists."""
+    if not os.path.isdir("/root/reference/env_ws/src/limu"):
+        return os.path.exists(REF_SO)
+    subprocess.check_call(["make", "-s", "-j2", "-C", HERE, "ref"])
+    return True
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+class _Api:
+    """Uniform API. ``p`` is the symbol prefix ('ref_' or 'lo_'); ``kind`` is 'reference' or 'port'."""
+
+    def __init__(self, lib, p, kind):
+        self.lib, self.p, self.kind = lib, p, kind
+        f = self._f
+        f("vox_index", None, [_dp, C.c_long, C.c_double, _ip])
+        f("transform", None, [_dp, _dp, C.c_long])
+        f("se3_exp", None, [_dp, _dp])
+        f("se3_log", None, [_dp, _dp])
+        f("se3_mul", None, [_dp, _dp, _dp])
+        f("se3_inv", None, [_dp, _dp])
+        f("delta_pose", None, [_dp, _dp, _dp])
+        f("map_create", C.c_void_p, [C.c_double, C.c_double, C.c_int])
+        f("map_destroy", None, [C.c_void_p])
+        f("map_clear", None, [C.c_void_p])
+        f("map_empty", C.c_int, [C.c_void_p])
+        f("map_num_voxels", C.c_long, [C.c_void_p])
+        f("map_insert", None, [C.c_void_p, _dp, C.c_long])
+        f("map_update", None, [C.c_void_p, _dp, C.c_long, _dp])
+        f("map_remove_far", None, [C.c_void_p, _dp])
+        f("map_dump", C.c_long, [C.c_void_p, _ip, _ip, _dp, C.c_long, C.c_long, _lp])
+        f("deskew", None, [_fp, _dp, C.c_long, _dp, _dp, _dp])
+        if kind == "reference":
+            f("map_closest", None, [C.c_void_p, _dp, C.c_long, _dp])
+            f("map_correspondences", C.c_long, [C.c_void_p, _dp, C.c_long, C.c_double, _dp, _dp])
+            f("align", None, [_dp, _dp, C.c_long, C.c_double, _dp])
+            f("icp", None, [C.c_void_p, _dp, C.c_long, _dp, C.c_double, C.c_double, C.c_int, C.c_double, _dp])
+            f("icp_trace", C.c_int, [C.c_void_p, _dp, C.c_long, _dp, C.c_double, C.c_double, C.c_int, C.c_double, _dp, _dp, _lp, _dp])
+            f("threshold_create", C.c_void_p, [C.c_double, C.c_double, C.c_double])
+            f("threshold_destroy", None, [C.c_void_p])
+            f("threshold_step", C.c_double, [C.c_void_p, _dp])
+            f("voxel_downsample", C.c_long, [C.c_void_p, _dp, C.c_long, C.c_double, _dp])
+            f("voxelize", None, [C.c_void_p, _dp, C.c_long, C.c_double, _dp, _lp, _dp, _lp])
+            f("iqr", C.c_long, [C.c_void_p, _dp, C.c_long, _dp])
+            f("num_threads", C.c_int, [])
+        else:
+            f("map_closest", None, [C.c_void_p, _dp, C.c_long, _dp, _ip, _ip])
+            f("map_correspondences", C.c_long, [C.c_void_p, _dp, C.c_long, C.c_double, _dp, _dp, _lp])
+            f("align", None, [_dp, _dp, C.c_long, C.c_double, _dp, _dp, _dp, _dp])
+            f("icp", C.c_int, [C.c_void_p, _dp, C.c_long, _dp, C.c_double, C.c_double, C.c_int, C.c_double, _dp, _dp, _lp, _dp, _dp])
+            f("threshold_init", None, [C.c_void_p, C.c_double, C.c_double, C.c_double])
+            f("threshold_step", C.c_double, [C.c_void_p, _dp])
+            f("voxel_downsample", C.c_long, [_dp, C.c_long, C.c_double, _dp, _lp])
+            f("voxelize", None, [_dp, C.c_long, C.c_double, _dp, _lp, _dp, _lp])
+            f("iqr", C.c_long, [_dp, C.c_long, _dp, _dp])
+            f("kiss_last_iterations", C.c_int, [C.c_void_p])
+            f("kiss_last_sigma", C.c_double, [C.c_void_p])
+            f("kiss_map", C.c_void_p, [C.c_void_p])
+        f("kiss_create", C.c_void_p, [C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double])
+        f("kiss_destroy", None, [C.c_void_p])
+        f("kiss_register_points", None, [C.c_void_p, _dp, C.c_long, _dp, _lp, _dp, _lp, _dp])
+        f("kiss_register_cloud", None, [C.c_void_p, _fp, _dp, C.c_long, _dp, _lp, _dp, _lp, _dp])
+        f("kiss_num_poses", C.c_long, [C.c_void_p])
+        f("kiss_pose", None, [C.c_void_p, C.c_long, _dp])
+        self._scratch_kiss = None
+
+    def _f(self, name, res, args):
+        fn = getattr(self.lib, self.p + name)
+        fn.restype, fn.argtypes = res, args
+        setattr(self, "_" + name, fn)
+
+    # -- utils ---------------------------------------------------------------------------------------
+    def num_threads(self) -> int:
+        return int(self._num_threads()) if self.kind == "reference" else 1
+
+    def vox_index(self, xyz, v):
+        xyz = _pts(xyz)
+        keys = np.empty((len(xyz), 3), np.int32)
+        self._vox_index(_d(xyz), len(xyz), float(v), _i(keys))
+        return keys
+
+    def transform(self, pose7, xyz):
+        out = _pts(xyz).copy()
+        pose7 = np.ascontiguousarray(pose7, np.float64)
+        if len(out):
+            self._transform(_d(pose7), _d(out), len(out))
+        return out
+
+    def se3_exp(self, x6):
+        x6 = np.ascontiguousarray(x6, np.float64)
+        out = np.empty(7)
+        self._se3_exp(_d(x6), _d(out))
+        return out
+
+    def se3_log(self, p7):
+        p7 = np.ascontiguousarray(p7, np.float64)
+        out = np.empty(6)
+        self._se3_log(_d(p7), _d(out))
+        return out
+
+    def se3_mul(self, a, b):
+        a = np.ascontiguousarray(a, np.float64)
+        b = np.ascontiguousarray(b, np.float64)
+        out = np.empty(7)
+        self._se3_mul(_d(a), _d(b), _d(out))
+        return out
+
+    def se3_inv(self, a):
+        a = np.ascontiguousarray(a, np.float64)
+        out = np.empty(7)
+        self._se3_inv(_d(a), _d(out))
+        return out
+
+    def delta_pose(self, a, b):
+        a = np.ascontiguousarray(a, np.float64)
+        b = np.ascontiguousarray(b, np.float64)
+        out = np.empty(6)
+        self._delta_pose(_d(a), _d(b), _d(out))
+        return out
+
+    # -- free functions ----------------------------------------------------------------------------------
+    def deskew(self, xyz_f32, ts, T0, T1):
+        x = np.ascontiguousarray(xyz_f32, np.float32).reshape(-1, 3)
+        ts = np.ascontiguousarray(ts, np.float64)
+        T0 = np.ascontiguousarray(T0, np.float64)
+        T1 = np.ascontiguousarray(T1, np.float64)
+        out = np.empty((len(x), 3))
+        self._deskew(_f(x), _d(ts), len(x), _d(T0), _d(T1), _d(out))
+        return out
+
+    def align(self, src, tgt, th):
+        """Returns dict(pose=7) for the reference; the port adds H (6x6), g (6), x (6)."""
+        src, tgt = _pts(src), _pts(tgt)
+        pose = np.empty(7)
+        if self.kind == "reference":
+            self._align(_d(src), _d(tgt), len(src), float(th), _d(pose))
+            return {"pose": pose}
+        H, g, x = np.empty((6, 6)), np.empty(6), np.empty(6)
+        self._align(_d(src), _d(tgt), len(src), float(th), _d(H), _d(g), _d(x), _d(pose))
+        return {"pose": pose, "H": H, "g": g, "x": x}
+
+    def _kiss_scratch(self):
+        if self._scratch_kiss is None:
+            self._scratch_kiss = self._kiss_create(1.0, 100.0, 10, 0, 0.1, 500, 2.0, 1e-4)
+        return self._scratch_kiss
+
+    def voxel_downsample(self, xyz, s):
+        xyz = _pts(xyz)
+        out = np.empty((max(len(xyz), 1), 3))
+        if self.kind == "reference":
+            n = self._voxel_downsample(self._kiss_scratch(), _d(xyz), len(xyz), float(s), _d(out))
+        else:
+            n = self._voxel_downsample(_d(xyz), len(xyz), float(s), _d(out), None)
+        return out[:n].copy()
+
+    def iqr(self, xyz):
+        xyz = _pts(xyz)
+        out = np.empty((max(len(xyz), 1), 3))
+        if self.kind == "reference":
+            n = self._iqr(self._kiss_scratch(), _d(xyz), len(xyz), _d(out))
+        else:
+            n = self._iqr(_d(xyz), len(xyz), _d(out), None)
+        return out[:n].copy()
+
+    def voxelize(self, xyz, v):
+        xyz = _pts(xyz)
+        src = np.empty((max(len(xyz), 1), 3))
+        down = np.empty((max(len(xyz), 1), 3))
+        ns, nd = C.c_long(0), C.c_long(0)
+        if self.kind == "reference":
+            self._voxelize(self._kiss_scratch(), _d(xyz), len(xyz), float(v), _d(src), C.byref(ns), _d(down), C.byref(nd))
+        else:
+            self._voxelize(_d(xyz), len(xyz), float(v), _d(src), C.byref(ns), _d(down), C.byref(nd))
+        return src[: ns.value].copy(), down[: nd.value].copy()
+
+    def Map(self, vox_size, max_distance, cap):
+        return _Map(self, vox_size, max_distance, cap)
+
+    def Threshold(self, init_th, min_motion, max_range):
+        return _Threshold(self, init_th, min_motion, max_range)
+
+    def Kiss(self, **cfg):
+        return _Kiss(self, **cfg)
+
+    def icp(self, m, xyz, init7, tau, th, max_iter, eps, trace=False):
+        """Returns dict(pose, iters[, est (iters x 7), ncorr (iters), hg (iters x 42, port only), src_after])."""
+        xyz = _pts(xyz)
+        init7 = np.ascontiguousarray(init7, np.float64)
+        pose = np.empty(7)
+        if not trace and self.kind == "reference":
+            self._icp(m.h, _d(xyz), len(xyz), _d(init7), tau, th, max_iter, eps, _d(pose))
+            return {"pose": pose}
+        est = np.zeros((max_iter, 7))
+        nc = np.zeros(max_iter, dtype=np.int64)
+        after = np.empty((max(len(xyz), 1), 3))
+        if self.kind == "reference":
+            it = self._icp_trace(m.h, _d(xyz), len(xyz), _d(init7), tau, th, max_iter, eps, _d(pose), _d(est), _l(nc), _d(after))
+            return {"pose": pose, "iters": it, "est": est[:it], "ncorr": nc[:it], "src_after": after[: len(xyz)]}
+        hg = np.zeros((max_iter, 42))
+        it = self._icp(m.h, _d(xyz), len(xyz), _d(init7), tau, th, max_iter, eps, _d(pose), _d(est), _l(nc), _d(hg), _d(after))
+        return {"pose": pose, "iters": it, "est": est[:it], "ncorr": nc[:it], "hg": hg[:it], "src_after": after[: len(xyz)]}
+
+
+class _Map:
+    def __init__(self, api, vox_size, max_distance, cap, handle=None):
+        self.api, self.cap = api, cap
+        self.owned = handle is None
+        self.h = api._map_create(float(vox_size), float(max_distance), int(cap)) if handle is None else handle
+
+    def __del__(self):
+        if getattr(self, "owned", False) and self.h:
+            self.api._map_destroy(self.h)
+            self.h = None
+
+    def insert(self, xyz):
+        xyz = _pts(xyz)
+        self.api._map_insert(self.h, _d(xyz), len(xyz))
+
+    def update(self, xyz, pose7):
+        xyz = _pts(xyz)
+        pose7 = np.ascontiguousarray(pose7, np.float64)
+        self.api._map_update(self.h, _d(xyz), len(xyz), _d(pose7))
+
+    def remove_far(self, origin):
+        o = np.ascontiguousarray(origin, np.float64)
+        self.api._map_remove_far(self.h, _d(o))
+
+    def clear(self):
+        self.api._map_clear(self.h)
+
+    def empty(self):
+        return bool(self.api._map_empty(self.h))
+
+    def num_voxels(self):
+        return int(self.api._map_num_voxels(self.h))
+
+    def closest(self, xyz, with_index=False):
+        xyz = _pts(xyz)
+        out = np.empty((len(xyz), 3))
+        if self.api.kind == "reference":
+            self.api._map_closest(self.h, _d(xyz), len(xyz), _d(out))
+            return out
+        key = np.empty((len(xyz), 3), np.int32)
+        rank = np.empty(len(xyz), np.int32)
+        self.api._map_closest(self.h, _d(xyz), len(xyz), _d(out), _i(key), _i(rank))
+        return (out, key, rank) if with_index else out
+
+    def correspondences(self, xyz, tau, with_index=False):
+        xyz = _pts(xyz)
+        src = np.empty((max(len(xyz), 1), 3))
+        tgt = np.empty((max(len(xyz), 1), 3))
+        if self.api.kind == "reference":
+            n = self.api._map_correspondences(self.h, _d(xyz), len(xyz), float(tau), _d(src), _d(tgt))
+            return src[:n].copy(), tgt[:n].copy()
+        idx = np.empty(max(len(xyz), 1), np.int64)
+        n = self.api._map_correspondences(self.h, _d(xyz), len(xyz), float(tau), _d(src), _d(tgt), _l(idx))
+        return (src[:n].copy(), tgt[:n].copy(), idx[:n].copy()) if with_index else (src[:n].copy(), tgt[:n].copy())
+
+    def dump(self):
+        """(keys [V,3] int32, counts [V] int32, pts [sum(counts),3]) in creation order."""
+        npts = C.c_long(0)
+        nv = self.api._map_dump(self.h, None, None, None, 0, 0, C.byref(npts))
+        keys = np.empty((max(nv, 1), 3), np.int32)
+        counts = np.empty(max(nv, 1), np.int32)
+        pts = np.empty((max(npts.value, 1), 3))
+        self.api._map_dump(self.h, _i(keys), _i(counts), _d(pts), nv, npts.value, C.byref(npts))
+        return keys[:nv], counts[:nv], pts[: npts.value]
+
+
+class _Threshold:
+    def __init__(self, api, init_th, min_motion, max_range):
+        self.api = api
+        if api.kind == "reference":
+            self.h = api._threshold_create(init_th, min_motion, max_range)
+        else:
+            self.buf = (C.c_double * 16)()
+            self.h = C.cast(self.buf, C.c_void_p)
+            api._threshold_init(self.h, init_th, min_motion, max_range)
+
+    def step(self, dev7):
+        dev7 = np.ascontiguousarray(dev7, np.float64)
+        return float(self.api._threshold_step(self.h, _d(dev7)))
+
+    def __del__(self):
+        if self.api.kind == "reference" and getattr(self, "h", None):
+            self.api._threshold_destroy(self.h)
+            self.h = None
+
+
+class _Kiss:
+    """KissICP pipeline object (icp.hpp:31-68)."""
+
+    def __init__(self, api, voxel_size=1.0, max_range=100.0, cap=10, deskew=False, min_motion_th=0.1,
+                 icp_max_iteration=500, initial_threshold=2.0, estimation_threshold=1e-4):
+        self.api = api
+        self.h = api._kiss_create(voxel_size, max_range, cap, int(deskew), min_motion_th, icp_max_iteration,
+                                  initial_threshold, estimation_threshold)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.api._kiss_destroy(self.h)
+            self.h = None
+
+    def _out(self, n):
+        return np.empty((max(n, 1), 3)), np.empty((max(n, 1), 3)), C.c_long(0), C.c_long(0), np.empty(7)
+
+    def register_points(self, xyz):
+        xyz = _pts(xyz)
+        down, src, nd, ns, pose = self._out(len(xyz))
+        self.api._kiss_register_points(self.h, _d(xyz), len(xyz), _d(down), C.byref(nd), _d(src), C.byref(ns), _d(pose))
+        return down[: nd.value].copy(), src[: ns.value].copy(), pose
+
+    def register_cloud(self, xyz_f32, ts):
+        x = np.ascontiguousarray(xyz_f32, np.float32).reshape(-1, 3)
+        ts = np.ascontiguousarray(ts, np.float64)
+        down, src, nd, ns, pose = self._out(len(x))
+        self.api._kiss_register_cloud(self.h, _f(x), _d(ts), len(x), _d(down), C.byref(nd), _d(src), C.byref(ns), _d(pose))
+        return down[: nd.value].copy(), src[: ns.value].copy(), pose
+
+    def poses(self):
+        n = self.api._kiss_num_poses(self.h)
+        out = np.empty((n, 7))
+        for i in range(n):
+            self.api._kiss_pose(self.h, i, _d(out[i]))
+        return out
+
+    def last_iterations(self):
+        return int(self.api._kiss_last_iterations(self.h)) if self.api.kind == "port" else -1
+
+    def last_sigma(self):
+        return float(self.api._kiss_last_sigma(self.h)) if self.api.kind == "port" else float("nan")
+
+    def map(self):
+        if self.api.kind != "port":
+            raise NotImplementedError
+        m = _Map(self.api, 0, 0, 0, handle=self.api._kiss_map(self.h))
+        return m
+
+
+_cache = {}
+
+
+def load_ref(mt: bool = False) -> _Api:
+    key = "ref_mt" if mt else "ref"
+    if key not in _cache:
+        path = REF_MT_SO if mt else REF_SO
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing: build it where /root/reference exists (make -C oracle ref)")
+        _cache[key] = _Api(C.CDLL(path), "ref_", "reference")
+    return _cache[key]
+
+
+def load_port() -> _Api:
+    if "port" not in _cache:
+        build_port()
+        _cache["port"] = _Api(C.CDLL(PORT_SO), "lo_", "port")
+    return _cache["port"]

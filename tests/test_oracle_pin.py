@@ -1,0 +1,229 @@
+"""Pins the plain-C oracle (oracle/limu_oracle.c) against the reference's own compiled sources
+(oracle/_ref/liblimu_ref.so = Oreoluwa-Se/Lidar-Imu-Slam env_ws/src/limu, unmodified, serial shims).
+
+Bar: every per-point quantity (voxel index, transformed point, neighbour, correspondence set,
+downsampled / IQR-filtered clouds, map contents) is BIT-IDENTICAL; pose-level algebra that runs
+through libm and Eigen's pivoted LDLT agrees to a few ulp (tolerances written at each assert).
+"""
+import numpy as np
+import pytest
+
+from conftest import random_pose
+
+
+def test_se3_algebra(ref, port, rng):
+    for _ in range(500):
+        x = rng.normal(size=6) * np.array([5, 5, 5, 1, 1, 1])
+        A = ref.se3_exp(x)
+        assert np.array_equal(A, port.se3_exp(x))                     # SE3::exp bit-exact
+        B = random_pose(ref, rng)
+        assert np.array_equal(ref.se3_mul(A, B), port.se3_mul(A, B))  # group product bit-exact
+        assert np.array_equal(ref.se3_inv(A), port.se3_inv(A))        # inverse bit-exact
+        np.testing.assert_allclose(port.se3_log(A), ref.se3_log(A), rtol=0, atol=1e-13)  # log: few ulp
+        np.testing.assert_allclose(port.delta_pose(A, B), ref.delta_pose(A, B), rtol=0, atol=1e-13)
+    # small-angle branches (theta^2 < 1e-20, sophus/so3.hpp:706, :281)
+    for s in (0.0, 1e-12, 1e-11, 3e-11):
+        x = np.array([1.0, -2.0, 0.5, s, -s, 0.5 * s])
+        A = ref.se3_exp(x)
+        assert np.array_equal(A, port.se3_exp(x))
+        np.testing.assert_allclose(port.se3_log(A), ref.se3_log(A), rtol=0, atol=1e-15)
+
+
+def test_vox_index_and_transform(ref, port, rng):
+    pts = rng.normal(size=(200000, 3)) * 40
+    pts[:1000] = np.round(pts[:1000])            # exact lattice points
+    pts[1000:2000] = np.round(pts[1000:2000]) * 0.5
+    pts[2000:2010] = 0.0
+    pts[2010:2020] *= 1e-9                       # inside the double-width cell around zero
+    for v in (1.0, 0.5, 1.5, 0.25, 0.3, 0.1):
+        assert np.array_equal(ref.vox_index(pts, v), port.vox_index(pts, v))
+    T = random_pose(ref, rng)
+    assert np.array_equal(ref.transform(T, pts), port.transform(T, pts))
+
+
+@pytest.mark.parametrize("cap,vox,spread,qspread", [(10, 1.0, 10.0, 11.0), (1, 0.5, 3.0, 4.0), (20, 1.0, 3.0, 3.5), (3, 2.0, 30.0, 33.0)])
+def test_map_insert_closest_correspondences(ref, port, rng, cap, vox, spread, qspread):
+    mr, mp = ref.Map(vox, 100.0, cap), port.Map(vox, 100.0, cap)
+    for _ in range(3):                            # several batches: append until cap, in input order
+        pts = rng.normal(size=(20000, 3)) * spread
+        mr.insert(pts)
+        mp.insert(pts)
+    kr, cr, pr = mr.dump()
+    kp, cp, pp = mp.dump()
+    assert np.array_equal(kr, kp) and np.array_equal(cr, cp) and np.array_equal(pr, pp)
+    assert cr.max() <= cap
+    q = rng.normal(size=(30000, 3)) * qspread     # includes own-voxel hits, 27-cell fallbacks and total misses
+    a = mr.closest(q)
+    b, key, rank = mp.closest(q, with_index=True)
+    assert np.array_equal(a, b)
+    assert (rank < 0).any() and (rank >= 0).any()
+    own = np.all(port.vox_index(q, vox) == key, axis=1)
+    assert own.any() and (~own & (rank >= 0)).any()          # both hit kinds are exercised
+    for tau in (0.3, 1.0, 2.5):
+        sa, ta = mr.correspondences(q, tau)
+        sb, tb = mp.correspondences(q, tau)
+        assert np.array_equal(sa, sb) and np.array_equal(ta, tb)
+
+
+def test_origin_match_when_nothing_found(ref, port):
+    """No occupied cell in the 27-neighbourhood -> (0,0,0) is returned and range-tested like a real
+    point (voxel_hash_map.cpp:98-99,118-124)."""
+    for api in (ref, port):
+        m = api.Map(1.0, 100.0, 10)
+        m.insert(np.array([[50.0, 50.0, 50.0]]))
+        q = np.array([[0.3, 0.2, -0.1], [5.0, 5.0, 5.0]])
+        out = m.closest(q)
+        assert np.array_equal(out, np.zeros((2, 3)))
+        s, t = m.correspondences(q, 1.0)
+        assert len(s) == 1 and np.array_equal(s[0], q[0]) and np.array_equal(t[0], np.zeros(3))
+
+
+def test_remove_points_from_far(ref, port, rng):
+    """The reference's eviction under null locks (oracle/shims/common/boost/thread/shared_mutex.hpp)."""
+    for vox, maxd in ((1.0, 20.0), (0.5, 30.0), (0.1, 5.0)):
+        mr, mp = ref.Map(vox, maxd, 5), port.Map(vox, maxd, 5)
+        pts = rng.normal(size=(20000, 3)) * maxd
+        mr.insert(pts)
+        mp.insert(pts)
+        o = rng.normal(size=3) * 3
+        mr.remove_far(o)
+        mp.remove_far(o)
+        a, b = mr.dump(), mp.dump()
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        more = rng.normal(size=(5000, 3)) * maxd          # insertion after eviction (re-creation order)
+        T = random_pose(ref, rng, trans=2.0, rot=0.1)
+        mr.update(more, T)
+        mp.update(more, T)
+        a, b = mr.dump(), mp.dump()
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        q = rng.normal(size=(5000, 3)) * maxd
+        assert np.array_equal(mr.closest(q), mp.closest(q))
+
+
+def test_downsample_iqr_voxelize(ref, port, rng):
+    pts = rng.normal(size=(60000, 3)) * np.array([30, 30, 3])
+    for s in (0.5, 1.5, 0.25, 0.75):
+        assert np.array_equal(ref.voxel_downsample(pts, s), port.voxel_downsample(pts, s))
+    for n in (1, 2, 3, 4, 5, 29, 30, 31, 1000, 4097):
+        assert np.array_equal(ref.iqr(pts[:n]), port.iqr(pts[:n]))
+    heavy = np.concatenate([pts[:3000], rng.normal(size=(60, 3)) * 400])     # real outliers
+    a, b = ref.iqr(heavy), port.iqr(heavy)
+    assert np.array_equal(a, b) and len(a) < len(heavy)
+    for v in (1.0, 0.5):
+        sa, da = ref.voxelize(pts, v)
+        sb, db = port.voxelize(pts, v)
+        assert np.array_equal(sa, sb) and np.array_equal(da, db)
+
+
+def test_deskew(ref, port, rng):
+    xyz = (rng.normal(size=(50000, 3)) * 30).astype(np.float32)
+    ts = rng.random(50000)
+    T0 = random_pose(ref, rng)
+    T1 = ref.se3_mul(T0, ref.se3_exp(np.array([1.0, 0.1, -0.05, 0.01, -0.02, 0.1])))
+    a, b = ref.deskew(xyz, ts, T0, T1), port.deskew(xyz, ts, T0, T1)
+    # twist = log(T0^-1 T1) differs by <= 4 ulp between the two (test_se3_algebra), so points agree to ~1e-13 m
+    np.testing.assert_allclose(b, a, rtol=0, atol=1e-12)
+
+
+def test_align_clouds(ref, port, rng):
+    for n in (1, 2, 3, 7, 100, 20000):
+        src = rng.normal(size=(n, 3)) * 20
+        T = ref.se3_exp(rng.normal(size=6) * 0.05)
+        tgt = ref.transform(T, src) + rng.normal(size=(n, 3)) * 0.01
+        for th in (2.0 / 3.0, 0.1):
+            a = ref.align(src, tgt, th)["pose"]
+            b = port.align(src, tgt, th)
+            if n >= 3:      # full-rank normal equations: solutions agree to rounding
+                np.testing.assert_allclose(b["pose"], a, rtol=0, atol=1e-10)
+            H, g = b["H"], b["g"]
+            np.testing.assert_allclose(H, H.T, rtol=1e-13, atol=1e-9)
+    # n == 0: H = 0, g = 0 -> x = 0 -> identity (Eigen LDLT zero-pivot path)
+    a = ref.align(np.zeros((0, 3)), np.zeros((0, 3)), 0.5)["pose"]
+    b = port.align(np.zeros((0, 3)), np.zeros((0, 3)), 0.5)["pose"]
+    assert np.array_equal(a, b) and np.array_equal(a, [0, 0, 0, 1, 0, 0, 0])
+
+
+def _dense_scene(rng, n=40000):
+    """Points on three orthogonal noisy planes plus clutter: well-conditioned for point-to-point ICP."""
+    a = rng.random((n // 3, 3)) * 40 - 20
+    a[:, 2] = rng.normal(size=len(a)) * 0.02
+    b = rng.random((n // 3, 3)) * 40 - 20
+    b[:, 0] = 20 + rng.normal(size=len(b)) * 0.02
+    c = rng.random((n // 3, 3)) * 40 - 20
+    c[:, 1] = -20 + rng.normal(size=len(c)) * 0.02
+    return np.concatenate([a, b, c])
+
+
+def test_icp_trace_and_pose(ref, port, rng):
+    world = _dense_scene(rng)
+    mr, mp = ref.Map(1.0, 100.0, 20), port.Map(1.0, 100.0, 20)
+    mr.insert(world)
+    mp.insert(world)
+    true = ref.se3_exp(np.array([0.3, -0.2, 0.05, 0.004, -0.003, 0.02]))
+    src = ref.transform(ref.se3_inv(true), world[rng.choice(len(world), 5000, replace=False)])
+    init = np.array([0, 0, 0, 1.0, 0, 0, 0])
+    sigma = 2.0
+    r_full = ref.icp(mr, src, init, 3 * sigma, sigma / 3, 60, 1e-4)
+    r = ref.icp(mr, src, init, 3 * sigma, sigma / 3, 60, 1e-4, trace=True)
+    assert np.array_equal(r_full["pose"], r["pose"])        # the unrolled trace IS lidar::ICP
+    p = port.icp(mp, src, init, 3 * sigma, sigma / 3, 60, 1e-4, trace=True)
+    assert p["iters"] == r["iters"] and r["iters"] < 60
+    assert np.array_equal(p["ncorr"], r["ncorr"])           # identical correspondence counts per iteration
+    np.testing.assert_allclose(p["est"], r["est"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(p["pose"][4:], r["pose"][4:], rtol=0, atol=1e-9)   # << 1e-5 m
+    np.testing.assert_allclose(p["pose"][:4], r["pose"][:4], rtol=0, atol=1e-10)  # << 1e-6 rad
+    np.testing.assert_allclose(p["src_after"], r["src_after"], rtol=0, atol=1e-9)
+    # empty map -> init_guess returned untouched (registration.cpp:99-100)
+    e_r, e_p = ref.Map(1.0, 100.0, 20), port.Map(1.0, 100.0, 20)
+    assert np.array_equal(ref.icp(e_r, src, true, 6, 0.6, 10, 1e-4)["pose"], true)
+    assert np.array_equal(port.icp(e_p, src, true, 6, 0.6, 10, 1e-4, trace=True)["pose"], true)
+
+
+def test_adaptive_threshold(ref, port, rng):
+    tr, tp = ref.Threshold(2.0, 0.1, 100.0), port.Threshold(2.0, 0.1, 100.0)
+    for i in range(200):
+        scale = 10 ** rng.uniform(-6, 0)
+        dev = ref.se3_exp(rng.normal(size=6) * scale * np.array([1, 1, 1, 0.05, 0.05, 0.05]))
+        a, b = tr.step(dev), tp.step(dev)
+        assert abs(a - b) <= 1e-12 * max(1.0, abs(a))
+
+
+def test_kiss_pipeline(ref, port, rng):
+    """register_frame over a short moving sequence (icp.cpp:49-86): same clouds, poses to tolerance."""
+    world = _dense_scene(rng, 90000)
+    kr = ref.Kiss(voxel_size=1.0, max_range=100.0, cap=20, deskew=True, icp_max_iteration=100)
+    kp = port.Kiss(voxel_size=1.0, max_range=100.0, cap=20, deskew=True, icp_max_iteration=100)
+    pose = np.array([0, 0, 0, 1.0, 0, 0, 0])
+    step = ref.se3_exp(np.array([0.4, 0.05, 0.0, 0.0, 0.0, 0.01]))
+    for i in range(6):
+        local = ref.transform(ref.se3_inv(pose), world)
+        keep = np.linalg.norm(local, axis=1) < 30
+        scan = local[keep][:: 2].astype(np.float32)
+        ts = np.linspace(0, 1, len(scan), endpoint=False)
+        da, sa, pa = kr.register_cloud(scan, ts)
+        db, sb, pb = kp.register_cloud(scan, ts)
+        if i < 3:   # deskew gate closed (poses <= 2): everything before ICP is bit-identical
+            assert np.array_equal(da, db) and np.array_equal(sa, sb)
+        else:
+            assert da.shape == db.shape and sa.shape == sb.shape
+            np.testing.assert_allclose(db, da, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(pb[4:], pa[4:], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(pb[:4], pa[:4], rtol=0, atol=1e-8)
+        pose = ref.se3_mul(pose, step)
+    assert len(kr.poses()) == len(kp.poses()) == 6
+
+
+def test_mt_flavour_matches_serial(ref, ref_mt, rng):
+    """The thread-pool TBB shim (timed CPU baseline) computes the same thing as the serial oracle."""
+    world = _dense_scene(rng)
+    ms, mm = ref.Map(1.0, 100.0, 10), ref_mt.Map(1.0, 100.0, 10)
+    ms.insert(world)
+    mm.insert(world)
+    q = world[:5000] + rng.normal(size=(5000, 3)) * 0.1
+    sa, ta = ms.correspondences(q, 1.0)
+    sb, tb = mm.correspondences(q, 1.0)
+    assert np.array_equal(sa, sb) and np.array_equal(ta, tb)
+    a = ref.align(sa, ta, 0.5)["pose"]
+    b = ref_mt.align(sb, tb, 0.5)["pose"]
+    np.testing.assert_allclose(b, a, rtol=0, atol=1e-11)    # join order differs from the serial sum
+    assert np.array_equal(ref.iqr(world), ref_mt.iqr(world))
