@@ -1,0 +1,173 @@
+/* limu_cuda.h -- C ABI of liblimu_cuda.so: the B200 (sm_100a) LiDAR odometry hot path.
+ *
+ * Drop-in boundary for Oreoluwa-Se/Lidar-Imu-Slam's lidar:: classes ("L/" = env_ws/src/limu of the
+ * reference). The reference has no FFI layer: its boundary is the C++ class surface called from the
+ * single odometry thread (L/src/odom_run.cpp:154-185). Each entry point below names the reference
+ * interface it replaces; the header-only C++ classes in include/limu_dropin/ put the reference's own
+ * signatures (lidar::VoxelHashMap, lidar::ICP, lidar::KissICP, ...) back on top of these calls, and
+ * INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no exceptions, no STL, no torch types.
+ *   - every call returns LIMU_OK (0) or a negative limu_status; limu_last_error() gives the message of
+ *     the calling thread's last failure.
+ *   - points : double xyz[3*n] array-of-structs == utils::Vec3dVector storage (L/include/limu/utils/types.hpp:19)
+ *   - raw scan points : float xyzt[4*n] = {x, y, z, t}, t in [0,1] = normalised per-point timestamp
+ *     (float x,y,z as in pcl::PointXYZINormal, types.hpp:36; t as produced by
+ *     utils::normalize_timestamps, L/src/utils/calculation_helpers.cpp:52-66)
+ *   - pose   : double[7] = {qx,qy,qz,qw, tx,ty,tz} == Sophus::SE3d::data() order
+ *   - voxel  : int32[3] == utils::Voxel (types.hpp:15)
+ *   - pointers are HOST memory unless the function name ends in _dev (then: device memory of the
+ *     handle's GPU, e.g. torch.Tensor.data_ptr()); host buffers may be pageable or pinned
+ *     (limu_host_alloc gives pinned memory; pinned makes the copies asynchronous DMA).
+ *   - a handle owns its device buffers and one CUDA stream; calls on one handle are serialised by the
+ *     caller (the reference is single-threaded here too); different handles are independent.
+ *   - there is NO CPU fallback: every entry point fails with LIMU_ERR_CUDA when no device is usable.
+ */
+#ifndef LIMU_CUDA_H
+#define LIMU_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIMU_ABI_VERSION 1
+
+typedef enum limu_status {
+    LIMU_OK = 0,
+    LIMU_ERR_INVALID = -1,   /* bad argument (null pointer, negative size, cap < 1, ...) */
+    LIMU_ERR_CUDA = -2,      /* CUDA runtime failure (message carries cudaGetErrorString) */
+    LIMU_ERR_KEY_RANGE = -3, /* a voxel index fell outside +-2^20 (the packed 3x21-bit key range) */
+    LIMU_ERR_MAP_FULL = -4,  /* hash table could not grow (out of device memory) */
+    LIMU_ERR_NOMEM = -5,
+    LIMU_ERR_COMM = -6       /* multi-GPU exchange failed */
+} limu_status;
+
+const char *limu_last_error(void);
+int limu_abi_version(void);
+/* Number of kernel launches issued by this process so far (all handles). bench.py reports the delta. */
+uint64_t limu_kernel_launches(void);
+int limu_device_count(void);
+/* Pinned host memory (cudaHostAlloc); optional, any host pointer is accepted everywhere. */
+void *limu_host_alloc(size_t bytes);
+void limu_host_free(void *p);
+
+/* ---- context: one GPU, one stream, scratch memory ---------------------------------------------- */
+typedef struct limu_ctx limu_ctx;
+int limu_ctx_create(int device, limu_ctx **out);
+void limu_ctx_destroy(limu_ctx *c);
+int limu_ctx_sync(limu_ctx *c);
+void *limu_ctx_stream(limu_ctx *c); /* cudaStream_t, for callers that enqueue their own work around ours */
+
+/* ---- stateless point operations ------------------------------------------------------------------ */
+/* utils::get_vox_index, calculation_helpers.cpp:142-147: keys[3i+a] = (int)(xyz[3i+a] / v). */
+int limu_voxel_keys(limu_ctx *c, const double *xyz, int64_t n, double v, int32_t *keys);
+/* utils::transform_points, calculation_helpers.cpp:121-133: xyz <- T * xyz in place. */
+int limu_transform_points(limu_ctx *c, const double pose[7], double *xyz, int64_t n);
+/* lidar::MotionCompensator::deskew_scan, helpers/deskew.cpp:10-28:
+ * out[i] = exp((t_i - 0.5) * log(T0^-1 T1)) * (x_i,y_i,z_i). */
+int limu_deskew(limu_ctx *c, const float *xyzt, int64_t n, const double T0[7], const double T1[7], double *out_xyz);
+/* voxel_downsample (file-local), sensors/lidar/icp.cpp:9-30: first point per voxel of edge s wins;
+ * output in first-occurrence order. out_xyz must hold n points; out_idx (optional) the source indices. */
+int limu_voxel_downsample(limu_ctx *c, const double *xyz, int64_t n, double s, double *out_xyz, int64_t *out_idx, int64_t *n_out);
+/* KissICP::iqr_processing, icp.cpp:88-124 + outlier::IQR, common.hpp:22-63. bounds (optional) = {low, high}. */
+int limu_iqr_filter(limu_ctx *c, const double *xyz, int64_t n, double *out_xyz, int64_t *n_out, double bounds[2]);
+/* KissICP::voxelize, icp.cpp:126-136: down = ds(frame, 0.5 v); src = IQR(ds(down, 1.5 v)). */
+int limu_voxelize(limu_ctx *c, const double *xyz, int64_t n, double v, double *src_xyz, int64_t *n_src, double *down_xyz, int64_t *n_down);
+/* lidar::align_clouds, helpers/registration.cpp:43-92. H (6x6 row-major), g, x optional. */
+int limu_align(limu_ctx *c, const double *src, const double *tgt, int64_t n, double th, double H[36], double g[6], double x[6], double pose_out[7]);
+
+/* ---- lidar::VoxelHashMap, helpers/voxel_hash_map.hpp:14-48 -------------------------------------- */
+typedef struct limu_map limu_map;
+/* ctor (:17-19). capacity_voxels: expected number of occupied voxels (the table grows when exceeded). */
+int limu_map_create(limu_ctx *c, double vox_size, double max_distance, int max_points_per_voxel, int64_t capacity_voxels, limu_map **out);
+void limu_map_destroy(limu_map *m);
+int limu_map_clear(limu_map *m);                                   /* clear() :200-204 */
+int limu_map_empty(limu_map *m, int *out);                         /* empty() :206-210 */
+int limu_map_size(limu_map *m, int64_t *n_voxels, int64_t *n_points);
+int limu_map_insert(limu_map *m, const double *xyz, int64_t n);    /* insert_points :12-62 */
+int limu_map_insert_dev(limu_map *m, const double *xyz_dev, int64_t n);
+int limu_map_update(limu_map *m, const double *xyz, int64_t n, const double pose[7]); /* update(points, pose) :138-144 */
+int limu_map_update_origin(limu_map *m, const double *xyz, int64_t n, const double origin[3]); /* update(points, origin) :132-136 */
+int limu_map_remove_far(limu_map *m, const double origin[3]);      /* remove_points_from_far :146-171 */
+/* get_closest_neighbour :64-102 for n queries. Optional out_key[3n] = voxel of the match (INT32_MIN x3
+ * when nothing was found and (0,0,0) is returned), out_rank[n] = position of the match inside its voxel (-1). */
+int limu_map_closest(limu_map *m, const double *xyz, int64_t n, double *out_xyz, int32_t *out_key, int32_t *out_rank);
+/* get_correspondences :104-130. src/tgt hold up to n points; pairs come out in query order. out_idx optional. */
+int limu_map_correspondences(limu_map *m, const double *xyz, int64_t n, double max_correspondance, double *src, double *tgt, int64_t *out_idx, int64_t *n_out);
+/* pointcloud() :173-198, in voxel creation order. Pass out_xyz = NULL to query the size. */
+int limu_map_pointcloud(limu_map *m, double *out_xyz, int64_t max_points, int64_t *n_out);
+/* Structured dump in voxel creation order (replaces reading the public robin_map member, hpp:40). */
+int limu_map_dump(limu_map *m, int32_t *keys, int32_t *counts, double *pts, int64_t max_voxels, int64_t max_points, int64_t *n_voxels, int64_t *n_points);
+
+/* ---- lidar::ICP, helpers/registration.cpp:94-130 ------------------------------------------------ */
+typedef struct limu_icp_stats {
+    int32_t iterations;       /* Gauss-Newton iterations executed */
+    int32_t converged;        /* 1 if |log(estimate)| < est_threshold stopped the loop */
+    int64_t last_ncorr;       /* correspondences in the last iteration */
+    double mean_candidates;   /* k-bar: mean points compared per query (last iteration) */
+    double miss_fraction;     /* f_miss: share of queries whose own voxel was absent (last iteration) */
+} limu_icp_stats;
+/* Whole loop on device (persistent cooperative kernel, no host round trip per iteration).
+ * Optional traces: est_trace[7*max_iter], ncorr_trace[max_iter], hg_trace[42*max_iter] (H row-major + g). */
+int limu_icp(limu_map *m, const double *xyz, int64_t n, const double init_guess[7], double max_corresp_dist, double kernel,
+             int icp_max_iteration, double est_threshold, double pose_out[7], limu_icp_stats *stats,
+             double *est_trace, int64_t *ncorr_trace, double *hg_trace);
+int limu_icp_dev(limu_map *m, const double *xyz_dev, int64_t n, const double init_guess[7], double max_corresp_dist, double kernel,
+                 int icp_max_iteration, double est_threshold, double pose_out[7], limu_icp_stats *stats);
+
+/* ---- lidar::KissICP, sensors/lidar/icp.hpp:31-68 ------------------------------------------------ */
+typedef struct limu_odom_config {   /* frame::Lidar::ProcessingInfo fields the path reads, lidar/frame.hpp:34-58, defaults :64-80 */
+    double voxel_size;            /* 1.0 (= max_range / 100) */
+    double max_range;             /* 100.0 */
+    int32_t max_points_per_voxel; /* 10 */
+    int32_t deskew;               /* 0 */
+    double min_motion_th;         /* 0.1 */
+    int32_t icp_max_iteration;    /* 500 */
+    int32_t reserved0;
+    double initial_threshold;     /* 2.0 */
+    double estimation_threshold;  /* 1e-4 */
+    int64_t map_capacity_voxels;  /* 0 = derive from max_range / voxel_size */
+    int64_t max_points_per_scan;  /* 0 = grow on demand */
+} limu_odom_config;
+void limu_odom_default_config(limu_odom_config *cfg);
+
+typedef struct limu_frame_stats {
+    int64_t n_points, n_down, n_keypoints;
+    double sigma;                 /* adaptive threshold used (icp.cpp:138-144) */
+    limu_icp_stats icp;
+    int32_t deskewed;             /* 1 if the deskew gate was open (icp.cpp:40-46) */
+    int32_t reserved0;
+} limu_frame_stats;
+
+typedef struct limu_odom limu_odom;
+int limu_odom_create(limu_ctx *c, const limu_odom_config *cfg, limu_odom **out);
+void limu_odom_destroy(limu_odom *o);
+/* register_frame(cloud, timestamps) icp.cpp:49-55. Outputs are optional (NULL = not copied back):
+ * down_xyz / keypoints_xyz must hold n points each. */
+int limu_odom_register_frame(limu_odom *o, const float *xyzt, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down,
+                             double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats);
+int limu_odom_register_frame_dev(limu_odom *o, const float *xyzt_dev, int64_t n, double pose_out[7], limu_frame_stats *stats);
+/* register_frame(Vec3dVector) icp.cpp:58-86 (no deskew). */
+int limu_odom_register_points(limu_odom *o, const double *xyz, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down,
+                              double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats);
+int limu_odom_num_poses(limu_odom *o, int64_t *n);                 /* poses_() icp.hpp:57 */
+int limu_odom_pose(limu_odom *o, int64_t i, double pose_out[7]);
+int limu_odom_adaptive_threshold(limu_odom *o, double *sigma);     /* get_adaptive_threshold() icp.cpp:138-144 (has the reference's side effect) */
+int limu_odom_prediction(limu_odom *o, double pose_out[7]);        /* get_prediction_model() icp.cpp:146-154 */
+int limu_odom_has_moved(limu_odom *o, int *out);                   /* has_moved() icp.cpp:156-163 */
+limu_map *limu_odom_map(limu_odom *o);                             /* the local map (owned by the odometry handle) */
+
+/* ---- host-side SE(3) helpers (the same restatement of Sophus 1.22.10 the device code uses) ------ */
+void limu_se3_exp(const double x[6], double pose_out[7]);
+void limu_se3_log(const double pose[7], double x_out[6]);
+void limu_se3_mul(const double a[7], const double b[7], double out[7]);
+void limu_se3_inverse(const double a[7], double out[7]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIMU_CUDA_H */

@@ -1,0 +1,461 @@
+"""limu_b200 -- Python face of liblimu_cuda.so (the C ABI in include/limu_cuda.h).
+
+A thin ctypes binding used by the tests, bench.py and __graft_entry__.py. Class and method names follow
+the reference's C++ surface (lidar::VoxelHashMap, lidar::ICP, lidar::KissICP in
+Oreoluwa-Se/Lidar-Imu-Slam env_ws/src/limu) so parity tests read like the reference's own
+hash_map_test.hpp. There is NO CPU fallback: importing works anywhere (so CPU-only checks can verify the
+exported symbols), but creating a Context without a usable B200 raises LimuError.
+
+The directory name has a hyphen, so import it through ``__graft_entry__.load_package()`` (or
+``importlib`` with this file's path); the module registers itself as ``limu_b200``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblimu_cuda.so")
+HEADER = os.path.join(os.path.dirname(HERE), "include", "limu_cuda.h")
+
+_dp, _fp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+_vp = C.c_void_p
+
+
+class LimuError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"limu status {status}: {msg}")
+        self.status = status
+
+
+class IcpStats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("last_ncorr", C.c_int64),
+                ("mean_candidates", C.c_double), ("miss_fraction", C.c_double)]
+
+
+class OdomConfig(C.Structure):
+    _fields_ = [("voxel_size", C.c_double), ("max_range", C.c_double), ("max_points_per_voxel", C.c_int32),
+                ("deskew", C.c_int32), ("min_motion_th", C.c_double), ("icp_max_iteration", C.c_int32),
+                ("reserved0", C.c_int32), ("initial_threshold", C.c_double), ("estimation_threshold", C.c_double),
+                ("map_capacity_voxels", C.c_int64), ("max_points_per_scan", C.c_int64)]
+
+
+class FrameStats(C.Structure):
+    _fields_ = [("n_points", C.c_int64), ("n_down", C.c_int64), ("n_keypoints", C.c_int64), ("sigma", C.c_double),
+                ("icp", IcpStats), ("deskewed", C.c_int32), ("reserved0", C.c_int32)]
+
+
+def build(force: bool = False) -> str:
+    """Compile liblimu_cuda.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    srcs = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + [HEADER]
+    stale = not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-s", "-j8", "-C", HERE])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (fails loudly if it was not built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LimuError(-2, f"{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.limu_last_error.restype = C.c_char_p
+        L.limu_kernel_launches.restype = C.c_uint64
+        L.limu_host_alloc.restype = _vp
+        L.limu_host_alloc.argtypes = [C.c_size_t]
+        L.limu_host_free.argtypes = [_vp]
+        L.limu_ctx_stream.restype = _vp
+        L.limu_ctx_stream.argtypes = [_vp]
+        L.limu_odom_map.restype = _vp
+        L.limu_odom_map.argtypes = [_vp]
+        sig = {
+            "limu_ctx_create": [C.c_int, C.POINTER(_vp)], "limu_ctx_destroy": [_vp], "limu_ctx_sync": [_vp],
+            "limu_voxel_keys": [_vp, _dp, C.c_int64, C.c_double, _ip],
+            "limu_transform_points": [_vp, _dp, _dp, C.c_int64],
+            "limu_deskew": [_vp, _fp, C.c_int64, _dp, _dp, _dp],
+            "limu_voxel_downsample": [_vp, _dp, C.c_int64, C.c_double, _dp, _lp, _lp],
+            "limu_iqr_filter": [_vp, _dp, C.c_int64, _dp, _lp, _dp],
+            "limu_voxelize": [_vp, _dp, C.c_int64, C.c_double, _dp, _lp, _dp, _lp],
+            "limu_align": [_vp, _dp, _dp, C.c_int64, C.c_double, _dp, _dp, _dp, _dp],
+            "limu_map_create": [_vp, C.c_double, C.c_double, C.c_int, C.c_int64, C.POINTER(_vp)],
+            "limu_map_destroy": [_vp], "limu_map_clear": [_vp], "limu_map_empty": [_vp, C.POINTER(C.c_int)],
+            "limu_map_size": [_vp, _lp, _lp],
+            "limu_map_insert": [_vp, _dp, C.c_int64], "limu_map_insert_dev": [_vp, _vp, C.c_int64],
+            "limu_map_update": [_vp, _dp, C.c_int64, _dp], "limu_map_update_origin": [_vp, _dp, C.c_int64, _dp],
+            "limu_map_remove_far": [_vp, _dp],
+            "limu_map_closest": [_vp, _dp, C.c_int64, _dp, _ip, _ip],
+            "limu_map_correspondences": [_vp, _dp, C.c_int64, C.c_double, _dp, _dp, _lp, _lp],
+            "limu_map_pointcloud": [_vp, _dp, C.c_int64, _lp],
+            "limu_map_dump": [_vp, _ip, _ip, _dp, C.c_int64, C.c_int64, _lp, _lp],
+            "limu_icp": [_vp, _dp, C.c_int64, _dp, C.c_double, C.c_double, C.c_int, C.c_double, _dp, C.POINTER(IcpStats), _dp, _lp, _dp],
+            "limu_icp_dev": [_vp, _vp, C.c_int64, _dp, C.c_double, C.c_double, C.c_int, C.c_double, _dp, C.POINTER(IcpStats)],
+            "limu_odom_default_config": [C.POINTER(OdomConfig)],
+            "limu_odom_create": [_vp, C.POINTER(OdomConfig), C.POINTER(_vp)], "limu_odom_destroy": [_vp],
+            "limu_odom_register_frame": [_vp, _fp, C.c_int64, _dp, _dp, _lp, _dp, _lp, C.POINTER(FrameStats)],
+            "limu_odom_register_frame_dev": [_vp, _vp, C.c_int64, _dp, C.POINTER(FrameStats)],
+            "limu_odom_register_points": [_vp, _dp, C.c_int64, _dp, _dp, _lp, _dp, _lp, C.POINTER(FrameStats)],
+            "limu_odom_num_poses": [_vp, _lp], "limu_odom_pose": [_vp, C.c_int64, _dp],
+            "limu_odom_adaptive_threshold": [_vp, _dp], "limu_odom_prediction": [_vp, _dp], "limu_odom_has_moved": [_vp, C.POINTER(C.c_int)],
+            "limu_se3_exp": [_dp, _dp], "limu_se3_log": [_dp, _dp], "limu_se3_mul": [_dp, _dp, _dp], "limu_se3_inverse": [_dp, _dp],
+        }
+        for name, args in sig.items():
+            getattr(L, name).argtypes = args
+        _lib = L
+    return _lib
+
+
+def _chk(st):
+    if st != 0:
+        raise LimuError(st, lib().limu_last_error().decode())
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _pts(x):
+    return np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)
+
+
+def _pose(p):
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    assert p.shape == (7,)
+    return p
+
+
+def kernel_launches() -> int:
+    return int(lib().limu_kernel_launches())
+
+
+def device_count() -> int:
+    return int(lib().limu_device_count())
+
+
+# ---- host-side SE(3) helpers -----------------------------------------------------------------------
+def se3_exp(x6):
+    x6 = np.ascontiguousarray(x6, np.float64)
+    out = np.empty(7)
+    lib().limu_se3_exp(_d(x6), _d(out))
+    return out
+
+
+def se3_log(p7):
+    out = np.empty(6)
+    lib().limu_se3_log(_d(_pose(p7)), _d(out))
+    return out
+
+
+def se3_mul(a, b):
+    out = np.empty(7)
+    lib().limu_se3_mul(_d(_pose(a)), _d(_pose(b)), _d(out))
+    return out
+
+
+def se3_inverse(a):
+    out = np.empty(7)
+    lib().limu_se3_inverse(_d(_pose(a)), _d(out))
+    return out
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc memory (limu_host_alloc)."""
+
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = lib().limu_host_alloc(max(self.nbytes, 1))
+        if not self.ptr:
+            raise LimuError(-5, lib().limu_last_error().decode())
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().limu_host_free(self.ptr)
+            self.ptr = None
+
+
+class Context:
+    """One GPU + one stream (limu_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.h = _vp()
+        _chk(lib().limu_ctx_create(device, C.byref(self.h)))
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().limu_ctx_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _chk(lib().limu_ctx_sync(self.h))
+
+    def stream(self) -> int:
+        return int(lib().limu_ctx_stream(self.h) or 0)
+
+    # utils::get_vox_index
+    def voxel_keys(self, xyz, v):
+        xyz = _pts(xyz)
+        keys = np.empty((len(xyz), 3), np.int32)
+        _chk(lib().limu_voxel_keys(self.h, _d(xyz), len(xyz), float(v), keys.ctypes.data_as(_ip)))
+        return keys
+
+    # utils::transform_points
+    def transform_points(self, pose7, xyz):
+        out = _pts(xyz).copy()
+        _chk(lib().limu_transform_points(self.h, _d(_pose(pose7)), _d(out), len(out)))
+        return out
+
+    # MotionCompensator::deskew_scan
+    def deskew_scan(self, xyzt_f32, T0, T1):
+        x = np.ascontiguousarray(xyzt_f32, np.float32).reshape(-1, 4)
+        out = np.empty((len(x), 3))
+        _chk(lib().limu_deskew(self.h, x.ctypes.data_as(_fp), len(x), _d(_pose(T0)), _d(_pose(T1)), _d(out)))
+        return out
+
+    def voxel_downsample(self, xyz, s, with_index=False):
+        xyz = _pts(xyz)
+        out = np.empty((max(len(xyz), 1), 3))
+        idx = np.empty(max(len(xyz), 1), np.int64)
+        n = C.c_int64(0)
+        _chk(lib().limu_voxel_downsample(self.h, _d(xyz), len(xyz), float(s), _d(out), idx.ctypes.data_as(_lp), C.byref(n)))
+        return (out[: n.value].copy(), idx[: n.value].copy()) if with_index else out[: n.value].copy()
+
+    def iqr_processing(self, xyz, with_bounds=False):
+        xyz = _pts(xyz)
+        out = np.empty((max(len(xyz), 1), 3))
+        n = C.c_int64(0)
+        b = np.zeros(2)
+        _chk(lib().limu_iqr_filter(self.h, _d(xyz), len(xyz), _d(out), C.byref(n), _d(b)))
+        return (out[: n.value].copy(), b) if with_bounds else out[: n.value].copy()
+
+    def voxelize(self, xyz, v):
+        xyz = _pts(xyz)
+        src = np.empty((max(len(xyz), 1), 3))
+        down = np.empty((max(len(xyz), 1), 3))
+        ns, nd = C.c_int64(0), C.c_int64(0)
+        _chk(lib().limu_voxelize(self.h, _d(xyz), len(xyz), float(v), _d(src), C.byref(ns), _d(down), C.byref(nd)))
+        return src[: ns.value].copy(), down[: nd.value].copy()
+
+    # lidar::align_clouds
+    def align_clouds(self, src, tgt, th):
+        src, tgt = _pts(src), _pts(tgt)
+        H, g, x, pose = np.empty((6, 6)), np.empty(6), np.empty(6), np.empty(7)
+        _chk(lib().limu_align(self.h, _d(src), _d(tgt), len(src), float(th), _d(H), _d(g), _d(x), _d(pose)))
+        return {"pose": pose, "H": H, "g": g, "x": x}
+
+    def VoxelHashMap(self, vox_size, max_distance, max_points_per_voxel, capacity_voxels=0):
+        return VoxelHashMap(self, vox_size, max_distance, max_points_per_voxel, capacity_voxels)
+
+    def KissICP(self, **cfg):
+        return KissICP(self, **cfg)
+
+
+class VoxelHashMap:
+    """lidar::VoxelHashMap (helpers/voxel_hash_map.hpp:14-48) resident in HBM."""
+
+    def __init__(self, ctx, vox_size, max_distance, max_points_per_voxel, capacity_voxels=0, handle=None):
+        self.ctx, self.cap = ctx, max_points_per_voxel
+        self.owned = handle is None
+        if handle is None:
+            self.h = _vp()
+            _chk(lib().limu_map_create(ctx.h, float(vox_size), float(max_distance), int(max_points_per_voxel), int(capacity_voxels), C.byref(self.h)))
+        else:
+            self.h = handle
+
+    def close(self):
+        if self.owned and self.h:
+            lib().limu_map_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def insert_points(self, xyz):
+        xyz = _pts(xyz)
+        _chk(lib().limu_map_insert(self.h, _d(xyz), len(xyz)))
+
+    def update(self, xyz, pose_or_origin):
+        xyz = _pts(xyz)
+        p = np.ascontiguousarray(pose_or_origin, np.float64)
+        if p.shape == (7,):
+            _chk(lib().limu_map_update(self.h, _d(xyz), len(xyz), _d(p)))
+        else:
+            _chk(lib().limu_map_update_origin(self.h, _d(xyz), len(xyz), _d(p)))
+
+    def remove_points_from_far(self, origin):
+        o = np.ascontiguousarray(origin, np.float64)
+        _chk(lib().limu_map_remove_far(self.h, _d(o)))
+
+    def clear(self):
+        _chk(lib().limu_map_clear(self.h))
+
+    def empty(self):
+        e = C.c_int(0)
+        _chk(lib().limu_map_empty(self.h, C.byref(e)))
+        return bool(e.value)
+
+    def size(self):
+        nv, npt = C.c_int64(0), C.c_int64(0)
+        _chk(lib().limu_map_size(self.h, C.byref(nv), C.byref(npt)))
+        return nv.value, npt.value
+
+    def get_closest_neighbour(self, xyz, with_index=False):
+        xyz = _pts(xyz)
+        out = np.empty((len(xyz), 3))
+        key = np.empty((len(xyz), 3), np.int32)
+        rank = np.empty(len(xyz), np.int32)
+        _chk(lib().limu_map_closest(self.h, _d(xyz), len(xyz), _d(out), key.ctypes.data_as(_ip), rank.ctypes.data_as(_ip)))
+        return (out, key, rank) if with_index else out
+
+    def get_correspondences(self, xyz, max_correspondance, with_index=False):
+        xyz = _pts(xyz)
+        n = max(len(xyz), 1)
+        src, tgt, idx = np.empty((n, 3)), np.empty((n, 3)), np.empty(n, np.int64)
+        k = C.c_int64(0)
+        _chk(lib().limu_map_correspondences(self.h, _d(xyz), len(xyz), float(max_correspondance), _d(src), _d(tgt), idx.ctypes.data_as(_lp), C.byref(k)))
+        k = k.value
+        return (src[:k].copy(), tgt[:k].copy(), idx[:k].copy()) if with_index else (src[:k].copy(), tgt[:k].copy())
+
+    def pointcloud(self):
+        n = C.c_int64(0)
+        _chk(lib().limu_map_pointcloud(self.h, None, 0, C.byref(n)))
+        out = np.empty((max(n.value, 1), 3))
+        _chk(lib().limu_map_pointcloud(self.h, _d(out), n.value, C.byref(n)))
+        return out[: n.value]
+
+    def dump(self):
+        """(keys [V,3], counts [V], points [sum(counts),3]) in voxel creation order."""
+        nv, npt = C.c_int64(0), C.c_int64(0)
+        _chk(lib().limu_map_dump(self.h, None, None, None, 0, 0, C.byref(nv), C.byref(npt)))
+        keys = np.empty((max(nv.value, 1), 3), np.int32)
+        counts = np.empty(max(nv.value, 1), np.int32)
+        pts = np.empty((max(npt.value, 1), 3))
+        _chk(lib().limu_map_dump(self.h, keys.ctypes.data_as(_ip), counts.ctypes.data_as(_ip), _d(pts), nv.value, npt.value, C.byref(nv), C.byref(npt)))
+        return keys[: nv.value], counts[: nv.value], pts[: npt.value]
+
+    # lidar::ICP(local_map, points, init_guess, max_corresp_dist, kernel, icp_max_iteration, est_threshold)
+    def icp(self, xyz, init_guess, max_corresp_dist, kernel, icp_max_iteration, est_threshold, trace=False):
+        xyz = _pts(xyz)
+        pose = np.empty(7)
+        st = IcpStats()
+        it = max(int(icp_max_iteration), 1)
+        est = np.zeros((it, 7)) if trace else None
+        nc = np.zeros(it, np.int64) if trace else None
+        hg = np.zeros((it, 42)) if trace else None
+        _chk(lib().limu_icp(self.h, _d(xyz), len(xyz), _d(_pose(init_guess)), float(max_corresp_dist), float(kernel), int(icp_max_iteration),
+                            float(est_threshold), _d(pose), C.byref(st), _d(est), nc.ctypes.data_as(_lp) if trace else None, _d(hg)))
+        r = {"pose": pose, "iters": st.iterations, "converged": bool(st.converged), "last_ncorr": st.last_ncorr,
+             "mean_candidates": st.mean_candidates, "miss_fraction": st.miss_fraction}
+        if trace:
+            r.update(est=est[: st.iterations], ncorr=nc[: st.iterations], hg=hg[: st.iterations])
+        return r
+
+    def icp_dev(self, xyz_dev_ptr, n, init_guess, max_corresp_dist, kernel, icp_max_iteration, est_threshold):
+        pose = np.empty(7)
+        st = IcpStats()
+        _chk(lib().limu_icp_dev(self.h, _vp(xyz_dev_ptr), int(n), _d(_pose(init_guess)), float(max_corresp_dist), float(kernel),
+                                int(icp_max_iteration), float(est_threshold), _d(pose), C.byref(st)))
+        return {"pose": pose, "iters": st.iterations, "converged": bool(st.converged), "last_ncorr": st.last_ncorr,
+                "mean_candidates": st.mean_candidates, "miss_fraction": st.miss_fraction}
+
+    def insert_points_dev(self, xyz_dev_ptr, n):
+        _chk(lib().limu_map_insert_dev(self.h, _vp(xyz_dev_ptr), int(n)))
+
+
+class KissICP:
+    """lidar::KissICP (sensors/lidar/icp.hpp:31-68); config = frame::Lidar::ProcessingInfo fields."""
+
+    def __init__(self, ctx, voxel_size=1.0, max_range=100.0, cap=10, deskew=False, min_motion_th=0.1, icp_max_iteration=500,
+                 initial_threshold=2.0, estimation_threshold=1e-4, map_capacity_voxels=0):
+        self.ctx = ctx
+        cfg = OdomConfig()
+        lib().limu_odom_default_config(C.byref(cfg))
+        cfg.voxel_size, cfg.max_range, cfg.max_points_per_voxel, cfg.deskew = voxel_size, max_range, cap, int(deskew)
+        cfg.min_motion_th, cfg.icp_max_iteration = min_motion_th, icp_max_iteration
+        cfg.initial_threshold, cfg.estimation_threshold = initial_threshold, estimation_threshold
+        cfg.map_capacity_voxels = map_capacity_voxels
+        self.cfg = cfg
+        self.h = _vp()
+        _chk(lib().limu_odom_create(ctx.h, C.byref(cfg), C.byref(self.h)))
+        self.stats = FrameStats()
+
+    def close(self):
+        if self.h:
+            lib().limu_odom_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def register_frame(self, xyzt_f32, want_clouds=True):
+        """register_frame(cloud, timestamps): xyzt = float32 [n,4] (x,y,z,t in [0,1]). -> (down, keypoints, pose)."""
+        x = xyzt_f32 if isinstance(xyzt_f32, np.ndarray) and xyzt_f32.dtype == np.float32 and xyzt_f32.flags.c_contiguous else np.ascontiguousarray(xyzt_f32, np.float32)
+        x = x.reshape(-1, 4)
+        n = len(x)
+        pose = np.empty(7)
+        if not want_clouds:
+            _chk(lib().limu_odom_register_frame(self.h, x.ctypes.data_as(_fp), n, _d(pose), None, None, None, None, C.byref(self.stats)))
+            return None, None, pose
+        down, src = np.empty((max(n, 1), 3)), np.empty((max(n, 1), 3))
+        nd, ns = C.c_int64(0), C.c_int64(0)
+        _chk(lib().limu_odom_register_frame(self.h, x.ctypes.data_as(_fp), n, _d(pose), _d(down), C.byref(nd), _d(src), C.byref(ns), C.byref(self.stats)))
+        return down[: nd.value].copy(), src[: ns.value].copy(), pose
+
+    def register_frame_dev(self, xyzt_dev_ptr, n):
+        pose = np.empty(7)
+        _chk(lib().limu_odom_register_frame_dev(self.h, _vp(xyzt_dev_ptr), int(n), _d(pose), C.byref(self.stats)))
+        return pose
+
+    def register_points(self, xyz):
+        """register_frame(Vec3dVector)."""
+        xyz = _pts(xyz)
+        n = len(xyz)
+        pose = np.empty(7)
+        down, src = np.empty((max(n, 1), 3)), np.empty((max(n, 1), 3))
+        nd, ns = C.c_int64(0), C.c_int64(0)
+        _chk(lib().limu_odom_register_points(self.h, _d(xyz), n, _d(pose), _d(down), C.byref(nd), _d(src), C.byref(ns), C.byref(self.stats)))
+        return down[: nd.value].copy(), src[: ns.value].copy(), pose
+
+    def poses(self):
+        n = C.c_int64(0)
+        _chk(lib().limu_odom_num_poses(self.h, C.byref(n)))
+        out = np.empty((n.value, 7))
+        for i in range(n.value):
+            _chk(lib().limu_odom_pose(self.h, i, _d(out[i])))
+        return out
+
+    def local_map(self):
+        return VoxelHashMap(self.ctx, 0, 0, self.cfg.max_points_per_voxel, handle=_vp(lib().limu_odom_map(self.h)))
+
+    def has_moved(self):
+        e = C.c_int(0)
+        _chk(lib().limu_odom_has_moved(self.h, C.byref(e)))
+        return bool(e.value)
+
+    def get_prediction_model(self):
+        out = np.empty(7)
+        _chk(lib().limu_odom_prediction(self.h, _d(out)))
+        return out

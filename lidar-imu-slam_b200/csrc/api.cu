@@ -1,0 +1,122 @@
+// api.cu -- context, error state and host-side helpers of the C ABI (include/limu_cuda.h).
+#include <stdarg.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace limu {
+
+static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+void release_ctx_scratch(limu_ctx *c);
+
+int check_status(limu_ctx *c) {
+    LIMU_CUDA_TRY(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, c->stream));
+    LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const DevStatus s = *c->h_status;
+    if (s.key_range || s.table_full) {
+        LIMU_CUDA_TRY(cudaMemsetAsync(c->d_status, 0, sizeof(DevStatus), c->stream));
+        if (s.key_range) { set_error("voxel index outside the packed key range (|index| >= 2^20): point too far for this voxel size"); return LIMU_ERR_KEY_RANGE; }
+        set_error("voxel hash table full");
+        return LIMU_ERR_MAP_FULL;
+    }
+    return LIMU_OK;
+}
+
+}  // namespace limu
+
+using namespace limu;
+
+extern "C" {
+
+const char *limu_last_error(void) { return g_err; }
+int limu_abi_version(void) { return LIMU_ABI_VERSION; }
+uint64_t limu_kernel_launches(void) { return g_launches.load(); }
+
+int limu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void *limu_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+void limu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int limu_ctx_create(int device, limu_ctx **out) {
+    LIMU_REQUIRE(out, "limu_ctx_create: out is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no usable CUDA device (%s); liblimu_cuda has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        cudaGetLastError();
+        return LIMU_ERR_CUDA;
+    }
+    LIMU_REQUIRE(device >= 0 && device < n, "limu_ctx_create: device index out of range");
+    LIMU_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LIMU_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; liblimu_cuda is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return LIMU_ERR_CUDA;
+    }
+    int coop = 0;
+    LIMU_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    if (!coop) { set_error("device %d does not support cooperative launch", device); return LIMU_ERR_CUDA; }
+    limu_ctx *c = new limu_ctx;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    LIMU_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    LIMU_CUDA_TRY(cudaMalloc(&c->d_status, sizeof(DevStatus)));
+    LIMU_CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(DevStatus)));
+    LIMU_CUDA_TRY(cudaHostAlloc(&c->h_status, sizeof(DevStatus), cudaHostAllocDefault));
+    c->h_pinned_bytes = 8192;
+    LIMU_CUDA_TRY(cudaHostAlloc(&c->h_pinned, c->h_pinned_bytes, cudaHostAllocDefault));
+    LIMU_TRY(c->d_small.reserve(8192));
+    LIMU_CUDA_TRY(cudaMemset(c->d_small.p, 0, 8192));
+    *out = c;
+    return LIMU_OK;
+}
+
+void limu_ctx_destroy(limu_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    release_ctx_scratch(c);
+    limu::DevBuf *bufs[] = {&c->in0, &c->in1, &c->out0, &c->out1, &c->out2, &c->tmp0, &c->tmp1, &c->tmp2, &c->tmp3, &c->tmp4, &c->tmp5, &c->d_small};
+    for (auto *b : bufs) b->release();
+    cudaFree(c->d_status);
+    cudaFreeHost(c->h_status);
+    cudaFreeHost(c->h_pinned);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int limu_ctx_sync(limu_ctx *c) {
+    LIMU_TRY(bind(c));
+    LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return LIMU_OK;
+}
+void *limu_ctx_stream(limu_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+void limu_se3_exp(const double x[6], double pose_out[7]) { pose_store(se3_exp(x), pose_out); }
+void limu_se3_log(const double pose[7], double x_out[6]) { se3_log(pose_load(pose), x_out); }
+void limu_se3_mul(const double a[7], const double b[7], double out[7]) { pose_store(mul(pose_load(a), pose_load(b)), out); }
+void limu_se3_inverse(const double a[7], double out[7]) { pose_store(inverse(pose_load(a)), out); }
+
+}  // extern "C"

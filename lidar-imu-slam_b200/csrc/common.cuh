@@ -1,0 +1,101 @@
+// common.cuh -- internal plumbing of liblimu_cuda: error state, context, device buffers, launch counting.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/limu_cuda.h"
+#include "se3.cuh"
+
+namespace limu {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define LIMU_CUDA_TRY(expr)                                                                      \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            limu::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return LIMU_ERR_CUDA;                                                                \
+        }                                                                                        \
+    } while (0)
+
+#define LIMU_TRY(expr)                  \
+    do {                                \
+        int _s = (expr);                \
+        if (_s != LIMU_OK) return _s;   \
+    } while (0)
+
+#define LIMU_REQUIRE(cond, msg)                              \
+    do {                                                     \
+        if (!(cond)) { limu::set_error("%s", msg); return LIMU_ERR_INVALID; } \
+    } while (0)
+
+// Count a launch and check it was accepted.
+#define LIMU_LAUNCHED()                                     \
+    do {                                                    \
+        limu::g_launches.fetch_add(1, std::memory_order_relaxed); \
+        LIMU_CUDA_TRY(cudaGetLastError());                  \
+    } while (0)
+
+// Growable device buffer (never shrinks; contents are NOT preserved on growth unless asked).
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t want, cudaStream_t s = 0, bool keep = false) {
+        if (want <= bytes) return LIMU_OK;
+        size_t nb = bytes ? bytes : 256;
+        while (nb < want) nb *= 2;
+        void *np = nullptr;
+        LIMU_CUDA_TRY(cudaMalloc(&np, nb));
+        if (keep && p && bytes) LIMU_CUDA_TRY(cudaMemcpyAsync(np, p, bytes, cudaMemcpyDeviceToDevice, s));
+        if (p) { LIMU_CUDA_TRY(cudaStreamSynchronize(s)); cudaFree(p); }
+        p = np; bytes = nb;
+        return LIMU_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+// Device-side status word shared by kernels of one context.
+struct DevStatus {
+    int key_range;    // some voxel index fell outside the packed key range
+    int table_full;   // an insert probe ran through the whole table
+    int pad[2];
+};
+
+}  // namespace limu
+
+struct limu_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    limu::DevStatus *d_status = nullptr;   // device
+    limu::DevStatus *h_status = nullptr;   // pinned host mirror
+    // scratch pools reused by the stateless entry points and the pipeline
+    limu::DevBuf in0, in1, out0, out1, out2, tmp0, tmp1, tmp2, tmp3, tmp4, tmp5;
+    void *h_pinned = nullptr;  // small pinned staging area for scalars / poses / counts
+    size_t h_pinned_bytes = 0;
+    limu::DevBuf d_small;      // small device staging area (poses, counts, partial sums)
+};
+
+namespace limu {
+// Bind the calling thread to the context's device (cheap when already current).
+inline int bind(limu_ctx *c) {
+    if (!c) { set_error("null context"); return LIMU_ERR_INVALID; }
+    LIMU_CUDA_TRY(cudaSetDevice(c->device));
+    return LIMU_OK;
+}
+int check_status(limu_ctx *c);   // sync + read DevStatus; maps flags to limu_status and clears them
+// out <- T * in for n points (n read from *n_dev when given); pose7 is DEVICE memory.
+int transform_device(limu_ctx *c, const double *pose_dev, const double *in, double *out, int64_t n_max, const int *n_dev);
+// H2D helpers on the context's stream.
+int stage_in(limu_ctx *c, DevBuf &buf, const void *host, size_t bytes);
+int stage_small(limu_ctx *c, const double *host, int count, int off, double **dev);
+inline int div_up(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
+}  // namespace limu

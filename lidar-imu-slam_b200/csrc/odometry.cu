@@ -1,0 +1,279 @@
+// odometry.cu -- lidar::KissICP (L/include/limu/sensors/lidar/icp.hpp:31-68, L/src/sensors/lidar/icp.cpp)
+// as a device pipeline: one H2D of the raw scan, every stage enqueued on the handle's stream with
+// device-side counts, ONE host synchronisation per scan (to read the pose the scalar host glue needs:
+// adaptive threshold, constant-velocity prediction -- L/src/sensors/lidar/helpers/threshold.cpp, icp.cpp:138-163).
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "ops.cuh"
+#include "voxel_map.cuh"
+
+namespace limu {
+int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t n_max, const int *n_dev, const double *init_pose_dev,
+               double tau, double th, int max_iter, double eps, double *partials_dev, size_t partial_rows, unsigned int *barrier_dev,
+               double *out13_dev, int64_t n_hint, double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev);
+int icp_partial_rows(limu_ctx *c);
+
+// theta = Eigen::AngleAxisd(model_dev.rotationMatrix()).angle() (threshold.cpp:7): quaternion -> matrix
+// (Eigen Quaternion::toRotationMatrix) -> quaternion (Eigen RotationBase assign, Quaternion.h) -> 2 atan2(|v|, |w|).
+static double rotation_angle(const Pose &T) {
+    const double x = T.qx, y = T.qy, z = T.qz, w = T.qw;
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    double m[3][3];
+    m[0][0] = 1 - (tyy + tzz); m[0][1] = txy - twz; m[0][2] = txz + twy;
+    m[1][0] = txy + twz; m[1][1] = 1 - (txx + tzz); m[1][2] = tyz - twx;
+    m[2][0] = txz - twy; m[2][1] = tyz + twx; m[2][2] = 1 - (txx + tyy);
+    double c[4];
+    double t = (m[0][0] + m[1][1]) + m[2][2];
+    if (t > 0) {
+        t = sqrt(t + 1.0);
+        c[3] = 0.5 * t; t = 0.5 / t;
+        c[0] = (m[2][1] - m[1][2]) * t; c[1] = (m[0][2] - m[2][0]) * t; c[2] = (m[1][0] - m[0][1]) * t;
+    } else {
+        int i = 0;
+        if (m[1][1] > m[0][0]) i = 1;
+        if (m[2][2] > m[i][i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrt(m[i][i] - m[j][j] - m[k][k] + 1.0);
+        c[i] = 0.5 * t; t = 0.5 / t;
+        c[3] = (m[k][j] - m[j][k]) * t; c[j] = (m[j][i] + m[i][j]) * t; c[k] = (m[k][i] + m[i][k]) * t;
+    }
+    const double n = sqrt(sqnorm3(c[0], c[1], c[2]));
+    return n != 0.0 ? 2.0 * atan2(n, fabs(c[3])) : 0.0;
+}
+}  // namespace limu
+
+struct limu_odom {
+    limu_ctx *ctx = nullptr;
+    limu_odom_config cfg;
+    limu_map *map = nullptr;
+    std::vector<limu::Pose> poses;
+    // AdaptiveThreshold (helpers/threshold.hpp:9-33)
+    double model_error_sq = 0.0;
+    int num_samples = 0;
+    limu::Pose model_deviation = limu::pose_identity();
+    // device buffers
+    limu::DevBuf raw, frame, down, src0, src, work, world, partials;
+    limu::StageScratch sa, sb;
+    int64_t nk_hint = 4096;
+};
+
+using namespace limu;
+
+static bool odom_has_moved(const limu_odom *o) {   // icp.cpp:156-163
+    if (o->poses.empty()) return false;
+    const Pose d = mul(inverse(o->poses.front()), o->poses.back());
+    return sqrt(sqnorm3(d.tx, d.ty, d.tz)) > 5.0 * o->cfg.min_motion_th;
+}
+static double odom_compute_threshold(limu_odom *o) {   // threshold.cpp:16-28 (+ :5-12)
+    const double theta = rotation_angle(o->model_deviation);
+    const double delta_rot = 2.0 * o->cfg.max_range * sin(theta / 2.0);
+    const double delta_trans = sqrt(sqnorm3(o->model_deviation.tx, o->model_deviation.ty, o->model_deviation.tz));
+    const double model_error = delta_rot + delta_trans;
+    if (model_error > o->cfg.min_motion_th) { o->model_error_sq += model_error * model_error; o->num_samples++; }
+    if (o->num_samples < 1) return o->cfg.initial_threshold;
+    return sqrt(o->model_error_sq / o->num_samples);
+}
+static double odom_adaptive_threshold(limu_odom *o) {   // icp.cpp:138-144
+    if (!odom_has_moved(o)) return o->cfg.initial_threshold;
+    return odom_compute_threshold(o);
+}
+static Pose odom_prediction(const limu_odom *o) {   // icp.cpp:146-154
+    const size_t N = o->poses.size();
+    if (N < 2) return pose_identity();
+    return mul(inverse(o->poses[N - 2]), o->poses[N - 1]);
+}
+
+// Everything after the scan is in device memory as doubles (frame_dev, n points).
+static int odom_register_device(limu_odom *o, const double *frame_dev, int64_t n, int deskewed, double pose_out[7], double *down_xyz,
+                                int64_t *n_down, double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
+    limu_ctx *c = o->ctx;
+    const size_t nb = (size_t)std::max<int64_t>(n, 1) * 24;
+    LIMU_TRY(o->down.reserve(nb, c->stream));
+    LIMU_TRY(o->src0.reserve(nb, c->stream));
+    LIMU_TRY(o->src.reserve(nb, c->stream));
+    LIMU_TRY(o->work.reserve(nb, c->stream));
+    LIMU_TRY(o->world.reserve(nb, c->stream));
+    const int rows = icp_partial_rows(c);
+    LIMU_TRY(o->partials.reserve((size_t)2 * rows * 20 * 8 + 256, c->stream));
+    int *cnt = reinterpret_cast<int *>(c->d_small.as<double>() + 32);   // [0]=n_down [1]=n_src0 [2]=n_keypoints
+    double *out13 = c->d_small.as<double>() + 40;
+    const double v = o->cfg.voxel_size;
+
+    // voxelize (icp.cpp:126-136)
+    LIMU_TRY(downsample_device(c, o->sa, frame_dev, n, nullptr, v * 0.5, o->down.as<double>(), cnt + 0));
+    LIMU_TRY(downsample_device(c, o->sb, o->down.as<double>(), n, cnt + 0, v * 1.5, o->src0.as<double>(), cnt + 1));
+    LIMU_TRY(iqr_device(c, o->sb, o->src0.as<double>(), n, cnt + 1, o->src.as<double>(), cnt + 2, nullptr));
+
+    // host scalar glue (icp.cpp:66-71)
+    const double sigma = odom_adaptive_threshold(o);
+    const Pose pred = odom_prediction(o);
+    const Pose last = o->poses.empty() ? pose_identity() : o->poses.back();
+    const Pose init = mul(last, pred);
+    double init7[7];
+    pose_store(init, init7);
+    double *dinit;
+    LIMU_TRY(stage_small(c, init7, 7, 8, &dinit));
+
+    // ICP (icp.cpp:74-76)
+    double *partials = o->partials.as<double>();
+    unsigned int *barrier = reinterpret_cast<unsigned int *>(partials + (size_t)2 * rows * 20);
+    LIMU_TRY(icp_device(o->map, o->src.as<double>(), o->work.as<double>(), n, cnt + 2, dinit, 3.0 * sigma, sigma / 3.0, o->cfg.icp_max_iteration,
+                        o->cfg.estimation_threshold, partials, (size_t)rows, barrier, out13, o->nk_hint, nullptr, nullptr, nullptr));
+
+    // local_map.update(down_sampled, new_pose) (icp.cpp:81; voxel_hash_map.cpp:138-144)
+    LIMU_TRY(map_maybe_grow(o->map, n));
+    LIMU_TRY(transform_device(c, out13, o->down.as<double>(), o->world.as<double>(), n, cnt + 0));
+    const int64_t upper_before = o->map->used_upper;
+    LIMU_TRY(map_insert_device(o->map, o->world.as<double>(), n, cnt + 0));
+    LIMU_TRY(map_remove_far_device(o->map, out13 + 4));
+
+    // the one synchronisation of the scan
+    double *h = static_cast<double *>(c->h_pinned) + 32;
+    LIMU_CUDA_TRY(cudaMemcpyAsync(h, c->d_small.as<double>() + 32, (8 + 13) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LIMU_TRY(check_status(c));
+    const int *hc = reinterpret_cast<const int *>(h);
+    const int64_t nd = hc[0], nk = hc[2];
+    const double *ho = h + 8;
+    const Pose new_pose = pose_load(ho);
+    o->map->used_upper = upper_before + nd;   // exact: at most one new voxel per inserted point
+    o->nk_hint = std::max<int64_t>(nk, 256);
+
+    o->model_deviation = mul(inverse(init), new_pose);   // icp.cpp:78-79
+    o->poses.push_back(new_pose);                        // :82
+    if (pose_out) pose_store(new_pose, pose_out);
+    if (n_down) *n_down = nd;
+    if (n_keypoints) *n_keypoints = nk;
+    bool copied = false;
+    if (down_xyz && nd > 0) { LIMU_CUDA_TRY(cudaMemcpyAsync(down_xyz, o->down.p, (size_t)nd * 24, cudaMemcpyDeviceToHost, c->stream)); copied = true; }
+    if (keypoints_xyz && nk > 0) { LIMU_CUDA_TRY(cudaMemcpyAsync(keypoints_xyz, o->src.p, (size_t)nk * 24, cudaMemcpyDeviceToHost, c->stream)); copied = true; }
+    if (copied) LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (stats) {
+        stats->n_points = n; stats->n_down = nd; stats->n_keypoints = nk; stats->sigma = sigma; stats->deskewed = deskewed; stats->reserved0 = 0;
+        stats->icp.iterations = (int)ho[7]; stats->icp.converged = (int)ho[8]; stats->icp.last_ncorr = (int64_t)ho[9];
+        stats->icp.mean_candidates = nk > 0 ? ho[10] / (double)nk : 0.0;
+        stats->icp.miss_fraction = nk > 0 ? ho[11] / (double)nk : 0.0;
+    }
+    return LIMU_OK;
+}
+
+// deskew gate + widening (icp.cpp:36-47) on a raw scan already in device memory.
+static int odom_prepare_frame(limu_odom *o, const float *xyzt_dev, int64_t n, int *deskewed) {
+    limu_ctx *c = o->ctx;
+    LIMU_TRY(o->frame.reserve((size_t)std::max<int64_t>(n, 1) * 24, c->stream));
+    const size_t N = o->poses.size();
+    if (o->cfg.deskew && N > 2) {
+        double twist[6];
+        se3_log(mul(inverse(o->poses[N - 2]), o->poses[N - 1]), twist);   // delta_pose(start, end) deskew.cpp:14
+        double *dtw;
+        LIMU_TRY(stage_small(c, twist, 6, 0, &dtw));
+        LIMU_TRY(deskew_device(c, xyzt_dev, n, dtw, o->frame.as<double>()));
+        *deskewed = 1;
+    } else {
+        LIMU_TRY(widen_device(c, xyzt_dev, n, o->frame.as<double>()));
+        *deskewed = 0;
+    }
+    return LIMU_OK;
+}
+
+extern "C" {
+
+void limu_odom_default_config(limu_odom_config *cfg) {   // lidar/frame.hpp:64-80
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->max_range = 100.0;
+    cfg->voxel_size = cfg->max_range / 100.0;
+    cfg->max_points_per_voxel = 10;
+    cfg->deskew = 0;
+    cfg->min_motion_th = 0.1;
+    cfg->icp_max_iteration = 500;
+    cfg->initial_threshold = 2.0;
+    cfg->estimation_threshold = 0.0001;
+}
+
+int limu_odom_create(limu_ctx *c, const limu_odom_config *cfg, limu_odom **out) {
+    LIMU_TRY(bind(c));
+    LIMU_REQUIRE(cfg && out, "limu_odom_create: null argument");
+    LIMU_REQUIRE(cfg->voxel_size > 0 && cfg->max_points_per_voxel >= 1, "limu_odom_create: voxel_size must be > 0 and max_points_per_voxel >= 1");
+    limu_odom *o = new limu_odom;
+    o->ctx = c;
+    o->cfg = *cfg;
+    int64_t capv = cfg->map_capacity_voxels;
+    if (capv <= 0) {   // a sensor sees a shell, not a ball: ~ (2 r / v)^2 * 8 voxels is generous for one neighbourhood
+        const double side = 2.0 * cfg->max_range / cfg->voxel_size;
+        capv = (int64_t)std::min(4.0e6, std::max(65536.0, side * side * 8.0));
+    }
+    int st = limu_map_create(c, cfg->voxel_size, cfg->max_range, cfg->max_points_per_voxel, capv, &o->map);   // icp.hpp:35-37
+    if (st != LIMU_OK) { delete o; return st; }
+    *out = o;
+    return LIMU_OK;
+}
+
+void limu_odom_destroy(limu_odom *o) {
+    if (!o) return;
+    cudaSetDevice(o->ctx->device);
+    cudaStreamSynchronize(o->ctx->stream);
+    limu_map_destroy(o->map);
+    DevBuf *bufs[] = {&o->raw, &o->frame, &o->down, &o->src0, &o->src, &o->work, &o->world, &o->partials};
+    for (auto *b : bufs) b->release();
+    o->sa.release(); o->sb.release();
+    delete o;
+}
+
+int limu_odom_register_frame(limu_odom *o, const float *xyzt, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down,
+                             double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
+    LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyzt), "limu_odom_register_frame: bad arguments");
+    LIMU_TRY(bind(o->ctx));
+    LIMU_TRY(stage_in(o->ctx, o->raw, xyzt, (size_t)n * 16));
+    int deskewed = 0;
+    LIMU_TRY(odom_prepare_frame(o, o->raw.as<float>(), n, &deskewed));
+    return odom_register_device(o, o->frame.as<double>(), n, deskewed, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+}
+
+int limu_odom_register_frame_dev(limu_odom *o, const float *xyzt_dev, int64_t n, double pose_out[7], limu_frame_stats *stats) {
+    LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyzt_dev), "limu_odom_register_frame_dev: bad arguments");
+    LIMU_TRY(bind(o->ctx));
+    int deskewed = 0;
+    LIMU_TRY(odom_prepare_frame(o, xyzt_dev, n, &deskewed));
+    return odom_register_device(o, o->frame.as<double>(), n, deskewed, pose_out, nullptr, nullptr, nullptr, nullptr, stats);
+}
+
+int limu_odom_register_points(limu_odom *o, const double *xyz, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down,
+                              double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
+    LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyz), "limu_odom_register_points: bad arguments");
+    LIMU_TRY(bind(o->ctx));
+    LIMU_TRY(stage_in(o->ctx, o->frame, xyz, (size_t)n * 24));
+    return odom_register_device(o, o->frame.as<double>(), n, 0, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+}
+
+int limu_odom_num_poses(limu_odom *o, int64_t *n) {
+    LIMU_REQUIRE(o && n, "limu_odom_num_poses: null argument");
+    *n = (int64_t)o->poses.size();
+    return LIMU_OK;
+}
+int limu_odom_pose(limu_odom *o, int64_t i, double pose_out[7]) {
+    LIMU_REQUIRE(o && pose_out && i >= 0 && i < (int64_t)o->poses.size(), "limu_odom_pose: index out of range");
+    pose_store(o->poses[(size_t)i], pose_out);
+    return LIMU_OK;
+}
+int limu_odom_adaptive_threshold(limu_odom *o, double *sigma) {
+    LIMU_REQUIRE(o && sigma, "limu_odom_adaptive_threshold: null argument");
+    *sigma = odom_adaptive_threshold(o);
+    return LIMU_OK;
+}
+int limu_odom_prediction(limu_odom *o, double pose_out[7]) {
+    LIMU_REQUIRE(o && pose_out, "limu_odom_prediction: null argument");
+    pose_store(odom_prediction(o), pose_out);
+    return LIMU_OK;
+}
+int limu_odom_has_moved(limu_odom *o, int *out) {
+    LIMU_REQUIRE(o && out, "limu_odom_has_moved: null argument");
+    *out = odom_has_moved(o) ? 1 : 0;
+    return LIMU_OK;
+}
+limu_map *limu_odom_map(limu_odom *o) { return o ? o->map : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,31 @@
+// ops.cuh -- device-pointer entry points of the per-scan stages (shared by the C ABI wrappers in
+// ops.cu and the fused pipeline in odometry.cu). All counts may live in device memory (n_dev) so
+// stages chain without a host round trip; n_max is the launch bound.
+#pragma once
+#include "common.cuh"
+
+namespace limu {
+
+// Scratch owned by whoever runs a downsample / IQR stage.
+struct StageScratch {
+    DevBuf table;     // [keys u64 x Cs | minidx u32 x Cs]
+    DevBuf pslot;     // u32 per point
+    DevBuf flags;     // u8 per point
+    DevBuf blockcnt;  // int per 1024 points
+    DevBuf idx;       // int per point (survivor indices)
+    DevBuf d2;        // double per point (IQR)
+    void release() { table.release(); pslot.release(); flags.release(); blockcnt.release(); idx.release(); d2.release(); }
+};
+
+// deskew.cpp:10-28. twist_dev: 6 doubles (device). out: n x 3 doubles.
+int deskew_device(limu_ctx *c, const float *xyzt_dev, int64_t n, const double *twist_dev, double *out_dev);
+// pointcloud2eigen, calculation_helpers.cpp:83-97: widen float xyz to double.
+int widen_device(limu_ctx *c, const float *xyzt_dev, int64_t n, double *out_dev);
+// icp.cpp:9-30 first-point-wins downsample. out_idx_dev: survivor indices (int, n_max), out_count_dev: int.
+int downsample_device(limu_ctx *c, StageScratch &sc, const double *xyz_dev, int64_t n_max, const int *n_dev, double s,
+                      double *out_xyz_dev, int *out_count_dev);
+// icp.cpp:88-124 + common.hpp:22-63. bounds_dev: 2 doubles (optional).
+int iqr_device(limu_ctx *c, StageScratch &sc, const double *xyz_dev, int64_t n_max, const int *n_dev, double *out_xyz_dev,
+               int *out_count_dev, double *bounds_dev);
+
+}  // namespace limu

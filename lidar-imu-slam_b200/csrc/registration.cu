@@ -1,0 +1,331 @@
+// registration.cu -- correspondence search + point-to-point residual/Jacobian + normal-equation
+// reduction + the Gauss-Newton loop, fused into ONE persistent cooperative kernel.
+// Replaces (L/ = env_ws/src/limu):
+//   VoxelHashMap::get_correspondences / get_closest_neighbour  L/src/sensors/lidar/helpers/voxel_hash_map.cpp:64-130
+//   lidar::align_clouds                                        L/src/sensors/lidar/helpers/registration.cpp:43-92
+//   lidar::ICP                                                 registration.cpp:94-130
+//
+// Per iteration the reference materialises two correspondence vectors, reduces 42-double tuples with
+// tbb::parallel_reduce, solves 6x6 on the host and rewrites the source cloud. Here every query thread
+// does lookup -> gate -> weight -> 16 FP64 partial sums in registers (J = [I | -hat(s)] makes H and g
+// functions of sum w, w s, w s s^T, w r, w s x r); warps shuffle-reduce, CTAs write one partial row,
+// a grid barrier publishes them, and every CTA redundantly folds the rows in a fixed order and runs
+// the identical LDLT / exp / log on one thread, so the next iteration starts without any host or
+// second-barrier round trip. Sums are FP64 throughout; the fold order is fixed -> run-to-run deterministic.
+#include <algorithm>
+#include <vector>
+
+#include "voxel_map.cuh"
+
+namespace limu {
+
+constexpr int ICP_BLOCK = 256;
+constexpr int NS = 20;   // 16 sums + ncorr + ncand + nmiss + pad
+
+struct IcpArgs {
+    MapView map;
+    const unsigned long long *map_counters;   // [0] = live voxels (empty map -> return init_guess, registration.cpp:99-100)
+    const double *points;       // n x 3, sensor frame (read only)
+    double *work;               // n x 3, running source cloud
+    int64_t n_max;
+    const int *n_dev;
+    const double *init_pose;    // 7, device
+    double tau_sq;              // max_corresp_dist^2 (voxel_hash_map.cpp:112)
+    double th;                  // kernel (registration.cpp:57-58)
+    int max_iter;
+    double eps;
+    double *partials;           // [2][gridDim][NS]
+    unsigned int *barrier;      // zeroed before launch
+    double *out;                // [0..6] pose, [7] iterations, [8] converged, [9] ncorr, [10] ncand, [11] nmiss, [12] n
+    double *est_trace;          // optional [max_iter][7]
+    long long *ncorr_trace;     // optional [max_iter]
+    double *hg_trace;           // optional [max_iter][42]
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// Accumulate one gated correspondence (registration.cpp:46-58,75-76).
+__device__ __forceinline__ void accumulate(double *a, const V3 &s, const V3 &t, double d2, double th) {
+    const double rx = s.x - t.x, ry = s.y - t.y, rz = s.z - t.z;       // residual = source - target (:48)
+    const double den = th + d2;
+    const double w = (th * th) / (den * den);                           // :57-58
+    const double wx = w * s.x, wy = w * s.y, wz = w * s.z;
+    a[0] += w;
+    a[1] += wx; a[2] += wy; a[3] += wz;
+    a[4] = fma(wx, s.x, a[4]); a[5] = fma(wx, s.y, a[5]); a[6] = fma(wx, s.z, a[6]);
+    a[7] = fma(wy, s.y, a[7]); a[8] = fma(wy, s.z, a[8]); a[9] = fma(wz, s.z, a[9]);
+    a[10] = fma(w, rx, a[10]); a[11] = fma(w, ry, a[11]); a[12] = fma(w, rz, a[12]);
+    a[13] = fma(w, s.y * rz - s.z * ry, a[13]);
+    a[14] = fma(w, s.z * rx - s.x * rz, a[14]);
+    a[15] = fma(w, s.x * ry - s.y * rx, a[15]);
+}
+
+// Block-level reduction of NS values per thread into row[NS] (fixed tree -> deterministic).
+__device__ __forceinline__ void block_reduce_row(double *a, double *smem /* [ICP_BLOCK/32][NS] */, double *row) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const double v = warp_sum(a[k]);
+        if (lane == 0) smem[warp * NS + k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NS) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < ICP_BLOCK / 32; ++w) v += smem[w * NS + threadIdx.x];
+        row[threadIdx.x] = v;
+    }
+}
+
+static __global__ void __launch_bounds__(ICP_BLOCK) k_icp_persistent(const IcpArgs A) {
+    __shared__ double red[(ICP_BLOCK / 32) * NS];
+    __shared__ double S[NS];
+    __shared__ double E[7];
+    __shared__ int done;
+    const int64_t n = A.n_dev ? (int64_t)*A.n_dev : A.n_max;
+    const int64_t tid = (int64_t)blockIdx.x * ICP_BLOCK + threadIdx.x, nthreads = (int64_t)gridDim.x * ICP_BLOCK;
+    const Pose T_init = pose_load(A.init_pose);
+    if (A.map_counters[0] == 0ull || A.max_iter <= 0) {   // ICP :99-100 (and a zero-iteration loop returns T_icp * init = init)
+        if (tid == 0) {
+            pose_store(A.map_counters[0] == 0ull ? T_init : mul(pose_identity(), T_init), A.out);
+            for (int k = 7; k < 13; ++k) A.out[k] = 0.0;
+            A.out[12] = (double)n;
+        }
+        return;
+    }
+    Pose T_icp = pose_identity();   // only thread 0 of each CTA keeps it current
+    int j = 0;
+    int converged = 0;
+    for (;; ) {
+        double acc[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) acc[k] = 0.0;
+        Pose Ej;
+        if (j > 0) Ej = Pose{E[0], E[1], E[2], E[3], E[4], E[5], E[6]};
+        for (int64_t q = tid; q < n; q += nthreads) {
+            V3 s;
+            if (j == 0) {   // source = init_guess * points (:102-103)
+                s = apply(T_init, V3{A.points[3 * q], A.points[3 * q + 1], A.points[3 * q + 2]});
+            } else {        // source <- estimate * source (:119), applied lazily at the next visit
+                s = apply(Ej, V3{A.work[3 * q], A.work[3 * q + 1], A.work[3 * q + 2]});
+            }
+            A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z;
+            const Nearest nn = map_closest(A.map, s);
+            const double d2 = sqnorm3(nn.x - s.x, nn.y - s.y, nn.z - s.z);   // (found - point).squaredNorm() voxel_hash_map.cpp:120
+            if (d2 < A.tau_sq) {
+                accumulate(acc, s, V3{nn.x, nn.y, nn.z}, d2, A.th);
+                acc[16] += 1.0;
+            }
+            acc[17] += (double)nn.ncand;
+            acc[18] += nn.own ? 0.0 : 1.0;
+        }
+        double *rows = A.partials + (size_t)(j & 1) * gridDim.x * NS;
+        block_reduce_row(acc, red, rows + (size_t)blockIdx.x * NS);
+        grid_barrier(A.barrier, (unsigned int)(j + 1) * gridDim.x);
+        // fold the per-CTA rows: warp w takes columns w, w+8, w+16; lanes stride over CTAs
+        {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            for (int col = warp; col < NS; col += ICP_BLOCK / 32) {
+                double v = 0.0;
+                for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(rows + (size_t)b * NS + col);
+                v = warp_sum(v);
+                if (lane == 0) S[col] = v;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double H[36], g[6], x[6], lg[6];
+            expand_normal_equations(S, H, g);
+            for (int k = 0; k < 6; ++k) g[k] = -g[k];
+            ldlt6_solve(H, g, x);                       // JTJ.ldlt().solve(-JTr) :90
+            const Pose est = se3_exp(x);                // vector6d_to_mat4d :91
+            T_icp = mul(est, T_icp);                    // :122
+            se3_log(est, lg);
+            const int stop = norm6(lg) < A.eps;         // :124
+            pose_store(est, E);
+            done = stop;
+            if (blockIdx.x == 0) {
+                if (A.est_trace) pose_store(est, A.est_trace + 7 * (size_t)j);
+                if (A.ncorr_trace) A.ncorr_trace[j] = (long long)S[16];
+                if (A.hg_trace) {
+                    double *o = A.hg_trace + 42 * (size_t)j;
+                    for (int k = 0; k < 36; ++k) o[k] = H[k];
+                    for (int k = 0; k < 6; ++k) o[36 + k] = -g[k];
+                }
+            }
+        }
+        __syncthreads();
+        ++j;
+        if (done) { converged = 1; break; }
+        if (j >= A.max_iter) break;
+    }
+    if (tid == 0) {
+        pose_store(mul(T_icp, T_init), A.out);          // T_icp * init_guess :129
+        A.out[7] = (double)j; A.out[8] = (double)converged; A.out[9] = S[16]; A.out[10] = S[17]; A.out[11] = S[18]; A.out[12] = (double)n;
+    }
+}
+
+// ---- stand-alone align_clouds -------------------------------------------------------------------------
+static __global__ void __launch_bounds__(ICP_BLOCK) k_align_partial(const double *__restrict__ src, const double *__restrict__ tgt, int64_t n, double th,
+                                                                   double *partials) {
+    __shared__ double red[(ICP_BLOCK / 32) * NS];
+    double acc[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) acc[k] = 0.0;
+    for (int64_t q = (int64_t)blockIdx.x * ICP_BLOCK + threadIdx.x; q < n; q += (int64_t)gridDim.x * ICP_BLOCK) {
+        const V3 s{src[3 * q], src[3 * q + 1], src[3 * q + 2]}, t{tgt[3 * q], tgt[3 * q + 1], tgt[3 * q + 2]};
+        accumulate(acc, s, t, sqnorm3(s.x - t.x, s.y - t.y, s.z - t.z), th);
+        acc[16] += 1.0;
+    }
+    block_reduce_row(acc, red, partials + (size_t)blockIdx.x * NS);
+}
+static __global__ void k_align_solve(const double *partials, int nblocks, double *out /* H36 g6 x6 pose7 */) {
+    __shared__ double S[NS];
+    if (threadIdx.x < NS) {
+        double v = 0.0;
+        for (int b = 0; b < nblocks; ++b) v += partials[(size_t)b * NS + threadIdx.x];
+        S[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double H[36], g[6], ng[6], x[6];
+        expand_normal_equations(S, H, g);
+        for (int k = 0; k < 6; ++k) ng[k] = -g[k];
+        ldlt6_solve(H, ng, x);
+        for (int k = 0; k < 36; ++k) out[k] = H[k];
+        for (int k = 0; k < 6; ++k) { out[36 + k] = g[k]; out[42 + k] = x[k]; }
+        pose_store(se3_exp(x), out + 48);
+    }
+}
+
+static int g_icp_blocks_per_sm = 0;
+
+// Enqueue the persistent ICP kernel. All pointers are device memory; `out13` receives pose + stats.
+int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t n_max, const int *n_dev, const double *init_pose_dev,
+               double tau, double th, int max_iter, double eps, double *partials_dev, size_t partial_rows, unsigned int *barrier_dev,
+               double *out13_dev, int64_t n_hint, double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev) {
+    limu_ctx *c = m->ctx;
+    if (g_icp_blocks_per_sm == 0) {
+        int b = 0;
+        LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_icp_persistent, ICP_BLOCK, 0));
+        g_icp_blocks_per_sm = std::max(1, b);
+    }
+    const int64_t want = std::max<int64_t>(1, div_up(std::max<int64_t>(n_hint, 1), ICP_BLOCK));
+    int grid = (int)std::min<int64_t>(want, (int64_t)c->sm_count * std::min(g_icp_blocks_per_sm, 4));
+    grid = (int)std::min<int64_t>(grid, (int64_t)partial_rows);
+    IcpArgs A;
+    A.map = m->view();
+    A.map_counters = m->counters.as<unsigned long long>();
+    A.points = points_dev; A.work = work_dev; A.n_max = n_max; A.n_dev = n_dev; A.init_pose = init_pose_dev;
+    A.tau_sq = tau * tau; A.th = th; A.max_iter = max_iter; A.eps = eps;
+    A.partials = partials_dev; A.barrier = barrier_dev; A.out = out13_dev;
+    A.est_trace = est_trace_dev; A.ncorr_trace = ncorr_trace_dev; A.hg_trace = hg_trace_dev;
+    LIMU_CUDA_TRY(cudaMemsetAsync(barrier_dev, 0, sizeof(unsigned int), c->stream));
+    void *args[] = {&A};
+    LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_icp_persistent, dim3(grid), dim3(ICP_BLOCK), args, 0, c->stream));
+    LIMU_LAUNCHED();
+    return LIMU_OK;
+}
+
+int icp_partial_rows(limu_ctx *c) { return c->sm_count * 4; }
+
+}  // namespace limu
+
+using namespace limu;
+
+static int icp_common(limu_map *m, const double *points_dev, int64_t n, const double init_guess[7], double tau, double th, int max_iter, double eps,
+                      double pose_out[7], limu_icp_stats *stats, double *est_trace, int64_t *ncorr_trace, double *hg_trace) {
+    limu_ctx *c = m->ctx;
+    double *dinit;
+    LIMU_TRY(stage_small(c, init_guess, 7, 0, &dinit));
+    const int rows = icp_partial_rows(c);
+    LIMU_TRY(c->tmp4.reserve((size_t)std::max<int64_t>(n, 1) * 24, c->stream));                 // working cloud
+    LIMU_TRY(c->tmp5.reserve((size_t)2 * rows * NS * 8 + 256, c->stream));                     // partial rows + barrier
+    const bool tr = est_trace || ncorr_trace || hg_trace;
+    const size_t it = (size_t)std::max(max_iter, 1);
+    if (tr) LIMU_TRY(c->tmp3.reserve(it * (7 + 1 + 42) * 8, c->stream));
+    double *partials = c->tmp5.as<double>();
+    unsigned int *barrier = reinterpret_cast<unsigned int *>(partials + (size_t)2 * rows * NS);
+    double *out13 = c->d_small.as<double>() + 16;
+    double *d_est = tr ? c->tmp3.as<double>() : nullptr;
+    long long *d_nc = tr ? reinterpret_cast<long long *>(d_est + it * 7) : nullptr;
+    double *d_hg = tr ? d_est + it * 8 : nullptr;
+    LIMU_TRY(icp_device(m, points_dev, c->tmp4.as<double>(), n, nullptr, dinit, tau, th, max_iter, eps, partials, (size_t)rows, barrier, out13, n,
+                        d_est, d_nc, d_hg));
+    double *h = static_cast<double *>(c->h_pinned) + 16;
+    LIMU_CUDA_TRY(cudaMemcpyAsync(h, out13, 13 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 7; ++k) pose_out[k] = h[k];
+    const int iters = (int)h[7];
+    if (stats) {
+        stats->iterations = iters; stats->converged = (int)h[8]; stats->last_ncorr = (int64_t)h[9];
+        stats->mean_candidates = n > 0 ? h[10] / (double)n : 0.0;
+        stats->miss_fraction = n > 0 ? h[11] / (double)n : 0.0;
+    }
+    if (tr && iters > 0) {
+        if (est_trace) LIMU_CUDA_TRY(cudaMemcpyAsync(est_trace, d_est, (size_t)iters * 56, cudaMemcpyDeviceToHost, c->stream));
+        if (ncorr_trace) LIMU_CUDA_TRY(cudaMemcpyAsync(ncorr_trace, d_nc, (size_t)iters * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (hg_trace) LIMU_CUDA_TRY(cudaMemcpyAsync(hg_trace, d_hg, (size_t)iters * 42 * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return check_status(c);
+}
+
+extern "C" {
+
+int limu_icp(limu_map *m, const double *xyz, int64_t n, const double init_guess[7], double max_corresp_dist, double kernel, int icp_max_iteration,
+             double est_threshold, double pose_out[7], limu_icp_stats *stats, double *est_trace, int64_t *ncorr_trace, double *hg_trace) {
+    LIMU_REQUIRE(m && init_guess && pose_out && n >= 0 && (n == 0 || xyz), "limu_icp: bad arguments");
+    LIMU_TRY(bind(m->ctx));
+    LIMU_TRY(stage_in(m->ctx, m->ctx->in0, xyz, (size_t)n * 24));
+    return icp_common(m, m->ctx->in0.as<double>(), n, init_guess, max_corresp_dist, kernel, icp_max_iteration, est_threshold, pose_out, stats,
+                      est_trace, ncorr_trace, hg_trace);
+}
+
+int limu_icp_dev(limu_map *m, const double *xyz_dev, int64_t n, const double init_guess[7], double max_corresp_dist, double kernel,
+                 int icp_max_iteration, double est_threshold, double pose_out[7], limu_icp_stats *stats) {
+    LIMU_REQUIRE(m && init_guess && pose_out && n >= 0 && (n == 0 || xyz_dev), "limu_icp_dev: bad arguments");
+    LIMU_TRY(bind(m->ctx));
+    return icp_common(m, xyz_dev, n, init_guess, max_corresp_dist, kernel, icp_max_iteration, est_threshold, pose_out, stats, nullptr, nullptr, nullptr);
+}
+
+int limu_align(limu_ctx *c, const double *src, const double *tgt, int64_t n, double th, double H[36], double g[6], double x[6], double pose_out[7]) {
+    LIMU_TRY(bind(c));
+    LIMU_REQUIRE(n >= 0 && (n == 0 || (src && tgt)), "limu_align: bad arguments");
+    LIMU_TRY(stage_in(c, c->in0, src, (size_t)n * 24));
+    LIMU_TRY(stage_in(c, c->in1, tgt, (size_t)n * 24));
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(div_up(n, ICP_BLOCK), (int64_t)c->sm_count * 4));
+    LIMU_TRY(c->tmp5.reserve((size_t)blocks * NS * 8 + 64 * 8, c->stream));
+    double *partials = c->tmp5.as<double>();
+    double *out = c->d_small.as<double>() + 128;
+    k_align_partial<<<blocks, ICP_BLOCK, 0, c->stream>>>(c->in0.as<double>(), c->in1.as<double>(), n, th, partials);
+    LIMU_LAUNCHED();
+    k_align_solve<<<1, 32, 0, c->stream>>>(partials, blocks, out);
+    LIMU_LAUNCHED();
+    double *h = static_cast<double *>(c->h_pinned) + 128;
+    LIMU_CUDA_TRY(cudaMemcpyAsync(h, out, 55 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (H) memcpy(H, h, 36 * 8);
+    if (g) memcpy(g, h + 36, 6 * 8);
+    if (x) memcpy(x, h + 42, 6 * 8);
+    if (pose_out) memcpy(pose_out, h + 48, 7 * 8);
+    return check_status(c);
+}
+
+}  // extern "C"

@@ -1,0 +1,243 @@
+// se3.cuh -- SE(3) / small dense algebra shared by host glue and device kernels.
+//
+// Restates the parts of Sophus 1.22.10 and Eigen 3.4.0 the reference path calls, with the SAME
+// floating-point operation order wherever a result feeds a voxel key, a distance comparison or a
+// transformed point (those must be bit-identical to the x86-64 reference build, which has no FMA
+// contraction: L/CMakeLists.txt:5 -> this library is compiled with -fmad=false and
+// -Xcompiler -ffp-contract=off). Citations are to sophus/{so3,se3}.hpp and Eigen/src/...
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define LIMU_HD __host__ __device__ __forceinline__
+#else
+#define LIMU_HD inline
+#endif
+
+namespace limu {
+
+struct V3 { double x, y, z; };
+// Pose = Sophus::SE3d parameters: unit quaternion (x,y,z,w) + translation.
+struct Pose { double qx, qy, qz, qw, tx, ty, tz; };
+
+LIMU_HD Pose pose_identity() { return Pose{0, 0, 0, 1, 0, 0, 0}; }
+LIMU_HD Pose pose_load(const double *p) { return Pose{p[0], p[1], p[2], p[3], p[4], p[5], p[6]}; }
+LIMU_HD void pose_store(const Pose &T, double *p) { p[0] = T.qx; p[1] = T.qy; p[2] = T.qz; p[3] = T.qw; p[4] = T.tx; p[5] = T.ty; p[6] = T.tz; }
+
+// Eigen squaredNorm of a fixed 3-vector under SSE2: (a^2 + b^2) + c^2.
+LIMU_HD double sqnorm3(double a, double b, double c) { return (a * a + b * b) + c * c; }
+
+LIMU_HD V3 cross(const V3 &a, const V3 &b) {  // Eigen/src/Geometry/OrthoMethods.h cross3
+    return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+// SO3::operator*(point), so3.hpp:388-399: uv = qv x p; uv += uv; p + w*uv + qv x uv.
+LIMU_HD V3 rotate(const Pose &T, const V3 &p) {
+    const V3 qv{T.qx, T.qy, T.qz};
+    V3 uv = cross(qv, p);
+    uv.x += uv.x; uv.y += uv.y; uv.z += uv.z;
+    const V3 c = cross(qv, uv);
+    return V3{(p.x + T.qw * uv.x) + c.x, (p.y + T.qw * uv.y) + c.y, (p.z + T.qw * uv.z) + c.z};
+}
+// SE3::operator*(point), se3.hpp:319-322.
+LIMU_HD V3 apply(const Pose &T, const V3 &p) {
+    const V3 r = rotate(T, p);
+    return V3{r.x + T.tx, r.y + T.ty, r.z + T.tz};
+}
+
+// SO3(quaternion) constructor -> normalize(), so3.hpp:318-325; 4-vector squaredNorm under SSE2
+// reduces two packets: (x^2 + z^2) + (y^2 + w^2).
+LIMU_HD void quat_normalize(double &x, double &y, double &z, double &w) {
+    const double len = sqrt((x * x + z * z) + (y * y + w * w));
+    x /= len; y /= len; z /= len; w /= len;
+}
+
+// SE3 product, se3.hpp:302-307 with SO3 product so3.hpp:344-369 (renormalises).
+LIMU_HD Pose mul(const Pose &a, const Pose &b) {
+    Pose o;
+    o.qw = a.qw * b.qw - a.qx * b.qx - a.qy * b.qy - a.qz * b.qz;
+    o.qx = a.qw * b.qx + a.qx * b.qw + a.qy * b.qz - a.qz * b.qy;
+    o.qy = a.qw * b.qy + a.qy * b.qw + a.qz * b.qx - a.qx * b.qz;
+    o.qz = a.qw * b.qz + a.qz * b.qw + a.qx * b.qy - a.qy * b.qx;
+    quat_normalize(o.qx, o.qy, o.qz, o.qw);
+    const V3 r = rotate(a, V3{b.tx, b.ty, b.tz});
+    o.tx = a.tx + r.x; o.ty = a.ty + r.y; o.tz = a.tz + r.z;
+    return o;
+}
+// SE3::inverse, se3.hpp:222-225; SO3::inverse so3.hpp:246-248 (conjugate, renormalised).
+LIMU_HD Pose inverse(const Pose &a) {
+    Pose o;
+    o.qx = -a.qx; o.qy = -a.qy; o.qz = -a.qz; o.qw = a.qw;
+    quat_normalize(o.qx, o.qy, o.qz, o.qw);
+    o.tx = o.ty = o.tz = 0.0;
+    const V3 r = rotate(o, V3{a.tx * -1.0, a.ty * -1.0, a.tz * -1.0});
+    o.tx = r.x; o.ty = r.y; o.tz = r.z;
+    return o;
+}
+
+#define LIMU_SOPHUS_EPS 1e-10  // sophus/common.hpp:157
+
+// Row-major 3x3 helpers. Eigen's fixed 3x3 lazy products (column-major, SSE2): rows 0-1 accumulate
+// ((k0 + k1) + k2) through the packet path, row 2 through the scalar unroller k0 + (k1 + k2).
+LIMU_HD void hat(const double *w, double *O) {  // so3.hpp:783-792
+    O[0] = 0; O[1] = -w[2]; O[2] = w[1];
+    O[3] = w[2]; O[4] = 0; O[5] = -w[0];
+    O[6] = -w[1]; O[7] = w[0]; O[8] = 0;
+}
+LIMU_HD void mat3mul(const double *A, const double *B, double *C) {
+    for (int j = 0; j < 3; ++j) {
+        C[j] = (A[0] * B[j] + A[1] * B[3 + j]) + A[2] * B[6 + j];
+        C[3 + j] = (A[3] * B[j] + A[4] * B[3 + j]) + A[5] * B[6 + j];
+        C[6 + j] = A[6] * B[j] + (A[7] * B[3 + j] + A[8] * B[6 + j]);
+    }
+}
+LIMU_HD void mat3vec(const double *A, const double *v, double *o) {
+    o[0] = (A[0] * v[0] + A[1] * v[1]) + A[2] * v[2];
+    o[1] = (A[3] * v[0] + A[4] * v[1]) + A[5] * v[2];
+    o[2] = A[6] * v[0] + (A[7] * v[1] + A[8] * v[2]);
+}
+
+// SE3::exp, se3.hpp:852-861; SO3::expAndTheta so3.hpp:694-732; SO3::leftJacobian so3.hpp:550-571.
+LIMU_HD Pose se3_exp(const double *a) {
+    const double *ups = a, *om = a + 3;
+    const double theta_sq = sqnorm3(om[0], om[1], om[2]);
+    double theta, imag, real;
+    if (theta_sq < LIMU_SOPHUS_EPS * LIMU_SOPHUS_EPS) {
+        theta = 0.0;
+        const double theta_po4 = theta_sq * theta_sq;
+        imag = 0.5 - (1.0 / 48.0) * theta_sq + (1.0 / 3840.0) * theta_po4;
+        real = 1.0 - (1.0 / 8.0) * theta_sq + (1.0 / 384.0) * theta_po4;
+    } else {
+        theta = sqrt(theta_sq);
+        const double half = 0.5 * theta;
+        imag = sin(half) / theta;
+        real = cos(half);
+    }
+    Pose T;
+    T.qw = real; T.qx = imag * om[0]; T.qy = imag * om[1]; T.qz = imag * om[2];
+    const double tsq = theta * theta;  // leftJacobian(omega, theta) recomputes theta^2 (so3.hpp:556)
+    double Om[9], Om2[9], V[9], t[3];
+    hat(om, Om);
+    mat3mul(Om, Om, Om2);
+    if (tsq < LIMU_SOPHUS_EPS * LIMU_SOPHUS_EPS) {
+        for (int i = 0; i < 9; ++i) V[i] = ((i % 4 == 0) ? 1.0 : 0.0) + 0.5 * Om[i];
+    } else {
+        const double c1 = (1.0 - cos(theta)) / tsq, c2 = (theta - sin(theta)) / (tsq * theta);
+        for (int i = 0; i < 9; ++i) V[i] = (((i % 4 == 0) ? 1.0 : 0.0) + c1 * Om[i]) + c2 * Om2[i];
+    }
+    mat3vec(V, ups, t);
+    T.tx = t[0]; T.ty = t[1]; T.tz = t[2];
+    return T;
+}
+
+// SE3::log, se3.hpp:237-253; SO3::logAndTheta so3.hpp:264-310; leftJacobianInverse so3.hpp:573-597.
+LIMU_HD void se3_log(const Pose &T, double *x) {
+    const double sqn = sqnorm3(T.qx, T.qy, T.qz), w = T.qw;
+    double two_atan, theta;
+    if (sqn < LIMU_SOPHUS_EPS * LIMU_SOPHUS_EPS) {
+        const double sw = w * w;
+        two_atan = 2.0 / w - (2.0 / 3.0) * sqn / (w * sw);
+        theta = 2.0 * sqn / w;
+    } else {
+        const double n = sqrt(sqn);
+        const double at = (w < 0.0) ? atan2(-n, -w) : atan2(n, w);
+        two_atan = 2.0 * at / n;
+        theta = two_atan * n;
+    }
+    const double om[3] = {two_atan * T.qx, two_atan * T.qy, two_atan * T.qz};
+    const double tsq = theta * theta;
+    double Om[9], Om2[9], Vi[9];
+    hat(om, Om);
+    mat3mul(Om, Om, Om2);
+    if (tsq < LIMU_SOPHUS_EPS * LIMU_SOPHUS_EPS) {
+        for (int i = 0; i < 9; ++i) Vi[i] = (((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * Om[i]) + (1. / 12.) * Om2[i];
+    } else {
+        const double half = 0.5 * theta;
+        const double c = (1.0 - 0.5 * theta * cos(half) / sin(half)) / (theta * theta);
+        for (int i = 0; i < 9; ++i) Vi[i] = (((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * Om[i]) + c * Om2[i];
+    }
+    const double t[3] = {T.tx, T.ty, T.tz};
+    mat3vec(Vi, t, x);
+    x[3] = om[0]; x[4] = om[1]; x[5] = om[2];
+}
+
+// |v| of a 6-vector as Eigen reduces it (three SSE2 packets, then the horizontal add).
+LIMU_HD double norm6(const double *x) {
+    const double a = (x[0] * x[0] + x[2] * x[2]) + x[4] * x[4];
+    const double b = (x[1] * x[1] + x[3] * x[3]) + x[5] * x[5];
+    return sqrt(a + b);
+}
+
+// Eigen 3.4.0 LDLT<Matrix6d>: diagonal-pivoted in-place factorisation of the lower triangle
+// (Cholesky/LDLT.h:300-395) and the solve with pseudo-inverse of D (:569-607). A is row-major 6x6.
+LIMU_HD void ldlt6_solve(const double *Ain, const double *b, double *x) {
+    double A[36];
+    int tr[6];
+    for (int i = 0; i < 36; ++i) A[i] = Ain[i];
+    double temp[6];
+#define LA(r, c) A[6 * (r) + (c)]
+    for (int k = 0; k < 6; ++k) {
+        int big = k;
+        double bigv = fabs(LA(k, k));
+        for (int i = k + 1; i < 6; ++i) { const double v = fabs(LA(i, i)); if (v > bigv) { bigv = v; big = i; } }
+        tr[k] = big;
+        if (k != big) {
+            for (int c = 0; c < k; ++c) { const double t = LA(k, c); LA(k, c) = LA(big, c); LA(big, c) = t; }
+            for (int r = big + 1; r < 6; ++r) { const double t = LA(r, k); LA(r, k) = LA(r, big); LA(r, big) = t; }
+            { const double t = LA(k, k); LA(k, k) = LA(big, big); LA(big, big) = t; }
+            for (int i = k + 1; i < big; ++i) { const double t = LA(i, k); LA(i, k) = LA(big, i); LA(big, i) = t; }
+        }
+        if (k > 0) {
+            for (int c = 0; c < k; ++c) temp[c] = LA(c, c) * LA(k, c);
+            double acc = 0.0;
+            for (int c = 0; c < k; ++c) acc += LA(k, c) * temp[c];
+            LA(k, k) -= acc;
+            for (int r = k + 1; r < 6; ++r) {
+                double a2 = 0.0;
+                for (int c = 0; c < k; ++c) a2 += LA(r, c) * temp[c];
+                LA(r, k) -= a2;
+            }
+        }
+        const double akk = LA(k, k);
+        const bool valid = fabs(akk) > 0.0;
+        if (k == 0 && !valid) { for (int j = 0; j < 6; ++j) tr[j] = j; break; }
+        if (valid) for (int r = k + 1; r < 6; ++r) LA(r, k) /= akk;
+    }
+    double d[6];
+    for (int i = 0; i < 6; ++i) d[i] = b[i];
+    for (int k = 0; k < 6; ++k) if (tr[k] != k) { const double t = d[k]; d[k] = d[tr[k]]; d[tr[k]] = t; }
+    for (int i = 0; i < 6; ++i) for (int c = 0; c < i; ++c) d[i] -= LA(i, c) * d[c];
+    for (int i = 0; i < 6; ++i) { if (fabs(LA(i, i)) > 2.2250738585072014e-308) d[i] /= LA(i, i); else d[i] = 0.0; }
+    for (int i = 5; i >= 0; --i) for (int c = i + 1; c < 6; ++c) d[i] -= LA(c, i) * d[c];
+    for (int k = 5; k >= 0; --k) if (tr[k] != k) { const double t = d[k]; d[k] = d[tr[k]]; d[tr[k]] = t; }
+    for (int i = 0; i < 6; ++i) x[i] = d[i];
+#undef LA
+}
+
+// The 17 sums that determine H = sum w J^T J and g = sum w J^T r for J = [I | -hat(s)]
+// (registration.cpp:46-54,75-76): w, w*s (3), w*s*s^T (6, upper), w*r (3), w*(s x r) (3), count.
+struct NormalSums {
+    double w, ws[3], wss[6] /* xx xy xz yy yz zz */, wr[3], wsxr[3];
+};
+enum { LIMU_NSUMS = 16 };
+
+// Expand the sums into H (row-major 6x6) and g (6). With A = -hat(s): H = [[wI, wA],[wA^T, wA^T A]],
+// A^T A = (s.s) I - s s^T, g = [w r; w (s x r)].
+LIMU_HD void expand_normal_equations(const double *S, double *H, double *g) {
+    const double w = S[0], sx = S[1], sy = S[2], sz = S[3];
+    const double xx = S[4], xy = S[5], xz = S[6], yy = S[7], yz = S[8], zz = S[9];
+    for (int i = 0; i < 36; ++i) H[i] = 0.0;
+    H[0] = H[7] = H[14] = w;
+    // A = [[0, sz, -sy], [-sz, 0, sx], [sy, -sx, 0]]
+    H[0 * 6 + 4] = sz;  H[0 * 6 + 5] = -sy;
+    H[1 * 6 + 3] = -sz; H[1 * 6 + 5] = sx;
+    H[2 * 6 + 3] = sy;  H[2 * 6 + 4] = -sx;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) H[(3 + c) * 6 + r] = H[r * 6 + 3 + c];
+    H[3 * 6 + 3] = yy + zz; H[3 * 6 + 4] = -xy;     H[3 * 6 + 5] = -xz;
+    H[4 * 6 + 3] = -xy;     H[4 * 6 + 4] = xx + zz; H[4 * 6 + 5] = -yz;
+    H[5 * 6 + 3] = -xz;     H[5 * 6 + 4] = -yz;     H[5 * 6 + 5] = xx + yy;
+    g[0] = S[10]; g[1] = S[11]; g[2] = S[12]; g[3] = S[13]; g[4] = S[14]; g[5] = S[15];
+}
+
+}  // namespace limu

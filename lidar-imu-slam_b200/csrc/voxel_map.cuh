@@ -1,0 +1,167 @@
+// voxel_map.cuh -- device view of the GPU-resident voxel hash map and the lookups kernels inline.
+//
+// Replaces lidar::VoxelHashMap + lidar::VoxelBlock (L/include/limu/sensors/lidar/helpers/
+// voxel_hash_map.hpp:14-48, voxel_block.hpp:13-56): tsl::robin_map<Voxel, VoxelBlock> whose blocks hold
+// one heap node per point becomes ONE open-addressing table in HBM:
+//
+//   slots[C]        16 B  {u64 packed (i,j,k) key, i32 count, u32 spare}   C = power of two, load <= 0.5
+//   birth[C]         8 B  creation sequence of the voxel (= the reference container's address order,
+//                          used only by the 27-cell fallback tie-break, voxel_hash_map.cpp:81-101)
+//   pts[C*cap*3]    24 B  per point, slot-indexed: voxel s owns pts[s*cap .. s*cap+count)
+//   pend[C*cap]      4 B  per point slot: insert scratch (sorted pending input indices), all-ones at rest
+//
+// One 16-byte load answers "is this my voxel and how many points does it hold"; the points of a voxel
+// are contiguous (cap*24 B), so a query touches 1 + ceil(24*count/32) sectors.
+#pragma once
+#include "common.cuh"
+
+namespace limu {
+
+constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+constexpr unsigned long long KEY_TOMB = 0xFFFFFFFFFFFFFFFEull;
+constexpr unsigned long long BIRTH_NONE = 0xFFFFFFFFFFFFFFFFull;
+constexpr unsigned int PEND_NONE = 0xFFFFFFFFu;
+constexpr int KEY_BIAS = 1 << 20;  // voxel indices in (-2^20, 2^20) pack into 3 x 21 bits
+
+struct __align__(16) Slot {
+    unsigned long long key;
+    int count;
+    unsigned int spare;
+};
+
+struct MapView {
+    Slot *slots;
+    unsigned long long *birth;
+    double *pts;
+    unsigned int *pend;
+    unsigned int mask;   // C - 1
+    int shift;           // 64 - log2(C)
+    int cap;
+    double vox;
+};
+
+// utils::get_vox_index, calculation_helpers.cpp:142-147: IEEE double division, truncation toward zero.
+__device__ __forceinline__ int vox_index(double p, double v) { return __double2int_rz(p / v); }
+
+__device__ __forceinline__ bool key_in_range(int x, int y, int z) {
+    return (unsigned)(x + KEY_BIAS - 1) < (unsigned)(2 * KEY_BIAS - 1) && (unsigned)(y + KEY_BIAS - 1) < (unsigned)(2 * KEY_BIAS - 1) &&
+           (unsigned)(z + KEY_BIAS - 1) < (unsigned)(2 * KEY_BIAS - 1);
+}
+__device__ __forceinline__ unsigned long long pack_key(int x, int y, int z) {
+    return ((unsigned long long)(unsigned)(x + KEY_BIAS) << 42) | ((unsigned long long)(unsigned)(y + KEY_BIAS) << 21) |
+           (unsigned long long)(unsigned)(z + KEY_BIAS);
+}
+__host__ __device__ __forceinline__ void unpack_key(unsigned long long k, int &x, int &y, int &z) {
+    x = (int)((k >> 42) & 0x1FFFFF) - KEY_BIAS;
+    y = (int)((k >> 21) & 0x1FFFFF) - KEY_BIAS;
+    z = (int)(k & 0x1FFFFF) - KEY_BIAS;
+}
+// Fibonacci hashing of the packed key; the top log2(C) bits index the table.
+__device__ __forceinline__ unsigned int slot_of(unsigned long long key, int shift) {
+    return (unsigned int)((key * 0x9E3779B97F4A7C15ull) >> shift);
+}
+
+__device__ __forceinline__ void load_slot(const Slot *s, unsigned long long &key, int &count) {
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(s));
+    key = v.x;
+    count = (int)(unsigned int)(v.y & 0xFFFFFFFFull);
+}
+
+// Read-only lookup. Returns slot index or -1; count of the voxel in *count.
+__device__ __forceinline__ int map_find(const MapView &m, unsigned long long key, int *count) {
+    unsigned int s = slot_of(key, m.shift);
+    for (;;) {
+        unsigned long long k; int c;
+        load_slot(m.slots + s, k, c);
+        if (k == key) { *count = c; return (int)s; }
+        if (k == KEY_EMPTY) return -1;
+        s = (s + 1) & m.mask;
+    }
+}
+
+struct Nearest {
+    double x, y, z;   // matched map point, or (0,0,0) when nothing was found
+    int slot;         // table slot of the matched voxel, -1 if none
+    int rank;         // position of the match inside its voxel, -1 if none
+    int ncand;        // points compared
+    int own;          // 1 if the query's own voxel was present
+};
+
+// VoxelBlock::get_closest_point, voxel_block.cpp:87-105: linear scan, strict '<', first minimum wins.
+__device__ __forceinline__ void block_closest(const MapView &m, int slot, int count, const V3 &p, Nearest &r) {
+    const double *b = m.pts + (size_t)slot * (size_t)m.cap * 3;
+    double best = 1.7976931348623157e308;
+    r.rank = -1;
+    for (int i = 0; i < count; ++i) {
+        const double bx = __ldg(b + 3 * i), by = __ldg(b + 3 * i + 1), bz = __ldg(b + 3 * i + 2);
+        const double d = sqnorm3(p.x - bx, p.y - by, p.z - bz);
+        if (d < best) { best = d; r.rank = i; r.x = bx; r.y = by; r.z = bz; }
+    }
+    r.ncand = count;
+}
+
+// VoxelHashMap::get_closest_neighbour, voxel_hash_map.cpp:64-102:
+//  (a) own voxel present            -> closest point inside it only (:71-73)
+//  (b) else the top of a max-heap on (|delta index|^2, block address) over the occupied cells of the
+//      27-neighbourhood (:76-96,101) = the FARTHEST occupied cell, ties to the later-created voxel
+//  (c) nothing                      -> (0,0,0) (:98-99)
+__device__ __forceinline__ Nearest map_closest(const MapView &m, const V3 &p) {
+    Nearest r;
+    r.x = r.y = r.z = 0.0; r.slot = -1; r.rank = -1; r.ncand = 0; r.own = 0;
+    const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
+    int count = 0;
+    if (key_in_range(kx, ky, kz)) {
+        const int s = map_find(m, pack_key(kx, ky, kz), &count);
+        if (s >= 0) {
+            r.slot = s; r.own = 1;
+            block_closest(m, s, count, p, r);
+            return r;
+        }
+    }
+    int best_slot = -1, best_d = -1, best_count = 0;
+    unsigned long long best_birth = 0;
+#pragma unroll 1
+    for (int c = 0; c < 27; ++c) {
+        if (c == 13) continue;  // own voxel: known absent
+        const int dx = c / 9 - 1, dy = (c / 3) % 3 - 1, dz = c % 3 - 1;
+        const int x = kx + dx, y = ky + dy, z = kz + dz;
+        if (!key_in_range(x, y, z)) continue;
+        int cnt;
+        const int s = map_find(m, pack_key(x, y, z), &cnt);
+        if (s < 0) continue;
+        const int d = dx * dx + dy * dy + dz * dz;
+        if (d < best_d) continue;
+        const unsigned long long b = __ldg(m.birth + s);
+        if (d > best_d || b > best_birth) { best_d = d; best_birth = b; best_slot = s; best_count = cnt; }
+    }
+    if (best_slot >= 0) {
+        r.slot = best_slot;
+        block_closest(m, best_slot, best_count, p, r);
+        if (r.rank < 0) { r.x = r.y = r.z = 0.0; }
+    }
+    return r;
+}
+
+}  // namespace limu
+
+// Host-side object behind the C handle.
+struct limu_map {
+    limu_ctx *ctx = nullptr;
+    double vox_size = 1.0, max_distance = 100.0;
+    int cap = 10;
+    int64_t capacity = 0;          // C (slots), power of two
+    limu::DevBuf slots, birth, pts, pend;
+    limu::DevBuf counters;         // device: [0] n_live voxels, [1] n_tomb, [2] n_points, [3] n_used (live + tomb)
+    uint64_t birth_base = 0;       // creation sequence offset of the next insert batch
+    int64_t used_upper = 0;        // host upper bound on live + tomb slots
+    limu::DevBuf pslot;            // per-point slot scratch of the current insert batch
+    limu::DevBuf world;            // transformed copy for update(points, pose)
+    limu::MapView view() const;
+};
+
+namespace limu {
+int map_alloc(limu_map *m, int64_t capacity_slots);
+int map_insert_device(limu_map *m, const double *xyz_dev, int64_t n, const int *n_dev /* optional device count */);
+int map_remove_far_device(limu_map *m, const double *origin_dev3);
+int map_maybe_grow(limu_map *m, int64_t incoming);
+}  // namespace limu

@@ -1,0 +1,120 @@
+"""Synthetic spinning-LiDAR scans for tests and bench.py (the reference ships no
+input data -- its rosbag is git-ignored -- so the workload is generated, seeded and deterministic).
+
+Scene: ground plane + axis-aligned boxes + vertical cylinders (non-symmetric, seeded). A scan is ray-cast
+from a sensor that MOVES during the sweep (pose interpolated between the scan's start and end pose), so
+constant-velocity deskewing has something to undo. Output rows are float32 (x, y, z, t) in the sensor
+frame at each ray's firing time, t in [0,1) = azimuth fraction -- the layout liblimu_cuda takes.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class Scene:
+    def __init__(self, seed=42, n_boxes=28, n_cyl=14, extent=90.0, street=False):
+        rng = np.random.default_rng(seed)
+        if street:   # urban canyon: two facade rows along x, clutter between them
+            ys = np.concatenate([np.full(n_boxes // 2, 14.0), np.full(n_boxes - n_boxes // 2, -15.0)]) + rng.normal(size=n_boxes) * 1.5
+            xs = rng.uniform(-extent, extent, n_boxes)
+            c = np.stack([xs, ys], 1)
+            half = np.stack([rng.uniform(4, 12, n_boxes), rng.uniform(2, 5, n_boxes)], 1)
+        else:
+            c = rng.uniform(-extent, extent, (n_boxes, 2))
+            half = rng.uniform(1.0, 7.0, (n_boxes, 2))
+        h = rng.uniform(2.0, 18.0, n_boxes)
+        self.box_lo = np.concatenate([c - half, np.zeros((n_boxes, 1))], 1)
+        self.box_hi = np.concatenate([c + half, h[:, None]], 1)
+        self.cyl_c = rng.uniform(-extent, extent, (n_cyl, 2))
+        self.cyl_r = rng.uniform(0.2, 1.2, n_cyl)
+        self.cyl_h = rng.uniform(3.0, 12.0, n_cyl)
+        self.sensor_height = 1.8
+
+
+def _rot_z(yaw):
+    c, s = np.cos(yaw), np.sin(yaw)
+    z, o = np.zeros_like(c), np.ones_like(c)
+    return np.stack([np.stack([c, -s, z], -1), np.stack([s, c, z], -1), np.stack([z, z, o], -1)], -2)
+
+
+def loop_trajectory(n, radius=30.0, step=1.0):
+    """n poses (x, y, yaw) on a circle of `radius`, `step` metres of arc apart, yaw along the tangent."""
+    a = np.arange(n) * (step / radius)
+    return np.stack([radius * np.sin(a), radius * (1 - np.cos(a)), a], 1)
+
+
+def pose7_of(xyyaw, height=1.8):
+    """(x, y, yaw) -> pose {qx,qy,qz,qw,tx,ty,tz}."""
+    x, y, yaw = xyyaw
+    return np.array([0.0, 0.0, np.sin(yaw / 2), np.cos(yaw / 2), x, y, height])
+
+
+def cast_scan(scene, pose_start, pose_end, beams=64, azimuth_steps=2000, elev=(-25.0, 2.0), rng_gate=(5.0, 100.0),
+              noise=0.02, seed=0, keep_all=False):
+    """Ray-cast one sweep. pose_* = (x, y, yaw) world poses at sweep start / end."""
+    rng = np.random.default_rng(seed)
+    el = np.deg2rad(np.linspace(elev[0], elev[1], beams))
+    az_i = np.arange(azimuth_steps)
+    t = np.repeat(az_i / azimuth_steps, beams)                    # time-ordered: all beams fire per azimuth step
+    az = np.repeat(az_i * (2 * np.pi / azimuth_steps), beams)
+    e = np.tile(el, azimuth_steps)
+    d_s = np.stack([np.cos(e) * np.cos(az), np.cos(e) * np.sin(az), np.sin(e)], 1)   # sensor-frame directions
+    p0, p1 = np.asarray(pose_start, float), np.asarray(pose_end, float)
+    xy = p0[None, :2] + t[:, None] * (p1[:2] - p0[:2])[None]
+    yaw = p0[2] + t * (p1[2] - p0[2])
+    R = _rot_z(yaw)
+    d_w = np.einsum("nij,nj->ni", R, d_s)
+    o_w = np.concatenate([xy, np.full((len(t), 1), scene.sensor_height)], 1)
+    best = np.full(len(t), np.inf)
+    # ground z = 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tg = -o_w[:, 2] / d_w[:, 2]
+    tg[~(tg > 0)] = np.inf
+    best = np.minimum(best, tg)
+    # boxes (slab test), chunked to bound memory
+    for b0 in range(0, len(scene.box_lo), 8):
+        lo, hi = scene.box_lo[b0:b0 + 8], scene.box_hi[b0:b0 + 8]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = 1.0 / d_w
+            t1 = (lo[None] - o_w[:, None]) * inv[:, None]
+            t2 = (hi[None] - o_w[:, None]) * inv[:, None]
+        tn = np.nanmax(np.minimum(t1, t2), axis=2)
+        tf = np.nanmin(np.maximum(t1, t2), axis=2)
+        hit = (tf >= tn) & (tf > 0)
+        tt = np.where(hit, np.where(tn > 0, tn, np.inf), np.inf)
+        best = np.minimum(best, tt.min(axis=1))
+    # vertical cylinders
+    for c, r, h in zip(scene.cyl_c, scene.cyl_r, scene.cyl_h):
+        oc = o_w[:, :2] - c
+        a = (d_w[:, :2] ** 2).sum(1)
+        b = 2 * (oc * d_w[:, :2]).sum(1)
+        cc = (oc ** 2).sum(1) - r * r
+        disc = b * b - 4 * a * cc
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tc = (-b - np.sqrt(disc)) / (2 * a)
+        z = o_w[:, 2] + tc * d_w[:, 2]
+        ok = (disc > 0) & (tc > 0) & (z >= 0) & (z <= h)
+        best = np.minimum(best, np.where(ok, tc, np.inf))
+    rngs = best + rng.normal(size=len(best)) * noise
+    valid = np.isfinite(best) & (rngs >= rng_gate[0]) & (rngs <= rng_gate[1])   # range gate lidar/frame.hpp:65-66
+    if keep_all:
+        rngs = np.where(valid, rngs, rng_gate[1] * 0.5)
+        valid[:] = True
+    rngs = np.where(valid, rngs, 0.0)
+    pts = d_s * rngs[:, None]
+    out = np.concatenate([pts, t[:, None]], 1)[valid].astype(np.float32)
+    return np.ascontiguousarray(out)
+
+
+def pad_scan(scan, n, seed=0):
+    """Resize a scan to exactly n points (subsample, or repeat with sub-centimetre jitter), keeping time order."""
+    if len(scan) == n:
+        return scan
+    rng = np.random.default_rng(seed)
+    if len(scan) > n:
+        idx = np.sort(rng.choice(len(scan), n, replace=False))
+        return np.ascontiguousarray(scan[idx])
+    extra = scan[rng.integers(0, len(scan), n - len(scan))].copy()
+    extra[:, :3] += rng.normal(size=(len(extra), 3)).astype(np.float32) * 0.005
+    out = np.concatenate([scan, extra])
+    return np.ascontiguousarray(out[np.argsort(out[:, 3], kind="stable")])

@@ -1,0 +1,61 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol
+include/limu_cuda.h declares, its host-side SE(3) helpers match the oracle bit for bit, and creating a
+context without a device fails loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, random_pose
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as g
+    p = g.load_package()
+    if not os.path.exists(p.LIB_PATH):
+        p.build()
+    return p
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "limu_cuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(limu_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(pkg):
+    lib = ctypes.CDLL(pkg.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 45
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.limu_abi_version() == 1
+
+
+def test_binding_covers_the_header(pkg):
+    bound = set(re.findall(r"\blimu_[a-z0-9_]+", open(os.path.join(os.path.dirname(pkg.LIB_PATH), "__init__.py")).read()))
+    skip = {"limu_last_error", "limu_abi_version"}
+    assert not [n for n in declared_symbols() if n not in bound and n not in skip]
+
+
+def test_host_se3_matches_oracle(pkg, port, rng):
+    for _ in range(300):
+        x = rng.normal(size=6) * np.array([5, 5, 5, 1, 1, 1])
+        A, B = pkg.se3_exp(x), random_pose(port, rng)
+        assert np.array_equal(A, port.se3_exp(x))
+        assert np.array_equal(pkg.se3_mul(A, B), port.se3_mul(A, B))
+        assert np.array_equal(pkg.se3_inverse(A), port.se3_inv(A))
+        np.testing.assert_allclose(pkg.se3_log(A), port.se3_log(A), rtol=0, atol=1e-13)
+
+
+def test_no_device_means_error_not_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.LimuError) as e:
+        pkg.Context(0)
+    assert "no CPU fallback" in str(e.value)
+    assert pkg.device_count() == 0

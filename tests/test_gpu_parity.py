@@ -1,0 +1,278 @@
+"""Parity of the CUDA path (through the C ABI, liblimu_cuda.so) against the oracle.
+
+Bar (BASELINE.json north_star): voxel keys, downsampled / filtered clouds, map contents and
+correspondence indices BIT-EXACT; poses within 1e-5 m / 1e-6 rad per update (asserted much tighter
+where the math allows). The oracle is the plain-C restatement (always) and the compiled reference
+itself (when its prebuilt binary travelled with the repo).
+"""
+import numpy as np
+import pytest
+
+from conftest import random_pose
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as g
+    return g.load_package()
+
+
+@pytest.fixture(scope="module")
+def ctx(pkg):
+    c = pkg.Context(0)
+    yield c
+    c.close()
+
+
+def oracles(request):
+    out = [request.getfixturevalue("port")]
+    import oracle
+    if oracle.have_ref():
+        out.append(request.getfixturevalue("ref"))
+    return out
+
+
+def test_library_loaded_is_in_tree(pkg):
+    import os
+    assert os.path.samefile(os.path.dirname(pkg.LIB_PATH), os.path.dirname(pkg.__file__))
+    assert pkg.device_count() >= 1
+
+
+def test_host_se3_helpers(pkg, port, rng):
+    for _ in range(200):
+        x = rng.normal(size=6) * np.array([5, 5, 5, 1, 1, 1])
+        A = pkg.se3_exp(x)
+        B = random_pose(port, rng)
+        assert np.array_equal(A, port.se3_exp(x))
+        assert np.array_equal(pkg.se3_mul(A, B), port.se3_mul(A, B))
+        assert np.array_equal(pkg.se3_inverse(A), port.se3_inv(A))
+        np.testing.assert_allclose(pkg.se3_log(A), port.se3_log(A), rtol=0, atol=1e-13)
+
+
+def test_voxel_keys_and_transform_bit_exact(ctx, request, rng):
+    pts = rng.normal(size=(300000, 3)) * 40
+    pts[:1000] = np.round(pts[:1000])
+    pts[1000:2000] = np.round(pts[1000:2000]) * 0.5
+    pts[2000:2010] = 0.0
+    pts[2010:2020] *= 1e-9
+    for o in oracles(request):
+        for v in (1.0, 0.5, 1.5, 0.25, 0.3, 0.1):
+            assert np.array_equal(ctx.voxel_keys(pts, v), o.vox_index(pts, v))
+        T = random_pose(o, rng)
+        assert np.array_equal(ctx.transform_points(T, pts), o.transform(T, pts))
+
+
+@pytest.mark.parametrize("cap,vox,spread,qspread", [(10, 1.0, 10.0, 11.0), (1, 0.5, 3.0, 4.0), (20, 1.0, 3.0, 3.5), (3, 2.0, 30.0, 33.0)])
+def test_map_contents_neighbours_correspondences_bit_exact(ctx, request, rng, cap, vox, spread, qspread):
+    batches = [rng.normal(size=(20000, 3)) * spread for _ in range(3)]
+    q = rng.normal(size=(30000, 3)) * qspread
+    gm = ctx.VoxelHashMap(vox, 100.0, cap)
+    for b in batches:
+        gm.insert_points(b)
+    gk, gc, gp = gm.dump()
+    gout, gkey, grank = gm.get_closest_neighbour(q, with_index=True)
+    for o in oracles(request):
+        om = o.Map(vox, 100.0, cap)
+        for b in batches:
+            om.insert(b)
+        ok, oc, op = om.dump()
+        assert np.array_equal(gk, ok) and np.array_equal(gc, oc) and np.array_equal(gp, op)   # same voxels, creation order, points
+        if o.kind == "port":
+            oout, okey, orank = om.closest(q, with_index=True)
+            assert np.array_equal(gkey, okey) and np.array_equal(grank, orank)                # correspondence INDICES
+        else:
+            oout = om.closest(q)
+        assert np.array_equal(gout, oout)
+        for tau in (0.3, 1.0, 2.5):
+            gs, gt, gi = gm.get_correspondences(q, tau, with_index=True)
+            os_, ot = om.correspondences(q, tau)[:2]
+            assert np.array_equal(gs, os_) and np.array_equal(gt, ot)
+            assert np.array_equal(gs, q[gi])
+    assert (grank < 0).any() and (grank >= 0).any()
+    gm.close()
+
+
+def test_empty_and_origin_semantics(ctx, port):
+    gm = ctx.VoxelHashMap(1.0, 100.0, 10)
+    assert gm.empty() and gm.size() == (0, 0)
+    gm.insert_points(np.zeros((0, 3)))
+    assert gm.empty()
+    gm.insert_points(np.array([[50.0, 50.0, 50.0]]))
+    assert not gm.empty()
+    q = np.array([[0.3, 0.2, -0.1], [5.0, 5.0, 5.0]])
+    assert np.array_equal(gm.get_closest_neighbour(q), np.zeros((2, 3)))        # nothing found -> (0,0,0)
+    s, t = gm.get_correspondences(q, 1.0)
+    assert len(s) == 1 and np.array_equal(s[0], q[0]) and np.array_equal(t[0], np.zeros(3))
+    s, t = gm.get_correspondences(np.zeros((0, 3)), 1.0)
+    assert len(s) == 0
+    gm.clear()
+    assert gm.empty()
+    gm.close()
+
+
+def test_remove_points_from_far_and_update(ctx, request, rng):
+    for vox, maxd in ((1.0, 20.0), (0.5, 30.0), (0.1, 5.0)):
+        pts = rng.normal(size=(20000, 3)) * maxd
+        o3 = rng.normal(size=3) * 3
+        more = rng.normal(size=(5000, 3)) * maxd
+        q = rng.normal(size=(5000, 3)) * maxd
+        for o in oracles(request):
+            T = random_pose(o, np.random.default_rng(5), trans=2.0, rot=0.1)
+            gm = ctx.VoxelHashMap(vox, maxd, 5)
+            om = o.Map(vox, maxd, 5)
+            gm.insert_points(pts)
+            om.insert(pts)
+            gm.remove_points_from_far(o3)
+            om.remove_far(o3)
+            assert all(np.array_equal(a, b) for a, b in zip(gm.dump(), om.dump()))
+            gm.update(more, T)
+            om.update(more, T)
+            assert all(np.array_equal(a, b) for a, b in zip(gm.dump(), om.dump()))
+            assert np.array_equal(gm.get_closest_neighbour(q), om.closest(q))
+            gm.close()
+
+
+def test_map_growth_keeps_contents(ctx, port, rng):
+    gm = ctx.VoxelHashMap(0.5, 1000.0, 4, capacity_voxels=512)      # forces several rehash/grow cycles
+    om = port.Map(0.5, 1000.0, 4)
+    for _ in range(6):
+        b = rng.normal(size=(30000, 3)) * 25
+        gm.insert_points(b)
+        om.insert(b)
+    assert all(np.array_equal(a, b) for a, b in zip(gm.dump(), om.dump()))
+    q = rng.normal(size=(20000, 3)) * 25
+    assert np.array_equal(gm.get_closest_neighbour(q), om.closest(q))
+    gm.close()
+
+
+def test_downsample_iqr_voxelize_bit_exact(ctx, request, rng):
+    pts = rng.normal(size=(120000, 3)) * np.array([30, 30, 3])
+    for o in oracles(request):
+        for s in (0.5, 1.5, 0.25, 0.75):
+            assert np.array_equal(ctx.voxel_downsample(pts, s), o.voxel_downsample(pts, s))
+        for n in (1, 2, 3, 4, 5, 29, 30, 31, 1000, 4097, 50000):
+            assert np.array_equal(ctx.iqr_processing(pts[:n]), o.iqr(pts[:n]))
+        heavy = np.concatenate([pts[:3000], rng.normal(size=(60, 3)) * 400])
+        a = ctx.iqr_processing(heavy)
+        assert np.array_equal(a, o.iqr(heavy)) and len(a) < len(heavy)
+        for v in (1.0, 0.5):
+            gs, gd = ctx.voxelize(pts, v)
+            os_, od = o.voxelize(pts, v)
+            assert np.array_equal(gs, os_) and np.array_equal(gd, od)
+    out, idx = ctx.voxel_downsample(pts, 1.0, with_index=True)
+    assert np.array_equal(out, pts[idx]) and np.all(np.diff(idx) > 0)
+    assert len(ctx.voxel_downsample(np.zeros((0, 3)), 1.0)) == 0
+    assert len(ctx.iqr_processing(np.zeros((0, 3)))) == 0
+
+
+def test_deskew(ctx, request, rng):
+    xyzt = np.concatenate([(rng.normal(size=(100000, 3)) * 30), rng.random((100000, 1))], 1).astype(np.float32)
+    for o in oracles(request):
+        T0 = random_pose(o, rng)
+        T1 = o.se3_mul(T0, o.se3_exp(np.array([1.0, 0.1, -0.05, 0.01, -0.02, 0.1])))
+        a = ctx.deskew_scan(xyzt, T0, T1)
+        b = o.deskew(xyzt[:, :3], xyzt[:, 3].astype(np.float64), T0, T1)
+        # device sin/cos differ from glibc by <= 2 ulp: points agree to ~1e-13 m (tolerance 1e-11 m)
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-11)
+
+
+def test_align_clouds(ctx, request, rng):
+    for n in (3, 7, 100, 20000, 300000):
+        src = rng.normal(size=(n, 3)) * 20
+        for o in oracles(request):
+            T = o.se3_exp(rng.normal(size=6) * 0.05)
+            tgt = o.transform(T, src) + rng.normal(size=(n, 3)) * 0.01
+            for th in (2.0 / 3.0, 0.1):
+                g = ctx.align_clouds(src, tgt, th)
+                r = o.align(src, tgt, th)
+                np.testing.assert_allclose(g["pose"], r["pose"], rtol=0, atol=1e-10)
+                if "H" in r:   # normal equations themselves: <= 1e-12 relative to their scale
+                    np.testing.assert_allclose(g["H"], r["H"], rtol=0, atol=1e-12 * np.abs(r["H"]).max())
+                    np.testing.assert_allclose(g["g"], r["g"], rtol=0, atol=1e-12 * max(np.abs(r["g"]).max(), np.abs(r["H"]).max() * 1e-3))
+    g = ctx.align_clouds(np.zeros((0, 3)), np.zeros((0, 3)), 0.5)
+    assert np.array_equal(g["pose"], [0, 0, 0, 1, 0, 0, 0])
+
+
+def _dense_scene(rng, n=40000):
+    a = rng.random((n // 3, 3)) * 40 - 20
+    a[:, 2] = rng.normal(size=len(a)) * 0.02
+    b = rng.random((n // 3, 3)) * 40 - 20
+    b[:, 0] = 20 + rng.normal(size=len(b)) * 0.02
+    c = rng.random((n // 3, 3)) * 40 - 20
+    c[:, 1] = -20 + rng.normal(size=len(c)) * 0.02
+    return np.concatenate([a, b, c])
+
+
+@pytest.mark.parametrize("nq", [300, 5000, 60000])
+def test_icp_per_iteration_and_pose(ctx, request, rng, nq):
+    world = _dense_scene(rng, 90000)
+    gm = ctx.VoxelHashMap(1.0, 100.0, 20)
+    gm.insert_points(world)
+    for o in oracles(request):
+        om = o.Map(1.0, 100.0, 20)
+        om.insert(world)
+        true = o.se3_exp(np.array([0.3, -0.2, 0.05, 0.004, -0.003, 0.02]))
+        src = o.transform(o.se3_inv(true), world[rng.choice(len(world), nq, replace=nq > len(world))])
+        init = np.array([0, 0, 0, 1.0, 0, 0, 0])
+        sigma = 2.0
+        g = gm.icp(src, init, 3 * sigma, sigma / 3, 60, 1e-4, trace=True)
+        r = o.icp(om, src, init, 3 * sigma, sigma / 3, 60, 1e-4, trace=True)
+        assert g["iters"] == r["iters"] and g["converged"]
+        assert np.array_equal(g["ncorr"], r["ncorr"])                       # same correspondence sets every iteration
+        np.testing.assert_allclose(g["est"], r["est"], rtol=0, atol=1e-10)
+        if "hg" in r:
+            scale = np.abs(r["hg"]).max(axis=1, keepdims=True)
+            np.testing.assert_allclose(g["hg"], r["hg"], rtol=0, atol=1e-12 * scale.max())
+        np.testing.assert_allclose(g["pose"][4:], r["pose"][4:], rtol=0, atol=1e-9)    # bar: 1e-5 m
+        np.testing.assert_allclose(g["pose"][:4], r["pose"][:4], rtol=0, atol=1e-10)   # bar: 1e-6 rad
+    # empty map -> init_guess untouched; max_iter cap respected
+    em = ctx.VoxelHashMap(1.0, 100.0, 20)
+    T = random_pose(oracles(request)[0], rng)
+    assert np.array_equal(em.icp(src, T, 6, 0.6, 10, 1e-4)["pose"], T)
+    capped = gm.icp(src, init, 6, 2 / 3, 2, 1e-12)
+    assert capped["iters"] == 2 and not capped["converged"]
+    em.close()
+    gm.close()
+
+
+def test_register_frame_sequence(ctx, pkg, request, rng):
+    """KissICP::register_frame over a moving synthetic LiDAR sequence, deskew on."""
+    from importlib import import_module
+    synth = import_module("limu_b200.synth")
+    scene = synth.Scene(seed=3)
+    traj = synth.loop_trajectory(9, radius=30.0, step=0.6)
+    scans = [synth.cast_scan(scene, traj[i], traj[i + 1], beams=32, azimuth_steps=900, seed=i) for i in range(8)]
+    for o in oracles(request):
+        gk = ctx.KissICP(voxel_size=1.0, cap=10, deskew=True, icp_max_iteration=80)
+        ok = o.Kiss(voxel_size=1.0, max_range=100.0, cap=10, deskew=True, icp_max_iteration=80)
+        for i, scan in enumerate(scans):
+            gd, gs, gp = gk.register_frame(scan)
+            od, os_, op = ok.register_cloud(scan[:, :3], scan[:, 3].astype(np.float64))
+            assert gd.shape == od.shape and gs.shape == os_.shape
+            if i < 3:
+                assert np.array_equal(gd, od) and np.array_equal(gs, os_)
+            else:
+                np.testing.assert_allclose(gd, od, rtol=0, atol=1e-9)
+            assert np.abs(gp[4:] - op[4:]).max() < 1e-5 and np.abs(gp[:4] - op[:4]).max() < 1e-6
+            assert gk.stats.n_points == len(scan) and gk.stats.n_down == len(gd) and gk.stats.n_keypoints == len(gs)
+            assert gk.stats.deskewed == (1 if i >= 3 else 0)
+        np.testing.assert_allclose(gk.poses(), ok.poses(), rtol=0, atol=1e-5)
+        gmap, omap = gk.local_map().dump(), (ok.map().dump() if o.kind == "port" else None)
+        if omap is not None:
+            assert np.array_equal(gmap[0], omap[0]) and np.array_equal(gmap[1], omap[1])
+            np.testing.assert_allclose(gmap[2], omap[2], rtol=0, atol=1e-6)
+        gk.close()
+
+
+def test_no_cpu_fallback_and_errors(pkg, ctx):
+    with pytest.raises(pkg.LimuError):
+        pkg.Context(9999)
+    gm = ctx.VoxelHashMap(1e-6, 100.0, 4)
+    with pytest.raises(pkg.LimuError) as e:
+        gm.insert_points(np.array([[1e3, 0.0, 0.0]]))      # voxel index 1e9: outside the packed key range
+    assert e.value.status == -3
+    gm.close()
+    with pytest.raises(pkg.LimuError):
+        ctx.VoxelHashMap(1.0, 100.0, 0)
