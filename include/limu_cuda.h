@@ -61,6 +61,13 @@ int limu_ctx_create(int device, limu_ctx **out);
 void limu_ctx_destroy(limu_ctx *c);
 int limu_ctx_sync(limu_ctx *c);
 void *limu_ctx_stream(limu_ctx *c); /* cudaStream_t, for callers that enqueue their own work around ours */
+/* Optional per-stage device timing of limu_odom_register_* with CUDA events on the context's stream
+ * (what bench.py's roofline reads). Stages: */
+enum { LIMU_STAGE_PREPARE = 0, /* deskew / widen */
+       LIMU_STAGE_DOWNSAMPLE = 1, LIMU_STAGE_IQR = 2, LIMU_STAGE_ICP = 3, /* the fused registration kernel alone */
+       LIMU_STAGE_MAP_UPDATE = 4, LIMU_NUM_STAGES = 5 };
+int limu_ctx_set_profiling(limu_ctx *c, int enabled);   /* also resets the accumulators */
+int limu_ctx_get_profile(limu_ctx *c, double ms[LIMU_NUM_STAGES], int64_t frames[1]);
 
 /* ---- stateless point operations ------------------------------------------------------------------ */
 /* utils::get_vox_index, calculation_helpers.cpp:142-147: keys[3i+a] = (int)(xyz[3i+a] / v). */

@@ -79,6 +79,7 @@ def lib():
         L.limu_odom_map.argtypes = [_vp]
         sig = {
             "limu_ctx_create": [C.c_int, C.POINTER(_vp)], "limu_ctx_destroy": [_vp], "limu_ctx_sync": [_vp],
+            "limu_ctx_set_profiling": [_vp, C.c_int], "limu_ctx_get_profile": [_vp, _dp, _lp],
             "limu_voxel_keys": [_vp, _dp, C.c_int64, C.c_double, _ip],
             "limu_transform_points": [_vp, _dp, _dp, C.c_int64],
             "limu_deskew": [_vp, _fp, C.c_int64, _dp, _dp, _dp],
@@ -208,6 +209,18 @@ class Context:
 
     def stream(self) -> int:
         return int(lib().limu_ctx_stream(self.h) or 0)
+
+    STAGES = ("prepare", "downsample", "iqr", "icp", "map_update")
+
+    def set_profiling(self, enabled: bool):
+        _chk(lib().limu_ctx_set_profiling(self.h, int(enabled)))
+
+    def profile(self):
+        """{stage: accumulated device ms} and the number of frames folded in."""
+        ms = np.zeros(len(self.STAGES))
+        fr = np.zeros(1, np.int64)
+        _chk(lib().limu_ctx_get_profile(self.h, _d(ms), fr.ctypes.data_as(_lp)))
+        return dict(zip(self.STAGES, ms.tolist())), int(fr[0])
 
     # utils::get_vox_index
     def voxel_keys(self, xyz, v):
@@ -403,6 +416,9 @@ class KissICP:
         if self.h:
             lib().limu_odom_destroy(self.h)
             self.h = None
+            for b in getattr(self, "_outs", []):
+                b.free()
+            self._outs, self._out_n = [], -1
 
     def __del__(self):
         try:
@@ -410,8 +426,18 @@ class KissICP:
         except Exception:
             pass
 
-    def register_frame(self, xyzt_f32, want_clouds=True):
-        """register_frame(cloud, timestamps): xyzt = float32 [n,4] (x,y,z,t in [0,1]). -> (down, keypoints, pose)."""
+    def _out_buffers(self, n):
+        """Persistent pinned output buffers (grown on demand) so D2H copies are plain DMA."""
+        if getattr(self, "_out_n", -1) < n:
+            for b in getattr(self, "_outs", []):
+                b.free()
+            self._outs = [PinnedArray((max(n, 1), 3), np.float64), PinnedArray((max(n, 1), 3), np.float64)]
+            self._out_n = n
+        return self._outs[0].array, self._outs[1].array
+
+    def register_frame(self, xyzt_f32, want_clouds=True, copy=True):
+        """register_frame(cloud, timestamps): xyzt = float32 [n,4] (x,y,z,t in [0,1]). -> (down, keypoints, pose).
+        With copy=False the clouds are views into pinned buffers that the next call overwrites."""
         x = xyzt_f32 if isinstance(xyzt_f32, np.ndarray) and xyzt_f32.dtype == np.float32 and xyzt_f32.flags.c_contiguous else np.ascontiguousarray(xyzt_f32, np.float32)
         x = x.reshape(-1, 4)
         n = len(x)
@@ -419,10 +445,12 @@ class KissICP:
         if not want_clouds:
             _chk(lib().limu_odom_register_frame(self.h, x.ctypes.data_as(_fp), n, _d(pose), None, None, None, None, C.byref(self.stats)))
             return None, None, pose
-        down, src = np.empty((max(n, 1), 3)), np.empty((max(n, 1), 3))
+        down, src = self._out_buffers(n)
         nd, ns = C.c_int64(0), C.c_int64(0)
         _chk(lib().limu_odom_register_frame(self.h, x.ctypes.data_as(_fp), n, _d(pose), _d(down), C.byref(nd), _d(src), C.byref(ns), C.byref(self.stats)))
-        return down[: nd.value].copy(), src[: ns.value].copy(), pose
+        if copy:
+            return down[: nd.value].copy(), src[: ns.value].copy(), pose
+        return down[: nd.value], src[: ns.value], pose
 
     def register_frame_dev(self, xyzt_dev_ptr, n):
         pose = np.empty(7)

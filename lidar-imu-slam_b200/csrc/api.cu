@@ -32,11 +32,40 @@ int check_status(limu_ctx *c) {
     return LIMU_OK;
 }
 
+int prof_collect(limu_ctx *c) {
+    if (!c->profiling) return LIMU_OK;
+    for (int s = 0; s < LIMU_NUM_STAGES; ++s) {
+        if (!c->ev_used[s]) continue;
+        float ms = 0.f;
+        LIMU_CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[s][0], c->ev[s][1]));
+        c->stage_ms[s] += (double)ms;
+        c->ev_used[s] = false;
+    }
+    ++c->profiled_frames;
+    return LIMU_OK;
+}
+
 }  // namespace limu
 
 using namespace limu;
 
 extern "C" {
+
+int limu_ctx_set_profiling(limu_ctx *c, int enabled) {
+    LIMU_TRY(bind(c));
+    if (enabled && !c->ev[0][0])
+        for (int s = 0; s < LIMU_NUM_STAGES; ++s) for (int k = 0; k < 2; ++k) LIMU_CUDA_TRY(cudaEventCreate(&c->ev[s][k]));
+    c->profiling = enabled != 0;
+    for (int s = 0; s < LIMU_NUM_STAGES; ++s) { c->stage_ms[s] = 0.0; c->ev_used[s] = false; }
+    c->profiled_frames = 0;
+    return LIMU_OK;
+}
+int limu_ctx_get_profile(limu_ctx *c, double ms[LIMU_NUM_STAGES], int64_t frames[1]) {
+    LIMU_REQUIRE(c && ms && frames, "limu_ctx_get_profile: null argument");
+    for (int s = 0; s < LIMU_NUM_STAGES; ++s) ms[s] = c->stage_ms[s];
+    frames[0] = c->profiled_frames;
+    return LIMU_OK;
+}
 
 const char *limu_last_error(void) { return g_err; }
 int limu_abi_version(void) { return LIMU_ABI_VERSION; }
@@ -100,6 +129,7 @@ void limu_ctx_destroy(limu_ctx *c) {
     release_ctx_scratch(c);
     limu::DevBuf *bufs[] = {&c->in0, &c->in1, &c->out0, &c->out1, &c->out2, &c->tmp0, &c->tmp1, &c->tmp2, &c->tmp3, &c->tmp4, &c->tmp5, &c->d_small};
     for (auto *b : bufs) b->release();
+    for (int s = 0; s < LIMU_NUM_STAGES; ++s) for (int k = 0; k < 2; ++k) if (c->ev[s][k]) cudaEventDestroy(c->ev[s][k]);
     cudaFree(c->d_status);
     cudaFreeHost(c->h_status);
     cudaFreeHost(c->h_pinned);

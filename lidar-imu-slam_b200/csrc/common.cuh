@@ -82,6 +82,12 @@ struct limu_ctx {
     void *h_pinned = nullptr;  // small pinned staging area for scalars / poses / counts
     size_t h_pinned_bytes = 0;
     limu::DevBuf d_small;      // small device staging area (poses, counts, partial sums)
+    // optional per-stage event timing (limu_ctx_set_profiling)
+    bool profiling = false;
+    cudaEvent_t ev[LIMU_NUM_STAGES][2] = {};
+    bool ev_used[LIMU_NUM_STAGES] = {};
+    double stage_ms[LIMU_NUM_STAGES] = {};
+    int64_t profiled_frames = 0;
 };
 
 namespace limu {
@@ -97,5 +103,14 @@ int transform_device(limu_ctx *c, const double *pose_dev, const double *in, doub
 // H2D helpers on the context's stream.
 int stage_in(limu_ctx *c, DevBuf &buf, const void *host, size_t bytes);
 int stage_small(limu_ctx *c, const double *host, int count, int off, double **dev);
+inline int prof_begin(limu_ctx *c, int stage) {
+    if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(c->ev[stage][0], c->stream)); c->ev_used[stage] = true; }
+    return LIMU_OK;
+}
+inline int prof_end(limu_ctx *c, int stage) {
+    if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(c->ev[stage][1], c->stream));
+    return LIMU_OK;
+}
+int prof_collect(limu_ctx *c);   // after a stream sync: fold the recorded stage times into the accumulators
 inline int div_up(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 }  // namespace limu

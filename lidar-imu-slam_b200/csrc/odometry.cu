@@ -104,9 +104,13 @@ static int odom_register_device(limu_odom *o, const double *frame_dev, int64_t n
     const double v = o->cfg.voxel_size;
 
     // voxelize (icp.cpp:126-136)
+    LIMU_TRY(prof_begin(c, LIMU_STAGE_DOWNSAMPLE));
     LIMU_TRY(downsample_device(c, o->sa, frame_dev, n, nullptr, v * 0.5, o->down.as<double>(), cnt + 0));
     LIMU_TRY(downsample_device(c, o->sb, o->down.as<double>(), n, cnt + 0, v * 1.5, o->src0.as<double>(), cnt + 1));
+    LIMU_TRY(prof_end(c, LIMU_STAGE_DOWNSAMPLE));
+    LIMU_TRY(prof_begin(c, LIMU_STAGE_IQR));
     LIMU_TRY(iqr_device(c, o->sb, o->src0.as<double>(), n, cnt + 1, o->src.as<double>(), cnt + 2, nullptr));
+    LIMU_TRY(prof_end(c, LIMU_STAGE_IQR));
 
     // host scalar glue (icp.cpp:66-71)
     const double sigma = odom_adaptive_threshold(o);
@@ -126,15 +130,18 @@ static int odom_register_device(limu_odom *o, const double *frame_dev, int64_t n
 
     // local_map.update(down_sampled, new_pose) (icp.cpp:81; voxel_hash_map.cpp:138-144)
     LIMU_TRY(map_maybe_grow(o->map, n));
+    LIMU_TRY(prof_begin(c, LIMU_STAGE_MAP_UPDATE));
     LIMU_TRY(transform_device(c, out13, o->down.as<double>(), o->world.as<double>(), n, cnt + 0));
     const int64_t upper_before = o->map->used_upper;
     LIMU_TRY(map_insert_device(o->map, o->world.as<double>(), n, cnt + 0));
     LIMU_TRY(map_remove_far_device(o->map, out13 + 4));
+    LIMU_TRY(prof_end(c, LIMU_STAGE_MAP_UPDATE));
 
     // the one synchronisation of the scan
     double *h = static_cast<double *>(c->h_pinned) + 32;
     LIMU_CUDA_TRY(cudaMemcpyAsync(h, c->d_small.as<double>() + 32, (8 + 13) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     LIMU_TRY(check_status(c));
+    LIMU_TRY(prof_collect(c));
     const int *hc = reinterpret_cast<const int *>(h);
     const int64_t nd = hc[0], nk = hc[2];
     const double *ho = h + 8;
@@ -170,12 +177,15 @@ static int odom_prepare_frame(limu_odom *o, const float *xyzt_dev, int64_t n, in
         se3_log(mul(inverse(o->poses[N - 2]), o->poses[N - 1]), twist);   // delta_pose(start, end) deskew.cpp:14
         double *dtw;
         LIMU_TRY(stage_small(c, twist, 6, 0, &dtw));
+        LIMU_TRY(prof_begin(c, LIMU_STAGE_PREPARE));
         LIMU_TRY(deskew_device(c, xyzt_dev, n, dtw, o->frame.as<double>()));
         *deskewed = 1;
     } else {
+        LIMU_TRY(prof_begin(c, LIMU_STAGE_PREPARE));
         LIMU_TRY(widen_device(c, xyzt_dev, n, o->frame.as<double>()));
         *deskewed = 0;
     }
+    LIMU_TRY(prof_end(c, LIMU_STAGE_PREPARE));
     return LIMU_OK;
 }
 

@@ -239,8 +239,10 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
     A.est_trace = est_trace_dev; A.ncorr_trace = ncorr_trace_dev; A.hg_trace = hg_trace_dev;
     LIMU_CUDA_TRY(cudaMemsetAsync(barrier_dev, 0, sizeof(unsigned int), c->stream));
     void *args[] = {&A};
+    LIMU_TRY(prof_begin(c, LIMU_STAGE_ICP));
     LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_icp_persistent, dim3(grid), dim3(ICP_BLOCK), args, 0, c->stream));
     LIMU_LAUNCHED();
+    LIMU_TRY(prof_end(c, LIMU_STAGE_ICP));
     return LIMU_OK;
 }
 

@@ -50,60 +50,59 @@ def pose7_of(xyyaw, height=1.8):
 
 
 def cast_scan(scene, pose_start, pose_end, beams=64, azimuth_steps=2000, elev=(-25.0, 2.0), rng_gate=(5.0, 100.0),
-              noise=0.02, seed=0, keep_all=False):
-    """Ray-cast one sweep. pose_* = (x, y, yaw) world poses at sweep start / end."""
-    rng = np.random.default_rng(seed)
-    el = np.deg2rad(np.linspace(elev[0], elev[1], beams))
-    az_i = np.arange(azimuth_steps)
-    t = np.repeat(az_i / azimuth_steps, beams)                    # time-ordered: all beams fire per azimuth step
-    az = np.repeat(az_i * (2 * np.pi / azimuth_steps), beams)
-    e = np.tile(el, azimuth_steps)
-    d_s = np.stack([np.cos(e) * np.cos(az), np.cos(e) * np.sin(az), np.sin(e)], 1)   # sensor-frame directions
-    p0, p1 = np.asarray(pose_start, float), np.asarray(pose_end, float)
+              noise=0.02, seed=0, device="cpu"):
+    """Ray-cast one sweep. pose_* = (x, y, yaw) world poses at sweep start / end. The arithmetic runs in
+    torch float64 on `device` (bench.py uses the GPU to build its workload quickly; the range noise is
+    always drawn on the host from `seed`, so a scan depends on the device only through libm rounding)."""
+    import torch
+    dev = torch.device(device)
+    f64 = dict(dtype=torch.float64, device=dev)
+    el = torch.deg2rad(torch.linspace(elev[0], elev[1], beams, **f64))
+    az_i = torch.arange(azimuth_steps, **f64)
+    t = (az_i / azimuth_steps).repeat_interleave(beams)            # time-ordered: all beams fire per azimuth step
+    az = (az_i * (2 * np.pi / azimuth_steps)).repeat_interleave(beams)
+    e = el.repeat(azimuth_steps)
+    d_s = torch.stack([torch.cos(e) * torch.cos(az), torch.cos(e) * torch.sin(az), torch.sin(e)], 1)   # sensor-frame directions
+    p0 = torch.as_tensor(np.asarray(pose_start, float), **f64)
+    p1 = torch.as_tensor(np.asarray(pose_end, float), **f64)
     xy = p0[None, :2] + t[:, None] * (p1[:2] - p0[:2])[None]
     yaw = p0[2] + t * (p1[2] - p0[2])
-    R = _rot_z(yaw)
-    d_w = np.einsum("nij,nj->ni", R, d_s)
-    o_w = np.concatenate([xy, np.full((len(t), 1), scene.sensor_height)], 1)
-    best = np.full(len(t), np.inf)
+    c, s = torch.cos(yaw), torch.sin(yaw)
+    d_w = torch.stack([c * d_s[:, 0] - s * d_s[:, 1], s * d_s[:, 0] + c * d_s[:, 1], d_s[:, 2]], 1)
+    o_w = torch.cat([xy, torch.full((len(t), 1), scene.sensor_height, **f64)], 1)
+    inf = torch.tensor(float("inf"), **f64)
     # ground z = 0
-    with np.errstate(divide="ignore", invalid="ignore"):
-        tg = -o_w[:, 2] / d_w[:, 2]
-    tg[~(tg > 0)] = np.inf
-    best = np.minimum(best, tg)
+    tg = -o_w[:, 2] / d_w[:, 2]
+    best = torch.where(tg > 0, tg, inf)
     # boxes (slab test), chunked to bound memory
-    for b0 in range(0, len(scene.box_lo), 8):
-        lo, hi = scene.box_lo[b0:b0 + 8], scene.box_hi[b0:b0 + 8]
-        with np.errstate(divide="ignore", invalid="ignore"):
-            inv = 1.0 / d_w
-            t1 = (lo[None] - o_w[:, None]) * inv[:, None]
-            t2 = (hi[None] - o_w[:, None]) * inv[:, None]
-        tn = np.nanmax(np.minimum(t1, t2), axis=2)
-        tf = np.nanmin(np.maximum(t1, t2), axis=2)
-        hit = (tf >= tn) & (tf > 0)
-        tt = np.where(hit, np.where(tn > 0, tn, np.inf), np.inf)
-        best = np.minimum(best, tt.min(axis=1))
+    inv = 1.0 / d_w
+    lo_all = torch.as_tensor(scene.box_lo, **f64)
+    hi_all = torch.as_tensor(scene.box_hi, **f64)
+    for b0 in range(0, len(lo_all), 8):
+        lo, hi = lo_all[b0:b0 + 8], hi_all[b0:b0 + 8]
+        t1 = (lo[None] - o_w[:, None]) * inv[:, None]
+        t2 = (hi[None] - o_w[:, None]) * inv[:, None]
+        tn = torch.minimum(t1, t2).nan_to_num(nan=-float("inf")).amax(dim=2)
+        tf = torch.maximum(t1, t2).nan_to_num(nan=float("inf")).amin(dim=2)
+        hit = (tf >= tn) & (tf > 0) & (tn > 0)
+        best = torch.minimum(best, torch.where(hit, tn, inf).amin(dim=1))
     # vertical cylinders
-    for c, r, h in zip(scene.cyl_c, scene.cyl_r, scene.cyl_h):
-        oc = o_w[:, :2] - c
+    for cc, r, h in zip(scene.cyl_c, scene.cyl_r, scene.cyl_h):
+        oc = o_w[:, :2] - torch.as_tensor(cc, **f64)
         a = (d_w[:, :2] ** 2).sum(1)
         b = 2 * (oc * d_w[:, :2]).sum(1)
-        cc = (oc ** 2).sum(1) - r * r
-        disc = b * b - 4 * a * cc
-        with np.errstate(divide="ignore", invalid="ignore"):
-            tc = (-b - np.sqrt(disc)) / (2 * a)
+        c0 = (oc ** 2).sum(1) - r * r
+        disc = b * b - 4 * a * c0
+        tc = (-b - torch.sqrt(disc.clamp_min(0))) / (2 * a)
         z = o_w[:, 2] + tc * d_w[:, 2]
         ok = (disc > 0) & (tc > 0) & (z >= 0) & (z <= h)
-        best = np.minimum(best, np.where(ok, tc, np.inf))
-    rngs = best + rng.normal(size=len(best)) * noise
-    valid = np.isfinite(best) & (rngs >= rng_gate[0]) & (rngs <= rng_gate[1])   # range gate lidar/frame.hpp:65-66
-    if keep_all:
-        rngs = np.where(valid, rngs, rng_gate[1] * 0.5)
-        valid[:] = True
-    rngs = np.where(valid, rngs, 0.0)
-    pts = d_s * rngs[:, None]
-    out = np.concatenate([pts, t[:, None]], 1)[valid].astype(np.float32)
-    return np.ascontiguousarray(out)
+        best = torch.minimum(best, torch.where(ok, tc, inf))
+    nz = torch.as_tensor(np.random.default_rng(seed).normal(size=len(t)) * noise, **f64)
+    rngs = best + nz
+    valid = torch.isfinite(best) & (rngs >= rng_gate[0]) & (rngs <= rng_gate[1])   # range gate lidar/frame.hpp:65-66
+    rngs = torch.where(valid, rngs, torch.zeros_like(rngs))
+    out = torch.cat([d_s * rngs[:, None], t[:, None]], 1)[valid].to(torch.float32)
+    return np.ascontiguousarray(out.cpu().numpy())
 
 
 def pad_scan(scan, n, seed=0):
