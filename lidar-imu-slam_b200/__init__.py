@@ -18,7 +18,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblimu_cuda.so")
+LIB_PATH = os.environ.get("LIMU_LIB", os.path.join(HERE, "liblimu_cuda.so"))   # LIMU_LIB: instrumented builds (tools/)
 HEADER = os.path.join(os.path.dirname(HERE), "include", "limu_cuda.h")
 
 _dp, _fp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32)

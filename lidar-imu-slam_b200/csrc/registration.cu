@@ -61,20 +61,46 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Accumulate one gated correspondence (registration.cpp:46-58,75-76).
-__device__ __forceinline__ void accumulate(double *a, const V3 &s, const V3 &t, double d2, double th) {
+// The 16 sums one gated correspondence adds to (registration.cpp:46-58,75-76); zeros when gated out.
+__device__ __forceinline__ void contribution(double *c, const V3 &s, const V3 &t, double d2, double th, bool on) {
     const double rx = s.x - t.x, ry = s.y - t.y, rz = s.z - t.z;       // residual = source - target (:48)
     const double den = th + d2;
-    const double w = (th * th) / (den * den);                           // :57-58
+    const double w = on ? (th * th) / (den * den) : 0.0;                // :57-58
     const double wx = w * s.x, wy = w * s.y, wz = w * s.z;
-    a[0] += w;
-    a[1] += wx; a[2] += wy; a[3] += wz;
-    a[4] = fma(wx, s.x, a[4]); a[5] = fma(wx, s.y, a[5]); a[6] = fma(wx, s.z, a[6]);
-    a[7] = fma(wy, s.y, a[7]); a[8] = fma(wy, s.z, a[8]); a[9] = fma(wz, s.z, a[9]);
-    a[10] = fma(w, rx, a[10]); a[11] = fma(w, ry, a[11]); a[12] = fma(w, rz, a[12]);
-    a[13] = fma(w, s.y * rz - s.z * ry, a[13]);
-    a[14] = fma(w, s.z * rx - s.x * rz, a[14]);
-    a[15] = fma(w, s.x * ry - s.y * rx, a[15]);
+    c[0] = w;
+    c[1] = wx; c[2] = wy; c[3] = wz;
+    c[4] = wx * s.x; c[5] = wx * s.y; c[6] = wx * s.z;
+    c[7] = wy * s.y; c[8] = wy * s.z; c[9] = wz * s.z;
+    c[10] = w * rx; c[11] = w * ry; c[12] = w * rz;
+    c[13] = w * (s.y * rz - s.z * ry);
+    c[14] = w * (s.z * rx - s.x * rz);
+    c[15] = w * (s.x * ry - s.y * rx);
+}
+
+// Warp reduce-scatter of 16 values per lane: after five exchange steps lane L holds the warp total of
+// value L>>1 (both lanes of a pair hold it). 16 double shuffles per 32 queries instead of 16 x 5, and each
+// lane carries ONE running FP64 accumulator instead of 16 (registers are what bounds occupancy here).
+// The exchange pattern is fixed, so sums are run-to-run deterministic.
+__device__ __forceinline__ double warp_reduce_scatter16(const double *c) {
+    const int lane = threadIdx.x & 31;
+    double d[8], e[4], f[2];
+    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = (u16 ? c[i + 8] : c[i]) + __shfl_xor_sync(0xFFFFFFFFu, u16 ? c[i] : c[i + 8], 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) e[i] = (u8 ? d[i + 4] : d[i]) + __shfl_xor_sync(0xFFFFFFFFu, u8 ? d[i] : d[i + 4], 8);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) f[i] = (u4 ? e[i + 2] : e[i]) + __shfl_xor_sync(0xFFFFFFFFu, u4 ? e[i] : e[i + 2], 4);
+    const double g = (u2 ? f[1] : f[0]) + __shfl_xor_sync(0xFFFFFFFFu, u2 ? f[0] : f[1], 2);
+    return g + __shfl_xor_sync(0xFFFFFFFFu, g, 1);
+}
+
+// Legacy-style accumulation used by the stand-alone align kernel (16 accumulators per thread).
+__device__ __forceinline__ void accumulate(double *a, const V3 &s, const V3 &t, double d2, double th) {
+    double c[16];
+    contribution(c, s, t, d2, th, true);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] += c[k];
 }
 
 // Block-level reduction of NS values per thread into row[NS] (fixed tree -> deterministic).
@@ -94,69 +120,113 @@ __device__ __forceinline__ void block_reduce_row(double *a, double *smem /* [ICP
     }
 }
 
-static __global__ void __launch_bounds__(ICP_BLOCK) k_icp_persistent(const IcpArgs A) {
-    __shared__ double red[(ICP_BLOCK / 32) * NS];
+#ifdef LIMU_ICP_PHASE_TIMING
+#define PT_MARK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && A.hg_trace) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); A.hg_trace[42 * (size_t)j + (k)] = (double)_t; } } while (0)
+#else
+#define PT_MARK(k) do {} while (0)
+#endif
+
+static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_persistent(const IcpArgs A) {
+    __shared__ double red[(ICP_BLOCK / 32) * 32];
     __shared__ double S[NS];
-    __shared__ double E[7];
+    __shared__ double E[7], Tinit[7], Ticp[7];
     __shared__ int done;
     const int64_t n = A.n_dev ? (int64_t)*A.n_dev : A.n_max;
-    const int64_t tid = (int64_t)blockIdx.x * ICP_BLOCK + threadIdx.x, nthreads = (int64_t)gridDim.x * ICP_BLOCK;
-    const Pose T_init = pose_load(A.init_pose);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (A.map_counters[0] == 0ull || A.max_iter <= 0) {   // ICP :99-100 (and a zero-iteration loop returns T_icp * init = init)
-        if (tid == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const Pose T_init = pose_load(A.init_pose);
             pose_store(A.map_counters[0] == 0ull ? T_init : mul(pose_identity(), T_init), A.out);
             for (int k = 7; k < 13; ++k) A.out[k] = 0.0;
             A.out[12] = (double)n;
         }
         return;
     }
-    Pose T_icp = pose_identity();   // only thread 0 of each CTA keeps it current
+    if (threadIdx.x < 7) { Tinit[threadIdx.x] = A.init_pose[threadIdx.x]; Ticp[threadIdx.x] = threadIdx.x == 3 ? 1.0 : 0.0; }
+    __syncthreads();
+    const int64_t wbase = ((int64_t)blockIdx.x * (ICP_BLOCK / 32) + warp) * 32, wstride = (int64_t)gridDim.x * ICP_BLOCK;
     int j = 0;
     int converged = 0;
     for (;; ) {
-        double acc[NS];
-#pragma unroll
-        for (int k = 0; k < NS; ++k) acc[k] = 0.0;
-        Pose Ej;
-        if (j > 0) Ej = Pose{E[0], E[1], E[2], E[3], E[4], E[5], E[6]};
-        for (int64_t q = tid; q < n; q += nthreads) {
-            V3 s;
-            if (j == 0) {   // source = init_guess * points (:102-103)
-                s = apply(T_init, V3{A.points[3 * q], A.points[3 * q + 1], A.points[3 * q + 2]});
-            } else {        // source <- estimate * source (:119), applied lazily at the next visit
-                s = apply(Ej, V3{A.work[3 * q], A.work[3 * q + 1], A.work[3 * q + 2]});
+        PT_MARK(0);
+        double acc = 0.0;            // lane L: running total of sum index L>>1
+        int ncorr = 0, ncand = 0, nmiss = 0;
+        const Pose P = pose_load(j == 0 ? Tinit : E);
+        const double *in = j == 0 ? A.points : A.work;
+        for (int64_t base = wbase; base < n; base += wstride) {
+            const int64_t q = base + lane;
+            const bool on = q < n;
+            V3 s{0.0, 0.0, 0.0};
+            Nearest nn;
+            nn.x = nn.y = nn.z = 0.0; nn.ncand = 0; nn.own = 1;
+            if (on) {
+                // j == 0: source = init_guess * points (:102-103); later: source <- estimate * source (:119),
+                // applied lazily at the next visit
+                s = apply(P, V3{in[3 * q], in[3 * q + 1], in[3 * q + 2]});
+                A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z;
+                nn = map_closest(A.map, s);
             }
-            A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z;
-            const Nearest nn = map_closest(A.map, s);
             const double d2 = sqnorm3(nn.x - s.x, nn.y - s.y, nn.z - s.z);   // (found - point).squaredNorm() voxel_hash_map.cpp:120
-            if (d2 < A.tau_sq) {
-                accumulate(acc, s, V3{nn.x, nn.y, nn.z}, d2, A.th);
-                acc[16] += 1.0;
-            }
-            acc[17] += (double)nn.ncand;
-            acc[18] += nn.own ? 0.0 : 1.0;
+            const bool gate = on && d2 < A.tau_sq;
+            double c[16];
+            contribution(c, s, V3{nn.x, nn.y, nn.z}, d2, A.th, gate);
+            acc += warp_reduce_scatter16(c);
+            ncorr += gate ? 1 : 0;
+            ncand += nn.ncand;
+            nmiss += (on && !nn.own) ? 1 : 0;
         }
+        PT_MARK(1);
+        // CTA row: 16 sums (even lanes hold them) + 3 counters
+        ncorr = __reduce_add_sync(0xFFFFFFFFu, ncorr);
+        ncand = __reduce_add_sync(0xFFFFFFFFu, ncand);
+        nmiss = __reduce_add_sync(0xFFFFFFFFu, nmiss);
+        red[warp * 32 + lane] = (lane & 1) ? (lane == 1 ? (double)ncorr : lane == 3 ? (double)ncand : lane == 5 ? (double)nmiss : 0.0) : acc;
+        __syncthreads();
         double *rows = A.partials + (size_t)(j & 1) * gridDim.x * NS;
-        block_reduce_row(acc, red, rows + (size_t)blockIdx.x * NS);
+        if (threadIdx.x < NS) {
+            const int src_lane = threadIdx.x < 16 ? 2 * threadIdx.x : 2 * (threadIdx.x - 16) + 1;
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < ICP_BLOCK / 32; ++w) v += red[w * 32 + src_lane];
+            rows[(size_t)blockIdx.x * NS + threadIdx.x] = v;
+        }
+        PT_MARK(2);
         grid_barrier(A.barrier, (unsigned int)(j + 1) * gridDim.x);
-        // fold the per-CTA rows: warp w takes columns w, w+8, w+16; lanes stride over CTAs
+        PT_MARK(3);
+        // fold the per-CTA rows in a fixed order: lane = column, warp g sums rows g, g+8, ... (four independent
+        // accumulators keep the L2 loads in flight), then one thread per column adds the 8 warp partials.
         {
-            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-            for (int col = warp; col < NS; col += ICP_BLOCK / 32) {
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+            if (lane < NS) {
+                const int G = ICP_BLOCK / 32;
+                int b = warp;
+                for (; b + 3 * G < (int)gridDim.x; b += 4 * G) {
+                    v0 += __ldcg(rows + (size_t)b * NS + lane);
+                    v1 += __ldcg(rows + (size_t)(b + G) * NS + lane);
+                    v2 += __ldcg(rows + (size_t)(b + 2 * G) * NS + lane);
+                    v3 += __ldcg(rows + (size_t)(b + 3 * G) * NS + lane);
+                }
+                for (; b < (int)gridDim.x; b += G) v0 += __ldcg(rows + (size_t)b * NS + lane);
+            }
+            red[warp * 32 + lane] = (v0 + v1) + (v2 + v3);
+            __syncthreads();
+            if (threadIdx.x < NS) {
                 double v = 0.0;
-                for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(rows + (size_t)b * NS + col);
-                v = warp_sum(v);
-                if (lane == 0) S[col] = v;
+#pragma unroll
+                for (int w = 0; w < ICP_BLOCK / 32; ++w) v += red[w * 32 + threadIdx.x];
+                S[threadIdx.x] = v;
             }
         }
         __syncthreads();
+        PT_MARK(4);
         if (threadIdx.x == 0) {
             double H[36], g[6], x[6], lg[6];
             expand_normal_equations(S, H, g);
+#pragma unroll
             for (int k = 0; k < 6; ++k) g[k] = -g[k];
             ldlt6_solve(H, g, x);                       // JTJ.ldlt().solve(-JTr) :90
             const Pose est = se3_exp(x);                // vector6d_to_mat4d :91
-            T_icp = mul(est, T_icp);                    // :122
+            pose_store(mul(est, pose_load(Ticp)), Ticp);   // T_icp = estimate * T_icp :122
             se3_log(est, lg);
             const int stop = norm6(lg) < A.eps;         // :124
             pose_store(est, E);
@@ -164,20 +234,23 @@ static __global__ void __launch_bounds__(ICP_BLOCK) k_icp_persistent(const IcpAr
             if (blockIdx.x == 0) {
                 if (A.est_trace) pose_store(est, A.est_trace + 7 * (size_t)j);
                 if (A.ncorr_trace) A.ncorr_trace[j] = (long long)S[16];
+#ifndef LIMU_ICP_PHASE_TIMING
                 if (A.hg_trace) {
                     double *o = A.hg_trace + 42 * (size_t)j;
                     for (int k = 0; k < 36; ++k) o[k] = H[k];
                     for (int k = 0; k < 6; ++k) o[36 + k] = -g[k];
                 }
+#endif
             }
         }
         __syncthreads();
+        PT_MARK(5);
         ++j;
         if (done) { converged = 1; break; }
         if (j >= A.max_iter) break;
     }
-    if (tid == 0) {
-        pose_store(mul(T_icp, T_init), A.out);          // T_icp * init_guess :129
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        pose_store(mul(pose_load(Ticp), pose_load(Tinit)), A.out);          // T_icp * init_guess :129
         A.out[7] = (double)j; A.out[8] = (double)converged; A.out[9] = S[16]; A.out[10] = S[17]; A.out[11] = S[18]; A.out[12] = (double)n;
     }
 }

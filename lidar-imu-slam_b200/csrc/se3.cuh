@@ -86,6 +86,7 @@ LIMU_HD void hat(const double *w, double *O) {  // so3.hpp:783-792
     O[6] = -w[1]; O[7] = w[0]; O[8] = 0;
 }
 LIMU_HD void mat3mul(const double *A, const double *B, double *C) {
+#pragma unroll
     for (int j = 0; j < 3; ++j) {
         C[j] = (A[0] * B[j] + A[1] * B[3 + j]) + A[2] * B[6 + j];
         C[3 + j] = (A[3] * B[j] + A[4] * B[3 + j]) + A[5] * B[6 + j];
@@ -121,9 +122,11 @@ LIMU_HD Pose se3_exp(const double *a) {
     hat(om, Om);
     mat3mul(Om, Om, Om2);
     if (tsq < LIMU_SOPHUS_EPS * LIMU_SOPHUS_EPS) {
+#pragma unroll
         for (int i = 0; i < 9; ++i) V[i] = ((i % 4 == 0) ? 1.0 : 0.0) + 0.5 * Om[i];
     } else {
         const double c1 = (1.0 - cos(theta)) / tsq, c2 = (theta - sin(theta)) / (tsq * theta);
+#pragma unroll
         for (int i = 0; i < 9; ++i) V[i] = (((i % 4 == 0) ? 1.0 : 0.0) + c1 * Om[i]) + c2 * Om2[i];
     }
     mat3vec(V, ups, t);
@@ -151,10 +154,12 @@ LIMU_HD void se3_log(const Pose &T, double *x) {
     hat(om, Om);
     mat3mul(Om, Om, Om2);
     if (tsq < LIMU_SOPHUS_EPS * LIMU_SOPHUS_EPS) {
+#pragma unroll
         for (int i = 0; i < 9; ++i) Vi[i] = (((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * Om[i]) + (1. / 12.) * Om2[i];
     } else {
         const double half = 0.5 * theta;
         const double c = (1.0 - 0.5 * theta * cos(half) / sin(half)) / (theta * theta);
+#pragma unroll
         for (int i = 0; i < 9; ++i) Vi[i] = (((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * Om[i]) + c * Om2[i];
     }
     const double t[3] = {T.tx, T.ty, T.tz};
@@ -171,48 +176,91 @@ LIMU_HD double norm6(const double *x) {
 
 // Eigen 3.4.0 LDLT<Matrix6d>: diagonal-pivoted in-place factorisation of the lower triangle
 // (Cholesky/LDLT.h:300-395) and the solve with pseudo-inverse of D (:569-607). A is row-major 6x6.
+// Every loop has compile-time bounds and the runtime pivot index only selects among statically indexed
+// swaps, so on the device the whole factorisation lives in registers (the Gauss-Newton solve runs on ONE
+// thread while the grid waits: its latency is on the critical path of every iteration).
+LIMU_HD void swapd(double &a, double &b) { const double t = a; a = b; b = t; }
+// Conditional swap written as two selects on statically indexed operands (keeps the matrix in registers:
+// an `if (pivot == i) swap(...)` chain gets re-rolled by the compiler into a dynamically indexed local array).
+LIMU_HD void cswapd(bool sw, double &a, double &b) { const double ta = a, tb = b; a = sw ? tb : ta; b = sw ? ta : tb; }
 LIMU_HD void ldlt6_solve(const double *Ain, const double *b, double *x) {
-    double A[36];
+    double a[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) a[i][j] = Ain[6 * i + j];
     int tr[6];
-    for (int i = 0; i < 36; ++i) A[i] = Ain[i];
-    double temp[6];
-#define LA(r, c) A[6 * (r) + (c)]
+    bool zero = false;   // "entire diagonal is zero" exit of LDLT.h:364-375
+#pragma unroll
     for (int k = 0; k < 6; ++k) {
         int big = k;
-        double bigv = fabs(LA(k, k));
-        for (int i = k + 1; i < 6; ++i) { const double v = fabs(LA(i, i)); if (v > bigv) { bigv = v; big = i; } }
+        double bigv = fabs(a[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) { const double v = fabs(a[i][i]); if (v > bigv) { bigv = v; big = i; } }
+        if (zero) big = k;
         tr[k] = big;
-        if (k != big) {
-            for (int c = 0; c < k; ++c) { const double t = LA(k, c); LA(k, c) = LA(big, c); LA(big, c) = t; }
-            for (int r = big + 1; r < 6; ++r) { const double t = LA(r, k); LA(r, k) = LA(r, big); LA(r, big) = t; }
-            { const double t = LA(k, k); LA(k, k) = LA(big, big); LA(big, big) = t; }
-            for (int i = k + 1; i < big; ++i) { const double t = LA(i, k); LA(i, k) = LA(big, i); LA(big, i) = t; }
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) {
+            const bool sw = (big == i);
+#pragma unroll
+            for (int c = 0; c < k; ++c) cswapd(sw, a[k][c], a[i][c]);
+#pragma unroll
+            for (int r = i + 1; r < 6; ++r) cswapd(sw, a[r][k], a[r][i]);
+            cswapd(sw, a[k][k], a[i][i]);
+#pragma unroll
+            for (int m = k + 1; m < i; ++m) cswapd(sw, a[m][k], a[i][m]);
         }
-        if (k > 0) {
-            for (int c = 0; c < k; ++c) temp[c] = LA(c, c) * LA(k, c);
-            double acc = 0.0;
-            for (int c = 0; c < k; ++c) acc += LA(k, c) * temp[c];
-            LA(k, k) -= acc;
-            for (int r = k + 1; r < 6; ++r) {
-                double a2 = 0.0;
-                for (int c = 0; c < k; ++c) a2 += LA(r, c) * temp[c];
-                LA(r, k) -= a2;
+        if (!zero) {
+            if (k > 0) {
+                double temp[6];
+#pragma unroll
+                for (int c = 0; c < k; ++c) temp[c] = a[c][c] * a[k][c];
+                double acc = 0.0;
+#pragma unroll
+                for (int c = 0; c < k; ++c) acc += a[k][c] * temp[c];
+                a[k][k] -= acc;
+#pragma unroll
+                for (int r = k + 1; r < 6; ++r) {
+                    double a2 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < k; ++c) a2 += a[r][c] * temp[c];
+                    a[r][k] -= a2;
+                }
+            }
+            const double akk = a[k][k];
+            const bool valid = fabs(akk) > 0.0;
+            if (k == 0 && !valid) zero = true;
+            if (valid) {
+#pragma unroll
+                for (int r = k + 1; r < 6; ++r) a[r][k] /= akk;
             }
         }
-        const double akk = LA(k, k);
-        const bool valid = fabs(akk) > 0.0;
-        if (k == 0 && !valid) { for (int j = 0; j < 6; ++j) tr[j] = j; break; }
-        if (valid) for (int r = k + 1; r < 6; ++r) LA(r, k) /= akk;
     }
     double d[6];
+#pragma unroll
     for (int i = 0; i < 6; ++i) d[i] = b[i];
-    for (int k = 0; k < 6; ++k) if (tr[k] != k) { const double t = d[k]; d[k] = d[tr[k]]; d[tr[k]] = t; }
-    for (int i = 0; i < 6; ++i) for (int c = 0; c < i; ++c) d[i] -= LA(i, c) * d[c];
-    for (int i = 0; i < 6; ++i) { if (fabs(LA(i, i)) > 2.2250738585072014e-308) d[i] /= LA(i, i); else d[i] = 0.0; }
-    for (int i = 5; i >= 0; --i) for (int c = i + 1; c < 6; ++c) d[i] -= LA(c, i) * d[c];
-    for (int k = 5; k >= 0; --k) if (tr[k] != k) { const double t = d[k]; d[k] = d[tr[k]]; d[tr[k]] = t; }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) cswapd(tr[k] == i, d[k], d[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int c = 0; c < i; ++c) d[i] -= a[i][c] * d[c];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { if (fabs(a[i][i]) > 2.2250738585072014e-308) d[i] /= a[i][i]; else d[i] = 0.0; }
+#pragma unroll
+    for (int i = 5; i >= 0; --i)
+#pragma unroll
+        for (int c = i + 1; c < 6; ++c) d[i] -= a[c][i] * d[c];
+#pragma unroll
+    for (int k = 5; k >= 0; --k) {
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) cswapd(tr[k] == i, d[k], d[i]);
+    }
+#pragma unroll
     for (int i = 0; i < 6; ++i) x[i] = d[i];
-#undef LA
 }
 
 // The 17 sums that determine H = sum w J^T J and g = sum w J^T r for J = [I | -hat(s)]
@@ -227,13 +275,17 @@ enum { LIMU_NSUMS = 16 };
 LIMU_HD void expand_normal_equations(const double *S, double *H, double *g) {
     const double w = S[0], sx = S[1], sy = S[2], sz = S[3];
     const double xx = S[4], xy = S[5], xz = S[6], yy = S[7], yz = S[8], zz = S[9];
+#pragma unroll
     for (int i = 0; i < 36; ++i) H[i] = 0.0;
     H[0] = H[7] = H[14] = w;
     // A = [[0, sz, -sy], [-sz, 0, sx], [sy, -sx, 0]]
     H[0 * 6 + 4] = sz;  H[0 * 6 + 5] = -sy;
     H[1 * 6 + 3] = -sz; H[1 * 6 + 5] = sx;
     H[2 * 6 + 3] = sy;  H[2 * 6 + 4] = -sx;
-    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) H[(3 + c) * 6 + r] = H[r * 6 + 3 + c];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) H[(3 + c) * 6 + r] = H[r * 6 + 3 + c];
     H[3 * 6 + 3] = yy + zz; H[3 * 6 + 4] = -xy;     H[3 * 6 + 5] = -xz;
     H[4 * 6 + 3] = -xy;     H[4 * 6 + 4] = xx + zz; H[4 * 6 + 5] = -yz;
     H[5 * 6 + 3] = -xz;     H[5 * 6 + 4] = -yz;     H[5 * 6 + 5] = xx + yy;

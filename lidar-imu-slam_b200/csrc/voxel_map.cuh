@@ -79,6 +79,12 @@ __device__ __forceinline__ int map_find(const MapView &m, unsigned long long key
     }
 }
 
+// 27-neighbourhood offsets by |delta|^2 class.
+__device__ constexpr signed char NB_CORNERS[8][3] = {{-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}, {1, -1, -1}, {1, -1, 1}, {1, 1, -1}, {1, 1, 1}};
+__device__ constexpr signed char NB_EDGES[12][3] = {{-1, -1, 0}, {-1, 1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 0, -1}, {-1, 0, 1},
+                                                    {1, 0, -1},  {1, 0, 1},  {0, -1, -1}, {0, -1, 1}, {0, 1, -1}, {0, 1, 1}};
+__device__ constexpr signed char NB_FACES[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+
 struct Nearest {
     double x, y, z;   // matched map point, or (0,0,0) when nothing was found
     int slot;         // table slot of the matched voxel, -1 if none
@@ -88,14 +94,24 @@ struct Nearest {
 };
 
 // VoxelBlock::get_closest_point, voxel_block.cpp:87-105: linear scan, strict '<', first minimum wins.
+// Candidates are fetched four at a time (12 independent 8-byte loads in flight) and then compared in order.
 __device__ __forceinline__ void block_closest(const MapView &m, int slot, int count, const V3 &p, Nearest &r) {
     const double *b = m.pts + (size_t)slot * (size_t)m.cap * 3;
     double best = 1.7976931348623157e308;
     r.rank = -1;
-    for (int i = 0; i < count; ++i) {
-        const double bx = __ldg(b + 3 * i), by = __ldg(b + 3 * i + 1), bz = __ldg(b + 3 * i + 2);
-        const double d = sqnorm3(p.x - bx, p.y - by, p.z - bz);
-        if (d < best) { best = d; r.rank = i; r.x = bx; r.y = by; r.z = bz; }
+    for (int base = 0; base < count; base += 4) {
+        double c[12];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool on = base + k < count;
+            const double *q = b + 3 * (base + (on ? k : 0));
+            c[3 * k] = __ldg(q); c[3 * k + 1] = __ldg(q + 1); c[3 * k + 2] = __ldg(q + 2);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double d = sqnorm3(p.x - c[3 * k], p.y - c[3 * k + 1], p.z - c[3 * k + 2]);
+            if (base + k < count && d < best) { best = d; r.rank = base + k; r.x = c[3 * k]; r.y = c[3 * k + 1]; r.z = c[3 * k + 2]; }
+        }
     }
     r.ncand = count;
 }
@@ -118,25 +134,39 @@ __device__ __forceinline__ Nearest map_closest(const MapView &m, const V3 &p) {
             return r;
         }
     }
-    int best_slot = -1, best_d = -1, best_count = 0;
+    // Fallback (b): the winner is the occupied neighbour with the largest (|delta|^2, birth). Visit the
+    // three distance classes in decreasing |delta|^2 -- 8 corners (3), 12 edges (2), 6 faces (1) -- and stop
+    // at the first class with an occupied cell. Within a class all home-slot loads are issued before any
+    // is consumed (one L2 round trip per class instead of one per cell).
+    int best_slot = -1;
     unsigned long long best_birth = 0;
-#pragma unroll 1
-    for (int c = 0; c < 27; ++c) {
-        if (c == 13) continue;  // own voxel: known absent
-        const int dx = c / 9 - 1, dy = (c / 3) % 3 - 1, dz = c % 3 - 1;
-        const int x = kx + dx, y = ky + dy, z = kz + dz;
-        if (!key_in_range(x, y, z)) continue;
-        int cnt;
-        const int s = map_find(m, pack_key(x, y, z), &cnt);
-        if (s < 0) continue;
-        const int d = dx * dx + dy * dy + dz * dz;
-        if (d < best_d) continue;
-        const unsigned long long b = __ldg(m.birth + s);
-        if (d > best_d || b > best_birth) { best_d = d; best_birth = b; best_slot = s; best_count = cnt; }
+#define LIMU_PROBE_CLASS(N, TABLE)                                                                          \
+    if (best_slot < 0) {                                                                                    \
+        unsigned long long got[N];                                                                          \
+        _Pragma("unroll") for (int c = 0; c < N; ++c) {                                                     \
+            const int x = kx + TABLE[c][0], y = ky + TABLE[c][1], z = kz + TABLE[c][2];                     \
+            got[c] = key_in_range(x, y, z) ? __ldg(&m.slots[slot_of(pack_key(x, y, z), m.shift)].key) : KEY_EMPTY; \
+        }                                                                                                   \
+        _Pragma("unroll") for (int c = 0; c < N; ++c) {                                                     \
+            unsigned long long k = got[c];                                                                  \
+            if (k != KEY_EMPTY) {                                                                           \
+                const unsigned long long want = pack_key(kx + TABLE[c][0], ky + TABLE[c][1], kz + TABLE[c][2]); \
+                unsigned int s = slot_of(want, m.shift);                                                    \
+                while (k != want && k != KEY_EMPTY) { s = (s + 1) & m.mask; k = __ldg(&m.slots[s].key); }   \
+                if (k == want) {                                                                            \
+                    const unsigned long long bth = __ldg(m.birth + s);                                      \
+                    if (best_slot < 0 || bth > best_birth) { best_birth = bth; best_slot = (int)s; }        \
+                }                                                                                           \
+            }                                                                                               \
+        }                                                                                                   \
     }
+    LIMU_PROBE_CLASS(8, NB_CORNERS)
+    LIMU_PROBE_CLASS(12, NB_EDGES)
+    LIMU_PROBE_CLASS(6, NB_FACES)
+#undef LIMU_PROBE_CLASS
     if (best_slot >= 0) {
         r.slot = best_slot;
-        block_closest(m, best_slot, best_count, p, r);
+        block_closest(m, best_slot, __ldg(&m.slots[best_slot].count), p, r);
         if (r.rank < 0) { r.x = r.y = r.z = 0.0; }
     }
     return r;
