@@ -77,6 +77,10 @@ int limu_transform_points(limu_ctx *c, const double pose[7], double *xyz, int64_
 /* lidar::MotionCompensator::deskew_scan, helpers/deskew.cpp:10-28:
  * out[i] = exp((t_i - 0.5) * log(T0^-1 T1)) * (x_i,y_i,z_i). */
 int limu_deskew(limu_ctx *c, const float *xyzt, int64_t n, const double T0[7], const double T1[7], double *out_xyz);
+/* The same on the reference's own input layout: point records `stride_bytes` apart with float x,y,z at offset 0
+ * (pcl::PointXYZINormal = 48 B, types.hpp:36) and FP64 timestamps (std::vector<double>). */
+int limu_deskew_cloud(limu_ctx *c, const void *points, int32_t stride_bytes, const double *timestamps, int64_t n, const double T0[7],
+                      const double T1[7], double *out_xyz);
 /* voxel_downsample (file-local), sensors/lidar/icp.cpp:9-30: first point per voxel of edge s wins;
  * output in first-occurrence order. out_xyz must hold n points; out_idx (optional) the source indices. */
 int limu_voxel_downsample(limu_ctx *c, const double *xyz, int64_t n, double s, double *out_xyz, int64_t *out_idx, int64_t *n_out);
@@ -157,6 +161,9 @@ void limu_odom_destroy(limu_odom *o);
  * down_xyz / keypoints_xyz must hold n points each. */
 int limu_odom_register_frame(limu_odom *o, const float *xyzt, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down,
                              double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats);
+/* register_frame(cloud, timestamps) on the reference's own layout (PCL point records + FP64 timestamps). */
+int limu_odom_register_cloud(limu_odom *o, const void *points, int32_t stride_bytes, const double *timestamps, int64_t n, double pose_out[7],
+                             double *down_xyz, int64_t *n_down, double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats);
 int limu_odom_register_frame_dev(limu_odom *o, const float *xyzt_dev, int64_t n, double pose_out[7], limu_frame_stats *stats);
 /* register_frame(Vec3dVector) icp.cpp:58-86 (no deskew). */
 int limu_odom_register_points(limu_odom *o, const double *xyz, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down,

@@ -83,6 +83,8 @@ def lib():
             "limu_voxel_keys": [_vp, _dp, C.c_int64, C.c_double, _ip],
             "limu_transform_points": [_vp, _dp, _dp, C.c_int64],
             "limu_deskew": [_vp, _fp, C.c_int64, _dp, _dp, _dp],
+            "limu_deskew_cloud": [_vp, _vp, C.c_int32, _dp, C.c_int64, _dp, _dp, _dp],
+            "limu_odom_register_cloud": [_vp, _vp, C.c_int32, _dp, C.c_int64, _dp, _dp, _lp, _dp, _lp, C.POINTER(FrameStats)],
             "limu_voxel_downsample": [_vp, _dp, C.c_int64, C.c_double, _dp, _lp, _lp],
             "limu_iqr_filter": [_vp, _dp, C.c_int64, _dp, _lp, _dp],
             "limu_voxelize": [_vp, _dp, C.c_int64, C.c_double, _dp, _lp, _dp, _lp],
@@ -240,6 +242,14 @@ class Context:
         x = np.ascontiguousarray(xyzt_f32, np.float32).reshape(-1, 4)
         out = np.empty((len(x), 3))
         _chk(lib().limu_deskew(self.h, x.ctypes.data_as(_fp), len(x), _d(_pose(T0)), _d(_pose(T1)), _d(out)))
+        return out
+
+    def deskew_cloud(self, records, stride_bytes, timestamps, T0, T1):
+        """MotionCompensator::deskew_scan on strided point records (float x,y,z first) + float64 timestamps."""
+        rec = np.ascontiguousarray(records)
+        ts = np.ascontiguousarray(timestamps, np.float64)
+        out = np.empty((len(ts), 3))
+        _chk(lib().limu_deskew_cloud(self.h, rec.ctypes.data_as(_vp), int(stride_bytes), _d(ts), len(ts), _d(_pose(T0)), _d(_pose(T1)), _d(out)))
         return out
 
     def voxel_downsample(self, xyz, s, with_index=False):
@@ -451,6 +461,17 @@ class KissICP:
         if copy:
             return down[: nd.value].copy(), src[: ns.value].copy(), pose
         return down[: nd.value], src[: ns.value], pose
+
+    def register_cloud(self, records, stride_bytes, timestamps):
+        """register_frame(cloud, timestamps) on strided point records + float64 timestamps (the reference's layout)."""
+        rec = np.ascontiguousarray(records)
+        ts = np.ascontiguousarray(timestamps, np.float64)
+        n = len(ts)
+        pose = np.empty(7)
+        down, src = self._out_buffers(n)
+        nd, ns = C.c_int64(0), C.c_int64(0)
+        _chk(lib().limu_odom_register_cloud(self.h, rec.ctypes.data_as(_vp), int(stride_bytes), _d(ts), n, _d(pose), _d(down), C.byref(nd), _d(src), C.byref(ns), C.byref(self.stats)))
+        return down[: nd.value].copy(), src[: ns.value].copy(), pose
 
     def register_frame_dev(self, xyzt_dev_ptr, n):
         pose = np.empty(7)

@@ -56,7 +56,7 @@ struct limu_odom {
     int num_samples = 0;
     limu::Pose model_deviation = limu::pose_identity();
     // device buffers
-    limu::DevBuf raw, frame, down, src0, src, work, world, partials;
+    limu::DevBuf raw, ts, frame, down, src0, src, work, world, partials;
     limu::StageScratch sa, sb;
     int64_t nk_hint = 4096;
 };
@@ -168,7 +168,9 @@ static int odom_register_device(limu_odom *o, const double *frame_dev, int64_t n
 }
 
 // deskew gate + widening (icp.cpp:36-47) on a raw scan already in device memory.
-static int odom_prepare_frame(limu_odom *o, const float *xyzt_dev, int64_t n, int *deskewed) {
+// stride == 0: packed float4 {x,y,z,t}; otherwise records `stride` bytes apart + FP64 timestamps.
+static int odom_prepare_frame(limu_odom *o, const void *rec_dev, int stride, const double *ts_dev, int64_t n, int *deskewed) {
+    const float *xyzt_dev = static_cast<const float *>(rec_dev);
     limu_ctx *c = o->ctx;
     LIMU_TRY(o->frame.reserve((size_t)std::max<int64_t>(n, 1) * 24, c->stream));
     const size_t N = o->poses.size();
@@ -178,11 +180,13 @@ static int odom_prepare_frame(limu_odom *o, const float *xyzt_dev, int64_t n, in
         double *dtw;
         LIMU_TRY(stage_small(c, twist, 6, 0, &dtw));
         LIMU_TRY(prof_begin(c, LIMU_STAGE_PREPARE));
-        LIMU_TRY(deskew_device(c, xyzt_dev, n, dtw, o->frame.as<double>()));
+        if (stride == 0) LIMU_TRY(deskew_device(c, xyzt_dev, n, dtw, o->frame.as<double>()));
+        else LIMU_TRY(deskew_records_device(c, rec_dev, stride, ts_dev, n, dtw, o->frame.as<double>()));
         *deskewed = 1;
     } else {
         LIMU_TRY(prof_begin(c, LIMU_STAGE_PREPARE));
-        LIMU_TRY(widen_device(c, xyzt_dev, n, o->frame.as<double>()));
+        if (stride == 0) LIMU_TRY(widen_device(c, xyzt_dev, n, o->frame.as<double>()));
+        else LIMU_TRY(widen_records_device(c, rec_dev, stride, n, o->frame.as<double>()));
         *deskewed = 0;
     }
     LIMU_TRY(prof_end(c, LIMU_STAGE_PREPARE));
@@ -227,7 +231,7 @@ void limu_odom_destroy(limu_odom *o) {
     cudaSetDevice(o->ctx->device);
     cudaStreamSynchronize(o->ctx->stream);
     limu_map_destroy(o->map);
-    DevBuf *bufs[] = {&o->raw, &o->frame, &o->down, &o->src0, &o->src, &o->work, &o->world, &o->partials};
+    DevBuf *bufs[] = {&o->raw, &o->ts, &o->frame, &o->down, &o->src0, &o->src, &o->work, &o->world, &o->partials};
     for (auto *b : bufs) b->release();
     o->sa.release(); o->sb.release();
     delete o;
@@ -239,7 +243,18 @@ int limu_odom_register_frame(limu_odom *o, const float *xyzt, int64_t n, double 
     LIMU_TRY(bind(o->ctx));
     LIMU_TRY(stage_in(o->ctx, o->raw, xyzt, (size_t)n * 16));
     int deskewed = 0;
-    LIMU_TRY(odom_prepare_frame(o, o->raw.as<float>(), n, &deskewed));
+    LIMU_TRY(odom_prepare_frame(o, o->raw.p, 0, nullptr, n, &deskewed));
+    return odom_register_device(o, o->frame.as<double>(), n, deskewed, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+}
+
+int limu_odom_register_cloud(limu_odom *o, const void *points, int32_t stride_bytes, const double *timestamps, int64_t n, double pose_out[7],
+                             double *down_xyz, int64_t *n_down, double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
+    LIMU_REQUIRE(o && n >= 0 && stride_bytes >= 12 && stride_bytes % 4 == 0 && (n == 0 || (points && timestamps)), "limu_odom_register_cloud: bad arguments");
+    LIMU_TRY(bind(o->ctx));
+    LIMU_TRY(stage_in(o->ctx, o->raw, points, (size_t)n * stride_bytes));
+    LIMU_TRY(stage_in(o->ctx, o->ts, timestamps, (size_t)n * 8));
+    int deskewed = 0;
+    LIMU_TRY(odom_prepare_frame(o, o->raw.p, stride_bytes, o->ts.as<double>(), n, &deskewed));
     return odom_register_device(o, o->frame.as<double>(), n, deskewed, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
 }
 
@@ -247,7 +262,7 @@ int limu_odom_register_frame_dev(limu_odom *o, const float *xyzt_dev, int64_t n,
     LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyzt_dev), "limu_odom_register_frame_dev: bad arguments");
     LIMU_TRY(bind(o->ctx));
     int deskewed = 0;
-    LIMU_TRY(odom_prepare_frame(o, xyzt_dev, n, &deskewed));
+    LIMU_TRY(odom_prepare_frame(o, xyzt_dev, 0, nullptr, n, &deskewed));
     return odom_register_device(o, o->frame.as<double>(), n, deskewed, pose_out, nullptr, nullptr, nullptr, nullptr, stats);
 }
 

@@ -38,6 +38,29 @@ static __global__ void __launch_bounds__(256) k_deskew(const float4 *__restrict_
     out[3 * i] = o.x; out[3 * i + 1] = o.y; out[3 * i + 2] = o.z;
 }
 
+// The same two stages for the reference's own input layout: an array of point records `stride` bytes apart with
+// float x,y,z at offset 0 (pcl::PointXYZINormal: 48 B, types.hpp:36) and a separate double timestamp per point
+// (std::vector<double>, icp.cpp:49-50). Timestamps stay FP64, so results match the reference bit for bit up to libm.
+static __global__ void __launch_bounds__(256) k_deskew_rec(const unsigned char *__restrict__ rec, int stride, const double *__restrict__ ts, int64_t n,
+                                                          const double *__restrict__ twist, double *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *q = reinterpret_cast<const float *>(rec + (size_t)i * stride);
+    const double s = ts[i] - 0.5;
+    double st[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) st[k] = s * twist[k];
+    const Pose M = se3_exp(st);
+    const V3 o = apply(M, V3{(double)q[0], (double)q[1], (double)q[2]});
+    out[3 * i] = o.x; out[3 * i + 1] = o.y; out[3 * i + 2] = o.z;
+}
+static __global__ void __launch_bounds__(256) k_widen_rec(const unsigned char *__restrict__ rec, int stride, int64_t n, double *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *q = reinterpret_cast<const float *>(rec + (size_t)i * stride);
+    out[3 * i] = (double)q[0]; out[3 * i + 1] = (double)q[1]; out[3 * i + 2] = (double)q[2];
+}
+
 static __global__ void __launch_bounds__(256) k_widen(const float4 *__restrict__ xyzt, int64_t n, double *__restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -189,6 +212,19 @@ int widen_device(limu_ctx *c, const float *xyzt_dev, int64_t n, double *out_dev)
     return LIMU_OK;
 }
 
+int deskew_records_device(limu_ctx *c, const void *rec_dev, int stride, const double *ts_dev, int64_t n, const double *twist_dev, double *out_dev) {
+    if (n <= 0) return LIMU_OK;
+    k_deskew_rec<<<div_up(n, 256), 256, 0, c->stream>>>(static_cast<const unsigned char *>(rec_dev), stride, ts_dev, n, twist_dev, out_dev);
+    LIMU_LAUNCHED();
+    return LIMU_OK;
+}
+int widen_records_device(limu_ctx *c, const void *rec_dev, int stride, int64_t n, double *out_dev) {
+    if (n <= 0) return LIMU_OK;
+    k_widen_rec<<<div_up(n, 256), 256, 0, c->stream>>>(static_cast<const unsigned char *>(rec_dev), stride, n, out_dev);
+    LIMU_LAUNCHED();
+    return LIMU_OK;
+}
+
 static int64_t table_slots(int64_t n) { int64_t p = 1024; while (p < 2 * n) p <<= 1; return p; }
 
 int downsample_device(limu_ctx *c, StageScratch &sc, const double *xyz_dev, int64_t n_max, const int *n_dev, double s, double *out_xyz_dev,
@@ -294,6 +330,23 @@ int limu_deskew(limu_ctx *c, const float *xyzt, int64_t n, const double T0[7], c
 }  // extern "C"
 
 extern "C" {
+
+int limu_deskew_cloud(limu_ctx *c, const void *points, int32_t stride_bytes, const double *timestamps, int64_t n, const double T0[7],
+                      const double T1[7], double *out_xyz) {
+    LIMU_TRY(bind(c));
+    LIMU_REQUIRE(T0 && T1 && n >= 0 && stride_bytes >= 12 && stride_bytes % 4 == 0 && (n == 0 || (points && timestamps && out_xyz)), "limu_deskew_cloud: bad arguments");
+    if (n == 0) return LIMU_OK;
+    double twist[6];
+    se3_log(mul(inverse(pose_load(T0)), pose_load(T1)), twist);   // utils::delta_pose, calculation_helpers.cpp:99-102
+    double *dtw;
+    LIMU_TRY(stage_small(c, twist, 6, 0, &dtw));
+    LIMU_TRY(stage_in(c, c->in1, points, (size_t)n * stride_bytes));
+    LIMU_TRY(stage_in(c, c->in0, timestamps, (size_t)n * 8));
+    LIMU_TRY(c->out0.reserve((size_t)n * 24, c->stream));
+    LIMU_TRY(deskew_records_device(c, c->in1.p, stride_bytes, c->in0.as<double>(), n, dtw, c->out0.as<double>()));
+    LIMU_CUDA_TRY(cudaMemcpyAsync(out_xyz, c->out0.p, (size_t)n * 24, cudaMemcpyDeviceToHost, c->stream));
+    return check_status(c);
+}
 
 int limu_voxel_downsample(limu_ctx *c, const double *xyz, int64_t n, double s, double *out_xyz, int64_t *out_idx, int64_t *n_out) {
     LIMU_TRY(bind(c));

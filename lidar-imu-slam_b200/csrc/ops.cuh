@@ -19,6 +19,9 @@ struct StageScratch {
 
 // deskew.cpp:10-28. twist_dev: 6 doubles (device). out: n x 3 doubles.
 int deskew_device(limu_ctx *c, const float *xyzt_dev, int64_t n, const double *twist_dev, double *out_dev);
+// the same for strided point records + FP64 timestamps (the reference's PCL cloud + std::vector<double>)
+int deskew_records_device(limu_ctx *c, const void *rec_dev, int stride, const double *ts_dev, int64_t n, const double *twist_dev, double *out_dev);
+int widen_records_device(limu_ctx *c, const void *rec_dev, int stride, int64_t n, double *out_dev);
 // pointcloud2eigen, calculation_helpers.cpp:83-97: widen float xyz to double.
 int widen_device(limu_ctx *c, const float *xyzt_dev, int64_t n, double *out_dev);
 // icp.cpp:9-30 first-point-wins downsample. out_idx_dev: survivor indices (int, n_max), out_count_dev: int.

@@ -151,7 +151,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_persistent(const Ic
         PT_MARK(0);
         double acc = 0.0;            // lane L: running total of sum index L>>1
         int ncorr = 0, ncand = 0, nmiss = 0;
-        const Pose P = pose_load(j == 0 ? Tinit : E);
+        const volatile double *Pv = j == 0 ? Tinit : E;   // re-read per batch: keeps 14 registers free across the lookup
         const double *in = j == 0 ? A.points : A.work;
         for (int64_t base = wbase; base < n; base += wstride) {
             const int64_t q = base + lane;
@@ -162,6 +162,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_persistent(const Ic
             if (on) {
                 // j == 0: source = init_guess * points (:102-103); later: source <- estimate * source (:119),
                 // applied lazily at the next visit
+                const Pose P{Pv[0], Pv[1], Pv[2], Pv[3], Pv[4], Pv[5], Pv[6]};
                 s = apply(P, V3{in[3 * q], in[3 * q + 1], in[3 * q + 2]});
                 A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z;
                 nn = map_closest(A.map, s);

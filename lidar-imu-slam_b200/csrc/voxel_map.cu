@@ -12,16 +12,15 @@ namespace limu {
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-static __global__ void k_map_clear(Slot *slots, unsigned long long *birth, int64_t C) {
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < C; s += (int64_t)gridDim.x * blockDim.x) {
-        slots[s] = Slot{KEY_EMPTY, 0, 0u};
-        birth[s] = BIRTH_NONE;
-    }
+static __global__ void k_map_clear(Slot *slots, int64_t C) {
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < C; s += (int64_t)gridDim.x * blockDim.x)
+        slots[s] = Slot{KEY_EMPTY, META_NONE};
 }
 
 // Pass 1 of insert_points (voxel_hash_map.cpp:12-62). One thread per input point:
 //   - voxel key (get_vox_index), claim-or-find its slot (64-bit CAS on the packed key),
-//   - birth[slot] = min(birth, base + i): the voxel's creation sequence = first input index that named it,
+//   - meta = min(meta, (base + i) << 13): a fresh slot (meta all-ones) becomes {birth = first input index that
+//     named the voxel, count 0}; an existing voxel's meta is smaller and stays untouched,
 //   - sorted insertion of i into the voxel's pending list pend[slot*cap + count .. slot*cap + cap):
 //     each position keeps the minimum it has seen and passes the loser on (atomicMin chain), so when
 //     the kernel ends the list holds the (cap - count) smallest input indices in ascending order --
@@ -54,8 +53,9 @@ static __global__ void __launch_bounds__(256) k_insert_claim(MapView m, const do
         }
         pslot[i] = slot;
         if (slot != PEND_NONE) {
-            atomicMin(&m.birth[slot], birth_base + (unsigned long long)i);
-            const int count = m.slots[slot].count;   // only pass 2 changes counts
+            const unsigned long long mine = (birth_base + (unsigned long long)i) << META_COUNT_BITS;
+            const unsigned long long old = atomicMin(&m.slots[slot].meta, mine);
+            const int count = meta_count(old < mine ? old : mine);   // only pass 2 changes counts
             unsigned int x = (unsigned int)i;
             unsigned int *list = m.pend + (size_t)slot * m.cap;
             for (int r = count; r < m.cap; ++r) {
@@ -88,7 +88,7 @@ static __global__ void __launch_bounds__(256) k_insert_place(MapView m, const do
             double *d = m.pts + ((size_t)slot * m.cap + r) * 3;
             d[0] = xyz[3 * i]; d[1] = xyz[3 * i + 1]; d[2] = xyz[3 * i + 2];
             list[r] = PEND_NONE;
-            atomicAdd(&m.slots[slot].count, 1);
+            atomicAdd(&m.slots[slot].meta, 1ull);
             break;
         }
     }
@@ -112,7 +112,8 @@ static __global__ void __launch_bounds__(256) k_remove_far(MapView m, int64_t C,
     const long long d2 = dx * dx + dy * dy + dz * dz;
     if (!((double)d2 > max_sq)) return;
     double *p = m.pts + (size_t)s * m.cap * 3;
-    const int count = m.slots[s].count;
+    const unsigned long long meta = m.slots[s].meta;
+    const int count = meta_count(meta);
     int w = 0;
     for (int r = 0; r < count; ++r) {
         const double ax = p[3 * r], ay = p[3 * r + 1], az = p[3 * r + 2];
@@ -121,10 +122,10 @@ static __global__ void __launch_bounds__(256) k_remove_far(MapView m, int64_t C,
             ++w;
         }
     }
-    if (w != count) m.slots[s].count = w;
+    if (w != count) m.slots[s].meta = (meta & ~META_COUNT_MASK) | (unsigned long long)w;
     if (w == 0) {
         m.slots[s].key = KEY_TOMB;
-        m.birth[s] = BIRTH_NONE;
+        m.slots[s].meta = META_NONE;
         atomicAdd(&counters[0], ~0ull);  // --live
         atomicAdd(&counters[1], 1ull);   // ++tombstones
     }
@@ -142,9 +143,9 @@ static __global__ void __launch_bounds__(256) k_rehash(MapView old, int64_t oldC
         if (cur == KEY_EMPTY) break;
         t = (t + 1) & nw.mask;
     }
-    const int count = old.slots[s].count;
-    nw.slots[t].count = count;
-    nw.birth[t] = old.birth[s];
+    const unsigned long long meta = old.slots[s].meta;
+    const int count = meta_count(meta);
+    nw.slots[t].meta = meta;
     const double *src = old.pts + (size_t)s * old.cap * 3;
     double *dst = nw.pts + (size_t)t * nw.cap * 3;
     for (int r = 0; r < 3 * count; ++r) dst[r] = src[r];
@@ -153,14 +154,14 @@ static __global__ void __launch_bounds__(256) k_rehash(MapView old, int64_t oldC
 static __global__ void k_sum_counts(const Slot *slots, int64_t C, unsigned long long *out /* [0]=voxels [1]=points */) {
     unsigned long long v = 0, p = 0;
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < C; s += (int64_t)gridDim.x * blockDim.x) {
-        if (slots[s].key < KEY_TOMB) { ++v; p += (unsigned long long)slots[s].count; }
+        if (slots[s].key < KEY_TOMB) { ++v; p += (unsigned long long)meta_count(slots[s].meta); }
     }
     for (int o = 16; o > 0; o >>= 1) { v += __shfl_down_sync(0xFFFFFFFFu, v, o); p += __shfl_down_sync(0xFFFFFFFFu, p, o); }
     if ((threadIdx.x & 31) == 0 && (v | p)) { atomicAdd(&out[0], v); atomicAdd(&out[1], p); }
 }
 
 // Live slots -> (birth, slot) pairs, unordered; the host sorts by birth to recover creation order.
-static __global__ void k_collect_live(const Slot *slots, const unsigned long long *birth, int64_t C, unsigned long long *pairs, unsigned long long *n_out) {
+static __global__ void k_collect_live(const Slot *slots, int64_t C, unsigned long long *pairs, unsigned long long *n_out) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = s < C && slots[s].key < KEY_TOMB;
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, live);
@@ -170,7 +171,7 @@ static __global__ void k_collect_live(const Slot *slots, const unsigned long lon
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (live) {
         const unsigned long long j = base + __popc(bal & ((1u << lane) - 1u));
-        pairs[2 * j] = birth[s];
+        pairs[2 * j] = meta_birth(slots[s].meta);
         pairs[2 * j + 1] = (unsigned long long)s;
     }
 }
@@ -182,7 +183,7 @@ static __global__ void k_gather_voxels(MapView m, const unsigned int *order, int
     int x, y, z;
     unpack_key(m.slots[s].key, x, y, z);
     keys[3 * j] = x; keys[3 * j + 1] = y; keys[3 * j + 2] = z;
-    const int c = m.slots[s].count;
+    const int c = meta_count(m.slots[s].meta);
     counts[j] = c;
     for (int r = 0; r < 3 * c; ++r) pts[(size_t)j * m.cap * 3 + r] = m.pts[(size_t)s * m.cap * 3 + r];
 }
@@ -230,14 +231,13 @@ int transform_device(limu_ctx *c, const double *pose_dev, const double *in, doub
 
 int map_alloc(limu_map *m, int64_t C) {
     limu_ctx *c = m->ctx;
-    m->slots.release(); m->birth.release(); m->pts.release(); m->pend.release();
+    m->slots.release(); m->pts.release(); m->pend.release();
     LIMU_TRY(m->slots.reserve((size_t)C * sizeof(Slot)));
-    LIMU_TRY(m->birth.reserve((size_t)C * 8));
     LIMU_TRY(m->pts.reserve((size_t)C * m->cap * 24));
     LIMU_TRY(m->pend.reserve((size_t)C * m->cap * 4));
     m->capacity = C;
     const int blocks = std::min<int64_t>(div_up(C, 256), (int64_t)c->sm_count * 32);
-    k_map_clear<<<blocks, 256, 0, c->stream>>>(m->slots.as<Slot>(), m->birth.as<unsigned long long>(), C);
+    k_map_clear<<<blocks, 256, 0, c->stream>>>(m->slots.as<Slot>(), C);
     LIMU_LAUNCHED();
     LIMU_CUDA_TRY(cudaMemsetAsync(m->pend.p, 0xFF, (size_t)C * m->cap * 4, c->stream));
     LIMU_TRY(m->counters.reserve(8 * sizeof(unsigned long long)));
@@ -251,7 +251,6 @@ int map_alloc(limu_map *m, int64_t C) {
 limu::MapView limu_map::view() const {
     limu::MapView v;
     v.slots = slots.as<limu::Slot>();
-    v.birth = birth.as<unsigned long long>();
     v.pts = pts.as<double>();
     v.pend = pend.as<unsigned int>();
     v.mask = (unsigned int)(capacity - 1);
@@ -285,11 +284,11 @@ int map_maybe_grow(limu_map *m, int64_t incoming) {
     limu_ctx *c = m->ctx;
     const int64_t newC = std::max<int64_t>(next_pow2((live + incoming) * 4), 1024);
     limu_map old = *m;  // shallow: keeps the old buffers alive
-    m->slots = DevBuf(); m->birth = DevBuf(); m->pts = DevBuf(); m->pend = DevBuf(); m->counters = DevBuf();
+    m->slots = DevBuf(); m->pts = DevBuf(); m->pend = DevBuf(); m->counters = DevBuf();
     int st = map_alloc(m, newC);
     if (st != LIMU_OK) {
-        m->slots.release(); m->birth.release(); m->pts.release(); m->pend.release(); m->counters.release();
-        m->slots = old.slots; m->birth = old.birth; m->pts = old.pts; m->pend = old.pend; m->counters = old.counters;
+        m->slots.release(); m->pts.release(); m->pend.release(); m->counters.release();
+        m->slots = old.slots; m->pts = old.pts; m->pend = old.pend; m->counters = old.counters;
         m->capacity = old.capacity;
         set_error("voxel map cannot grow to %lld slots", (long long)newC);
         return LIMU_ERR_MAP_FULL;
@@ -300,7 +299,7 @@ int map_maybe_grow(limu_map *m, int64_t incoming) {
     h[0] = (unsigned long long)live; h[1] = 0; h[2] = 0; h[3] = (unsigned long long)live;
     LIMU_CUDA_TRY(cudaMemcpyAsync(m->counters.p, h, 4 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
     LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    old.slots.release(); old.birth.release(); old.pts.release(); old.pend.release(); old.counters.release();
+    old.slots.release(); old.pts.release(); old.pend.release(); old.counters.release();
     old.pslot = DevBuf(); old.world = DevBuf();  // still owned by *m
     m->used_upper = live;
     return LIMU_OK;
@@ -370,7 +369,7 @@ void limu_map_destroy(limu_map *m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
-    m->slots.release(); m->birth.release(); m->pts.release(); m->pend.release(); m->counters.release();
+    m->slots.release(); m->pts.release(); m->pend.release(); m->counters.release();
     m->pslot.release(); m->world.release();
     delete m;
 }
@@ -380,7 +379,7 @@ int limu_map_clear(limu_map *m) {
     LIMU_TRY(bind(m->ctx));
     limu_ctx *c = m->ctx;
     const int blocks = std::min<int64_t>(div_up(m->capacity, 256), (int64_t)c->sm_count * 32);
-    k_map_clear<<<blocks, 256, 0, c->stream>>>(m->slots.as<Slot>(), m->birth.as<unsigned long long>(), m->capacity);
+    k_map_clear<<<blocks, 256, 0, c->stream>>>(m->slots.as<Slot>(), m->capacity);
     LIMU_LAUNCHED();
     LIMU_CUDA_TRY(cudaMemsetAsync(m->pend.p, 0xFF, (size_t)m->capacity * m->cap * 4, c->stream));
     LIMU_CUDA_TRY(cudaMemsetAsync(m->counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
@@ -538,7 +537,7 @@ int limu_map_dump(limu_map *m, int32_t *keys, int32_t *counts, double *pts, int6
     LIMU_TRY(c->tmp0.reserve((size_t)nv * 16 + 16, c->stream));
     unsigned long long *cnt = m->counters.as<unsigned long long>() + 6;
     LIMU_CUDA_TRY(cudaMemsetAsync(cnt, 0, 8, c->stream));
-    k_collect_live<<<div_up(m->capacity, 256), 256, 0, c->stream>>>(m->slots.as<Slot>(), m->birth.as<unsigned long long>(), m->capacity,
+    k_collect_live<<<div_up(m->capacity, 256), 256, 0, c->stream>>>(m->slots.as<Slot>(), m->capacity,
                                                                    c->tmp0.as<unsigned long long>(), cnt);
     LIMU_LAUNCHED();
     std::vector<unsigned long long> pairs((size_t)nv * 2);

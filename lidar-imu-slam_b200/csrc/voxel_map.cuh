@@ -4,14 +4,14 @@
 // voxel_hash_map.hpp:14-48, voxel_block.hpp:13-56): tsl::robin_map<Voxel, VoxelBlock> whose blocks hold
 // one heap node per point becomes ONE open-addressing table in HBM:
 //
-//   slots[C]        16 B  {u64 packed (i,j,k) key, i32 count, u32 spare}   C = power of two, load <= 0.5
-//   birth[C]         8 B  creation sequence of the voxel (= the reference container's address order,
+//   slots[C]        16 B  {u64 packed (i,j,k) key, u64 meta = birth << 13 | count}   C = power of two, load <= 0.5
+//                          birth = creation sequence of the voxel (= the reference container's address order,
 //                          used only by the 27-cell fallback tie-break, voxel_hash_map.cpp:81-101)
 //   pts[C*cap*3]    24 B  per point, slot-indexed: voxel s owns pts[s*cap .. s*cap+count)
 //   pend[C*cap]      4 B  per point slot: insert scratch (sorted pending input indices), all-ones at rest
 //
-// One 16-byte load answers "is this my voxel and how many points does it hold"; the points of a voxel
-// are contiguous (cap*24 B), so a query touches 1 + ceil(24*count/32) sectors.
+// One 16-byte load answers "is this my voxel, how many points does it hold, and how old is it"; the points
+// of a voxel are contiguous (cap*24 B), so a query touches 1 + ceil(24*count/32) sectors.
 #pragma once
 #include "common.cuh"
 
@@ -19,19 +19,21 @@ namespace limu {
 
 constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
 constexpr unsigned long long KEY_TOMB = 0xFFFFFFFFFFFFFFFEull;
-constexpr unsigned long long BIRTH_NONE = 0xFFFFFFFFFFFFFFFFull;
+constexpr unsigned long long META_NONE = 0xFFFFFFFFFFFFFFFFull;
+constexpr int META_COUNT_BITS = 13;                       // max_points_per_voxel <= 4096 < 2^13
+constexpr unsigned long long META_COUNT_MASK = (1ull << META_COUNT_BITS) - 1ull;
 constexpr unsigned int PEND_NONE = 0xFFFFFFFFu;
 constexpr int KEY_BIAS = 1 << 20;  // voxel indices in (-2^20, 2^20) pack into 3 x 21 bits
 
 struct __align__(16) Slot {
     unsigned long long key;
-    int count;
-    unsigned int spare;
+    unsigned long long meta;   // birth << 13 | count
 };
+__host__ __device__ __forceinline__ int meta_count(unsigned long long meta) { return (int)(meta & META_COUNT_MASK); }
+__host__ __device__ __forceinline__ unsigned long long meta_birth(unsigned long long meta) { return meta >> META_COUNT_BITS; }
 
 struct MapView {
     Slot *slots;
-    unsigned long long *birth;
     double *pts;
     unsigned int *pend;
     unsigned int mask;   // C - 1
@@ -61,20 +63,15 @@ __device__ __forceinline__ unsigned int slot_of(unsigned long long key, int shif
     return (unsigned int)((key * 0x9E3779B97F4A7C15ull) >> shift);
 }
 
-__device__ __forceinline__ void load_slot(const Slot *s, unsigned long long &key, int &count) {
-    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(s));
-    key = v.x;
-    count = (int)(unsigned int)(v.y & 0xFFFFFFFFull);
-}
+__device__ __forceinline__ ulonglong2 load_slot(const Slot *s) { return __ldg(reinterpret_cast<const ulonglong2 *>(s)); }
 
 // Read-only lookup. Returns slot index or -1; count of the voxel in *count.
 __device__ __forceinline__ int map_find(const MapView &m, unsigned long long key, int *count) {
     unsigned int s = slot_of(key, m.shift);
     for (;;) {
-        unsigned long long k; int c;
-        load_slot(m.slots + s, k, c);
-        if (k == key) { *count = c; return (int)s; }
-        if (k == KEY_EMPTY) return -1;
+        const ulonglong2 v = load_slot(m.slots + s);
+        if (v.x == key) { *count = meta_count(v.y); return (int)s; }
+        if (v.x == KEY_EMPTY) return -1;
         s = (s + 1) & m.mask;
     }
 }
@@ -83,7 +80,8 @@ __device__ __forceinline__ int map_find(const MapView &m, unsigned long long key
 __device__ constexpr signed char NB_CORNERS[8][3] = {{-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}, {1, -1, -1}, {1, -1, 1}, {1, 1, -1}, {1, 1, 1}};
 __device__ constexpr signed char NB_EDGES[12][3] = {{-1, -1, 0}, {-1, 1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 0, -1}, {-1, 0, 1},
                                                     {1, 0, -1},  {1, 0, 1},  {0, -1, -1}, {0, -1, 1}, {0, 1, -1}, {0, 1, 1}};
-__device__ constexpr signed char NB_FACES[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+// faces are padded to 8 entries (two chunks of four); the padding repeats real faces, which is harmless for a maximum
+__device__ constexpr signed char NB_FACES[8][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}, {0, 0, -1}, {0, 0, 1}};
 
 struct Nearest {
     double x, y, z;   // matched map point, or (0,0,0) when nothing was found
@@ -136,37 +134,42 @@ __device__ __forceinline__ Nearest map_closest(const MapView &m, const V3 &p) {
     }
     // Fallback (b): the winner is the occupied neighbour with the largest (|delta|^2, birth). Visit the
     // three distance classes in decreasing |delta|^2 -- 8 corners (3), 12 edges (2), 6 faces (1) -- and stop
-    // at the first class with an occupied cell. Within a class all home-slot loads are issued before any
-    // is consumed (one L2 round trip per class instead of one per cell).
+    // after the first class with an occupied cell. Cells are probed four at a time: the four 16-byte home-slot
+    // loads are issued before any is consumed, and each answers key, birth and count at once.
     int best_slot = -1;
-    unsigned long long best_birth = 0;
-#define LIMU_PROBE_CLASS(N, TABLE)                                                                          \
-    if (best_slot < 0) {                                                                                    \
-        unsigned long long got[N];                                                                          \
-        _Pragma("unroll") for (int c = 0; c < N; ++c) {                                                     \
-            const int x = kx + TABLE[c][0], y = ky + TABLE[c][1], z = kz + TABLE[c][2];                     \
-            got[c] = key_in_range(x, y, z) ? __ldg(&m.slots[slot_of(pack_key(x, y, z), m.shift)].key) : KEY_EMPTY; \
+    unsigned long long best_meta = 0;
+#define LIMU_PROBE_CHUNK(TABLE, FIRST)                                                                      \
+    {                                                                                                       \
+        ulonglong2 got[4];                                                                                  \
+        _Pragma("unroll") for (int c = 0; c < 4; ++c) {                                                     \
+            const int x = kx + TABLE[FIRST + c][0], y = ky + TABLE[FIRST + c][1], z = kz + TABLE[FIRST + c][2]; \
+            got[c] = key_in_range(x, y, z) ? load_slot(m.slots + slot_of(pack_key(x, y, z), m.shift)) : make_ulonglong2(KEY_EMPTY, 0ull); \
         }                                                                                                   \
-        _Pragma("unroll") for (int c = 0; c < N; ++c) {                                                     \
-            unsigned long long k = got[c];                                                                  \
-            if (k != KEY_EMPTY) {                                                                           \
-                const unsigned long long want = pack_key(kx + TABLE[c][0], ky + TABLE[c][1], kz + TABLE[c][2]); \
+        _Pragma("unroll") for (int c = 0; c < 4; ++c) {                                                     \
+            ulonglong2 v = got[c];                                                                          \
+            if (v.x != KEY_EMPTY) {                                                                         \
+                const unsigned long long want = pack_key(kx + TABLE[FIRST + c][0], ky + TABLE[FIRST + c][1], kz + TABLE[FIRST + c][2]); \
                 unsigned int s = slot_of(want, m.shift);                                                    \
-                while (k != want && k != KEY_EMPTY) { s = (s + 1) & m.mask; k = __ldg(&m.slots[s].key); }   \
-                if (k == want) {                                                                            \
-                    const unsigned long long bth = __ldg(m.birth + s);                                      \
-                    if (best_slot < 0 || bth > best_birth) { best_birth = bth; best_slot = (int)s; }        \
-                }                                                                                           \
+                while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(m.slots + s); } \
+                if (v.x == want && (best_slot < 0 || v.y > best_meta)) { best_meta = v.y; best_slot = (int)s; } \
             }                                                                                               \
         }                                                                                                   \
     }
-    LIMU_PROBE_CLASS(8, NB_CORNERS)
-    LIMU_PROBE_CLASS(12, NB_EDGES)
-    LIMU_PROBE_CLASS(6, NB_FACES)
-#undef LIMU_PROBE_CLASS
+    LIMU_PROBE_CHUNK(NB_CORNERS, 0)
+    LIMU_PROBE_CHUNK(NB_CORNERS, 4)
+    if (best_slot < 0) {
+        LIMU_PROBE_CHUNK(NB_EDGES, 0)
+        LIMU_PROBE_CHUNK(NB_EDGES, 4)
+        LIMU_PROBE_CHUNK(NB_EDGES, 8)
+    }
+    if (best_slot < 0) {
+        LIMU_PROBE_CHUNK(NB_FACES, 0)
+        LIMU_PROBE_CHUNK(NB_FACES, 4)
+    }
+#undef LIMU_PROBE_CHUNK
     if (best_slot >= 0) {
         r.slot = best_slot;
-        block_closest(m, best_slot, __ldg(&m.slots[best_slot].count), p, r);
+        block_closest(m, best_slot, meta_count(best_meta), p, r);   // births are unique, so comparing meta compares birth
         if (r.rank < 0) { r.x = r.y = r.z = 0.0; }
     }
     return r;
@@ -180,7 +183,7 @@ struct limu_map {
     double vox_size = 1.0, max_distance = 100.0;
     int cap = 10;
     int64_t capacity = 0;          // C (slots), power of two
-    limu::DevBuf slots, birth, pts, pend;
+    limu::DevBuf slots, pts, pend;
     limu::DevBuf counters;         // device: [0] n_live voxels, [1] n_tomb, [2] n_points, [3] n_used (live + tomb)
     uint64_t birth_base = 0;       // creation sequence offset of the next insert batch
     int64_t used_upper = 0;        // host upper bound on live + tomb slots
