@@ -14,6 +14,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import weakref
 
 import numpy as np
 
@@ -192,11 +193,14 @@ class Context:
 
     def __init__(self, device: int = 0):
         self.h = _vp()
+        self._children = weakref.WeakSet()   # maps / odometry handles must die before their context
         _chk(lib().limu_ctx_create(device, C.byref(self.h)))
         self.device = device
 
     def close(self):
         if self.h:
+            for child in list(self._children):
+                child.close()
             lib().limu_ctx_destroy(self.h)
             self.h = _vp()
 
@@ -299,6 +303,7 @@ class VoxelHashMap:
         if handle is None:
             self.h = _vp()
             _chk(lib().limu_map_create(ctx.h, float(vox_size), float(max_distance), int(max_points_per_voxel), int(capacity_voxels), C.byref(self.h)))
+            ctx._children.add(self)
         else:
             self.h = handle
 
@@ -420,6 +425,7 @@ class KissICP:
         self.cfg = cfg
         self.h = _vp()
         _chk(lib().limu_odom_create(ctx.h, C.byref(cfg), C.byref(self.h)))
+        ctx._children.add(self)
         self.stats = FrameStats()
 
     def close(self):
