@@ -37,6 +37,7 @@ struct IcpArgs {
     double *partials;           // [2][gridDim][NS]
     unsigned int *barrier;      // zeroed before launch
     double *out;                // [0..6] pose, [7] iterations, [8] converged, [9] ncorr, [10] ncand, [11] nmiss, [12] n
+    int coop_scan;              // 1: sub-warp cooperative candidate scan (bandwidth shape); 0: one lane per query (latency shape)
     double *est_trace;          // optional [max_iter][7]
     long long *ncorr_trace;     // optional [max_iter]
     double *hg_trace;           // optional [max_iter][42]
@@ -120,6 +121,52 @@ __device__ __forceinline__ void block_reduce_row(double *a, double *smem /* [ICP
     }
 }
 
+// Cooperative candidate scan (VoxelBlock::get_closest_point, voxel_block.cpp:87-105): the warp works as four groups
+// of eight lanes; in step t group g scans the voxel of ITS lane t. Eight lanes read ranks r..r+7 of the x / y / z rows
+// = three 64-byte coalesced segments (instead of 32 scattered 8-byte loads per instruction), each lane keeps its best
+// (d2, rank) and a 3-step butterfly leaves the lexicographic minimum -- smallest distance, then lowest rank = "first
+// minimum wins" -- in every lane of the group. ROUNDS = ceil(cap / 8) is a template parameter so every load of a step
+// is unconditional and can be issued before the first one is consumed (ROUNDS == 0: generic loop for cap > 24).
+template <int ROUNDS>
+__device__ __forceinline__ void coop_scan(const MapView &m, const V3 &s, int slot, int count, int lane, double &my_d2, int &my_rank) {
+    const int l8 = lane & 7;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const double qx = __shfl_sync(0xFFFFFFFFu, s.x, t, 8), qy = __shfl_sync(0xFFFFFFFFu, s.y, t, 8), qz = __shfl_sync(0xFFFFFFFFu, s.z, t, 8);
+        const int qslot = __shfl_sync(0xFFFFFFFFu, slot, t, 8);
+        const int qcount = qslot >= 0 ? __shfl_sync(0xFFFFFFFFu, count, t, 8) : (__shfl_sync(0xFFFFFFFFu, count, t, 8), 0);
+        const double *bx = voxel_rows(m, (unsigned int)(qslot >= 0 ? qslot : 0)), *by = bx + m.capp, *bz = by + m.capp;
+        double bd = 1.7976931348623157e308;
+        int br = 0x7FFFFFFF;
+        if (ROUNDS > 0) {
+            double x[ROUNDS > 0 ? ROUNDS : 1], y[ROUNDS > 0 ? ROUNDS : 1], z[ROUNDS > 0 ? ROUNDS : 1];
+#pragma unroll
+            for (int k = 0; k < ROUNDS; ++k) {   // out-of-range ranks re-read rank l8 (always inside the block) and are ignored below
+                const int r = l8 + 8 * k, rr = r < qcount ? r : l8;
+                x[k] = __ldg(bx + rr); y[k] = __ldg(by + rr); z[k] = __ldg(bz + rr);
+            }
+#pragma unroll
+            for (int k = 0; k < ROUNDS; ++k) {
+                const int r = l8 + 8 * k;
+                const double d = sqnorm3(qx - x[k], qy - y[k], qz - z[k]);
+                if (r < qcount && d < bd) { bd = d; br = r; }
+            }
+        } else {
+            for (int r = l8; r < qcount; r += 8) {
+                const double d = sqnorm3(qx - __ldg(bx + r), qy - __ldg(by + r), qz - __ldg(bz + r));
+                if (d < bd) { bd = d; br = r; }
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xFFFFFFFFu, bd, o);
+            const int orr = __shfl_xor_sync(0xFFFFFFFFu, br, o);
+            if (od < bd || (od == bd && orr < br)) { bd = od; br = orr; }
+        }
+        if (l8 == t) { my_d2 = bd; my_rank = br == 0x7FFFFFFF ? -1 : br; }
+    }
+}
+
 #ifdef LIMU_ICP_PHASE_TIMING
 #define PT_MARK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && A.hg_trace) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); A.hg_trace[42 * (size_t)j + (k)] = (double)_t; } } while (0)
 #else
@@ -157,24 +204,43 @@ static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_persistent(const Ic
             const int64_t q = base + lane;
             const bool on = q < n;
             V3 s{0.0, 0.0, 0.0};
-            Nearest nn;
-            nn.x = nn.y = nn.z = 0.0; nn.ncand = 0; nn.own = 1;
+            int slot = -1, count = 0, own = 1;
             if (on) {
                 // j == 0: source = init_guess * points (:102-103); later: source <- estimate * source (:119),
                 // applied lazily at the next visit
                 const Pose P{Pv[0], Pv[1], Pv[2], Pv[3], Pv[4], Pv[5], Pv[6]};
                 s = apply(P, V3{in[3 * q], in[3 * q + 1], in[3 * q + 2]});
                 A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z;
-                nn = map_closest(A.map, s);
+                slot = map_locate(A.map, s, &count, &own);   // which voxel answers (own, else farthest/latest of the 27)
             }
-            const double d2 = sqnorm3(nn.x - s.x, nn.y - s.y, nn.z - s.z);   // (found - point).squaredNorm() voxel_hash_map.cpp:120
+            double my_d2 = 0.0;
+            int my_rank = -1;
+            if (A.coop_scan) {
+                if (A.map.cap <= 8) coop_scan<1>(A.map, s, slot, count, lane, my_d2, my_rank);
+                else if (A.map.cap <= 16) coop_scan<2>(A.map, s, slot, count, lane, my_d2, my_rank);
+                else if (A.map.cap <= 24) coop_scan<3>(A.map, s, slot, count, lane, my_d2, my_rank);
+                else coop_scan<0>(A.map, s, slot, count, lane, my_d2, my_rank);
+            } else if (slot >= 0) {
+                // latency shape (a few thousand keypoint queries): every lane scans its own voxel, one L2 round trip per
+                // four candidates instead of eight dependent group steps
+                Nearest nn;
+                block_closest(A.map, slot, count, s, nn);
+                my_rank = nn.rank;
+                my_d2 = sqnorm3(nn.x - s.x, nn.y - s.y, nn.z - s.z);
+            }
+            V3 tg{0.0, 0.0, 0.0};   // nothing found -> (0,0,0), range-tested like a real point (voxel_hash_map.cpp:98-99,118-124)
+            if (my_rank >= 0) {
+                const double *bx = voxel_rows(A.map, (unsigned int)slot);
+                tg = V3{__ldg(bx + my_rank), __ldg(bx + A.map.capp + my_rank), __ldg(bx + 2 * A.map.capp + my_rank)};
+            }
+            const double d2 = my_rank >= 0 ? my_d2 : sqnorm3(tg.x - s.x, tg.y - s.y, tg.z - s.z);   // (found - point).squaredNorm() :120
             const bool gate = on && d2 < A.tau_sq;
             double c[16];
-            contribution(c, s, V3{nn.x, nn.y, nn.z}, d2, A.th, gate);
+            contribution(c, s, tg, d2, A.th, gate);
             acc += warp_reduce_scatter16(c);
             ncorr += gate ? 1 : 0;
-            ncand += nn.ncand;
-            nmiss += (on && !nn.own) ? 1 : 0;
+            ncand += count;
+            nmiss += (on && !own) ? 1 : 0;
         }
         PT_MARK(1);
         // CTA row: 16 sums (even lanes hold them) + 3 counters
@@ -311,6 +377,7 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
     A.tau_sq = tau * tau; A.th = th; A.max_iter = max_iter; A.eps = eps;
     A.partials = partials_dev; A.barrier = barrier_dev; A.out = out13_dev;
     A.est_trace = est_trace_dev; A.ncorr_trace = ncorr_trace_dev; A.hg_trace = hg_trace_dev;
+    A.coop_scan = n_hint >= 32768 ? 1 : 0;
     LIMU_CUDA_TRY(cudaMemsetAsync(barrier_dev, 0, sizeof(unsigned int), c->stream));
     void *args[] = {&A};
     LIMU_TRY(prof_begin(c, LIMU_STAGE_ICP));

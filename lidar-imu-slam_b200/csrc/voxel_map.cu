@@ -85,8 +85,8 @@ static __global__ void __launch_bounds__(256) k_insert_place(MapView m, const do
     unsigned int *list = m.pend + (size_t)slot * m.cap;
     for (int r = 0; r < m.cap; ++r) {
         if (list[r] == (unsigned int)i) {
-            double *d = m.pts + ((size_t)slot * m.cap + r) * 3;
-            d[0] = xyz[3 * i]; d[1] = xyz[3 * i + 1]; d[2] = xyz[3 * i + 2];
+            double *d = voxel_rows(m, slot);
+            d[r] = xyz[3 * i]; d[m.capp + r] = xyz[3 * i + 1]; d[2 * m.capp + r] = xyz[3 * i + 2];
             list[r] = PEND_NONE;
             atomicAdd(&m.slots[slot].meta, 1ull);
             break;
@@ -111,14 +111,14 @@ static __global__ void __launch_bounds__(256) k_remove_far(MapView m, int64_t C,
     const long long dx = x - vox_index(ox, m.vox), dy = y - vox_index(oy, m.vox), dz = z - vox_index(oz, m.vox);
     const long long d2 = dx * dx + dy * dy + dz * dz;
     if (!((double)d2 > max_sq)) return;
-    double *p = m.pts + (size_t)s * m.cap * 3;
+    double *px = voxel_rows(m, (unsigned int)s), *py = px + m.capp, *pz = py + m.capp;
     const unsigned long long meta = m.slots[s].meta;
     const int count = meta_count(meta);
     int w = 0;
     for (int r = 0; r < count; ++r) {
-        const double ax = p[3 * r], ay = p[3 * r + 1], az = p[3 * r + 2];
+        const double ax = px[r], ay = py[r], az = pz[r];
         if (!(sqnorm3(ax - ox, ay - oy, az - oz) > max_sq)) {
-            if (w != r) { p[3 * w] = ax; p[3 * w + 1] = ay; p[3 * w + 2] = az; }
+            if (w != r) { px[w] = ax; py[w] = ay; pz[w] = az; }
             ++w;
         }
     }
@@ -146,9 +146,9 @@ static __global__ void __launch_bounds__(256) k_rehash(MapView old, int64_t oldC
     const unsigned long long meta = old.slots[s].meta;
     const int count = meta_count(meta);
     nw.slots[t].meta = meta;
-    const double *src = old.pts + (size_t)s * old.cap * 3;
-    double *dst = nw.pts + (size_t)t * nw.cap * 3;
-    for (int r = 0; r < 3 * count; ++r) dst[r] = src[r];
+    const double *src = voxel_rows(old, (unsigned int)s);
+    double *dst = voxel_rows(nw, t);
+    for (int r = 0; r < count; ++r) { dst[r] = src[r]; dst[nw.capp + r] = src[old.capp + r]; dst[2 * nw.capp + r] = src[2 * old.capp + r]; }
 }
 
 static __global__ void k_sum_counts(const Slot *slots, int64_t C, unsigned long long *out /* [0]=voxels [1]=points */) {
@@ -185,7 +185,11 @@ static __global__ void k_gather_voxels(MapView m, const unsigned int *order, int
     keys[3 * j] = x; keys[3 * j + 1] = y; keys[3 * j + 2] = z;
     const int c = meta_count(m.slots[s].meta);
     counts[j] = c;
-    for (int r = 0; r < 3 * c; ++r) pts[(size_t)j * m.cap * 3 + r] = m.pts[(size_t)s * m.cap * 3 + r];
+    const double *b = voxel_rows(m, s);
+    for (int r = 0; r < c; ++r) {   // back to array-of-structs for the host
+        double *o = pts + ((size_t)j * m.cap + r) * 3;
+        o[0] = b[r]; o[1] = b[m.capp + r]; o[2] = b[2 * m.capp + r];
+    }
 }
 
 // get_closest_neighbour for a batch (voxel_hash_map.cpp:64-102); flag = within max_correspondance (:120).
@@ -233,7 +237,7 @@ int map_alloc(limu_map *m, int64_t C) {
     limu_ctx *c = m->ctx;
     m->slots.release(); m->pts.release(); m->pend.release();
     LIMU_TRY(m->slots.reserve((size_t)C * sizeof(Slot)));
-    LIMU_TRY(m->pts.reserve((size_t)C * m->cap * 24));
+    LIMU_TRY(m->pts.reserve((size_t)C * limu::block_stride(m->cap) * 8));
     LIMU_TRY(m->pend.reserve((size_t)C * m->cap * 4));
     m->capacity = C;
     const int blocks = std::min<int64_t>(div_up(C, 256), (int64_t)c->sm_count * 32);
@@ -258,6 +262,8 @@ limu::MapView limu_map::view() const {
     while ((int64_t(1) << lg) < capacity) ++lg;
     v.shift = 64 - lg;
     v.cap = cap;
+    v.capp = limu::cap_padded(cap);
+    v.stride = limu::block_stride(cap);
     v.vox = vox_size;
     return v;
 }

@@ -7,11 +7,13 @@
 //   slots[C]        16 B  {u64 packed (i,j,k) key, u64 meta = birth << 13 | count}   C = power of two, load <= 0.5
 //                          birth = creation sequence of the voxel (= the reference container's address order,
 //                          used only by the 27-cell fallback tie-break, voxel_hash_map.cpp:81-101)
-//   pts[C*cap*3]    24 B  per point, slot-indexed: voxel s owns pts[s*cap .. s*cap+count)
+//   pts[C*stride]   24 B  per point, slot-indexed, structure-of-arrays INSIDE a voxel: voxel s owns three rows
+//                          x[capp] y[capp] z[capp] at pts + s*3*capp (capp = cap rounded up to 4 doubles = one 32 B
+//                          sector), so eight lanes reading ranks r..r+7 of one row fetch 64 contiguous bytes
 //   pend[C*cap]      4 B  per point slot: insert scratch (sorted pending input indices), all-ones at rest
 //
 // One 16-byte load answers "is this my voxel, how many points does it hold, and how old is it"; the points
-// of a voxel are contiguous (cap*24 B), so a query touches 1 + ceil(24*count/32) sectors.
+// of a voxel are contiguous (capp*24 B), so a query touches 1 + 3*ceil(8*count/32) sectors.
 #pragma once
 #include "common.cuh"
 
@@ -39,8 +41,14 @@ struct MapView {
     unsigned int mask;   // C - 1
     int shift;           // 64 - log2(C)
     int cap;
+    int capp;            // cap rounded up to a multiple of 4: row length of the per-voxel SoA block
+    int stride;          // doubles per voxel block: 3*capp rounded up to 16 (= one 128 B L2 line), so a block never straddles an extra line
     double vox;
 };
+__host__ __device__ __forceinline__ int cap_padded(int cap) { return (cap + 3) & ~3; }
+__host__ __device__ __forceinline__ int block_stride(int cap) { return (3 * cap_padded(cap) + 15) & ~15; }
+// row pointers of voxel `slot`: x = base, y = base + capp, z = base + 2*capp
+__device__ __forceinline__ double *voxel_rows(const MapView &m, unsigned int slot) { return m.pts + (size_t)slot * (size_t)m.stride; }
 
 // utils::get_vox_index, calculation_helpers.cpp:142-147: IEEE double division, truncation toward zero.
 __device__ __forceinline__ int vox_index(double p, double v) { return __double2int_rz(p / v); }
@@ -92,45 +100,34 @@ struct Nearest {
 };
 
 // VoxelBlock::get_closest_point, voxel_block.cpp:87-105: linear scan, strict '<', first minimum wins.
-// Candidates are fetched four at a time (12 independent 8-byte loads in flight) and then compared in order.
+// One-thread-per-query form: candidates are fetched four at a time (one 32 B sector per row) and compared in order.
 __device__ __forceinline__ void block_closest(const MapView &m, int slot, int count, const V3 &p, Nearest &r) {
-    const double *b = m.pts + (size_t)slot * (size_t)m.cap * 3;
+    const double *bx = voxel_rows(m, (unsigned int)slot), *by = bx + m.capp, *bz = by + m.capp;
     double best = 1.7976931348623157e308;
     r.rank = -1;
-    for (int base = 0; base < count; base += 4) {
-        double c[12];
+    for (int base = 0; base < count; base += 4) {   // rows are padded to a multiple of 4, so the loads stay in bounds
+        double cx[4], cy[4], cz[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { cx[k] = __ldg(bx + base + k); cy[k] = __ldg(by + base + k); cz[k] = __ldg(bz + base + k); }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const bool on = base + k < count;
-            const double *q = b + 3 * (base + (on ? k : 0));
-            c[3 * k] = __ldg(q); c[3 * k + 1] = __ldg(q + 1); c[3 * k + 2] = __ldg(q + 2);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double d = sqnorm3(p.x - c[3 * k], p.y - c[3 * k + 1], p.z - c[3 * k + 2]);
-            if (base + k < count && d < best) { best = d; r.rank = base + k; r.x = c[3 * k]; r.y = c[3 * k + 1]; r.z = c[3 * k + 2]; }
+            const double d = sqnorm3(p.x - cx[k], p.y - cy[k], p.z - cz[k]);
+            if (base + k < count && d < best) { best = d; r.rank = base + k; r.x = cx[k]; r.y = cy[k]; r.z = cz[k]; }
         }
     }
     r.ncand = count;
 }
 
-// VoxelHashMap::get_closest_neighbour, voxel_hash_map.cpp:64-102:
-//  (a) own voxel present            -> closest point inside it only (:71-73)
-//  (b) else the top of a max-heap on (|delta index|^2, block address) over the occupied cells of the
-//      27-neighbourhood (:76-96,101) = the FARTHEST occupied cell, ties to the later-created voxel
-//  (c) nothing                      -> (0,0,0) (:98-99)
-__device__ __forceinline__ Nearest map_closest(const MapView &m, const V3 &p) {
-    Nearest r;
-    r.x = r.y = r.z = 0.0; r.slot = -1; r.rank = -1; r.ncand = 0; r.own = 0;
+// Step 1 of the lookup: WHICH voxel answers the query (rules (a)/(b) below). Returns its slot (or -1), its count,
+// and whether it is the query's own voxel.
+__device__ __forceinline__ int map_locate(const MapView &m, const V3 &p, int *count_out, int *own_out) {
     const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
-    int count = 0;
+    *own_out = 0;
+    *count_out = 0;
     if (key_in_range(kx, ky, kz)) {
+        int count = 0;
         const int s = map_find(m, pack_key(kx, ky, kz), &count);
-        if (s >= 0) {
-            r.slot = s; r.own = 1;
-            block_closest(m, s, count, p, r);
-            return r;
-        }
+        if (s >= 0) { *own_out = 1; *count_out = count; return s; }
     }
     // Fallback (b): the winner is the occupied neighbour with the largest (|delta|^2, birth). Visit the
     // three distance classes in decreasing |delta|^2 -- 8 corners (3), 12 edges (2), 6 faces (1) -- and stop
@@ -167,9 +164,22 @@ __device__ __forceinline__ Nearest map_closest(const MapView &m, const V3 &p) {
         LIMU_PROBE_CHUNK(NB_FACES, 4)
     }
 #undef LIMU_PROBE_CHUNK
-    if (best_slot >= 0) {
-        r.slot = best_slot;
-        block_closest(m, best_slot, meta_count(best_meta), p, r);   // births are unique, so comparing meta compares birth
+    if (best_slot >= 0) *count_out = meta_count(best_meta);   // births are unique, so comparing meta compared birth
+    return best_slot;
+}
+
+// VoxelHashMap::get_closest_neighbour, voxel_hash_map.cpp:64-102:
+//  (a) own voxel present            -> closest point inside it only (:71-73)
+//  (b) else the top of a max-heap on (|delta index|^2, block address) over the occupied cells of the
+//      27-neighbourhood (:76-96,101) = the FARTHEST occupied cell, ties to the later-created voxel
+//  (c) nothing                      -> (0,0,0) (:98-99)
+__device__ __forceinline__ Nearest map_closest(const MapView &m, const V3 &p) {
+    Nearest r;
+    r.x = r.y = r.z = 0.0; r.rank = -1; r.ncand = 0;
+    int count;
+    r.slot = map_locate(m, p, &count, &r.own);
+    if (r.slot >= 0) {
+        block_closest(m, r.slot, count, p, r);
         if (r.rank < 0) { r.x = r.y = r.z = 0.0; }
     }
     return r;
