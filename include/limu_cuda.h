@@ -130,6 +130,22 @@ int limu_icp(limu_map *m, const double *xyz, int64_t n, const double init_guess[
 int limu_icp_dev(limu_map *m, const double *xyz_dev, int64_t n, const double init_guess[7], double max_corresp_dist, double kernel,
                  int icp_max_iteration, double est_threshold, double pose_out[7], limu_icp_stats *stats);
 
+/* ---- point-sharded ICP over several GPUs (BASELINE configs[4]; no counterpart in the single-process reference) ----
+ * One process per GPU. Every rank holds a full replica of the map and a contiguous shard of the query points; per
+ * Gauss-Newton iteration the ranks exchange ONE row of 20 doubles (the normal-equation sums). LIMU_SHARD_FUSED does
+ * that inside the persistent kernel with stores into peer-mapped mailboxes over NVLink; LIMU_SHARD_NCCL is the un-fused
+ * baseline (kernel -> ncclAllReduce -> solve kernel, host in the loop). All ranks return the same pose.
+ * Setup: limu_comm_create on every rank -> exchange the 64-byte handles (any transport) -> limu_comm_connect. */
+enum { LIMU_SHARD_FUSED = 0, LIMU_SHARD_NCCL = 1 };
+int limu_comm_create(limu_ctx *c, int rank, int nranks, unsigned char ipc_handle_out[64]);
+int limu_comm_connect(limu_ctx *c, const unsigned char *all_handles /* nranks x 64 bytes, rank order */);
+void limu_comm_destroy(limu_ctx *c);
+int limu_comm_nccl_unique_id(unsigned char id_out[128]);            /* rank 0, then broadcast */
+int limu_comm_nccl_init(limu_ctx *c, const unsigned char id[128]);  /* only needed for LIMU_SHARD_NCCL */
+/* stats->mean_candidates / miss_fraction carry GLOBAL candidate / miss COUNTS in a sharded call. */
+int limu_icp_sharded_dev(limu_map *m, const double *xyz_dev, int64_t n_local, const double init_guess[7], double max_corresp_dist, double kernel,
+                         int icp_max_iteration, double est_threshold, int mode, double pose_out[7], limu_icp_stats *stats);
+
 /* ---- lidar::KissICP, sensors/lidar/icp.hpp:31-68 ------------------------------------------------ */
 typedef struct limu_odom_config {   /* frame::Lidar::ProcessingInfo fields the path reads, lidar/frame.hpp:34-58, defaults :64-80 */
     double voxel_size;            /* 1.0 (= max_range / 100) */

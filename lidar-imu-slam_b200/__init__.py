@@ -102,6 +102,9 @@ def lib():
             "limu_map_dump": [_vp, _ip, _ip, _dp, C.c_int64, C.c_int64, _lp, _lp],
             "limu_icp": [_vp, _dp, C.c_int64, _dp, C.c_double, C.c_double, C.c_int, C.c_double, _dp, C.POINTER(IcpStats), _dp, _lp, _dp],
             "limu_icp_dev": [_vp, _vp, C.c_int64, _dp, C.c_double, C.c_double, C.c_int, C.c_double, _dp, C.POINTER(IcpStats)],
+            "limu_comm_create": [_vp, C.c_int, C.c_int, C.c_char_p], "limu_comm_connect": [_vp, C.c_char_p], "limu_comm_destroy": [_vp],
+            "limu_comm_nccl_unique_id": [C.c_char_p], "limu_comm_nccl_init": [_vp, C.c_char_p],
+            "limu_icp_sharded_dev": [_vp, _vp, C.c_int64, _dp, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int, _dp, C.POINTER(IcpStats)],
             "limu_odom_default_config": [C.POINTER(OdomConfig)],
             "limu_odom_create": [_vp, C.POINTER(OdomConfig), C.POINTER(_vp)], "limu_odom_destroy": [_vp],
             "limu_odom_register_frame": [_vp, _fp, C.c_int64, _dp, _dp, _lp, _dp, _lp, C.POINTER(FrameStats)],
@@ -215,6 +218,25 @@ class Context:
 
     def stream(self) -> int:
         return int(lib().limu_ctx_stream(self.h) or 0)
+
+    # ---- multi-GPU (one process per GPU): mailbox handles are exchanged by the caller's transport ------------------
+    def comm_init(self, rank, nranks, all_gather_bytes, broadcast_bytes=None, nccl_baseline=False):
+        """all_gather_bytes(b) -> [b_rank0, b_rank1, ...]; broadcast_bytes(b_or_None) -> bytes from rank 0."""
+        buf = C.create_string_buffer(64)
+        _chk(lib().limu_comm_create(self.h, int(rank), int(nranks), buf))
+        handles = all_gather_bytes(buf.raw)
+        assert len(handles) == nranks and all(len(h) == 64 for h in handles)
+        _chk(lib().limu_comm_connect(self.h, b"".join(handles)))
+        if nccl_baseline:
+            idb = C.create_string_buffer(128)
+            if rank == 0:
+                _chk(lib().limu_comm_nccl_unique_id(idb))
+            idr = broadcast_bytes(idb.raw if rank == 0 else None)
+            _chk(lib().limu_comm_nccl_init(self.h, idr))
+        self.rank, self.nranks = rank, nranks
+
+    def comm_destroy(self):
+        lib().limu_comm_destroy(self.h)
 
     STAGES = ("prepare", "downsample", "iqr", "icp", "map_update")
 
@@ -405,6 +427,15 @@ class VoxelHashMap:
                                 int(icp_max_iteration), float(est_threshold), _d(pose), C.byref(st)))
         return {"pose": pose, "iters": st.iterations, "converged": bool(st.converged), "last_ncorr": st.last_ncorr,
                 "mean_candidates": st.mean_candidates, "miss_fraction": st.miss_fraction}
+
+    def icp_sharded_dev(self, xyz_dev_ptr, n_local, init_guess, max_corresp_dist, kernel, icp_max_iteration, est_threshold, mode=0):
+        """Point-sharded lidar::ICP: this rank's shard of the queries against the replicated map (mode 0 fused peer exchange, 1 NCCL baseline)."""
+        pose = np.empty(7)
+        st = IcpStats()
+        _chk(lib().limu_icp_sharded_dev(self.h, _vp(xyz_dev_ptr), int(n_local), _d(_pose(init_guess)), float(max_corresp_dist), float(kernel),
+                                        int(icp_max_iteration), float(est_threshold), int(mode), _d(pose), C.byref(st)))
+        return {"pose": pose, "iters": st.iterations, "converged": bool(st.converged), "last_ncorr": st.last_ncorr,
+                "candidates_total": st.mean_candidates, "misses_total": st.miss_fraction}
 
     def insert_points_dev(self, xyz_dev_ptr, n):
         _chk(lib().limu_map_insert_dev(self.h, _vp(xyz_dev_ptr), int(n)))

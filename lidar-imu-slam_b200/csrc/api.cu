@@ -126,6 +126,7 @@ void limu_ctx_destroy(limu_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    limu_comm_destroy(c);
     release_ctx_scratch(c);
     limu::DevBuf *bufs[] = {&c->in0, &c->in1, &c->out0, &c->out1, &c->out2, &c->tmp0, &c->tmp1, &c->tmp2, &c->tmp3, &c->tmp4, &c->tmp5, &c->d_small};
     for (auto *b : bufs) b->release();

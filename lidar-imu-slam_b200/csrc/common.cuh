@@ -71,6 +71,18 @@ struct DevStatus {
 
 }  // namespace limu
 
+// Multi-GPU exchange state of one rank (comm.cu).
+struct limu_comm {
+    int rank = 0, nranks = 1;
+    double *mbox_local = nullptr;          // [2][8][24] doubles in this rank's memory (IPC-exported)
+    double *mbox_peer[8] = {};             // peer mappings of every rank's mailbox ([rank] == mbox_local)
+    bool peer_opened[8] = {};
+    unsigned long long stamp_base = 0;     // advances identically on every rank
+    int *d_error = nullptr;                // device flag: a peer timed out
+    double *d_state = nullptr;             // NCCL baseline: [0..19] sums, [24..30] E, [32..38] T_icp, [40] done, [41] iter
+    void *nccl_lib = nullptr, *nccl_comm = nullptr;
+};
+
 struct limu_ctx {
     int device = 0;
     int sm_count = 0;
@@ -82,6 +94,7 @@ struct limu_ctx {
     void *h_pinned = nullptr;  // small pinned staging area for scalars / poses / counts
     size_t h_pinned_bytes = 0;
     limu::DevBuf d_small;      // small device staging area (poses, counts, partial sums)
+    limu_comm *comm = nullptr;
     // optional per-stage event timing (limu_ctx_set_profiling)
     bool profiling = false;
     cudaEvent_t ev[LIMU_NUM_STAGES][2] = {};

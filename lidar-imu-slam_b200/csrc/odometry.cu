@@ -13,7 +13,7 @@
 namespace limu {
 int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t n_max, const int *n_dev, const double *init_pose_dev,
                double tau, double th, int max_iter, double eps, double *partials_dev, size_t partial_rows, unsigned int *barrier_dev,
-               double *out13_dev, int64_t n_hint, double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev);
+               double *out13_dev, int64_t n_hint, double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev, int max_iter_all_ranks);
 int icp_partial_rows(limu_ctx *c);
 
 // theta = Eigen::AngleAxisd(model_dev.rotationMatrix()).angle() (threshold.cpp:7): quaternion -> matrix
@@ -126,7 +126,7 @@ static int odom_register_device(limu_odom *o, const double *frame_dev, int64_t n
     double *partials = o->partials.as<double>();
     unsigned int *barrier = reinterpret_cast<unsigned int *>(partials + (size_t)2 * rows * 20);
     LIMU_TRY(icp_device(o->map, o->src.as<double>(), o->work.as<double>(), n, cnt + 2, dinit, 3.0 * sigma, sigma / 3.0, o->cfg.icp_max_iteration,
-                        o->cfg.estimation_threshold, partials, (size_t)rows, barrier, out13, o->nk_hint, nullptr, nullptr, nullptr));
+                        o->cfg.estimation_threshold, partials, (size_t)rows, barrier, out13, o->nk_hint, nullptr, nullptr, nullptr, -1));
 
     // local_map.update(down_sampled, new_pose) (icp.cpp:81; voxel_hash_map.cpp:138-144)
     LIMU_TRY(map_maybe_grow(o->map, n));

@@ -21,6 +21,7 @@ namespace limu {
 
 constexpr int ICP_BLOCK = 256;
 constexpr int NS = 20;   // 16 sums + ncorr + ncand + nmiss + pad
+constexpr int MBOX_MAX_RANKS = 8, MBOX_ROW = 24;   // mailbox row: NS doubles + stamp + pad
 
 struct IcpArgs {
     MapView map;
@@ -38,6 +39,13 @@ struct IcpArgs {
     unsigned int *barrier;      // zeroed before launch
     double *out;                // [0..6] pose, [7] iterations, [8] converged, [9] ncorr, [10] ncand, [11] nmiss, [12] n
     int coop_scan;              // 1: sub-warp cooperative candidate scan (bandwidth shape); 0: one lane per query (latency shape)
+    // point-sharded multi-GPU: every rank owns a contiguous shard of the queries and a full replica of
+    // the map; per iteration the ranks exchange their NS-double row through peer-mapped mailboxes (NVLink stores).
+    int nranks, rank;
+    double *mbox_local;         // [2][MAX_RANKS][MBOX_ROW] in this rank's memory
+    double *mbox_peer[8];       // the same buffer of every rank (peer mappings; [rank] == mbox_local)
+    unsigned long long stamp_base;   // stamps of this call are stamp_base + iteration + 1 (monotonic across calls)
+    int *comm_error;            // set to 1 if a peer did not show up in time
     double *est_trace;          // optional [max_iter][7]
     long long *ncorr_trace;     // optional [max_iter]
     double *hg_trace;           // optional [max_iter][42]
@@ -167,6 +175,53 @@ __device__ __forceinline__ void coop_scan(const MapView &m, const V3 &s, int slo
     }
 }
 
+// One pass over this warp's share of the queries: transform, locate, scan, gate, weight, accumulate.
+__device__ __forceinline__ void icp_query_pass(const IcpArgs &A, const volatile double *Pv, const double *in, int64_t n, int64_t wbase, int64_t wstride,
+                                               int lane, double &acc, int &ncorr, int &ncand, int &nmiss) {
+    for (int64_t base = wbase; base < n; base += wstride) {
+        const int64_t q = base + lane;
+        const bool on = q < n;
+        V3 s{0.0, 0.0, 0.0};
+        int slot = -1, count = 0, own = 1;
+        if (on) {
+            // j == 0: source = init_guess * points (:102-103); later: source <- estimate * source (:119),
+            // applied lazily at the next visit
+            const Pose P{Pv[0], Pv[1], Pv[2], Pv[3], Pv[4], Pv[5], Pv[6]};
+            s = apply(P, V3{in[3 * q], in[3 * q + 1], in[3 * q + 2]});
+            A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z;
+            slot = map_locate(A.map, s, &count, &own);   // which voxel answers (own, else farthest/latest of the 27)
+        }
+        double my_d2 = 0.0;
+        int my_rank = -1;
+        if (A.coop_scan) {
+            if (A.map.cap <= 8) coop_scan<1>(A.map, s, slot, count, lane, my_d2, my_rank);
+            else if (A.map.cap <= 16) coop_scan<2>(A.map, s, slot, count, lane, my_d2, my_rank);
+            else if (A.map.cap <= 24) coop_scan<3>(A.map, s, slot, count, lane, my_d2, my_rank);
+            else coop_scan<0>(A.map, s, slot, count, lane, my_d2, my_rank);
+        } else if (slot >= 0) {
+            // latency shape (a few thousand keypoint queries): every lane scans its own voxel, one L2 round trip per
+            // four candidates instead of eight dependent group steps
+            Nearest nn;
+            block_closest(A.map, slot, count, s, nn);
+            my_rank = nn.rank;
+            my_d2 = sqnorm3(nn.x - s.x, nn.y - s.y, nn.z - s.z);
+        }
+        V3 tg{0.0, 0.0, 0.0};   // nothing found -> (0,0,0), range-tested like a real point (voxel_hash_map.cpp:98-99,118-124)
+        if (my_rank >= 0) {
+            const double *bx = voxel_rows(A.map, (unsigned int)slot);
+            tg = V3{__ldg(bx + my_rank), __ldg(bx + A.map.capp + my_rank), __ldg(bx + 2 * A.map.capp + my_rank)};
+        }
+        const double d2 = my_rank >= 0 ? my_d2 : sqnorm3(tg.x - s.x, tg.y - s.y, tg.z - s.z);   // (found - point).squaredNorm() :120
+        const bool gate = on && d2 < A.tau_sq;
+        double c[16];
+        contribution(c, s, tg, d2, A.th, gate);
+        acc += warp_reduce_scatter16(c);
+        ncorr += gate ? 1 : 0;
+        ncand += count;
+        nmiss += (on && !own) ? 1 : 0;
+    }
+}
+
 #ifdef LIMU_ICP_PHASE_TIMING
 #define PT_MARK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && A.hg_trace) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); A.hg_trace[42 * (size_t)j + (k)] = (double)_t; } } while (0)
 #else
@@ -200,48 +255,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_persistent(const Ic
         int ncorr = 0, ncand = 0, nmiss = 0;
         const volatile double *Pv = j == 0 ? Tinit : E;   // re-read per batch: keeps 14 registers free across the lookup
         const double *in = j == 0 ? A.points : A.work;
-        for (int64_t base = wbase; base < n; base += wstride) {
-            const int64_t q = base + lane;
-            const bool on = q < n;
-            V3 s{0.0, 0.0, 0.0};
-            int slot = -1, count = 0, own = 1;
-            if (on) {
-                // j == 0: source = init_guess * points (:102-103); later: source <- estimate * source (:119),
-                // applied lazily at the next visit
-                const Pose P{Pv[0], Pv[1], Pv[2], Pv[3], Pv[4], Pv[5], Pv[6]};
-                s = apply(P, V3{in[3 * q], in[3 * q + 1], in[3 * q + 2]});
-                A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z;
-                slot = map_locate(A.map, s, &count, &own);   // which voxel answers (own, else farthest/latest of the 27)
-            }
-            double my_d2 = 0.0;
-            int my_rank = -1;
-            if (A.coop_scan) {
-                if (A.map.cap <= 8) coop_scan<1>(A.map, s, slot, count, lane, my_d2, my_rank);
-                else if (A.map.cap <= 16) coop_scan<2>(A.map, s, slot, count, lane, my_d2, my_rank);
-                else if (A.map.cap <= 24) coop_scan<3>(A.map, s, slot, count, lane, my_d2, my_rank);
-                else coop_scan<0>(A.map, s, slot, count, lane, my_d2, my_rank);
-            } else if (slot >= 0) {
-                // latency shape (a few thousand keypoint queries): every lane scans its own voxel, one L2 round trip per
-                // four candidates instead of eight dependent group steps
-                Nearest nn;
-                block_closest(A.map, slot, count, s, nn);
-                my_rank = nn.rank;
-                my_d2 = sqnorm3(nn.x - s.x, nn.y - s.y, nn.z - s.z);
-            }
-            V3 tg{0.0, 0.0, 0.0};   // nothing found -> (0,0,0), range-tested like a real point (voxel_hash_map.cpp:98-99,118-124)
-            if (my_rank >= 0) {
-                const double *bx = voxel_rows(A.map, (unsigned int)slot);
-                tg = V3{__ldg(bx + my_rank), __ldg(bx + A.map.capp + my_rank), __ldg(bx + 2 * A.map.capp + my_rank)};
-            }
-            const double d2 = my_rank >= 0 ? my_d2 : sqnorm3(tg.x - s.x, tg.y - s.y, tg.z - s.z);   // (found - point).squaredNorm() :120
-            const bool gate = on && d2 < A.tau_sq;
-            double c[16];
-            contribution(c, s, tg, d2, A.th, gate);
-            acc += warp_reduce_scatter16(c);
-            ncorr += gate ? 1 : 0;
-            ncand += count;
-            nmiss += (on && !own) ? 1 : 0;
-        }
+        icp_query_pass(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
         PT_MARK(1);
         // CTA row: 16 sums (even lanes hold them) + 3 counters
         ncorr = __reduce_add_sync(0xFFFFFFFFu, ncorr);
@@ -285,6 +299,43 @@ static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_persistent(const Ic
             }
         }
         __syncthreads();
+        if (A.nranks > 1) {
+            // Fused exchange: CTA 0 stores this rank's row into EVERY rank's mailbox (its own included) over NVLink, then a
+            // system-scope release of the stamp; every CTA of every rank then waits for all stamps in its LOCAL mailbox and
+            // adds the rows in rank order -- the same order everywhere, so all ranks solve bit-identical normal equations
+            // and take identical convergence decisions. No host, no NCCL launch, no second grid barrier.
+            const unsigned long long stamp = A.stamp_base + (unsigned long long)j + 1ull;
+            const size_t par = (size_t)(j & 1) * MBOX_MAX_RANKS * MBOX_ROW;
+            if (blockIdx.x == 0) {
+                if (threadIdx.x < NS) {
+                    const double v = S[threadIdx.x];
+                    for (int r = 0; r < A.nranks; ++r) A.mbox_peer[r][par + (size_t)A.rank * MBOX_ROW + threadIdx.x] = v;
+                }
+                __threadfence_system();
+                __syncthreads();
+                if (threadIdx.x < A.nranks) {
+                    unsigned long long *flag = reinterpret_cast<unsigned long long *>(A.mbox_peer[threadIdx.x] + par + (size_t)A.rank * MBOX_ROW + NS);
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(stamp) : "memory");
+                }
+            }
+            if (threadIdx.x < A.nranks) {
+                const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(A.mbox_local + par + (size_t)threadIdx.x * MBOX_ROW + NS);
+                unsigned long long v, t0, t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                do {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 5000000000ull) { *A.comm_error = 1; break; }   // 5 s: a peer never arrived
+                } while (v != stamp);
+            }
+            __syncthreads();
+            if (threadIdx.x < NS) {
+                double v = 0.0;
+                for (int r = 0; r < A.nranks; ++r) v += *reinterpret_cast<const volatile double *>(A.mbox_local + par + (size_t)r * MBOX_ROW + threadIdx.x);
+                S[threadIdx.x] = v;
+            }
+            __syncthreads();
+        }
         PT_MARK(4);
         if (threadIdx.x == 0) {
             double H[36], g[6], x[6], lg[6];
@@ -360,7 +411,7 @@ static int g_icp_blocks_per_sm = 0;
 // Enqueue the persistent ICP kernel. All pointers are device memory; `out13` receives pose + stats.
 int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t n_max, const int *n_dev, const double *init_pose_dev,
                double tau, double th, int max_iter, double eps, double *partials_dev, size_t partial_rows, unsigned int *barrier_dev,
-               double *out13_dev, int64_t n_hint, double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev) {
+               double *out13_dev, int64_t n_hint, double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev, int max_iter_all_ranks) {
     limu_ctx *c = m->ctx;
     if (g_icp_blocks_per_sm == 0) {
         int b = 0;
@@ -378,6 +429,15 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
     A.partials = partials_dev; A.barrier = barrier_dev; A.out = out13_dev;
     A.est_trace = est_trace_dev; A.ncorr_trace = ncorr_trace_dev; A.hg_trace = hg_trace_dev;
     A.coop_scan = n_hint >= 32768 ? 1 : 0;
+    A.nranks = 1; A.rank = 0; A.mbox_local = nullptr; A.stamp_base = 0; A.comm_error = nullptr;
+    for (int r = 0; r < 8; ++r) A.mbox_peer[r] = nullptr;
+    if (max_iter_all_ranks >= 0 && c->comm && c->comm->nranks > 1) {   // point-sharded call: fused peer exchange
+        limu_comm *cm = c->comm;
+        A.nranks = cm->nranks; A.rank = cm->rank; A.mbox_local = cm->mbox_local; A.comm_error = cm->d_error;
+        for (int r = 0; r < cm->nranks; ++r) A.mbox_peer[r] = cm->mbox_peer[r];
+        A.stamp_base = cm->stamp_base;
+        cm->stamp_base += (unsigned long long)max_iter_all_ranks + 2ull;
+    }
     LIMU_CUDA_TRY(cudaMemsetAsync(barrier_dev, 0, sizeof(unsigned int), c->stream));
     void *args[] = {&A};
     LIMU_TRY(prof_begin(c, LIMU_STAGE_ICP));
@@ -389,12 +449,101 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
 
 int icp_partial_rows(limu_ctx *c) { return c->sm_count * 4; }
 
+// ---- un-fused baseline for the sharded loop: step kernel -> fold kernel -> ncclAllReduce -> solve kernel, host in the loop ----
+static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_step(const IcpArgs A, const double *state /* E at +24 */, int first, double *rows) {
+    __shared__ double red[(ICP_BLOCK / 32) * 32];
+    __shared__ double Pose7[7];
+    const int64_t n = A.n_max;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 7) Pose7[threadIdx.x] = first ? A.init_pose[threadIdx.x] : state[24 + threadIdx.x];
+    __syncthreads();
+    double acc = 0.0;
+    int ncorr = 0, ncand = 0, nmiss = 0;
+    const int64_t wbase = ((int64_t)blockIdx.x * (ICP_BLOCK / 32) + warp) * 32, wstride = (int64_t)gridDim.x * ICP_BLOCK;
+    icp_query_pass(A, Pose7, first ? A.points : A.work, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
+    ncorr = __reduce_add_sync(0xFFFFFFFFu, ncorr);
+    ncand = __reduce_add_sync(0xFFFFFFFFu, ncand);
+    nmiss = __reduce_add_sync(0xFFFFFFFFu, nmiss);
+    red[warp * 32 + lane] = (lane & 1) ? (lane == 1 ? (double)ncorr : lane == 3 ? (double)ncand : lane == 5 ? (double)nmiss : 0.0) : acc;
+    __syncthreads();
+    if (threadIdx.x < NS) {
+        const int src_lane = threadIdx.x < 16 ? 2 * threadIdx.x : 2 * (threadIdx.x - 16) + 1;
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < ICP_BLOCK / 32; ++w) v += red[w * 32 + src_lane];
+        rows[(size_t)blockIdx.x * NS + threadIdx.x] = v;
+    }
+}
+static __global__ void k_icp_fold_rows(const double *rows, int nblocks, double *sums) {
+    if (threadIdx.x < NS) {
+        double v = 0.0;
+        for (int b = 0; b < nblocks; ++b) v += rows[(size_t)b * NS + threadIdx.x];
+        sums[threadIdx.x] = v;
+    }
+}
+static __global__ void k_icp_solve_step(double *state, double eps, int first) {
+    if (threadIdx.x != 0) return;
+    double H[36], g[6], x[6], lg[6];
+    expand_normal_equations(state, H, g);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g[k] = -g[k];
+    ldlt6_solve(H, g, x);
+    const Pose est = se3_exp(x);
+    const Pose Ticp = first ? pose_identity() : pose_load(state + 32);
+    pose_store(mul(est, Ticp), state + 32);
+    pose_store(est, state + 24);
+    se3_log(est, lg);
+    state[40] = norm6(lg) < eps ? 1.0 : 0.0;
+    state[41] = first ? 1.0 : state[41] + 1.0;
+}
+
+typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+int comm_nccl_allreduce_sum_f64(limu_ctx *c, double *buf, size_t count);   // comm.cu
+
+static int icp_sharded_nccl(limu_map *m, const double *points_dev, int64_t n, const double init_guess[7], double tau, double th, int max_iter,
+                            double eps, double pose_out[7], limu_icp_stats *stats) {
+    limu_ctx *c = m->ctx;
+    limu_comm *cm = c->comm;
+    double *dinit;
+    LIMU_TRY(stage_small(c, init_guess, 7, 0, &dinit));
+    const int rows = icp_partial_rows(c);
+    LIMU_TRY(c->tmp4.reserve((size_t)std::max<int64_t>(n, 1) * 24, c->stream));
+    LIMU_TRY(c->tmp5.reserve((size_t)rows * NS * 8 + 256, c->stream));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(div_up(std::max<int64_t>(n, 1), ICP_BLOCK), rows));
+    IcpArgs A;
+    memset(&A, 0, sizeof A);
+    A.map = m->view(); A.points = points_dev; A.work = c->tmp4.as<double>(); A.n_max = n; A.init_pose = dinit;
+    A.tau_sq = tau * tau; A.th = th; A.coop_scan = n >= 32768 ? 1 : 0; A.nranks = 1;
+    double *state = cm->d_state;
+    double *h = static_cast<double *>(c->h_pinned) + 256;
+    int64_t nv = 0;
+    LIMU_TRY(limu_map_size(m, &nv, nullptr));
+    if (nv == 0 || max_iter <= 0) { for (int k = 0; k < 7; ++k) pose_out[k] = init_guess[k]; if (stats) memset(stats, 0, sizeof *stats); return LIMU_OK; }
+    int j = 0, done = 0;
+    for (; j < max_iter && !done; ++j) {
+        k_icp_step<<<grid, ICP_BLOCK, 0, c->stream>>>(A, state, j == 0 ? 1 : 0, c->tmp5.as<double>());
+        LIMU_LAUNCHED();
+        k_icp_fold_rows<<<1, 32, 0, c->stream>>>(c->tmp5.as<double>(), grid, state);
+        LIMU_LAUNCHED();
+        LIMU_TRY(comm_nccl_allreduce_sum_f64(c, state, NS));
+        k_icp_solve_step<<<1, 32, 0, c->stream>>>(state, eps, j == 0 ? 1 : 0);
+        LIMU_LAUNCHED();
+        LIMU_CUDA_TRY(cudaMemcpyAsync(h, state, 48 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        done = h[40] != 0.0;
+    }
+    const Pose out = mul(pose_load(h + 32), pose_load(init_guess));
+    pose_store(out, pose_out);
+    if (stats) { stats->iterations = j; stats->converged = done; stats->last_ncorr = (int64_t)h[16]; stats->mean_candidates = h[17]; stats->miss_fraction = h[18]; }
+    return check_status(c);
+}
+
 }  // namespace limu
 
 using namespace limu;
 
 static int icp_common(limu_map *m, const double *points_dev, int64_t n, const double init_guess[7], double tau, double th, int max_iter, double eps,
-                      double pose_out[7], limu_icp_stats *stats, double *est_trace, int64_t *ncorr_trace, double *hg_trace) {
+                      double pose_out[7], limu_icp_stats *stats, double *est_trace, int64_t *ncorr_trace, double *hg_trace, bool sharded = false) {
     limu_ctx *c = m->ctx;
     double *dinit;
     LIMU_TRY(stage_small(c, init_guess, 7, 0, &dinit));
@@ -411,16 +560,21 @@ static int icp_common(limu_map *m, const double *points_dev, int64_t n, const do
     long long *d_nc = tr ? reinterpret_cast<long long *>(d_est + it * 7) : nullptr;
     double *d_hg = tr ? d_est + it * 8 : nullptr;
     LIMU_TRY(icp_device(m, points_dev, c->tmp4.as<double>(), n, nullptr, dinit, tau, th, max_iter, eps, partials, (size_t)rows, barrier, out13, n,
-                        d_est, d_nc, d_hg));
+                        d_est, d_nc, d_hg, sharded ? max_iter : -1));
     double *h = static_cast<double *>(c->h_pinned) + 16;
     LIMU_CUDA_TRY(cudaMemcpyAsync(h, out13, 13 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < 7; ++k) pose_out[k] = h[k];
     const int iters = (int)h[7];
-    if (stats) {
+    if (stats) {   // in a sharded call the counters are global sums; the caller divides by the global query count
         stats->iterations = iters; stats->converged = (int)h[8]; stats->last_ncorr = (int64_t)h[9];
-        stats->mean_candidates = n > 0 ? h[10] / (double)n : 0.0;
-        stats->miss_fraction = n > 0 ? h[11] / (double)n : 0.0;
+        stats->mean_candidates = sharded ? h[10] : (n > 0 ? h[10] / (double)n : 0.0);
+        stats->miss_fraction = sharded ? h[11] : (n > 0 ? h[11] / (double)n : 0.0);
+    }
+    if (sharded && c->comm && c->comm->nranks > 1) {
+        int err = 0;
+        LIMU_CUDA_TRY(cudaMemcpy(&err, c->comm->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) { set_error("limu_icp_sharded: a peer rank did not reach the exchange within 5 s"); cudaMemset(c->comm->d_error, 0, sizeof(int)); return LIMU_ERR_COMM; }
     }
     if (tr && iters > 0) {
         if (est_trace) LIMU_CUDA_TRY(cudaMemcpyAsync(est_trace, d_est, (size_t)iters * 56, cudaMemcpyDeviceToHost, c->stream));
@@ -446,6 +600,18 @@ int limu_icp_dev(limu_map *m, const double *xyz_dev, int64_t n, const double ini
     LIMU_REQUIRE(m && init_guess && pose_out && n >= 0 && (n == 0 || xyz_dev), "limu_icp_dev: bad arguments");
     LIMU_TRY(bind(m->ctx));
     return icp_common(m, xyz_dev, n, init_guess, max_corresp_dist, kernel, icp_max_iteration, est_threshold, pose_out, stats, nullptr, nullptr, nullptr);
+}
+
+int limu_icp_sharded_dev(limu_map *m, const double *xyz_dev, int64_t n_local, const double init_guess[7], double max_corresp_dist, double kernel,
+                         int icp_max_iteration, double est_threshold, int mode, double pose_out[7], limu_icp_stats *stats) {
+    LIMU_REQUIRE(m && init_guess && pose_out && n_local >= 0 && (n_local == 0 || xyz_dev), "limu_icp_sharded_dev: bad arguments");
+    LIMU_TRY(bind(m->ctx));
+    LIMU_REQUIRE(m->ctx->comm, "limu_icp_sharded_dev: call limu_comm_create / limu_comm_connect first");
+    if (mode == LIMU_SHARD_NCCL) {
+        LIMU_REQUIRE(m->ctx->comm->nccl_comm, "limu_icp_sharded_dev: NCCL baseline requested but limu_comm_nccl_init was not called");
+        return icp_sharded_nccl(m, xyz_dev, n_local, init_guess, max_corresp_dist, kernel, icp_max_iteration, est_threshold, pose_out, stats);
+    }
+    return icp_common(m, xyz_dev, n_local, init_guess, max_corresp_dist, kernel, icp_max_iteration, est_threshold, pose_out, stats, nullptr, nullptr, nullptr, true);
 }
 
 int limu_align(limu_ctx *c, const double *src, const double *tgt, int64_t n, double th, double H[36], double g[6], double x[6], double pose_out[7]) {
