@@ -1,0 +1,15 @@
+// frame_fusion.cuh -- what the odometry pipeline asks the persistent registration kernel to do around the ICP loop.
+#pragma once
+namespace limu {
+struct FrameFusion {
+    const double *iqr_in;      // src0 after the two downsampling stages (nullptr: no IQR prologue)
+    const int *iqr_n;
+    double *iqr_d2, *iqr_out;
+    int *iqr_count;
+    const double *upd_down;    // downsampled scan, sensor frame (nullptr: no map-update epilogue)
+    const int *upd_n;
+    double *upd_world;
+    unsigned int *upd_pslot;
+    unsigned long long upd_birth_base;
+};
+}  // namespace limu

@@ -7,13 +7,14 @@
 #include <algorithm>
 #include <vector>
 
+#include "frame_fusion.cuh"
 #include "ops.cuh"
 #include "voxel_map.cuh"
 
 namespace limu {
 int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t n_max, const int *n_dev, const double *init_pose_dev,
-               double tau, double th, int max_iter, double eps, double *partials_dev, size_t partial_rows, unsigned int *barrier_dev,
-               double *out13_dev, int64_t n_hint, double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev, int max_iter_all_ranks);
+               double tau, double th, int max_iter, double eps, double *partials_dev, size_t partial_rows, double *out13_dev, int64_t n_hint,
+               double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev, int max_iter_all_ranks, const FrameFusion *fuse);
 int icp_partial_rows(limu_ctx *c);
 
 // theta = Eigen::AngleAxisd(model_dev.rotationMatrix()).angle() (threshold.cpp:7): quaternion -> matrix
@@ -56,9 +57,10 @@ struct limu_odom {
     int num_samples = 0;
     limu::Pose model_deviation = limu::pose_identity();
     // device buffers
-    limu::DevBuf raw, ts, frame, down, src0, src, work, world, partials;
+    limu::DevBuf raw, ts, frame, down, src0, src, work, world, partials, d2;
     limu::StageScratch sa, sb;
-    int64_t nk_hint = 4096;
+    limu::VoxelizeScratch vx;
+    int64_t nk_hint = 4096, nd_hint = 16384;
 };
 
 using namespace limu;
@@ -88,10 +90,21 @@ static Pose odom_prediction(const limu_odom *o) {   // icp.cpp:146-154
 }
 
 // Everything after the scan is in device memory as doubles (frame_dev, n points).
-static int odom_register_device(limu_odom *o, const double *frame_dev, int64_t n, int deskewed, double pose_out[7], double *down_xyz,
+// Input already in device memory. mode 0: float4 {x,y,z,t}; 1: records `stride` bytes apart + FP64 timestamps; 2: double xyz.
+static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int stride, const double *ts_dev, int64_t n, double pose_out[7], double *down_xyz,
                                 int64_t *n_down, double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
     limu_ctx *c = o->ctx;
     const size_t nb = (size_t)std::max<int64_t>(n, 1) * 24;
+    LIMU_TRY(o->frame.reserve(nb, c->stream));
+    // deskew gate (icp.cpp:40-46): config.deskew && poses.size() > 2; twist = delta_pose(poses[N-2], poses[N-1]) (deskew.cpp:14)
+    const size_t NP = o->poses.size();
+    const int deskewed = (mode != 2 && o->cfg.deskew && NP > 2) ? 1 : 0;
+    double *dtw = nullptr;
+    if (deskewed) {
+        double twist[6];
+        se3_log(mul(inverse(o->poses[NP - 2]), o->poses[NP - 1]), twist);
+        LIMU_TRY(stage_small(c, twist, 6, 0, &dtw));
+    }
     LIMU_TRY(o->down.reserve(nb, c->stream));
     LIMU_TRY(o->src0.reserve(nb, c->stream));
     LIMU_TRY(o->src.reserve(nb, c->stream));
@@ -103,15 +116,10 @@ static int odom_register_device(limu_odom *o, const double *frame_dev, int64_t n
     double *out13 = c->d_small.as<double>() + 40;
     const double v = o->cfg.voxel_size;
 
-    // voxelize (icp.cpp:126-136)
+    // deskew_scan + voxelize's two downsampling stages (icp.cpp:36-47, :126-131): one cooperative launch
     LIMU_TRY(prof_begin(c, LIMU_STAGE_DOWNSAMPLE));
-    LIMU_TRY(downsample_device(c, o->sa, frame_dev, n, nullptr, v * 0.5, o->down.as<double>(), cnt + 0));
-    LIMU_TRY(downsample_device(c, o->sb, o->down.as<double>(), n, cnt + 0, v * 1.5, o->src0.as<double>(), cnt + 1));
+    LIMU_TRY(voxelize_device(c, o->vx, raw_dev, mode, stride, ts_dev, deskewed, dtw, n, v, o->frame.as<double>(), o->down.as<double>(), o->src0.as<double>(), cnt + 0));
     LIMU_TRY(prof_end(c, LIMU_STAGE_DOWNSAMPLE));
-    LIMU_TRY(prof_begin(c, LIMU_STAGE_IQR));
-    LIMU_TRY(iqr_device(c, o->sb, o->src0.as<double>(), n, cnt + 1, o->src.as<double>(), cnt + 2, nullptr));
-    LIMU_TRY(prof_end(c, LIMU_STAGE_IQR));
-
     // host scalar glue (icp.cpp:66-71)
     const double sigma = odom_adaptive_threshold(o);
     const Pose pred = odom_prediction(o);
@@ -122,20 +130,19 @@ static int odom_register_device(limu_odom *o, const double *frame_dev, int64_t n
     double *dinit;
     LIMU_TRY(stage_small(c, init7, 7, 8, &dinit));
 
-    // ICP (icp.cpp:74-76)
-    double *partials = o->partials.as<double>();
-    unsigned int *barrier = reinterpret_cast<unsigned int *>(partials + (size_t)2 * rows * 20);
-    LIMU_TRY(icp_device(o->map, o->src.as<double>(), o->work.as<double>(), n, cnt + 2, dinit, 3.0 * sigma, sigma / 3.0, o->cfg.icp_max_iteration,
-                        o->cfg.estimation_threshold, partials, (size_t)rows, barrier, out13, o->nk_hint, nullptr, nullptr, nullptr, -1));
-
-    // local_map.update(down_sampled, new_pose) (icp.cpp:81; voxel_hash_map.cpp:138-144)
+    // iqr_processing (icp.cpp:133) + ICP (icp.cpp:74-76) + local_map.update(down_sampled, new_pose) (icp.cpp:81;
+    // voxel_hash_map.cpp:138-144): ONE persistent cooperative launch (registration.cu)
     LIMU_TRY(map_maybe_grow(o->map, n));
-    LIMU_TRY(prof_begin(c, LIMU_STAGE_MAP_UPDATE));
-    LIMU_TRY(transform_device(c, out13, o->down.as<double>(), o->world.as<double>(), n, cnt + 0));
+    LIMU_TRY(o->map->pslot.reserve((size_t)std::max<int64_t>(n, 1) * 4, c->stream));
+    LIMU_TRY(o->d2.reserve((size_t)std::max<int64_t>(n, 1) * 8, c->stream));
+    FrameFusion fuse;
+    fuse.iqr_in = o->src0.as<double>(); fuse.iqr_n = cnt + 1; fuse.iqr_d2 = o->d2.as<double>(); fuse.iqr_out = o->src.as<double>(); fuse.iqr_count = cnt + 2;
+    fuse.upd_down = o->down.as<double>(); fuse.upd_n = cnt + 0; fuse.upd_world = o->world.as<double>(); fuse.upd_pslot = o->map->pslot.as<unsigned int>();
+    fuse.upd_birth_base = o->map->birth_base;
     const int64_t upper_before = o->map->used_upper;
-    LIMU_TRY(map_insert_device(o->map, o->world.as<double>(), n, cnt + 0));
-    LIMU_TRY(map_remove_far_device(o->map, out13 + 4));
-    LIMU_TRY(prof_end(c, LIMU_STAGE_MAP_UPDATE));
+    LIMU_TRY(icp_device(o->map, o->src.as<double>(), o->work.as<double>(), n, cnt + 2, dinit, 3.0 * sigma, sigma / 3.0, o->cfg.icp_max_iteration,
+                        o->cfg.estimation_threshold, o->partials.as<double>(), (size_t)rows, out13, o->nk_hint, nullptr, nullptr, nullptr, -1, &fuse));
+    o->map->birth_base += (uint64_t)n;
 
     // the one synchronisation of the scan
     double *h = static_cast<double *>(c->h_pinned) + 32;
@@ -148,6 +155,7 @@ static int odom_register_device(limu_odom *o, const double *frame_dev, int64_t n
     const Pose new_pose = pose_load(ho);
     o->map->used_upper = upper_before + nd;   // exact: at most one new voxel per inserted point
     o->nk_hint = std::max<int64_t>(nk, 256);
+    o->nd_hint = std::max<int64_t>(nd, 256);
 
     o->model_deviation = mul(inverse(init), new_pose);   // icp.cpp:78-79
     o->poses.push_back(new_pose);                        // :82
@@ -164,32 +172,6 @@ static int odom_register_device(limu_odom *o, const double *frame_dev, int64_t n
         stats->icp.mean_candidates = nk > 0 ? ho[10] / (double)nk : 0.0;
         stats->icp.miss_fraction = nk > 0 ? ho[11] / (double)nk : 0.0;
     }
-    return LIMU_OK;
-}
-
-// deskew gate + widening (icp.cpp:36-47) on a raw scan already in device memory.
-// stride == 0: packed float4 {x,y,z,t}; otherwise records `stride` bytes apart + FP64 timestamps.
-static int odom_prepare_frame(limu_odom *o, const void *rec_dev, int stride, const double *ts_dev, int64_t n, int *deskewed) {
-    const float *xyzt_dev = static_cast<const float *>(rec_dev);
-    limu_ctx *c = o->ctx;
-    LIMU_TRY(o->frame.reserve((size_t)std::max<int64_t>(n, 1) * 24, c->stream));
-    const size_t N = o->poses.size();
-    if (o->cfg.deskew && N > 2) {
-        double twist[6];
-        se3_log(mul(inverse(o->poses[N - 2]), o->poses[N - 1]), twist);   // delta_pose(start, end) deskew.cpp:14
-        double *dtw;
-        LIMU_TRY(stage_small(c, twist, 6, 0, &dtw));
-        LIMU_TRY(prof_begin(c, LIMU_STAGE_PREPARE));
-        if (stride == 0) LIMU_TRY(deskew_device(c, xyzt_dev, n, dtw, o->frame.as<double>()));
-        else LIMU_TRY(deskew_records_device(c, rec_dev, stride, ts_dev, n, dtw, o->frame.as<double>()));
-        *deskewed = 1;
-    } else {
-        LIMU_TRY(prof_begin(c, LIMU_STAGE_PREPARE));
-        if (stride == 0) LIMU_TRY(widen_device(c, xyzt_dev, n, o->frame.as<double>()));
-        else LIMU_TRY(widen_records_device(c, rec_dev, stride, n, o->frame.as<double>()));
-        *deskewed = 0;
-    }
-    LIMU_TRY(prof_end(c, LIMU_STAGE_PREPARE));
     return LIMU_OK;
 }
 
@@ -231,9 +213,9 @@ void limu_odom_destroy(limu_odom *o) {
     cudaSetDevice(o->ctx->device);
     cudaStreamSynchronize(o->ctx->stream);
     limu_map_destroy(o->map);
-    DevBuf *bufs[] = {&o->raw, &o->ts, &o->frame, &o->down, &o->src0, &o->src, &o->work, &o->world, &o->partials};
+    DevBuf *bufs[] = {&o->d2, &o->raw, &o->ts, &o->frame, &o->down, &o->src0, &o->src, &o->work, &o->world, &o->partials};
     for (auto *b : bufs) b->release();
-    o->sa.release(); o->sb.release();
+    o->sa.release(); o->sb.release(); o->vx.release();
     delete o;
 }
 
@@ -242,9 +224,7 @@ int limu_odom_register_frame(limu_odom *o, const float *xyzt, int64_t n, double 
     LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyzt), "limu_odom_register_frame: bad arguments");
     LIMU_TRY(bind(o->ctx));
     LIMU_TRY(stage_in(o->ctx, o->raw, xyzt, (size_t)n * 16));
-    int deskewed = 0;
-    LIMU_TRY(odom_prepare_frame(o, o->raw.p, 0, nullptr, n, &deskewed));
-    return odom_register_device(o, o->frame.as<double>(), n, deskewed, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+    return odom_register_device(o, o->raw.p, 0, 0, nullptr, n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
 }
 
 int limu_odom_register_cloud(limu_odom *o, const void *points, int32_t stride_bytes, const double *timestamps, int64_t n, double pose_out[7],
@@ -253,25 +233,21 @@ int limu_odom_register_cloud(limu_odom *o, const void *points, int32_t stride_by
     LIMU_TRY(bind(o->ctx));
     LIMU_TRY(stage_in(o->ctx, o->raw, points, (size_t)n * stride_bytes));
     LIMU_TRY(stage_in(o->ctx, o->ts, timestamps, (size_t)n * 8));
-    int deskewed = 0;
-    LIMU_TRY(odom_prepare_frame(o, o->raw.p, stride_bytes, o->ts.as<double>(), n, &deskewed));
-    return odom_register_device(o, o->frame.as<double>(), n, deskewed, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+    return odom_register_device(o, o->raw.p, 1, stride_bytes, o->ts.as<double>(), n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
 }
 
 int limu_odom_register_frame_dev(limu_odom *o, const float *xyzt_dev, int64_t n, double pose_out[7], limu_frame_stats *stats) {
     LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyzt_dev), "limu_odom_register_frame_dev: bad arguments");
     LIMU_TRY(bind(o->ctx));
-    int deskewed = 0;
-    LIMU_TRY(odom_prepare_frame(o, xyzt_dev, 0, nullptr, n, &deskewed));
-    return odom_register_device(o, o->frame.as<double>(), n, deskewed, pose_out, nullptr, nullptr, nullptr, nullptr, stats);
+    return odom_register_device(o, xyzt_dev, 0, 0, nullptr, n, pose_out, nullptr, nullptr, nullptr, nullptr, stats);
 }
 
 int limu_odom_register_points(limu_odom *o, const double *xyz, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down,
                               double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
     LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyz), "limu_odom_register_points: bad arguments");
     LIMU_TRY(bind(o->ctx));
-    LIMU_TRY(stage_in(o->ctx, o->frame, xyz, (size_t)n * 24));
-    return odom_register_device(o, o->frame.as<double>(), n, 0, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+    LIMU_TRY(stage_in(o->ctx, o->raw, xyz, (size_t)n * 24));
+    return odom_register_device(o, o->raw.p, 2, 0, nullptr, n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
 }
 
 int limu_odom_num_poses(limu_odom *o, int64_t *n) {

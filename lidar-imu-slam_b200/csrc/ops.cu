@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "compact.cuh"
+#include "iqr.cuh"
 #include "ops.cuh"
 #include "voxel_map.cuh"
 
@@ -107,93 +108,10 @@ static __global__ void __launch_bounds__(256) k_ds_flag(int64_t n_max, const int
     flags[i] = (s != PEND_NONE && minidx[s] == (unsigned int)i) ? 1 : 0;
 }
 
-// KissICP::iqr_processing (icp.cpp:88-124) in ONE CTA of 1024 threads (keypoint clouds are 1e3..1e5
-// points): squared ranges, the <= 4 order statistics outlier::IQR needs (common.hpp:40-63: medians of
-// the lower and upper halves of the sorted ranges) by an 8-pass MSB radix select over the IEEE bit
-// patterns (non-negative doubles order like unsigned integers), Tukey bounds with IQR_TUCHEY = 1.25
-// (common.hpp:15), then an order-preserving compaction of the inliers.
 static __global__ void __launch_bounds__(1024) k_iqr(const double *__restrict__ xyz, int64_t n_max, const int *n_dev, double *__restrict__ d2,
                                                    double *__restrict__ out, int *out_count, double *bounds) {
-    __shared__ int hist[4][256];
-    __shared__ unsigned long long prefix[4];
-    __shared__ int rank[4];
-    __shared__ int ws[32];
-    __shared__ int total;
-    const int n = (int)(n_dev ? (int64_t)*n_dev : n_max);
-    const int tid = threadIdx.x;
-    if (n <= 0) { if (tid == 0) *out_count = 0; return; }
-    for (int i = tid; i < n; i += 1024) {
-        const double x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
-        d2[i] = x * x + y * y + z * z;   // icp.cpp:97-100
-    }
-    double q1, q3, iqr;
-    const int half = n / 2, m = half, u0 = half + n % 2;
-    if (n == 1) {
-        __syncthreads();
-        q1 = 0.0; q3 = d2[0]; iqr = d2[0];   // common.hpp:49-52
-    } else {
-        if (tid < 4) {
-            const int lo = (m % 2 == 0) ? m / 2 - 1 : m / 2, hi = m / 2;   // median(): common.hpp:22-38
-            rank[tid] = (tid & 1 ? hi : lo) + (tid >= 2 ? u0 : 0);
-            prefix[tid] = 0ull;
-        }
-        for (int pass = 0; pass < 8; ++pass) {
-            const int shift = 56 - 8 * pass;
-            for (int b = tid; b < 4 * 256; b += 1024) (&hist[0][0])[b] = 0;
-            __syncthreads();
-            for (int i = tid; i < n; i += 1024) {
-                const unsigned long long bits = (unsigned long long)__double_as_longlong(d2[i]);
-                const unsigned long long hi_bits = pass == 0 ? 0ull : (bits >> (shift + 8));
-                const int digit = (int)((bits >> shift) & 0xFF);
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    if (hi_bits == prefix[t]) atomicAdd(&hist[t][digit], 1);
-            }
-            __syncthreads();
-            const int warp = tid >> 5, lane = tid & 31;
-            if (warp < 4) {
-                int c[8], sum = 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) { c[k] = hist[warp][lane * 8 + k]; sum += c[k]; }
-                int incl = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
-                int cum = incl - sum;
-                const int r = rank[warp];
-                __syncwarp();
-                if (r >= cum && r < incl) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        if (r < cum + c[k]) { prefix[warp] = (prefix[warp] << 8) | (unsigned long long)(lane * 8 + k); rank[warp] = r - cum; break; }
-                        cum += c[k];
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        const double v0 = __longlong_as_double((long long)prefix[0]), v1 = __longlong_as_double((long long)prefix[1]);
-        const double v2 = __longlong_as_double((long long)prefix[2]), v3 = __longlong_as_double((long long)prefix[3]);
-        q1 = (m % 2 == 0) ? (v0 + v1) / 2.0 : v1;
-        q3 = (m % 2 == 0) ? (v2 + v3) / 2.0 : v3;
-        iqr = q3 - q1;
-    }
-    const double low = q1 - 1.25 * iqr, high = q3 + 1.25 * iqr;   // icp.cpp:104-105
-    if (tid == 0 && bounds) { bounds[0] = low; bounds[1] = high; }
-    int base = 0;
-    for (int start = 0; start < n; start += 1024) {
-        const int i = start + tid;
-        const double d = i < n ? d2[i] : 0.0;
-        const int f = i < n && d >= low && d <= high;   // icp.cpp:117
-        const int r = block_exclusive_scan_flag(f, &total, ws);
-        if (f) {
-            out[3 * (size_t)(base + r)] = xyz[3 * (size_t)i];
-            out[3 * (size_t)(base + r) + 1] = xyz[3 * (size_t)i + 1];
-            out[3 * (size_t)(base + r) + 2] = xyz[3 * (size_t)i + 2];
-        }
-        base += total;
-        __syncthreads();
-    }
-    if (tid == 0) *out_count = base;
+    __shared__ IqrSmem sm;
+    iqr_block<1024>(sm, xyz, (int)(n_dev ? (int64_t)*n_dev : n_max), d2, out, out_count, bounds);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -17,6 +17,16 @@ struct StageScratch {
     void release() { table.release(); pslot.release(); flags.release(); blockcnt.release(); idx.release(); d2.release(); }
 };
 
+// Scratch of the fused deskew + two-stage downsample kernel (voxelize.cu).
+struct VoxelizeScratch {
+    DevBuf table, pslot, tiles;
+    void release() { table.release(); pslot.release(); tiles.release(); }
+};
+// KissICP::deskew_scan + the two voxel_downsample stages of KissICP::voxelize in one cooperative launch.
+// mode 0: raw = float4 {x,y,z,t}; 1: records `stride` bytes apart + FP64 ts; 2: double xyz (register_frame(Vec3dVector)).
+int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int mode, int stride, const double *ts_dev, int deskew, const double *twist_dev,
+                    int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev);
+
 // deskew.cpp:10-28. twist_dev: 6 doubles (device). out: n x 3 doubles.
 int deskew_device(limu_ctx *c, const float *xyzt_dev, int64_t n, const double *twist_dev, double *out_dev);
 // the same for strided point records + FP64 timestamps (the reference's PCL cloud + std::vector<double>)

@@ -15,6 +15,8 @@
 #include <algorithm>
 #include <vector>
 
+#include "grid_sync.cuh"
+#include "iqr.cuh"
 #include "voxel_map.cuh"
 
 namespace limu {
@@ -22,6 +24,10 @@ namespace limu {
 constexpr int ICP_BLOCK = 256;
 constexpr int NS = 20;   // 16 sums + ncorr + ncand + nmiss + pad
 constexpr int MBOX_MAX_RANKS = 8, MBOX_ROW = 24;   // mailbox row: NS doubles + stamp + pad
+
+}  // namespace limu
+#include "frame_fusion.cuh"
+namespace limu {
 
 struct IcpArgs {
     MapView map;
@@ -38,6 +44,7 @@ struct IcpArgs {
     double *partials;           // [2][gridDim][NS]
     unsigned int *barrier;      // zeroed before launch
     double *out;                // [0..6] pose, [7] iterations, [8] converged, [9] ncorr, [10] ncand, [11] nmiss, [12] n
+    int grouped;                // 1: eight lanes per query (latency shape: a few thousand keypoints)
     int coop_scan;              // 1: sub-warp cooperative candidate scan (bandwidth shape); 0: one lane per query (latency shape)
     // point-sharded multi-GPU: every rank owns a contiguous shard of the queries and a full replica of
     // the map; per iteration the ranks exchange their NS-double row through peer-mapped mailboxes (NVLink stores).
@@ -46,23 +53,28 @@ struct IcpArgs {
     double *mbox_peer[8];       // the same buffer of every rank (peer mappings; [rank] == mbox_local)
     unsigned long long stamp_base;   // stamps of this call are stamp_base + iteration + 1 (monotonic across calls)
     int *comm_error;            // set to 1 if a peer did not show up in time
+    // ---- fused frame mode (odometry.cu): optional IQR prologue and local_map.update epilogue in the same launch ----
+    const double *iqr_in;       // src0 (after the two downsampling stages); nullptr = no prologue
+    const int *iqr_n;           // its count (device)
+    double *iqr_d2;             // scratch, one double per point
+    double *iqr_out;            // filtered keypoints (== points); count written to iqr_count
+    int *iqr_count;
+    const double *upd_down;     // downsampled scan (sensor frame); nullptr = no epilogue
+    const int *upd_n;           // its count (device)
+    double *upd_world;          // transformed copy
+    unsigned int *upd_pslot;
+    unsigned long long *upd_counters;   // map counters (writable)
+    unsigned long long upd_birth_base;
+    long long upd_capacity;     // C
+    double upd_max_distance;
+    DevStatus *status;
+    unsigned int *exit_count;   // last CTA out resets the barrier words (no memset per launch)
+    unsigned int *barrier_icp;  // barrier of the leading `icp_blocks` CTAs that run the Gauss-Newton loop
+    int icp_blocks;
     double *est_trace;          // optional [max_iter][7]
     long long *ncorr_trace;     // optional [max_iter]
     double *hg_trace;           // optional [max_iter][42]
 };
-
-__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
-        unsigned int v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-        } while (v < target);
-    }
-    __syncthreads();
-}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -222,10 +234,49 @@ __device__ __forceinline__ void icp_query_pass(const IcpArgs &A, const volatile 
     }
 }
 
+// The same pass in the latency shape: eight lanes per query (four queries per warp), see group8_closest.
+__device__ __forceinline__ void icp_query_pass_grouped(const IcpArgs &A, const volatile double *Pv, const double *in, int64_t n, int64_t gbase, int64_t gstride,
+                                                       int lane, double &acc, int &ncorr, int &ncand, int &nmiss) {
+    const int l8 = lane & 7;
+    const unsigned gmask = 0xFFu << (lane & 24);
+    const int64_t wfirst = gbase - (lane >> 3);   // first group of this warp: the four groups of a warp iterate together
+    for (int64_t q0 = wfirst; q0 < n; q0 += gstride) {
+        const int64_t q = q0 + (lane >> 3);
+        const bool on = q < n;
+        V3 s{0.0, 0.0, 0.0}, tg{0.0, 0.0, 0.0};
+        int slot = -1, count = 0, own = 1, my_rank = -1;
+        double d2 = 0.0;
+        if (on) {
+            const Pose P{Pv[0], Pv[1], Pv[2], Pv[3], Pv[4], Pv[5], Pv[6]};
+            s = apply(P, V3{in[3 * q], in[3 * q + 1], in[3 * q + 2]});
+            if (l8 == 0) { A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z; }
+            group8_closest(A.map, s, gmask, l8, slot, count, own, d2, my_rank);
+            if (my_rank >= 0) {
+                const double *bx = voxel_rows(A.map, (unsigned int)slot);
+                tg = V3{__ldg(bx + my_rank), __ldg(bx + A.map.capp + my_rank), __ldg(bx + 2 * A.map.capp + my_rank)};
+            } else {
+                d2 = sqnorm3(tg.x - s.x, tg.y - s.y, tg.z - s.z);   // nothing found -> (0,0,0), range-tested like a real point
+            }
+        }
+        const bool lead = on && l8 == 0;
+        const bool gate = lead && d2 < A.tau_sq;
+        double c[16];
+        contribution(c, s, tg, d2, A.th, gate);
+        acc += warp_reduce_scatter16(c);
+        ncorr += gate ? 1 : 0;
+        ncand += lead ? count : 0;
+        nmiss += (lead && !own) ? 1 : 0;
+    }
+}
+
 #ifdef LIMU_ICP_PHASE_TIMING
+// developer build only (tools/icp_phase_timing.py, tools/frame_phase_timing.py): %globaltimer stamps of CTA 0 / thread 0
+__device__ unsigned long long g_frame_marks[16];
+#define FT_MARK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_frame_marks[k] = _t; } } while (0)
 #define PT_MARK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && A.hg_trace) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); A.hg_trace[42 * (size_t)j + (k)] = (double)_t; } } while (0)
 #else
 #define PT_MARK(k) do {} while (0)
+#define FT_MARK(k) do {} while (0)
 #endif
 
 static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_persistent(const IcpArgs A) {
@@ -233,29 +284,33 @@ static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_persistent(const Ic
     __shared__ double S[NS];
     __shared__ double E[7], Tinit[7], Ticp[7];
     __shared__ int done;
-    const int64_t n = A.n_dev ? (int64_t)*A.n_dev : A.n_max;
+    __shared__ IqrSmem iqr_sm;
+    GridSync gs{A.barrier, 0u, gridDim.x};
+    GridSync gs_icp{A.barrier_icp, 0u, (unsigned int)A.icp_blocks};
+    const bool icp_member = (int)blockIdx.x < A.icp_blocks;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (A.map_counters[0] == 0ull || A.max_iter <= 0) {   // ICP :99-100 (and a zero-iteration loop returns T_icp * init = init)
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            const Pose T_init = pose_load(A.init_pose);
-            pose_store(A.map_counters[0] == 0ull ? T_init : mul(pose_identity(), T_init), A.out);
-            for (int k = 7; k < 13; ++k) A.out[k] = 0.0;
-            A.out[12] = (double)n;
-        }
-        return;
+    FT_MARK(0);
+    if (A.iqr_in) {   // KissICP::iqr_processing (icp.cpp:88-124, :133) on CTA 0, then publish the keypoints to the grid
+        if (blockIdx.x == 0) iqr_block<ICP_BLOCK>(iqr_sm, A.iqr_in, *A.iqr_n, A.iqr_d2, A.iqr_out, A.iqr_count, nullptr);
+        gs.sync();
     }
+    FT_MARK(1);
+    const int64_t n = A.n_dev ? (int64_t)__ldcg(A.n_dev) : A.n_max;
+    const bool run_icp = !(__ldcg(A.map_counters) == 0ull || A.max_iter <= 0);   // ICP :99-100: empty map -> init_guess
     if (threadIdx.x < 7) { Tinit[threadIdx.x] = A.init_pose[threadIdx.x]; Ticp[threadIdx.x] = threadIdx.x == 3 ? 1.0 : 0.0; }
+    if (threadIdx.x < NS) S[threadIdx.x] = 0.0;
     __syncthreads();
-    const int64_t wbase = ((int64_t)blockIdx.x * (ICP_BLOCK / 32) + warp) * 32, wstride = (int64_t)gridDim.x * ICP_BLOCK;
+    const int64_t wbase = ((int64_t)blockIdx.x * (ICP_BLOCK / 32) + warp) * 32, wstride = (int64_t)A.icp_blocks * ICP_BLOCK;
     int j = 0;
     int converged = 0;
-    for (;; ) {
+    while (run_icp && icp_member) {
         PT_MARK(0);
         double acc = 0.0;            // lane L: running total of sum index L>>1
         int ncorr = 0, ncand = 0, nmiss = 0;
         const volatile double *Pv = j == 0 ? Tinit : E;   // re-read per batch: keeps 14 registers free across the lookup
         const double *in = j == 0 ? A.points : A.work;
-        icp_query_pass(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
+        if (A.grouped) icp_query_pass_grouped(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
+        else icp_query_pass(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
         PT_MARK(1);
         // CTA row: 16 sums (even lanes hold them) + 3 counters
         ncorr = __reduce_add_sync(0xFFFFFFFFu, ncorr);
@@ -263,7 +318,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_persistent(const Ic
         nmiss = __reduce_add_sync(0xFFFFFFFFu, nmiss);
         red[warp * 32 + lane] = (lane & 1) ? (lane == 1 ? (double)ncorr : lane == 3 ? (double)ncand : lane == 5 ? (double)nmiss : 0.0) : acc;
         __syncthreads();
-        double *rows = A.partials + (size_t)(j & 1) * gridDim.x * NS;
+        double *rows = A.partials + (size_t)(j & 1) * A.icp_blocks * NS;
         if (threadIdx.x < NS) {
             const int src_lane = threadIdx.x < 16 ? 2 * threadIdx.x : 2 * (threadIdx.x - 16) + 1;
             double v = 0.0;
@@ -272,7 +327,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_persistent(const Ic
             rows[(size_t)blockIdx.x * NS + threadIdx.x] = v;
         }
         PT_MARK(2);
-        grid_barrier(A.barrier, (unsigned int)(j + 1) * gridDim.x);
+        gs_icp.sync();
         PT_MARK(3);
         // fold the per-CTA rows in a fixed order: lane = column, warp g sums rows g, g+8, ... (four independent
         // accumulators keep the L2 loads in flight), then one thread per column adds the 8 warp partials.
@@ -281,13 +336,13 @@ static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_persistent(const Ic
             if (lane < NS) {
                 const int G = ICP_BLOCK / 32;
                 int b = warp;
-                for (; b + 3 * G < (int)gridDim.x; b += 4 * G) {
+                for (; b + 3 * G < A.icp_blocks; b += 4 * G) {
                     v0 += __ldcg(rows + (size_t)b * NS + lane);
                     v1 += __ldcg(rows + (size_t)(b + G) * NS + lane);
                     v2 += __ldcg(rows + (size_t)(b + 2 * G) * NS + lane);
                     v3 += __ldcg(rows + (size_t)(b + 3 * G) * NS + lane);
                 }
-                for (; b < (int)gridDim.x; b += G) v0 += __ldcg(rows + (size_t)b * NS + lane);
+                for (; b < A.icp_blocks; b += G) v0 += __ldcg(rows + (size_t)b * NS + lane);
             }
             red[warp * 32 + lane] = (v0 + v1) + (v2 + v3);
             __syncthreads();
@@ -367,9 +422,58 @@ static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_persistent(const Ic
         if (done) { converged = 1; break; }
         if (j >= A.max_iter) break;
     }
+    FT_MARK(2);
+    // new_pose = T_icp * init_guess (:129); with an empty map the loop did not run and this is init_guess itself (:99-100)
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        pose_store(mul(pose_load(Ticp), pose_load(Tinit)), A.out);          // T_icp * init_guess :129
+        const Pose np = run_icp ? mul(pose_load(Ticp), pose_load(Tinit)) : pose_load(Tinit);
+        pose_store(np, A.out);
         A.out[7] = (double)j; A.out[8] = (double)converged; A.out[9] = S[16]; A.out[10] = S[17]; A.out[11] = S[18]; A.out[12] = (double)n;
+    }
+    if (A.upd_down) {
+        // local_map.update(down_sampled, new_pose) (icp.cpp:81; voxel_hash_map.cpp:138-144): transform + capped ordered insert
+        // (two passes separated by a grid barrier) + eviction sweep around the new position. The CTAs that sat out the
+        // Gauss-Newton loop join here; everybody reads the new pose that CTA 0 published.
+        gs.sync();
+        if (threadIdx.x < 7) E[threadIdx.x] = __ldcg(A.out + threadIdx.x);
+        __syncthreads();
+        const Pose np = pose_load(E);
+        const int64_t nd = (int64_t)__ldcg(A.upd_n);
+        const int64_t gtid = (int64_t)blockIdx.x * ICP_BLOCK + threadIdx.x, gthreads = (int64_t)gridDim.x * ICP_BLOCK;
+        for (int64_t base = (int64_t)blockIdx.x * ICP_BLOCK; base < nd; base += gthreads) {   // whole warps stay converged for the ballot
+            const int64_t i = base + threadIdx.x;
+            bool claimed = false;
+            if (i < nd) {
+                const V3 w = apply(np, V3{A.upd_down[3 * i], A.upd_down[3 * i + 1], A.upd_down[3 * i + 2]});
+                A.upd_world[3 * i] = w.x; A.upd_world[3 * i + 1] = w.y; A.upd_world[3 * i + 2] = w.z;
+                A.upd_pslot[i] = insert_claim_one(A.map, w, (unsigned int)i, A.upd_birth_base, A.status, &claimed);
+            }
+            insert_account(claimed, A.upd_counters);
+        }
+        gs.sync();
+        FT_MARK(3);
+        for (int64_t i = gtid; i < nd; i += gthreads)
+            insert_place_one(A.map, V3{A.upd_world[3 * i], A.upd_world[3 * i + 1], A.upd_world[3 * i + 2]}, (unsigned int)i, __ldcg(A.upd_pslot + i));
+        gs.sync();
+        FT_MARK(4);
+        // eviction sweep over all C slots: eight independent key loads in flight per thread (the slot array is 16 B/slot)
+        for (int64_t s0 = gtid; s0 < (int64_t)A.upd_capacity; s0 += 8 * gthreads) {
+            unsigned long long keys[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t sidx = s0 + (int64_t)u * gthreads;
+                keys[u] = sidx < (int64_t)A.upd_capacity ? __ldcg(&A.map.slots[sidx].key) : KEY_EMPTY;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (keys[u] < KEY_TOMB) remove_far_one(A.map, s0 + (int64_t)u * gthreads, np.tx, np.ty, np.tz, A.upd_max_distance, A.upd_counters);
+        }
+    }
+    FT_MARK(5);
+    // the last CTA out re-arms the barrier for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(A.exit_count, 1u) == gridDim.x - 1) { *A.barrier = 0u; *A.barrier_icp = 0u; *A.exit_count = 0u; __threadfence(); }
     }
 }
 
@@ -410,27 +514,37 @@ static int g_icp_blocks_per_sm = 0;
 
 // Enqueue the persistent ICP kernel. All pointers are device memory; `out13` receives pose + stats.
 int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t n_max, const int *n_dev, const double *init_pose_dev,
-               double tau, double th, int max_iter, double eps, double *partials_dev, size_t partial_rows, unsigned int *barrier_dev,
-               double *out13_dev, int64_t n_hint, double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev, int max_iter_all_ranks) {
+               double tau, double th, int max_iter, double eps, double *partials_dev, size_t partial_rows, double *out13_dev, int64_t n_hint,
+               double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev, int max_iter_all_ranks, const FrameFusion *fuse) {
     limu_ctx *c = m->ctx;
     if (g_icp_blocks_per_sm == 0) {
         int b = 0;
         LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_icp_persistent, ICP_BLOCK, 0));
         g_icp_blocks_per_sm = std::max(1, b);
     }
-    const int64_t want = std::max<int64_t>(1, div_up(std::max<int64_t>(n_hint, 1), ICP_BLOCK));
+    const bool grouped = n_hint <= 16384 && m->cap <= 64;   // latency shape: eight lanes per query
+    const int64_t want = std::max<int64_t>(1, div_up(std::max<int64_t>(n_hint, 1) * (grouped ? 8 : 1), ICP_BLOCK));
     int grid = (int)std::min<int64_t>(want, (int64_t)c->sm_count * std::min(g_icp_blocks_per_sm, 4));
     grid = (int)std::min<int64_t>(grid, (int64_t)partial_rows);
+    const int icp_blocks = grid;   // the Gauss-Newton loop is latency bound at keypoint counts: it runs on the leading CTAs only
+    if (fuse && fuse->upd_down) grid = std::max(grid, c->sm_count);   // the insert and the eviction sweep want one CTA per SM
     IcpArgs A;
+    memset(&A, 0, sizeof A);
     A.map = m->view();
     A.map_counters = m->counters.as<unsigned long long>();
     A.points = points_dev; A.work = work_dev; A.n_max = n_max; A.n_dev = n_dev; A.init_pose = init_pose_dev;
     A.tau_sq = tau * tau; A.th = th; A.max_iter = max_iter; A.eps = eps;
-    A.partials = partials_dev; A.barrier = barrier_dev; A.out = out13_dev;
+    A.partials = partials_dev; A.out = out13_dev;
+    // grid barrier + exit counter live in the context's zero-initialised small area; the last CTA out re-arms them
+    A.barrier = reinterpret_cast<unsigned int *>(c->d_small.as<double>() + 56);
+    A.exit_count = A.barrier + 1;
+    A.barrier_icp = A.barrier + 2;
+    A.icp_blocks = icp_blocks;
     A.est_trace = est_trace_dev; A.ncorr_trace = ncorr_trace_dev; A.hg_trace = hg_trace_dev;
     A.coop_scan = n_hint >= 32768 ? 1 : 0;
-    A.nranks = 1; A.rank = 0; A.mbox_local = nullptr; A.stamp_base = 0; A.comm_error = nullptr;
-    for (int r = 0; r < 8; ++r) A.mbox_peer[r] = nullptr;
+    A.grouped = grouped ? 1 : 0;
+    A.nranks = 1; A.rank = 0;
+    A.status = c->d_status;
     if (max_iter_all_ranks >= 0 && c->comm && c->comm->nranks > 1) {   // point-sharded call: fused peer exchange
         limu_comm *cm = c->comm;
         A.nranks = cm->nranks; A.rank = cm->rank; A.mbox_local = cm->mbox_local; A.comm_error = cm->d_error;
@@ -438,7 +552,12 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
         A.stamp_base = cm->stamp_base;
         cm->stamp_base += (unsigned long long)max_iter_all_ranks + 2ull;
     }
-    LIMU_CUDA_TRY(cudaMemsetAsync(barrier_dev, 0, sizeof(unsigned int), c->stream));
+    if (fuse) {
+        A.iqr_in = fuse->iqr_in; A.iqr_n = fuse->iqr_n; A.iqr_d2 = fuse->iqr_d2; A.iqr_out = fuse->iqr_out; A.iqr_count = fuse->iqr_count;
+        A.upd_down = fuse->upd_down; A.upd_n = fuse->upd_n; A.upd_world = fuse->upd_world; A.upd_pslot = fuse->upd_pslot;
+        A.upd_counters = m->counters.as<unsigned long long>(); A.upd_birth_base = fuse->upd_birth_base;
+        A.upd_capacity = (long long)m->capacity; A.upd_max_distance = m->max_distance;
+    }
     void *args[] = {&A};
     LIMU_TRY(prof_begin(c, LIMU_STAGE_ICP));
     LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_icp_persistent, dim3(grid), dim3(ICP_BLOCK), args, 0, c->stream));
@@ -448,6 +567,15 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
 }
 
 int icp_partial_rows(limu_ctx *c) { return c->sm_count * 4; }
+
+#ifdef LIMU_ICP_PHASE_TIMING
+extern "C" int limu_debug_frame_marks(double out[16]) {
+    unsigned long long h[16];
+    if (cudaMemcpyFromSymbol(h, g_frame_marks, sizeof h) != cudaSuccess) return -1;
+    for (int k = 0; k < 16; ++k) out[k] = (double)h[k];
+    return 0;
+}
+#endif
 
 // ---- un-fused baseline for the sharded loop: step kernel -> fold kernel -> ncclAllReduce -> solve kernel, host in the loop ----
 static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_step(const IcpArgs A, const double *state /* E at +24 */, int first, double *rows) {
@@ -459,7 +587,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_step(const IcpArgs 
     __syncthreads();
     double acc = 0.0;
     int ncorr = 0, ncand = 0, nmiss = 0;
-    const int64_t wbase = ((int64_t)blockIdx.x * (ICP_BLOCK / 32) + warp) * 32, wstride = (int64_t)gridDim.x * ICP_BLOCK;
+    const int64_t wbase = ((int64_t)blockIdx.x * (ICP_BLOCK / 32) + warp) * 32, wstride = (int64_t)A.icp_blocks * ICP_BLOCK;
     icp_query_pass(A, Pose7, first ? A.points : A.work, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
     ncorr = __reduce_add_sync(0xFFFFFFFFu, ncorr);
     ncand = __reduce_add_sync(0xFFFFFFFFu, ncand);
@@ -549,18 +677,17 @@ static int icp_common(limu_map *m, const double *points_dev, int64_t n, const do
     LIMU_TRY(stage_small(c, init_guess, 7, 0, &dinit));
     const int rows = icp_partial_rows(c);
     LIMU_TRY(c->tmp4.reserve((size_t)std::max<int64_t>(n, 1) * 24, c->stream));                 // working cloud
-    LIMU_TRY(c->tmp5.reserve((size_t)2 * rows * NS * 8 + 256, c->stream));                     // partial rows + barrier
+    LIMU_TRY(c->tmp5.reserve((size_t)2 * rows * NS * 8 + 256, c->stream));                     // partial rows
     const bool tr = est_trace || ncorr_trace || hg_trace;
     const size_t it = (size_t)std::max(max_iter, 1);
     if (tr) LIMU_TRY(c->tmp3.reserve(it * (7 + 1 + 42) * 8, c->stream));
     double *partials = c->tmp5.as<double>();
-    unsigned int *barrier = reinterpret_cast<unsigned int *>(partials + (size_t)2 * rows * NS);
     double *out13 = c->d_small.as<double>() + 16;
     double *d_est = tr ? c->tmp3.as<double>() : nullptr;
     long long *d_nc = tr ? reinterpret_cast<long long *>(d_est + it * 7) : nullptr;
     double *d_hg = tr ? d_est + it * 8 : nullptr;
-    LIMU_TRY(icp_device(m, points_dev, c->tmp4.as<double>(), n, nullptr, dinit, tau, th, max_iter, eps, partials, (size_t)rows, barrier, out13, n,
-                        d_est, d_nc, d_hg, sharded ? max_iter : -1));
+    LIMU_TRY(icp_device(m, points_dev, c->tmp4.as<double>(), n, nullptr, dinit, tau, th, max_iter, eps, partials, (size_t)rows, out13, n,
+                        d_est, d_nc, d_hg, sharded ? max_iter : -1, nullptr));
     double *h = static_cast<double *>(c->h_pinned) + 16;
     LIMU_CUDA_TRY(cudaMemcpyAsync(h, out13, 13 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));

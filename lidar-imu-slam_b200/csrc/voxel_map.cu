@@ -17,118 +17,29 @@ static __global__ void k_map_clear(Slot *slots, int64_t C) {
         slots[s] = Slot{KEY_EMPTY, META_NONE};
 }
 
-// Pass 1 of insert_points (voxel_hash_map.cpp:12-62). One thread per input point:
-//   - voxel key (get_vox_index), claim-or-find its slot (64-bit CAS on the packed key),
-//   - meta = min(meta, (base + i) << 13): a fresh slot (meta all-ones) becomes {birth = first input index that
-//     named the voxel, count 0}; an existing voxel's meta is smaller and stays untouched,
-//   - sorted insertion of i into the voxel's pending list pend[slot*cap + count .. slot*cap + cap):
-//     each position keeps the minimum it has seen and passes the loser on (atomicMin chain), so when
-//     the kernel ends the list holds the (cap - count) smallest input indices in ascending order --
-//     exactly the points a serial "append until full" loop (voxel_block.cpp:68-73) would have kept.
 static __global__ void __launch_bounds__(256) k_insert_claim(MapView m, const double *__restrict__ xyz, int64_t n_max, const int *n_dev,
                                                             unsigned long long birth_base, unsigned int *__restrict__ pslot,
                                                             unsigned long long *counters, DevStatus *st) {
     const int64_t n = n_dev ? (int64_t)*n_dev : n_max;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool claimed = false;
-    if (i < n) {
-        const double px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
-        const int kx = vox_index(px, m.vox), ky = vox_index(py, m.vox), kz = vox_index(pz, m.vox);
-        unsigned int slot = PEND_NONE;
-        if (!key_in_range(kx, ky, kz)) {
-            st->key_range = 1;
-        } else {
-            const unsigned long long key = pack_key(kx, ky, kz);
-            unsigned int s = slot_of(key, m.shift);
-            for (unsigned int probes = 0; probes <= m.mask; ++probes) {
-                unsigned long long cur = __ldcg(&m.slots[s].key);
-                if (cur == KEY_EMPTY) {
-                    cur = atomicCAS(&m.slots[s].key, KEY_EMPTY, key);
-                    if (cur == KEY_EMPTY) { claimed = true; cur = key; }
-                }
-                if (cur == key) { slot = s; break; }
-                s = (s + 1) & m.mask;
-            }
-            if (slot == PEND_NONE) st->table_full = 1;
-        }
-        pslot[i] = slot;
-        if (slot != PEND_NONE) {
-            const unsigned long long mine = (birth_base + (unsigned long long)i) << META_COUNT_BITS;
-            const unsigned long long old = atomicMin(&m.slots[slot].meta, mine);
-            const int count = meta_count(old < mine ? old : mine);   // only pass 2 changes counts
-            unsigned int x = (unsigned int)i;
-            unsigned int *list = m.pend + (size_t)slot * m.cap;
-            for (int r = count; r < m.cap; ++r) {
-                const unsigned int old = atomicMin(&list[r], x);
-                if (old == PEND_NONE) break;
-                if (old > x) x = old;
-            }
-        }
-    }
-    // warp-aggregated occupancy accounting
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, claimed);
-    if ((threadIdx.x & 31) == 0 && bal) {
-        atomicAdd(&counters[0], (unsigned long long)__popc(bal));  // live voxels
-        atomicAdd(&counters[3], (unsigned long long)__popc(bal));  // used slots (live + tombstones)
-    }
+    if (i < n) pslot[i] = insert_claim_one(m, V3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, (unsigned int)i, birth_base, st, &claimed);
+    insert_account(claimed, counters);
 }
 
-// Pass 2: every point looks for its own index in its voxel's pending list; position r IS its storage
-// rank (the list started at the old count). Winners store their coordinates and clear the entry.
 static __global__ void __launch_bounds__(256) k_insert_place(MapView m, const double *__restrict__ xyz, int64_t n_max, const int *n_dev,
                                                             const unsigned int *__restrict__ pslot) {
     const int64_t n = n_dev ? (int64_t)*n_dev : n_max;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const unsigned int slot = pslot[i];
-    if (slot == PEND_NONE) return;
-    unsigned int *list = m.pend + (size_t)slot * m.cap;
-    for (int r = 0; r < m.cap; ++r) {
-        if (list[r] == (unsigned int)i) {
-            double *d = voxel_rows(m, slot);
-            d[r] = xyz[3 * i]; d[m.capp + r] = xyz[3 * i + 1]; d[2 * m.capp + r] = xyz[3 * i + 2];
-            list[r] = PEND_NONE;
-            atomicAdd(&m.slots[slot].meta, 1ull);
-            break;
-        }
-    }
+    insert_place_one(m, V3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, (unsigned int)i, pslot[i]);
 }
 
-// remove_points_from_far (voxel_hash_map.cpp:146-171) as it executes under null locks, one thread per
-// slot: voxels whose INDEX distance^2 to the origin voxel exceeds max_distance^2 (units as written,
-// :148,:160) drop their points farther than max_distance metres from origin, order preserved
-// (voxel_block.cpp:107-118); empty voxels are erased (tombstoned).
 static __global__ void __launch_bounds__(256) k_remove_far(MapView m, int64_t C, const double *__restrict__ origin, double max_distance,
                                                           unsigned long long *counters) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= C) return;
-    const unsigned long long key = m.slots[s].key;
-    if (key >= KEY_TOMB) return;
-    const double ox = origin[0], oy = origin[1], oz = origin[2];
-    const double max_sq = max_distance * max_distance;
-    int x, y, z;
-    unpack_key(key, x, y, z);
-    const long long dx = x - vox_index(ox, m.vox), dy = y - vox_index(oy, m.vox), dz = z - vox_index(oz, m.vox);
-    const long long d2 = dx * dx + dy * dy + dz * dz;
-    if (!((double)d2 > max_sq)) return;
-    double *px = voxel_rows(m, (unsigned int)s), *py = px + m.capp, *pz = py + m.capp;
-    const unsigned long long meta = m.slots[s].meta;
-    const int count = meta_count(meta);
-    int w = 0;
-    for (int r = 0; r < count; ++r) {
-        const double ax = px[r], ay = py[r], az = pz[r];
-        if (!(sqnorm3(ax - ox, ay - oy, az - oz) > max_sq)) {
-            if (w != r) { px[w] = ax; py[w] = ay; pz[w] = az; }
-            ++w;
-        }
-    }
-    if (w != count) m.slots[s].meta = (meta & ~META_COUNT_MASK) | (unsigned long long)w;
-    if (w == 0) {
-        m.slots[s].key = KEY_TOMB;
-        m.slots[s].meta = META_NONE;
-        atomicAdd(&counters[0], ~0ull);  // --live
-        atomicAdd(&counters[1], 1ull);   // ++tombstones
-    }
+    remove_far_one(m, s, origin[0], origin[1], origin[2], max_distance, counters);
 }
 
 // Move every live voxel of `old` into the (cleared) table `nw`.

@@ -185,6 +185,185 @@ __device__ __forceinline__ Nearest map_closest(const MapView &m, const V3 &p) {
     return r;
 }
 
+// The 26 neighbour offsets in one table (corners, edges, faces) for the group-cooperative fallback below.
+__device__ constexpr signed char NB_ALL[26][3] = {
+    {-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}, {1, -1, -1}, {1, -1, 1}, {1, 1, -1}, {1, 1, 1},
+    {-1, -1, 0}, {-1, 1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 0, -1}, {-1, 0, 1}, {1, 0, -1}, {1, 0, 1}, {0, -1, -1}, {0, -1, 1}, {0, 1, -1}, {0, 1, 1},
+    {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+
+// Group-cooperative lookup for the latency-bound shape (a few thousand queries): EIGHT lanes serve one query.
+// All lanes probe the query's own voxel (same address -> one broadcast load); on a miss lane l probes neighbours
+// l, l+8, l+16, l+24 of the 26 at once (one L2 round trip instead of up to seven dependent ones) and a 3-step butterfly
+// picks the lexicographic maximum of (|delta|^2, birth) = the reference's max-heap top (voxel_hash_map.cpp:81-101);
+// then the lanes read candidate ranks l, l+8, ... of the chosen voxel and a second butterfly picks the lexicographic
+// minimum of (d^2, rank) = "first minimum wins" (voxel_block.cpp:87-105). Every lane of the group returns the result.
+__device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, unsigned gmask, int l8, int &slot_out, int &count_out, int &own_out,
+                                               double &d2_out, int &rank_out) {
+    const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
+    int slot = -1, count = 0;
+    own_out = 0;
+    if (key_in_range(kx, ky, kz)) {
+        slot = map_find(m, pack_key(kx, ky, kz), &count);
+        if (slot >= 0) own_out = 1;
+    }
+    if (slot < 0) {
+        int bd = -1, bslot = -1;
+        unsigned long long bmeta = 0ull;
+        ulonglong2 got[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = l8 + 8 * u;
+            got[u] = make_ulonglong2(KEY_EMPTY, 0ull);
+            if (c < 26) {
+                const int x = kx + NB_ALL[c][0], y = ky + NB_ALL[c][1], z = kz + NB_ALL[c][2];
+                if (key_in_range(x, y, z)) got[u] = load_slot(m.slots + slot_of(pack_key(x, y, z), m.shift));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = l8 + 8 * u;
+            ulonglong2 v = got[u];
+            if (c < 26 && v.x != KEY_EMPTY) {
+                const unsigned long long want = pack_key(kx + NB_ALL[c][0], ky + NB_ALL[c][1], kz + NB_ALL[c][2]);
+                unsigned int s = slot_of(want, m.shift);
+                while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(m.slots + s); }
+                if (v.x == want) {
+                    const int d = c < 8 ? 3 : (c < 20 ? 2 : 1);
+                    if (d > bd || (d == bd && v.y > bmeta)) { bd = d; bmeta = v.y; bslot = (int)s; }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const int od = __shfl_xor_sync(gmask, bd, o), os = __shfl_xor_sync(gmask, bslot, o);
+            const unsigned long long om = __shfl_xor_sync(gmask, bmeta, o);
+            if (od > bd || (od == bd && om > bmeta)) { bd = od; bmeta = om; bslot = os; }
+        }
+        slot = bslot;
+        count = bslot >= 0 ? meta_count(bmeta) : 0;
+    }
+    double bd2 = 1.7976931348623157e308;
+    int br = 0x7FFFFFFF;
+    if (slot >= 0) {
+        const double *bx = voxel_rows(m, (unsigned int)slot), *by = bx + m.capp, *bz = by + m.capp;
+        double x[2], y[2], z[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {   // ranks l8 and l8+8 in one go (covers cap <= 16); out-of-range ranks re-read rank l8
+            const int r = l8 + 8 * k, rr = r < count ? r : l8;
+            x[k] = __ldg(bx + rr); y[k] = __ldg(by + rr); z[k] = __ldg(bz + rr);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int r = l8 + 8 * k;
+            const double d = sqnorm3(p.x - x[k], p.y - y[k], p.z - z[k]);
+            if (r < count && d < bd2) { bd2 = d; br = r; }
+        }
+        for (int r = l8 + 16; r < count; r += 8) {
+            const double d = sqnorm3(p.x - __ldg(bx + r), p.y - __ldg(by + r), p.z - __ldg(bz + r));
+            if (d < bd2) { bd2 = d; br = r; }
+        }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(gmask, bd2, o);
+        const int orr = __shfl_xor_sync(gmask, br, o);
+        if (od < bd2 || (od == bd2 && orr < br)) { bd2 = od; br = orr; }
+    }
+    slot_out = slot; count_out = count; d2_out = bd2; rank_out = br == 0x7FFFFFFF ? -1 : br;
+}
+
+// ---- insertion / eviction, one element per call (used by the stand-alone kernels and the fused frame kernel) -------
+// Pass 1 of insert_points (voxel_hash_map.cpp:12-62) for input point `i` of the batch:
+//   - voxel key (get_vox_index), claim-or-find its slot (64-bit CAS on the packed key),
+//   - meta = min(meta, (base + i) << 13): a fresh slot (meta all-ones) becomes {birth = first input index that named
+//     the voxel, count 0}; an existing voxel's meta is smaller and stays untouched,
+//   - sorted insertion of i into the voxel's pending list pend[slot*cap + count .. slot*cap + cap): each position keeps
+//     the minimum it has seen and passes the loser on (atomicMin chain), so when the pass ends the list holds the
+//     (cap - count) smallest input indices in ascending order -- exactly the points a serial "append until full" loop
+//     (voxel_block.cpp:68-73) would have kept. Returns the slot (PEND_NONE on failure).
+__device__ __forceinline__ unsigned int insert_claim_one(const MapView &m, const V3 &p, unsigned int i, unsigned long long birth_base, DevStatus *st, bool *claimed) {
+    const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
+    unsigned int slot = PEND_NONE;
+    if (!key_in_range(kx, ky, kz)) { st->key_range = 1; return slot; }
+    const unsigned long long key = pack_key(kx, ky, kz);
+    unsigned int s = slot_of(key, m.shift);
+    for (unsigned int probes = 0; probes <= m.mask; ++probes) {
+        unsigned long long cur = __ldcg(&m.slots[s].key);
+        if (cur == KEY_EMPTY) {
+            cur = atomicCAS(&m.slots[s].key, KEY_EMPTY, key);
+            if (cur == KEY_EMPTY) { *claimed = true; cur = key; }
+        }
+        if (cur == key) { slot = s; break; }
+        s = (s + 1) & m.mask;
+    }
+    if (slot == PEND_NONE) { st->table_full = 1; return slot; }
+    const unsigned long long mine = (birth_base + (unsigned long long)i) << META_COUNT_BITS;
+    const unsigned long long old = atomicMin(&m.slots[slot].meta, mine);
+    const int count = meta_count(old < mine ? old : mine);   // only pass 2 changes counts
+    unsigned int x = i;
+    unsigned int *list = m.pend + (size_t)slot * m.cap;
+    for (int r = count; r < m.cap; ++r) {
+        const unsigned int prev = atomicMin(&list[r], x);
+        if (prev == PEND_NONE) break;
+        if (prev > x) x = prev;
+    }
+    return slot;
+}
+// warp-aggregated occupancy accounting (call with the whole warp converged)
+__device__ __forceinline__ void insert_account(bool claimed, unsigned long long *counters) {
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, claimed);
+    if ((threadIdx.x & 31) == 0 && bal) {
+        atomicAdd(&counters[0], (unsigned long long)__popc(bal));  // live voxels
+        atomicAdd(&counters[3], (unsigned long long)__popc(bal));  // used slots (live + tombstones)
+    }
+}
+// Pass 2: the point looks for its own index in its voxel's pending list; position r IS its storage rank (the list
+// started at the old count). Winners store their coordinates and clear the entry.
+__device__ __forceinline__ void insert_place_one(const MapView &m, const V3 &p, unsigned int i, unsigned int slot) {
+    if (slot == PEND_NONE) return;
+    unsigned int *list = m.pend + (size_t)slot * m.cap;
+    for (int r = 0; r < m.cap; ++r) {
+        if (__ldcg(list + r) == i) {
+            double *d = voxel_rows(m, slot);
+            d[r] = p.x; d[m.capp + r] = p.y; d[2 * m.capp + r] = p.z;
+            list[r] = PEND_NONE;
+            atomicAdd(&m.slots[slot].meta, 1ull);
+            break;
+        }
+    }
+}
+// remove_points_from_far (voxel_hash_map.cpp:146-171) as it executes under null locks, for slot s: voxels whose INDEX
+// distance^2 to the origin voxel exceeds max_distance^2 (units as written, :148,:160) drop their points farther than
+// max_distance metres from origin, order preserved (voxel_block.cpp:107-118); empty voxels are erased (tombstoned).
+__device__ __forceinline__ void remove_far_one(const MapView &m, int64_t s, double ox, double oy, double oz, double max_distance, unsigned long long *counters) {
+    const unsigned long long key = m.slots[s].key;
+    if (key >= KEY_TOMB) return;
+    const double max_sq = max_distance * max_distance;
+    int x, y, z;
+    unpack_key(key, x, y, z);
+    const long long dx = x - vox_index(ox, m.vox), dy = y - vox_index(oy, m.vox), dz = z - vox_index(oz, m.vox);
+    const long long d2 = dx * dx + dy * dy + dz * dz;
+    if (!((double)d2 > max_sq)) return;
+    double *px = voxel_rows(m, (unsigned int)s), *py = px + m.capp, *pz = py + m.capp;
+    const unsigned long long meta = m.slots[s].meta;
+    const int count = meta_count(meta);
+    int w = 0;
+    for (int r = 0; r < count; ++r) {
+        const double ax = px[r], ay = py[r], az = pz[r];
+        if (!(sqnorm3(ax - ox, ay - oy, az - oz) > max_sq)) {
+            if (w != r) { px[w] = ax; py[w] = ay; pz[w] = az; }
+            ++w;
+        }
+    }
+    if (w != count) m.slots[s].meta = (meta & ~META_COUNT_MASK) | (unsigned long long)w;
+    if (w == 0) {
+        m.slots[s].key = KEY_TOMB;
+        m.slots[s].meta = META_NONE;
+        atomicAdd(&counters[0], ~0ull);  // --live
+        atomicAdd(&counters[1], 1ull);   // ++tombstones
+    }
+}
+
 }  // namespace limu
 
 // Host-side object behind the C handle.

@@ -1,0 +1,221 @@
+// voxelize.cu -- KissICP::deskew_scan + KissICP::voxelize's two downsampling stages as ONE persistent cooperative
+// kernel (L/src/sensors/lidar/icp.cpp:36-47, :9-30, :126-131; helpers/deskew.cpp:10-28).
+//
+// The stand-alone stages (ops.cu) cost 13 launches + 2 memsets per scan, each a few microseconds of work on 128k points;
+// here the phases are separated by grid barriers instead of kernel boundaries:
+//   P0 clear both scan-local tables            P3 ordered scatter of stage-1 winners -> down[], stage-2 claim
+//   P1 deskew/widen -> frame[], stage-1 claim  P4 stage-2 winner flags, per-tile counts
+//   P2 stage-1 winner flags, per-tile counts   P5 ordered scatter of stage-2 winners -> src0[]
+// "First point per voxel wins, output in first-occurrence order" (icp.cpp:13-27 + the oracle's ordered map) becomes:
+// atomicMin of the input index per voxel, then a stable compaction over 256-point tiles.
+#include <algorithm>
+
+#include "compact.cuh"
+#include "grid_sync.cuh"
+#include "ops.cuh"
+#include "voxel_map.cuh"
+
+namespace limu {
+
+constexpr int VX_BLOCK = 256;
+
+struct VoxelizeArgs {
+    const void *raw;            // mode 0: float4 {x,y,z,t}; mode 1: records `stride` bytes apart + ts; mode 2: double xyz (already a frame)
+    const double *ts;
+    int mode, stride, deskew;
+    const double *twist;        // 6 doubles (device), read when deskew != 0
+    int64_t n;
+    double vs1, vs2;            // 0.5 v and 1.5 v (icp.cpp:129-130)
+    double *frame, *down, *src0;
+    unsigned long long *keys1, *keys2;
+    unsigned int *min1, *min2, *pslot1, *pslot2;
+    unsigned int mask1, mask2;
+    int shift1, shift2;
+    int *tile1, *tile2;
+    int *counts;                // [0] n_down, [1] n_src0
+    unsigned int *barrier;
+    DevStatus *st;
+};
+
+__device__ __forceinline__ unsigned int claim_min(unsigned long long *keys, unsigned int *minidx, unsigned int mask, int shift, const V3 &p, double vs,
+                                                  unsigned int index, DevStatus *st) {
+    const int kx = vox_index(p.x, vs), ky = vox_index(p.y, vs), kz = vox_index(p.z, vs);
+    if (!key_in_range(kx, ky, kz)) { st->key_range = 1; return PEND_NONE; }
+    const unsigned long long key = pack_key(kx, ky, kz);
+    unsigned int s = slot_of(key, shift);
+    for (unsigned int probes = 0; probes <= mask; ++probes) {
+        unsigned long long cur = __ldcg(&keys[s]);
+        if (cur == KEY_EMPTY) {
+            cur = atomicCAS(&keys[s], KEY_EMPTY, key);
+            if (cur == KEY_EMPTY) cur = key;
+        }
+        if (cur == key) { atomicMin(&minidx[s], index); return s; }
+        s = (s + 1) & mask;
+    }
+    st->table_full = 1;
+    return PEND_NONE;
+}
+
+// exclusive prefix of tile counts: sum of counts[0..tile) computed by the whole CTA
+__device__ __forceinline__ int tile_base(const int *counts, int tile, int *ws /* 32 ints */) {
+    int part = 0;
+    for (int b = threadIdx.x; b < tile; b += VX_BLOCK) part += __ldcg(counts + b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xFFFFFFFFu, part, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = part;
+    __syncthreads();
+    int v = 0;
+#pragma unroll
+    for (int w = 0; w < VX_BLOCK / 32; ++w) v += ws[w];
+    __syncthreads();
+    return v;
+}
+
+static __global__ void __launch_bounds__(VX_BLOCK, 4) k_voxelize(const VoxelizeArgs A) {
+    __shared__ int ws[32];
+    __shared__ int total;
+    GridSync gs{A.barrier, 0u, gridDim.x};
+    const int64_t n = A.n;
+    const int64_t gtid = (int64_t)blockIdx.x * VX_BLOCK + threadIdx.x, gthreads = (int64_t)gridDim.x * VX_BLOCK;
+    const int ntiles = (int)((n + VX_BLOCK - 1) / VX_BLOCK);
+    // P0: clear the scan-local tables (all-ones = empty key / no index)
+    {
+        const int64_t w1 = (int64_t)A.mask1 + 1, w2 = (int64_t)A.mask2 + 1;
+        for (int64_t i = gtid; i < w1; i += gthreads) { A.keys1[i] = KEY_EMPTY; A.min1[i] = PEND_NONE; }
+        for (int64_t i = gtid; i < w2; i += gthreads) { A.keys2[i] = KEY_EMPTY; A.min2[i] = PEND_NONE; }
+    }
+    gs.sync();
+    // P1: frame[i] = deskewed / widened point (icp.cpp:36-47, deskew.cpp:18-26); stage-1 claim at 0.5 v
+    {
+        double tw[6];
+        if (A.deskew) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) tw[k] = A.twist[k];
+        }
+        for (int64_t i = gtid; i < n; i += gthreads) {
+            V3 p;
+            double t = 0.0;
+            if (A.mode == 0) {
+                const float4 q = __ldg(reinterpret_cast<const float4 *>(A.raw) + i);
+                p = V3{(double)q.x, (double)q.y, (double)q.z};
+                t = (double)q.w;
+            } else if (A.mode == 1) {
+                const float *q = reinterpret_cast<const float *>(static_cast<const unsigned char *>(A.raw) + (size_t)i * A.stride);
+                p = V3{(double)q[0], (double)q[1], (double)q[2]};
+                if (A.deskew) t = A.ts[i];
+            } else {
+                const double *q = static_cast<const double *>(A.raw) + 3 * i;
+                p = V3{q[0], q[1], q[2]};
+            }
+            if (A.deskew) {
+                const double s = t - 0.5;   // mid_pose_timestamp, deskew.hpp:12
+                double st[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) st[k] = s * tw[k];
+                p = apply(se3_exp(st), p);
+            }
+            A.frame[3 * i] = p.x; A.frame[3 * i + 1] = p.y; A.frame[3 * i + 2] = p.z;
+            A.pslot1[i] = claim_min(A.keys1, A.min1, A.mask1, A.shift1, p, A.vs1, (unsigned int)i, A.st);
+        }
+    }
+    gs.sync();
+    // P2: a point survives stage 1 iff it holds its voxel's smallest input index; count survivors per 256-point tile
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t i = (int64_t)tile * VX_BLOCK + threadIdx.x;
+        int f = 0;
+        if (i < n) { const unsigned int s = A.pslot1[i]; f = s != PEND_NONE && __ldcg(A.min1 + s) == (unsigned int)i; }
+        block_exclusive_scan_flag(f, &total, ws);
+        if (threadIdx.x == 0) A.tile1[tile] = total;
+        __syncthreads();
+    }
+    gs.sync();
+    // P3: ordered scatter -> down[]; each winner immediately claims its 1.5 v voxel with its OUTPUT index
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int base = tile_base(A.tile1, tile, ws);
+        const int64_t i = (int64_t)tile * VX_BLOCK + threadIdx.x;
+        int f = 0;
+        if (i < n) { const unsigned int s = A.pslot1[i]; f = s != PEND_NONE && __ldcg(A.min1 + s) == (unsigned int)i; }
+        const int r = block_exclusive_scan_flag(f, &total, ws);
+        if (f) {
+            const int j = base + r;
+            const V3 p{A.frame[3 * i], A.frame[3 * i + 1], A.frame[3 * i + 2]};
+            A.down[3 * (size_t)j] = p.x; A.down[3 * (size_t)j + 1] = p.y; A.down[3 * (size_t)j + 2] = p.z;
+            A.pslot2[j] = claim_min(A.keys2, A.min2, A.mask2, A.shift2, p, A.vs2, (unsigned int)j, A.st);
+        }
+        if (tile == ntiles - 1 && threadIdx.x == 0) A.counts[0] = base + total;
+        __syncthreads();
+    }
+    if (ntiles == 0 && gtid == 0) A.counts[0] = 0;
+    gs.sync();
+    // P4 / P5: the same flag -> count -> scatter over down[] for stage 2
+    const int nd = __ldcg(A.counts);
+    const int ntiles2 = (nd + VX_BLOCK - 1) / VX_BLOCK;
+    for (int tile = blockIdx.x; tile < ntiles2; tile += gridDim.x) {
+        const int j = tile * VX_BLOCK + threadIdx.x;
+        int f = 0;
+        if (j < nd) { const unsigned int s = __ldcg(A.pslot2 + j); f = s != PEND_NONE && __ldcg(A.min2 + s) == (unsigned int)j; }
+        block_exclusive_scan_flag(f, &total, ws);
+        if (threadIdx.x == 0) A.tile2[tile] = total;
+        __syncthreads();
+    }
+    gs.sync();
+    for (int tile = blockIdx.x; tile < ntiles2; tile += gridDim.x) {
+        const int base = tile_base(A.tile2, tile, ws);
+        const int j = tile * VX_BLOCK + threadIdx.x;
+        int f = 0;
+        if (j < nd) { const unsigned int s = __ldcg(A.pslot2 + j); f = s != PEND_NONE && __ldcg(A.min2 + s) == (unsigned int)j; }
+        const int r = block_exclusive_scan_flag(f, &total, ws);
+        if (f) {
+            const size_t k = (size_t)(base + r);
+            A.src0[3 * k] = __ldcg(A.down + 3 * (size_t)j); A.src0[3 * k + 1] = __ldcg(A.down + 3 * (size_t)j + 1); A.src0[3 * k + 2] = __ldcg(A.down + 3 * (size_t)j + 2);
+        }
+        if (tile == ntiles2 - 1 && threadIdx.x == 0) A.counts[1] = base + total;
+        __syncthreads();
+    }
+    if (ntiles2 == 0 && gtid == 0) A.counts[1] = 0;
+}
+
+static int g_vx_blocks_per_sm = 0;
+
+static int64_t pow2_slots(int64_t n) { int64_t p = 1024; while (p < 2 * n) p <<= 1; return p; }
+
+// Enqueue the fused kernel. raw/ts/twist are device pointers; outputs: frame (n x 3), down, src0, counts[0..1].
+int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int mode, int stride, const double *ts_dev, int deskew, const double *twist_dev,
+                    int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev) {
+    if (n <= 0) { LIMU_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int), c->stream)); return LIMU_OK; }
+    if (g_vx_blocks_per_sm == 0) {
+        int b = 0;
+        LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_voxelize, VX_BLOCK, 0));
+        g_vx_blocks_per_sm = std::max(1, std::min(b, 4));
+    }
+    const int64_t C1 = pow2_slots(n), C2 = pow2_slots(n);
+    int lg = 0;
+    while ((int64_t(1) << lg) < C1) ++lg;
+    const int ntiles = div_up(n, VX_BLOCK);
+    LIMU_TRY(sc.table.reserve((size_t)(C1 + C2) * 12, c->stream));
+    LIMU_TRY(sc.pslot.reserve((size_t)n * 8, c->stream));
+    LIMU_TRY(sc.tiles.reserve((size_t)ntiles * 8 + 64, c->stream));
+    VoxelizeArgs A;
+    A.raw = raw_dev; A.ts = ts_dev; A.mode = mode; A.stride = stride; A.deskew = deskew; A.twist = twist_dev; A.n = n;
+    A.vs1 = v * 0.5; A.vs2 = v * 1.5;
+    A.frame = frame_dev; A.down = down_dev; A.src0 = src0_dev;
+    A.keys1 = sc.table.as<unsigned long long>();
+    A.keys2 = A.keys1 + C1;
+    A.min1 = reinterpret_cast<unsigned int *>(A.keys2 + C2);
+    A.min2 = A.min1 + C1;
+    A.mask1 = (unsigned int)(C1 - 1); A.mask2 = (unsigned int)(C2 - 1); A.shift1 = A.shift2 = 64 - lg;
+    A.pslot1 = sc.pslot.as<unsigned int>(); A.pslot2 = A.pslot1 + n;
+    A.tile1 = sc.tiles.as<int>(); A.tile2 = A.tile1 + ntiles;
+    A.counts = counts_dev;
+    A.barrier = reinterpret_cast<unsigned int *>(A.tile2 + ntiles);
+    A.st = c->d_status;
+    LIMU_CUDA_TRY(cudaMemsetAsync(A.barrier, 0, sizeof(unsigned int), c->stream));
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->sm_count * g_vx_blocks_per_sm);
+    void *args[] = {&A};
+    LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize, dim3(grid), dim3(VX_BLOCK), args, 0, c->stream));
+    LIMU_LAUNCHED();
+    return LIMU_OK;
+}
+
+}  // namespace limu
