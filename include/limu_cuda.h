@@ -177,6 +177,10 @@ void limu_odom_destroy(limu_odom *o);
  * down_xyz / keypoints_xyz must hold n points each. */
 int limu_odom_register_frame(limu_odom *o, const float *xyzt, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down,
                              double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats);
+/* Replay / batch use: start uploading the NEXT scan (pinned host memory) on a separate stream while the current one is
+ * being registered; the following limu_odom_register_frame call with the same pointer and size skips its own upload.
+ * The buffer must stay untouched until that call. Results are identical with or without prefetching. */
+int limu_odom_prefetch(limu_odom *o, const float *xyzt, int64_t n);
 /* register_frame(cloud, timestamps) on the reference's own layout (PCL point records + FP64 timestamps). */
 int limu_odom_register_cloud(limu_odom *o, const void *points, int32_t stride_bytes, const double *timestamps, int64_t n, double pose_out[7],
                              double *down_xyz, int64_t *n_down, double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats);

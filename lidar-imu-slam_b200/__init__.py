@@ -109,6 +109,7 @@ def lib():
             "limu_odom_create": [_vp, C.POINTER(OdomConfig), C.POINTER(_vp)], "limu_odom_destroy": [_vp],
             "limu_odom_register_frame": [_vp, _fp, C.c_int64, _dp, _dp, _lp, _dp, _lp, C.POINTER(FrameStats)],
             "limu_odom_register_frame_dev": [_vp, _vp, C.c_int64, _dp, C.POINTER(FrameStats)],
+            "limu_odom_prefetch": [_vp, _fp, C.c_int64],
             "limu_odom_register_points": [_vp, _dp, C.c_int64, _dp, _dp, _lp, _dp, _lp, C.POINTER(FrameStats)],
             "limu_odom_num_poses": [_vp, _lp], "limu_odom_pose": [_vp, C.c_int64, _dp],
             "limu_odom_adaptive_threshold": [_vp, _dp], "limu_odom_prediction": [_vp, _dp], "limu_odom_has_moved": [_vp, C.POINTER(C.c_int)],
@@ -498,6 +499,11 @@ class KissICP:
         if copy:
             return down[: nd.value].copy(), src[: ns.value].copy(), pose
         return down[: nd.value], src[: ns.value], pose
+
+    def prefetch(self, xyzt_f32):
+        """Start the H2D copy of the NEXT scan (pinned float32 [n,4]); pass the same array to the next register_frame."""
+        assert isinstance(xyzt_f32, np.ndarray) and xyzt_f32.dtype == np.float32 and xyzt_f32.flags.c_contiguous
+        _chk(lib().limu_odom_prefetch(self.h, xyzt_f32.ctypes.data_as(_fp), xyzt_f32.size // 4))
 
     def register_cloud(self, records, stride_bytes, timestamps):
         """register_frame(cloud, timestamps) on strided point records + float64 timestamps (the reference's layout)."""

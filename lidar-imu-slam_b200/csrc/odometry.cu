@@ -12,7 +12,7 @@
 #include "voxel_map.cuh"
 
 namespace limu {
-int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t n_max, const int *n_dev, const double *init_pose_dev,
+int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t n_max, const int *n_dev, const double *init_pose_host,
                double tau, double th, int max_iter, double eps, double *partials_dev, size_t partial_rows, double *out13_dev, int64_t n_hint,
                double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev, int max_iter_all_ranks, const FrameFusion *fuse);
 int icp_partial_rows(limu_ctx *c);
@@ -61,6 +61,13 @@ struct limu_odom {
     limu::StageScratch sa, sb;
     limu::VoxelizeScratch vx;
     int64_t nk_hint = 4096, nd_hint = 16384;
+    // limu_odom_prefetch: the next scan is uploaded on its own stream while the current one is being registered
+    limu::DevBuf pf_buf[2];                 // two slots: the scan about to be registered and the one after it
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t pf_done[2] = {nullptr, nullptr};
+    const void *pf_host[2] = {nullptr, nullptr};
+    int64_t pf_n[2] = {-1, -1};
+    int pf_next = 0;
 };
 
 using namespace limu;
@@ -99,12 +106,8 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     // deskew gate (icp.cpp:40-46): config.deskew && poses.size() > 2; twist = delta_pose(poses[N-2], poses[N-1]) (deskew.cpp:14)
     const size_t NP = o->poses.size();
     const int deskewed = (mode != 2 && o->cfg.deskew && NP > 2) ? 1 : 0;
-    double *dtw = nullptr;
-    if (deskewed) {
-        double twist[6];
-        se3_log(mul(inverse(o->poses[NP - 2]), o->poses[NP - 1]), twist);
-        LIMU_TRY(stage_small(c, twist, 6, 0, &dtw));
-    }
+    double twist[6] = {0, 0, 0, 0, 0, 0};
+    if (deskewed) se3_log(mul(inverse(o->poses[NP - 2]), o->poses[NP - 1]), twist);
     LIMU_TRY(o->down.reserve(nb, c->stream));
     LIMU_TRY(o->src0.reserve(nb, c->stream));
     LIMU_TRY(o->src.reserve(nb, c->stream));
@@ -118,7 +121,7 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
 
     // deskew_scan + voxelize's two downsampling stages (icp.cpp:36-47, :126-131): one cooperative launch
     LIMU_TRY(prof_begin(c, LIMU_STAGE_DOWNSAMPLE));
-    LIMU_TRY(voxelize_device(c, o->vx, raw_dev, mode, stride, ts_dev, deskewed, dtw, n, v, o->frame.as<double>(), o->down.as<double>(), o->src0.as<double>(), cnt + 0));
+    LIMU_TRY(voxelize_device(c, o->vx, raw_dev, mode, stride, ts_dev, deskewed, twist, n, v, o->frame.as<double>(), o->down.as<double>(), o->src0.as<double>(), cnt + 0));
     LIMU_TRY(prof_end(c, LIMU_STAGE_DOWNSAMPLE));
     // host scalar glue (icp.cpp:66-71)
     const double sigma = odom_adaptive_threshold(o);
@@ -127,8 +130,6 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     const Pose init = mul(last, pred);
     double init7[7];
     pose_store(init, init7);
-    double *dinit;
-    LIMU_TRY(stage_small(c, init7, 7, 8, &dinit));
 
     // iqr_processing (icp.cpp:133) + ICP (icp.cpp:74-76) + local_map.update(down_sampled, new_pose) (icp.cpp:81;
     // voxel_hash_map.cpp:138-144): ONE persistent cooperative launch (registration.cu)
@@ -140,7 +141,7 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     fuse.upd_down = o->down.as<double>(); fuse.upd_n = cnt + 0; fuse.upd_world = o->world.as<double>(); fuse.upd_pslot = o->map->pslot.as<unsigned int>();
     fuse.upd_birth_base = o->map->birth_base;
     const int64_t upper_before = o->map->used_upper;
-    LIMU_TRY(icp_device(o->map, o->src.as<double>(), o->work.as<double>(), n, cnt + 2, dinit, 3.0 * sigma, sigma / 3.0, o->cfg.icp_max_iteration,
+    LIMU_TRY(icp_device(o->map, o->src.as<double>(), o->work.as<double>(), n, cnt + 2, init7, 3.0 * sigma, sigma / 3.0, o->cfg.icp_max_iteration,
                         o->cfg.estimation_threshold, o->partials.as<double>(), (size_t)rows, out13, o->nk_hint, nullptr, nullptr, nullptr, -1, &fuse));
     o->map->birth_base += (uint64_t)n;
 
@@ -213,7 +214,8 @@ void limu_odom_destroy(limu_odom *o) {
     cudaSetDevice(o->ctx->device);
     cudaStreamSynchronize(o->ctx->stream);
     limu_map_destroy(o->map);
-    DevBuf *bufs[] = {&o->d2, &o->raw, &o->ts, &o->frame, &o->down, &o->src0, &o->src, &o->work, &o->world, &o->partials};
+    if (o->copy_stream) { cudaStreamSynchronize(o->copy_stream); cudaStreamDestroy(o->copy_stream); cudaEventDestroy(o->pf_done[0]); cudaEventDestroy(o->pf_done[1]); }
+    DevBuf *bufs[] = {&o->pf_buf[0], &o->pf_buf[1], &o->d2, &o->raw, &o->ts, &o->frame, &o->down, &o->src0, &o->src, &o->work, &o->world, &o->partials};
     for (auto *b : bufs) b->release();
     o->sa.release(); o->sb.release(); o->vx.release();
     delete o;
@@ -223,8 +225,37 @@ int limu_odom_register_frame(limu_odom *o, const float *xyzt, int64_t n, double 
                              double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
     LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyzt), "limu_odom_register_frame: bad arguments");
     LIMU_TRY(bind(o->ctx));
-    LIMU_TRY(stage_in(o->ctx, o->raw, xyzt, (size_t)n * 16));
+    int hit = -1;
+    for (int s = 0; s < 2; ++s) if (n > 0 && o->pf_host[s] == xyzt && o->pf_n[s] == n) hit = s;
+    if (hit >= 0) {   // uploaded ahead of time by limu_odom_prefetch
+        LIMU_CUDA_TRY(cudaStreamWaitEvent(o->ctx->stream, o->pf_done[hit], 0));
+        std::swap(o->raw, o->pf_buf[hit]);
+        o->pf_host[hit] = nullptr; o->pf_n[hit] = -1;
+    } else {
+        LIMU_TRY(stage_in(o->ctx, o->raw, xyzt, (size_t)n * 16));
+    }
     return odom_register_device(o, o->raw.p, 0, 0, nullptr, n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+}
+
+int limu_odom_prefetch(limu_odom *o, const float *xyzt, int64_t n) {
+    LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyzt), "limu_odom_prefetch: bad arguments");
+    LIMU_TRY(bind(o->ctx));
+    if (n == 0) return LIMU_OK;
+    if (!o->copy_stream) {
+        LIMU_CUDA_TRY(cudaStreamCreateWithFlags(&o->copy_stream, cudaStreamNonBlocking));
+        for (int s = 0; s < 2; ++s) LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->pf_done[s], cudaEventDisableTiming));
+    }
+    for (int s = 0; s < 2; ++s) if (o->pf_host[s] == xyzt && o->pf_n[s] == n) return LIMU_OK;   // already in flight
+    int s = o->pf_host[0] == nullptr ? 0 : (o->pf_host[1] == nullptr ? 1 : o->pf_next);
+    o->pf_next = s ^ 1;
+    if (o->pf_buf[s].bytes < (size_t)n * 16) {   // growing may free a buffer the copy stream still writes: drain it first
+        LIMU_CUDA_TRY(cudaStreamSynchronize(o->copy_stream));
+        LIMU_TRY(o->pf_buf[s].reserve((size_t)n * 16, o->copy_stream));
+    }
+    LIMU_CUDA_TRY(cudaMemcpyAsync(o->pf_buf[s].p, xyzt, (size_t)n * 16, cudaMemcpyHostToDevice, o->copy_stream));
+    LIMU_CUDA_TRY(cudaEventRecord(o->pf_done[s], o->copy_stream));
+    o->pf_host[s] = xyzt; o->pf_n[s] = n;
+    return LIMU_OK;
 }
 
 int limu_odom_register_cloud(limu_odom *o, const void *points, int32_t stride_bytes, const double *timestamps, int64_t n, double pose_out[7],

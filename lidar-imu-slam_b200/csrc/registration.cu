@@ -36,7 +36,7 @@ struct IcpArgs {
     double *work;               // n x 3, running source cloud
     int64_t n_max;
     const int *n_dev;
-    const double *init_pose;    // 7, device
+    double init_pose[7];        // init_guess, by value (no staging copy per call)
     double tau_sq;              // max_corresp_dist^2 (voxel_hash_map.cpp:112)
     double th;                  // kernel (registration.cpp:57-58)
     int max_iter;
@@ -279,7 +279,11 @@ __device__ unsigned long long g_frame_marks[16];
 #define FT_MARK(k) do {} while (0)
 #endif
 
-static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_persistent(const IcpArgs A) {
+// SHAPE 0 = latency build (eight lanes per query, a few thousand keypoints: one CTA per SM at most, so the compiler may
+// use up to 255 registers and the serial Gauss-Newton solve stays out of local memory); SHAPE 1 = bandwidth build
+// (one lane per query + cooperative scan, 64 registers -> 4 CTAs/SM for the HBM-bound kernel mode).
+template <int SHAPE>
+static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_persistent(const IcpArgs A) {
     __shared__ double red[(ICP_BLOCK / 32) * 32];
     __shared__ double S[NS];
     __shared__ double E[7], Tinit[7], Ticp[7];
@@ -309,7 +313,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_persistent(const Ic
         int ncorr = 0, ncand = 0, nmiss = 0;
         const volatile double *Pv = j == 0 ? Tinit : E;   // re-read per batch: keeps 14 registers free across the lookup
         const double *in = j == 0 ? A.points : A.work;
-        if (A.grouped) icp_query_pass_grouped(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
+        if (SHAPE == 0) icp_query_pass_grouped(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
         else icp_query_pass(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
         PT_MARK(1);
         // CTA row: 16 sums (even lanes hold them) + 3 counters
@@ -392,26 +396,44 @@ static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_persistent(const Ic
             __syncthreads();
         }
         PT_MARK(4);
-        if (threadIdx.x == 0) {
-            double H[36], g[6], x[6], lg[6];
-            expand_normal_equations(S, H, g);
+        if (warp == 0) {
+            // normal equations -> twist -> estimate (lane 0, all in registers in the latency build), then T_icp on lane 0
+            // while lane 1 takes log(estimate) for the convergence test
+            FT_MARK(8);
+            if (lane == 0) {
+                double H[36], g[6], x[6];
+                expand_normal_equations(S, H, g);
 #pragma unroll
-            for (int k = 0; k < 6; ++k) g[k] = -g[k];
-            ldlt6_solve(H, g, x);                       // JTJ.ldlt().solve(-JTr) :90
-            const Pose est = se3_exp(x);                // vector6d_to_mat4d :91
-            pose_store(mul(est, pose_load(Ticp)), Ticp);   // T_icp = estimate * T_icp :122
-            se3_log(est, lg);
-            const int stop = norm6(lg) < A.eps;         // :124
-            pose_store(est, E);
-            done = stop;
-            if (blockIdx.x == 0) {
+                for (int k = 0; k < 6; ++k) g[k] = -g[k];
+                ldlt6_solve(H, g, x);                             // JTJ.ldlt().solve(-JTr) :90
+#pragma unroll
+                for (int k = 0; k < 6; ++k) red[k] = x[k];
+                FT_MARK(9);
+            }
+            __syncwarp();
+            // estimate = SE3::exp(x) (vector6d_to_mat4d :91): rotation half on lane 0, translation half on lane 1
+            if (lane == 0) { double th_; se3_exp_rotation(red, E, &th_); }
+            if (lane == 1) se3_exp_translation(red, E + 4);
+            __syncwarp();
+            FT_MARK(10);
+            const Pose est = pose_load(E);
+            if (lane == 0) pose_store(mul(est, pose_load(Ticp)), Ticp);   // T_icp = estimate * T_icp :122
+            if (lane == 1) {
+                double lg[6];
+                se3_log(est, lg);
+                done = norm6(lg) < A.eps;                          // :124
+            }
+            FT_MARK(12);
+            if (blockIdx.x == 0 && lane == 2) {
                 if (A.est_trace) pose_store(est, A.est_trace + 7 * (size_t)j);
                 if (A.ncorr_trace) A.ncorr_trace[j] = (long long)S[16];
 #ifndef LIMU_ICP_PHASE_TIMING
                 if (A.hg_trace) {
+                    double H[36], g[6];
+                    expand_normal_equations(S, H, g);
                     double *o = A.hg_trace + 42 * (size_t)j;
                     for (int k = 0; k < 36; ++k) o[k] = H[k];
-                    for (int k = 0; k < 6; ++k) o[36 + k] = -g[k];
+                    for (int k = 0; k < 6; ++k) o[36 + k] = g[k];
                 }
 #endif
             }
@@ -513,18 +535,18 @@ static __global__ void k_align_solve(const double *partials, int nblocks, double
 static int g_icp_blocks_per_sm = 0;
 
 // Enqueue the persistent ICP kernel. All pointers are device memory; `out13` receives pose + stats.
-int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t n_max, const int *n_dev, const double *init_pose_dev,
+int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t n_max, const int *n_dev, const double *init_pose_host,
                double tau, double th, int max_iter, double eps, double *partials_dev, size_t partial_rows, double *out13_dev, int64_t n_hint,
                double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev, int max_iter_all_ranks, const FrameFusion *fuse) {
     limu_ctx *c = m->ctx;
     if (g_icp_blocks_per_sm == 0) {
         int b = 0;
-        LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_icp_persistent, ICP_BLOCK, 0));
+        LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_icp_persistent<1>, ICP_BLOCK, 0));
         g_icp_blocks_per_sm = std::max(1, b);
     }
-    const bool grouped = n_hint <= 16384 && m->cap <= 64;   // latency shape: eight lanes per query
+    const bool grouped = n_hint <= 16384 && m->cap <= 64;   // latency shape: eight lanes per query, one CTA per SM
     const int64_t want = std::max<int64_t>(1, div_up(std::max<int64_t>(n_hint, 1) * (grouped ? 8 : 1), ICP_BLOCK));
-    int grid = (int)std::min<int64_t>(want, (int64_t)c->sm_count * std::min(g_icp_blocks_per_sm, 4));
+    int grid = (int)std::min<int64_t>(want, (int64_t)c->sm_count * (grouped ? 1 : std::min(g_icp_blocks_per_sm, 4)));
     grid = (int)std::min<int64_t>(grid, (int64_t)partial_rows);
     const int icp_blocks = grid;   // the Gauss-Newton loop is latency bound at keypoint counts: it runs on the leading CTAs only
     if (fuse && fuse->upd_down) grid = std::max(grid, c->sm_count);   // the insert and the eviction sweep want one CTA per SM
@@ -532,7 +554,8 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
     memset(&A, 0, sizeof A);
     A.map = m->view();
     A.map_counters = m->counters.as<unsigned long long>();
-    A.points = points_dev; A.work = work_dev; A.n_max = n_max; A.n_dev = n_dev; A.init_pose = init_pose_dev;
+    A.points = points_dev; A.work = work_dev; A.n_max = n_max; A.n_dev = n_dev;
+    for (int k = 0; k < 7; ++k) A.init_pose[k] = init_pose_host[k];
     A.tau_sq = tau * tau; A.th = th; A.max_iter = max_iter; A.eps = eps;
     A.partials = partials_dev; A.out = out13_dev;
     // grid barrier + exit counter live in the context's zero-initialised small area; the last CTA out re-arms them
@@ -560,7 +583,8 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
     }
     void *args[] = {&A};
     LIMU_TRY(prof_begin(c, LIMU_STAGE_ICP));
-    LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_icp_persistent, dim3(grid), dim3(ICP_BLOCK), args, 0, c->stream));
+    const void *fn = grouped ? (const void *)k_icp_persistent<0> : (const void *)k_icp_persistent<1>;
+    LIMU_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(ICP_BLOCK), args, 0, c->stream));
     LIMU_LAUNCHED();
     LIMU_TRY(prof_end(c, LIMU_STAGE_ICP));
     return LIMU_OK;
@@ -632,15 +656,14 @@ static int icp_sharded_nccl(limu_map *m, const double *points_dev, int64_t n, co
                             double eps, double pose_out[7], limu_icp_stats *stats) {
     limu_ctx *c = m->ctx;
     limu_comm *cm = c->comm;
-    double *dinit;
-    LIMU_TRY(stage_small(c, init_guess, 7, 0, &dinit));
     const int rows = icp_partial_rows(c);
     LIMU_TRY(c->tmp4.reserve((size_t)std::max<int64_t>(n, 1) * 24, c->stream));
     LIMU_TRY(c->tmp5.reserve((size_t)rows * NS * 8 + 256, c->stream));
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(div_up(std::max<int64_t>(n, 1), ICP_BLOCK), rows));
     IcpArgs A;
     memset(&A, 0, sizeof A);
-    A.map = m->view(); A.points = points_dev; A.work = c->tmp4.as<double>(); A.n_max = n; A.init_pose = dinit;
+    A.map = m->view(); A.points = points_dev; A.work = c->tmp4.as<double>(); A.n_max = n;
+    for (int k = 0; k < 7; ++k) A.init_pose[k] = init_guess[k];
     A.tau_sq = tau * tau; A.th = th; A.coop_scan = n >= 32768 ? 1 : 0; A.nranks = 1;
     double *state = cm->d_state;
     double *h = static_cast<double *>(c->h_pinned) + 256;
@@ -673,8 +696,6 @@ using namespace limu;
 static int icp_common(limu_map *m, const double *points_dev, int64_t n, const double init_guess[7], double tau, double th, int max_iter, double eps,
                       double pose_out[7], limu_icp_stats *stats, double *est_trace, int64_t *ncorr_trace, double *hg_trace, bool sharded = false) {
     limu_ctx *c = m->ctx;
-    double *dinit;
-    LIMU_TRY(stage_small(c, init_guess, 7, 0, &dinit));
     const int rows = icp_partial_rows(c);
     LIMU_TRY(c->tmp4.reserve((size_t)std::max<int64_t>(n, 1) * 24, c->stream));                 // working cloud
     LIMU_TRY(c->tmp5.reserve((size_t)2 * rows * NS * 8 + 256, c->stream));                     // partial rows
@@ -686,7 +707,7 @@ static int icp_common(limu_map *m, const double *points_dev, int64_t n, const do
     double *d_est = tr ? c->tmp3.as<double>() : nullptr;
     long long *d_nc = tr ? reinterpret_cast<long long *>(d_est + it * 7) : nullptr;
     double *d_hg = tr ? d_est + it * 8 : nullptr;
-    LIMU_TRY(icp_device(m, points_dev, c->tmp4.as<double>(), n, nullptr, dinit, tau, th, max_iter, eps, partials, (size_t)rows, out13, n,
+    LIMU_TRY(icp_device(m, points_dev, c->tmp4.as<double>(), n, nullptr, init_guess, tau, th, max_iter, eps, partials, (size_t)rows, out13, n,
                         d_est, d_nc, d_hg, sharded ? max_iter : -1, nullptr));
     double *h = static_cast<double *>(c->h_pinned) + 16;
     LIMU_CUDA_TRY(cudaMemcpyAsync(h, out13, 13 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

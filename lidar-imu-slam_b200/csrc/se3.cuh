@@ -100,8 +100,10 @@ LIMU_HD void mat3vec(const double *A, const double *v, double *o) {
 }
 
 // SE3::exp, se3.hpp:852-861; SO3::expAndTheta so3.hpp:694-732; SO3::leftJacobian so3.hpp:550-571.
-LIMU_HD Pose se3_exp(const double *a) {
-    const double *ups = a, *om = a + 3;
+// The two halves below (rotation / translation) are independent given the twist; the Gauss-Newton solve evaluates them
+// on two lanes at once. se3_exp() is their composition and is bit-identical to Sophus on x86-64.
+LIMU_HD void se3_exp_rotation(const double *a, double *q /* x y z w */, double *theta_out) {
+    const double *om = a + 3;
     const double theta_sq = sqnorm3(om[0], om[1], om[2]);
     double theta, imag, real;
     if (theta_sq < LIMU_SOPHUS_EPS * LIMU_SOPHUS_EPS) {
@@ -115,10 +117,15 @@ LIMU_HD Pose se3_exp(const double *a) {
         imag = sin(half) / theta;
         real = cos(half);
     }
-    Pose T;
-    T.qw = real; T.qx = imag * om[0]; T.qy = imag * om[1]; T.qz = imag * om[2];
+    q[3] = real; q[0] = imag * om[0]; q[1] = imag * om[1]; q[2] = imag * om[2];
+    *theta_out = theta;
+}
+LIMU_HD void se3_exp_translation(const double *a, double *t) {
+    const double *ups = a, *om = a + 3;
+    const double theta_sq = sqnorm3(om[0], om[1], om[2]);
+    const double theta = theta_sq < LIMU_SOPHUS_EPS * LIMU_SOPHUS_EPS ? 0.0 : sqrt(theta_sq);
     const double tsq = theta * theta;  // leftJacobian(omega, theta) recomputes theta^2 (so3.hpp:556)
-    double Om[9], Om2[9], V[9], t[3];
+    double Om[9], Om2[9], V[9];
     hat(om, Om);
     mat3mul(Om, Om, Om2);
     if (tsq < LIMU_SOPHUS_EPS * LIMU_SOPHUS_EPS) {
@@ -130,8 +137,12 @@ LIMU_HD Pose se3_exp(const double *a) {
         for (int i = 0; i < 9; ++i) V[i] = (((i % 4 == 0) ? 1.0 : 0.0) + c1 * Om[i]) + c2 * Om2[i];
     }
     mat3vec(V, ups, t);
-    T.tx = t[0]; T.ty = t[1]; T.tz = t[2];
-    return T;
+}
+LIMU_HD Pose se3_exp(const double *a) {
+    double q[4], t[3], theta;
+    se3_exp_rotation(a, q, &theta);
+    se3_exp_translation(a, t);
+    return Pose{q[0], q[1], q[2], q[3], t[0], t[1], t[2]};
 }
 
 // SE3::log, se3.hpp:237-253; SO3::logAndTheta so3.hpp:264-310; leftJacobianInverse so3.hpp:573-597.
@@ -190,6 +201,9 @@ LIMU_HD void ldlt6_solve(const double *Ain, const double *b, double *x) {
 #pragma unroll
         for (int j = 0; j < 6; ++j) a[i][j] = Ain[6 * i + j];
     int tr[6];
+    double inv[6];       // 1 / D_k: FP64 division is a ~200-cycle subroutine on the device and this solve sits on the critical
+                         // path of every Gauss-Newton iteration, so each pivot is inverted once (one division per column instead of
+                         // up to six; entries of L and the solution then differ from Eigen's by <= 1 ulp per operation)
     bool zero = false;   // "entire diagonal is zero" exit of LDLT.h:364-375
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -230,10 +244,13 @@ LIMU_HD void ldlt6_solve(const double *Ain, const double *b, double *x) {
             const double akk = a[k][k];
             const bool valid = fabs(akk) > 0.0;
             if (k == 0 && !valid) zero = true;
+            inv[k] = fabs(akk) > 2.2250738585072014e-308 ? 1.0 / akk : 0.0;   // pseudo-inverse of D (LDLT.h:590-596)
             if (valid) {
 #pragma unroll
-                for (int r = k + 1; r < 6; ++r) a[r][k] /= akk;
+                for (int r = k + 1; r < 6; ++r) a[r][k] *= inv[k];
             }
+        } else {
+            inv[k] = 0.0;
         }
     }
     double d[6];
@@ -249,7 +266,7 @@ LIMU_HD void ldlt6_solve(const double *Ain, const double *b, double *x) {
 #pragma unroll
         for (int c = 0; c < i; ++c) d[i] -= a[i][c] * d[c];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { if (fabs(a[i][i]) > 2.2250738585072014e-308) d[i] /= a[i][i]; else d[i] = 0.0; }
+    for (int i = 0; i < 6; ++i) d[i] *= inv[i];
 #pragma unroll
     for (int i = 5; i >= 0; --i)
 #pragma unroll

@@ -23,7 +23,7 @@ struct VoxelizeArgs {
     const void *raw;            // mode 0: float4 {x,y,z,t}; mode 1: records `stride` bytes apart + ts; mode 2: double xyz (already a frame)
     const double *ts;
     int mode, stride, deskew;
-    const double *twist;        // 6 doubles (device), read when deskew != 0
+    double twist[6];            // by value, read when deskew != 0
     int64_t n;
     double vs1, vs2;            // 0.5 v and 1.5 v (icp.cpp:129-130)
     double *frame, *down, *src0;
@@ -181,7 +181,7 @@ static int g_vx_blocks_per_sm = 0;
 static int64_t pow2_slots(int64_t n) { int64_t p = 1024; while (p < 2 * n) p <<= 1; return p; }
 
 // Enqueue the fused kernel. raw/ts/twist are device pointers; outputs: frame (n x 3), down, src0, counts[0..1].
-int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int mode, int stride, const double *ts_dev, int deskew, const double *twist_dev,
+int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int mode, int stride, const double *ts_dev, int deskew, const double *twist_host,
                     int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev) {
     if (n <= 0) { LIMU_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int), c->stream)); return LIMU_OK; }
     if (g_vx_blocks_per_sm == 0) {
@@ -197,7 +197,8 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     LIMU_TRY(sc.pslot.reserve((size_t)n * 8, c->stream));
     LIMU_TRY(sc.tiles.reserve((size_t)ntiles * 8 + 64, c->stream));
     VoxelizeArgs A;
-    A.raw = raw_dev; A.ts = ts_dev; A.mode = mode; A.stride = stride; A.deskew = deskew; A.twist = twist_dev; A.n = n;
+    A.raw = raw_dev; A.ts = ts_dev; A.mode = mode; A.stride = stride; A.deskew = deskew; A.n = n;
+    for (int k = 0; k < 6; ++k) A.twist[k] = (deskew && twist_host) ? twist_host[k] : 0.0;
     A.vs1 = v * 0.5; A.vs2 = v * 1.5;
     A.frame = frame_dev; A.down = down_dev; A.src0 = src0_dev;
     A.keys1 = sc.table.as<unsigned long long>();

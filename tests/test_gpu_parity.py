@@ -277,3 +277,26 @@ def test_no_cpu_fallback_and_errors(pkg, ctx):
     gm.close()
     with pytest.raises(pkg.LimuError):
         ctx.VoxelHashMap(1.0, 100.0, 0)
+
+
+def test_prefetch_gives_identical_results(ctx, pkg):
+    """limu_odom_prefetch (double-buffered upload of the next scan) must not change anything."""
+    from importlib import import_module
+    synth = import_module("limu_b200.synth")
+    scene = synth.Scene(seed=9)
+    traj = synth.loop_trajectory(7, radius=30.0, step=0.7)
+    scans = [synth.cast_scan(scene, traj[i], traj[i + 1], beams=16, azimuth_steps=600, seed=70 + i) for i in range(6)]
+    pinned = [pkg.PinnedArray(s.shape, np.float32) for s in scans]
+    for p, s in zip(pinned, scans):
+        p.array[...] = s
+    a, b = ctx.KissICP(deskew=True, icp_max_iteration=60), ctx.KissICP(deskew=True, icp_max_iteration=60)
+    for i in range(6):
+        if i + 1 < 6:
+            b.prefetch(pinned[i + 1].array)
+        da, sa, pa = a.register_frame(pinned[i].array)
+        db, sb, pb = b.register_frame(pinned[i].array)
+        assert np.array_equal(da, db) and np.array_equal(sa, sb) and np.array_equal(pa, pb)
+    a.close()
+    b.close()
+    for p in pinned:
+        p.free()
