@@ -114,6 +114,23 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu --set full
+    capture of this same command (profiles/r1_frame_kernels_ncu.json; cold cache). None if the capture is absent."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_frame_kernels_ncu.json")))
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = []
+        for l in d["launches"]:
+            if "k_icp_persistent" in l["kernel"]:
+                r, ru = l["dram__bytes_read.sum"].split()
+                w, wu = l["dram__bytes_write.sum"].split()
+                vals.append(float(r) * unit[ru] + float(w) * unit[wu])
+        return float(np.mean(vals)) if vals else None
+    except Exception:
+        return None
+
+
 def k4_bytes(n_q, iters, kbar, fmiss):
     """Algorithmic bytes of the fused registration loop: per query per iteration
     24 B query + 16 B own-voxel slot + 24*kbar B candidate points + fmiss * 27 * 16 B fallback probes."""
@@ -304,14 +321,14 @@ def main():
                 "icp_max_iteration": args.max_iter,
             },
             "mpoints_per_s": value * n_pts / 1e6,
-            "iterations_per_scan": iters_total / K,
+            "iterations_per_scan": iters_total / K, "scans_at_iteration_cap": int((fr[:, 1] >= args.max_iter).sum()),
             "keypoints_per_scan": float(fr[:, 0].mean()), "downsampled_per_scan": float(fr[:, 4].mean()),
             "k_bar": float(fr[:, 2].mean()), "f_miss": float(fr[:, 3].mean()),
             "e2e": {"value": n_gpus * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": scan_bytes, "d2h_bytes_per_step": int(e2e_d2h),
                     "api": "limu_odom_register_frame (host pointers, pinned) with limu_odom_prefetch of the following scan: every step uploads one 2 MB scan (overlapped with the previous step's kernels) and reads back pose + downsampled + keypoint clouds"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_icp_persistent<latency> (one launch per scan: IQR filter + fused correspondence/residual/Jacobian/normal-equation Gauss-Newton loop + map insert + eviction sweep)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / max(nframes, 1), "avg_launch_ms": icp_ms / max(nframes, 1),
                          "share_of_step": stage_share.get("icp"),
                          "registration_loop_bytes_per_launch": icp_only_bytes / max(nframes, 1),
