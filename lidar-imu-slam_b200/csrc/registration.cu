@@ -288,6 +288,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
     __shared__ double S[NS];
     __shared__ double E[7], Tinit[7], Ticp[7];
     __shared__ int done;
+    __shared__ int comm_dead;
     __shared__ IqrSmem iqr_sm;
     GridSync gs{A.barrier, 0u, gridDim.x};
     GridSync gs_icp{A.barrier_icp, 0u, (unsigned int)A.icp_blocks};
@@ -303,6 +304,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
     const bool run_icp = !(__ldcg(A.map_counters) == 0ull || A.max_iter <= 0);   // ICP :99-100: empty map -> init_guess
     if (threadIdx.x < 7) { Tinit[threadIdx.x] = A.init_pose[threadIdx.x]; Ticp[threadIdx.x] = threadIdx.x == 3 ? 1.0 : 0.0; }
     if (threadIdx.x < NS) S[threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) comm_dead = 0;
     __syncthreads();
     const int64_t wbase = ((int64_t)blockIdx.x * (ICP_BLOCK / 32) + warp) * 32, wstride = (int64_t)A.icp_blocks * ICP_BLOCK;
     int j = 0;
@@ -384,10 +386,11 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
                 do {
                     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                    if (t1 - t0 > 5000000000ull) { *A.comm_error = 1; break; }   // 5 s: a peer never arrived
+                    if (t1 - t0 > 2000000000ull) { *A.comm_error = 1; comm_dead = 1; break; }   // 2 s: a peer never arrived
                 } while (v != stamp);
             }
             __syncthreads();
+            if (comm_dead) break;   // every CTA of this rank times out the same way; the host reports LIMU_ERR_COMM
             if (threadIdx.x < NS) {
                 double v = 0.0;
                 for (int r = 0; r < A.nranks; ++r) v += *reinterpret_cast<const volatile double *>(A.mbox_local + par + (size_t)r * MBOX_ROW + threadIdx.x);
@@ -722,7 +725,7 @@ static int icp_common(limu_map *m, const double *points_dev, int64_t n, const do
     if (sharded && c->comm && c->comm->nranks > 1) {
         int err = 0;
         LIMU_CUDA_TRY(cudaMemcpy(&err, c->comm->d_error, sizeof(int), cudaMemcpyDeviceToHost));
-        if (err) { set_error("limu_icp_sharded: a peer rank did not reach the exchange within 5 s"); cudaMemset(c->comm->d_error, 0, sizeof(int)); return LIMU_ERR_COMM; }
+        if (err) { set_error("limu_icp_sharded: a peer rank did not reach the exchange within 2 s"); cudaMemset(c->comm->d_error, 0, sizeof(int)); return LIMU_ERR_COMM; }
     }
     if (tr && iters > 0) {
         if (est_trace) LIMU_CUDA_TRY(cudaMemcpyAsync(est_trace, d_est, (size_t)iters * 56, cudaMemcpyDeviceToHost, c->stream));

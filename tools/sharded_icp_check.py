@@ -19,16 +19,28 @@ ap.add_argument("--queries", default="100000,4194304")
 ap.add_argument("--voxels", type=float, default=1.0e6)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--no-nccl", action="store_true", help="skip the un-fused NCCL baseline (forced above 2 ranks, see profiles/r1_multi_gpu_sharded_icp.json)")
+ap.add_argument("--alarm", type=int, default=180, help="hard wall-clock limit of this process (s)")
 args = ap.parse_args()
+import signal
+signal.alarm(args.alarm)      # never hold a multi-GPU box on a hang
+
+
+def log(msg):
+    print(f"[rank {os.environ.get('RANK', 0)}] {msg}", file=sys.stderr, flush=True)
 
 rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+if world > 2:
+    args.no_nccl = True
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 pkg = g.load_package()
 from importlib import import_module
 sh = import_module("limu_b200.sharding")
 ctx = pkg.Context(local)
-sh.connect(ctx, nccl_baseline=True)
+log("context ok")
+sh.connect(ctx, nccl_baseline=not args.no_nccl)
+log("communicator connected")
 ext = torch.cuda.ExternalStream(ctx.stream())
 
 # replicated map: every rank inserts the same seeded points
@@ -45,6 +57,7 @@ while done < total:
     torch.cuda.synchronize()
     m.insert_points_dev(p.data_ptr(), n)
     done += n
+log("map built")
 sizes = [None] * world
 dist.all_gather_object(sizes, m.size())
 ok = all(s == sizes[0] for s in sizes)
@@ -75,8 +88,14 @@ for nq in [int(x) for x in args.queries.split(",")]:
     lo, hi = sh.shard_range(nq, rank, world)
     shard = q[lo:hi].contiguous()
     single = m.icp_dev(q.data_ptr(), nq, init, 1.5, 0.5, args.iters, 1e-9)            # every rank: the 1-GPU answer
+    log(f"nq={nq}: single-GPU done ({single['iters']} iterations)")
     t_fused, fused = timed(lambda: m.icp_sharded_dev(shard.data_ptr(), hi - lo, init, 1.5, 0.5, args.iters, 1e-9, mode=0))
-    t_nccl, nccl = timed(lambda: m.icp_sharded_dev(shard.data_ptr(), hi - lo, init, 1.5, 0.5, args.iters, 1e-9, mode=1))
+    log(f"nq={nq}: fused sharded done")
+    if args.no_nccl:
+        t_nccl, nccl = t_fused, fused
+    else:
+        t_nccl, nccl = timed(lambda: m.icp_sharded_dev(shard.data_ptr(), hi - lo, init, 1.5, 0.5, args.iters, 1e-9, mode=1))
+        log(f"nq={nq}: NCCL baseline done")
     t_single, _ = timed(lambda: m.icp_dev(q.data_ptr(), nq, init, 1.5, 0.5, args.iters, 1e-9))
     poses = [None] * world
     dist.all_gather_object(poses, (fused["pose"].tolist(), nccl["pose"].tolist(), fused["iters"], nccl["iters"]))
