@@ -81,6 +81,16 @@ int limu_deskew(limu_ctx *c, const float *xyzt, int64_t n, const double T0[7], c
  * (pcl::PointXYZINormal = 48 B, types.hpp:36) and FP64 timestamps (std::vector<double>). */
 int limu_deskew_cloud(limu_ctx *c, const void *points, int32_t stride_bytes, const double *timestamps, int64_t n, const double T0[7],
                       const double T1[7], double *out_xyz);
+/* IMU-propagated backward deskew: the per-point loop of kalman::EKF::motion_compensation_with_imu, L/src/kalman/ekf.cpp:420-468
+ * (dead code at runtime in the reference). The host IMU forward pass (:315-410) supplies: `table` = its
+ * kalman::Pose6D rows (ekf.hpp:88-105), rot_end (row-major) and pos_lidar_end (:393-418), p_imu_lidar = state POS_IMU_LIDAR.
+ * points: records stride_bytes apart with float x,y,z at offset 0 and the float per-point offset time in ms (PCL
+ * `curvature`: offset 36 in pcl::PointXYZINormal) at curvature_offset_bytes, sorted by that time (lidar/frame.cpp:28-51).
+ * out_xyz (optional, n x 3 doubles) = meas->deskewed (:458-468); write_back != 0 also stores the float x,y,z into the records (:451-453). */
+typedef struct limu_imu_pose { double offset_time, acc[3], gyr[3], vel[3], pos[3], rot[9]; } limu_imu_pose;
+int limu_deskew_imu(limu_ctx *c, void *points, int32_t stride_bytes, int32_t curvature_offset_bytes, int64_t n, const limu_imu_pose *table,
+                    int32_t n_poses, const double rot_end[9], const double pos_lidar_end[3], const double p_imu_lidar[3], double *out_xyz,
+                    int32_t write_back);
 /* voxel_downsample (file-local), sensors/lidar/icp.cpp:9-30: first point per voxel of edge s wins;
  * output in first-occurrence order. out_xyz must hold n points; out_idx (optional) the source indices. */
 int limu_voxel_downsample(limu_ctx *c, const double *xyz, int64_t n, double s, double *out_xyz, int64_t *out_idx, int64_t *n_out);

@@ -85,6 +85,7 @@ def lib():
             "limu_transform_points": [_vp, _dp, _dp, C.c_int64],
             "limu_deskew": [_vp, _fp, C.c_int64, _dp, _dp, _dp],
             "limu_deskew_cloud": [_vp, _vp, C.c_int32, _dp, C.c_int64, _dp, _dp, _dp],
+            "limu_deskew_imu": [_vp, _vp, C.c_int32, C.c_int32, C.c_int64, _dp, C.c_int32, _dp, _dp, _dp, _dp, C.c_int32],
             "limu_odom_register_cloud": [_vp, _vp, C.c_int32, _dp, C.c_int64, _dp, _dp, _lp, _dp, _lp, C.POINTER(FrameStats)],
             "limu_voxel_downsample": [_vp, _dp, C.c_int64, C.c_double, _dp, _lp, _lp],
             "limu_iqr_filter": [_vp, _dp, C.c_int64, _dp, _lp, _dp],
@@ -278,6 +279,16 @@ class Context:
         out = np.empty((len(ts), 3))
         _chk(lib().limu_deskew_cloud(self.h, rec.ctypes.data_as(_vp), int(stride_bytes), _d(ts), len(ts), _d(_pose(T0)), _d(_pose(T1)), _d(out)))
         return out
+
+    def deskew_imu(self, xyzc_f32, table, rot_end, pos_lidar_end, p_imu_lidar):
+        """EKF::motion_compensation_with_imu's per-point loop. xyzc = float32 [n,4] rows (x, y, z, curvature_ms) sorted by time;
+        table = [M,22] kalman::Pose6D rows. Returns (deskewed float64 [n,3], written-back float32 [n,3])."""
+        rec = np.ascontiguousarray(xyzc_f32, np.float32).reshape(-1, 4).copy()
+        t = np.ascontiguousarray(table, np.float64).reshape(-1, 22)
+        out = np.empty((len(rec), 3))
+        re, pe, pil = (np.ascontiguousarray(v, np.float64) for v in (rot_end, pos_lidar_end, p_imu_lidar))
+        _chk(lib().limu_deskew_imu(self.h, rec.ctypes.data_as(_vp), 16, 12, len(rec), _d(t), len(t), _d(re), _d(pe), _d(pil), _d(out), 1))
+        return out, rec[:, :3].copy()
 
     def voxel_downsample(self, xyz, s, with_index=False):
         xyz = _pts(xyz)

@@ -95,6 +95,10 @@ class _Api:
         f("map_remove_far", None, [C.c_void_p, _dp])
         f("map_dump", C.c_long, [C.c_void_p, _ip, _ip, _dp, C.c_long, C.c_long, _lp])
         f("deskew", None, [_fp, _dp, C.c_long, _dp, _dp, _dp])
+        if kind == "port":
+            f("deskew_imu", None, [_fp, _fp, C.c_long, _dp, C.c_long, _dp, _dp, _dp, _dp])
+        elif hasattr(lib, "ref_imu_deskew"):
+            f("imu_deskew", C.c_long, [_fp, _fp, C.c_long, _dp, C.c_long, C.c_double, _dp, _dp, _dp, _dp, _dp, C.c_long, _dp, _dp, _fp])
         if kind == "reference":
             f("map_closest", None, [C.c_void_p, _dp, C.c_long, _dp])
             f("map_correspondences", C.c_long, [C.c_void_p, _dp, C.c_long, C.c_double, _dp, _dp])
@@ -192,6 +196,33 @@ class _Api:
         out = np.empty((len(x), 3))
         self._deskew(_f(x), _d(ts), len(x), _d(T0), _d(T1), _d(out))
         return out
+
+    def imu_deskew_reference(self, xyz_f32, curv_ms, imu, lidar_beg_time, mean_acc, p_imu_lidar, gyro_bias):
+        """REFERENCE ONLY: run kalman::EKF::motion_compensation_with_imu (ekf.cpp:292-469) on one scan + IMU window.
+        Returns dict(deskewed [n,3] f64, written_back [n,3] f32, table [M,22], rot_end [9], pos_lidar_end [3])."""
+        assert self.kind == "reference"
+        x = np.ascontiguousarray(xyz_f32, np.float32).reshape(-1, 3)
+        c = np.ascontiguousarray(curv_ms, np.float32)
+        imu = np.ascontiguousarray(imu, np.float64).reshape(-1, 7)
+        out = np.empty((len(x), 3))
+        wb = np.empty((len(x), 3), np.float32)
+        table = np.zeros((len(imu) + 4, 22))
+        rot_end, ple = np.empty(9), np.empty(3)
+        ma, pil, gb = (np.ascontiguousarray(v, np.float64) for v in (mean_acc, p_imu_lidar, gyro_bias))
+        M = self._imu_deskew(_f(x), _f(c), len(x), _d(imu), len(imu), float(lidar_beg_time), _d(ma), _d(pil), _d(gb), _d(out), _d(table), len(table),
+                             _d(rot_end), _d(ple), _f(wb))
+        return {"deskewed": out, "written_back": wb, "table": table[:M].copy(), "rot_end": rot_end, "pos_lidar_end": ple}
+
+    def deskew_imu(self, xyz_f32, curv_ms, table, rot_end, pos_lidar_end, p_imu_lidar):
+        """PORT ONLY: per-point loop of motion_compensation_with_imu (ekf.cpp:420-468). Returns (deskewed f64, written-back f32)."""
+        assert self.kind == "port"
+        x = np.ascontiguousarray(xyz_f32, np.float32).reshape(-1, 3).copy()
+        c = np.ascontiguousarray(curv_ms, np.float32)
+        t = np.ascontiguousarray(table, np.float64).reshape(-1, 22)
+        out = np.empty((len(x), 3))
+        re, pe, pil = (np.ascontiguousarray(v, np.float64) for v in (rot_end, pos_lidar_end, p_imu_lidar))
+        self._deskew_imu(_f(x), _f(c), len(x), _d(t), len(t), _d(re), _d(pe), _d(pil), _d(out))
+        return out, x
 
     def align(self, src, tgt, th):
         """Returns dict(pose=7) for the reference; the port adds H (6x6), g (6), x (6)."""

@@ -553,6 +553,52 @@ void lo_deskew(const float *xyz, const double *ts, long n, const double *T0, con
 }
 
 /* ================================================================================================
+ * IMU-propagated backward deskew: kalman/ekf.cpp:420-468, kalman/helper.hpp:35-40
+ * ============================================================================================== */
+/* utils::ang_vel_to_rmat (helper.hpp:35-40): Eigen::AngleAxisd(dt*|w|, w.normalized()).toRotationMatrix()
+ * (Eigen/src/Geometry/AngleAxis.h toRotationMatrix; normalized(): v / sqrt(squaredNorm) when squaredNorm > 0). */
+static void ang_vel_to_rmat(const double *w, double dt, double *R) {
+    const double z = sqn3(w[0], w[1], w[2]);
+    const double nrm = sqrt(z);
+    double ax[3] = {w[0], w[1], w[2]};
+    if (z > 0.0) { ax[0] = w[0] / nrm; ax[1] = w[1] / nrm; ax[2] = w[2] / nrm; }
+    const double angle = dt * nrm;
+    const double s = sin(angle), c = cos(angle);
+    const double sx = s * ax[0], sy = s * ax[1], sz = s * ax[2];
+    const double cx = (1.0 - c) * ax[0], cy = (1.0 - c) * ax[1], cz = (1.0 - c) * ax[2];
+    double tmp;
+    tmp = cx * ax[1]; R[1] = tmp - sz; R[3] = tmp + sz;
+    tmp = cx * ax[2]; R[2] = tmp + sy; R[6] = tmp - sy;
+    tmp = cy * ax[2]; R[5] = tmp - sx; R[7] = tmp + sx;
+    R[0] = cx * ax[0] + c; R[4] = cy * ax[1] + c; R[8] = cz * ax[2] + c;
+}
+void lo_deskew_imu(float *xyz, const float *curv_ms, long n, const double *table, long M, const double *rot_end, const double *pos_lidar_end,
+                   const double *p_il, double *out) {
+    long i = n - 1;
+    for (long h = M - 2; h >= 0 && n > 0; --h) {                       /* it_kp = end-1 .. begin+1, head = *(it_kp-1) (:422-424) */
+        const double *T = table + 22 * h;
+        const double off = T[0], *acc = T + 1, *gyr = T + 4, *vel = T + 7, *pos = T + 10, *Rimu = T + 13;
+        for (; (double)curv_ms[i] / 1000.0 > off; --i) {                /* :433 */
+            const double dt = (double)curv_ms[i] / 1000.0 - off;        /* :435 */
+            double Rw[9], Ri[9], t1[3], t2[3];
+            ang_vel_to_rmat(gyr, dt, Rw);
+            mat3_mul(Rimu, Rw, Ri);                                     /* R_i = R_imu * ang_vel_to_rmat(gyr, dt) :444 */
+            mat3_vec(Ri, p_il, t1);
+            double Tei[3];
+            for (int a = 0; a < 3; ++a) Tei[a] = (((pos[a] + vel[a] * dt) + (0.5 * acc[a]) * (dt * dt)) + t1[a]) - pos_lidar_end[a];   /* :445 */
+            const double P[3] = {(double)xyz[3 * i], (double)xyz[3 * i + 1], (double)xyz[3 * i + 2]};
+            mat3_vec(Ri, P, t2);
+            const double v[3] = {t2[0] + Tei[0], t2[1] + Tei[1], t2[2] + Tei[2]};
+            for (int a = 0; a < 3; ++a)                                 /* rot_end^T * v :448, stored as float :451-453 */
+                xyz[3 * i + a] = (float)((rot_end[a] * v[0] + rot_end[3 + a] * v[1]) + rot_end[6 + a] * v[2]);
+            if (i == 0) break;                                          /* :455-456: the first point is NOT consumed, so every remaining
+                                                                         * (older) head whose offset is below its time compensates it AGAIN */
+        }
+    }
+    for (long k = 0; k < 3 * n; ++k) out[k] = (double)xyz[k];           /* :458-468 */
+}
+
+/* ================================================================================================
  * Downsampling and IQR: icp.cpp:9-30, :88-136, common.hpp:22-63
  * ============================================================================================== */
 long lo_voxel_downsample(const double *xyz, long n, double s, double *out, long *out_idx) {

@@ -59,6 +59,15 @@ int lo_icp(const lo_map *m, const double *xyz, long n, const double *init7, doub
 /* ---- deskew.cpp :10-28 ---------------------------------------------------------------------------- */
 void lo_deskew(const float *xyz, const double *ts, long n, const double *T0, const double *T1, double *out);
 
+/* ---- IMU-propagated backward deskew: per-point loop of kalman::EKF::motion_compensation_with_imu, L/src/kalman/ekf.cpp:420-468
+ * (dead code at runtime in the reference). table: M rows of 22 doubles = kalman::Pose6D
+ * {offset_time, acc[3], gyr[3], vel[3], pos[3], rot[9] row-major} (ekf.hpp:88-105) built by the host IMU forward pass (:315-391);
+ * rot_end / pos_lidar_end: scan-end IMU rotation and lidar position (:393-418); p_il: IMU->lidar translation (state
+ * POS_IMU_LIDAR). curv_ms: per-point offset time in ms (PCL `curvature`), points sorted by it (lidar/frame.cpp:28-51).
+ * Writes the compensated xyz back as FLOAT (like :449-451) into xyz_f32 (in place) and widened to double into out. */
+void lo_deskew_imu(float *xyz_f32, const float *curv_ms, long n, const double *table, long M, const double *rot_end9,
+                   const double *pos_lidar_end3, const double *p_il3, double *out);
+
 /* ---- icp.cpp ---------------------------------------------------------------------------------------- */
 long lo_voxel_downsample(const double *xyz, long n, double s, double *out, long *out_idx);   /* :9-30 */
 long lo_iqr(const double *xyz, long n, double *out, double *bounds2);                         /* :88-124, common.hpp:22-63 */

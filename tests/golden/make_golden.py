@@ -151,6 +151,22 @@ def path_fixtures(ref):
     T0 = ref.se3_exp(np.array([4.0, 1.0, 0.0, 0.0, 0.01, 0.3]))
     T1 = ref.se3_mul(T0, ref.se3_exp(np.array([1.0, 0.1, -0.05, 0.01, -0.02, 0.1])))
     out.update(dk_xyz=xyz, dk_ts=ts, dk_T0=T0, dk_T1=T1, dk_out=ref.deskew(xyz, ts, T0, T1))
+    # IMU-propagated backward deskew (kalman::EKF::motion_compensation_with_imu, ekf.cpp:292-469): 200 Hz IMU window,
+    # turning + accelerating platform; the first point sits at t > 0 so the reference's repeated compensation of the
+    # never-consumed first point (:455-456) is part of the fixture
+    kimu, nimu = 22, 4000
+    t0 = 100.0
+    its = t0 - 0.004 + np.arange(kimu) * 0.005
+    gyr = np.array([0.02, -0.01, 0.35]) + rng.normal(size=(kimu, 3)) * 0.002
+    acc = np.array([0.3, -0.2, 9.81]) + rng.normal(size=(kimu, 3)) * 0.03
+    imu = np.concatenate([its[:, None], gyr, acc], 1)
+    curv = np.sort(rng.random(nimu) * 100.0).astype(np.float32)
+    curv[0] = 0.37
+    ixyz = (rng.normal(size=(nimu, 3)) * 25).astype(np.float32)
+    pil = np.array([0.1, -0.05, 0.2])
+    r = ref.imu_deskew_reference(ixyz, curv, imu, t0, [0.3, -0.2, 9.81], pil, [0.001, 0.002, -0.001])
+    out.update(imu_xyz=ixyz, imu_curv=curv, imu_table=r["table"], imu_rot_end=r["rot_end"], imu_pos_lidar_end=r["pos_lidar_end"], imu_pil=pil,
+               imu_deskewed=r["deskewed"], imu_written_back=r["written_back"])
     # KissICP sequence (register_frame x 6, deskew on), scans from the package's own generator
     import __graft_entry__ as g
     g.load_package()
