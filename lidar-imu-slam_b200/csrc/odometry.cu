@@ -58,7 +58,6 @@ struct limu_odom {
     limu::Pose model_deviation = limu::pose_identity();
     // device buffers
     limu::DevBuf raw, ts, frame, down, src0, src, work, world, partials, d2;
-    limu::StageScratch sa, sb;
     limu::VoxelizeScratch vx;
     int64_t nk_hint = 4096, nd_hint = 16384;
     // limu_odom_prefetch: the next scan is uploaded on its own stream while the current one is being registered
@@ -217,7 +216,7 @@ void limu_odom_destroy(limu_odom *o) {
     if (o->copy_stream) { cudaStreamSynchronize(o->copy_stream); cudaStreamDestroy(o->copy_stream); cudaEventDestroy(o->pf_done[0]); cudaEventDestroy(o->pf_done[1]); }
     DevBuf *bufs[] = {&o->pf_buf[0], &o->pf_buf[1], &o->d2, &o->raw, &o->ts, &o->frame, &o->down, &o->src0, &o->src, &o->work, &o->world, &o->partials};
     for (auto *b : bufs) b->release();
-    o->sa.release(); o->sb.release(); o->vx.release();
+    o->vx.release();
     delete o;
 }
 

@@ -181,7 +181,7 @@ int iqr_device(limu_ctx *c, StageScratch &sc, const double *xyz_dev, int64_t n_m
 }
 
 // Stage scratch of the stateless C entry points, one pair per context (the voxelize chain uses both).
-struct CtxScratch { StageScratch a, b; };
+struct CtxScratch { StageScratch a, b; VoxelizeScratch vx; };
 static std::mutex g_sc_mu;
 static std::unordered_map<limu_ctx *, CtxScratch *> g_sc;
 static StageScratch *scratch_of(limu_ctx *c, int which) {
@@ -190,11 +190,16 @@ static StageScratch *scratch_of(limu_ctx *c, int which) {
     if (it == g_sc.end()) it = g_sc.emplace(c, new CtxScratch).first;
     return which == 0 ? &it->second->a : &it->second->b;
 }
+static VoxelizeScratch *vx_scratch_of(limu_ctx *c) {
+    scratch_of(c, 0);
+    std::lock_guard<std::mutex> lk(g_sc_mu);
+    return &g_sc.find(c)->second->vx;
+}
 void release_ctx_scratch(limu_ctx *c) {
     std::lock_guard<std::mutex> lk(g_sc_mu);
     auto it = g_sc.find(c);
     if (it == g_sc.end()) return;
-    it->second->a.release(); it->second->b.release();
+    it->second->a.release(); it->second->b.release(); it->second->vx.release();
     delete it->second;
     g_sc.erase(it);
 }
@@ -317,14 +322,15 @@ int limu_voxelize(limu_ctx *c, const double *xyz, int64_t n, double v, double *s
     LIMU_REQUIRE(n >= 0 && n_src && n_down && v > 0 && (n == 0 || xyz), "limu_voxelize: bad arguments");
     *n_src = *n_down = 0;
     if (n == 0) return LIMU_OK;
-    StageScratch &sa = *scratch_of(c, 0), &sb = *scratch_of(c, 1);
+    StageScratch &sb = *scratch_of(c, 1);
     LIMU_TRY(stage_in(c, c->in0, xyz, (size_t)n * 24));
+    LIMU_TRY(c->in1.reserve((size_t)n * 24, c->stream));    // frame copy written by the fused kernel
     LIMU_TRY(c->out0.reserve((size_t)n * 24, c->stream));   // down
     LIMU_TRY(c->out1.reserve((size_t)n * 24, c->stream));   // ds(down, 1.5v)
     LIMU_TRY(c->out2.reserve((size_t)n * 24, c->stream));   // after IQR
     int *cnt = reinterpret_cast<int *>(c->d_small.as<double>());   // [0]=n_down [1]=n_src0 [2]=n_src
-    LIMU_TRY(downsample_device(c, sa, c->in0.as<double>(), n, nullptr, v * 0.5, c->out0.as<double>(), cnt + 0));       // icp.cpp:129
-    LIMU_TRY(downsample_device(c, sb, c->out0.as<double>(), n, cnt + 0, v * 1.5, c->out1.as<double>(), cnt + 1));      // :130
+    LIMU_TRY(voxelize_device(c, *vx_scratch_of(c), c->in0.p, 2, 0, nullptr, 0, nullptr, n, v, c->in1.as<double>(), c->out0.as<double>(),
+                             c->out1.as<double>(), cnt + 0));                                                       // icp.cpp:129-130
     LIMU_TRY(iqr_device(c, sb, c->out1.as<double>(), n, cnt + 1, c->out2.as<double>(), cnt + 2, nullptr));             // :133
     int *h = static_cast<int *>(c->h_pinned);
     LIMU_CUDA_TRY(cudaMemcpyAsync(h, cnt, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
