@@ -205,6 +205,48 @@ int limu_odom_prediction(limu_odom *o, double pose_out[7]);        /* get_predic
 int limu_odom_has_moved(limu_odom *o, int *out);                   /* has_moved() icp.cpp:156-163 */
 limu_map *limu_odom_map(limu_odom *o);                             /* the local map (owned by the odometry handle) */
 
+/* ---- frame::Lidar::process_frame, L/src/sensors/lidar/frame.cpp:101-193 ------------------------------
+ * The host preprocessing in front of register_frame: range gate [min_range, max_range] + NaN drop (:143-145), per-point offset
+ * time in ms ("curvature", :156; or the constant-rotation model :159-182 when the last point carries no offset time), order by
+ * that time (sort_clouds :28-51), drop the first point and cut into frame_split_num segments (split_clouds :53-99), per-point
+ * timestamps via utils::get_time_stamps / normalize_timestamps (L/src/utils/calculation_helpers.cpp:3-81).
+ * Input: the sensor_msgs::PointCloud2 payload as it arrives (n records of point_step bytes). */
+typedef struct limu_cloud_fields {   /* byte offsets inside one record; -1 = the message has no such field (the member stays 0) */
+    int32_t point_step;
+    int32_t off_x, off_y, off_z;     /* FLOAT32: what pcl::fromROSMsg copies into the reference's LidarPoint (lidar/frame.hpp:12-23) */
+    int32_t off_intensity;           /* UINT8 */
+    int32_t off_ring;                /* UINT16 */
+    int32_t off_timestamp;           /* FLOAT64 LidarPoint::timestamp, absolute seconds */
+    int32_t off_time_field;          /* the field utils::get_time_stamps picks: the LAST one named "t", "timestamp" or "time" */
+    int32_t time_field_is_f64;       /* 1: that field is "time" (read as double, used as is); 0: "t"/"timestamp" (its first 4 bytes read as
+                                      * uint32 whatever the datatype, then divided by the maximum when that is >= 1) */
+} limu_cloud_fields;
+/* Applies the reference's field selection rules to a PointField list (names: nf NUL-terminated strings back to back; datatypes:
+ * sensor_msgs::PointField codes). LIMU_ERR_INVALID with the reference's exception text when no timestamp field exists. */
+int limu_cloud_fields_from_pointfields(int32_t nf, const char *names, const int32_t *offsets, const int32_t *datatypes, const int32_t *counts,
+                                       int32_t point_step, limu_cloud_fields *out);
+typedef struct limu_lidar_config {   /* frame::Lidar::ProcessingInfo, lidar/frame.hpp:39-45, defaults :64-70 */
+    double min_range, max_range, min_angle, max_angle, frame_rate;
+    int32_t num_scan_lines, frame_split_num;
+} limu_lidar_config;
+void limu_lidar_default_config(limu_lidar_config *cfg);
+/* scan_count: value of the reference's message counter during process_frame (initialize() has incremented it, frame.cpp:13): the
+ * 1-based index of this message; below MIN_SCAN_COUNT = 20 the frame is never split (:64).
+ * Outputs: segments back to back -- out_points (optional): 48-byte pcl::PointXYZINormal records {x,y,z,1 | 0,0,0,0 | intensity,
+ * curvature,0,0}, out_ts (optional): normalised FP64 timestamps, both with room for n entries; seg_sizes / seg_time
+ * (accumulated_segment_time, seconds) with room for max_segments. Points of EQUAL offset time keep message order (std::sort leaves
+ * their order unspecified in the reference). */
+int limu_preprocess_frame(limu_ctx *c, const void *data, int64_t n, const limu_cloud_fields *fields, const limu_lidar_config *cfg, double message_time,
+                          int32_t scan_count, void *out_points, double *out_ts, int32_t max_segments, int64_t *seg_sizes, double *seg_time,
+                          int32_t *n_segments);
+/* lidar_callback -> lidar_process -> estimate_lidar_odometry (L/src/odom_run.cpp:51-106) for one message: preprocess on the device, then
+ * register_frame on every segment straight from device memory (no host copy of the processed cloud). poses_out: 7 doubles per
+ * segment; stats (optional): one entry per segment. Segments of <= 1 point are skipped like odom_run.cpp:78-83 (their pose slot
+ * repeats the previous pose and seg_sizes keeps the size). */
+int limu_odom_register_msg(limu_odom *o, const void *data, int64_t n, const limu_cloud_fields *fields, const limu_lidar_config *cfg, double message_time,
+                           int32_t scan_count, int32_t max_segments, double *poses_out, int64_t *seg_sizes, double *seg_time, int32_t *n_segments,
+                           limu_frame_stats *stats);
+
 /* ---- host-side SE(3) helpers (the same restatement of Sophus 1.22.10 the device code uses) ------ */
 void limu_se3_exp(const double x[6], double pose_out[7]);
 void limu_se3_log(const double pose[7], double x_out[6]);

@@ -50,6 +50,38 @@ class FrameStats(C.Structure):
                 ("icp", IcpStats), ("deskewed", C.c_int32), ("reserved0", C.c_int32)]
 
 
+class CloudFields(C.Structure):
+    """Where a PointCloud2 payload keeps the members of the reference's LidarPoint (lidar/frame.hpp:12-23); -1 = absent."""
+    _fields_ = [("point_step", C.c_int32), ("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32), ("off_intensity", C.c_int32),
+                ("off_ring", C.c_int32), ("off_timestamp", C.c_int32), ("off_time_field", C.c_int32), ("time_field_is_f64", C.c_int32)]
+
+
+class LidarConfig(C.Structure):
+    """frame::Lidar::ProcessingInfo's sensor fields (lidar/frame.hpp:39-45)."""
+    _fields_ = [("min_range", C.c_double), ("max_range", C.c_double), ("min_angle", C.c_double), ("max_angle", C.c_double),
+                ("frame_rate", C.c_double), ("num_scan_lines", C.c_int32), ("frame_split_num", C.c_int32)]
+
+
+def cloud_fields(fields, point_step) -> CloudFields:
+    """fields: [(name, offset, PointField datatype, count)] -> the selection frame::Lidar::process_frame makes of them."""
+    names = b"".join(f[0].encode() + b"\0" for f in fields)
+    offs = np.array([f[1] for f in fields], np.int32)
+    dts = np.array([f[2] for f in fields], np.int32)
+    cnts = np.array([f[3] for f in fields], np.int32)
+    out = CloudFields()
+    _chk(lib().limu_cloud_fields_from_pointfields(len(fields), names, offs.ctypes.data_as(_ip), dts.ctypes.data_as(_ip), cnts.ctypes.data_as(_ip),
+                                                  int(point_step), C.byref(out)))
+    return out
+
+
+def lidar_config(**kw) -> LidarConfig:
+    cfg = LidarConfig()
+    lib().limu_lidar_default_config(C.byref(cfg))
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
 def build(force: bool = False) -> str:
     """Compile liblimu_cuda.so for sm_100a with nvcc (cross-compiles without a GPU)."""
     srcs = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + [HEADER]
@@ -114,6 +146,12 @@ def lib():
             "limu_odom_register_points": [_vp, _dp, C.c_int64, _dp, _dp, _lp, _dp, _lp, C.POINTER(FrameStats)],
             "limu_odom_num_poses": [_vp, _lp], "limu_odom_pose": [_vp, C.c_int64, _dp],
             "limu_odom_adaptive_threshold": [_vp, _dp], "limu_odom_prediction": [_vp, _dp], "limu_odom_has_moved": [_vp, C.POINTER(C.c_int)],
+            "limu_cloud_fields_from_pointfields": [C.c_int32, C.c_char_p, _ip, _ip, _ip, C.c_int32, C.POINTER(CloudFields)],
+            "limu_lidar_default_config": [C.POINTER(LidarConfig)],
+            "limu_preprocess_frame": [_vp, _vp, C.c_int64, C.POINTER(CloudFields), C.POINTER(LidarConfig), C.c_double, C.c_int32, _vp, _dp, C.c_int32, _lp, _dp,
+                                      C.POINTER(C.c_int32)],
+            "limu_odom_register_msg": [_vp, _vp, C.c_int64, C.POINTER(CloudFields), C.POINTER(LidarConfig), C.c_double, C.c_int32, C.c_int32, _dp, _lp, _dp,
+                                       C.POINTER(C.c_int32), C.POINTER(FrameStats)],
             "limu_se3_exp": [_dp, _dp], "limu_se3_log": [_dp, _dp], "limu_se3_mul": [_dp, _dp, _dp], "limu_se3_inverse": [_dp, _dp],
         }
         for name, args in sig.items():
@@ -289,6 +327,29 @@ class Context:
         re, pe, pil = (np.ascontiguousarray(v, np.float64) for v in (rot_end, pos_lidar_end, p_imu_lidar))
         _chk(lib().limu_deskew_imu(self.h, rec.ctypes.data_as(_vp), 16, 12, len(rec), _d(t), len(t), _d(re), _d(pe), _d(pil), _d(out), 1))
         return out, rec[:, :3].copy()
+
+    def process_frame(self, data, fields, cfg, message_time, scan_count, max_segments=16):
+        """frame::Lidar::process_frame (lidar/frame.cpp:101-193) on one PointCloud2 payload. data: uint8 [n, point_step];
+        fields: [(name, offset, datatype, count)] or a CloudFields; cfg: LidarConfig or dict. Returns a list of segments
+        dict(points [m,5] f32 = x,y,z,intensity,curvature; records [m,12] f32 = the 48-byte PCL rows; ts [m] f64; time)."""
+        data = np.ascontiguousarray(data, np.uint8)
+        n, step = data.shape
+        cf = fields if isinstance(fields, CloudFields) else cloud_fields(fields, step)
+        lc = cfg if isinstance(cfg, LidarConfig) else lidar_config(**cfg)
+        rec = np.zeros((max(n, 1), 12), np.float32)
+        ts = np.zeros(max(n, 1))
+        sizes = np.zeros(max(max_segments, 1), np.int64)
+        times = np.zeros(max(max_segments, 1))
+        ns = C.c_int32(0)
+        _chk(lib().limu_preprocess_frame(self.h, data.ctypes.data_as(_vp), n, C.byref(cf), C.byref(lc), float(message_time), int(scan_count),
+                                         rec.ctypes.data_as(_vp), _d(ts), int(max_segments), sizes.ctypes.data_as(_lp), _d(times), C.byref(ns)))
+        out, at = [], 0
+        for k in range(ns.value):
+            m = int(sizes[k])
+            r = rec[at:at + m]
+            out.append({"points": np.ascontiguousarray(r[:, [0, 1, 2, 8, 9]]), "records": r.copy(), "ts": ts[at:at + m].copy(), "time": float(times[k])})
+            at += m
+        return out
 
     def voxel_downsample(self, xyz, s, with_index=False):
         xyz = _pts(xyz)
@@ -526,6 +587,23 @@ class KissICP:
         nd, ns = C.c_int64(0), C.c_int64(0)
         _chk(lib().limu_odom_register_cloud(self.h, rec.ctypes.data_as(_vp), int(stride_bytes), _d(ts), n, _d(pose), _d(down), C.byref(nd), _d(src), C.byref(ns), C.byref(self.stats)))
         return down[: nd.value].copy(), src[: ns.value].copy(), pose
+
+    def register_msg(self, data, fields, cfg, message_time, scan_count, max_segments=16):
+        """lidar_callback -> estimate_lidar_odometry for one PointCloud2 payload: preprocess + register every segment on the
+        device. Returns (poses [k,7], segment sizes [k], segment times [k], [FrameStats] * k)."""
+        data = np.ascontiguousarray(data, np.uint8)
+        n, step = data.shape
+        cf = fields if isinstance(fields, CloudFields) else cloud_fields(fields, step)
+        lc = cfg if isinstance(cfg, LidarConfig) else lidar_config(**cfg)
+        poses = np.zeros((max(max_segments, 1), 7))
+        sizes = np.zeros(max(max_segments, 1), np.int64)
+        times = np.zeros(max(max_segments, 1))
+        stats = (FrameStats * max(max_segments, 1))()
+        ns = C.c_int32(0)
+        _chk(lib().limu_odom_register_msg(self.h, data.ctypes.data_as(_vp), n, C.byref(cf), C.byref(lc), float(message_time), int(scan_count),
+                                          int(max_segments), _d(poses), sizes.ctypes.data_as(_lp), _d(times), C.byref(ns), stats))
+        k = ns.value
+        return poses[:k].copy(), sizes[:k].copy(), times[:k].copy(), [stats[j] for j in range(k)]
 
     def register_frame_dev(self, xyzt_dev_ptr, n):
         pose = np.empty(7)

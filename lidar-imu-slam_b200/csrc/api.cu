@@ -18,13 +18,15 @@ void set_error(const char *fmt, ...) {
 }
 
 void release_ctx_scratch(limu_ctx *c);
+void release_pre_scratch(limu_ctx *c);
 
 int check_status(limu_ctx *c) {
     LIMU_CUDA_TRY(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, c->stream));
     LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
     const DevStatus s = *c->h_status;
-    if (s.key_range || s.table_full) {
+    if (s.key_range || s.table_full || s.pad[0]) {
         LIMU_CUDA_TRY(cudaMemsetAsync(c->d_status, 0, sizeof(DevStatus), c->stream));
+        if (s.pad[0]) { set_error("a point's ring index is >= num_scan_lines (the reference indexes its per-ring state out of bounds here)"); return LIMU_ERR_INVALID; }
         if (s.key_range) { set_error("voxel index outside the packed key range (|index| >= 2^20): point too far for this voxel size"); return LIMU_ERR_KEY_RANGE; }
         set_error("voxel hash table full");
         return LIMU_ERR_MAP_FULL;
@@ -128,6 +130,7 @@ void limu_ctx_destroy(limu_ctx *c) {
     cudaStreamSynchronize(c->stream);
     limu_comm_destroy(c);
     release_ctx_scratch(c);
+    release_pre_scratch(c);
     limu::DevBuf *bufs[] = {&c->in0, &c->in1, &c->out0, &c->out1, &c->out2, &c->tmp0, &c->tmp1, &c->tmp2, &c->tmp3, &c->tmp4, &c->tmp5, &c->d_small};
     for (auto *b : bufs) b->release();
     for (int s = 0; s < LIMU_NUM_STAGES; ++s) for (int k = 0; k < 2; ++k) if (c->ev[s][k]) cudaEventDestroy(c->ev[s][k]);

@@ -66,7 +66,7 @@ struct DevBuf {
 struct DevStatus {
     int key_range;    // some voxel index fell outside the packed key range
     int table_full;   // an insert probe ran through the whole table
-    int pad[2];
+    int pad[2];       // pad[0]: a ring index exceeded num_scan_lines in the constant-rotation preprocessing path
 };
 
 }  // namespace limu

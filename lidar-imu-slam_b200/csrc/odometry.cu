@@ -59,6 +59,7 @@ struct limu_odom {
     // device buffers
     limu::DevBuf raw, ts, frame, down, src0, src, work, world, partials, d2;
     limu::VoxelizeScratch vx;
+    limu::PreScratch pre;                   // limu_odom_register_msg: frame::Lidar::process_frame on the device
     int64_t nk_hint = 4096, nd_hint = 16384;
     // limu_odom_prefetch: the next scan is uploaded on its own stream while the current one is being registered
     limu::DevBuf pf_buf[2];                 // two slots: the scan about to be registered and the one after it
@@ -217,6 +218,7 @@ void limu_odom_destroy(limu_odom *o) {
     DevBuf *bufs[] = {&o->pf_buf[0], &o->pf_buf[1], &o->d2, &o->raw, &o->ts, &o->frame, &o->down, &o->src0, &o->src, &o->work, &o->world, &o->partials};
     for (auto *b : bufs) b->release();
     o->vx.release();
+    o->pre.release();
     delete o;
 }
 
@@ -278,6 +280,36 @@ int limu_odom_register_points(limu_odom *o, const double *xyz, int64_t n, double
     LIMU_TRY(bind(o->ctx));
     LIMU_TRY(stage_in(o->ctx, o->raw, xyz, (size_t)n * 24));
     return odom_register_device(o, o->raw.p, 2, 0, nullptr, n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+}
+
+int limu_odom_register_msg(limu_odom *o, const void *data, int64_t n, const limu_cloud_fields *fields, const limu_lidar_config *cfg, double message_time,
+                           int32_t scan_count, int32_t max_segments, double *poses_out, int64_t *seg_sizes, double *seg_time, int32_t *n_segments,
+                           limu_frame_stats *stats) {
+    LIMU_REQUIRE(o && n >= 0 && (n == 0 || data) && n_segments && max_segments >= 0 && (max_segments == 0 || (poses_out && seg_sizes && seg_time)) &&
+                     n < (int64_t(1) << 31), "limu_odom_register_msg: bad arguments");
+    LIMU_TRY(bind(o->ctx));
+    LIMU_TRY(preprocess_validate(fields, cfg, max_segments));
+    *n_segments = 0;
+    if (n == 0) return LIMU_OK;
+    limu_ctx *c = o->ctx;
+    LIMU_TRY(stage_in(c, o->pre.raw, data, (size_t)n * fields->point_step));
+    LIMU_TRY(preprocess_device(c, o->pre, o->pre.raw.as<unsigned char>(), n, *fields, *cfg, message_time, scan_count));   // lidar_callback, odom_run.cpp:51-67
+    const SegTable &T = *o->pre.h_seg;
+    const int ns = std::min<int>(T.nseg, max_segments);
+    for (int k = 0; k < ns; ++k) {
+        const int64_t off = T.begin[k], nk = T.end[k] - T.begin[k];
+        seg_sizes[k] = nk; seg_time[k] = T.time[k];
+        if (stats) memset(&stats[k], 0, sizeof(limu_frame_stats));
+        if (nk <= 1) {   // "Too few input point cloud!" (odom_run.cpp:78-83): the segment is popped without being registered
+            pose_store(o->poses.empty() ? pose_identity() : o->poses.back(), poses_out + 7 * k);
+            continue;
+        }
+        // estimate_lidar_odometry -> register_frame(*processed_frame, time_buffer) (odom_run.cpp:103-106) on the device-resident segment
+        LIMU_TRY(odom_register_device(o, o->pre.rec.as<unsigned char>() + (size_t)off * 48, 1, 48, o->pre.ts.as<double>() + off, nk, poses_out + 7 * k, nullptr,
+                                      nullptr, nullptr, nullptr, stats ? &stats[k] : nullptr));
+    }
+    *n_segments = ns;
+    return LIMU_OK;
 }
 
 int limu_odom_num_poses(limu_odom *o, int64_t *n) {

@@ -41,4 +41,30 @@ int downsample_device(limu_ctx *c, StageScratch &sc, const double *xyz_dev, int6
 int iqr_device(limu_ctx *c, StageScratch &sc, const double *xyz_dev, int64_t n_max, const int *n_dev, double *out_xyz_dev,
                int *out_count_dev, double *bounds_dev);
 
+
+// ---- frame::Lidar::process_frame on the device (preprocess.cu) ----
+constexpr int PRE_MAX_SEG = 64;
+struct SegTable {                      // device + pinned host mirror
+    int nseg, m, pad0, pad1;
+    int begin[PRE_MAX_SEG], end[PRE_MAX_SEG];   // sorted positions (begin, end] -> output rows begin .. end-1
+    double adj[PRE_MAX_SEG];           // message_time_ms - last_frame_end_time of the segment (frame.cpp:74)
+    double time[PRE_MAX_SEG];          // accumulated_segment_time (:89)
+    double tmax[PRE_MAX_SEG];          // maximum of the segment's timestamps (normalize_timestamps :87)
+};
+struct PreScratch {
+    DevBuf raw, curv, ext, flags, blockcnt, sidx, keys[2], vals[2], hist, small, rec, ts;
+    SegTable *h_seg = nullptr;   // pinned
+    void release() {
+        DevBuf *b[] = {&raw, &curv, &ext, &flags, &blockcnt, &sidx, &keys[0], &keys[1], &vals[0], &vals[1], &hist, &small, &rec, &ts};
+        for (auto *x : b) x->release();
+        if (h_seg) { cudaFreeHost(h_seg); h_seg = nullptr; }
+    }
+};
+// Everything up to the processed records in device memory. data_dev: the message payload on the device. On return
+// sc.rec / sc.ts hold the concatenated segments (48-byte pcl::PointXYZINormal records + FP64 timestamps) and *sc.h_seg the
+// segment table (host; the call synchronises once to read it).
+int preprocess_device(limu_ctx *c, PreScratch &sc, const unsigned char *data_dev, int64_t n, const limu_cloud_fields &f, const limu_lidar_config &cfg,
+                      double message_time, int scan_count);
+int preprocess_validate(const limu_cloud_fields *f, const limu_lidar_config *cfg, int max_segments);
+
 }  // namespace limu

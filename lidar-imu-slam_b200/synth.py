@@ -117,3 +117,31 @@ def pad_scan(scan, n, seed=0):
     extra[:, :3] += rng.normal(size=(len(extra), 3)).astype(np.float32) * 0.005
     out = np.concatenate([scan, extra])
     return np.ascontiguousarray(out[np.argsort(out[:, 3], kind="stable")])
+
+
+# sensor_msgs::PointField datatype codes
+PF_INT8, PF_UINT8, PF_INT16, PF_UINT16, PF_INT32, PF_UINT32, PF_FLOAT32, PF_FLOAT64 = range(1, 9)
+# The message layout the reference registers for its LidarPoint (lidar/frame.hpp:12-23): x y z intensity(u8) ring(u16) timestamp(f64)
+LIDAR_POINT_FIELDS = [("x", 0, PF_FLOAT32, 1), ("y", 4, PF_FLOAT32, 1), ("z", 8, PF_FLOAT32, 1), ("intensity", 12, PF_UINT8, 1),
+                      ("ring", 14, PF_UINT16, 1), ("timestamp", 16, PF_FLOAT64, 1)]
+LIDAR_POINT_STEP = 24
+
+
+def make_pointcloud2(xyz, ring, stamp_s, intensity=None, point_step=LIDAR_POINT_STEP, fields=None):
+    """Pack one scan as a sensor_msgs::PointCloud2 payload: uint8 [n, point_step] + the field list.
+    stamp_s: absolute per-point firing time in seconds (float64), the `timestamp` field of the reference's LidarPoint."""
+    fields = fields or LIDAR_POINT_FIELDS
+    n = len(xyz)
+    buf = np.zeros((n, point_step), np.uint8)
+    off = {f[0]: f[1] for f in fields}
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    for k, name in enumerate("xyz"):
+        buf[:, off[name]:off[name] + 4] = xyz[:, k:k + 1].copy().view(np.uint8)
+    if "intensity" in off:
+        inten = np.zeros(n, np.uint8) if intensity is None else np.asarray(intensity, np.uint8)
+        buf[:, off["intensity"]] = inten
+    if "ring" in off:
+        buf[:, off["ring"]:off["ring"] + 2] = np.asarray(ring, np.uint16).reshape(-1, 1).copy().view(np.uint8)
+    if "timestamp" in off:
+        buf[:, off["timestamp"]:off["timestamp"] + 8] = np.asarray(stamp_s, np.float64).reshape(-1, 1).copy().view(np.uint8)
+    return buf, list(fields)

@@ -55,7 +55,8 @@ def _pts(x):
 
 def build_port(force: bool = False) -> str:
     """Compile the C restatement (gcc only)."""
-    if force or not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < os.path.getmtime(os.path.join(HERE, "limu_oracle.c")):
+    srcs = [os.path.join(HERE, f) for f in ("limu_oracle.c", "limu_oracle_frame.c", "limu_oracle.h")]
+    if force or not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-s", "-C", HERE, "port"])
     return PORT_SO
 
@@ -125,6 +126,8 @@ class _Api:
             f("kiss_last_iterations", C.c_int, [C.c_void_p])
             f("kiss_last_sigma", C.c_double, [C.c_void_p])
             f("kiss_map", C.c_void_p, [C.c_void_p])
+        if hasattr(lib, p + "process_frame"):
+            f("process_frame", C.c_long, [C.c_char_p, C.c_long, C.c_int, C.c_int, C.c_char_p, _ip, _ip, _ip, _dp, C.c_double, C.c_int, C.c_long, _lp, _dp, _fp, _dp])
         f("kiss_create", C.c_void_p, [C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double])
         f("kiss_destroy", None, [C.c_void_p])
         f("kiss_register_points", None, [C.c_void_p, _dp, C.c_long, _dp, _lp, _dp, _lp, _dp])
@@ -223,6 +226,34 @@ class _Api:
         re, pe, pil = (np.ascontiguousarray(v, np.float64) for v in (rot_end, pos_lidar_end, p_imu_lidar))
         self._deskew_imu(_f(x), _f(c), len(x), _d(t), len(t), _d(re), _d(pe), _d(pil), _d(out))
         return out, x
+
+    def process_frame(self, data, fields, cfg, message_time, scan_count, max_segments=16):
+        """frame::Lidar::process_frame (lidar/frame.cpp:101-193) on one PointCloud2 payload.
+        data: uint8 [n, point_step]; fields: [(name, offset, PointField datatype, count)];
+        cfg: dict(min_range, max_range, min_angle, max_angle, frame_rate, num_scan_lines, frame_split_num).
+        Returns a list of segments dict(points [m,5] f32 = x,y,z,intensity,curvature; ts [m] f64; time) or a negative status."""
+        data = np.ascontiguousarray(data, np.uint8)
+        n, step = data.shape
+        names = b"".join(f[0].encode() + b"\0" for f in fields)
+        offs = np.array([f[1] for f in fields], np.int32)
+        dts = np.array([f[2] for f in fields], np.int32)
+        cnts = np.array([f[3] for f in fields], np.int32)
+        c = np.array([cfg["min_range"], cfg["max_range"], cfg["min_angle"], cfg["max_angle"], cfg["frame_rate"], cfg["num_scan_lines"],
+                      cfg["frame_split_num"]], np.float64)
+        seg_sizes = np.zeros(max_segments, np.int64)
+        seg_time = np.zeros(max_segments)
+        rec5 = np.zeros((max(n, 1), 5), np.float32)
+        ts = np.zeros(max(n, 1))
+        k = self._process_frame(data.ctypes.data_as(C.c_char_p), n, step, len(fields), names, _i(offs), _i(dts), _i(cnts), _d(c), float(message_time),
+                                int(scan_count), max_segments, _l(seg_sizes), _d(seg_time), _f(rec5), _d(ts))
+        if k < 0:
+            return int(k)
+        out, at = [], 0
+        for j in range(k):
+            m = int(seg_sizes[j])
+            out.append({"points": rec5[at:at + m].copy(), "ts": ts[at:at + m].copy(), "time": float(seg_time[j])})
+            at += m
+        return out
 
     def align(self, src, tgt, th):
         """Returns dict(pose=7) for the reference; the port adds H (6x6), g (6), x (6)."""

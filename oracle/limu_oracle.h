@@ -68,6 +68,16 @@ void lo_deskew(const float *xyz, const double *ts, long n, const double *T0, con
 void lo_deskew_imu(float *xyz_f32, const float *curv_ms, long n, const double *table, long M, const double *rot_end9,
                    const double *pos_lidar_end3, const double *p_il3, double *out);
 
+/* ---- frame::Lidar::process_frame, L/src/sensors/lidar/frame.cpp:101-193 (+ sort_clouds :28-51, split_clouds :53-99, utils::get_time_stamps
+ * calculation_helpers.cpp:3-81): SURVEY section 8f N3, the host preprocessing in front of register_frame. limu_oracle_frame.c.
+ * data: n point records `point_step` bytes apart; fields: nf PointField entries (names = NUL-terminated strings back to back).
+ * cfg = {min_range, max_range, min_angle, max_angle, frame_rate, num_scan_lines, frame_split_num}; scan_count = the counter's value during
+ * process_frame. Outputs for the concatenated segments: rec5[5*j] = {x, y, z, intensity, curvature}, ts[j]; per segment seg_sizes / seg_time.
+ * Returns the number of segments, -1 when no timestamp field exists, -2 when a ring index exceeds num_scan_lines (constant-rotation path). */
+long lo_process_frame(const unsigned char *data, long n, int point_step, int nf, const char *names, const int *offsets, const int *datatypes,
+                      const int *counts, const double *cfg, double message_time, int scan_count, long max_segments, long *seg_sizes, double *seg_time,
+                      float *rec5, double *ts);
+
 /* ---- icp.cpp ---------------------------------------------------------------------------------------- */
 long lo_voxel_downsample(const double *xyz, long n, double s, double *out, long *out_idx);   /* :9-30 */
 long lo_iqr(const double *xyz, long n, double *out, double *bounds2);                         /* :88-124, common.hpp:22-63 */

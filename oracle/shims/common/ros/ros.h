@@ -4,6 +4,10 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+// roscpp's own headers (ros/time.h, ros/duration.h -> <math.h>) put the C math names into the global namespace; the reference's
+// lidar/frame.cpp:144,161 relies on that for its unqualified isnan() / atan2() (libstdc++'s <math.h>: `using std::isnan;` etc.,
+// so atan2(float, float) is the FLOAT overload).
+#include <math.h>
 namespace ros {
 struct Time {
     double t = 0;

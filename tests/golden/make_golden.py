@@ -9,7 +9,9 @@ Two families:
   fixtures_hash_map_test.npz  the six known-answer inputs of L/src/tests/hash_map_test.hpp (the reference's
                               only tests, SURVEY section 4) with the reference's outputs on them;
   fixtures_path.npz           seeded synthetic inputs through every function of the hot path
-                               with the reference's outputs.
+                              (SURVEY section 8a rows a1-a19) with the reference's outputs;
+  fixtures_frame.npz          seeded PointCloud2 payloads through frame::Lidar::process_frame (SURVEY section 8f N3).
+Regenerate a subset with:  python tests/golden/make_golden.py frame
 """
 import ctypes
 import os
@@ -188,12 +190,38 @@ def path_fixtures(ref):
     return out
 
 
+def frame_fixtures(ref):
+    """frame::Lidar::process_frame (lidar/frame.cpp:101-193; SURVEY section 8f N3) on seeded PointCloud2 payloads in the layout the
+    reference registers for its LidarPoint (lidar/frame.hpp:12-23). Offset times are distinct, so std::sort's tie order plays no role."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_preprocess import CFG, make_msg
+    out = {}
+    cases = [(101, 3000, "distinct", 1, 1), (102, 3001, "distinct", 3, 25), (103, 2500, "distinct", 4, 60), (104, 2000, "nooffset", 1, 5)]
+    for k, (seed, n, kind, split, sc) in enumerate(cases):
+        data, fields, mt = make_msg(seed, n, kind=kind)
+        seg = ref.process_frame(data, fields, dict(CFG, frame_split_num=split), mt, sc)
+        out[f"c{k}_data"], out[f"c{k}_mt"], out[f"c{k}_sc"], out[f"c{k}_split"], out[f"c{k}_nooffset"] = data, mt, sc, split, kind == "nooffset"
+        out[f"c{k}_sizes"] = np.array([len(s["points"]) for s in seg], np.int64)
+        out[f"c{k}_points"] = np.concatenate([s["points"] for s in seg])
+        out[f"c{k}_ts"] = np.concatenate([s["ts"] for s in seg])
+        out[f"c{k}_times"] = np.array([s["time"] for s in seg])
+    out["n_cases"] = len(cases)
+    return out
+
+
 if __name__ == "__main__":
     oracle.build_ref()
     ref = oracle.load_ref()
-    a = hash_map_test_fixtures(ref)
-    np.savez_compressed(os.path.join(HERE, "fixtures_hash_map_test.npz"), **a)
-    b = path_fixtures(ref)
-    np.savez_compressed(os.path.join(HERE, "fixtures_path.npz"), **b)
-    for f in ("fixtures_hash_map_test.npz", "fixtures_path.npz"):
+    which = sys.argv[1:] or ["hash_map", "path", "frame"]
+    made = []
+    if "hash_map" in which:
+        np.savez_compressed(os.path.join(HERE, "fixtures_hash_map_test.npz"), **hash_map_test_fixtures(ref))
+        made.append("fixtures_hash_map_test.npz")
+    if "path" in which:
+        np.savez_compressed(os.path.join(HERE, "fixtures_path.npz"), **path_fixtures(ref))
+        made.append("fixtures_path.npz")
+    if "frame" in which:
+        np.savez_compressed(os.path.join(HERE, "fixtures_frame.npz"), **frame_fixtures(ref))
+        made.append("fixtures_frame.npz")
+    for f in made:
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
