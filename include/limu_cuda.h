@@ -140,6 +140,21 @@ int limu_icp(limu_map *m, const double *xyz, int64_t n, const double init_guess[
 int limu_icp_dev(limu_map *m, const double *xyz_dev, int64_t n, const double init_guess[7], double max_corresp_dist, double kernel,
                  int icp_max_iteration, double est_threshold, double pose_out[7], limu_icp_stats *stats);
 
+/* Opt-in variants of the registration loop. They have NO counterpart in the reference (whose neighbour rule
+ * is own-voxel-only and whose residual is point-to-point); the C oracle's restatement of the same definition is
+ * their parity oracle.
+ *   LIMU_ICP_NN27: correspondence = the NEAREST stored point over all 27 cells of the query's neighbourhood (what the north star and
+ *   upstream KISS-ICP describe), cells visited x-outermost, points in storage order, first minimum wins.
+ *   LIMU_ICP_PLANE: point-to-plane residual e = n.(s - t) with n = normal of the matched point's voxel (smallest-eigenvalue
+ *   direction of the scatter of its >= 5 stored points, planar when l_min <= 0.04 l_mid; other correspondences are dropped),
+ *   weight th^2/(th + e^2)^2, Jacobian row [n ; s x n]. Not available in the point-sharded loop. */
+enum { LIMU_ICP_REFERENCE = 0, LIMU_ICP_NN27 = 1, LIMU_ICP_PLANE = 2 };
+int limu_icp_ex(limu_map *m, const double *xyz, int64_t n, const double init_guess[7], double max_corresp_dist, double kernel,
+                int icp_max_iteration, double est_threshold, int32_t icp_mode, double pose_out[7], limu_icp_stats *stats,
+                double *est_trace, int64_t *ncorr_trace, double *hg_trace);
+/* get_closest_neighbour under a neighbour rule (icp_mode as above); outputs as limu_map_closest. */
+int limu_map_closest_ex(limu_map *m, const double *xyz, int64_t n, int32_t icp_mode, double *out_xyz, int32_t *out_key, int32_t *out_rank);
+
 /* ---- point-sharded ICP over several GPUs (BASELINE configs[4]; no counterpart in the single-process reference) ----
  * One process per GPU. Every rank holds a full replica of the map and a contiguous shard of the query points; per
  * Gauss-Newton iteration the ranks exchange ONE row of 20 doubles (the normal-equation sums). LIMU_SHARD_FUSED does
@@ -164,7 +179,7 @@ typedef struct limu_odom_config {   /* frame::Lidar::ProcessingInfo fields the p
     int32_t deskew;               /* 0 */
     double min_motion_th;         /* 0.1 */
     int32_t icp_max_iteration;    /* 500 */
-    int32_t reserved0;
+    int32_t icp_mode;             /* 0 = the reference's rules (default); LIMU_ICP_* bits opt into the north star's variants */
     double initial_threshold;     /* 2.0 */
     double estimation_threshold;  /* 1e-4 */
     int64_t map_capacity_voxels;  /* 0 = derive from max_range / voxel_size */

@@ -27,6 +27,9 @@ _lp = C.POINTER(C.c_int64)
 _vp = C.c_void_p
 
 
+ICP_REFERENCE, ICP_NN27, ICP_PLANE = 0, 1, 2   # limu_cuda.h LIMU_ICP_*: opt-in registration variants
+
+
 class LimuError(RuntimeError):
     def __init__(self, status, msg):
         super().__init__(f"limu status {status}: {msg}")
@@ -41,7 +44,7 @@ class IcpStats(C.Structure):
 class OdomConfig(C.Structure):
     _fields_ = [("voxel_size", C.c_double), ("max_range", C.c_double), ("max_points_per_voxel", C.c_int32),
                 ("deskew", C.c_int32), ("min_motion_th", C.c_double), ("icp_max_iteration", C.c_int32),
-                ("reserved0", C.c_int32), ("initial_threshold", C.c_double), ("estimation_threshold", C.c_double),
+                ("icp_mode", C.c_int32), ("initial_threshold", C.c_double), ("estimation_threshold", C.c_double),
                 ("map_capacity_voxels", C.c_int64), ("max_points_per_scan", C.c_int64)]
 
 
@@ -134,6 +137,8 @@ def lib():
             "limu_map_pointcloud": [_vp, _dp, C.c_int64, _lp],
             "limu_map_dump": [_vp, _ip, _ip, _dp, C.c_int64, C.c_int64, _lp, _lp],
             "limu_icp": [_vp, _dp, C.c_int64, _dp, C.c_double, C.c_double, C.c_int, C.c_double, _dp, C.POINTER(IcpStats), _dp, _lp, _dp],
+            "limu_icp_ex": [_vp, _dp, C.c_int64, _dp, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int32, _dp, C.POINTER(IcpStats), _dp, _lp, _dp],
+            "limu_map_closest_ex": [_vp, _dp, C.c_int64, C.c_int32, _dp, _ip, _ip],
             "limu_icp_dev": [_vp, _vp, C.c_int64, _dp, C.c_double, C.c_double, C.c_int, C.c_double, _dp, C.POINTER(IcpStats)],
             "limu_comm_create": [_vp, C.c_int, C.c_int, C.c_char_p], "limu_comm_connect": [_vp, C.c_char_p], "limu_comm_destroy": [_vp],
             "limu_comm_nccl_unique_id": [C.c_char_p], "limu_comm_nccl_init": [_vp, C.c_char_p],
@@ -442,12 +447,13 @@ class VoxelHashMap:
         _chk(lib().limu_map_size(self.h, C.byref(nv), C.byref(npt)))
         return nv.value, npt.value
 
-    def get_closest_neighbour(self, xyz, with_index=False):
+    def get_closest_neighbour(self, xyz, with_index=False, icp_mode=0):
+        """icp_mode: 0 = the reference's rule; ICP_NN27 = nearest point of the 27-cell neighbourhood (opt-in)."""
         xyz = _pts(xyz)
         out = np.empty((len(xyz), 3))
         key = np.empty((len(xyz), 3), np.int32)
         rank = np.empty(len(xyz), np.int32)
-        _chk(lib().limu_map_closest(self.h, _d(xyz), len(xyz), _d(out), key.ctypes.data_as(_ip), rank.ctypes.data_as(_ip)))
+        _chk(lib().limu_map_closest_ex(self.h, _d(xyz), len(xyz), int(icp_mode), _d(out), key.ctypes.data_as(_ip), rank.ctypes.data_as(_ip)))
         return (out, key, rank) if with_index else out
 
     def get_correspondences(self, xyz, max_correspondance, with_index=False):
@@ -477,7 +483,7 @@ class VoxelHashMap:
         return keys[: nv.value], counts[: nv.value], pts[: npt.value]
 
     # lidar::ICP(local_map, points, init_guess, max_corresp_dist, kernel, icp_max_iteration, est_threshold)
-    def icp(self, xyz, init_guess, max_corresp_dist, kernel, icp_max_iteration, est_threshold, trace=False):
+    def icp(self, xyz, init_guess, max_corresp_dist, kernel, icp_max_iteration, est_threshold, trace=False, icp_mode=0):
         xyz = _pts(xyz)
         pose = np.empty(7)
         st = IcpStats()
@@ -485,8 +491,8 @@ class VoxelHashMap:
         est = np.zeros((it, 7)) if trace else None
         nc = np.zeros(it, np.int64) if trace else None
         hg = np.zeros((it, 42)) if trace else None
-        _chk(lib().limu_icp(self.h, _d(xyz), len(xyz), _d(_pose(init_guess)), float(max_corresp_dist), float(kernel), int(icp_max_iteration),
-                            float(est_threshold), _d(pose), C.byref(st), _d(est), nc.ctypes.data_as(_lp) if trace else None, _d(hg)))
+        _chk(lib().limu_icp_ex(self.h, _d(xyz), len(xyz), _d(_pose(init_guess)), float(max_corresp_dist), float(kernel), int(icp_max_iteration),
+                               float(est_threshold), int(icp_mode), _d(pose), C.byref(st), _d(est), nc.ctypes.data_as(_lp) if trace else None, _d(hg)))
         r = {"pose": pose, "iters": st.iterations, "converged": bool(st.converged), "last_ncorr": st.last_ncorr,
              "mean_candidates": st.mean_candidates, "miss_fraction": st.miss_fraction}
         if trace:
@@ -518,7 +524,7 @@ class KissICP:
     """lidar::KissICP (sensors/lidar/icp.hpp:31-68); config = frame::Lidar::ProcessingInfo fields."""
 
     def __init__(self, ctx, voxel_size=1.0, max_range=100.0, cap=10, deskew=False, min_motion_th=0.1, icp_max_iteration=500,
-                 initial_threshold=2.0, estimation_threshold=1e-4, map_capacity_voxels=0):
+                 initial_threshold=2.0, estimation_threshold=1e-4, map_capacity_voxels=0, icp_mode=0):
         self.ctx = ctx
         cfg = OdomConfig()
         lib().limu_odom_default_config(C.byref(cfg))
@@ -526,6 +532,7 @@ class KissICP:
         cfg.min_motion_th, cfg.icp_max_iteration = min_motion_th, icp_max_iteration
         cfg.initial_threshold, cfg.estimation_threshold = initial_threshold, estimation_threshold
         cfg.map_capacity_voxels = map_capacity_voxels
+        cfg.icp_mode = icp_mode
         self.cfg = cfg
         self.h = _vp()
         _chk(lib().limu_odom_create(ctx.h, C.byref(cfg), C.byref(self.h)))

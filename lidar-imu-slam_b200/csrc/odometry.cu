@@ -14,7 +14,7 @@
 namespace limu {
 int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t n_max, const int *n_dev, const double *init_pose_host,
                double tau, double th, int max_iter, double eps, double *partials_dev, size_t partial_rows, double *out13_dev, int64_t n_hint,
-               double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev, int max_iter_all_ranks, const FrameFusion *fuse);
+               double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev, int max_iter_all_ranks, const FrameFusion *fuse, int icp_mode);
 int icp_partial_rows(limu_ctx *c);
 
 // theta = Eigen::AngleAxisd(model_dev.rotationMatrix()).angle() (threshold.cpp:7): quaternion -> matrix
@@ -114,7 +114,7 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     LIMU_TRY(o->work.reserve(nb, c->stream));
     LIMU_TRY(o->world.reserve(nb, c->stream));
     const int rows = icp_partial_rows(c);
-    LIMU_TRY(o->partials.reserve((size_t)2 * rows * 20 * 8 + 256, c->stream));
+    LIMU_TRY(o->partials.reserve((size_t)2 * rows * 32 * 8 + 256, c->stream));   // 32 doubles per row covers both residual variants
     int *cnt = reinterpret_cast<int *>(c->d_small.as<double>() + 32);   // [0]=n_down [1]=n_src0 [2]=n_keypoints
     double *out13 = c->d_small.as<double>() + 40;
     const double v = o->cfg.voxel_size;
@@ -142,7 +142,7 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     fuse.upd_birth_base = o->map->birth_base;
     const int64_t upper_before = o->map->used_upper;
     LIMU_TRY(icp_device(o->map, o->src.as<double>(), o->work.as<double>(), n, cnt + 2, init7, 3.0 * sigma, sigma / 3.0, o->cfg.icp_max_iteration,
-                        o->cfg.estimation_threshold, o->partials.as<double>(), (size_t)rows, out13, o->nk_hint, nullptr, nullptr, nullptr, -1, &fuse));
+                        o->cfg.estimation_threshold, o->partials.as<double>(), (size_t)rows, out13, o->nk_hint, nullptr, nullptr, nullptr, -1, &fuse, o->cfg.icp_mode));
     o->map->birth_base += (uint64_t)n;
 
     // the one synchronisation of the scan
@@ -195,6 +195,7 @@ int limu_odom_create(limu_ctx *c, const limu_odom_config *cfg, limu_odom **out) 
     LIMU_TRY(bind(c));
     LIMU_REQUIRE(cfg && out, "limu_odom_create: null argument");
     LIMU_REQUIRE(cfg->voxel_size > 0 && cfg->max_points_per_voxel >= 1, "limu_odom_create: voxel_size must be > 0 and max_points_per_voxel >= 1");
+    LIMU_REQUIRE((cfg->icp_mode & ~(LIMU_ICP_NN27 | LIMU_ICP_PLANE)) == 0, "limu_odom_create: unknown icp_mode bits");
     limu_odom *o = new limu_odom;
     o->ctx = c;
     o->cfg = *cfg;

@@ -23,6 +23,8 @@ namespace limu {
 
 constexpr int ICP_BLOCK = 256;
 constexpr int NS = 20;   // 16 sums + ncorr + ncand + nmiss + pad
+constexpr int NSP = 32;  // opt-in point-to-plane variant: 21 (upper triangle of H) + 6 (g) + ncorr + ncand + nmiss + 2 pad
+constexpr int NS_MAX = 32;
 constexpr int MBOX_MAX_RANKS = 8, MBOX_ROW = 24;   // mailbox row: NS doubles + stamp + pad
 
 }  // namespace limu
@@ -116,6 +118,55 @@ __device__ __forceinline__ double warp_reduce_scatter16(const double *c) {
     return g + __shfl_xor_sync(0xFFFFFFFFu, g, 1);
 }
 
+// ---- opt-in point-to-plane variant LIMU_ICP_PLANE (defined by the C oracle's plane_step) ------------
+// One correspondence with plane normal n: e = n.(s - t), w = th^2/(th + e^2)^2, a = [n ; s x n] (the reference's perturbation
+// model: J_point = [I | -hat(s)], registration.cpp:46-54), H += w a a^T (21 upper-triangle sums, row-major), g += w a e (6),
+// plus the three counters as doubles: 32 values, one per lane after the reduce-scatter.
+__device__ __forceinline__ void contribution_plane(double *c, const V3 &s, const V3 &t, const double *n, double th, bool on, int ncand, bool miss, bool lead) {
+    const double e = (n[0] * (s.x - t.x) + n[1] * (s.y - t.y)) + n[2] * (s.z - t.z);
+    const double den = th + e * e;
+    const double w = on ? (th * th) / (den * den) : 0.0;
+    const double a[6] = {n[0], n[1], n[2], s.y * n[2] - s.z * n[1], s.z * n[0] - s.x * n[2], s.x * n[1] - s.y * n[0]};
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const double wa = w * a[r];
+#pragma unroll
+        for (int q = r; q < 6; ++q) c[k++] = wa * a[q];
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) c[21 + r] = (w * a[r]) * e;
+    c[27] = on ? 1.0 : 0.0;
+    c[28] = lead ? (double)ncand : 0.0;
+    c[29] = miss ? 1.0 : 0.0;
+    c[30] = c[31] = 0.0;
+}
+// Warp reduce-scatter of 32 values per lane: lane L ends up with the warp total of value L (fixed exchange pattern).
+__device__ __forceinline__ double warp_reduce_scatter32(const double *c) {
+    const int lane = threadIdx.x & 31;
+    double d[16], e[8], f[4], g[2];
+    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2, u1 = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d[i] = (u16 ? c[i + 16] : c[i]) + __shfl_xor_sync(0xFFFFFFFFu, u16 ? c[i] : c[i + 16], 16);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = (u8 ? d[i + 8] : d[i]) + __shfl_xor_sync(0xFFFFFFFFu, u8 ? d[i] : d[i + 8], 8);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = (u4 ? e[i + 4] : e[i]) + __shfl_xor_sync(0xFFFFFFFFu, u4 ? e[i] : e[i + 4], 4);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) g[i] = (u2 ? f[i + 2] : f[i]) + __shfl_xor_sync(0xFFFFFFFFu, u2 ? f[i] : f[i + 2], 2);
+    return (u1 ? g[1] : g[0]) + __shfl_xor_sync(0xFFFFFFFFu, u1 ? g[0] : g[1], 1);
+}
+// S[0..20] = upper triangle of H row-major, S[21..26] = g.
+__device__ __forceinline__ void expand_plane_equations(const double *S, double *H, double *g) {
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int q = r; q < 6; ++q) { H[6 * r + q] = S[k]; H[6 * q + r] = S[k]; ++k; }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) g[r] = S[21 + r];
+}
+
 // Legacy-style accumulation used by the stand-alone align kernel (16 accumulators per thread).
 __device__ __forceinline__ void accumulate(double *a, const V3 &s, const V3 &t, double d2, double th) {
     double c[16];
@@ -188,6 +239,8 @@ __device__ __forceinline__ void coop_scan(const MapView &m, const V3 &s, int slo
 }
 
 // One pass over this warp's share of the queries: transform, locate, scan, gate, weight, accumulate.
+// NN27: the opt-in neighbour rule LIMU_NN_27 (nearest point of the 27-cell neighbourhood, voxel_map.cuh) instead of the reference's.
+template <bool NN27, bool PLANE>
 __device__ __forceinline__ void icp_query_pass(const IcpArgs &A, const volatile double *Pv, const double *in, int64_t n, int64_t wbase, int64_t wstride,
                                                int lane, double &acc, int &ncorr, int &ncand, int &nmiss) {
     for (int64_t base = wbase; base < n; base += wstride) {
@@ -201,11 +254,17 @@ __device__ __forceinline__ void icp_query_pass(const IcpArgs &A, const volatile 
             const Pose P{Pv[0], Pv[1], Pv[2], Pv[3], Pv[4], Pv[5], Pv[6]};
             s = apply(P, V3{in[3 * q], in[3 * q + 1], in[3 * q + 2]});
             A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z;
-            slot = map_locate(A.map, s, &count, &own);   // which voxel answers (own, else farthest/latest of the 27)
+            if (!NN27) slot = map_locate(A.map, s, &count, &own);   // which voxel answers (own, else farthest/latest of the 27)
         }
         double my_d2 = 0.0;
         int my_rank = -1;
-        if (A.coop_scan) {
+        if (NN27) {
+            if (on) {
+                const Nearest nn = map_closest27(A.map, s);
+                slot = nn.slot; my_rank = nn.rank; count = nn.ncand; own = nn.own;
+                my_d2 = sqnorm3(nn.x - s.x, nn.y - s.y, nn.z - s.z);
+            }
+        } else if (A.coop_scan) {
             if (A.map.cap <= 8) coop_scan<1>(A.map, s, slot, count, lane, my_d2, my_rank);
             else if (A.map.cap <= 16) coop_scan<2>(A.map, s, slot, count, lane, my_d2, my_rank);
             else if (A.map.cap <= 24) coop_scan<3>(A.map, s, slot, count, lane, my_d2, my_rank);
@@ -225,16 +284,26 @@ __device__ __forceinline__ void icp_query_pass(const IcpArgs &A, const volatile 
         }
         const double d2 = my_rank >= 0 ? my_d2 : sqnorm3(tg.x - s.x, tg.y - s.y, tg.z - s.z);   // (found - point).squaredNorm() :120
         const bool gate = on && d2 < A.tau_sq;
-        double c[16];
-        contribution(c, s, tg, d2, A.th, gate);
-        acc += warp_reduce_scatter16(c);
-        ncorr += gate ? 1 : 0;
-        ncand += count;
-        nmiss += (on && !own) ? 1 : 0;
+        if (PLANE) {
+            double nrm[3] = {0.0, 0.0, 0.0};
+            bool planar = false;
+            if (gate && my_rank >= 0) planar = voxel_normal(A.map, slot, meta_count(load_slot(A.map.slots + slot).y), nrm) != 0;
+            double c[32];
+            contribution_plane(c, s, tg, nrm, A.th, planar, count, on && !own, on);
+            acc += warp_reduce_scatter32(c);
+        } else {
+            double c[16];
+            contribution(c, s, tg, d2, A.th, gate);
+            acc += warp_reduce_scatter16(c);
+            ncorr += gate ? 1 : 0;
+            ncand += count;
+            nmiss += (on && !own) ? 1 : 0;
+        }
     }
 }
 
 // The same pass in the latency shape: eight lanes per query (four queries per warp), see group8_closest.
+template <bool NN27, bool PLANE>
 __device__ __forceinline__ void icp_query_pass_grouped(const IcpArgs &A, const volatile double *Pv, const double *in, int64_t n, int64_t gbase, int64_t gstride,
                                                        int lane, double &acc, int &ncorr, int &ncand, int &nmiss) {
     const int l8 = lane & 7;
@@ -250,7 +319,8 @@ __device__ __forceinline__ void icp_query_pass_grouped(const IcpArgs &A, const v
             const Pose P{Pv[0], Pv[1], Pv[2], Pv[3], Pv[4], Pv[5], Pv[6]};
             s = apply(P, V3{in[3 * q], in[3 * q + 1], in[3 * q + 2]});
             if (l8 == 0) { A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z; }
-            group8_closest(A.map, s, gmask, l8, slot, count, own, d2, my_rank);
+            if (NN27) group8_closest27(A.map, s, gmask, l8, slot, count, own, d2, my_rank);
+            else group8_closest(A.map, s, gmask, l8, slot, count, own, d2, my_rank);
             if (my_rank >= 0) {
                 const double *bx = voxel_rows(A.map, (unsigned int)slot);
                 tg = V3{__ldg(bx + my_rank), __ldg(bx + A.map.capp + my_rank), __ldg(bx + 2 * A.map.capp + my_rank)};
@@ -260,12 +330,21 @@ __device__ __forceinline__ void icp_query_pass_grouped(const IcpArgs &A, const v
         }
         const bool lead = on && l8 == 0;
         const bool gate = lead && d2 < A.tau_sq;
-        double c[16];
-        contribution(c, s, tg, d2, A.th, gate);
-        acc += warp_reduce_scatter16(c);
-        ncorr += gate ? 1 : 0;
-        ncand += lead ? count : 0;
-        nmiss += (lead && !own) ? 1 : 0;
+        if (PLANE) {
+            double nrm[3] = {0.0, 0.0, 0.0};
+            bool planar = false;   // the group's leading lane fits the plane of the matched voxel (sequential sums: bit-identical to the oracle)
+            if (gate && my_rank >= 0) planar = voxel_normal(A.map, slot, meta_count(load_slot(A.map.slots + slot).y), nrm) != 0;
+            double c[32];
+            contribution_plane(c, s, tg, nrm, A.th, planar, count, lead && !own, lead);
+            acc += warp_reduce_scatter32(c);
+        } else {
+            double c[16];
+            contribution(c, s, tg, d2, A.th, gate);
+            acc += warp_reduce_scatter16(c);
+            ncorr += gate ? 1 : 0;
+            ncand += lead ? count : 0;
+            nmiss += (lead && !own) ? 1 : 0;
+        }
     }
 }
 
@@ -282,10 +361,12 @@ __device__ unsigned long long g_frame_marks[16];
 // SHAPE 0 = latency build (eight lanes per query, a few thousand keypoints: one CTA per SM at most, so the compiler may
 // use up to 255 registers and the serial Gauss-Newton solve stays out of local memory); SHAPE 1 = bandwidth build
 // (one lane per query + cooperative scan, 64 registers -> 4 CTAs/SM for the HBM-bound kernel mode).
-template <int SHAPE>
+template <int SHAPE, bool NN27, bool PLANE>
 static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_persistent(const IcpArgs A) {
+    constexpr int NSX = PLANE ? NSP : NS;              // doubles per partial row
+    constexpr int I_NCORR = PLANE ? 27 : 16;           // where the three counters sit in a row
     __shared__ double red[(ICP_BLOCK / 32) * 32];
-    __shared__ double S[NS];
+    __shared__ double S[NSX];
     __shared__ double E[7], Tinit[7], Ticp[7];
     __shared__ int done;
     __shared__ int comm_dead;
@@ -303,7 +384,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
     const int64_t n = A.n_dev ? (int64_t)__ldcg(A.n_dev) : A.n_max;
     const bool run_icp = !(__ldcg(A.map_counters) == 0ull || A.max_iter <= 0);   // ICP :99-100: empty map -> init_guess
     if (threadIdx.x < 7) { Tinit[threadIdx.x] = A.init_pose[threadIdx.x]; Ticp[threadIdx.x] = threadIdx.x == 3 ? 1.0 : 0.0; }
-    if (threadIdx.x < NS) S[threadIdx.x] = 0.0;
+    if (threadIdx.x < NSX) S[threadIdx.x] = 0.0;
     if (threadIdx.x == 0) comm_dead = 0;
     __syncthreads();
     const int64_t wbase = ((int64_t)blockIdx.x * (ICP_BLOCK / 32) + warp) * 32, wstride = (int64_t)A.icp_blocks * ICP_BLOCK;
@@ -315,22 +396,34 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
         int ncorr = 0, ncand = 0, nmiss = 0;
         const volatile double *Pv = j == 0 ? Tinit : E;   // re-read per batch: keeps 14 registers free across the lookup
         const double *in = j == 0 ? A.points : A.work;
-        if (SHAPE == 0) icp_query_pass_grouped(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
-        else icp_query_pass(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
+        if (SHAPE == 0) icp_query_pass_grouped<NN27, PLANE>(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
+        else icp_query_pass<NN27, PLANE>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
         PT_MARK(1);
+        double *rows = A.partials + (size_t)(j & 1) * A.icp_blocks * NSX;
+        if (PLANE) {
+            // CTA row: lane L of every warp holds sum L (27 sums + 3 counters + 2 zeros)
+            red[warp * 32 + lane] = acc;
+            __syncthreads();
+            if (threadIdx.x < NSX) {
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < ICP_BLOCK / 32; ++w) v += red[w * 32 + threadIdx.x];
+                rows[(size_t)blockIdx.x * NSX + threadIdx.x] = v;
+            }
+        } else {
         // CTA row: 16 sums (even lanes hold them) + 3 counters
         ncorr = __reduce_add_sync(0xFFFFFFFFu, ncorr);
         ncand = __reduce_add_sync(0xFFFFFFFFu, ncand);
         nmiss = __reduce_add_sync(0xFFFFFFFFu, nmiss);
         red[warp * 32 + lane] = (lane & 1) ? (lane == 1 ? (double)ncorr : lane == 3 ? (double)ncand : lane == 5 ? (double)nmiss : 0.0) : acc;
         __syncthreads();
-        double *rows = A.partials + (size_t)(j & 1) * A.icp_blocks * NS;
         if (threadIdx.x < NS) {
             const int src_lane = threadIdx.x < 16 ? 2 * threadIdx.x : 2 * (threadIdx.x - 16) + 1;
             double v = 0.0;
 #pragma unroll
             for (int w = 0; w < ICP_BLOCK / 32; ++w) v += red[w * 32 + src_lane];
             rows[(size_t)blockIdx.x * NS + threadIdx.x] = v;
+        }
         }
         PT_MARK(2);
         gs_icp.sync();
@@ -339,20 +432,20 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
         // accumulators keep the L2 loads in flight), then one thread per column adds the 8 warp partials.
         {
             double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-            if (lane < NS) {
+            if (lane < NSX) {
                 const int G = ICP_BLOCK / 32;
                 int b = warp;
                 for (; b + 3 * G < A.icp_blocks; b += 4 * G) {
-                    v0 += __ldcg(rows + (size_t)b * NS + lane);
-                    v1 += __ldcg(rows + (size_t)(b + G) * NS + lane);
-                    v2 += __ldcg(rows + (size_t)(b + 2 * G) * NS + lane);
-                    v3 += __ldcg(rows + (size_t)(b + 3 * G) * NS + lane);
+                    v0 += __ldcg(rows + (size_t)b * NSX + lane);
+                    v1 += __ldcg(rows + (size_t)(b + G) * NSX + lane);
+                    v2 += __ldcg(rows + (size_t)(b + 2 * G) * NSX + lane);
+                    v3 += __ldcg(rows + (size_t)(b + 3 * G) * NSX + lane);
                 }
-                for (; b < A.icp_blocks; b += G) v0 += __ldcg(rows + (size_t)b * NS + lane);
+                for (; b < A.icp_blocks; b += G) v0 += __ldcg(rows + (size_t)b * NSX + lane);
             }
             red[warp * 32 + lane] = (v0 + v1) + (v2 + v3);
             __syncthreads();
-            if (threadIdx.x < NS) {
+            if (threadIdx.x < NSX) {
                 double v = 0.0;
 #pragma unroll
                 for (int w = 0; w < ICP_BLOCK / 32; ++w) v += red[w * 32 + threadIdx.x];
@@ -360,7 +453,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
             }
         }
         __syncthreads();
-        if (A.nranks > 1) {
+        if (!PLANE && A.nranks > 1) {
             // Fused exchange: CTA 0 stores this rank's row into EVERY rank's mailbox (its own included) over NVLink, then a
             // system-scope release of the stamp; every CTA of every rank then waits for all stamps in its LOCAL mailbox and
             // adds the rows in rank order -- the same order everywhere, so all ranks solve bit-identical normal equations
@@ -405,7 +498,8 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
             FT_MARK(8);
             if (lane == 0) {
                 double H[36], g[6], x[6];
-                expand_normal_equations(S, H, g);
+                if (PLANE) expand_plane_equations(S, H, g);
+                else expand_normal_equations(S, H, g);
 #pragma unroll
                 for (int k = 0; k < 6; ++k) g[k] = -g[k];
                 ldlt6_solve(H, g, x);                             // JTJ.ldlt().solve(-JTr) :90
@@ -429,11 +523,12 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
             FT_MARK(12);
             if (blockIdx.x == 0 && lane == 2) {
                 if (A.est_trace) pose_store(est, A.est_trace + 7 * (size_t)j);
-                if (A.ncorr_trace) A.ncorr_trace[j] = (long long)S[16];
+                if (A.ncorr_trace) A.ncorr_trace[j] = (long long)S[I_NCORR];
 #ifndef LIMU_ICP_PHASE_TIMING
                 if (A.hg_trace) {
                     double H[36], g[6];
-                    expand_normal_equations(S, H, g);
+                    if (PLANE) expand_plane_equations(S, H, g);
+                    else expand_normal_equations(S, H, g);
                     double *o = A.hg_trace + 42 * (size_t)j;
                     for (int k = 0; k < 36; ++k) o[k] = H[k];
                     for (int k = 0; k < 6; ++k) o[36 + k] = g[k];
@@ -452,7 +547,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const Pose np = run_icp ? mul(pose_load(Ticp), pose_load(Tinit)) : pose_load(Tinit);
         pose_store(np, A.out);
-        A.out[7] = (double)j; A.out[8] = (double)converged; A.out[9] = S[16]; A.out[10] = S[17]; A.out[11] = S[18]; A.out[12] = (double)n;
+        A.out[7] = (double)j; A.out[8] = (double)converged; A.out[9] = S[I_NCORR]; A.out[10] = S[I_NCORR + 1]; A.out[11] = S[I_NCORR + 2]; A.out[12] = (double)n;
     }
     if (A.upd_down) {
         // local_map.update(down_sampled, new_pose) (icp.cpp:81; voxel_hash_map.cpp:138-144): transform + capped ordered insert
@@ -540,11 +635,12 @@ static int g_icp_blocks_per_sm = 0;
 // Enqueue the persistent ICP kernel. All pointers are device memory; `out13` receives pose + stats.
 int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t n_max, const int *n_dev, const double *init_pose_host,
                double tau, double th, int max_iter, double eps, double *partials_dev, size_t partial_rows, double *out13_dev, int64_t n_hint,
-               double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev, int max_iter_all_ranks, const FrameFusion *fuse) {
+               double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev, int max_iter_all_ranks, const FrameFusion *fuse, int icp_mode) {
     limu_ctx *c = m->ctx;
+    const bool nn27 = (icp_mode & LIMU_ICP_NN27) != 0, plane = (icp_mode & LIMU_ICP_PLANE) != 0;
     if (g_icp_blocks_per_sm == 0) {
         int b = 0;
-        LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_icp_persistent<1>, ICP_BLOCK, 0));
+        LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_icp_persistent<1, false, false>, ICP_BLOCK, 0));
         g_icp_blocks_per_sm = std::max(1, b);
     }
     const bool grouped = n_hint <= 16384 && m->cap <= 64;   // latency shape: eight lanes per query, one CTA per SM
@@ -586,7 +682,12 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
     }
     void *args[] = {&A};
     LIMU_TRY(prof_begin(c, LIMU_STAGE_ICP));
-    const void *fn = grouped ? (const void *)k_icp_persistent<0> : (const void *)k_icp_persistent<1>;
+    if (plane && max_iter_all_ranks >= 0 && c->comm && c->comm->nranks > 1) { set_error("the point-to-plane variant is not available in the point-sharded loop"); return LIMU_ERR_INVALID; }
+    const void *fns[2][2][2] = {{{(const void *)k_icp_persistent<0, false, false>, (const void *)k_icp_persistent<0, false, true>},
+                                 {(const void *)k_icp_persistent<0, true, false>, (const void *)k_icp_persistent<0, true, true>}},
+                                {{(const void *)k_icp_persistent<1, false, false>, (const void *)k_icp_persistent<1, false, true>},
+                                 {(const void *)k_icp_persistent<1, true, false>, (const void *)k_icp_persistent<1, true, true>}}};
+    const void *fn = fns[grouped ? 0 : 1][nn27 ? 1 : 0][plane ? 1 : 0];
     LIMU_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(ICP_BLOCK), args, 0, c->stream));
     LIMU_LAUNCHED();
     LIMU_TRY(prof_end(c, LIMU_STAGE_ICP));
@@ -615,7 +716,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_step(const IcpArgs 
     double acc = 0.0;
     int ncorr = 0, ncand = 0, nmiss = 0;
     const int64_t wbase = ((int64_t)blockIdx.x * (ICP_BLOCK / 32) + warp) * 32, wstride = (int64_t)A.icp_blocks * ICP_BLOCK;
-    icp_query_pass(A, Pose7, first ? A.points : A.work, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
+    icp_query_pass<false, false>(A, Pose7, first ? A.points : A.work, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
     ncorr = __reduce_add_sync(0xFFFFFFFFu, ncorr);
     ncand = __reduce_add_sync(0xFFFFFFFFu, ncand);
     nmiss = __reduce_add_sync(0xFFFFFFFFu, nmiss);
@@ -697,11 +798,12 @@ static int icp_sharded_nccl(limu_map *m, const double *points_dev, int64_t n, co
 using namespace limu;
 
 static int icp_common(limu_map *m, const double *points_dev, int64_t n, const double init_guess[7], double tau, double th, int max_iter, double eps,
-                      double pose_out[7], limu_icp_stats *stats, double *est_trace, int64_t *ncorr_trace, double *hg_trace, bool sharded = false) {
+                      double pose_out[7], limu_icp_stats *stats, double *est_trace, int64_t *ncorr_trace, double *hg_trace, bool sharded = false,
+                      int icp_mode = 0) {
     limu_ctx *c = m->ctx;
     const int rows = icp_partial_rows(c);
     LIMU_TRY(c->tmp4.reserve((size_t)std::max<int64_t>(n, 1) * 24, c->stream));                 // working cloud
-    LIMU_TRY(c->tmp5.reserve((size_t)2 * rows * NS * 8 + 256, c->stream));                     // partial rows
+    LIMU_TRY(c->tmp5.reserve((size_t)2 * rows * NS_MAX * 8 + 256, c->stream));                 // partial rows
     const bool tr = est_trace || ncorr_trace || hg_trace;
     const size_t it = (size_t)std::max(max_iter, 1);
     if (tr) LIMU_TRY(c->tmp3.reserve(it * (7 + 1 + 42) * 8, c->stream));
@@ -711,7 +813,7 @@ static int icp_common(limu_map *m, const double *points_dev, int64_t n, const do
     long long *d_nc = tr ? reinterpret_cast<long long *>(d_est + it * 7) : nullptr;
     double *d_hg = tr ? d_est + it * 8 : nullptr;
     LIMU_TRY(icp_device(m, points_dev, c->tmp4.as<double>(), n, nullptr, init_guess, tau, th, max_iter, eps, partials, (size_t)rows, out13, n,
-                        d_est, d_nc, d_hg, sharded ? max_iter : -1, nullptr));
+                        d_est, d_nc, d_hg, sharded ? max_iter : -1, nullptr, icp_mode));
     double *h = static_cast<double *>(c->h_pinned) + 16;
     LIMU_CUDA_TRY(cudaMemcpyAsync(h, out13, 13 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -744,6 +846,16 @@ int limu_icp(limu_map *m, const double *xyz, int64_t n, const double init_guess[
     LIMU_TRY(stage_in(m->ctx, m->ctx->in0, xyz, (size_t)n * 24));
     return icp_common(m, m->ctx->in0.as<double>(), n, init_guess, max_corresp_dist, kernel, icp_max_iteration, est_threshold, pose_out, stats,
                       est_trace, ncorr_trace, hg_trace);
+}
+
+int limu_icp_ex(limu_map *m, const double *xyz, int64_t n, const double init_guess[7], double max_corresp_dist, double kernel, int icp_max_iteration,
+                double est_threshold, int32_t icp_mode, double pose_out[7], limu_icp_stats *stats, double *est_trace, int64_t *ncorr_trace, double *hg_trace) {
+    LIMU_REQUIRE(m && init_guess && pose_out && n >= 0 && (n == 0 || xyz), "limu_icp_ex: bad arguments");
+    LIMU_REQUIRE((icp_mode & ~(LIMU_ICP_NN27 | LIMU_ICP_PLANE)) == 0, "limu_icp_ex: unknown icp_mode bits");
+    LIMU_TRY(bind(m->ctx));
+    LIMU_TRY(stage_in(m->ctx, m->ctx->in0, xyz, (size_t)n * 24));
+    return icp_common(m, m->ctx->in0.as<double>(), n, init_guess, max_corresp_dist, kernel, icp_max_iteration, est_threshold, pose_out, stats,
+                      est_trace, ncorr_trace, hg_trace, false, icp_mode);
 }
 
 int limu_icp_dev(limu_map *m, const double *xyz_dev, int64_t n, const double init_guess[7], double max_corresp_dist, double kernel,

@@ -106,12 +106,12 @@ static __global__ void k_gather_voxels(MapView m, const unsigned int *order, int
 // get_closest_neighbour for a batch (voxel_hash_map.cpp:64-102); flag = within max_correspondance (:120).
 static __global__ void __launch_bounds__(256) k_closest(MapView m, const double *__restrict__ xyz, int64_t n_max, const int *n_dev, double max_sq,
                                                        double *__restrict__ out_xyz, int *__restrict__ out_key, int *__restrict__ out_rank,
-                                                       unsigned char *__restrict__ flags) {
+                                                       unsigned char *__restrict__ flags, int nn27) {
     const int64_t n = n_dev ? (int64_t)*n_dev : n_max;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const V3 p{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
-    const Nearest r = map_closest(m, p);
+    const Nearest r = nn27 ? map_closest27(m, p) : map_closest(m, p);
     if (out_xyz) { out_xyz[3 * i] = r.x; out_xyz[3 * i + 1] = r.y; out_xyz[3 * i + 2] = r.z; }
     if (out_key) {
         int x = INT32_MIN, y = INT32_MIN, z = INT32_MIN;
@@ -384,7 +384,11 @@ int limu_map_update(limu_map *m, const double *xyz, int64_t n, const double pose
 }
 
 int limu_map_closest(limu_map *m, const double *xyz, int64_t n, double *out_xyz, int32_t *out_key, int32_t *out_rank) {
-    LIMU_REQUIRE(m && (xyz || n == 0) && n >= 0 && (out_xyz || n == 0), "limu_map_closest: bad arguments");
+    return limu_map_closest_ex(m, xyz, n, LIMU_ICP_REFERENCE, out_xyz, out_key, out_rank);
+}
+
+int limu_map_closest_ex(limu_map *m, const double *xyz, int64_t n, int32_t icp_mode, double *out_xyz, int32_t *out_key, int32_t *out_rank) {
+    LIMU_REQUIRE(m && (xyz || n == 0) && n >= 0 && (out_xyz || n == 0) && (icp_mode & ~LIMU_ICP_NN27) == 0, "limu_map_closest: bad arguments");
     LIMU_TRY(bind(m->ctx));
     if (n == 0) return LIMU_OK;
     limu_ctx *c = m->ctx;
@@ -393,7 +397,8 @@ int limu_map_closest(limu_map *m, const double *xyz, int64_t n, double *out_xyz,
     LIMU_TRY(c->out1.reserve((size_t)n * 12, c->stream));
     LIMU_TRY(c->out2.reserve((size_t)n * 4, c->stream));
     k_closest<<<div_up(n, 256), 256, 0, c->stream>>>(m->view(), c->in0.as<double>(), n, nullptr, 0.0, c->out0.as<double>(),
-                                                     out_key ? c->out1.as<int>() : nullptr, out_rank ? c->out2.as<int>() : nullptr, nullptr);
+                                                     out_key ? c->out1.as<int>() : nullptr, out_rank ? c->out2.as<int>() : nullptr, nullptr,
+                                                     (icp_mode & LIMU_ICP_NN27) ? 1 : 0);
     LIMU_LAUNCHED();
     LIMU_CUDA_TRY(cudaMemcpyAsync(out_xyz, c->out0.p, (size_t)n * 24, cudaMemcpyDeviceToHost, c->stream));
     if (out_key) LIMU_CUDA_TRY(cudaMemcpyAsync(out_key, c->out1.p, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
@@ -419,7 +424,7 @@ int limu_map_correspondences(limu_map *m, const double *xyz, int64_t n, double m
     int *count_dev = reinterpret_cast<int *>(c->d_small.as<double>());
     const double max_sq = max_correspondance * max_correspondance;   // voxel_hash_map.cpp:112
     k_closest<<<div_up(n, 256), 256, 0, c->stream>>>(m->view(), c->in0.as<double>(), n, nullptr, max_sq, c->out0.as<double>(), nullptr, nullptr,
-                                                     c->tmp0.as<unsigned char>());
+                                                     c->tmp0.as<unsigned char>(), 0);
     LIMU_LAUNCHED();
     LIMU_TRY(compact_flags(c, c->tmp0.as<unsigned char>(), n, nullptr, c->tmp1.as<int>(), c->tmp2.as<int>(), count_dev));
     const int gb = std::min<int64_t>(div_up(n, 256), (int64_t)c->sm_count * 8);

@@ -272,6 +272,148 @@ __device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, un
     slot_out = slot; count_out = count; d2_out = bd2; rank_out = br == 0x7FFFFFFF ? -1 : br;
 }
 
+// ---- opt-in neighbour rule LIMU_NN_27 (no counterpart in the reference) -----------------------------
+// What the north star literally names and upstream KISS-ICP does: the NEAREST stored point over all 27 cells of the
+// query's neighbourhood (the reference only looks into the query's own voxel when it exists, voxel_hash_map.cpp:71-73).
+// Defined order: cells c = (dx+1)*9 + (dy+1)*3 + (dz+1) for dx, dy, dz in -1..1 (x outermost), points in storage order,
+// strict '<' -- the first minimum in (cell, rank) order wins, so the result is the lexicographic minimum of (d^2, c, rank)
+// and any evaluation order gives the same answer. Nothing stored in the 27 cells -> (0,0,0) like rule (c) above.
+__device__ __forceinline__ Nearest map_closest27(const MapView &m, const V3 &p) {
+    Nearest r;
+    r.x = r.y = r.z = 0.0; r.rank = -1; r.ncand = 0; r.slot = -1; r.own = 0;
+    const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
+    double best = 1.7976931348623157e308;
+    for (int dx = -1; dx <= 1; ++dx) {
+        ulonglong2 got[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {   // nine home-slot loads in flight
+            const int x = kx + dx, y = ky + (c / 3 - 1), z = kz + (c % 3 - 1);
+            got[c] = key_in_range(x, y, z) ? load_slot(m.slots + slot_of(pack_key(x, y, z), m.shift)) : make_ulonglong2(KEY_EMPTY, 0ull);
+        }
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            ulonglong2 v = got[c];
+            if (v.x == KEY_EMPTY) continue;
+            const unsigned long long want = pack_key(kx + dx, ky + (c / 3 - 1), kz + (c % 3 - 1));
+            unsigned int s = slot_of(want, m.shift);
+            while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(m.slots + s); }
+            if (v.x != want) continue;
+            if (dx == 0 && c == 4) r.own = 1;
+            const int count = meta_count(v.y);
+            const double *bx = voxel_rows(m, s), *by = bx + m.capp, *bz = by + m.capp;
+            for (int k = 0; k < count; ++k) {
+                const double cx = __ldg(bx + k), cy = __ldg(by + k), cz = __ldg(bz + k);
+                const double d = sqnorm3(p.x - cx, p.y - cy, p.z - cz);
+                if (d < best) { best = d; r.rank = k; r.slot = (int)s; r.x = cx; r.y = cy; r.z = cz; }
+            }
+            r.ncand += count;
+        }
+    }
+    return r;
+}
+
+// The same rule with eight lanes per query (latency shape): lane l probes cells l, l+8, l+16 (and 24..26), scans the
+// points of the cells it found, and a 3-step butterfly takes the lexicographic minimum of (d^2, cell, rank).
+__device__ __forceinline__ void group8_closest27(const MapView &m, const V3 &p, unsigned gmask, int l8, int &slot_out, int &count_out, int &own_out,
+                                                 double &d2_out, int &rank_out) {
+    const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
+    ulonglong2 got[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int c = l8 + 8 * u;
+        got[u] = make_ulonglong2(KEY_EMPTY, 0ull);
+        if (c < 27) {
+            const int x = kx + (c / 9 - 1), y = ky + ((c / 3) % 3 - 1), z = kz + (c % 3 - 1);
+            if (key_in_range(x, y, z)) got[u] = load_slot(m.slots + slot_of(pack_key(x, y, z), m.shift));
+        }
+    }
+    double bd2 = 1.7976931348623157e308;
+    int bc = 0x7FFFFFFF, br = 0x7FFFFFFF, bslot = -1, ncand = 0, own = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int c = l8 + 8 * u;
+        ulonglong2 v = got[u];
+        if (c < 27 && v.x != KEY_EMPTY) {
+            const unsigned long long want = pack_key(kx + (c / 9 - 1), ky + ((c / 3) % 3 - 1), kz + (c % 3 - 1));
+            unsigned int s = slot_of(want, m.shift);
+            while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(m.slots + s); }
+            if (v.x == want) {
+                if (c == 13) own = 1;
+                const int count = meta_count(v.y);
+                const double *bx = voxel_rows(m, s), *by = bx + m.capp, *bz = by + m.capp;
+                for (int k = 0; k < count; ++k) {   // cells and ranks are visited in increasing order: strict '<' keeps the first minimum
+                    const double d = sqnorm3(p.x - __ldg(bx + k), p.y - __ldg(by + k), p.z - __ldg(bz + k));
+                    if (d < bd2) { bd2 = d; bc = c; br = k; bslot = (int)s; }
+                }
+                ncand += count;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(gmask, bd2, o);
+        const int oc = __shfl_xor_sync(gmask, bc, o), orr = __shfl_xor_sync(gmask, br, o), os = __shfl_xor_sync(gmask, bslot, o);
+        ncand += __shfl_xor_sync(gmask, ncand, o);
+        own |= __shfl_xor_sync(gmask, own, o);
+        if (od < bd2 || (od == bd2 && (oc < bc || (oc == bc && orr < br)))) { bd2 = od; bc = oc; br = orr; bslot = os; }
+    }
+    slot_out = bslot; count_out = ncand; own_out = own; d2_out = bd2; rank_out = bslot >= 0 ? br : -1;
+}
+
+// ---- opt-in point-to-plane residual LIMU_ICP_PLANE (no counterpart in the reference) -----------------
+// Plane of a correspondence = plane of the matched point's VOXEL: with c >= 5 stored points, mean mu and scatter
+// S = sum (p-mu)(p-mu)^T, the normal is the eigenvector of S's smallest eigenvalue by 5 cyclic Jacobi sweeps (only + - * /
+// sqrt in a fixed order, compiled without FMA: bit-identical to the C oracle's voxel_normal). Planar when
+// l_min <= 0.04 l_mid; otherwise (or with < 5 points) the correspondence is dropped. Returns 1 and the normal if planar.
+constexpr int PLANE_MIN_POINTS = 5;
+constexpr double PLANE_RATIO = 0.04;
+__device__ __forceinline__ int voxel_normal(const MapView &m, int slot, int c, double *nrm) {
+    if (c < PLANE_MIN_POINTS) return 0;
+    const double *bx = voxel_rows(m, (unsigned int)slot), *by = bx + m.capp, *bz = by + m.capp;
+    double mx = 0.0, my = 0.0, mz = 0.0;
+    for (int r = 0; r < c; ++r) { mx += __ldg(bx + r); my += __ldg(by + r); mz += __ldg(bz + r); }
+    mx /= (double)c; my /= (double)c; mz /= (double)c;
+    double a00 = 0.0, a01 = 0.0, a02 = 0.0, a11 = 0.0, a12 = 0.0, a22 = 0.0;
+    for (int r = 0; r < c; ++r) {
+        const double dx = __ldg(bx + r) - mx, dy = __ldg(by + r) - my, dz = __ldg(bz + r) - mz;
+        a00 += dx * dx; a01 += dx * dy; a02 += dx * dz; a11 += dy * dy; a12 += dy * dz; a22 += dz * dz;
+    }
+    double v00 = 1.0, v01 = 0.0, v02 = 0.0, v10 = 0.0, v11 = 1.0, v12 = 0.0, v20 = 0.0, v21 = 0.0, v22 = 1.0;
+    // One Jacobi rotation in the (p,q) plane; o is the third index. App/Aqq/Apq: the pivot block; Aop/Aoq: the other two entries;
+    // Vxp/Vxq: the eigenvector columns p and q.
+#define LIMU_JACOBI(App, Aqq, Apq, Aop, Aoq, V0p, V0q, V1p, V1q, V2p, V2q)                                   \
+    if (Apq != 0.0) {                                                                                       \
+        const double theta = (Aqq - App) / (2.0 * Apq);                                                     \
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));           \
+        const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;                                             \
+        const double app = App, aqq = Aqq, aop = Aop, aoq = Aoq;                                            \
+        App = app - t * Apq; Aqq = aqq + t * Apq; Apq = 0.0;                                                \
+        Aop = cs * aop - sn * aoq; Aoq = sn * aop + cs * aoq;                                               \
+        double vp, vq;                                                                                      \
+        vp = V0p; vq = V0q; V0p = cs * vp - sn * vq; V0q = sn * vp + cs * vq;                               \
+        vp = V1p; vq = V1q; V1p = cs * vp - sn * vq; V1q = sn * vp + cs * vq;                               \
+        vp = V2p; vq = V2q; V2p = cs * vp - sn * vq; V2q = sn * vp + cs * vq;                               \
+    }
+#pragma unroll 1
+    for (int sweep = 0; sweep < 5; ++sweep) {
+        LIMU_JACOBI(a00, a11, a01, a02, a12, v00, v01, v10, v11, v20, v21)   // (p,q) = (0,1), o = 2: A[2][0], A[2][1]
+        LIMU_JACOBI(a00, a22, a02, a01, a12, v00, v02, v10, v12, v20, v22)   // (0,2), o = 1: A[1][0], A[1][2]
+        LIMU_JACOBI(a11, a22, a12, a01, a02, v01, v02, v11, v12, v21, v22)   // (1,2), o = 0: A[0][1], A[0][2]
+    }
+#undef LIMU_JACOBI
+    int lo = 0;
+    double l_lo = a00;
+    if (a11 < l_lo) { lo = 1; l_lo = a11; }
+    if (a22 < l_lo) { lo = 2; l_lo = a22; }
+    const double l1 = lo == 0 ? a11 : (lo == 1 ? a22 : a00), l2 = lo == 0 ? a22 : (lo == 1 ? a00 : a11);
+    const double mid = l1 < l2 ? l1 : l2;
+    if (!(mid > 0.0) || !(l_lo <= PLANE_RATIO * mid)) return 0;
+    nrm[0] = lo == 0 ? v00 : (lo == 1 ? v01 : v02);
+    nrm[1] = lo == 0 ? v10 : (lo == 1 ? v11 : v12);
+    nrm[2] = lo == 0 ? v20 : (lo == 1 ? v21 : v22);
+    return 1;
+}
+
 // ---- insertion / eviction, one element per call (used by the stand-alone kernels and the fused frame kernel) -------
 // Pass 1 of insert_points (voxel_hash_map.cpp:12-62) for input point `i` of the batch:
 //   - voxel key (get_vox_index), claim-or-find its slot (64-bit CAS on the packed key),

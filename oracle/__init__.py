@@ -126,6 +126,8 @@ class _Api:
             f("kiss_last_iterations", C.c_int, [C.c_void_p])
             f("kiss_last_sigma", C.c_double, [C.c_void_p])
             f("kiss_map", C.c_void_p, [C.c_void_p])
+            f("map_set_mode", None, [C.c_void_p, C.c_int])
+            f("kiss_set_mode", None, [C.c_void_p, C.c_int])
         if hasattr(lib, p + "process_frame"):
             f("process_frame", C.c_long, [C.c_char_p, C.c_long, C.c_int, C.c_int, C.c_char_p, _ip, _ip, _ip, _dp, C.c_double, C.c_int, C.c_long, _lp, _dp, _fp, _dp])
         f("kiss_create", C.c_void_p, [C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double])
@@ -339,6 +341,10 @@ class _Map:
             self.api._map_destroy(self.h)
             self.h = None
 
+    def set_mode(self, icp_mode):
+        """PORT ONLY: opt-in neighbour rule (1 = nearest of the 27-cell neighbourhood)."""
+        self.api._map_set_mode(self.h, int(icp_mode))
+
     def insert(self, xyz):
         xyz = _pts(xyz)
         self.api._map_insert(self.h, _d(xyz), len(xyz))
@@ -427,6 +433,10 @@ class _Kiss:
         if getattr(self, "h", None):
             self.api._kiss_destroy(self.h)
             self.h = None
+
+    def set_mode(self, icp_mode):
+        """PORT ONLY: opt-in neighbour rule of the local map."""
+        self.api._kiss_set_mode(self.h, int(icp_mode))
 
     def _out(self, n):
         return np.empty((max(n, 1), 3)), np.empty((max(n, 1), 3)), C.c_long(0), C.c_long(0), np.empty(7)

@@ -203,6 +203,7 @@ static inline uint64_t key_hash(const int *k) {
 struct lo_map {
     double vox_size, max_distance;
     int cap;
+    int icp_mode;  /* 0 = the reference's neighbour rule; bit 0 (LO_ICP_NN27) = nearest point of the 27-cell neighbourhood */
     long n_entries, n_alive, entries_cap;
     int *keys;     /* 3 per entry (creation order) */
     int *counts;   /* points stored; -1 = erased entry */
@@ -370,12 +371,41 @@ static long closest_entry(const lo_map *m, const double *p) {
     return best;
 }
 
+/* Opt-in neighbour rule LO_ICP_NN27 (NOT in the reference -- this restatement is the definition the CUDA path is
+ * checked against): the nearest stored point over all 27 cells around the query's voxel, cells visited x-outermost, points in storage
+ * order, strict '<' (first minimum wins); nothing stored there -> no match, i.e. (0,0,0) like rule (c). */
+static long closest27_entry(const lo_map *m, const double *p, int *rank_out) {
+    int k[3];
+    lo_vox_index(p, 1, m->vox_size, k);
+    long best = -1;
+    double min_dist = 1.7976931348623157e308;
+    *rank_out = -1;
+    for (int i = k[0] - 1; i <= k[0] + 1; ++i)
+        for (int j = k[1] - 1; j <= k[1] + 1; ++j)
+            for (int l = k[2] - 1; l <= k[2] + 1; ++l) {
+                const int q[3] = {i, j, l};
+                const long c = map_find(m, q);
+                if (c < 0) continue;
+                const double *b = m->pts + 3 * (size_t)c * (size_t)m->cap;
+                for (int r = 0; r < m->counts[c]; ++r) {
+                    const double d = sqn3(p[0] - b[3 * r], p[1] - b[3 * r + 1], p[2] - b[3 * r + 2]);
+                    if (d < min_dist) { min_dist = d; best = c; *rank_out = r; }
+                }
+            }
+    return best;
+}
+void lo_map_set_mode(lo_map *m, int icp_mode) { m->icp_mode = icp_mode; }
+
 void lo_map_closest(const lo_map *m, const double *xyz, long n, double *out, int *out_key, int *out_rank) {
     for (long i = 0; i < n; ++i) {
         const double *p = xyz + 3 * i;
-        const long e = closest_entry(m, p);
         int r = -1;
-        if (e >= 0) r = block_closest(m, e, p);
+        long e;
+        if (m->icp_mode & 1) e = closest27_entry(m, p, &r);
+        else {
+            e = closest_entry(m, p);
+            if (e >= 0) r = block_closest(m, e, p);
+        }
         if (e >= 0 && r >= 0) {
             const double *t = m->pts + 3 * ((size_t)e * (size_t)m->cap + (size_t)r);
             out[3 * i] = t[0]; out[3 * i + 1] = t[1]; out[3 * i + 2] = t[2];
@@ -502,6 +532,82 @@ void lo_align(const double *src, const double *tgt, long n, double th, double *H
     if (pose7) lo_se3_exp(x, pose7);
 }
 
+/* ---- opt-in point-to-plane residual LO_ICP_PLANE (NOT in the reference: this restatement is the definition) ----
+ * Plane of a correspondence = the plane of the matched point's VOXEL: with c >= 5 stored points, mean mu and scatter S = sum (p-mu)(p-mu)^T,
+ * the normal is the eigenvector of S's smallest eigenvalue, found by 5 cyclic Jacobi sweeps (rotations (0,1), (0,2), (1,2); only + - * /
+ * sqrt, so the device reproduces it bit for bit). The voxel is planar when l_min <= 0.04 l_mid (thickness <= 0.2 x the minor in-plane
+ * spread; line-like and blob-like voxels are rejected) and its correspondences are dropped otherwise, as are voxels with < 5 points.
+ * Residual e = n.(s - t), weight w = th^2/(th + e^2)^2, Jacobian row a = [n ; s x n] in the reference's perturbation model
+ * (s' = exp(x) s, J_point = [I | -hat(s)], registration.cpp:46-54), H += w a a^T, g += w a e, x = LDLT(H).solve(-g). */
+#define LO_PLANE_MIN_POINTS 5
+#define LO_PLANE_RATIO 0.04
+static int voxel_normal(const lo_map *m, long e, double *nrm) {
+    const int c = m->counts[e];
+    if (c < LO_PLANE_MIN_POINTS) return 0;
+    const double *b = m->pts + 3 * (size_t)e * (size_t)m->cap;
+    double mu[3] = {0, 0, 0};
+    for (int r = 0; r < c; ++r) { mu[0] += b[3 * r]; mu[1] += b[3 * r + 1]; mu[2] += b[3 * r + 2]; }
+    mu[0] /= (double)c; mu[1] /= (double)c; mu[2] /= (double)c;
+    double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int r = 0; r < c; ++r) {
+        const double dx = b[3 * r] - mu[0], dy = b[3 * r + 1] - mu[1], dz = b[3 * r + 2] - mu[2];
+        A[0][0] += dx * dx; A[0][1] += dx * dy; A[0][2] += dx * dz; A[1][1] += dy * dy; A[1][2] += dy * dz; A[2][2] += dz * dz;
+    }
+    A[1][0] = A[0][1]; A[2][0] = A[0][2]; A[2][1] = A[1][2];
+    static const int PQ[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+    for (int sweep = 0; sweep < 5; ++sweep)
+        for (int k = 0; k < 3; ++k) {
+            const int p = PQ[k][0], q = PQ[k][1];
+            const double apq = A[p][q];
+            if (apq == 0.0) continue;
+            const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+            const int o = 3 - p - q;                     /* the third index */
+            const double app = A[p][p], aqq = A[q][q], aop = A[o][p], aoq = A[o][q];
+            A[p][p] = app - t * apq; A[q][q] = aqq + t * apq; A[p][q] = A[q][p] = 0.0;
+            A[o][p] = A[p][o] = cs * aop - sn * aoq;
+            A[o][q] = A[q][o] = sn * aop + cs * aoq;
+            for (int i = 0; i < 3; ++i) { const double vip = V[i][p], viq = V[i][q]; V[i][p] = cs * vip - sn * viq; V[i][q] = sn * vip + cs * viq; }
+        }
+    int lo = 0;
+    if (A[1][1] < A[lo][lo]) lo = 1;
+    if (A[2][2] < A[lo][lo]) lo = 2;
+    const int i1 = (lo + 1) % 3, i2 = (lo + 2) % 3;
+    const double mid = A[i1][i1] < A[i2][i2] ? A[i1][i1] : A[i2][i2];
+    if (!(mid > 0.0) || !(A[lo][lo] <= LO_PLANE_RATIO * mid)) return 0;
+    nrm[0] = V[0][lo]; nrm[1] = V[1][lo]; nrm[2] = V[2][lo];
+    return 1;
+}
+
+/* One Gauss-Newton step of the point-to-plane variant over the current source cloud. Returns the number of plane correspondences. */
+static long plane_step(const lo_map *m, const double *source, long n, double tau, double th, double *H, double *g) {
+    memset(H, 0, 36 * sizeof(double)); memset(g, 0, 6 * sizeof(double));
+    const double max_sq = tau * tau;
+    long used = 0;
+    for (long i = 0; i < n; ++i) {
+        const double *s = source + 3 * i;
+        double t[3];
+        int key[3], rank;
+        lo_map_closest(m, s, 1, t, key, &rank);
+        if (rank < 0) continue;
+        if (!(sqn3(t[0] - s[0], t[1] - s[1], t[2] - s[2]) < max_sq)) continue;
+        double nr[3];
+        if (!voxel_normal(m, map_find(m, key), nr)) continue;
+        const double e = (nr[0] * (s[0] - t[0]) + nr[1] * (s[1] - t[1])) + nr[2] * (s[2] - t[2]);
+        const double den = th + e * e;
+        const double w = (th * th) / (den * den);
+        const double a[6] = {nr[0], nr[1], nr[2], s[1] * nr[2] - s[2] * nr[1], s[2] * nr[0] - s[0] * nr[2], s[0] * nr[1] - s[1] * nr[0]};
+        for (int r = 0; r < 6; ++r) {
+            const double wa = w * a[r];
+            for (int c = 0; c < 6; ++c) H[6 * r + c] += wa * a[c];
+            g[r] += wa * e;
+        }
+        ++used;
+    }
+    return used;
+}
+
 static double norm6(const double *x) { /* Eigen norm() of a 6-vector, SSE2: 3 packets then predux */
     const double a = (x[0] * x[0] + x[2] * x[2]) + x[4] * x[4];
     const double b = (x[1] * x[1] + x[3] * x[3]) + x[5] * x[5];
@@ -519,9 +625,18 @@ int lo_icp(const lo_map *m, const double *xyz, long n, const double *init7, doub
     double T_icp[7] = {0, 0, 0, 1, 0, 0, 0};                          /* :106 */
     int j = 0;
     for (; j < max_iter; ++j) {                                       /* :108 */
-        const long c = lo_map_correspondences(m, source, n, tau, cs, ct, NULL); /* :111 */
+        long c;
         double est[7], H[36], g[6], lg[6], tmp[7];
-        lo_align(cs, ct, c, th, H, g, NULL, est);                     /* :116 */
+        if (m->icp_mode & 2) {                                        /* opt-in point-to-plane variant (not in the reference) */
+            double ng[6], x[6];
+            c = plane_step(m, source, n, tau, th, H, g);
+            for (int i = 0; i < 6; ++i) ng[i] = -g[i];
+            ldlt6_solve(H, ng, x);
+            lo_se3_exp(x, est);
+        } else {
+            c = lo_map_correspondences(m, source, n, tau, cs, ct, NULL); /* :111 */
+            lo_align(cs, ct, c, th, H, g, NULL, est);                 /* :116 */
+        }
         lo_transform(est, source, n);                                 /* :119 */
         lo_se3_mul(est, T_icp, tmp); memcpy(T_icp, tmp, sizeof tmp);  /* :122 */
         if (est_trace) memcpy(est_trace + 7 * j, est, sizeof est);
@@ -736,6 +851,7 @@ void lo_kiss_destroy(lo_kiss *k) { if (k) { lo_map_destroy(k->map); free(k->pose
 long lo_kiss_num_poses(const lo_kiss *k) { return k->n_poses; }
 void lo_kiss_pose(const lo_kiss *k, long i, double *p) { memcpy(p, k->poses + 7 * i, 7 * sizeof(double)); }
 lo_map *lo_kiss_map(lo_kiss *k) { return k->map; }
+void lo_kiss_set_mode(lo_kiss *k, int icp_mode) { lo_map_set_mode(k->map, icp_mode); }
 int lo_kiss_last_iterations(const lo_kiss *k) { return k->last_iters; }
 double lo_kiss_last_sigma(const lo_kiss *k) { return k->last_sigma; }
 

@@ -37,6 +37,12 @@ void lo_map_destroy(lo_map *m);
 void lo_map_clear(lo_map *m);                                                /* :200-204 */
 int lo_map_empty(const lo_map *m);                                           /* :206-210 */
 long lo_map_num_voxels(const lo_map *m);
+/* Opt-in registration variants. NOT in the reference: this restatement DEFINES them and is the parity oracle of the
+ * CUDA path for them. LO_ICP_NN27: get_closest_neighbour returns the nearest stored point over all 27 cells around the query's voxel
+ * (cells visited x-outermost, points in storage order, first minimum wins). Every function below that looks neighbours up
+ * (closest, correspondences, icp, the KissICP pipeline) follows the map's mode. */
+enum { LO_ICP_REFERENCE = 0, LO_ICP_NN27 = 1 };
+void lo_map_set_mode(lo_map *m, int icp_mode);
 void lo_map_insert(lo_map *m, const double *xyz, long n);                    /* insert_points :12-62 */
 void lo_map_update(lo_map *m, const double *xyz, long n, const double *pose7); /* update :138-144 */
 void lo_map_remove_far(lo_map *m, const double *origin3);                    /* :146-171 under null locks */
@@ -100,6 +106,7 @@ void lo_kiss_register_cloud(lo_kiss *k, const float *xyz, const double *ts, long
 long lo_kiss_num_poses(const lo_kiss *k);
 void lo_kiss_pose(const lo_kiss *k, long i, double *pose7);
 lo_map *lo_kiss_map(lo_kiss *k);
+void lo_kiss_set_mode(lo_kiss *k, int icp_mode);   /* LO_ICP_* of the local map */
 int lo_kiss_last_iterations(const lo_kiss *k);
 double lo_kiss_last_sigma(const lo_kiss *k);
 
