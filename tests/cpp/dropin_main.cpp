@@ -10,7 +10,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "limu/sensors/lidar/icp.hpp"   // resolves to include/limu_dropin/limu/sensors/lidar/icp.hpp
+#include "limu/sensors/lidar/icp.hpp"   // resolves to include/limu_dropin/limu/sensors/lidar/icp.hpp (which pulls the drop-in lidar/frame.hpp)
 
 using Arr = std::vector<double>;
 
@@ -113,6 +113,51 @@ int main(int argc, char **argv) {
         lidar::MotionCompensator mc;
         const auto poses = kiss.poses_();
         out.push_back(flat(mc.deskew_scan(cloud, ts, poses[poses.size() - 2], poses[poses.size() - 1])));
+    }
+    // frame::Lidar (the drop-in lidar/frame.hpp): in[14 + 2 n_scans] = PointCloud2 payload bytes (one per double),
+    // in[15 + 2 n_scans] = {message_time, point_step, frame_split_num, messages_to_replay}; the LidarPoint field layout of lidar/frame.hpp:21-23
+    {
+        const size_t at = static_cast<size_t>(14 + 2 * n_scans);
+        if (in.size() > at + 1) {
+            const Arr &bytes = in[at], &par = in[at + 1];
+            ros::NodeHandle nh;
+            frame::Lidar lidar_frame(nh);
+            lidar_frame.config->frame_split_num = static_cast<int>(par[2]);
+            auto msg = std::make_shared<sensor_msgs::PointCloud2>();
+            msg->point_step = static_cast<std::uint32_t>(par[1]);
+            msg->height = 1; msg->width = static_cast<std::uint32_t>(bytes.size() / static_cast<size_t>(par[1]));
+            msg->data.resize(bytes.size());
+            for (size_t i = 0; i < bytes.size(); ++i) msg->data[i] = static_cast<std::uint8_t>(bytes[i]);
+            const char *names[6] = {"x", "y", "z", "intensity", "ring", "timestamp"};
+            const int offs[6] = {0, 4, 8, 12, 14, 16}, types[6] = {7, 7, 7, 2, 4, 8};
+            for (int k = 0; k < 6; ++k) {
+                sensor_msgs::PointField f;
+                f.name = names[k]; f.offset = static_cast<std::uint32_t>(offs[k]); f.datatype = static_cast<std::uint8_t>(types[k]); f.count = 1;
+                msg->fields.push_back(f);
+            }
+            const int replay = static_cast<int>(par[3]);   // the same payload `replay` times: the 20th message onwards is split (frame.cpp:64)
+            Arr sizes, times, rec, tss;
+            for (int r = 0; r < replay; ++r) {
+                msg->header.stamp.fromSec(par[0]);
+                lidar_frame.initialize(msg);
+                lidar_frame.process_frame();
+                while (!lidar_frame.buffer_empty()) {
+                    const auto cloud = lidar_frame.get_lidar_buffer_front();
+                    const auto t = lidar_frame.get_segment_ts_front();
+                    if (r == replay - 1) {
+                        sizes.push_back(static_cast<double>(cloud->points.size()));
+                        times.push_back(lidar_frame.curr_acc_segment_time());
+                        for (size_t i = 0; i < cloud->points.size(); ++i) {
+                            const auto &q = cloud->points[i];
+                            rec.insert(rec.end(), {q.x, q.y, q.z, q.intensity, q.curvature});
+                            tss.push_back(t[i]);
+                        }
+                    }
+                    lidar_frame.pop();
+                }
+            }
+            out.push_back(sizes); out.push_back(times); out.push_back(rec); out.push_back(tss);
+        }
     }
     write_all(argv[2], out);
     std::printf("dropin_test ok: %zu output arrays\n", out.size());

@@ -39,6 +39,8 @@ def test_dropin_headers_name_the_reference_interfaces():
                                            "remove_points_from_far", "pointcloud", "clear", "empty", "update"],
             "helpers/registration.hpp": ["align_clouds", "SE3d ICP("],
             "helpers/deskew.hpp": ["class MotionCompensator", "deskew_scan"],
+            "frame.hpp": ["class Lidar", "struct ProcessingInfo", "initialize", "process_frame", "buffer_empty", "get_lidar_buffer_front",
+                          "get_segment_ts_front", "curr_acc_segment_time", "pop", "set_current_pose_nav", "return_prev_ts"],
             "icp.hpp": ["class KissICP", "register_frame", "voxelize", "iqr_processing", "get_prediction_model", "get_adaptive_threshold",
                         "current_vel", "has_moved", "local_map_", "poses_"]}
     for rel, names in want.items():
@@ -77,6 +79,12 @@ def test_cpp_consumer_matches_oracle(tmp_path, port, rng):
     arrs = [A, B, q, [tau], origin, T, asrc, atgt, [0.5], world, isrc, init, [6.0, 2.0 / 3.0, 60, 1e-4], [len(scans)]]
     for s, t in zip(scans, ts):
         arrs += [s[:, :3].astype(np.float64), t]
+    # frame::Lidar drop-in: one PointCloud2 payload replayed 21 times (the 21st is split in three, frame.cpp:64)
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_preprocess import CFG, make_msg
+    msg, mfields, mt = make_msg(77, 3000)
+    arrs += [msg.reshape(-1).astype(np.float64), [mt, msg.shape[1], 3, 21]]
     fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
     write_arrays(fin, arrs)
     r = subprocess.run([BIN, fin, fout], capture_output=True, text=True, timeout=300)
@@ -116,3 +124,8 @@ def test_cpp_consumer_matches_oracle(tmp_path, port, rng):
     np.testing.assert_allclose(o[j + 1], port.se3_mul(port.se3_inv(poses[-2]), poses[-1]), rtol=0, atol=1e-6)
     dk = port.deskew(scans[-1][:, :3], ts[-1], poses[-2], poses[-1])
     np.testing.assert_allclose(o[j + 2].reshape(-1, 3), dk, rtol=0, atol=1e-5)
+    seg = port.process_frame(msg, mfields, dict(CFG, frame_split_num=3), mt, 21)
+    assert len(seg) == 3 and o[j + 3].tolist() == [len(s["points"]) for s in seg]
+    assert np.array_equal(o[j + 4], [s["time"] for s in seg])
+    assert np.array_equal(o[j + 5].reshape(-1, 5), np.concatenate([s["points"] for s in seg]).astype(np.float64))
+    assert np.array_equal(o[j + 6], np.concatenate([s["ts"] for s in seg]))
