@@ -34,7 +34,8 @@ UNIT = "scans/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=150, help="scans timed; the loop of radius 30 m closes after ~188 scans at 1 m/scan, where the reference's "
+                    "Gauss-Newton loop stops converging and runs to its 500-iteration cap (both arms alike): W + K <= 180 stays in the converging regime")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=128000)
@@ -44,6 +45,8 @@ def parse():
     ap.add_argument("--voxel", type=float, default=1.0)
     ap.add_argument("--cap", type=int, default=10)
     ap.add_argument("--max-iter", type=int, default=500)
+    ap.add_argument("--icp-mode", type=int, default=0, help="0 = the reference's registration rules (the parity configuration, default); 1 = nearest of the "
+                    "27-cell neighbourhood, 2 = point-to-plane, 3 = both (opt-in variants, SURVEY 8f N2; the CPU arm is then the C oracle)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--ref-seconds", type=float, default=150.0, help="budget of the --impl reference run")
     return ap.parse_args()
@@ -143,17 +146,19 @@ def frame_kernel_bytes(n_q, iters, kbar, fmiss, n_src0, n_down, map_slots):
     return k4_bytes(n_q, iters, kbar, fmiss) + 24.0 * n_src0 + 64.0 * n_down + 16.0 * map_slots
 
 
-def cpu_reference_api():
+def cpu_reference_api(icp_mode=0):
     import oracle
-    if os.path.exists(oracle.REF_MT_SO):
+    if icp_mode == 0 and os.path.exists(oracle.REF_MT_SO):
         return oracle.load_ref(mt=True), "reference"
-    return oracle.load_port(), "port"
+    return oracle.load_port(), "port"   # the opt-in variants do not exist in the reference: the C oracle defines them
 
 
 def time_cpu(args, scans, warmup, max_steps, budget_s):
     """The reference's own register_frame on the host cores over a bounded prefix of the same sequence."""
-    api, kind = cpu_reference_api()
+    api, kind = cpu_reference_api(args.icp_mode)
     k = api.Kiss(voxel_size=args.voxel, max_range=100.0, cap=args.cap, deskew=True, icp_max_iteration=args.max_iter)
+    if args.icp_mode:
+        k.set_mode(args.icp_mode)
     xyz = [np.ascontiguousarray(s[:, :3]) for s in scans]
     ts = [s[:, 3].astype(np.float64) for s in scans]
     for i in range(min(warmup, len(scans))):
@@ -187,7 +192,9 @@ def main():
             "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": n_gpus, "steps": done, "steps_requested": K, "warmup": W,
             "ms_per_step": 1e3 * dt / done, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"configs[1]: synthetic {args.beams}-beam LiDAR, {args.points} pts/scan, loop r=30 m at {args.step_m} m/scan, voxel {args.voxel} m, cap {args.cap}, deskew on",
-                       "note": "the reference's unmodified register_frame (oracle/_ref, thread-pool TBB shim) on the host cores; rank 0 only"},
+                       "icp_mode": args.icp_mode,
+                       "note": "the reference's unmodified register_frame (oracle/_ref, thread-pool TBB shim) on the host cores; rank 0 only"
+                               if kind == "reference" else "C oracle (single thread): the opt-in registration variant has no counterpart in the reference"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": f"{done} consecutive scans after {W} warm-up scans (budget {args.ref_seconds:.0f} s)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "mpoints_per_s": val * args.points / 1e6,
@@ -226,7 +233,7 @@ def main():
             dist.barrier()
 
     def new_odom():
-        return ctx.KissICP(voxel_size=args.voxel, max_range=100.0, cap=args.cap, deskew=True, icp_max_iteration=args.max_iter)
+        return ctx.KissICP(voxel_size=args.voxel, max_range=100.0, cap=args.cap, deskew=True, icp_max_iteration=args.max_iter, icp_mode=args.icp_mode)
 
     def max_over_ranks(x):
         if world == 1:
@@ -319,6 +326,7 @@ def main():
                 "l2": "L2 flushed (512 MB write) after staging; every step reads a different scan, none re-read; the local map is persistent state",
                 "timing": "K steps bracketed by stream sync (+ barrier); CUDA events on the library stream and host wall clock, the larger one, max over ranks",
                 "icp_max_iteration": args.max_iter,
+                "icp_mode": args.icp_mode,
             },
             "mpoints_per_s": value * n_pts / 1e6,
             "iterations_per_scan": iters_total / K, "scans_at_iteration_cap": int((fr[:, 1] >= args.max_iter).sum()),
