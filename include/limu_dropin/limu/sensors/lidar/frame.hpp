@@ -65,22 +65,25 @@ namespace frame
 
         explicit Lidar(ros::NodeHandle &nh) : config(std::make_shared<ProcessingInfo>())
         {
-            // parameter names and defaults: lidar/frame.hpp:64-80
-            nh.param<double>("frame_rate", config->frame_rate, 10.0);
-            nh.param<double>("max_range", config->max_range, 100.0);
-            nh.param<double>("min_range", config->min_range, 5.0);
-            nh.param<double>("min_angle", config->min_angle, 0.0);
-            nh.param<double>("max_angle", config->max_angle, 360.0);
-            nh.param<int>("num_scan_lines", config->num_scan_lines, 16);
-            nh.param<int>("frame_split_num", config->frame_split_num, 1);
-            nh.param<double>("voxel_size", config->voxel_size, config->max_range / 100.0);
-            nh.param<int>("vox_side_length", config->vox_side_length, 3);
-            nh.param<int>("max_points_per_voxel", config->max_points_per_voxel, 10);
-            nh.param<bool>("deskew", config->deskew, false);
-            nh.param<double>("min_motion_th", config->min_motion_th, 0.1);
-            nh.param<int>("icp_max_iteration", config->icp_max_iteration, 500);
-            nh.param<double>("initial_threshold", config->initial_threshold, 2.0);
-            nh.param<double>("estimation_threshold", config->estimation_threshold, 0.0001);
+            // ROS parameter names and defaults of lidar/frame.hpp:64-80, read through two small typed helpers
+            ProcessingInfo &c = *config;
+            const auto real = [&nh](const char *key, double &dst, double fallback) { nh.param<double>(key, dst, fallback); };
+            const auto whole = [&nh](const char *key, int &dst, int fallback) { nh.param<int>(key, dst, fallback); };
+            real("frame_rate", c.frame_rate, 10.0);
+            real("max_range", c.max_range, 100.0);
+            real("min_range", c.min_range, 5.0);
+            real("min_angle", c.min_angle, 0.0);
+            real("max_angle", c.max_angle, 360.0);
+            whole("num_scan_lines", c.num_scan_lines, 16);
+            whole("frame_split_num", c.frame_split_num, 1);
+            real("voxel_size", c.voxel_size, c.max_range / 100.0);   // default: one hundredth of the range
+            whole("vox_side_length", c.vox_side_length, 3);
+            whole("max_points_per_voxel", c.max_points_per_voxel, 10);
+            nh.param<bool>("deskew", c.deskew, false);
+            real("min_motion_th", c.min_motion_th, 0.1);
+            whole("icp_max_iteration", c.icp_max_iteration, 500);
+            real("initial_threshold", c.initial_threshold, 2.0);
+            real("estimation_threshold", c.estimation_threshold, 1e-4);
         }
 
         // frame.cpp:10-26: count the message, detect a looped bag, hold the message for process_frame
