@@ -20,10 +20,16 @@ void set_error(const char *fmt, ...) {
 void release_ctx_scratch(limu_ctx *c);
 void release_pre_scratch(limu_ctx *c);
 
+int status_to_error(limu_ctx *c, const DevStatus &s);
+
 int check_status(limu_ctx *c) {
     LIMU_CUDA_TRY(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, c->stream));
     LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    const DevStatus s = *c->h_status;
+    return status_to_error(c, *c->h_status);
+}
+
+// Map a status word that is already on the host to a limu_status; clears the device word when something was flagged.
+int status_to_error(limu_ctx *c, const DevStatus &s) {
     if (s.key_range || s.table_full || s.pad[0]) {
         LIMU_CUDA_TRY(cudaMemsetAsync(c->d_status, 0, sizeof(DevStatus), c->stream));
         if (s.pad[0]) { set_error("a point's ring index is >= num_scan_lines (the reference indexes its per-ring state out of bounds here)"); return LIMU_ERR_INVALID; }
@@ -113,13 +119,14 @@ int limu_ctx_create(int device, limu_ctx **out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     LIMU_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    LIMU_CUDA_TRY(cudaMalloc(&c->d_status, sizeof(DevStatus)));
-    LIMU_CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(DevStatus)));
     LIMU_CUDA_TRY(cudaHostAlloc(&c->h_status, sizeof(DevStatus), cudaHostAllocDefault));
     c->h_pinned_bytes = 8192;
     LIMU_CUDA_TRY(cudaHostAlloc(&c->h_pinned, c->h_pinned_bytes, cudaHostAllocDefault));
     LIMU_TRY(c->d_small.reserve(8192));
     LIMU_CUDA_TRY(cudaMemset(c->d_small.p, 0, 8192));
+    // the device status word lives inside the small area, right behind the pipeline's per-scan result block ([32..52]), so one
+    // device-to-host copy per scan brings back counts, pose, loop statistics AND the status
+    c->d_status = reinterpret_cast<DevStatus *>(c->d_small.as<double>() + 53);
     *out = c;
     return LIMU_OK;
 }
@@ -134,7 +141,6 @@ void limu_ctx_destroy(limu_ctx *c) {
     limu::DevBuf *bufs[] = {&c->in0, &c->in1, &c->out0, &c->out1, &c->out2, &c->tmp0, &c->tmp1, &c->tmp2, &c->tmp3, &c->tmp4, &c->tmp5, &c->d_small};
     for (auto *b : bufs) b->release();
     for (int s = 0; s < LIMU_NUM_STAGES; ++s) for (int k = 0; k < 2; ++k) if (c->ev[s][k]) cudaEventDestroy(c->ev[s][k]);
-    cudaFree(c->d_status);
     cudaFreeHost(c->h_status);
     cudaFreeHost(c->h_pinned);
     cudaStreamDestroy(c->stream);

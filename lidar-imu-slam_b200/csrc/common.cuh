@@ -111,6 +111,7 @@ inline int bind(limu_ctx *c) {
     return LIMU_OK;
 }
 int check_status(limu_ctx *c);   // sync + read DevStatus; maps flags to limu_status and clears them
+int status_to_error(limu_ctx *c, const DevStatus &s);   // the same for a status word the caller already copied to the host
 // out <- T * in for n points (n read from *n_dev when given); pose7 is DEVICE memory.
 int transform_device(limu_ctx *c, const double *pose_dev, const double *in, double *out, int64_t n_max, const int *n_dev);
 // H2D helpers on the context's stream.

@@ -147,8 +147,14 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
 
     // the one synchronisation of the scan
     double *h = static_cast<double *>(c->h_pinned) + 32;
-    LIMU_CUDA_TRY(cudaMemcpyAsync(h, c->d_small.as<double>() + 32, (8 + 13) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    LIMU_TRY(check_status(c));
+    // counts [32..39], pose + loop statistics [40..52] and the status word [53..54] in ONE copy
+    LIMU_CUDA_TRY(cudaMemcpyAsync(h, c->d_small.as<double>() + 32, (8 + 13 + 2) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    {
+        DevStatus st;
+        memcpy(&st, h + 21, sizeof st);
+        LIMU_TRY(status_to_error(c, st));
+    }
     LIMU_TRY(prof_collect(c));
     const int *hc = reinterpret_cast<const int *>(h);
     const int64_t nd = hc[0], nk = hc[2];

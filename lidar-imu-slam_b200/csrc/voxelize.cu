@@ -33,7 +33,7 @@ struct VoxelizeArgs {
     int shift1, shift2;
     int *tile1, *tile2;
     int *counts;                // [0] n_down, [1] n_src0
-    unsigned int *barrier;
+    unsigned int *barrier;      // [0] grid barrier, [1] exit counter; zero at rest (the last CTA out re-arms them, no memset per launch)
     DevStatus *st;
 };
 
@@ -174,6 +174,12 @@ static __global__ void __launch_bounds__(VX_BLOCK, 4) k_voxelize(const VoxelizeA
         __syncthreads();
     }
     if (ntiles2 == 0 && gtid == 0) A.counts[1] = 0;
+    // every CTA has left the last barrier before it gets here, so the last one out can re-arm it for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(A.barrier + 1, 1u) == gridDim.x - 1) { A.barrier[0] = 0u; A.barrier[1] = 0u; __threadfence(); }
+    }
 }
 
 static int g_vx_blocks_per_sm = 0;
@@ -195,7 +201,11 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     const int ntiles = div_up(n, VX_BLOCK);
     LIMU_TRY(sc.table.reserve((size_t)(C1 + C2) * 12, c->stream));
     LIMU_TRY(sc.pslot.reserve((size_t)n * 8, c->stream));
-    LIMU_TRY(sc.tiles.reserve((size_t)ntiles * 8 + 64, c->stream));
+    {   // [16 ints: barrier words | tile counts]; a fresh allocation is zeroed once, afterwards the kernel keeps the barrier words at zero
+        const void *before = sc.tiles.p;
+        LIMU_TRY(sc.tiles.reserve((size_t)ntiles * 8 + 128, c->stream));
+        if (sc.tiles.p != before) LIMU_CUDA_TRY(cudaMemsetAsync(sc.tiles.p, 0, sc.tiles.bytes, c->stream));
+    }
     VoxelizeArgs A;
     A.raw = raw_dev; A.ts = ts_dev; A.mode = mode; A.stride = stride; A.deskew = deskew; A.n = n;
     for (int k = 0; k < 6; ++k) A.twist[k] = (deskew && twist_host) ? twist_host[k] : 0.0;
@@ -207,11 +217,10 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     A.min2 = A.min1 + C1;
     A.mask1 = (unsigned int)(C1 - 1); A.mask2 = (unsigned int)(C2 - 1); A.shift1 = A.shift2 = 64 - lg;
     A.pslot1 = sc.pslot.as<unsigned int>(); A.pslot2 = A.pslot1 + n;
-    A.tile1 = sc.tiles.as<int>(); A.tile2 = A.tile1 + ntiles;
+    A.barrier = sc.tiles.as<unsigned int>();
+    A.tile1 = sc.tiles.as<int>() + 16; A.tile2 = A.tile1 + ntiles;
     A.counts = counts_dev;
-    A.barrier = reinterpret_cast<unsigned int *>(A.tile2 + ntiles);
     A.st = c->d_status;
-    LIMU_CUDA_TRY(cudaMemsetAsync(A.barrier, 0, sizeof(unsigned int), c->stream));
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->sm_count * g_vx_blocks_per_sm);
     void *args[] = {&A};
     LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize, dim3(grid), dim3(VX_BLOCK), args, 0, c->stream));
