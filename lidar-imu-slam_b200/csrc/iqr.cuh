@@ -21,25 +21,10 @@ __device__ __forceinline__ void iqr_block(IqrSmem &sm, const double *__restrict_
                                           int *out_count, double *bounds) {
     const int tid = threadIdx.x;
     if (n <= 0) { if (tid == 0) *out_count = 0; return; }
-    // Keypoint clouds are a few thousand points: up to 4096 squared ranges stay in registers (REG per thread), so the eight
-    // select passes and the filter never go back to memory for them (each dependent L2 round trip costs as much as a pass).
-    constexpr int REG = 4096 / BLOCK;
-    const bool in_regs = n <= 4096;
-    double v[REG];
-#pragma unroll
-    for (int k = 0; k < REG; ++k) {
-        const int i = tid + k * BLOCK;
-        v[k] = 0.0;
-        if (in_regs && i < n) {
-            const double x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
-            v[k] = x * x + y * y + z * z;   // icp.cpp:97-100
-        }
+    for (int i = tid; i < n; i += BLOCK) {
+        const double x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+        d2[i] = x * x + y * y + z * z;   // icp.cpp:97-100
     }
-    if (!in_regs || n == 1)
-        for (int i = tid; i < n; i += BLOCK) {
-            const double x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
-            d2[i] = x * x + y * y + z * z;   // icp.cpp:97-100
-        }
     double q1, q3, iqr;
     const int half = n / 2, m = half, u0 = half + n % 2;
     if (n == 1) {
@@ -55,28 +40,6 @@ __device__ __forceinline__ void iqr_block(IqrSmem &sm, const double *__restrict_
             const int shift = 56 - 8 * pass;
             for (int b = tid; b < 4 * 256; b += BLOCK) (&sm.hist[0][0])[b] = 0;
             __syncthreads();
-            if (in_regs) {
-                // Squared ranges of one scan share their leading bytes, so in the first passes (nearly) every element lands in the same
-                // bin: the adds are aggregated per warp (one match on the digit, one ballot per order statistic, the lowest lane of each
-                // group adds the group's size) instead of thousands of same-address shared atomics.
-                const unsigned lane_lt = (1u << (tid & 31)) - 1u;
-#pragma unroll
-                for (int k = 0; k < REG; ++k) {
-                    if (k * BLOCK < n) {   // uniform across the CTA
-                        const bool valid = tid + k * BLOCK < n;
-                        const unsigned long long bits = (unsigned long long)__double_as_longlong(v[k]);
-                        const unsigned long long hi_bits = pass == 0 ? 0ull : (bits >> (shift + 8));
-                        const int digit = valid ? (int)((bits >> shift) & 0xFF) : 256 + (tid & 31);
-                        const unsigned peers = __match_any_sync(0xFFFFFFFFu, digit);
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const bool hit = valid && hi_bits == sm.prefix[t];
-                            const unsigned grp = __ballot_sync(0xFFFFFFFFu, hit) & peers;
-                            if (hit && (grp & lane_lt) == 0u) atomicAdd(&sm.hist[t][digit], __popc(grp));
-                        }
-                    }
-                }
-            } else
             for (int i = tid; i < n; i += BLOCK) {
                 const unsigned long long bits = (unsigned long long)__double_as_longlong(d2[i]);
                 const unsigned long long hi_bits = pass == 0 ? 0ull : (bits >> (shift + 8));
@@ -116,25 +79,6 @@ __device__ __forceinline__ void iqr_block(IqrSmem &sm, const double *__restrict_
     const double low = q1 - 1.25 * iqr, high = q3 + 1.25 * iqr;   // icp.cpp:104-105
     if (tid == 0 && bounds) { bounds[0] = low; bounds[1] = high; }
     int base = 0;
-    if (in_regs && n > 1) {
-#pragma unroll
-        for (int k = 0; k < REG; ++k) {
-            if (k * BLOCK < n) {   // uniform across the CTA
-                const int i = tid + k * BLOCK;
-                const int f = i < n && v[k] >= low && v[k] <= high;   // icp.cpp:117
-                const int r = block_exclusive_scan_flag(f, &sm.total, sm.ws);
-                if (f) {
-                    out[3 * (size_t)(base + r)] = xyz[3 * (size_t)i];
-                    out[3 * (size_t)(base + r) + 1] = xyz[3 * (size_t)i + 1];
-                    out[3 * (size_t)(base + r) + 2] = xyz[3 * (size_t)i + 2];
-                }
-                base += sm.total;
-                __syncthreads();
-            }
-        }
-        if (tid == 0) *out_count = base;
-        return;
-    }
     for (int start = 0; start < n; start += BLOCK) {
         const int i = start + tid;
         const double d = i < n ? d2[i] : 0.0;

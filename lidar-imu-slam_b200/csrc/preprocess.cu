@@ -15,7 +15,7 @@
 //                     scan with a carried state reproduces it exactly
 //   compact           order-preserving compaction of the survivors (compact.cuh)
 //   k_rs_*            stable LSD radix sort (4 x 8 bit) of (curvature key, source index)
-//   k_pre_split       segment table of split_clouds (cut positions, accumulated segment time, per-segment timestamp maximum)
+//   k_pre_split       segment table of split_clouds (cut positions, accumulated segment time); k_pre_segmax: per-segment timestamp maximum
 //   k_pre_emit        writes the processed records and timestamps
 //
 // std::sort in sort_clouds is unstable: among EQUAL curvature keys the reference's order is whatever libstdc++'s introsort
@@ -193,43 +193,40 @@ static __global__ void __launch_bounds__(RS_BLOCK) k_rs_hist(const unsigned int 
     __syncthreads();
     if (threadIdx.x < 256) hist[threadIdx.x * B + blockIdx.x] = sh[threadIdx.x];
 }
-// exclusive scan of `total` ints in place by one CTA
-static __global__ void __launch_bounds__(1024) k_rs_scan(int *__restrict__ a, int total) {
-    __shared__ int ws[32];
+// hist is digit-major [256][B]. One CTA per digit row: exclusive scan of the row in place, row total -> totals[digit].
+// (A single-CTA scan of all 256*B counters cost 32 us per pass at 128k points; the rows are independent.)
+static __global__ void __launch_bounds__(256) k_rs_rowscan(int *__restrict__ hist, int B, int *__restrict__ totals) {
+    __shared__ int ws[8];
     __shared__ int carry;
+    int *row = hist + (size_t)blockIdx.x * B;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < total; base += 1024 * 4) {
-        int v[4], s = 0;
-        const int at = base + threadIdx.x * 4;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { v[k] = at + k < total ? a[at + k] : 0; s += v[k]; }
-        int incl = s;
+    for (int base = 0; base < B; base += 256) {
+        const int at = base + threadIdx.x;
+        const int v = at < B ? row[at] : 0;
+        int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
         if (lane == 31) ws[warp] = incl;
         __syncthreads();
-        if (warp == 0) {
-            const int w = ws[lane];
-            int wi = w;
+        int wbase = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += t; }
-            ws[lane] = wi - w;
-        }
+        for (int w = 0; w < 8; ++w) wbase += w < warp ? ws[w] : 0;
+        const int c = carry;
+        if (at < B) row[at] = c + wbase + incl - v;
         __syncthreads();
-        int run = carry + ws[warp] + (incl - s);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { if (at + k < total) a[at + k] = run; run += v[k]; }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = run;
+        if (threadIdx.x == 255) carry = c + wbase + incl;
         __syncthreads();
     }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 static __global__ void __launch_bounds__(RS_BLOCK) k_rs_scatter(const unsigned int *__restrict__ keys, const unsigned int *__restrict__ vals, const int *m_dev,
-                                                               int shift, const int *__restrict__ hist, int B, unsigned int *__restrict__ keys_out,
-                                                               unsigned int *__restrict__ vals_out) {
+                                                               int shift, const int *__restrict__ hist, const int *__restrict__ totals, int B,
+                                                               unsigned int *__restrict__ keys_out, unsigned int *__restrict__ vals_out) {
     __shared__ int cnt[RS_BLOCK / 32][256];
+    __shared__ int dbase[256];   // exclusive scan of the 256 digit totals: where each digit's range starts in the output
+    __shared__ int dws[8];
     const int m = *m_dev;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int k = threadIdx.x; k < (RS_BLOCK / 32) * 256; k += RS_BLOCK) (&cnt[0][0])[k] = 0;
@@ -242,8 +239,19 @@ static __global__ void __launch_bounds__(RS_BLOCK) k_rs_scatter(const unsigned i
     const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
     if (on && rank_in_warp == 0) cnt[warp][digit] = __popc(peers);
     __syncthreads();
+    if (threadIdx.x < 256) {   // warps 0..7 scan the digit totals
+        const int v = totals[threadIdx.x];
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) dws[warp] = incl;
+        dbase[threadIdx.x] = incl - v;
+    }
+    __syncthreads();
     if (threadIdx.x < 256) {
-        int run = hist[threadIdx.x * B + blockIdx.x];
+        int run = dbase[threadIdx.x] + hist[threadIdx.x * B + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) run += w < warp ? dws[w] : 0;
 #pragma unroll
         for (int w = 0; w < RS_BLOCK / 32; ++w) { const int c = cnt[w][threadIdx.x]; cnt[w][threadIdx.x] = run; run += c; }
     }
@@ -264,46 +272,67 @@ __device__ __forceinline__ double pre_normalised_ts(const double *ext, unsigned 
     const double v = ext[i];
     return global_norm ? v / gmax : v;
 }
-static __global__ void __launch_bounds__(1024) k_pre_split(const PreArgs A, const int *m_dev, const unsigned int *__restrict__ vals, SegTable *T) {
-    __shared__ double red[32];
+// order-preserving map double -> u64 (for atomicMax over possibly negative timestamps) and back
+__device__ __forceinline__ unsigned long long f64_ordered(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double f64_unordered(unsigned long long k) {
+    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k));
+}
+static __global__ void k_pre_split(const PreArgs A, const int *m_dev, const unsigned int *__restrict__ vals, SegTable *T, unsigned long long *tmax_keys) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int m = *m_dev;
+    const double message_time_ms = A.message_time * 1000;
+    double last_end = message_time_ms;
+    int nseg = 0, prev = 0;
+    const unsigned long long M = (unsigned long long)(m > 0 ? m : 0), cuts = (unsigned long long)A.cuts;
+    for (int cut = 0; cut < PRE_MAX_SEG && m > 1; ++cut) {
+        const int thr = (int)(((unsigned long long)(cut + 1) * M / cuts) - 1ull);
+        if (thr <= prev || thr > m - 1) break;
+        const double adj = message_time_ms - last_end;
+        T->begin[nseg] = prev; T->end[nseg] = thr; T->adj[nseg] = adj; T->time[nseg] = last_end / (double)1000;
+        tmax_keys[nseg] = 0ull;                                          // below every ordered key
+        const float c_end = (float)((double)A.curv[vals[thr]] + adj);   // :74 on the cut point
+        last_end += (double)c_end;                                    // :92
+        prev = thr;
+        ++nseg;
+    }
+    T->nseg = nseg; T->m = m;
+}
+// per-segment timestamp maximum (normalize_timestamps :87): grid-stride over the sorted positions, warp-reduced per segment
+static __global__ void __launch_bounds__(256) k_pre_segmax(const PreArgs A, const unsigned int *__restrict__ vals, const SegTable *T, unsigned long long *tmax_keys) {
+    __shared__ int s_end[PRE_MAX_SEG];
+    const int nseg = T->nseg;
+    for (int k = threadIdx.x; k < nseg; k += blockDim.x) s_end[k] = T->end[k];
+    __syncthreads();
+    if (nseg == 0) return;
+    const int last = s_end[nseg - 1];
     const double gmax = __longlong_as_double((long long)*A.gmax);
     const bool global_norm = !A.f.time_field_is_f64 && !(gmax < 1.0);
-    if (threadIdx.x == 0) {
-        const double message_time_ms = A.message_time * 1000;
-        double last_end = message_time_ms;
-        int nseg = 0, prev = 0;
-        const unsigned long long M = (unsigned long long)(m > 0 ? m : 0), cuts = (unsigned long long)A.cuts;
-        for (int cut = 0; cut < PRE_MAX_SEG && m > 1; ++cut) {
-            const int thr = (int)(((unsigned long long)(cut + 1) * M / cuts) - 1ull);
-            if (thr <= prev || thr > m - 1) break;
-            const double adj = message_time_ms - last_end;
-            T->begin[nseg] = prev; T->end[nseg] = thr; T->adj[nseg] = adj; T->time[nseg] = last_end / (double)1000;
-            const float c_end = (float)((double)A.curv[vals[thr]] + adj);   // :74 on the cut point
-            last_end += (double)c_end;                                    // :92
-            prev = thr;
-            ++nseg;
+    for (int p0 = 1 + blockIdx.x * blockDim.x; p0 <= last; p0 += gridDim.x * blockDim.x) {   // whole warps iterate together
+        const int p = p0 + threadIdx.x;
+        int k = -1;
+        unsigned long long key = 0ull;
+        if (p <= last) {
+            k = 0;
+            while (p > s_end[k]) ++k;
+            key = f64_ordered(pre_normalised_ts(A.ext, vals[p], global_norm, gmax));
         }
-        T->nseg = nseg; T->m = m;
-    }
-    __syncthreads();
-    const int nseg = T->nseg;
-    for (int k = 0; k < nseg; ++k) {
-        const int b = T->begin[k] + 1, e = T->end[k];
-        double mx = pre_normalised_ts(A.ext, vals[b], global_norm, gmax);
-        for (int p = b + (int)threadIdx.x; p <= e; p += 1024) { const double v = pre_normalised_ts(A.ext, vals[p], global_norm, gmax); mx = v > mx ? v : mx; }
+        // lanes of a warp almost always share the segment: reduce within the warp when they do
+        const int k0 = __shfl_sync(0xFFFFFFFFu, k, 0);
+        if (__all_sync(0xFFFFFFFFu, k == k0)) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xFFFFFFFFu, mx, o); mx = t > mx ? t : mx; }
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            double v = red[threadIdx.x];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xFFFFFFFFu, v, o); v = t > v ? t : v; }
-            if (threadIdx.x == 0) T->tmax[k] = v;
+            for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xFFFFFFFFu, key, o); key = t > key ? t : key; }
+            if ((threadIdx.x & 31) == 0 && k >= 0) atomicMax(tmax_keys + k, key);
+        } else if (k >= 0) {
+            atomicMax(tmax_keys + k, key);
         }
-        __syncthreads();
     }
+}
+static __global__ void k_pre_segmax_store(SegTable *T, const unsigned long long *tmax_keys) {
+    const int k = threadIdx.x;
+    if (k < T->nseg) T->tmax[k] = f64_unordered(tmax_keys[k]);
 }
 
 // Output rows: pcl::PointXYZINormal (48 B): {x, y, z, 1}, {normal 0,0,0, 0}, {intensity, curvature, 0, 0}; + FP64 timestamp.
@@ -352,13 +381,15 @@ int preprocess_device(limu_ctx *c, PreScratch &sc, const unsigned char *data_dev
     LIMU_TRY(sc.sidx.reserve(N * 4 + 16, c->stream));
     for (int k = 0; k < 2; ++k) { LIMU_TRY(sc.keys[k].reserve(N * 4, c->stream)); LIMU_TRY(sc.vals[k].reserve(N * 4, c->stream)); }
     const int B = div_up(n, RS_BLOCK);
-    LIMU_TRY(sc.hist.reserve((size_t)B * 256 * 4, c->stream));
-    LIMU_TRY(sc.small.reserve(256 + sizeof(SegTable), c->stream));
+    LIMU_TRY(sc.hist.reserve((size_t)B * 256 * 4 + 256 * 4, c->stream));   // [256][B] block counts + 256 digit totals
+    LIMU_TRY(sc.small.reserve(256 + sizeof(SegTable) + PRE_MAX_SEG * 8, c->stream));
     LIMU_TRY(sc.rec.reserve(N * 48, c->stream));
     LIMU_TRY(sc.ts.reserve(N * 8, c->stream));
     unsigned long long *gmax = sc.small.as<unsigned long long>();
     int *m_dev = reinterpret_cast<int *>(gmax + 1);
     SegTable *seg_dev = reinterpret_cast<SegTable *>(sc.small.as<unsigned char>() + 256);
+    unsigned long long *tmax_keys = reinterpret_cast<unsigned long long *>(sc.small.as<unsigned char>() + 256 + sizeof(SegTable));
+    int *totals = sc.hist.as<int>() + (size_t)B * 256;
     LIMU_CUDA_TRY(cudaMemsetAsync(sc.small.p, 0, 256, c->stream));
 
     PreArgs A;
@@ -383,16 +414,20 @@ int preprocess_device(limu_ctx *c, PreScratch &sc, const unsigned char *data_dev
         const int shift = 8 * pass;
         k_rs_hist<<<B, RS_BLOCK, 0, c->stream>>>(sc.keys[cur].as<unsigned int>(), m_dev, shift, sc.hist.as<int>(), B);
         LIMU_LAUNCHED();
-        k_rs_scan<<<1, 1024, 0, c->stream>>>(sc.hist.as<int>(), 256 * B);
+        k_rs_rowscan<<<256, 256, 0, c->stream>>>(sc.hist.as<int>(), B, totals);
         LIMU_LAUNCHED();
-        k_rs_scatter<<<B, RS_BLOCK, 0, c->stream>>>(sc.keys[cur].as<unsigned int>(), sc.vals[cur].as<unsigned int>(), m_dev, shift, sc.hist.as<int>(), B,
+        k_rs_scatter<<<B, RS_BLOCK, 0, c->stream>>>(sc.keys[cur].as<unsigned int>(), sc.vals[cur].as<unsigned int>(), m_dev, shift, sc.hist.as<int>(), totals, B,
                                                     sc.keys[cur ^ 1].as<unsigned int>(), sc.vals[cur ^ 1].as<unsigned int>());
         LIMU_LAUNCHED();
         cur ^= 1;
     }
-    k_pre_split<<<1, 1024, 0, c->stream>>>(A, m_dev, sc.vals[cur].as<unsigned int>(), seg_dev);
+    k_pre_split<<<1, 32, 0, c->stream>>>(A, m_dev, sc.vals[cur].as<unsigned int>(), seg_dev, tmax_keys);
     LIMU_LAUNCHED();
     const int eb = (int)std::min<int64_t>(div_up(n, 256), (int64_t)c->sm_count * 8);
+    k_pre_segmax<<<eb, 256, 0, c->stream>>>(A, sc.vals[cur].as<unsigned int>(), seg_dev, tmax_keys);
+    LIMU_LAUNCHED();
+    k_pre_segmax_store<<<1, PRE_MAX_SEG, 0, c->stream>>>(seg_dev, tmax_keys);
+    LIMU_LAUNCHED();
     k_pre_emit<<<eb, 256, 0, c->stream>>>(A, sc.vals[cur].as<unsigned int>(), seg_dev, sc.rec.as<float4>(), sc.ts.as<double>());
     LIMU_LAUNCHED();
     LIMU_CUDA_TRY(cudaMemcpyAsync(sc.h_seg, seg_dev, sizeof(SegTable), cudaMemcpyDeviceToHost, c->stream));
