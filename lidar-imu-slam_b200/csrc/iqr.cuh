@@ -95,4 +95,69 @@ __device__ __forceinline__ void iqr_block(IqrSmem &sm, const double *__restrict_
     if (tid == 0) *out_count = base;
 }
 
+// ---- the same filter spread over the whole cooperative grid (used by the fused frame kernel in its latency shape) ----
+// The one-CTA radix select above costs ~25 us per scan for ~2.3 k keypoints (eight dependent passes). Here EVERY CTA copies the squared
+// ranges into its shared memory and its warps rank their share of the elements by counting (#smaller, ties by index -> unique ranks);
+// the <= 4 elements whose rank is one of the wanted order statistics publish their value. After one grid barrier CTA 0 derives the
+// Tukey bounds and compacts the inliers from its shared copy. Same values as the select above (an order statistic is an order
+// statistic), so the filtered cloud is bit-identical.
+constexpr int IQR_GRID_MAX = 4096;
+
+template <int BLOCK>
+__device__ __forceinline__ void iqr_grid_select(double *sd2 /* shared, IQR_GRID_MAX */, const double *__restrict__ xyz, int n, double *sel /* global, 4 */) {
+    for (int i = threadIdx.x; i < n; i += BLOCK) {
+        const double x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+        sd2[i] = x * x + y * y + z * z;   // icp.cpp:97-100
+    }
+    __syncthreads();
+    const int half = n / 2, m = half, u0 = half + n % 2;
+    const int lo = (m % 2 == 0) ? m / 2 - 1 : m / 2, hi = m / 2;   // median(): common.hpp:22-38
+    const int r0 = lo, r1 = hi, r2 = lo + u0, r3 = hi + u0;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5), nwarps = gridDim.x * (BLOCK / 32);
+    for (int i = gwarp; i < n; i += nwarps) {   // warp-uniform trip count
+        const double d = sd2[i];
+        int c = 0;
+        for (int j = lane; j < n; j += 32) {
+            const double e = sd2[j];
+            c += (e < d || (e == d && j < i)) ? 1 : 0;
+        }
+        c = __reduce_add_sync(0xFFFFFFFFu, c);
+        if (lane == 0) {
+            if (c == r0) sel[0] = d;
+            if (c == r1) sel[1] = d;
+            if (c == r2) sel[2] = d;
+            if (c == r3) sel[3] = d;
+        }
+    }
+}
+
+template <int BLOCK>
+__device__ __forceinline__ void iqr_grid_filter(IqrSmem &sm, const double *sd2, const double *__restrict__ xyz, int n, const double *sel,
+                                                double *__restrict__ out, int *out_count, double *bounds) {
+    const int tid = threadIdx.x;
+    const int m = n / 2;
+    const double v0 = __ldcg(sel), v1 = __ldcg(sel + 1), v2 = __ldcg(sel + 2), v3 = __ldcg(sel + 3);
+    const double q1 = (m % 2 == 0) ? (v0 + v1) / 2.0 : v1;
+    const double q3 = (m % 2 == 0) ? (v2 + v3) / 2.0 : v3;
+    const double iqr = q3 - q1;
+    const double low = q1 - 1.25 * iqr, high = q3 + 1.25 * iqr;   // icp.cpp:104-105
+    if (tid == 0 && bounds) { bounds[0] = low; bounds[1] = high; }
+    int base = 0;
+    for (int start = 0; start < n; start += BLOCK) {
+        const int i = start + tid;
+        const double d = i < n ? sd2[i] : 0.0;
+        const int f = i < n && d >= low && d <= high;   // icp.cpp:117
+        const int r = block_exclusive_scan_flag(f, &sm.total, sm.ws);
+        if (f) {
+            out[3 * (size_t)(base + r)] = xyz[3 * (size_t)i];
+            out[3 * (size_t)(base + r) + 1] = xyz[3 * (size_t)i + 1];
+            out[3 * (size_t)(base + r) + 2] = xyz[3 * (size_t)i + 2];
+        }
+        base += sm.total;
+        __syncthreads();
+    }
+    if (tid == 0) *out_count = base;
+}
+
 }  // namespace limu
