@@ -35,6 +35,20 @@ def test_every_declared_symbol_is_exported(pkg):
     assert lib.limu_abi_version() == 1
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/limu_cuda.h must compile as strict C99 and as C++11, with nothing but <stddef.h>/<stdint.h>."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "limu_cuda.h"\nint main(void) { limu_odom_config c; limu_lidar_config l; limu_cloud_fields f; limu_imu_pose p;'
+                   ' limu_frame_stats s; (void)c; (void)l; (void)f; (void)p; (void)s; return LIMU_ABI_VERSION == 1 ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, "-c", str(src), "-o", str(tmp_path / "a.o")])
+    subprocess.check_call(["g++", "-std=c++11", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, "-x", "c++", "-c", str(src), "-o", str(tmp_path / "b.o")])
+    hdr = open(os.path.join(inc, "limu_cuda.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)   # comments may mention torch pointers; declarations may not
+    assert set(re.findall(r"#include\s*<([^>]+)>", code)) == {"stddef.h", "stdint.h"} and "torch" not in code and "std::" not in code
+
+
 def test_binding_covers_the_header(pkg):
     bound = set(re.findall(r"\blimu_[a-z0-9_]+", open(os.path.join(os.path.dirname(pkg.LIB_PATH), "__init__.py")).read()))
     skip = {"limu_last_error", "limu_abi_version"}
