@@ -73,3 +73,40 @@ def test_no_device_means_error_not_fallback(pkg):
         pkg.Context(0)
     assert "no CPU fallback" in str(e.value)
     assert pkg.device_count() == 0
+
+
+def test_product_never_imports_links_or_loads_the_oracle(pkg):
+    """oracle/ is test infrastructure: nothing under lidar-imu-slam_b200/ or include/ may import, include, link or dlopen it
+    (comments may mention it), and the shared library must not depend on any oracle binary."""
+    import subprocess
+    pkg_dir = os.path.dirname(pkg.LIB_PATH)
+    offenders = []
+    for base in (pkg_dir, os.path.join(ROOT, "include")):
+        for dirpath, _, files in os.walk(base):
+            if os.sep + "build" in dirpath or "__pycache__" in dirpath:
+                continue
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", "Makefile")):
+                    continue
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                code = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+                code = "\n".join(line.split("//")[0] for line in code.splitlines())
+                if f.endswith(".py"):
+                    code = "\n".join(line.split("#")[0] for line in re.sub(r'"""(.*?)"""', "", code, flags=re.S).splitlines())
+                if re.search(r"import\s+oracle|from\s+oracle|oracle/|limu_oracle|liblimu_ref|lo_[a-z_]+\(|ref_[a-z_]+\(", code):
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
+    needed = subprocess.run(["readelf", "-d", pkg.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in needed and "limu_ref" not in needed
+
+
+def test_config_defaults_are_the_reference_launch_defaults(pkg):
+    """limu_odom_default_config / limu_lidar_default_config are host code: they must carry frame::Lidar's parameter defaults
+    (lidar/frame.hpp:64-80)."""
+    import ctypes as C
+    cfg = pkg.OdomConfig()
+    pkg.lib().limu_odom_default_config(C.byref(cfg))
+    assert (cfg.voxel_size, cfg.max_range, cfg.max_points_per_voxel, cfg.deskew, cfg.min_motion_th, cfg.icp_max_iteration, cfg.icp_mode,
+            cfg.initial_threshold, cfg.estimation_threshold) == (1.0, 100.0, 10, 0, 0.1, 500, 0, 2.0, 1e-4)
+    lc = pkg.lidar_config()
+    assert (lc.min_range, lc.max_range, lc.min_angle, lc.max_angle, lc.frame_rate, lc.num_scan_lines, lc.frame_split_num) == (5.0, 100.0, 0.0, 360.0, 10.0, 16, 1)
