@@ -284,6 +284,8 @@ def main():
     e0.record(ext)
     t0 = time.perf_counter()
     for i in range(W, W + K):
+        if i + 1 < len(dev_scans):
+            odom.hint_next_dev(dev_scans[i + 1].data_ptr(), n_pts)   # replay hint; a no-op unless the library was built with LIMU_SPECULATIVE_VOXELIZE
         odom.register_frame_dev(dev_scans[i].data_ptr(), n_pts)
         st = odom.stats
         frames.append((st.n_keypoints, st.icp.iterations, st.icp.mean_candidates, st.icp.miss_fraction, st.n_down))

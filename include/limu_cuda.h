@@ -210,6 +210,11 @@ int limu_odom_prefetch(limu_odom *o, const float *xyzt, int64_t n);
 int limu_odom_register_cloud(limu_odom *o, const void *points, int32_t stride_bytes, const double *timestamps, int64_t n, double pose_out[7],
                              double *down_xyz, int64_t *n_down, double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats);
 int limu_odom_register_frame_dev(limu_odom *o, const float *xyzt_dev, int64_t n, double pose_out[7], limu_frame_stats *stats);
+/* Replay hint: the scan that will be registered AFTER the next limu_odom_register_frame_dev call already sits in device memory at
+ * xyzt_dev_next. A library built with LIMU_SPECULATIVE_VOXELIZE then enqueues that scan's deskew + downsampling launch right behind the
+ * current scan's registration (the deskew twist stays on the device), so the host round trip between two scans overlaps GPU work; other
+ * builds ignore the hint. Results do not depend on hints; a hint that is not followed by that scan is simply discarded. */
+int limu_odom_hint_next_dev(limu_odom *o, const float *xyzt_dev_next, int64_t n_next);
 /* register_frame(Vec3dVector) icp.cpp:58-86 (no deskew). */
 int limu_odom_register_points(limu_odom *o, const double *xyz, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down,
                               double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats);

@@ -148,6 +148,7 @@ def lib():
             "limu_odom_register_frame": [_vp, _fp, C.c_int64, _dp, _dp, _lp, _dp, _lp, C.POINTER(FrameStats)],
             "limu_odom_register_frame_dev": [_vp, _vp, C.c_int64, _dp, C.POINTER(FrameStats)],
             "limu_odom_prefetch": [_vp, _fp, C.c_int64],
+            "limu_odom_hint_next_dev": [_vp, _vp, C.c_int64],
             "limu_odom_register_points": [_vp, _dp, C.c_int64, _dp, _dp, _lp, _dp, _lp, C.POINTER(FrameStats)],
             "limu_odom_num_poses": [_vp, _lp], "limu_odom_pose": [_vp, C.c_int64, _dp],
             "limu_odom_adaptive_threshold": [_vp, _dp], "limu_odom_prediction": [_vp, _dp], "limu_odom_has_moved": [_vp, C.POINTER(C.c_int)],
@@ -616,6 +617,10 @@ class KissICP:
         pose = np.empty(7)
         _chk(lib().limu_odom_register_frame_dev(self.h, _vp(xyzt_dev_ptr), int(n), _d(pose), C.byref(self.stats)))
         return pose
+
+    def hint_next_dev(self, xyzt_dev_ptr, n):
+        """Replay hint: the scan after the next register_frame_dev call already sits at this device address (see limu_cuda.h)."""
+        _chk(lib().limu_odom_hint_next_dev(self.h, _vp(xyzt_dev_ptr), int(n)))
 
     def register_points(self, xyz):
         """register_frame(Vec3dVector)."""

@@ -68,6 +68,20 @@ struct limu_odom {
     const void *pf_host[2] = {nullptr, nullptr};
     int64_t pf_n[2] = {-1, -1};
     int pf_next = 0;
+#ifdef LIMU_SPECULATIVE_VOXELIZE
+    // Replay speed-up (limu_odom_hint_next_dev): the NEXT scan's deskew + downsampling launch is enqueued right behind this scan's
+    // frame kernel, with its twist left on the device by that kernel, so the host round trip of this scan (result copy, wake-up,
+    // scalar glue, launch) overlaps it instead of idling the GPU.
+    const void *hint_ptr = nullptr;         // next scan (device float4 rows), set by the caller before registering the current one
+    int64_t hint_n = 0;
+    const void *spec_ptr = nullptr;         // scan whose k_voxelize is already in flight / done
+    int64_t spec_n = 0;
+    int spec_deskewed = 0;
+    limu::DevBuf twist_next;                // 6 doubles written by the frame kernel
+    cudaEvent_t frame_done = nullptr;       // recorded after the result copy of the current scan
+    cudaEvent_t spec_ev[2] = {nullptr, nullptr};   // device time of the speculative launch, folded into LIMU_STAGE_DOWNSAMPLE one call later
+    bool spec_timed = false;
+#endif
 };
 
 using namespace limu;
@@ -101,15 +115,25 @@ static Pose odom_prediction(const limu_odom *o) {   // icp.cpp:146-154
 static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int stride, const double *ts_dev, int64_t n, double pose_out[7], double *down_xyz,
                                 int64_t *n_down, double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
     limu_ctx *c = o->ctx;
-    const size_t nb = (size_t)std::max<int64_t>(n, 1) * 24;
-    LIMU_TRY(o->frame.reserve(nb, c->stream));
     // deskew gate (icp.cpp:40-46): config.deskew && poses.size() > 2; twist = delta_pose(poses[N-2], poses[N-1]) (deskew.cpp:14)
     const size_t NP = o->poses.size();
     const int deskewed = (mode != 2 && o->cfg.deskew && NP > 2) ? 1 : 0;
     double twist[6] = {0, 0, 0, 0, 0, 0};
     if (deskewed) se3_log(mul(inverse(o->poses[NP - 2]), o->poses[NP - 1]), twist);
-    LIMU_TRY(o->down.reserve(nb, c->stream));
-    LIMU_TRY(o->src0.reserve(nb, c->stream));
+#ifdef LIMU_SPECULATIVE_VOXELIZE
+    // was this scan's k_voxelize already enqueued behind the previous scan (limu_odom_hint_next_dev)? Its outputs live in frame/down/src0:
+    // growing those buffers for a larger hinted scan must then keep their contents.
+    const bool spec_hit = mode == 0 && n > 0 && raw_dev == o->spec_ptr && n == o->spec_n && o->spec_deskewed == deskewed;
+    o->spec_ptr = nullptr;
+    const size_t nb = (size_t)std::max<int64_t>(std::max<int64_t>(n, o->hint_ptr ? o->hint_n : 0), 1) * 24;
+    const bool keep = spec_hit;
+#else
+    const size_t nb = (size_t)std::max<int64_t>(n, 1) * 24;
+    const bool keep = false;
+#endif
+    LIMU_TRY(o->frame.reserve(nb, c->stream, keep));
+    LIMU_TRY(o->down.reserve(nb, c->stream, keep));
+    LIMU_TRY(o->src0.reserve(nb, c->stream, keep));
     LIMU_TRY(o->src.reserve(nb, c->stream));
     LIMU_TRY(o->work.reserve(nb, c->stream));
     LIMU_TRY(o->world.reserve(nb, c->stream));
@@ -120,9 +144,14 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     const double v = o->cfg.voxel_size;
 
     // deskew_scan + voxelize's two downsampling stages (icp.cpp:36-47, :126-131): one cooperative launch
-    LIMU_TRY(prof_begin(c, LIMU_STAGE_DOWNSAMPLE));
-    LIMU_TRY(voxelize_device(c, o->vx, raw_dev, mode, stride, ts_dev, deskewed, twist, n, v, o->frame.as<double>(), o->down.as<double>(), o->src0.as<double>(), cnt + 0));
-    LIMU_TRY(prof_end(c, LIMU_STAGE_DOWNSAMPLE));
+#ifdef LIMU_SPECULATIVE_VOXELIZE
+    if (!spec_hit)
+#endif
+    {
+        LIMU_TRY(prof_begin(c, LIMU_STAGE_DOWNSAMPLE));
+        LIMU_TRY(voxelize_device(c, o->vx, raw_dev, mode, stride, ts_dev, deskewed, twist, n, v, o->frame.as<double>(), o->down.as<double>(), o->src0.as<double>(), cnt + 0));
+        LIMU_TRY(prof_end(c, LIMU_STAGE_DOWNSAMPLE));
+    }
     // host scalar glue (icp.cpp:66-71)
     const double sigma = odom_adaptive_threshold(o);
     const Pose pred = odom_prediction(o);
@@ -140,6 +169,17 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     fuse.iqr_in = o->src0.as<double>(); fuse.iqr_n = cnt + 1; fuse.iqr_d2 = o->d2.as<double>(); fuse.iqr_out = o->src.as<double>(); fuse.iqr_count = cnt + 2;
     fuse.upd_down = o->down.as<double>(); fuse.upd_n = cnt + 0; fuse.upd_world = o->world.as<double>(); fuse.upd_pslot = o->map->pslot.as<unsigned int>();
     fuse.upd_birth_base = o->map->birth_base;
+#ifdef LIMU_SPECULATIVE_VOXELIZE
+    // speculate only when nothing of this scan's clouds has to travel to the host after the synchronisation (their buffers are reused)
+    const bool speculate = o->hint_ptr && o->hint_n > 0 && mode == 0 && !down_xyz && !keypoints_xyz;
+    const int next_deskew = (o->cfg.deskew && NP + 1 > 2) ? 1 : 0;   // the gate of icp.cpp:40-46 as the next scan will see it
+    fuse.twist_out = nullptr;
+    if (speculate && next_deskew) {
+        LIMU_TRY(o->twist_next.reserve(6 * sizeof(double), c->stream));
+        fuse.twist_out = o->twist_next.as<double>();
+        pose_store(last, fuse.last_pose);
+    }
+#endif
     const int64_t upper_before = o->map->used_upper;
     LIMU_TRY(icp_device(o->map, o->src.as<double>(), o->work.as<double>(), n, cnt + 2, init7, 3.0 * sigma, sigma / 3.0, o->cfg.icp_max_iteration,
                         o->cfg.estimation_threshold, o->partials.as<double>(), (size_t)rows, out13, o->nk_hint, nullptr, nullptr, nullptr, -1, &fuse, o->cfg.icp_mode));
@@ -149,6 +189,29 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     double *h = static_cast<double *>(c->h_pinned) + 32;
     // counts [32..39], pose + loop statistics [40..52] and the status word [53..54] in ONE copy
     LIMU_CUDA_TRY(cudaMemcpyAsync(h, c->d_small.as<double>() + 32, (8 + 13 + 2) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+#ifdef LIMU_SPECULATIVE_VOXELIZE
+    if (o->spec_timed) {   // the speculative launch that prepared THIS scan finished long ago: account its device time now
+        float ms = 0.f;
+        if (c->profiling && cudaEventElapsedTime(&ms, o->spec_ev[0], o->spec_ev[1]) == cudaSuccess) c->stage_ms[LIMU_STAGE_DOWNSAMPLE] += (double)ms;
+        o->spec_timed = false;
+    }
+    if (speculate) {
+        if (!o->frame_done) {
+            LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->frame_done, cudaEventDisableTiming));
+            for (int k = 0; k < 2; ++k) LIMU_CUDA_TRY(cudaEventCreate(&o->spec_ev[k]));
+        }
+        LIMU_CUDA_TRY(cudaEventRecord(o->frame_done, c->stream));
+        // stream order: frame kernel (writes twist_next) -> result copy -> k_voxelize of the hinted scan (reads twist_next; overwrites
+        // frame/down/src0 and the two counts, which this scan no longer needs on the device)
+        if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->spec_ev[0], c->stream));
+        LIMU_TRY(voxelize_device(c, o->vx, o->hint_ptr, 0, 0, nullptr, next_deskew, nullptr, o->hint_n, v, o->frame.as<double>(), o->down.as<double>(),
+                                 o->src0.as<double>(), cnt + 0, next_deskew ? o->twist_next.as<double>() : nullptr));
+        if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->spec_ev[1], c->stream)); o->spec_timed = true; }
+        o->spec_ptr = o->hint_ptr; o->spec_n = o->hint_n; o->spec_deskewed = next_deskew;
+        o->hint_ptr = nullptr; o->hint_n = 0;
+        LIMU_CUDA_TRY(cudaEventSynchronize(o->frame_done));   // wakes up when the frame kernel and the copy are done; k_voxelize keeps running
+    } else
+#endif
     LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
     {
         DevStatus st;
@@ -226,6 +289,10 @@ void limu_odom_destroy(limu_odom *o) {
     for (auto *b : bufs) b->release();
     o->vx.release();
     o->pre.release();
+#ifdef LIMU_SPECULATIVE_VOXELIZE
+    o->twist_next.release();
+    if (o->frame_done) { cudaEventDestroy(o->frame_done); cudaEventDestroy(o->spec_ev[0]); cudaEventDestroy(o->spec_ev[1]); }
+#endif
     delete o;
 }
 
@@ -279,6 +346,17 @@ int limu_odom_register_frame_dev(limu_odom *o, const float *xyzt_dev, int64_t n,
     LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyzt_dev), "limu_odom_register_frame_dev: bad arguments");
     LIMU_TRY(bind(o->ctx));
     return odom_register_device(o, xyzt_dev, 0, 0, nullptr, n, pose_out, nullptr, nullptr, nullptr, nullptr, stats);
+}
+
+int limu_odom_hint_next_dev(limu_odom *o, const float *xyzt_dev_next, int64_t n_next) {
+    LIMU_REQUIRE(o && n_next >= 0, "limu_odom_hint_next_dev: bad arguments");
+#ifdef LIMU_SPECULATIVE_VOXELIZE
+    o->hint_ptr = n_next > 0 ? xyzt_dev_next : nullptr;
+    o->hint_n = n_next > 0 ? n_next : 0;
+#else
+    (void)xyzt_dev_next;   // a hint may be ignored: this build registers every scan start to finish inside its own call
+#endif
+    return LIMU_OK;
 }
 
 int limu_odom_register_points(limu_odom *o, const double *xyz, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down,

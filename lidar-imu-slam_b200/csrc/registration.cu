@@ -73,6 +73,10 @@ struct IcpArgs {
     unsigned int *exit_count;   // last CTA out resets the barrier words (no memset per launch)
     unsigned int *barrier_icp;  // barrier of the leading `icp_blocks` CTAs that run the Gauss-Newton loop
     int icp_blocks;
+#ifdef LIMU_SPECULATIVE_VOXELIZE
+    double *twist_out;          // see FrameFusion
+    double last_pose[7];
+#endif
     double *est_trace;          // optional [max_iter][7]
     long long *ncorr_trace;     // optional [max_iter]
     double *hg_trace;           // optional [max_iter][42]
@@ -559,6 +563,14 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const Pose np = run_icp ? mul(pose_load(Ticp), pose_load(Tinit)) : pose_load(Tinit);
         pose_store(np, A.out);
+#ifdef LIMU_SPECULATIVE_VOXELIZE
+        if (A.twist_out) {   // the next scan deskews with delta_pose(poses[N-2], poses[N-1]) = log(last^-1 * new): leave it on the device
+            double tw[6];
+            se3_log(mul(inverse(Pose{A.last_pose[0], A.last_pose[1], A.last_pose[2], A.last_pose[3], A.last_pose[4], A.last_pose[5], A.last_pose[6]}), np), tw);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) A.twist_out[k] = tw[k];
+        }
+#endif
         A.out[7] = (double)j; A.out[8] = (double)converged; A.out[9] = S[I_NCORR]; A.out[10] = S[I_NCORR + 1]; A.out[11] = S[I_NCORR + 2]; A.out[12] = (double)n;
     }
     if (A.upd_down) {
@@ -691,6 +703,10 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
         A.upd_down = fuse->upd_down; A.upd_n = fuse->upd_n; A.upd_world = fuse->upd_world; A.upd_pslot = fuse->upd_pslot;
         A.upd_counters = m->counters.as<unsigned long long>(); A.upd_birth_base = fuse->upd_birth_base;
         A.upd_capacity = (long long)m->capacity; A.upd_max_distance = m->max_distance;
+#ifdef LIMU_SPECULATIVE_VOXELIZE
+        A.twist_out = fuse->twist_out;
+        for (int k = 0; k < 7; ++k) A.last_pose[k] = fuse->last_pose[k];
+#endif
     }
     void *args[] = {&A};
     LIMU_TRY(prof_begin(c, LIMU_STAGE_ICP));

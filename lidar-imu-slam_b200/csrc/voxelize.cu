@@ -24,6 +24,9 @@ struct VoxelizeArgs {
     const double *ts;
     int mode, stride, deskew;
     double twist[6];            // by value, read when deskew != 0
+#ifdef LIMU_SPECULATIVE_VOXELIZE
+    const double *twist_dev;    // non-null: the twist was left in device memory by the previous scan's frame kernel (speculative launch)
+#endif
     int64_t n;
     double vs1, vs2;            // 0.5 v and 1.5 v (icp.cpp:129-130)
     double *frame, *down, *src0;
@@ -92,6 +95,12 @@ static __global__ void __launch_bounds__(VX_BLOCK, 4) k_voxelize(const VoxelizeA
         if (A.deskew) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) tw[k] = A.twist[k];
+#ifdef LIMU_SPECULATIVE_VOXELIZE
+            if (A.twist_dev) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) tw[k] = __ldcg(A.twist_dev + k);
+            }
+#endif
         }
         for (int64_t i = gtid; i < n; i += gthreads) {
             V3 p;
@@ -188,7 +197,7 @@ static int64_t pow2_slots(int64_t n) { int64_t p = 1024; while (p < 2 * n) p <<=
 
 // Enqueue the fused kernel. raw/ts/twist are device pointers; outputs: frame (n x 3), down, src0, counts[0..1].
 int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int mode, int stride, const double *ts_dev, int deskew, const double *twist_host,
-                    int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev) {
+                    int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev, const double *twist_dev) {
     if (n <= 0) { LIMU_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int), c->stream)); return LIMU_OK; }
     if (g_vx_blocks_per_sm == 0) {
         int b = 0;
@@ -209,6 +218,11 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     VoxelizeArgs A;
     A.raw = raw_dev; A.ts = ts_dev; A.mode = mode; A.stride = stride; A.deskew = deskew; A.n = n;
     for (int k = 0; k < 6; ++k) A.twist[k] = (deskew && twist_host) ? twist_host[k] : 0.0;
+#ifdef LIMU_SPECULATIVE_VOXELIZE
+    A.twist_dev = deskew ? twist_dev : nullptr;
+#else
+    (void)twist_dev;
+#endif
     A.vs1 = v * 0.5; A.vs2 = v * 1.5;
     A.frame = frame_dev; A.down = down_dev; A.src0 = src0_dev;
     A.keys1 = sc.table.as<unsigned long long>();
