@@ -210,9 +210,13 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
         o->spec_ptr = o->hint_ptr; o->spec_n = o->hint_n; o->spec_deskewed = next_deskew;
         o->hint_ptr = nullptr; o->hint_n = 0;
         LIMU_CUDA_TRY(cudaEventSynchronize(o->frame_done));   // wakes up when the frame kernel and the copy are done; k_voxelize keeps running
-    } else
-#endif
+    } else {
+        o->hint_ptr = nullptr; o->hint_n = 0;   // a hint is good for one call only
+        LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+#else
     LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+#endif
     {
         DevStatus st;
         memcpy(&st, h + 21, sizeof st);
