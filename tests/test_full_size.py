@@ -121,7 +121,7 @@ def test_pipeline_at_128k_is_deterministic_and_consistent(ctx, pkg, synth):
     traj = synth.loop_trajectory(6, radius=30.0, step=1.0)
     scans = [synth.pad_scan(synth.cast_scan(scene, traj[i], traj[i + 1], beams=64, azimuth_steps=2000, seed=42 * 100003 + i), 128000, seed=i) for i in range(5)]
     runs = []
-    for kind in ("host", "host", "dev"):
+    for kind in ("host", "host", "dev", "dev+hint"):
         k = ctx.KissICP(voxel_size=1.0, max_range=100.0, cap=10, deskew=True)
         poses = []
         for s in scans:
@@ -134,8 +134,16 @@ def test_pipeline_at_128k_is_deterministic_and_consistent(ctx, pkg, synth):
                     assert np.array_equal(down, xyz[f1]) and np.array_equal(src, np_iqr(xyz[f1][f2]))
                 assert k.stats.n_points == 128000 and k.stats.n_down == len(down) and k.stats.n_keypoints == len(src)
             else:
-                t = torch.from_numpy(s).cuda()
-                torch.cuda.synchronize()                                      # the library runs on its own non-blocking stream
+                if kind == "dev":
+                    t = torch.from_numpy(s).cuda()
+                    torch.cuda.synchronize()                                  # the library runs on its own non-blocking stream
+                else:   # replay hints (limu_odom_hint_next_dev): results must not depend on them, whatever the build does with them
+                    if not poses:
+                        staged = [torch.from_numpy(x).cuda() for x in scans]
+                        torch.cuda.synchronize()
+                    t = staged[len(poses)]
+                    if len(poses) + 1 < len(staged):
+                        k.hint_next_dev(staged[len(poses) + 1].data_ptr(), len(scans[len(poses) + 1]))
                 pose = k.register_frame_dev(t.data_ptr(), len(s))
             poses.append(pose.copy())
         runs.append(np.array(poses))
@@ -143,3 +151,5 @@ def test_pipeline_at_128k_is_deterministic_and_consistent(ctx, pkg, synth):
         assert nv > 1000 and npts >= nv
         k.close()
     assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
+    # a build that acts on the hints computes the deskew twist on the device: equal to the north-star tolerance, bit-equal otherwise
+    assert np.abs(runs[3] - runs[0]).max() < 1e-9
