@@ -91,6 +91,22 @@ typedef struct limu_imu_pose { double offset_time, acc[3], gyr[3], vel[3], pos[3
 int limu_deskew_imu(limu_ctx *c, void *points, int32_t stride_bytes, int32_t curvature_offset_bytes, int64_t n, const limu_imu_pose *table,
                     int32_t n_poses, const double rot_end[9], const double pos_lidar_end[3], const double p_imu_lidar[3], double *out_xyz,
                     int32_t write_back);
+/* The IMU forward pass of the same function (ekf.cpp:292-418): HOST code inside the library (about 20 IMU samples per scan) that builds
+ * what limu_deskew_imu consumes, so a caller does not need the reference's EKF object. samples[0] is the last sample of the previous window
+ * (mc_tracker->last_imu, :295), samples[1..k-1] the IMU buffer of this scan. state: the EKF state entries the function reads; in/out members
+ * carry what the reference keeps between windows. The quaternion 4-vector is used exactly as the reference does (S acts on it as stored,
+ * the rotation matrix reads it as x,y,z,w without normalising). exp(S) is closed-form here, Eigen's Pade approximant there: ~1e-16 apart. */
+typedef struct limu_imu_sample { double t, gyr[3], acc[3]; } limu_imu_sample;
+typedef struct limu_imu_state {
+    double pos[3], vel[3], quat[4];                          /* POS, VEL, ORI at the start of the window (position(), velocity(), orientation()) */
+    double bga[3], baa[3], bat[3], grav[3], p_imu_lidar[3];  /* BGA, BAA, BAT, GRAV, POS_IMU_LIDAR */
+    double mean_acc_norm, gravity;                           /* meas->get_mean_acc_norm(); 9.81 (common.hpp:16) */
+    double last_lidar_end_time;                              /* in/out (:413) */
+    double acc_s_last[3], ang_vel_last[3];                   /* in/out: the tracker members that fill row 0 of the table (:307, :386-387) */
+    double tracker_vel[3], tracker_pos[3], tracker_quat[4];  /* out: mc_tracker->vel / pos and the quaternion after the last IMU pair */
+} limu_imu_state;
+int limu_imu_forward_pass(limu_imu_state *state, const limu_imu_sample *samples, int32_t k, double lidar_beg_time, double last_point_curvature_ms,
+                          limu_imu_pose *table_out, int32_t max_rows, int32_t *n_rows, double rot_end[9], double pos_lidar_end[3]);
 /* voxel_downsample (file-local), sensors/lidar/icp.cpp:9-30: first point per voxel of edge s wins;
  * output in first-occurrence order. out_xyz must hold n points; out_idx (optional) the source indices. */
 int limu_voxel_downsample(limu_ctx *c, const double *xyz, int64_t n, double s, double *out_xyz, int64_t *out_idx, int64_t *n_out);

@@ -65,6 +65,31 @@ class LidarConfig(C.Structure):
                 ("frame_rate", C.c_double), ("num_scan_lines", C.c_int32), ("frame_split_num", C.c_int32)]
 
 
+class ImuSample(C.Structure):
+    _fields_ = [("t", C.c_double), ("gyr", C.c_double * 3), ("acc", C.c_double * 3)]
+
+
+class ImuState(C.Structure):
+    """The EKF state entries kalman::EKF::motion_compensation_with_imu reads (limu_cuda.h limu_imu_state)."""
+    _fields_ = [("pos", C.c_double * 3), ("vel", C.c_double * 3), ("quat", C.c_double * 4), ("bga", C.c_double * 3), ("baa", C.c_double * 3),
+                ("bat", C.c_double * 3), ("grav", C.c_double * 3), ("p_imu_lidar", C.c_double * 3), ("mean_acc_norm", C.c_double), ("gravity", C.c_double),
+                ("last_lidar_end_time", C.c_double), ("acc_s_last", C.c_double * 3), ("ang_vel_last", C.c_double * 3), ("tracker_vel", C.c_double * 3),
+                ("tracker_pos", C.c_double * 3), ("tracker_quat", C.c_double * 4)]
+
+
+def imu_forward_pass(state: ImuState, imu, lidar_beg_time, last_point_curvature_ms):
+    """IMU forward pass of EKF::motion_compensation_with_imu (ekf.cpp:292-418), host code. imu: [k,7] rows {t, gyr xyz, acc xyz}, row 0 = the last
+    sample of the previous window. Returns (table [M,22], rot_end [9], pos_lidar_end [3]); `state` is updated in place."""
+    imu = np.ascontiguousarray(imu, np.float64).reshape(-1, 7)
+    k = len(imu)
+    table = np.zeros((k + 2, 22))
+    rot_end, ple = np.zeros(9), np.zeros(3)
+    n = C.c_int32(0)
+    _chk(lib().limu_imu_forward_pass(C.byref(state), imu.ctypes.data_as(_vp), k, float(lidar_beg_time), float(last_point_curvature_ms),
+                                     table.ctypes.data_as(_vp), len(table), C.byref(n), _d(rot_end), _d(ple)))
+    return table[: n.value].copy(), rot_end, ple
+
+
 def cloud_fields(fields, point_step) -> CloudFields:
     """fields: [(name, offset, PointField datatype, count)] -> the selection frame::Lidar::process_frame makes of them."""
     names = b"".join(f[0].encode() + b"\0" for f in fields)
@@ -158,6 +183,7 @@ def lib():
                                       C.POINTER(C.c_int32)],
             "limu_odom_register_msg": [_vp, _vp, C.c_int64, C.POINTER(CloudFields), C.POINTER(LidarConfig), C.c_double, C.c_int32, C.c_int32, _dp, _lp, _dp,
                                        C.POINTER(C.c_int32), C.POINTER(FrameStats)],
+            "limu_imu_forward_pass": [C.POINTER(ImuState), _vp, C.c_int32, C.c_double, C.c_double, _vp, C.c_int32, C.POINTER(C.c_int32), _dp, _dp],
             "limu_se3_exp": [_dp, _dp], "limu_se3_log": [_dp, _dp], "limu_se3_mul": [_dp, _dp, _dp], "limu_se3_inverse": [_dp, _dp],
         }
         for name, args in sig.items():

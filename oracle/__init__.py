@@ -100,6 +100,8 @@ class _Api:
             f("deskew_imu", None, [_fp, _fp, C.c_long, _dp, C.c_long, _dp, _dp, _dp, _dp])
         elif hasattr(lib, "ref_imu_deskew"):
             f("imu_deskew", C.c_long, [_fp, _fp, C.c_long, _dp, C.c_long, C.c_double, _dp, _dp, _dp, _dp, _dp, C.c_long, _dp, _dp, _fp])
+            if hasattr(lib, "ref_imu_set_last_lidar_end_time"):
+                f("imu_set_last_lidar_end_time", None, [C.c_double])
         if kind == "reference":
             f("map_closest", None, [C.c_void_p, _dp, C.c_long, _dp])
             f("map_correspondences", C.c_long, [C.c_void_p, _dp, C.c_long, C.c_double, _dp, _dp])
@@ -201,6 +203,10 @@ class _Api:
         out = np.empty((len(x), 3))
         self._deskew(_f(x), _d(ts), len(x), _d(T0), _d(T1), _d(out))
         return out
+
+    def imu_set_last_lidar_end_time(self, t):
+        """REFERENCE ONLY: EKF::last_lidar_end_time as the next imu_deskew_reference call finds it (0 for a fresh filter)."""
+        self._imu_set_last_lidar_end_time(float(t))
 
     def imu_deskew_reference(self, xyz_f32, curv_ms, imu, lidar_beg_time, mean_acc, p_imu_lidar, gyro_bias):
         """REFERENCE ONLY: run kalman::EKF::motion_compensation_with_imu (ekf.cpp:292-469) on one scan + IMU window.

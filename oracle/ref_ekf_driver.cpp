@@ -28,7 +28,13 @@
 
 #include <cstring>
 
+static double g_last_lidar_end_time = 0.0;
+
 extern "C" {
+
+// EKF::last_lidar_end_time as the NEXT ref_imu_deskew call finds it (what the previous window's call left behind, ekf.cpp:413): lets a
+// test reach the "pair older than the previous scan's end" branches (:322-323, :340-341) without a long-lived EKF object.
+void ref_imu_set_last_lidar_end_time(double t) { g_last_lidar_end_time = t; }
 
 // imu: k rows of {t, gx, gy, gz, ax, ay, az}; row 0 plays mc_tracker->last_imu (the sample before the window).
 // xyz/curv_ms: n points sorted by curvature (per-point offset time in ms, lidar/frame.cpp:28-51).
@@ -47,6 +53,7 @@ long ref_imu_deskew(const float *xyz, const float *curv_ms, long n, const double
     kalman::EKF ekf(prm);
     for (int i = 0; i < 3; ++i) { ekf.m(kalman::POS_IMU_LIDAR + i) = p_imu_lidar3[i]; ekf.m(kalman::BGA + i) = gyro_bias3[i]; }
     ekf.m.segment(kalman::GRAV, 3) = ekf.grav;   // gravity in the state (what initialize_imu_global_orientation would have set)
+    ekf.last_lidar_end_time = g_last_lidar_end_time;
 
     auto mk = [&](long r) {
         auto p = std::make_shared<sensor_msgs::Imu>();
