@@ -129,6 +129,7 @@ class _Api:
             f("kiss_last_sigma", C.c_double, [C.c_void_p])
             f("kiss_map", C.c_void_p, [C.c_void_p])
             f("map_set_mode", None, [C.c_void_p, C.c_int])
+            f("plane_normal", C.c_int, [_dp, C.c_int, _dp])
             f("kiss_set_mode", None, [C.c_void_p, C.c_int])
         if hasattr(lib, p + "process_frame"):
             f("process_frame", C.c_long, [C.c_char_p, C.c_long, C.c_int, C.c_int, C.c_char_p, _ip, _ip, _ip, _dp, C.c_double, C.c_int, C.c_long, _lp, _dp, _fp, _dp])
@@ -262,6 +263,12 @@ class _Api:
             out.append({"points": rec5[at:at + m].copy(), "ts": ts[at:at + m].copy(), "time": float(seg_time[j])})
             at += m
         return out
+
+    def plane_normal(self, pts):
+        """PORT ONLY: the voxel plane of the opt-in point-to-plane variant. Returns the unit normal or None when not planar."""
+        pts = _pts(pts)
+        n = np.zeros(3)
+        return n if self._plane_normal(_d(pts), len(pts), _d(n)) else None
 
     def align(self, src, tgt, th):
         """Returns dict(pose=7) for the reference; the port adds H (6x6), g (6), x (6)."""

@@ -541,10 +541,8 @@ void lo_align(const double *src, const double *tgt, long n, double th, double *H
  * (s' = exp(x) s, J_point = [I | -hat(s)], registration.cpp:46-54), H += w a a^T, g += w a e, x = LDLT(H).solve(-g). */
 #define LO_PLANE_MIN_POINTS 5
 #define LO_PLANE_RATIO 0.04
-static int voxel_normal(const lo_map *m, long e, double *nrm) {
-    const int c = m->counts[e];
+int lo_plane_normal(const double *b, int c, double *nrm) {   /* b: c points, array-of-structs */
     if (c < LO_PLANE_MIN_POINTS) return 0;
-    const double *b = m->pts + 3 * (size_t)e * (size_t)m->cap;
     double mu[3] = {0, 0, 0};
     for (int r = 0; r < c; ++r) { mu[0] += b[3 * r]; mu[1] += b[3 * r + 1]; mu[2] += b[3 * r + 2]; }
     mu[0] /= (double)c; mu[1] /= (double)c; mu[2] /= (double)c;
@@ -578,6 +576,9 @@ static int voxel_normal(const lo_map *m, long e, double *nrm) {
     if (!(mid > 0.0) || !(A[lo][lo] <= LO_PLANE_RATIO * mid)) return 0;
     nrm[0] = V[0][lo]; nrm[1] = V[1][lo]; nrm[2] = V[2][lo];
     return 1;
+}
+static int voxel_normal(const lo_map *m, long e, double *nrm) {
+    return lo_plane_normal(m->pts + 3 * (size_t)e * (size_t)m->cap, m->counts[e], nrm);
 }
 
 /* One Gauss-Newton step of the point-to-plane variant over the current source cloud. Returns the number of plane correspondences. */

@@ -43,6 +43,9 @@ long lo_map_num_voxels(const lo_map *m);
  * (closest, correspondences, icp, the KissICP pipeline) follows the map's mode. */
 enum { LO_ICP_REFERENCE = 0, LO_ICP_NN27 = 1 };
 void lo_map_set_mode(lo_map *m, int icp_mode);
+/* The plane of LO_ICP_PLANE = 2 (point-to-plane residual): normal of c >= 5 points (array-of-structs) = eigenvector of the smallest eigenvalue
+ * of their scatter matrix by 5 cyclic Jacobi sweeps; returns 1 when planar (l_min <= 0.04 l_mid), 0 otherwise (nrm untouched). */
+int lo_plane_normal(const double *pts, int c, double *nrm);
 void lo_map_insert(lo_map *m, const double *xyz, long n);                    /* insert_points :12-62 */
 void lo_map_update(lo_map *m, const double *xyz, long n, const double *pose7); /* update :138-144 */
 void lo_map_remove_far(lo_map *m, const double *origin3);                    /* :146-171 under null locks */

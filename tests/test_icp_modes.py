@@ -52,6 +52,34 @@ def test_nn27_is_the_nearest_point_of_the_neighbourhood(port, rng, cap, spread):
         assert np.array_equal(np.trunc(got[i]).astype(np.int64), key[i])
 
 
+def test_plane_fit_is_the_smallest_eigenvector_of_the_scatter(port, rng):
+    """The plane of LIMU_ICP_PLANE (oracle voxel_normal = the definition the CUDA path reproduces bit for bit): 5 Jacobi sweeps against
+    numpy's eigh on random near-planar, line-like and blob-like point sets, and the degenerate cases."""
+    for _ in range(1500):
+        c = int(rng.integers(5, 21))
+        n0 = rng.normal(size=3)
+        n0 /= np.linalg.norm(n0)
+        basis = np.linalg.svd(np.outer(n0, n0))[0][:, 1:]
+        spread = rng.uniform(0.05, 0.5, size=2) * (1.0 if rng.random() < 0.7 else np.array([1.0, rng.uniform(0.0, 0.2)]))   # sometimes line-like
+        pts = (rng.normal(size=(c, 2)) * spread) @ basis.T + n0 * rng.normal(size=(c, 1)) * rng.uniform(0, 0.05) + rng.normal(size=3) * 30
+        n = port.plane_normal(pts)
+        x = pts - pts.mean(0)
+        w, v = np.linalg.eigh(x.T @ x)
+        margin = abs(w[0] - 0.04 * w[1]) > 1e-9 * w[2]          # away from the decision boundary
+        if margin:
+            assert (n is not None) == (w[1] > 0 and w[0] <= 0.04 * w[1])
+        if n is not None:
+            assert abs(np.linalg.norm(n) - 1) < 1e-12
+            if w[1] - w[0] > 1e-6 * w[2]:
+                assert abs(abs(n @ v[:, 0]) - 1) < 1e-8
+    assert port.plane_normal(rng.normal(size=(4, 3))) is None                        # fewer than 5 points
+    assert port.plane_normal(np.tile(rng.normal(size=(1, 3)), (8, 1))) is None       # all points equal: no spread at all
+    line = np.outer(np.arange(8.0), [1.0, 2.0, -1.0])
+    assert port.plane_normal(line) is None                                           # exactly collinear: l_mid = 0
+    flat = np.concatenate([rng.normal(size=(9, 2)), np.zeros((9, 1))], 1)
+    assert np.array_equal(np.abs(port.plane_normal(flat)), [0.0, 0.0, 1.0])          # exactly planar: the normal is exact
+
+
 @pytest.mark.parametrize("mode", [PLANE, NN27 | PLANE])
 def test_plane_icp_recovers_a_known_transform(port, rng, mode):
     world = three_planes(rng, 90000)
