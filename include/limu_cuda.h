@@ -100,7 +100,7 @@ typedef struct limu_imu_sample { double t, gyr[3], acc[3]; } limu_imu_sample;
 typedef struct limu_imu_state {
     double pos[3], vel[3], quat[4];                          /* POS, VEL, ORI at the start of the window (position(), velocity(), orientation()) */
     double bga[3], baa[3], bat[3], grav[3], p_imu_lidar[3];  /* BGA, BAA, BAT, GRAV, POS_IMU_LIDAR */
-    double mean_acc_norm, gravity;                           /* meas->get_mean_acc_norm(); 9.81 (common.hpp:16) */
+    double mean_acc_norm, gravity_norm;                      /* meas->get_mean_acc_norm(); the reference's `gravity` constant 9.81 (common.hpp:16) */
     double last_lidar_end_time;                              /* in/out (:413) */
     double acc_s_last[3], ang_vel_last[3];                   /* in/out: the tracker members that fill row 0 of the table (:307, :386-387) */
     double tracker_vel[3], tracker_pos[3], tracker_quat[4];  /* out: mc_tracker->vel / pos and the quaternion after the last IMU pair */

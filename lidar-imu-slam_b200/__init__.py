@@ -72,7 +72,7 @@ class ImuSample(C.Structure):
 class ImuState(C.Structure):
     """The EKF state entries kalman::EKF::motion_compensation_with_imu reads (limu_cuda.h limu_imu_state)."""
     _fields_ = [("pos", C.c_double * 3), ("vel", C.c_double * 3), ("quat", C.c_double * 4), ("bga", C.c_double * 3), ("baa", C.c_double * 3),
-                ("bat", C.c_double * 3), ("grav", C.c_double * 3), ("p_imu_lidar", C.c_double * 3), ("mean_acc_norm", C.c_double), ("gravity", C.c_double),
+                ("bat", C.c_double * 3), ("grav", C.c_double * 3), ("p_imu_lidar", C.c_double * 3), ("mean_acc_norm", C.c_double), ("gravity_norm", C.c_double),
                 ("last_lidar_end_time", C.c_double), ("acc_s_last", C.c_double * 3), ("ang_vel_last", C.c_double * 3), ("tracker_vel", C.c_double * 3),
                 ("tracker_pos", C.c_double * 3), ("tracker_quat", C.c_double * 4)]
 

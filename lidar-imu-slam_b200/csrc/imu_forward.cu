@@ -72,7 +72,7 @@ extern "C" int limu_imu_forward_pass(limu_imu_state *st, const limu_imu_sample *
         if (tail.t < st->last_lidar_end_time) continue;                                    // :322-323
         for (int a = 0; a < 3; ++a) { xg[a] = 0.5 * (head.gyr[a] + tail.gyr[a]); xa[a] = 0.5 * (head.acc[a] + tail.acc[a]); }
         dt = head.t < st->last_lidar_end_time ? tail.t - st->last_lidar_end_time : tail.t - head.t;   // :340-343
-        for (int a = 0; a < 3; ++a) xa[a] = xa[a] / st->mean_acc_norm * st->gravity;        // :357
+        for (int a = 0; a < 3; ++a) xa[a] = xa[a] / st->mean_acc_norm * st->gravity_norm;        // :357
         quat_step(xg, st->bga, -dt, q);                                                    // :373-375
         quat_to_rot(q, R);                                                                 // :376
         double T_ab[3];

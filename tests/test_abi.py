@@ -39,7 +39,9 @@ def test_header_is_plain_c(tmp_path):
     """The boundary is a C ABI: include/limu_cuda.h must compile as strict C99 and as C++11, with nothing but <stddef.h>/<stdint.h>."""
     import subprocess
     src = tmp_path / "abi.c"
-    src.write_text('#include "limu_cuda.h"\nint main(void) { limu_odom_config c; limu_lidar_config l; limu_cloud_fields f; limu_imu_pose p;'
+    # the reference's common.hpp defines object-like macros (PI_M, IQR_TUCHEY, gravity, :14-16) and is included BEFORE this header by
+    # the drop-in layer: no identifier of the ABI may collide with them
+    src.write_text('#define PI_M 3.14159265358979\n#define IQR_TUCHEY 1.25\n#define gravity 9.81\n#include "limu_cuda.h"\nint main(void) { limu_odom_config c; limu_lidar_config l; limu_cloud_fields f; limu_imu_pose p;'
                    ' limu_frame_stats s; (void)c; (void)l; (void)f; (void)p; (void)s; return LIMU_ABI_VERSION == 1 ? 0 : 1; }\n')
     inc = os.path.join(ROOT, "include")
     subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, "-c", str(src), "-o", str(tmp_path / "a.o")])

@@ -24,7 +24,7 @@ def make_state(pkg, mean_acc, pil, bg, last_end=0.0, row0=None):
     st.grav[:] = [0, 0, -9.81]                    # grav (:80)
     st.p_imu_lidar[:] = pil
     st.mean_acc_norm = float(np.linalg.norm(mean_acc))
-    st.gravity = 9.81
+    st.gravity_norm = 9.81
     st.last_lidar_end_time = last_end
     if row0 is not None:                          # the tracker's acc_s_last / ang_vel_last are uninitialised in a fresh reference EKF:
         st.acc_s_last[:] = row0[1:4]              # take whatever it put into row 0
