@@ -81,6 +81,12 @@ struct limu_odom {
     cudaEvent_t frame_done = nullptr;       // recorded after the result copy of the current scan
     cudaEvent_t spec_ev[2] = {nullptr, nullptr};   // device time of the speculative launch, folded into LIMU_STAGE_DOWNSAMPLE one call later
     bool spec_timed = false;
+    // host-pointer entry (limu_odom_register_frame + limu_odom_prefetch): the prefetched scan is the hinted one. This scan's clouds then
+    // leave on the copy stream while the speculative launch runs, so `down` is double-buffered (the launch writes the buffer this scan
+    // does not use); `src` is only rewritten by the NEXT frame kernel, which is launched after the clouds have arrived.
+    limu::DevBuf down_alt;
+    int down_cur = 0;
+    cudaEvent_t clouds_done = nullptr;
 #endif
 };
 
@@ -125,11 +131,23 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     // growing those buffers for a larger hinted scan must then keep their contents.
     const bool spec_hit = mode == 0 && n > 0 && raw_dev == o->spec_ptr && n == o->spec_n && o->spec_deskewed == deskewed;
     o->spec_ptr = nullptr;
-    const size_t nb = (size_t)std::max<int64_t>(std::max<int64_t>(n, o->hint_ptr ? o->hint_n : 0), 1) * 24;
+    if (spec_hit) o->down_cur ^= 1;   // the speculative launch wrote the other `down` buffer
+    // the scan after this one, if the caller told us where it is: a device-pointer hint, or the scan limu_odom_prefetch is uploading
+    const void *next_ptr = o->hint_ptr;
+    int64_t next_n = o->hint_ptr ? o->hint_n : 0;
+    cudaEvent_t next_ready = nullptr;
+    if (!next_ptr)
+        for (int sl = 0; sl < 2; ++sl)
+            if (o->pf_host[sl] && o->pf_n[sl] > 0) { next_ptr = o->pf_buf[sl].p; next_n = o->pf_n[sl]; next_ready = o->pf_done[sl]; }
+    o->hint_ptr = nullptr; o->hint_n = 0;   // a hint is good for one call only
+    const size_t nb = (size_t)std::max<int64_t>(std::max<int64_t>(n, next_n), 1) * 24;
     const bool keep = spec_hit;
+    LIMU_TRY(o->down_alt.reserve(nb, c->stream, keep));
+    limu::DevBuf &down_mine = o->down_cur ? o->down_alt : o->down, &down_other = o->down_cur ? o->down : o->down_alt;
 #else
     const size_t nb = (size_t)std::max<int64_t>(n, 1) * 24;
     const bool keep = false;
+    limu::DevBuf &down_mine = o->down;
 #endif
     LIMU_TRY(o->frame.reserve(nb, c->stream, keep));
     LIMU_TRY(o->down.reserve(nb, c->stream, keep));
@@ -149,7 +167,7 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
 #endif
     {
         LIMU_TRY(prof_begin(c, LIMU_STAGE_DOWNSAMPLE));
-        LIMU_TRY(voxelize_device(c, o->vx, raw_dev, mode, stride, ts_dev, deskewed, twist, n, v, o->frame.as<double>(), o->down.as<double>(), o->src0.as<double>(), cnt + 0));
+        LIMU_TRY(voxelize_device(c, o->vx, raw_dev, mode, stride, ts_dev, deskewed, twist, n, v, o->frame.as<double>(), down_mine.as<double>(), o->src0.as<double>(), cnt + 0));
         LIMU_TRY(prof_end(c, LIMU_STAGE_DOWNSAMPLE));
     }
     // host scalar glue (icp.cpp:66-71)
@@ -167,11 +185,10 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     LIMU_TRY(o->d2.reserve((size_t)std::max<int64_t>(n, 1) * 8, c->stream));
     FrameFusion fuse;
     fuse.iqr_in = o->src0.as<double>(); fuse.iqr_n = cnt + 1; fuse.iqr_d2 = o->d2.as<double>(); fuse.iqr_out = o->src.as<double>(); fuse.iqr_count = cnt + 2;
-    fuse.upd_down = o->down.as<double>(); fuse.upd_n = cnt + 0; fuse.upd_world = o->world.as<double>(); fuse.upd_pslot = o->map->pslot.as<unsigned int>();
+    fuse.upd_down = down_mine.as<double>(); fuse.upd_n = cnt + 0; fuse.upd_world = o->world.as<double>(); fuse.upd_pslot = o->map->pslot.as<unsigned int>();
     fuse.upd_birth_base = o->map->birth_base;
 #ifdef LIMU_SPECULATIVE_VOXELIZE
-    // speculate only when nothing of this scan's clouds has to travel to the host after the synchronisation (their buffers are reused)
-    const bool speculate = o->hint_ptr && o->hint_n > 0 && mode == 0 && !down_xyz && !keypoints_xyz;
+    const bool speculate = next_ptr && next_n > 0 && mode == 0;
     const int next_deskew = (o->cfg.deskew && NP + 1 > 2) ? 1 : 0;   // the gate of icp.cpp:40-46 as the next scan will see it
     fuse.twist_out = nullptr;
     if (speculate && next_deskew) {
@@ -201,17 +218,16 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
             for (int k = 0; k < 2; ++k) LIMU_CUDA_TRY(cudaEventCreate(&o->spec_ev[k]));
         }
         LIMU_CUDA_TRY(cudaEventRecord(o->frame_done, c->stream));
-        // stream order: frame kernel (writes twist_next) -> result copy -> k_voxelize of the hinted scan (reads twist_next; overwrites
-        // frame/down/src0 and the two counts, which this scan no longer needs on the device)
+        // stream order: frame kernel (writes twist_next) -> result copy -> [upload of the next scan done] -> k_voxelize of the next scan
+        // (reads twist_next; overwrites frame, src0, the two counts -- dead for this scan -- and the OTHER `down` buffer)
+        if (next_ready) LIMU_CUDA_TRY(cudaStreamWaitEvent(c->stream, next_ready, 0));
         if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->spec_ev[0], c->stream));
-        LIMU_TRY(voxelize_device(c, o->vx, o->hint_ptr, 0, 0, nullptr, next_deskew, nullptr, o->hint_n, v, o->frame.as<double>(), o->down.as<double>(),
+        LIMU_TRY(voxelize_device(c, o->vx, next_ptr, 0, 0, nullptr, next_deskew, nullptr, next_n, v, o->frame.as<double>(), down_other.as<double>(),
                                  o->src0.as<double>(), cnt + 0, next_deskew ? o->twist_next.as<double>() : nullptr));
         if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->spec_ev[1], c->stream)); o->spec_timed = true; }
-        o->spec_ptr = o->hint_ptr; o->spec_n = o->hint_n; o->spec_deskewed = next_deskew;
-        o->hint_ptr = nullptr; o->hint_n = 0;
+        o->spec_ptr = next_ptr; o->spec_n = next_n; o->spec_deskewed = next_deskew;
         LIMU_CUDA_TRY(cudaEventSynchronize(o->frame_done));   // wakes up when the frame kernel and the copy are done; k_voxelize keeps running
     } else {
-        o->hint_ptr = nullptr; o->hint_n = 0;   // a hint is good for one call only
         LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
 #else
@@ -237,9 +253,30 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     if (n_down) *n_down = nd;
     if (n_keypoints) *n_keypoints = nk;
     bool copied = false;
-    if (down_xyz && nd > 0) { LIMU_CUDA_TRY(cudaMemcpyAsync(down_xyz, o->down.p, (size_t)nd * 24, cudaMemcpyDeviceToHost, c->stream)); copied = true; }
-    if (keypoints_xyz && nk > 0) { LIMU_CUDA_TRY(cudaMemcpyAsync(keypoints_xyz, o->src.p, (size_t)nk * 24, cudaMemcpyDeviceToHost, c->stream)); copied = true; }
-    if (copied) LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaStream_t cloud_stream = c->stream;
+#ifdef LIMU_SPECULATIVE_VOXELIZE
+    if (speculate && ((down_xyz && nd > 0) || (keypoints_xyz && nk > 0))) {
+        // the main stream is busy with the next scan's k_voxelize: this scan's clouds leave on the copy stream (everything they read was
+        // complete at frame_done, and nothing in flight writes it)
+        if (!o->copy_stream) {
+            LIMU_CUDA_TRY(cudaStreamCreateWithFlags(&o->copy_stream, cudaStreamNonBlocking));
+            for (int sl = 0; sl < 2; ++sl) LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->pf_done[sl], cudaEventDisableTiming));
+        }
+        if (!o->clouds_done) LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->clouds_done, cudaEventDisableTiming));
+        cloud_stream = o->copy_stream;
+    }
+#endif
+    if (down_xyz && nd > 0) { LIMU_CUDA_TRY(cudaMemcpyAsync(down_xyz, down_mine.p, (size_t)nd * 24, cudaMemcpyDeviceToHost, cloud_stream)); copied = true; }
+    if (keypoints_xyz && nk > 0) { LIMU_CUDA_TRY(cudaMemcpyAsync(keypoints_xyz, o->src.p, (size_t)nk * 24, cudaMemcpyDeviceToHost, cloud_stream)); copied = true; }
+    if (copied) {
+#ifdef LIMU_SPECULATIVE_VOXELIZE
+        if (cloud_stream != c->stream) {
+            LIMU_CUDA_TRY(cudaEventRecord(o->clouds_done, cloud_stream));
+            LIMU_CUDA_TRY(cudaEventSynchronize(o->clouds_done));
+        } else
+#endif
+        LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
     if (stats) {
         stats->n_points = n; stats->n_down = nd; stats->n_keypoints = nk; stats->sigma = sigma; stats->deskewed = deskewed; stats->reserved0 = 0;
         stats->icp.iterations = (int)ho[7]; stats->icp.converged = (int)ho[8]; stats->icp.last_ncorr = (int64_t)ho[9];
@@ -295,7 +332,9 @@ void limu_odom_destroy(limu_odom *o) {
     o->pre.release();
 #ifdef LIMU_SPECULATIVE_VOXELIZE
     o->twist_next.release();
+    o->down_alt.release();
     if (o->frame_done) { cudaEventDestroy(o->frame_done); cudaEventDestroy(o->spec_ev[0]); cudaEventDestroy(o->spec_ev[1]); }
+    if (o->clouds_done) cudaEventDestroy(o->clouds_done);
 #endif
     delete o;
 }
@@ -306,6 +345,13 @@ int limu_odom_register_frame(limu_odom *o, const float *xyzt, int64_t n, double 
     LIMU_TRY(bind(o->ctx));
     int hit = -1;
     for (int s = 0; s < 2; ++s) if (n > 0 && o->pf_host[s] == xyzt && o->pf_n[s] == n) hit = s;
+#ifdef LIMU_SPECULATIVE_VOXELIZE
+    if (hit >= 0 && o->spec_ptr == o->pf_buf[hit].p && o->spec_n == n) {
+        // uploaded ahead of time AND already through k_voxelize (enqueued behind the previous scan): register it where it lies
+        o->pf_host[hit] = nullptr; o->pf_n[hit] = -1;
+        return odom_register_device(o, o->pf_buf[hit].p, 0, 0, nullptr, n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+    }
+#endif
     if (hit >= 0) {   // uploaded ahead of time by limu_odom_prefetch
         LIMU_CUDA_TRY(cudaStreamWaitEvent(o->ctx->stream, o->pf_done[hit], 0));
         std::swap(o->raw, o->pf_buf[hit]);
