@@ -48,6 +48,9 @@ typedef enum limu_status {
 
 const char *limu_last_error(void);
 int limu_abi_version(void);
+/* First 16 hex digits of the SHA-256 of the sources (csrc + this header) the loaded library was built from: bench.py quotes a committed
+ * ncu capture only when it was taken from the same sources. */
+const char *limu_source_hash(void);
 /* Number of kernel launches issued by this process so far (all handles). bench.py reports the delta. */
 uint64_t limu_kernel_launches(void);
 int limu_device_count(void);
@@ -215,7 +218,10 @@ typedef struct limu_odom limu_odom;
 int limu_odom_create(limu_ctx *c, const limu_odom_config *cfg, limu_odom **out);
 void limu_odom_destroy(limu_odom *o);
 /* register_frame(cloud, timestamps) icp.cpp:49-55. Outputs are optional (NULL = not copied back):
- * down_xyz / keypoints_xyz must hold n points each. */
+ * down_xyz / keypoints_xyz must hold n points each.
+ * Error behaviour of every limu_odom_register_*: LIMU_ERR_KEY_RANGE / LIMU_ERR_MAP_FULL are reported AFTER the frame has been committed
+ * (pose appended, threshold state and map updated, outputs filled): the offending points -- voxel index outside +-2^20, e.g. an inf
+ * coordinate that frame::Lidar::process_frame would have dropped -- were left out of the downsampled cloud and of the map. */
 int limu_odom_register_frame(limu_odom *o, const float *xyzt, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down,
                              double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats);
 /* Replay / batch use: start uploading the NEXT scan (pinned host memory) on a separate stream while the current one is
@@ -227,10 +233,15 @@ int limu_odom_register_cloud(limu_odom *o, const void *points, int32_t stride_by
                              double *down_xyz, int64_t *n_down, double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats);
 int limu_odom_register_frame_dev(limu_odom *o, const float *xyzt_dev, int64_t n, double pose_out[7], limu_frame_stats *stats);
 /* Replay hint: the scan that will be registered AFTER the next limu_odom_register_frame_dev call already sits in device memory at
- * xyzt_dev_next. A library built with LIMU_SPECULATIVE_VOXELIZE then enqueues that scan's deskew + downsampling launch right behind the
- * current scan's registration (the deskew twist stays on the device), so the host round trip between two scans overlaps GPU work; other
- * builds ignore the hint. Results do not depend on hints; a hint that is not followed by that scan is simply discarded. */
+ * xyzt_dev_next (and stays untouched until it has been registered). With LIMU_OPT_SPECULATE on (the default) that scan's deskew +
+ * downsampling launch is enqueued right behind the current scan's registration (the deskew twist stays on the device), so the host
+ * round trip between two scans overlaps GPU work; limu_odom_prefetch gives the host-pointer entry the same treatment. Poses do not
+ * depend on hints beyond rounding (the twist of a speculated scan is taken by the device's log instead of the host's: ~1e-15); a hint
+ * that is not followed by that scan is simply discarded. */
 int limu_odom_hint_next_dev(limu_odom *o, const float *xyzt_dev_next, int64_t n_next);
+/* Handle options. LIMU_OPT_SPECULATE (default 1; the environment variable LIMU_SPECULATE=0 changes the default): see above. */
+enum { LIMU_OPT_SPECULATE = 1 };
+int limu_odom_set_option(limu_odom *o, int32_t option, int64_t value);
 /* register_frame(Vec3dVector) icp.cpp:58-86 (no deskew). */
 int limu_odom_register_points(limu_odom *o, const double *xyz, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down,
                               double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats);

@@ -130,6 +130,7 @@ def lib():
             raise LimuError(-2, f"{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback.")
         L = C.CDLL(LIB_PATH)
         L.limu_last_error.restype = C.c_char_p
+        L.limu_source_hash.restype = C.c_char_p
         L.limu_kernel_launches.restype = C.c_uint64
         L.limu_host_alloc.restype = _vp
         L.limu_host_alloc.argtypes = [C.c_size_t]
@@ -174,6 +175,7 @@ def lib():
             "limu_odom_register_frame_dev": [_vp, _vp, C.c_int64, _dp, C.POINTER(FrameStats)],
             "limu_odom_prefetch": [_vp, _fp, C.c_int64],
             "limu_odom_hint_next_dev": [_vp, _vp, C.c_int64],
+            "limu_odom_set_option": [_vp, C.c_int32, C.c_int64],
             "limu_odom_register_points": [_vp, _dp, C.c_int64, _dp, _dp, _lp, _dp, _lp, C.POINTER(FrameStats)],
             "limu_odom_num_poses": [_vp, _lp], "limu_odom_pose": [_vp, C.c_int64, _dp],
             "limu_odom_adaptive_threshold": [_vp, _dp], "limu_odom_prediction": [_vp, _dp], "limu_odom_has_moved": [_vp, C.POINTER(C.c_int)],
@@ -209,6 +211,11 @@ def _pose(p):
     p = np.ascontiguousarray(p, dtype=np.float64)
     assert p.shape == (7,)
     return p
+
+
+def source_hash() -> str:
+    """Identity of the sources the LOADED library was built from (limu_source_hash)."""
+    return lib().limu_source_hash().decode()
 
 
 def kernel_launches() -> int:
@@ -551,7 +558,7 @@ class KissICP:
     """lidar::KissICP (sensors/lidar/icp.hpp:31-68); config = frame::Lidar::ProcessingInfo fields."""
 
     def __init__(self, ctx, voxel_size=1.0, max_range=100.0, cap=10, deskew=False, min_motion_th=0.1, icp_max_iteration=500,
-                 initial_threshold=2.0, estimation_threshold=1e-4, map_capacity_voxels=0, icp_mode=0):
+                 initial_threshold=2.0, estimation_threshold=1e-4, map_capacity_voxels=0, icp_mode=0, speculate=None):
         self.ctx = ctx
         cfg = OdomConfig()
         lib().limu_odom_default_config(C.byref(cfg))
@@ -565,6 +572,12 @@ class KissICP:
         _chk(lib().limu_odom_create(ctx.h, C.byref(cfg), C.byref(self.h)))
         ctx._children.add(self)
         self.stats = FrameStats()
+        if speculate is not None:
+            self.set_speculate(speculate)
+
+    def set_speculate(self, on: bool):
+        """LIMU_OPT_SPECULATE: enqueue the next scan's deskew + downsampling behind this scan's registration (see limu_cuda.h)."""
+        _chk(lib().limu_odom_set_option(self.h, 1, int(bool(on))))
 
     def close(self):
         if self.h:
@@ -611,16 +624,19 @@ class KissICP:
         assert isinstance(xyzt_f32, np.ndarray) and xyzt_f32.dtype == np.float32 and xyzt_f32.flags.c_contiguous
         _chk(lib().limu_odom_prefetch(self.h, xyzt_f32.ctypes.data_as(_fp), xyzt_f32.size // 4))
 
-    def register_cloud(self, records, stride_bytes, timestamps):
-        """register_frame(cloud, timestamps) on strided point records + float64 timestamps (the reference's layout)."""
-        rec = np.ascontiguousarray(records)
-        ts = np.ascontiguousarray(timestamps, np.float64)
+    def register_cloud(self, records, stride_bytes, timestamps, copy=True):
+        """register_frame(cloud, timestamps) on strided point records + float64 timestamps (the reference's layout).
+        With copy=False the clouds are views into pinned buffers that the next call overwrites."""
+        rec = records if isinstance(records, np.ndarray) and records.flags.c_contiguous else np.ascontiguousarray(records)
+        ts = timestamps if isinstance(timestamps, np.ndarray) and timestamps.dtype == np.float64 and timestamps.flags.c_contiguous else np.ascontiguousarray(timestamps, np.float64)
         n = len(ts)
         pose = np.empty(7)
         down, src = self._out_buffers(n)
         nd, ns = C.c_int64(0), C.c_int64(0)
         _chk(lib().limu_odom_register_cloud(self.h, rec.ctypes.data_as(_vp), int(stride_bytes), _d(ts), n, _d(pose), _d(down), C.byref(nd), _d(src), C.byref(ns), C.byref(self.stats)))
-        return down[: nd.value].copy(), src[: ns.value].copy(), pose
+        if copy:
+            return down[: nd.value].copy(), src[: ns.value].copy(), pose
+        return down[: nd.value], src[: ns.value], pose
 
     def register_msg(self, data, fields, cfg, message_time, scan_count, max_segments=16):
         """lidar_callback -> estimate_lidar_odometry for one PointCloud2 payload: preprocess + register every segment on the

@@ -77,6 +77,10 @@ int limu_ctx_get_profile(limu_ctx *c, double ms[LIMU_NUM_STAGES], int64_t frames
 
 const char *limu_last_error(void) { return g_err; }
 int limu_abi_version(void) { return LIMU_ABI_VERSION; }
+#ifndef LIMU_SOURCE_HASH
+#define LIMU_SOURCE_HASH "unknown"
+#endif
+const char *limu_source_hash(void) { return LIMU_SOURCE_HASH; }
 uint64_t limu_kernel_launches(void) { return g_launches.load(); }
 
 int limu_device_count(void) {

@@ -9,7 +9,7 @@
 
 namespace limu {
 
-constexpr int MBOX_DOUBLES = 2 * 8 * 24;
+constexpr int MBOX_DOUBLES = 4 * 8 * 24;   // MBOX_RING x MBOX_MAX_RANKS x MBOX_ROW (registration.cu)
 
 struct NcclId128 { char b[128]; };   // ncclUniqueId is passed BY VALUE to ncclCommInitRank (nccl.h: char internal[128])
 struct NcclApi {

@@ -74,10 +74,10 @@ struct DevStatus {
 // Multi-GPU exchange state of one rank (comm.cu).
 struct limu_comm {
     int rank = 0, nranks = 1;
-    double *mbox_local = nullptr;          // [2][8][24] doubles in this rank's memory (IPC-exported)
+    double *mbox_local = nullptr;          // [4][8][24] doubles in this rank's memory (IPC-exported)
     double *mbox_peer[8] = {};             // peer mappings of every rank's mailbox ([rank] == mbox_local)
     bool peer_opened[8] = {};
-    unsigned long long stamp_base = 0;     // advances identically on every rank
+    unsigned long long stamp_base = 0;     // exchanges completed so far; advances identically on every rank
     int *d_error = nullptr;                // device flag: a peer timed out
     double *d_state = nullptr;             // NCCL baseline: [0..19] sums, [24..30] E, [32..38] T_icp, [40] done, [41] iter
     void *nccl_lib = nullptr, *nccl_comm = nullptr;

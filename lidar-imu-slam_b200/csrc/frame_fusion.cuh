@@ -11,9 +11,7 @@ struct FrameFusion {
     double *upd_world;
     unsigned int *upd_pslot;
     unsigned long long upd_birth_base;
-#ifdef LIMU_SPECULATIVE_VOXELIZE
     double *twist_out;         // non-null: leave log(last_pose^-1 * new_pose) here for the NEXT scan's deskew (delta_pose, deskew.cpp:14)
     double last_pose[7];       // poses.back() before this scan
-#endif
 };
 }  // namespace limu

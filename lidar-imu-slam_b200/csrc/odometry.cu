@@ -3,6 +3,7 @@
 // device-side counts, ONE host synchronisation per scan (to read the pose the scalar host glue needs:
 // adaptive threshold, constant-velocity prediction -- L/src/sensors/lidar/helpers/threshold.cpp, icp.cpp:138-163).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -67,27 +68,28 @@ struct limu_odom {
     cudaEvent_t pf_done[2] = {nullptr, nullptr};
     const void *pf_host[2] = {nullptr, nullptr};
     int64_t pf_n[2] = {-1, -1};
-    int pf_next = 0;
-#ifdef LIMU_SPECULATIVE_VOXELIZE
-    // Replay speed-up (limu_odom_hint_next_dev): the NEXT scan's deskew + downsampling launch is enqueued right behind this scan's
-    // frame kernel, with its twist left on the device by that kernel, so the host round trip of this scan (result copy, wake-up,
-    // scalar glue, launch) overlaps it instead of idling the GPU.
+    uint64_t pf_seq[2] = {0, 0}, pf_counter = 0;   // order in which the pending uploads were requested
+    // Speculative voxelize (LIMU_OPT_SPECULATE, on by default): when the library knows which scan comes next (a device-pointer hint from
+    // limu_odom_hint_next_dev, or the scan limu_odom_prefetch is uploading) that scan's deskew + downsampling launch is enqueued right
+    // behind this scan's frame kernel, with its deskew twist left on the device by that kernel, so the host round trip of this scan
+    // (result copy, wake-up, scalar glue, launch) overlaps it instead of idling the GPU.
+    bool speculate = true;
     const void *hint_ptr = nullptr;         // next scan (device float4 rows), set by the caller before registering the current one
     int64_t hint_n = 0;
     const void *spec_ptr = nullptr;         // scan whose k_voxelize is already in flight / done
     int64_t spec_n = 0;
     int spec_deskewed = 0;
+    int spec_slot = -1;                     // prefetch slot the speculative launch reads (-1: a caller-owned device buffer)
     limu::DevBuf twist_next;                // 6 doubles written by the frame kernel
     cudaEvent_t frame_done = nullptr;       // recorded after the result copy of the current scan
+    cudaEvent_t spec_launched = nullptr;    // recorded right behind the speculative launch (completes when that kernel has finished)
     cudaEvent_t spec_ev[2] = {nullptr, nullptr};   // device time of the speculative launch, folded into LIMU_STAGE_DOWNSAMPLE one call later
     bool spec_timed = false;
-    // host-pointer entry (limu_odom_register_frame + limu_odom_prefetch): the prefetched scan is the hinted one. This scan's clouds then
-    // leave on the copy stream while the speculative launch runs, so `down` is double-buffered (the launch writes the buffer this scan
-    // does not use); `src` is only rewritten by the NEXT frame kernel, which is launched after the clouds have arrived.
+    // This scan's clouds leave on the copy stream while the speculative launch runs, so `down` is double-buffered (the launch writes the
+    // buffer this scan does not use); `src` is only rewritten by the NEXT frame kernel, which is launched after the clouds have arrived.
     limu::DevBuf down_alt;
     int down_cur = 0;
     cudaEvent_t clouds_done = nullptr;
-#endif
 };
 
 using namespace limu;
@@ -116,7 +118,15 @@ static Pose odom_prediction(const limu_odom *o) {   // icp.cpp:146-154
     return mul(inverse(o->poses[N - 2]), o->poses[N - 1]);
 }
 
-// Everything after the scan is in device memory as doubles (frame_dev, n points).
+static int odom_side_stream(limu_odom *o) {
+    if (!o->copy_stream) {
+        LIMU_CUDA_TRY(cudaStreamCreateWithFlags(&o->copy_stream, cudaStreamNonBlocking));
+        for (int sl = 0; sl < 2; ++sl) LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->pf_done[sl], cudaEventDisableTiming));
+    }
+    return LIMU_OK;
+}
+
+// Everything after the scan is in device memory.
 // Input already in device memory. mode 0: float4 {x,y,z,t}; 1: records `stride` bytes apart + FP64 timestamps; 2: double xyz.
 static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int stride, const double *ts_dev, int64_t n, double pose_out[7], double *down_xyz,
                                 int64_t *n_down, double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
@@ -126,29 +136,33 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     const int deskewed = (mode != 2 && o->cfg.deskew && NP > 2) ? 1 : 0;
     double twist[6] = {0, 0, 0, 0, 0, 0};
     if (deskewed) se3_log(mul(inverse(o->poses[NP - 2]), o->poses[NP - 1]), twist);
-#ifdef LIMU_SPECULATIVE_VOXELIZE
-    // was this scan's k_voxelize already enqueued behind the previous scan (limu_odom_hint_next_dev)? Its outputs live in frame/down/src0:
+    // was this scan's k_voxelize already enqueued behind the previous scan? Its outputs live in frame / src0 / the other `down` buffer:
     // growing those buffers for a larger hinted scan must then keep their contents.
-    const bool spec_hit = mode == 0 && n > 0 && raw_dev == o->spec_ptr && n == o->spec_n && o->spec_deskewed == deskewed;
-    o->spec_ptr = nullptr;
+    const bool spec_hit = mode == 0 && n > 0 && o->spec_ptr && raw_dev == o->spec_ptr && n == o->spec_n && o->spec_deskewed == deskewed;
+    if (o->spec_ptr && !spec_hit && o->spec_slot >= 0 && o->pf_buf[o->spec_slot].p == o->spec_ptr) {
+        // the caller registered something else than the scan it had prefetched: that upload is stale, do not speculate on it again
+        o->pf_host[o->spec_slot] = nullptr; o->pf_n[o->spec_slot] = -1;
+    }
+    o->spec_ptr = nullptr; o->spec_slot = -1;
     if (spec_hit) o->down_cur ^= 1;   // the speculative launch wrote the other `down` buffer
-    // the scan after this one, if the caller told us where it is: a device-pointer hint, or the scan limu_odom_prefetch is uploading
-    const void *next_ptr = o->hint_ptr;
-    int64_t next_n = o->hint_ptr ? o->hint_n : 0;
+    // the scan after this one, if the caller told us where it is: a device-pointer hint, or the OLDEST upload limu_odom_prefetch has pending
+    const void *next_ptr = nullptr;
+    int64_t next_n = 0;
+    int next_slot = -1;
     cudaEvent_t next_ready = nullptr;
-    if (!next_ptr)
-        for (int sl = 0; sl < 2; ++sl)
-            if (o->pf_host[sl] && o->pf_n[sl] > 0) { next_ptr = o->pf_buf[sl].p; next_n = o->pf_n[sl]; next_ready = o->pf_done[sl]; }
+    if (o->speculate && mode == 0) {
+        if (o->hint_ptr) { next_ptr = o->hint_ptr; next_n = o->hint_n; }
+        else {
+            for (int sl = 0; sl < 2; ++sl)
+                if (o->pf_host[sl] && o->pf_n[sl] > 0 && (next_slot < 0 || o->pf_seq[sl] < o->pf_seq[next_slot])) next_slot = sl;
+            if (next_slot >= 0) { next_ptr = o->pf_buf[next_slot].p; next_n = o->pf_n[next_slot]; next_ready = o->pf_done[next_slot]; }
+        }
+    }
     o->hint_ptr = nullptr; o->hint_n = 0;   // a hint is good for one call only
     const size_t nb = (size_t)std::max<int64_t>(std::max<int64_t>(n, next_n), 1) * 24;
     const bool keep = spec_hit;
-    LIMU_TRY(o->down_alt.reserve(nb, c->stream, keep));
+    if (o->speculate || o->down_cur) LIMU_TRY(o->down_alt.reserve(nb, c->stream, keep));
     limu::DevBuf &down_mine = o->down_cur ? o->down_alt : o->down, &down_other = o->down_cur ? o->down : o->down_alt;
-#else
-    const size_t nb = (size_t)std::max<int64_t>(n, 1) * 24;
-    const bool keep = false;
-    limu::DevBuf &down_mine = o->down;
-#endif
     LIMU_TRY(o->frame.reserve(nb, c->stream, keep));
     LIMU_TRY(o->down.reserve(nb, c->stream, keep));
     LIMU_TRY(o->src0.reserve(nb, c->stream, keep));
@@ -157,17 +171,18 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     LIMU_TRY(o->world.reserve(nb, c->stream));
     const int rows = icp_partial_rows(c);
     LIMU_TRY(o->partials.reserve((size_t)2 * rows * 32 * 8 + 256, c->stream));   // 32 doubles per row covers both residual variants
-    int *cnt = reinterpret_cast<int *>(c->d_small.as<double>() + 32);   // [0]=n_down [1]=n_src0 [2]=n_keypoints
+    // [0]=n_down [1]=n_src0 [2]=n_keypoints, [4..7] = the status word of THIS scan's k_voxelize (its own word, so that a speculative
+    // launch is never blamed on the scan before it)
+    int *cnt = reinterpret_cast<int *>(c->d_small.as<double>() + 32);
+    DevStatus *vox_status = reinterpret_cast<DevStatus *>(cnt + 4);
     double *out13 = c->d_small.as<double>() + 40;
     const double v = o->cfg.voxel_size;
 
     // deskew_scan + voxelize's two downsampling stages (icp.cpp:36-47, :126-131): one cooperative launch
-#ifdef LIMU_SPECULATIVE_VOXELIZE
-    if (!spec_hit)
-#endif
-    {
+    if (!spec_hit) {
         LIMU_TRY(prof_begin(c, LIMU_STAGE_DOWNSAMPLE));
-        LIMU_TRY(voxelize_device(c, o->vx, raw_dev, mode, stride, ts_dev, deskewed, twist, n, v, o->frame.as<double>(), down_mine.as<double>(), o->src0.as<double>(), cnt + 0));
+        LIMU_TRY(voxelize_device(c, o->vx, raw_dev, mode, stride, ts_dev, deskewed, twist, n, v, o->frame.as<double>(), down_mine.as<double>(), o->src0.as<double>(), cnt + 0,
+                                 nullptr, vox_status));
         LIMU_TRY(prof_end(c, LIMU_STAGE_DOWNSAMPLE));
     }
     // host scalar glue (icp.cpp:66-71)
@@ -187,26 +202,24 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     fuse.iqr_in = o->src0.as<double>(); fuse.iqr_n = cnt + 1; fuse.iqr_d2 = o->d2.as<double>(); fuse.iqr_out = o->src.as<double>(); fuse.iqr_count = cnt + 2;
     fuse.upd_down = down_mine.as<double>(); fuse.upd_n = cnt + 0; fuse.upd_world = o->world.as<double>(); fuse.upd_pslot = o->map->pslot.as<unsigned int>();
     fuse.upd_birth_base = o->map->birth_base;
-#ifdef LIMU_SPECULATIVE_VOXELIZE
-    const bool speculate = next_ptr && next_n > 0 && mode == 0;
+    const bool speculate = next_ptr && next_n > 0;
     const int next_deskew = (o->cfg.deskew && NP + 1 > 2) ? 1 : 0;   // the gate of icp.cpp:40-46 as the next scan will see it
     fuse.twist_out = nullptr;
+    pose_store(last, fuse.last_pose);
     if (speculate && next_deskew) {
         LIMU_TRY(o->twist_next.reserve(6 * sizeof(double), c->stream));
         fuse.twist_out = o->twist_next.as<double>();
-        pose_store(last, fuse.last_pose);
     }
-#endif
     const int64_t upper_before = o->map->used_upper;
     LIMU_TRY(icp_device(o->map, o->src.as<double>(), o->work.as<double>(), n, cnt + 2, init7, 3.0 * sigma, sigma / 3.0, o->cfg.icp_max_iteration,
                         o->cfg.estimation_threshold, o->partials.as<double>(), (size_t)rows, out13, o->nk_hint, nullptr, nullptr, nullptr, -1, &fuse, o->cfg.icp_mode));
     o->map->birth_base += (uint64_t)n;
+    o->map->used_upper = upper_before + std::max<int64_t>(n, 0);   // safe bound until the exact count arrives (at most one new voxel per point)
 
     // the one synchronisation of the scan
     double *h = static_cast<double *>(c->h_pinned) + 32;
-    // counts [32..39], pose + loop statistics [40..52] and the status word [53..54] in ONE copy
+    // counts + k_voxelize status [32..39], pose + loop statistics [40..52] and the context's status word [53..54] in ONE copy
     LIMU_CUDA_TRY(cudaMemcpyAsync(h, c->d_small.as<double>() + 32, (8 + 13 + 2) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-#ifdef LIMU_SPECULATIVE_VOXELIZE
     if (o->spec_timed) {   // the speculative launch that prepared THIS scan finished long ago: account its device time now
         float ms = 0.f;
         if (c->profiling && cudaEventElapsedTime(&ms, o->spec_ev[0], o->spec_ev[1]) == cudaSuccess) c->stage_ms[LIMU_STAGE_DOWNSAMPLE] += (double)ms;
@@ -215,38 +228,34 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     if (speculate) {
         if (!o->frame_done) {
             LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->frame_done, cudaEventDisableTiming));
+            LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->spec_launched, cudaEventDisableTiming));
             for (int k = 0; k < 2; ++k) LIMU_CUDA_TRY(cudaEventCreate(&o->spec_ev[k]));
         }
         LIMU_CUDA_TRY(cudaEventRecord(o->frame_done, c->stream));
         // stream order: frame kernel (writes twist_next) -> result copy -> [upload of the next scan done] -> k_voxelize of the next scan
-        // (reads twist_next; overwrites frame, src0, the two counts -- dead for this scan -- and the OTHER `down` buffer)
+        // (reads twist_next; overwrites frame, src0, the counts and its status word -- dead for this scan -- and the OTHER `down` buffer)
         if (next_ready) LIMU_CUDA_TRY(cudaStreamWaitEvent(c->stream, next_ready, 0));
         if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->spec_ev[0], c->stream));
         LIMU_TRY(voxelize_device(c, o->vx, next_ptr, 0, 0, nullptr, next_deskew, nullptr, next_n, v, o->frame.as<double>(), down_other.as<double>(),
-                                 o->src0.as<double>(), cnt + 0, next_deskew ? o->twist_next.as<double>() : nullptr));
+                                 o->src0.as<double>(), cnt + 0, next_deskew ? o->twist_next.as<double>() : nullptr, vox_status));
         if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->spec_ev[1], c->stream)); o->spec_timed = true; }
-        o->spec_ptr = next_ptr; o->spec_n = next_n; o->spec_deskewed = next_deskew;
+        LIMU_CUDA_TRY(cudaEventRecord(o->spec_launched, c->stream));
+        o->spec_ptr = next_ptr; o->spec_n = next_n; o->spec_deskewed = next_deskew; o->spec_slot = next_slot;
         LIMU_CUDA_TRY(cudaEventSynchronize(o->frame_done));   // wakes up when the frame kernel and the copy are done; k_voxelize keeps running
     } else {
         LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    }
-#else
-    LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
-#endif
-    {
-        DevStatus st;
-        memcpy(&st, h + 21, sizeof st);
-        LIMU_TRY(status_to_error(c, st));
     }
     LIMU_TRY(prof_collect(c));
     const int *hc = reinterpret_cast<const int *>(h);
     const int64_t nd = hc[0], nk = hc[2];
     const double *ho = h + 8;
     const Pose new_pose = pose_load(ho);
+    // Commit the whole frame -- map bookkeeping, pose history, threshold state -- BEFORE looking at the device status: the frame kernel
+    // has already inserted this scan into the map (points with out-of-range voxel indices were left out by both downsampling and the
+    // insert), so an error return must not leave a map that holds a scan without a pose.
     o->map->used_upper = upper_before + nd;   // exact: at most one new voxel per inserted point
     o->nk_hint = std::max<int64_t>(nk, 256);
     o->nd_hint = std::max<int64_t>(nd, 256);
-
     o->model_deviation = mul(inverse(init), new_pose);   // icp.cpp:78-79
     o->poses.push_back(new_pose);                        // :82
     if (pose_out) pose_store(new_pose, pose_out);
@@ -254,34 +263,35 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     if (n_keypoints) *n_keypoints = nk;
     bool copied = false;
     cudaStream_t cloud_stream = c->stream;
-#ifdef LIMU_SPECULATIVE_VOXELIZE
     if (speculate && ((down_xyz && nd > 0) || (keypoints_xyz && nk > 0))) {
         // the main stream is busy with the next scan's k_voxelize: this scan's clouds leave on the copy stream (everything they read was
         // complete at frame_done, and nothing in flight writes it)
-        if (!o->copy_stream) {
-            LIMU_CUDA_TRY(cudaStreamCreateWithFlags(&o->copy_stream, cudaStreamNonBlocking));
-            for (int sl = 0; sl < 2; ++sl) LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->pf_done[sl], cudaEventDisableTiming));
-        }
+        LIMU_TRY(odom_side_stream(o));
         if (!o->clouds_done) LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->clouds_done, cudaEventDisableTiming));
         cloud_stream = o->copy_stream;
     }
-#endif
     if (down_xyz && nd > 0) { LIMU_CUDA_TRY(cudaMemcpyAsync(down_xyz, down_mine.p, (size_t)nd * 24, cudaMemcpyDeviceToHost, cloud_stream)); copied = true; }
     if (keypoints_xyz && nk > 0) { LIMU_CUDA_TRY(cudaMemcpyAsync(keypoints_xyz, o->src.p, (size_t)nk * 24, cudaMemcpyDeviceToHost, cloud_stream)); copied = true; }
     if (copied) {
-#ifdef LIMU_SPECULATIVE_VOXELIZE
         if (cloud_stream != c->stream) {
             LIMU_CUDA_TRY(cudaEventRecord(o->clouds_done, cloud_stream));
             LIMU_CUDA_TRY(cudaEventSynchronize(o->clouds_done));
-        } else
-#endif
-        LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        } else {
+            LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        }
     }
     if (stats) {
-        stats->n_points = n; stats->n_down = nd; stats->n_keypoints = nk; stats->sigma = sigma; stats->deskewed = deskewed; stats->reserved0 = 0;
+        stats->n_points = n; stats->n_down = nd; stats->n_keypoints = nk; stats->sigma = sigma; stats->deskewed = deskewed; stats->reserved0 = spec_hit ? 1 : 0;
         stats->icp.iterations = (int)ho[7]; stats->icp.converged = (int)ho[8]; stats->icp.last_ncorr = (int64_t)ho[9];
         stats->icp.mean_candidates = nk > 0 ? ho[10] / (double)nk : 0.0;
         stats->icp.miss_fraction = nk > 0 ? ho[11] / (double)nk : 0.0;
+    }
+    {   // device status of this scan: its own k_voxelize word (counts area) and the context's word (frame kernel: insert)
+        DevStatus st, sv;
+        memcpy(&st, h + 21, sizeof st);
+        memcpy(&sv, hc + 4, sizeof sv);
+        st.key_range |= sv.key_range; st.table_full |= sv.table_full;
+        LIMU_TRY(status_to_error(c, st));   // the frame IS registered (see above); the caller learns that points were left out
     }
     return LIMU_OK;
 }
@@ -309,6 +319,7 @@ int limu_odom_create(limu_ctx *c, const limu_odom_config *cfg, limu_odom **out) 
     limu_odom *o = new limu_odom;
     o->ctx = c;
     o->cfg = *cfg;
+    if (const char *e = getenv("LIMU_SPECULATE")) o->speculate = atoi(e) != 0;   // default of LIMU_OPT_SPECULATE (on)
     int64_t capv = cfg->map_capacity_voxels;
     if (capv <= 0) {   // a sensor sees a shell, not a ball: ~ (2 r / v)^2 * 8 voxels is generous for one neighbourhood
         const double side = 2.0 * cfg->max_range / cfg->voxel_size;
@@ -330,12 +341,10 @@ void limu_odom_destroy(limu_odom *o) {
     for (auto *b : bufs) b->release();
     o->vx.release();
     o->pre.release();
-#ifdef LIMU_SPECULATIVE_VOXELIZE
     o->twist_next.release();
     o->down_alt.release();
-    if (o->frame_done) { cudaEventDestroy(o->frame_done); cudaEventDestroy(o->spec_ev[0]); cudaEventDestroy(o->spec_ev[1]); }
+    if (o->frame_done) { cudaEventDestroy(o->frame_done); cudaEventDestroy(o->spec_launched); cudaEventDestroy(o->spec_ev[0]); cudaEventDestroy(o->spec_ev[1]); }
     if (o->clouds_done) cudaEventDestroy(o->clouds_done);
-#endif
     delete o;
 }
 
@@ -345,13 +354,11 @@ int limu_odom_register_frame(limu_odom *o, const float *xyzt, int64_t n, double 
     LIMU_TRY(bind(o->ctx));
     int hit = -1;
     for (int s = 0; s < 2; ++s) if (n > 0 && o->pf_host[s] == xyzt && o->pf_n[s] == n) hit = s;
-#ifdef LIMU_SPECULATIVE_VOXELIZE
-    if (hit >= 0 && o->spec_ptr == o->pf_buf[hit].p && o->spec_n == n) {
+    if (hit >= 0 && o->spec_ptr && o->spec_ptr == o->pf_buf[hit].p && o->spec_n == n) {
         // uploaded ahead of time AND already through k_voxelize (enqueued behind the previous scan): register it where it lies
         o->pf_host[hit] = nullptr; o->pf_n[hit] = -1;
         return odom_register_device(o, o->pf_buf[hit].p, 0, 0, nullptr, n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
     }
-#endif
     if (hit >= 0) {   // uploaded ahead of time by limu_odom_prefetch
         LIMU_CUDA_TRY(cudaStreamWaitEvent(o->ctx->stream, o->pf_done[hit], 0));
         std::swap(o->raw, o->pf_buf[hit]);
@@ -366,20 +373,24 @@ int limu_odom_prefetch(limu_odom *o, const float *xyzt, int64_t n) {
     LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyzt), "limu_odom_prefetch: bad arguments");
     LIMU_TRY(bind(o->ctx));
     if (n == 0) return LIMU_OK;
-    if (!o->copy_stream) {
-        LIMU_CUDA_TRY(cudaStreamCreateWithFlags(&o->copy_stream, cudaStreamNonBlocking));
-        for (int s = 0; s < 2; ++s) LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->pf_done[s], cudaEventDisableTiming));
-    }
+    LIMU_TRY(odom_side_stream(o));
     for (int s = 0; s < 2; ++s) if (o->pf_host[s] == xyzt && o->pf_n[s] == n) return LIMU_OK;   // already in flight
-    int s = o->pf_host[0] == nullptr ? 0 : (o->pf_host[1] == nullptr ? 1 : o->pf_next);
-    o->pf_next = s ^ 1;
+    // a free slot, else the OLDEST pending upload is given up (its scan was evidently never registered)
+    int s = o->pf_host[0] == nullptr ? 0 : (o->pf_host[1] == nullptr ? 1 : (o->pf_seq[0] < o->pf_seq[1] ? 0 : 1));
+    if (o->spec_ptr && o->pf_buf[s].p == o->spec_ptr) {
+        // the speculative k_voxelize of the scan in this slot may still be reading it on the main stream: let it finish, and forget the
+        // speculation (the slot is about to hold a different scan, possibly of the same size)
+        LIMU_CUDA_TRY(cudaEventSynchronize(o->spec_launched));
+        o->spec_ptr = nullptr; o->spec_slot = -1;
+    }
+    o->pf_host[s] = nullptr; o->pf_n[s] = -1;
     if (o->pf_buf[s].bytes < (size_t)n * 16) {   // growing may free a buffer the copy stream still writes: drain it first
         LIMU_CUDA_TRY(cudaStreamSynchronize(o->copy_stream));
         LIMU_TRY(o->pf_buf[s].reserve((size_t)n * 16, o->copy_stream));
     }
     LIMU_CUDA_TRY(cudaMemcpyAsync(o->pf_buf[s].p, xyzt, (size_t)n * 16, cudaMemcpyHostToDevice, o->copy_stream));
     LIMU_CUDA_TRY(cudaEventRecord(o->pf_done[s], o->copy_stream));
-    o->pf_host[s] = xyzt; o->pf_n[s] = n;
+    o->pf_host[s] = xyzt; o->pf_n[s] = n; o->pf_seq[s] = ++o->pf_counter;
     return LIMU_OK;
 }
 
@@ -400,12 +411,8 @@ int limu_odom_register_frame_dev(limu_odom *o, const float *xyzt_dev, int64_t n,
 
 int limu_odom_hint_next_dev(limu_odom *o, const float *xyzt_dev_next, int64_t n_next) {
     LIMU_REQUIRE(o && n_next >= 0, "limu_odom_hint_next_dev: bad arguments");
-#ifdef LIMU_SPECULATIVE_VOXELIZE
-    o->hint_ptr = n_next > 0 ? xyzt_dev_next : nullptr;
-    o->hint_n = n_next > 0 ? n_next : 0;
-#else
-    (void)xyzt_dev_next;   // a hint may be ignored: this build registers every scan start to finish inside its own call
-#endif
+    o->hint_ptr = (o->speculate && n_next > 0) ? xyzt_dev_next : nullptr;   // with LIMU_OPT_SPECULATE off a hint is ignored
+    o->hint_n = (o->speculate && n_next > 0) ? n_next : 0;
     return LIMU_OK;
 }
 
@@ -473,5 +480,21 @@ int limu_odom_has_moved(limu_odom *o, int *out) {
     return LIMU_OK;
 }
 limu_map *limu_odom_map(limu_odom *o) { return o ? o->map : nullptr; }
+
+int limu_odom_set_option(limu_odom *o, int32_t option, int64_t value) {
+    LIMU_REQUIRE(o, "limu_odom_set_option: null handle");
+    if (option == LIMU_OPT_SPECULATE) {
+        LIMU_TRY(bind(o->ctx));
+        if (!value && o->spec_ptr) {   // a launch is in flight for a scan that will now be voxelized again: let it finish first
+            LIMU_CUDA_TRY(cudaStreamSynchronize(o->ctx->stream));
+            o->spec_ptr = nullptr; o->spec_slot = -1;
+        }
+        o->speculate = value != 0;
+        if (!o->speculate) { o->hint_ptr = nullptr; o->hint_n = 0; }
+        return LIMU_OK;
+    }
+    set_error("limu_odom_set_option: unknown option %d", (int)option);
+    return LIMU_ERR_INVALID;
+}
 
 }  // extern "C"

@@ -24,9 +24,11 @@ struct VoxelizeScratch {
 };
 // KissICP::deskew_scan + the two voxel_downsample stages of KissICP::voxelize in one cooperative launch.
 // mode 0: raw = float4 {x,y,z,t}; 1: records `stride` bytes apart + FP64 ts; 2: double xyz (register_frame(Vec3dVector)).
-// twist_dev (only in builds with LIMU_SPECULATIVE_VOXELIZE): read the deskew twist from device memory instead of twist_host.
+// twist_dev (speculative launches, odometry.cu): read the deskew twist from device memory instead of twist_host.
+// own_status: a status word private to this launch (cleared by the kernel itself); nullptr = the context's shared word.
 int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int mode, int stride, const double *ts_dev, int deskew, const double *twist_host,
-                    int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev, const double *twist_dev = nullptr);
+                    int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev, const double *twist_dev = nullptr,
+                    DevStatus *own_status = nullptr);
 
 // deskew.cpp:10-28. twist_dev: 6 doubles (device). out: n x 3 doubles.
 int deskew_device(limu_ctx *c, const float *xyzt_dev, int64_t n, const double *twist_dev, double *out_dev);

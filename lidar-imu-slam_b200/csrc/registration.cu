@@ -25,7 +25,7 @@ constexpr int ICP_BLOCK = 256;
 constexpr int NS = 20;   // 16 sums + ncorr + ncand + nmiss + pad
 constexpr int NSP = 32;  // opt-in point-to-plane variant: 21 (upper triangle of H) + 6 (g) + ncorr + ncand + nmiss + 2 pad
 constexpr int NS_MAX = 32;
-constexpr int MBOX_MAX_RANKS = 8, MBOX_ROW = 24;   // mailbox row: NS doubles + stamp + pad
+constexpr int MBOX_MAX_RANKS = 8, MBOX_ROW = 24, MBOX_RING = 4;   // mailbox row: NS doubles + stamp + pad; ring of 4 exchange slots
 
 }  // namespace limu
 #include "frame_fusion.cuh"
@@ -51,9 +51,11 @@ struct IcpArgs {
     // point-sharded multi-GPU: every rank owns a contiguous shard of the queries and a full replica of
     // the map; per iteration the ranks exchange their NS-double row through peer-mapped mailboxes (NVLink stores).
     int nranks, rank;
-    double *mbox_local;         // [2][MAX_RANKS][MBOX_ROW] in this rank's memory
+    double *mbox_local;         // [MBOX_RING][MAX_RANKS][MBOX_ROW] in this rank's memory
     double *mbox_peer[8];       // the same buffer of every rank (peer mappings; [rank] == mbox_local)
-    unsigned long long stamp_base;   // stamps of this call are stamp_base + iteration + 1 (monotonic across calls)
+    unsigned long long stamp_base;   // exchanges completed by earlier calls: iteration j of this call is exchange number stamp_base + j, its
+                                     // stamp is that number + 1 and its ring slot that number mod MBOX_RING (contiguous ACROSS calls, so a rank
+                                     // that is already in the next call can never overwrite a slot a slower peer is still reading)
     int *comm_error;            // set to 1 if a peer did not show up in time
     // ---- fused frame mode (odometry.cu): optional IQR prologue and local_map.update epilogue in the same launch ----
     const double *iqr_in;       // src0 (after the two downsampling stages); nullptr = no prologue
@@ -73,10 +75,8 @@ struct IcpArgs {
     unsigned int *exit_count;   // last CTA out resets the barrier words (no memset per launch)
     unsigned int *barrier_icp;  // barrier of the leading `icp_blocks` CTAs that run the Gauss-Newton loop
     int icp_blocks;
-#ifdef LIMU_SPECULATIVE_VOXELIZE
     double *twist_out;          // see FrameFusion
     double last_pose[7];
-#endif
     double *est_trace;          // optional [max_iter][7]
     long long *ncorr_trace;     // optional [max_iter]
     double *hg_trace;           // optional [max_iter][42]
@@ -474,8 +474,8 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
             // system-scope release of the stamp; every CTA of every rank then waits for all stamps in its LOCAL mailbox and
             // adds the rows in rank order -- the same order everywhere, so all ranks solve bit-identical normal equations
             // and take identical convergence decisions. No host, no NCCL launch, no second grid barrier.
-            const unsigned long long stamp = A.stamp_base + (unsigned long long)j + 1ull;
-            const size_t par = (size_t)(j & 1) * MBOX_MAX_RANKS * MBOX_ROW;
+            const unsigned long long seq = A.stamp_base + (unsigned long long)j, stamp = seq + 1ull;
+            const size_t par = (size_t)(seq % MBOX_RING) * MBOX_MAX_RANKS * MBOX_ROW;
             if (blockIdx.x == 0) {
                 if (threadIdx.x < NS) {
                     const double v = S[threadIdx.x];
@@ -496,7 +496,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
                     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
                     if (t1 - t0 > 2000000000ull) { *A.comm_error = 1; comm_dead = 1; break; }   // 2 s: a peer never arrived
-                } while (v != stamp);
+                } while (v < stamp);
             }
             __syncthreads();
             if (comm_dead) break;   // every CTA of this rank times out the same way; the host reports LIMU_ERR_COMM
@@ -563,14 +563,12 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const Pose np = run_icp ? mul(pose_load(Ticp), pose_load(Tinit)) : pose_load(Tinit);
         pose_store(np, A.out);
-#ifdef LIMU_SPECULATIVE_VOXELIZE
         if (A.twist_out) {   // the next scan deskews with delta_pose(poses[N-2], poses[N-1]) = log(last^-1 * new): leave it on the device
             double tw[6];
             se3_log(mul(inverse(Pose{A.last_pose[0], A.last_pose[1], A.last_pose[2], A.last_pose[3], A.last_pose[4], A.last_pose[5], A.last_pose[6]}), np), tw);
 #pragma unroll
             for (int k = 0; k < 6; ++k) A.twist_out[k] = tw[k];
         }
-#endif
         A.out[7] = (double)j; A.out[8] = (double)converged; A.out[9] = S[I_NCORR]; A.out[10] = S[I_NCORR + 1]; A.out[11] = S[I_NCORR + 2]; A.out[12] = (double)n;
     }
     if (A.upd_down) {
@@ -586,12 +584,13 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
         for (int64_t base = (int64_t)blockIdx.x * ICP_BLOCK; base < nd; base += gthreads) {   // whole warps stay converged for the ballot
             const int64_t i = base + threadIdx.x;
             bool claimed = false;
+            unsigned int slot = PEND_NONE;
             if (i < nd) {
                 const V3 w = apply(np, V3{A.upd_down[3 * i], A.upd_down[3 * i + 1], A.upd_down[3 * i + 2]});
                 A.upd_world[3 * i] = w.x; A.upd_world[3 * i + 1] = w.y; A.upd_world[3 * i + 2] = w.z;
-                A.upd_pslot[i] = insert_claim_one(A.map, w, (unsigned int)i, A.upd_birth_base, A.status, &claimed);
+                A.upd_pslot[i] = slot = insert_claim_one(A.map, w, (unsigned int)i, A.upd_birth_base, A.status, &claimed);
             }
-            insert_account(claimed, A.upd_counters);
+            insert_account(claimed, slot, A.upd_counters, A.map.live);
         }
         gs.sync();
         FT_MARK(3);
@@ -599,17 +598,19 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
             insert_place_one(A.map, V3{A.upd_world[3 * i], A.upd_world[3 * i + 1], A.upd_world[3 * i + 2]}, (unsigned int)i, __ldcg(A.upd_pslot + i));
         gs.sync();
         FT_MARK(4);
-        // eviction sweep over all C slots: eight independent key loads in flight per thread (the slot array is 16 B/slot)
-        for (int64_t s0 = gtid; s0 < (int64_t)A.upd_capacity; s0 += 8 * gthreads) {
-            unsigned long long keys[8];
+        // eviction sweep (remove_points_from_far, voxel_hash_map.cpp:146-171) over the dense list of voxels (V entries, 4 B + one
+        // 16 B slot each) instead of the C table slots: a scan that evicts nothing used to read the whole 16 MB slot array.
+        const int64_t used = (int64_t)__ldcg(A.upd_counters + 3);
+        for (int64_t i0 = gtid; i0 < used; i0 += 4 * gthreads) {
+            unsigned int sl[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int64_t sidx = s0 + (int64_t)u * gthreads;
-                keys[u] = sidx < (int64_t)A.upd_capacity ? __ldcg(&A.map.slots[sidx].key) : KEY_EMPTY;
+            for (int u = 0; u < 4; ++u) {
+                const int64_t idx = i0 + (int64_t)u * gthreads;
+                sl[u] = idx < used ? __ldcg(A.map.live + idx) : PEND_NONE;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (keys[u] < KEY_TOMB) remove_far_one(A.map, s0 + (int64_t)u * gthreads, np.tx, np.ty, np.tz, A.upd_max_distance, A.upd_counters);
+            for (int u = 0; u < 4; ++u)
+                if (sl[u] != PEND_NONE) remove_far_one(A.map, (int64_t)sl[u], np.tx, np.ty, np.tz, A.upd_max_distance, A.upd_counters);
         }
     }
     FT_MARK(5);
@@ -695,18 +696,15 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
         limu_comm *cm = c->comm;
         A.nranks = cm->nranks; A.rank = cm->rank; A.mbox_local = cm->mbox_local; A.comm_error = cm->d_error;
         for (int r = 0; r < cm->nranks; ++r) A.mbox_peer[r] = cm->mbox_peer[r];
-        A.stamp_base = cm->stamp_base;
-        cm->stamp_base += (unsigned long long)max_iter_all_ranks + 2ull;
+        A.stamp_base = cm->stamp_base;   // advanced by the iterations this call executes once they are known (icp_common)
     }
     if (fuse) {
         A.iqr_in = fuse->iqr_in; A.iqr_n = fuse->iqr_n; A.iqr_d2 = fuse->iqr_d2; A.iqr_out = fuse->iqr_out; A.iqr_count = fuse->iqr_count;
         A.upd_down = fuse->upd_down; A.upd_n = fuse->upd_n; A.upd_world = fuse->upd_world; A.upd_pslot = fuse->upd_pslot;
         A.upd_counters = m->counters.as<unsigned long long>(); A.upd_birth_base = fuse->upd_birth_base;
         A.upd_capacity = (long long)m->capacity; A.upd_max_distance = m->max_distance;
-#ifdef LIMU_SPECULATIVE_VOXELIZE
         A.twist_out = fuse->twist_out;
         for (int k = 0; k < 7; ++k) A.last_pose[k] = fuse->last_pose[k];
-#endif
     }
     void *args[] = {&A};
     LIMU_TRY(prof_begin(c, LIMU_STAGE_ICP));
@@ -797,6 +795,7 @@ static int icp_sharded_nccl(limu_map *m, const double *points_dev, int64_t n, co
     A.map = m->view(); A.points = points_dev; A.work = c->tmp4.as<double>(); A.n_max = n;
     for (int k = 0; k < 7; ++k) A.init_pose[k] = init_guess[k];
     A.tau_sq = tau * tau; A.th = th; A.coop_scan = n >= 32768 ? 1 : 0; A.nranks = 1;
+    A.icp_blocks = grid;   // k_icp_step strides its queries by icp_blocks * ICP_BLOCK (left at 0 this loop never ended: the "NCCL hang" of round 1)
     double *state = cm->d_state;
     double *h = static_cast<double *>(c->h_pinned) + 256;
     int64_t nv = 0;
@@ -853,6 +852,7 @@ static int icp_common(limu_map *m, const double *points_dev, int64_t n, const do
         stats->miss_fraction = sharded ? h[11] : (n > 0 ? h[11] / (double)n : 0.0);
     }
     if (sharded && c->comm && c->comm->nranks > 1) {
+        c->comm->stamp_base += (unsigned long long)iters;   // identical on every rank: all ranks solve the same equations
         int err = 0;
         LIMU_CUDA_TRY(cudaMemcpy(&err, c->comm->d_error, sizeof(int), cudaMemcpyDeviceToHost));
         if (err) { set_error("limu_icp_sharded: a peer rank did not reach the exchange within 2 s"); cudaMemset(c->comm->d_error, 0, sizeof(int)); return LIMU_ERR_COMM; }

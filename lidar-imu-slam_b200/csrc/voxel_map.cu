@@ -23,8 +23,9 @@ static __global__ void __launch_bounds__(256) k_insert_claim(MapView m, const do
     const int64_t n = n_dev ? (int64_t)*n_dev : n_max;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool claimed = false;
-    if (i < n) pslot[i] = insert_claim_one(m, V3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, (unsigned int)i, birth_base, st, &claimed);
-    insert_account(claimed, counters);
+    unsigned int slot = PEND_NONE;
+    if (i < n) pslot[i] = slot = insert_claim_one(m, V3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, (unsigned int)i, birth_base, st, &claimed);
+    insert_account(claimed, slot, counters, m.live);
 }
 
 static __global__ void __launch_bounds__(256) k_insert_place(MapView m, const double *__restrict__ xyz, int64_t n_max, const int *n_dev,
@@ -35,15 +36,15 @@ static __global__ void __launch_bounds__(256) k_insert_place(MapView m, const do
     insert_place_one(m, V3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, (unsigned int)i, pslot[i]);
 }
 
-static __global__ void __launch_bounds__(256) k_remove_far(MapView m, int64_t C, const double *__restrict__ origin, double max_distance,
-                                                          unsigned long long *counters) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= C) return;
-    remove_far_one(m, s, origin[0], origin[1], origin[2], max_distance, counters);
+// Walks the dense live list (one entry per voxel ever created since the last rebuild) instead of the C table slots.
+static __global__ void __launch_bounds__(256) k_remove_far(MapView m, const double *__restrict__ origin, double max_distance, unsigned long long *counters) {
+    const int64_t used = (int64_t)counters[3];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < used; i += (int64_t)gridDim.x * blockDim.x)
+        remove_far_one(m, (int64_t)m.live[i], origin[0], origin[1], origin[2], max_distance, counters);
 }
 
 // Move every live voxel of `old` into the (cleared) table `nw`.
-static __global__ void __launch_bounds__(256) k_rehash(MapView old, int64_t oldC, MapView nw) {
+static __global__ void __launch_bounds__(256) k_rehash(MapView old, int64_t oldC, MapView nw, unsigned long long *new_counters) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= oldC) return;
     const unsigned long long key = old.slots[s].key;
@@ -54,6 +55,7 @@ static __global__ void __launch_bounds__(256) k_rehash(MapView old, int64_t oldC
         if (cur == KEY_EMPTY) break;
         t = (t + 1) & nw.mask;
     }
+    nw.live[atomicAdd(&new_counters[3], 1ull)] = t;   // the rebuilt list holds live voxels only
     const unsigned long long meta = old.slots[s].meta;
     const int count = meta_count(meta);
     nw.slots[t].meta = meta;
@@ -146,8 +148,9 @@ int transform_device(limu_ctx *c, const double *pose_dev, const double *in, doub
 
 int map_alloc(limu_map *m, int64_t C) {
     limu_ctx *c = m->ctx;
-    m->slots.release(); m->pts.release(); m->pend.release();
+    m->slots.release(); m->pts.release(); m->pend.release(); m->live.release();
     LIMU_TRY(m->slots.reserve((size_t)C * sizeof(Slot)));
+    LIMU_TRY(m->live.reserve((size_t)C * 4));
     LIMU_TRY(m->pts.reserve((size_t)C * limu::block_stride(m->cap) * 8));
     LIMU_TRY(m->pend.reserve((size_t)C * m->cap * 4));
     m->capacity = C;
@@ -168,6 +171,7 @@ limu::MapView limu_map::view() const {
     v.slots = slots.as<limu::Slot>();
     v.pts = pts.as<double>();
     v.pend = pend.as<unsigned int>();
+    v.live = live.as<unsigned int>();
     v.mask = (unsigned int)(capacity - 1);
     int lg = 0;
     while ((int64_t(1) << lg) < capacity) ++lg;
@@ -201,22 +205,22 @@ int map_maybe_grow(limu_map *m, int64_t incoming) {
     limu_ctx *c = m->ctx;
     const int64_t newC = std::max<int64_t>(next_pow2((live + incoming) * 4), 1024);
     limu_map old = *m;  // shallow: keeps the old buffers alive
-    m->slots = DevBuf(); m->pts = DevBuf(); m->pend = DevBuf(); m->counters = DevBuf();
+    m->slots = DevBuf(); m->pts = DevBuf(); m->pend = DevBuf(); m->live = DevBuf(); m->counters = DevBuf();
     int st = map_alloc(m, newC);
     if (st != LIMU_OK) {
-        m->slots.release(); m->pts.release(); m->pend.release(); m->counters.release();
-        m->slots = old.slots; m->pts = old.pts; m->pend = old.pend; m->counters = old.counters;
+        m->slots.release(); m->pts.release(); m->pend.release(); m->live.release(); m->counters.release();
+        m->slots = old.slots; m->pts = old.pts; m->pend = old.pend; m->live = old.live; m->counters = old.counters;
         m->capacity = old.capacity;
         set_error("voxel map cannot grow to %lld slots", (long long)newC);
         return LIMU_ERR_MAP_FULL;
     }
-    k_rehash<<<div_up(old.capacity, 256), 256, 0, c->stream>>>(old.view(), old.capacity, m->view());
+    k_rehash<<<div_up(old.capacity, 256), 256, 0, c->stream>>>(old.view(), old.capacity, m->view(), m->counters.as<unsigned long long>());
     LIMU_LAUNCHED();
     unsigned long long *h = static_cast<unsigned long long *>(c->h_pinned);
-    h[0] = (unsigned long long)live; h[1] = 0; h[2] = 0; h[3] = (unsigned long long)live;
-    LIMU_CUDA_TRY(cudaMemcpyAsync(m->counters.p, h, 4 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+    h[0] = (unsigned long long)live; h[1] = 0; h[2] = 0;   // [3] (used slots = length of the live list) was counted by k_rehash itself
+    LIMU_CUDA_TRY(cudaMemcpyAsync(m->counters.p, h, 3 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
     LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    old.slots.release(); old.pts.release(); old.pend.release(); old.counters.release();
+    old.slots.release(); old.pts.release(); old.pend.release(); old.live.release(); old.counters.release();
     old.pslot = DevBuf(); old.world = DevBuf();  // still owned by *m
     m->used_upper = live;
     return LIMU_OK;
@@ -241,8 +245,8 @@ int map_insert_device(limu_map *m, const double *xyz_dev, int64_t n, const int *
 
 int map_remove_far_device(limu_map *m, const double *origin_dev3) {
     limu_ctx *c = m->ctx;
-    k_remove_far<<<div_up(m->capacity, 256), 256, 0, c->stream>>>(m->view(), m->capacity, origin_dev3, m->max_distance,
-                                                               m->counters.as<unsigned long long>());
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(div_up(std::max<int64_t>(m->used_upper, 1), 256), (int64_t)c->sm_count * 8));
+    k_remove_far<<<blocks, 256, 0, c->stream>>>(m->view(), origin_dev3, m->max_distance, m->counters.as<unsigned long long>());
     LIMU_LAUNCHED();
     return LIMU_OK;
 }
@@ -286,7 +290,7 @@ void limu_map_destroy(limu_map *m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
-    m->slots.release(); m->pts.release(); m->pend.release(); m->counters.release();
+    m->slots.release(); m->pts.release(); m->pend.release(); m->live.release(); m->counters.release();
     m->pslot.release(); m->world.release();
     delete m;
 }

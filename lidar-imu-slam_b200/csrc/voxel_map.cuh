@@ -11,6 +11,9 @@
 //                          x[capp] y[capp] z[capp] at pts + s*3*capp (capp = cap rounded up to 4 doubles = one 32 B
 //                          sector), so eight lanes reading ranks r..r+7 of one row fetch 64 contiguous bytes
 //   pend[C*cap]      4 B  per point slot: insert scratch (sorted pending input indices), all-ones at rest
+//   live[C]          4 B  dense list of the slots that ever became a voxel since the last rebuild (append order; an
+//                          erased voxel leaves its entry behind and its slot reads KEY_TOMB): the eviction sweep
+//                          walks this list (V entries) instead of the C table slots. Length = counters[3].
 //
 // One 16-byte load answers "is this my voxel, how many points does it hold, and how old is it"; the points
 // of a voxel are contiguous (capp*24 B), so a query touches 1 + 3*ceil(8*count/32) sectors.
@@ -38,6 +41,7 @@ struct MapView {
     Slot *slots;
     double *pts;
     unsigned int *pend;
+    unsigned int *live;  // dense list of used slots (live + erased), counters[3] entries
     unsigned int mask;   // C - 1
     int shift;           // 64 - log2(C)
     int cap;
@@ -71,7 +75,11 @@ __device__ __forceinline__ unsigned int slot_of(unsigned long long key, int shif
     return (unsigned int)((key * 0x9E3779B97F4A7C15ull) >> shift);
 }
 
-__device__ __forceinline__ ulonglong2 load_slot(const Slot *s) { return __ldg(reinterpret_cast<const ulonglong2 *>(s)); }
+// Map data is read with plain (coherent, L1-cached) loads, not ld.global.nc: the fused frame kernel WRITES slots and points
+// in its insert / eviction epilogue after the Gauss-Newton loop has read them, so the read-only-for-the-kernel-lifetime
+// contract of the non-coherent path does not hold there.
+__device__ __forceinline__ ulonglong2 load_slot(const Slot *s) { return *reinterpret_cast<const ulonglong2 *>(s); }
+__device__ __forceinline__ double ldm(const double *p) { return *p; }
 
 // Read-only lookup. Returns slot index or -1; count of the voxel in *count.
 __device__ __forceinline__ int map_find(const MapView &m, unsigned long long key, int *count) {
@@ -108,7 +116,7 @@ __device__ __forceinline__ void block_closest(const MapView &m, int slot, int co
     for (int base = 0; base < count; base += 4) {   // rows are padded to a multiple of 4, so the loads stay in bounds
         double cx[4], cy[4], cz[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { cx[k] = __ldg(bx + base + k); cy[k] = __ldg(by + base + k); cz[k] = __ldg(bz + base + k); }
+        for (int k = 0; k < 4; ++k) { cx[k] = ldm(bx + base + k); cy[k] = ldm(by + base + k); cz[k] = ldm(bz + base + k); }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const double d = sqnorm3(p.x - cx[k], p.y - cy[k], p.z - cz[k]);
@@ -250,7 +258,7 @@ __device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, un
 #pragma unroll
         for (int k = 0; k < 2; ++k) {   // ranks l8 and l8+8 in one go (covers cap <= 16); out-of-range ranks re-read rank l8
             const int r = l8 + 8 * k, rr = r < count ? r : l8;
-            x[k] = __ldg(bx + rr); y[k] = __ldg(by + rr); z[k] = __ldg(bz + rr);
+            x[k] = ldm(bx + rr); y[k] = ldm(by + rr); z[k] = ldm(bz + rr);
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -259,7 +267,7 @@ __device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, un
             if (r < count && d < bd2) { bd2 = d; br = r; }
         }
         for (int r = l8 + 16; r < count; r += 8) {
-            const double d = sqnorm3(p.x - __ldg(bx + r), p.y - __ldg(by + r), p.z - __ldg(bz + r));
+            const double d = sqnorm3(p.x - ldm(bx + r), p.y - ldm(by + r), p.z - ldm(bz + r));
             if (d < bd2) { bd2 = d; br = r; }
         }
     }
@@ -302,7 +310,7 @@ __device__ __forceinline__ Nearest map_closest27(const MapView &m, const V3 &p) 
             const int count = meta_count(v.y);
             const double *bx = voxel_rows(m, s), *by = bx + m.capp, *bz = by + m.capp;
             for (int k = 0; k < count; ++k) {
-                const double cx = __ldg(bx + k), cy = __ldg(by + k), cz = __ldg(bz + k);
+                const double cx = ldm(bx + k), cy = ldm(by + k), cz = ldm(bz + k);
                 const double d = sqnorm3(p.x - cx, p.y - cy, p.z - cz);
                 if (d < best) { best = d; r.rank = k; r.slot = (int)s; r.x = cx; r.y = cy; r.z = cz; }
             }
@@ -342,7 +350,7 @@ __device__ __forceinline__ void group8_closest27(const MapView &m, const V3 &p, 
                 const int count = meta_count(v.y);
                 const double *bx = voxel_rows(m, s), *by = bx + m.capp, *bz = by + m.capp;
                 for (int k = 0; k < count; ++k) {   // cells and ranks are visited in increasing order: strict '<' keeps the first minimum
-                    const double d = sqnorm3(p.x - __ldg(bx + k), p.y - __ldg(by + k), p.z - __ldg(bz + k));
+                    const double d = sqnorm3(p.x - ldm(bx + k), p.y - ldm(by + k), p.z - ldm(bz + k));
                     if (d < bd2) { bd2 = d; bc = c; br = k; bslot = (int)s; }
                 }
                 ncand += count;
@@ -371,11 +379,11 @@ __device__ __forceinline__ int voxel_normal(const MapView &m, int slot, int c, d
     if (c < PLANE_MIN_POINTS) return 0;
     const double *bx = voxel_rows(m, (unsigned int)slot), *by = bx + m.capp, *bz = by + m.capp;
     double mx = 0.0, my = 0.0, mz = 0.0;
-    for (int r = 0; r < c; ++r) { mx += __ldg(bx + r); my += __ldg(by + r); mz += __ldg(bz + r); }
+    for (int r = 0; r < c; ++r) { mx += ldm(bx + r); my += ldm(by + r); mz += ldm(bz + r); }
     mx /= (double)c; my /= (double)c; mz /= (double)c;
     double a00 = 0.0, a01 = 0.0, a02 = 0.0, a11 = 0.0, a12 = 0.0, a22 = 0.0;
     for (int r = 0; r < c; ++r) {
-        const double dx = __ldg(bx + r) - mx, dy = __ldg(by + r) - my, dz = __ldg(bz + r) - mz;
+        const double dx = ldm(bx + r) - mx, dy = ldm(by + r) - my, dz = ldm(bz + r) - mz;
         a00 += dx * dx; a01 += dx * dy; a02 += dx * dz; a11 += dy * dy; a12 += dy * dz; a22 += dz * dz;
     }
     double v00 = 1.0, v01 = 0.0, v02 = 0.0, v10 = 0.0, v11 = 1.0, v12 = 0.0, v20 = 0.0, v21 = 0.0, v22 = 1.0;
@@ -426,7 +434,7 @@ __device__ __forceinline__ int voxel_normal(const MapView &m, int slot, int c, d
 __device__ __forceinline__ unsigned int insert_claim_one(const MapView &m, const V3 &p, unsigned int i, unsigned long long birth_base, DevStatus *st, bool *claimed) {
     const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
     unsigned int slot = PEND_NONE;
-    if (!key_in_range(kx, ky, kz)) { st->key_range = 1; return slot; }
+    if (!key_in_range(kx, ky, kz) || p.x != p.x || p.y != p.y || p.z != p.z) { st->key_range = 1; return slot; }   // NaN -> INT_MIN in the reference
     const unsigned long long key = pack_key(kx, ky, kz);
     unsigned int s = slot_of(key, m.shift);
     for (unsigned int probes = 0; probes <= m.mask; ++probes) {
@@ -451,13 +459,19 @@ __device__ __forceinline__ unsigned int insert_claim_one(const MapView &m, const
     }
     return slot;
 }
-// warp-aggregated occupancy accounting (call with the whole warp converged)
-__device__ __forceinline__ void insert_account(bool claimed, unsigned long long *counters) {
+// warp-aggregated occupancy accounting + append of the new voxels' slots to the dense live list (call with the whole
+// warp converged; `slot` is what insert_claim_one returned)
+__device__ __forceinline__ void insert_account(bool claimed, unsigned int slot, unsigned long long *counters, unsigned int *live) {
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, claimed);
-    if ((threadIdx.x & 31) == 0 && bal) {
-        atomicAdd(&counters[0], (unsigned long long)__popc(bal));  // live voxels
-        atomicAdd(&counters[3], (unsigned long long)__popc(bal));  // used slots (live + tombstones)
+    if (!bal) return;   // warp-uniform
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) {
+        atomicAdd(&counters[0], (unsigned long long)__popc(bal));          // live voxels
+        base = atomicAdd(&counters[3], (unsigned long long)__popc(bal));   // used slots (live + tombstones) = length of the live list
     }
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (claimed) live[base + (unsigned long long)__popc(bal & ((1u << lane) - 1u))] = slot;
 }
 // Pass 2: the point looks for its own index in its voxel's pending list; position r IS its storage rank (the list
 // started at the old count). Winners store their coordinates and clear the entry.
@@ -514,7 +528,7 @@ struct limu_map {
     double vox_size = 1.0, max_distance = 100.0;
     int cap = 10;
     int64_t capacity = 0;          // C (slots), power of two
-    limu::DevBuf slots, pts, pend;
+    limu::DevBuf slots, pts, pend, live;
     limu::DevBuf counters;         // device: [0] n_live voxels, [1] n_tomb, [2] n_points, [3] n_used (live + tomb)
     uint64_t birth_base = 0;       // creation sequence offset of the next insert batch
     int64_t used_upper = 0;        // host upper bound on live + tomb slots

@@ -24,9 +24,7 @@ struct VoxelizeArgs {
     const double *ts;
     int mode, stride, deskew;
     double twist[6];            // by value, read when deskew != 0
-#ifdef LIMU_SPECULATIVE_VOXELIZE
     const double *twist_dev;    // non-null: the twist was left in device memory by the previous scan's frame kernel (speculative launch)
-#endif
     int64_t n;
     double vs1, vs2;            // 0.5 v and 1.5 v (icp.cpp:129-130)
     double *frame, *down, *src0;
@@ -38,12 +36,14 @@ struct VoxelizeArgs {
     int *counts;                // [0] n_down, [1] n_src0
     unsigned int *barrier;      // [0] grid barrier, [1] exit counter; zero at rest (the last CTA out re-arms them, no memset per launch)
     DevStatus *st;
+    int clear_status;           // 1: `st` is this launch's own status word (odometry.cu) and starts out clean
 };
 
 __device__ __forceinline__ unsigned int claim_min(unsigned long long *keys, unsigned int *minidx, unsigned int mask, int shift, const V3 &p, double vs,
                                                   unsigned int index, DevStatus *st) {
     const int kx = vox_index(p.x, vs), ky = vox_index(p.y, vs), kz = vox_index(p.z, vs);
-    if (!key_in_range(kx, ky, kz)) { st->key_range = 1; return PEND_NONE; }
+    // NaN: the reference's (int) cast gives INT_MIN on x86-64 (cvttsd2si), far outside the packed range; cvt.rzi gives 0
+    if (!key_in_range(kx, ky, kz) || p.x != p.x || p.y != p.y || p.z != p.z) { st->key_range = 1; return PEND_NONE; }
     const unsigned long long key = pack_key(kx, ky, kz);
     unsigned int s = slot_of(key, shift);
     for (unsigned int probes = 0; probes <= mask; ++probes) {
@@ -87,6 +87,7 @@ static __global__ void __launch_bounds__(VX_BLOCK, 4) k_voxelize(const VoxelizeA
         const int64_t w1 = (int64_t)A.mask1 + 1, w2 = (int64_t)A.mask2 + 1;
         for (int64_t i = gtid; i < w1; i += gthreads) { A.keys1[i] = KEY_EMPTY; A.min1[i] = PEND_NONE; }
         for (int64_t i = gtid; i < w2; i += gthreads) { A.keys2[i] = KEY_EMPTY; A.min2[i] = PEND_NONE; }
+        if (gtid == 0 && A.clear_status) *A.st = DevStatus{0, 0, {0, 0}};
     }
     gs.sync();
     // P1: frame[i] = deskewed / widened point (icp.cpp:36-47, deskew.cpp:18-26); stage-1 claim at 0.5 v
@@ -95,12 +96,10 @@ static __global__ void __launch_bounds__(VX_BLOCK, 4) k_voxelize(const VoxelizeA
         if (A.deskew) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) tw[k] = A.twist[k];
-#ifdef LIMU_SPECULATIVE_VOXELIZE
             if (A.twist_dev) {
 #pragma unroll
                 for (int k = 0; k < 6; ++k) tw[k] = __ldcg(A.twist_dev + k);
             }
-#endif
         }
         for (int64_t i = gtid; i < n; i += gthreads) {
             V3 p;
@@ -197,8 +196,12 @@ static int64_t pow2_slots(int64_t n) { int64_t p = 1024; while (p < 2 * n) p <<=
 
 // Enqueue the fused kernel. raw/ts/twist are device pointers; outputs: frame (n x 3), down, src0, counts[0..1].
 int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int mode, int stride, const double *ts_dev, int deskew, const double *twist_host,
-                    int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev, const double *twist_dev) {
-    if (n <= 0) { LIMU_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int), c->stream)); return LIMU_OK; }
+                    int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev, const double *twist_dev, DevStatus *own_status) {
+    if (n <= 0) {
+        LIMU_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int), c->stream));
+        if (own_status) LIMU_CUDA_TRY(cudaMemsetAsync(own_status, 0, sizeof(DevStatus), c->stream));
+        return LIMU_OK;
+    }
     if (g_vx_blocks_per_sm == 0) {
         int b = 0;
         LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_voxelize, VX_BLOCK, 0));
@@ -218,11 +221,7 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     VoxelizeArgs A;
     A.raw = raw_dev; A.ts = ts_dev; A.mode = mode; A.stride = stride; A.deskew = deskew; A.n = n;
     for (int k = 0; k < 6; ++k) A.twist[k] = (deskew && twist_host) ? twist_host[k] : 0.0;
-#ifdef LIMU_SPECULATIVE_VOXELIZE
     A.twist_dev = deskew ? twist_dev : nullptr;
-#else
-    (void)twist_dev;
-#endif
     A.vs1 = v * 0.5; A.vs2 = v * 1.5;
     A.frame = frame_dev; A.down = down_dev; A.src0 = src0_dev;
     A.keys1 = sc.table.as<unsigned long long>();
@@ -234,7 +233,8 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     A.barrier = sc.tiles.as<unsigned int>();
     A.tile1 = sc.tiles.as<int>() + 16; A.tile2 = A.tile1 + ntiles;
     A.counts = counts_dev;
-    A.st = c->d_status;
+    A.st = own_status ? own_status : c->d_status;
+    A.clear_status = own_status ? 1 : 0;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->sm_count * g_vx_blocks_per_sm);
     void *args[] = {&A};
     LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize, dim3(grid), dim3(VX_BLOCK), args, 0, c->stream));
