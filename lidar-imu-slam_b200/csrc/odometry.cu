@@ -83,8 +83,9 @@ struct limu_odom {
     limu::DevBuf twist_next;                // 6 doubles written by the frame kernel
     cudaEvent_t frame_done = nullptr;       // recorded after the result copy of the current scan
     cudaEvent_t spec_launched = nullptr;    // recorded right behind the speculative launch (completes when that kernel has finished)
-    cudaEvent_t spec_ev[2] = {nullptr, nullptr};   // device time of the speculative launch, folded into LIMU_STAGE_DOWNSAMPLE one call later
+    cudaEvent_t spec_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // device time of the speculative launch (two pairs, alternating), folded into LIMU_STAGE_DOWNSAMPLE one call later
     bool spec_timed = false;
+    int spec_par = 0;
     // This scan's clouds leave on the copy stream while the speculative launch runs, so `down` is double-buffered (the launch writes the
     // buffer this scan does not use); `src` is only rewritten by the NEXT frame kernel, which is launched after the clouds have arrived.
     limu::DevBuf down_alt;
@@ -220,30 +221,35 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     double *h = static_cast<double *>(c->h_pinned) + 32;
     // counts + k_voxelize status [32..39], pose + loop statistics [40..52] and the context's status word [53..54] in ONE copy
     LIMU_CUDA_TRY(cudaMemcpyAsync(h, c->d_small.as<double>() + 32, (8 + 13 + 2) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (o->spec_timed) {   // the speculative launch that prepared THIS scan finished long ago: account its device time now
-        float ms = 0.f;
-        if (c->profiling && cudaEventElapsedTime(&ms, o->spec_ev[0], o->spec_ev[1]) == cudaSuccess) c->stage_ms[LIMU_STAGE_DOWNSAMPLE] += (double)ms;
-        o->spec_timed = false;
-    }
+    // device time of the speculative launch that prepared THIS scan (recorded one call ago into the event pair `spec_par`): read after this
+    // scan's sync, when it is certainly complete; the launch made below uses the other pair
+    const int acct = o->spec_timed ? o->spec_par : -1;
+    o->spec_timed = false;
     if (speculate) {
         if (!o->frame_done) {
             LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->frame_done, cudaEventDisableTiming));
             LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->spec_launched, cudaEventDisableTiming));
-            for (int k = 0; k < 2; ++k) LIMU_CUDA_TRY(cudaEventCreate(&o->spec_ev[k]));
+            for (int k = 0; k < 4; ++k) LIMU_CUDA_TRY(cudaEventCreate(&o->spec_ev[k >> 1][k & 1]));
         }
         LIMU_CUDA_TRY(cudaEventRecord(o->frame_done, c->stream));
         // stream order: frame kernel (writes twist_next) -> result copy -> [upload of the next scan done] -> k_voxelize of the next scan
         // (reads twist_next; overwrites frame, src0, the counts and its status word -- dead for this scan -- and the OTHER `down` buffer)
         if (next_ready) LIMU_CUDA_TRY(cudaStreamWaitEvent(c->stream, next_ready, 0));
-        if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->spec_ev[0], c->stream));
+        const int par = o->spec_par ^ 1;
+        if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->spec_ev[par][0], c->stream));
         LIMU_TRY(voxelize_device(c, o->vx, next_ptr, 0, 0, nullptr, next_deskew, nullptr, next_n, v, o->frame.as<double>(), down_other.as<double>(),
                                  o->src0.as<double>(), cnt + 0, next_deskew ? o->twist_next.as<double>() : nullptr, vox_status));
-        if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->spec_ev[1], c->stream)); o->spec_timed = true; }
+        if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->spec_ev[par][1], c->stream)); o->spec_timed = true; o->spec_par = par; }
         LIMU_CUDA_TRY(cudaEventRecord(o->spec_launched, c->stream));
         o->spec_ptr = next_ptr; o->spec_n = next_n; o->spec_deskewed = next_deskew; o->spec_slot = next_slot;
         LIMU_CUDA_TRY(cudaEventSynchronize(o->frame_done));   // wakes up when the frame kernel and the copy are done; k_voxelize keeps running
     } else {
         LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    if (acct >= 0 && c->profiling) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, o->spec_ev[acct][0], o->spec_ev[acct][1]) == cudaSuccess) c->stage_ms[LIMU_STAGE_DOWNSAMPLE] += (double)ms;
+        else (void)cudaGetLastError();
     }
     LIMU_TRY(prof_collect(c));
     const int *hc = reinterpret_cast<const int *>(h);
@@ -343,7 +349,7 @@ void limu_odom_destroy(limu_odom *o) {
     o->pre.release();
     o->twist_next.release();
     o->down_alt.release();
-    if (o->frame_done) { cudaEventDestroy(o->frame_done); cudaEventDestroy(o->spec_launched); cudaEventDestroy(o->spec_ev[0]); cudaEventDestroy(o->spec_ev[1]); }
+    if (o->frame_done) { cudaEventDestroy(o->frame_done); cudaEventDestroy(o->spec_launched); for (int k = 0; k < 4; ++k) cudaEventDestroy(o->spec_ev[k >> 1][k & 1]); }
     if (o->clouds_done) cudaEventDestroy(o->clouds_done);
     delete o;
 }
