@@ -362,6 +362,50 @@ __device__ unsigned long long g_frame_marks[16];
 #define FT_MARK(k) do {} while (0)
 #endif
 
+// local_map.update(down_sampled, new_pose) (icp.cpp:81; voxel_hash_map.cpp:138-144) inside a frame kernel: transform + capped ordered insert
+// (two passes separated by a grid barrier) + eviction around the new position. Every CTA of the grid takes part (those that sat out the
+// Gauss-Newton loop join here); everybody reads the new pose that CTA 0 published in A.out. E: 7 doubles of shared memory.
+template <int BLOCK>
+__device__ __forceinline__ void frame_update_epilogue(const IcpArgs &A, GridSync &gs, double *E) {
+    gs.sync();
+    if (threadIdx.x < 7) E[threadIdx.x] = __ldcg(A.out + threadIdx.x);
+    __syncthreads();
+    const Pose np = pose_load(E);
+    const int64_t nd = (int64_t)__ldcg(A.upd_n);
+    const int64_t gtid = (int64_t)blockIdx.x * BLOCK + threadIdx.x, gthreads = (int64_t)gridDim.x * BLOCK;
+    for (int64_t base = (int64_t)blockIdx.x * BLOCK; base < nd; base += gthreads) {   // whole warps stay converged for the ballot
+        const int64_t i = base + threadIdx.x;
+        bool claimed = false;
+        unsigned int slot = PEND_NONE;
+        if (i < nd) {
+            const V3 w = apply(np, V3{A.upd_down[3 * i], A.upd_down[3 * i + 1], A.upd_down[3 * i + 2]});
+            A.upd_world[3 * i] = w.x; A.upd_world[3 * i + 1] = w.y; A.upd_world[3 * i + 2] = w.z;
+            A.upd_pslot[i] = slot = insert_claim_one(A.map, w, (unsigned int)i, A.upd_birth_base, A.status, &claimed);
+        }
+        insert_account(claimed, slot, A.upd_counters, A.map.live);
+    }
+    gs.sync();
+    FT_MARK(3);
+    for (int64_t i = gtid; i < nd; i += gthreads)
+        insert_place_one(A.map, V3{A.upd_world[3 * i], A.upd_world[3 * i + 1], A.upd_world[3 * i + 2]}, (unsigned int)i, __ldcg(A.upd_pslot + i));
+    gs.sync();
+    FT_MARK(4);
+    // eviction (remove_points_from_far, voxel_hash_map.cpp:146-171) over the dense list of voxels (V entries, 4 B + one 16 B slot each)
+    // instead of the C table slots: a scan that evicts nothing used to read the whole 16 MB slot array.
+    const int64_t used = (int64_t)__ldcg(A.upd_counters + 3);
+    for (int64_t i0 = gtid; i0 < used; i0 += 4 * gthreads) {
+        unsigned int sl[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t idx = i0 + (int64_t)u * gthreads;
+            sl[u] = idx < used ? __ldcg(A.map.live + idx) : PEND_NONE;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (sl[u] != PEND_NONE) remove_far_one(A.map, (int64_t)sl[u], np.tx, np.ty, np.tz, A.upd_max_distance, A.upd_counters);
+    }
+}
+
 // SHAPE 0 = latency build (eight lanes per query, a few thousand keypoints: one CTA per SM at most, so the compiler may
 // use up to 255 registers and the serial Gauss-Newton solve stays out of local memory); SHAPE 1 = bandwidth build
 // (one lane per query + cooperative scan, 64 registers -> 4 CTAs/SM for the HBM-bound kernel mode).
@@ -571,48 +615,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
         }
         A.out[7] = (double)j; A.out[8] = (double)converged; A.out[9] = S[I_NCORR]; A.out[10] = S[I_NCORR + 1]; A.out[11] = S[I_NCORR + 2]; A.out[12] = (double)n;
     }
-    if (A.upd_down) {
-        // local_map.update(down_sampled, new_pose) (icp.cpp:81; voxel_hash_map.cpp:138-144): transform + capped ordered insert
-        // (two passes separated by a grid barrier) + eviction sweep around the new position. The CTAs that sat out the
-        // Gauss-Newton loop join here; everybody reads the new pose that CTA 0 published.
-        gs.sync();
-        if (threadIdx.x < 7) E[threadIdx.x] = __ldcg(A.out + threadIdx.x);
-        __syncthreads();
-        const Pose np = pose_load(E);
-        const int64_t nd = (int64_t)__ldcg(A.upd_n);
-        const int64_t gtid = (int64_t)blockIdx.x * ICP_BLOCK + threadIdx.x, gthreads = (int64_t)gridDim.x * ICP_BLOCK;
-        for (int64_t base = (int64_t)blockIdx.x * ICP_BLOCK; base < nd; base += gthreads) {   // whole warps stay converged for the ballot
-            const int64_t i = base + threadIdx.x;
-            bool claimed = false;
-            unsigned int slot = PEND_NONE;
-            if (i < nd) {
-                const V3 w = apply(np, V3{A.upd_down[3 * i], A.upd_down[3 * i + 1], A.upd_down[3 * i + 2]});
-                A.upd_world[3 * i] = w.x; A.upd_world[3 * i + 1] = w.y; A.upd_world[3 * i + 2] = w.z;
-                A.upd_pslot[i] = slot = insert_claim_one(A.map, w, (unsigned int)i, A.upd_birth_base, A.status, &claimed);
-            }
-            insert_account(claimed, slot, A.upd_counters, A.map.live);
-        }
-        gs.sync();
-        FT_MARK(3);
-        for (int64_t i = gtid; i < nd; i += gthreads)
-            insert_place_one(A.map, V3{A.upd_world[3 * i], A.upd_world[3 * i + 1], A.upd_world[3 * i + 2]}, (unsigned int)i, __ldcg(A.upd_pslot + i));
-        gs.sync();
-        FT_MARK(4);
-        // eviction sweep (remove_points_from_far, voxel_hash_map.cpp:146-171) over the dense list of voxels (V entries, 4 B + one
-        // 16 B slot each) instead of the C table slots: a scan that evicts nothing used to read the whole 16 MB slot array.
-        const int64_t used = (int64_t)__ldcg(A.upd_counters + 3);
-        for (int64_t i0 = gtid; i0 < used; i0 += 4 * gthreads) {
-            unsigned int sl[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t idx = i0 + (int64_t)u * gthreads;
-                sl[u] = idx < used ? __ldcg(A.map.live + idx) : PEND_NONE;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (sl[u] != PEND_NONE) remove_far_one(A.map, (int64_t)sl[u], np.tx, np.ty, np.tz, A.upd_max_distance, A.upd_counters);
-        }
-    }
+    if (A.upd_down) frame_update_epilogue<ICP_BLOCK>(A, gs, E);
     FT_MARK(5);
     // the last CTA out re-arms the barrier for the next launch
     __syncthreads();

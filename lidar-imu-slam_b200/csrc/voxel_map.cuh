@@ -280,6 +280,99 @@ __device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, un
     slot_out = slot; count_out = count; d2_out = bd2; rank_out = br == 0x7FFFFFFF ? -1 : br;
 }
 
+// Pair-cooperative lookup for the cluster latency shape (registration.cu, k_frame_cluster): TWO lanes serve one query, so that one
+// 16-CTA cluster covers a whole keypoint cloud in a single pass. The common case -- the query's own voxel exists and sits in its home
+// slot (the pipeline's table is sparse: ~6 % load) -- costs ONE L2 round trip: the home slot and this lane's candidate ranks l2, l2+2, ...
+// of the home slot's block are requested together, before the key comparison can say whether they will be used. A displaced or absent
+// voxel falls back to dependent loads: linear probing, or the 26-cell fallback of get_closest_neighbour with 13 cells per lane.
+// Same decisions as map_locate + block_closest: first minimum in storage order wins (lexicographic minimum of (d^2, rank)).
+// Every lane of the warp must call this (the pair exchanges are warp-wide shuffles); lanes without a query pass any point and ignore the result.
+template <int ROUNDS>
+__device__ __forceinline__ void pair_load_candidates(const MapView &m, unsigned int slot, int l2, double *cx, double *cy, double *cz) {
+    const double *bx = voxel_rows(m, slot), *by = bx + m.capp, *bz = by + m.capp;
+#pragma unroll
+    for (int k = 0; k < ROUNDS; ++k) {   // ranks beyond the row re-read rank l2 (always inside the block) and are ignored by the caller
+        const int r = l2 + 2 * k, rr = r < m.capp ? r : l2;
+        cx[k] = ldm(bx + rr); cy[k] = ldm(by + rr); cz[k] = ldm(bz + rr);
+    }
+}
+template <int ROUNDS>
+__device__ __forceinline__ void pair_closest(const MapView &m, const V3 &p, int l2, int &count_out, int &own_out, double &d2_out, V3 &t_out, int &rank_out) {
+    const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
+    const bool inr = key_in_range(kx, ky, kz);
+    const unsigned long long key = pack_key(kx, ky, kz);
+    const unsigned int h = inr ? slot_of(key, m.shift) : 0u;
+    const ulonglong2 sv = load_slot(m.slots + h);
+    double cx[ROUNDS], cy[ROUNDS], cz[ROUNDS];
+    pair_load_candidates<ROUNDS>(m, h, l2, cx, cy, cz);
+    int slot = -1, count = 0;
+    own_out = 0;
+    if (inr) {
+        unsigned int s = h;
+        ulonglong2 v = sv;
+        while (v.x != key && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(m.slots + s); }
+        if (v.x == key) { slot = (int)s; count = meta_count(v.y); own_out = 1; }
+    }
+    // fallback (voxel_hash_map.cpp:76-101): the occupied neighbour with the largest (|delta|^2 class, birth); lane l2 probes cells l2, l2+2, ...
+    int bd = -1, bslot = -1;
+    unsigned long long bmeta = 0ull;
+    if (slot < 0) {
+        constexpr int BATCH = ROUNDS <= 5 ? 13 : 7;   // cells per lane and round trip (registers: 16 B per probe in flight)
+#pragma unroll
+        for (int u0 = 0; u0 < 13; u0 += BATCH) {
+            ulonglong2 got[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const int c = l2 + 2 * (u0 + u);
+                got[u] = make_ulonglong2(KEY_EMPTY, 0ull);
+                if (u0 + u < 13 && c < 26) {
+                    const int x = kx + NB_ALL[c][0], y = ky + NB_ALL[c][1], z = kz + NB_ALL[c][2];
+                    if (key_in_range(x, y, z)) got[u] = load_slot(m.slots + slot_of(pack_key(x, y, z), m.shift));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const int c = l2 + 2 * (u0 + u);
+                ulonglong2 v = got[u];
+                if (u0 + u < 13 && c < 26 && v.x != KEY_EMPTY) {
+                    const unsigned long long want = pack_key(kx + NB_ALL[c][0], ky + NB_ALL[c][1], kz + NB_ALL[c][2]);
+                    unsigned int s = slot_of(want, m.shift);
+                    while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(m.slots + s); }
+                    if (v.x == want) {
+                        const int d = c < 8 ? 3 : (c < 20 ? 2 : 1);
+                        if (d > bd || (d == bd && v.y > bmeta)) { bd = d; bmeta = v.y; bslot = (int)s; }
+                    }
+                }
+            }
+        }
+    }
+    {   // both lanes of the pair agree on the winner (warp-wide exchange; pairs that did not search carry bd = -1 on both lanes)
+        const int od = __shfl_xor_sync(0xFFFFFFFFu, bd, 1), os = __shfl_xor_sync(0xFFFFFFFFu, bslot, 1);
+        const unsigned long long om = __shfl_xor_sync(0xFFFFFFFFu, bmeta, 1);
+        if (od > bd || (od == bd && om > bmeta)) { bd = od; bmeta = om; bslot = os; }
+    }
+    if (slot < 0) { slot = bslot; count = bslot >= 0 ? meta_count(bmeta) : 0; }
+    if (slot >= 0 && (unsigned int)slot != h) pair_load_candidates<ROUNDS>(m, (unsigned int)slot, l2, cx, cy, cz);   // displaced or neighbour voxel: second trip
+    double bd2 = 1.7976931348623157e308, tx = 0.0, ty = 0.0, tz = 0.0;
+    int br = 0x7FFFFFFF;
+    if (slot >= 0) {
+#pragma unroll
+        for (int k = 0; k < ROUNDS; ++k) {
+            const int r = l2 + 2 * k;
+            const double d = sqnorm3(p.x - cx[k], p.y - cy[k], p.z - cz[k]);
+            if (r < count && d < bd2) { bd2 = d; br = r; tx = cx[k]; ty = cy[k]; tz = cz[k]; }
+        }
+    }
+    {
+        const double od = __shfl_xor_sync(0xFFFFFFFFu, bd2, 1), ox = __shfl_xor_sync(0xFFFFFFFFu, tx, 1), oy = __shfl_xor_sync(0xFFFFFFFFu, ty, 1),
+                     oz = __shfl_xor_sync(0xFFFFFFFFu, tz, 1);
+        const int orr = __shfl_xor_sync(0xFFFFFFFFu, br, 1);
+        if (od < bd2 || (od == bd2 && orr < br)) { bd2 = od; br = orr; tx = ox; ty = oy; tz = oz; }
+    }
+    count_out = count; d2_out = bd2; rank_out = br == 0x7FFFFFFF ? -1 : br;
+    t_out = V3{tx, ty, tz};   // (0,0,0) when nothing was found
+}
+
 // ---- opt-in neighbour rule LIMU_NN_27 (no counterpart in the reference) -----------------------------
 // What the north star literally names and upstream KISS-ICP does: the NEAREST stored point over all 27 cells of the
 // query's neighbourhood (the reference only looks into the query's own voxel when it exists, voxel_hash_map.cpp:71-73).

@@ -7,7 +7,8 @@ mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/b${N}_topo.txt 2>&1
 ( time timeout 600 python -m pytest tests/test_multi_gpu.py -m gpu -x -q ) > gpurun_out/b${N}_pytest.log 2>&1
 echo "pytest rc=$?"; tail -3 gpurun_out/b${N}_pytest.log
-for n in 1 $N; do
+NS="1 $N"; [ "$N" = "8" ] && NS="1 4 8"
+for n in $NS; do
   if [ "$n" = "1" ]; then
     ( time timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 --no-extras ) > gpurun_out/b${N}_bench_n1.json 2> gpurun_out/b${N}_bench_n1.err
   else
