@@ -12,6 +12,8 @@
 // a grid barrier publishes them, and every CTA redundantly folds the rows in a fixed order and runs
 // the identical LDLT / exp / log on one thread, so the next iteration starts without any host or
 // second-barrier round trip. Sums are FP64 throughout; the fold order is fixed -> run-to-run deterministic.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -625,6 +627,280 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
     }
 }
 
+// ============================================================================================================================
+// Cluster latency shape of the frame kernel (pipeline mode, the reference's registration rules): the Gauss-Newton loop of one scan
+// runs on ONE 16-CTA thread-block cluster instead of ~72 CTAs that meet at a global-memory barrier.
+//   * two lanes per query (pair_closest): 15 query warps x 16 pairs x 16 CTAs = 3 840 keypoints per pass, so a scan's ~2.4 k keypoints
+//     are ONE pass and every query lives in the registers of its lane pair for the whole loop (no working cloud in memory);
+//   * the common lookup is one L2 round trip (home slot + candidates requested together; the matched point comes back by shuffle);
+//   * the 16 CTA rows are exchanged through distributed shared memory: each CTA stores its 20-double row into every CTA's shared
+//     memory and a hardware cluster barrier (~0.2 us) replaces the global barrier + L2 fold (~3.5 us);
+//   * warp 0 of every CTA is a solver warp without queries: it folds the rows, solves (redundantly, bit-identically in all 16 CTAs),
+//     publishes the estimate, and finishes T_icp / log / the convergence test WHILE the query warps already run the next pass
+//     (a pass made after the converging iteration is simply dropped);
+//   * the IQR filter needs one grid barrier: the order statistics are ranked grid-wide, then every loop CTA derives bounds, flags and
+//     the compacted index list in its own shared memory (CTA 0 also writes the keypoints out for the host).
+// The other clusters of the grid only take part in the grid-wide phases (IQR ranking, map insert, eviction).
+constexpr int CL_THREADS = 512, CL_SIZE = 16, CL_QWARPS = CL_THREADS / 32 - 1, CL_QPC = CL_QWARPS * 16, CL_QPP = CL_SIZE * CL_QPC;
+
+struct ClusterSmem {
+    double sd2[IQR_GRID_MAX];                 // squared ranges of the IQR candidates
+    unsigned short qidx[IQR_GRID_MAX];        // source index of keypoint q (after the IQR filter)
+    double red[CL_THREADS / 32][32];          // per-warp partial sums of one pass
+    double rows[2][CL_SIZE][NS];              // the 16 CTA rows of an iteration (written by the peers through DSMEM), double-buffered
+    double S[NS];
+    double E[8], Tinit[8], Ticp[8], x[8];
+    int ws[32];
+    int total, done, pad0, pad1;
+    IqrSmem iqr;                              // one-CTA select for candidate clouds beyond IQR_GRID_MAX
+};
+
+__device__ __forceinline__ unsigned int cluster_ctarank() { unsigned int r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned int cluster_nctarank() { unsigned int r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void dsmem_store_f64(const double *local_smem, unsigned int cta, double v) {
+    const unsigned int la = (unsigned int)__cvta_generic_to_shared(local_smem);
+    unsigned int ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+
+// Tukey bounds from the four order statistics, inlier flags and the order-preserving index list, by one CTA in its shared memory
+// (icp.cpp:103-121; same bounds and comparisons as iqr_grid_filter). Returns the keypoint count.
+__device__ __forceinline__ int cluster_iqr_compact(ClusterSmem &sm, const IcpArgs &A, int n0, bool write_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = n0 / 2;
+    const double v0 = __ldcg(A.iqr_d2), v1 = __ldcg(A.iqr_d2 + 1), v2 = __ldcg(A.iqr_d2 + 2), v3 = __ldcg(A.iqr_d2 + 3);
+    const double q1 = (m % 2 == 0) ? (v0 + v1) / 2.0 : v1;
+    const double q3 = (m % 2 == 0) ? (v2 + v3) / 2.0 : v3;
+    const double iqr = q3 - q1;
+    const double low = q1 - 1.25 * iqr, high = q3 + 1.25 * iqr;   // icp.cpp:104-105
+    constexpr int PER = IQR_GRID_MAX / CL_THREADS;               // 8 consecutive candidates per thread
+    unsigned int f = 0;
+    int cnt = 0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int i = tid * PER + u;
+        const double d = i < n0 ? sm.sd2[i] : 0.0;
+        const bool in = i < n0 && d >= low && d <= high;         // icp.cpp:117
+        f |= (in ? 1u : 0u) << u;
+        cnt += in ? 1 : 0;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) sm.ws[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int v = lane < CL_THREADS / 32 ? sm.ws[lane] : 0;
+        int wi = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += t; }
+        sm.ws[lane] = wi - v;
+        if (lane == 31) sm.total = wi;
+    }
+    __syncthreads();
+    int pos = sm.ws[warp] + incl - cnt;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        if (f & (1u << u)) {
+            const int i = tid * PER + u;
+            sm.qidx[pos] = (unsigned short)i;
+            if (write_out) {
+                A.iqr_out[3 * (size_t)pos] = A.iqr_in[3 * (size_t)i];
+                A.iqr_out[3 * (size_t)pos + 1] = A.iqr_in[3 * (size_t)i + 1];
+                A.iqr_out[3 * (size_t)pos + 2] = A.iqr_in[3 * (size_t)i + 2];
+            }
+            ++pos;
+        }
+    }
+    if (write_out && tid == 0) *A.iqr_count = sm.total;
+    __syncthreads();
+    return sm.total;
+}
+
+#ifdef LIMU_ICP_PHASE_TIMING
+#define CT_MARK(k) do { if (blockIdx.x == 0 && lane == 0) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
+#else
+#define CT_MARK(k) do {} while (0)
+#endif
+
+// x = LDLT(H).solve(-g) from the 16 sums (registration.cpp:90), one thread. Kept out of line: its ~90 live registers would otherwise
+// compete with the query pass of the cluster kernel for the 128 registers a 512-thread CTA allows.
+static __device__ __noinline__ void solve_normal_equations(const double *S, double *x_out) {
+    double H[36], g[6], x[6];
+    expand_normal_equations(S, H, g);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g[k] = -g[k];
+    ldlt6_solve(H, g, x);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) x_out[k] = x[k];
+}
+
+template <int ROUNDS>   // candidate ranks per lane of a query pair: max_points_per_voxel <= 2 * ROUNDS
+static __global__ void __launch_bounds__(CL_THREADS, 1) k_frame_cluster(const IcpArgs A) {
+    extern __shared__ __align__(16) unsigned char cl_raw[];
+    ClusterSmem &sm = *reinterpret_cast<ClusterSmem *>(cl_raw);
+    GridSync gs{A.barrier, 0u, gridDim.x};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l2 = lane & 1;
+    const unsigned int crank = cluster_ctarank();
+    const bool loop_cta = blockIdx.x < CL_SIZE;   // cluster 0 (1-D cluster of CL_SIZE CTAs) runs the Gauss-Newton loop
+    FT_MARK(0);
+    // ---- KissICP::iqr_processing (icp.cpp:88-124, :133): exactly one grid barrier -------------------------------------------------
+    const int n0 = __ldcg(A.iqr_n);
+    const bool small = n0 <= IQR_GRID_MAX;     // uniform across the grid
+    int n = 0;                                 // keypoints (known to the loop CTAs)
+    if (small && n0 > 1) {
+        iqr_grid_select<CL_THREADS>(sm.sd2, A.iqr_in, n0, A.iqr_d2);
+        gs.sync();
+        if (loop_cta) n = cluster_iqr_compact(sm, A, n0, blockIdx.x == 0);
+    } else if (small) {                        // 0 or 1 candidate: outlier::IQR keeps a single value (common.hpp:49-52)
+        if (threadIdx.x == 0) {
+            sm.qidx[0] = 0;
+            if (blockIdx.x == 0) {
+                if (n0 == 1) { A.iqr_out[0] = A.iqr_in[0]; A.iqr_out[1] = A.iqr_in[1]; A.iqr_out[2] = A.iqr_in[2]; }
+                *A.iqr_count = n0;
+            }
+        }
+        n = n0;
+        gs.sync();
+    } else {
+        if (blockIdx.x == 0) iqr_block<CL_THREADS>(sm.iqr, A.iqr_in, n0, A.iqr_d2, A.iqr_out, A.iqr_count, nullptr);
+        gs.sync();
+        n = __ldcg(A.iqr_count);
+    }
+    FT_MARK(1);
+    const bool run_icp = !(__ldcg(A.map_counters) == 0ull || A.max_iter <= 0);   // ICP :99-100: empty map -> init_guess
+    if (threadIdx.x < 7) { sm.Tinit[threadIdx.x] = A.init_pose[threadIdx.x]; sm.Ticp[threadIdx.x] = threadIdx.x == 3 ? 1.0 : 0.0; }
+    if (threadIdx.x < NS) sm.S[threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) sm.done = 0;
+    __syncthreads();
+    int j = 0, converged = 0;
+    if (loop_cta && run_icp) {
+        const bool single = small && n <= CL_QPP;            // one pass: the running source point stays in the pair's registers
+        const int64_t pair0 = (int64_t)crank * CL_QPC + (int64_t)(warp - 1) * 16 + (lane >> 1);
+        V3 s_reg{0.0, 0.0, 0.0};
+        for (;;) {
+            const bool no_more = j >= A.max_iter;             // only wait for the tail of iteration j-1
+            if (warp > 0) {
+                if (!no_more) {
+                    double acc = 0.0;                         // lane L: running total of sum index L>>1
+                    int ncorr = 0, ncand = 0, nmiss = 0;
+                    const volatile double *Pv = j == 0 ? sm.Tinit : sm.E;
+                    for (int64_t base = 0; base < n; base += CL_QPP) {
+                        const int64_t q = base + pair0;
+                        const bool on = q < n;
+                        V3 s{0.0, 0.0, 0.0};
+                        if (on) {
+                            const Pose P{Pv[0], Pv[1], Pv[2], Pv[3], Pv[4], Pv[5], Pv[6]};
+                            V3 p;
+                            if (j == 0) {   // source = init_guess * points (:102-103); the keypoints are the IQR inliers of src0
+                                const size_t i = small ? (size_t)sm.qidx[q] : (size_t)q;
+                                const double *src = small ? A.iqr_in : A.iqr_out;
+                                p = V3{src[3 * i], src[3 * i + 1], src[3 * i + 2]};
+                            } else if (single) {
+                                p = s_reg;                    // source <- estimate * source (:119), applied at the next visit
+                            } else {
+                                p = V3{A.work[3 * q], A.work[3 * q + 1], A.work[3 * q + 2]};
+                            }
+                            s = apply(P, p);
+                            if (single) s_reg = s;
+                            else if (l2 == 0) { A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z; }
+                        }
+                        int count, own, my_rank;
+                        double d2;
+                        V3 tg;
+                        pair_closest<ROUNDS>(A.map, s, l2, count, own, d2, tg, my_rank);
+                        if (my_rank < 0) d2 = sqnorm3(tg.x - s.x, tg.y - s.y, tg.z - s.z);   // nothing found -> (0,0,0), range-tested like a real point
+                        const bool lead = on && l2 == 0;
+                        const bool gate = lead && d2 < A.tau_sq;
+                        double c[16];
+                        contribution(c, s, tg, d2, A.th, gate);
+                        acc += warp_reduce_scatter16(c);
+                        ncorr += gate ? 1 : 0;
+                        ncand += lead ? count : 0;
+                        nmiss += (lead && !own) ? 1 : 0;
+                    }
+                    ncorr = __reduce_add_sync(0xFFFFFFFFu, ncorr);
+                    ncand = __reduce_add_sync(0xFFFFFFFFu, ncand);
+                    nmiss = __reduce_add_sync(0xFFFFFFFFu, nmiss);
+                    sm.red[warp][lane] = (lane & 1) ? (lane == 1 ? (double)ncorr : lane == 3 ? (double)ncand : lane == 5 ? (double)nmiss : 0.0) : acc;
+                }
+            } else if (j > 0) {
+                // tail of iteration j-1 on the solver warp, overlapped with pass j: T_icp = estimate * T_icp (:122) on lane 0,
+                // |log(estimate)| < eps (:124) on lane 1
+                const Pose est = pose_load(sm.E);
+                if (lane == 0) pose_store(mul(est, pose_load(sm.Ticp)), sm.Ticp);
+                if (lane == 1) {
+                    double lg[6];
+                    se3_log(est, lg);
+                    sm.done = norm6(lg) < A.eps;
+                }
+            }
+            __syncthreads();                                  // S1: partial sums of pass j and the verdict on iteration j-1
+            if (j > 0 && sm.done) { converged = 1; break; }   // (the pass just made belongs to an iteration that does not exist)
+            if (no_more) break;
+            CT_MARK(6);
+            const int par = j & 1;
+            if (warp == 0 && lane < NS) {
+                // CTA row (fixed order over the query warps), stored into every CTA of the cluster
+                const int src_lane = lane < 16 ? 2 * lane : 2 * (lane - 16) + 1;
+                double v = 0.0;
+#pragma unroll
+                for (int w = 1; w <= CL_QWARPS; ++w) v += sm.red[w][src_lane];
+#pragma unroll
+                for (unsigned int r = 0; r < (unsigned int)CL_SIZE; ++r) dsmem_store_f64(&sm.rows[par][crank][lane], r, v);
+            }
+            cluster_arrive_release();
+            cluster_wait_acquire();
+            CT_MARK(7);
+            if (warp == 0) {
+                if (lane < NS) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int r = 0; r < CL_SIZE; ++r) v += sm.rows[par][r][lane];
+                    sm.S[lane] = v;
+                }
+                __syncwarp();
+                CT_MARK(8);
+                if (lane == 0) solve_normal_equations(sm.S, sm.x);   // JTJ.ldlt().solve(-JTr) :90
+                __syncwarp();
+                CT_MARK(9);
+                // estimate = SE3::exp(x) (vector6d_to_mat4d :91): rotation half on lane 0, translation half on lane 1
+                if (lane == 0) { double th_; se3_exp_rotation(sm.x, sm.E, &th_); }
+                if (lane == 1) se3_exp_translation(sm.x, sm.E + 4);
+                __syncwarp();
+                CT_MARK(10);
+            }
+            __syncthreads();                                  // S2: the estimate is visible to the query warps
+            ++j;
+        }
+    }
+    FT_MARK(2);
+    // new_pose = T_icp * init_guess (:129); with an empty map the loop did not run and this is init_guess itself (:99-100)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const Pose np = run_icp ? mul(pose_load(sm.Ticp), pose_load(sm.Tinit)) : pose_load(sm.Tinit);
+        pose_store(np, A.out);
+        if (A.twist_out) {   // the next scan deskews with delta_pose(poses[N-2], poses[N-1]) = log(last^-1 * new): leave it on the device
+            double tw[6];
+            se3_log(mul(inverse(Pose{A.last_pose[0], A.last_pose[1], A.last_pose[2], A.last_pose[3], A.last_pose[4], A.last_pose[5], A.last_pose[6]}), np), tw);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) A.twist_out[k] = tw[k];
+        }
+        A.out[7] = (double)j; A.out[8] = (double)converged; A.out[9] = sm.S[16]; A.out[10] = sm.S[17]; A.out[11] = sm.S[18]; A.out[12] = (double)n;
+    }
+    if (A.upd_down) frame_update_epilogue<CL_THREADS>(A, gs, sm.E);
+    FT_MARK(5);
+    // no CTA of a cluster may exit while a peer can still store into its shared memory: the last DSMEM store precedes the last cluster
+    // barrier of the loop, and every loop CTA passes the grid barriers above after it. The last CTA out re-arms the grid barrier.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(A.exit_count, 1u) == gridDim.x - 1) { *A.barrier = 0u; *A.barrier_icp = 0u; *A.exit_count = 0u; __threadfence(); }
+    }
+}
+
 // ---- stand-alone align_clouds -------------------------------------------------------------------------
 static __global__ void __launch_bounds__(ICP_BLOCK) k_align_partial(const double *__restrict__ src, const double *__restrict__ tgt, int64_t n, double th,
                                                                    double *partials) {
@@ -656,6 +932,59 @@ static __global__ void k_align_solve(const double *partials, int nblocks, double
         for (int k = 0; k < 6; ++k) { out[36 + k] = g[k]; out[42 + k] = x[k]; }
         pose_store(se3_exp(x), out + 48);
     }
+}
+
+// ---- launch of the cluster latency shape -----------------------------------------------------------------------------------------
+// Per device: 0 = not probed yet, -1 = unavailable (the classic kernel is used), > 0 = clusters of CL_SIZE CTAs that can be co-resident.
+static int g_cluster_state[64] = {};
+static int g_cluster_coop[64] = {};   // 1: launched with the cooperative attribute as well
+static bool cluster_shape_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("LIMU_GN_CLUSTER"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v != 0;
+}
+static int launch_frame_cluster(limu_ctx *c, IcpArgs &A, int cap) {
+    const int dev = c->device & 63;
+    if (g_cluster_state[dev] < 0) return LIMU_ERR_CUDA;
+    const void *fn = cap <= 10 ? (const void *)k_frame_cluster<5> : (const void *)k_frame_cluster<10>;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.blockDim = dim3(CL_THREADS);
+    cfg.dynamicSmemBytes = sizeof(ClusterSmem);
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL_SIZE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    cfg.attrs = at;
+    if (g_cluster_state[dev] == 0) {
+        g_cluster_state[dev] = -1;
+        const void *both[2] = {(const void *)k_frame_cluster<5>, (const void *)k_frame_cluster<10>};
+        for (const void *f : both) {
+            if (cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+                cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClusterSmem)) != cudaSuccess) { (void)cudaGetLastError(); return LIMU_ERR_CUDA; }
+        }
+        int ncl = 0;
+        cfg.gridDim = dim3(CL_SIZE * 8);
+        cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg) != cudaSuccess || ncl < 1) { (void)cudaGetLastError(); return LIMU_ERR_CUDA; }
+        g_cluster_state[dev] = std::min(ncl, 8);
+        g_cluster_coop[dev] = 1;
+    }
+    cfg.gridDim = dim3(CL_SIZE * g_cluster_state[dev]);
+    void *args[] = {&A};
+    cfg.numAttrs = g_cluster_coop[dev] ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
+    if (e != cudaSuccess && g_cluster_coop[dev]) {   // cooperative + cluster refused: the grid fits by construction (cudaOccupancyMaxActiveClusters), launch it plainly
+        (void)cudaGetLastError();
+        g_cluster_coop[dev] = 0;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelExC(&cfg, fn, args);
+    }
+    if (e != cudaSuccess) { (void)cudaGetLastError(); g_cluster_state[dev] = -1; return LIMU_ERR_CUDA; }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return LIMU_OK;
 }
 
 static int g_icp_blocks_per_sm = 0;
@@ -711,6 +1040,12 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
     }
     void *args[] = {&A};
     LIMU_TRY(prof_begin(c, LIMU_STAGE_ICP));
+    // pipeline mode with the reference's rules: the cluster latency shape (falls back to the classic kernel where clusters of 16 cannot be launched)
+    if (fuse && fuse->iqr_in && fuse->upd_down && icp_mode == 0 && A.nranks == 1 && !est_trace_dev && !ncorr_trace_dev && !hg_trace_dev && m->cap <= 20 &&
+        n_hint <= CL_QPP && cluster_shape_enabled() && launch_frame_cluster(c, A, m->cap) == LIMU_OK) {
+        LIMU_TRY(prof_end(c, LIMU_STAGE_ICP));
+        return LIMU_OK;
+    }
     if (plane && max_iter_all_ranks >= 0 && c->comm && c->comm->nranks > 1) { set_error("the point-to-plane variant is not available in the point-sharded loop"); return LIMU_ERR_INVALID; }
     const void *fns[2][2][2] = {{{(const void *)k_icp_persistent<0, false, false>, (const void *)k_icp_persistent<0, false, true>},
                                  {(const void *)k_icp_persistent<0, true, false>, (const void *)k_icp_persistent<0, true, true>}},
