@@ -96,7 +96,7 @@ def workload_text(args, name="c2", n_gpus=1):
     w = WORKLOADS[name]
     beams = args.beams if name == "c2" else w["beams"]
     t = w["text"].format(beams=beams, points=args.points, step=args.step_m, voxel=args.voxel, cap=args.cap)
-    return t + (f"; configs[3]: {n_gpus} independent sequences, one per GPU" if n_gpus > 1 else "")
+    return t + (f"; configs[3]: {n_gpus} independent sequences, one per GPU (same world, per-vehicle sensor-noise realisation)" if n_gpus > 1 else "")
 
 
 def make_config(args, n_gpus):
@@ -110,8 +110,9 @@ def make_config(args, n_gpus):
     }
 
 
-def make_scans(args, n_scans, seed, device, workload="c2", first=0):
-    """The sequence of one vehicle: scans first .. first+n_scans-1 along the loop, each resized to exactly --points rows."""
+def make_scans(args, n_scans, seed, device, workload="c2", first=0, vehicle=0):
+    """The sequence of one vehicle: scans first .. first+n_scans-1 along the loop, each resized to exactly --points rows.
+    `seed` picks the world, `vehicle` the realisation of the sensor noise (fleet replay: N vehicles in the same world)."""
     import __graft_entry__ as g
     g.load_package()
     from importlib import import_module
@@ -123,8 +124,8 @@ def make_scans(args, n_scans, seed, device, workload="c2", first=0):
     az = args.azimuth_steps if workload == "c2" else w["azimuth_steps"]
     scans = []
     for i in range(first, first + n_scans):
-        s = synth.cast_scan(scene, traj[i], traj[i + 1], beams=beams, azimuth_steps=az, elev=w["elev"], seed=seed * 100003 + i, device=device)
-        scans.append(synth.pad_scan(s, args.points, seed=i))
+        s = synth.cast_scan(scene, traj[i], traj[i + 1], beams=beams, azimuth_steps=az, elev=w["elev"], seed=(seed + 7919 * vehicle) * 100003 + i, device=device)
+        scans.append(synth.pad_scan(s, args.points, seed=i + 1000003 * vehicle))
     return scans
 
 
@@ -552,7 +553,10 @@ def main():
         dev = [torch.from_numpy(s).cuda() for s in scans]
         return pinned, dev
 
-    scans = make_scans(args, W + K, 42 + rank, f"cuda:{local_rank}")     # configs[3]: seeds 42..49, one sequence per GPU
+    # configs[3]: one independent sequence per GPU. Weak scaling needs EQUAL work per GPU, so every rank replays the same world (scene seed 42)
+    # with its own sensor-noise realisation. (Round 1 gave rank r scene seed 42 + r: on scene 45 the reference's Gauss-Newton loop runs to its
+    # 500-iteration cap on some of the first 25 scans, that rank did ~6x the work and the max-over-ranks time followed it: profiles/r2_multi_gpu_n8.json.)
+    scans = make_scans(args, W + K, 42, f"cuda:{local_rank}", vehicle=rank)
     pinned, dev_scans = stage(scans)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     flush.fill_(1)                                                      # push the staged scans out of L2
@@ -615,6 +619,7 @@ def main():
 
     fr = np.array(gpu_frames[W:], dtype=np.float64)
     iters_total = float(fr[:, 1].sum())
+    rank_work = b.gather([float(fr[:, 1].mean()), float(fr[:, 1].max()), float(fr[:, 0].mean())])   # equal work per GPU? (weak scaling)
     # bytes per launch over ALL profiled frames (warm-up included: set_profiling covers the whole window)
     pf = prof_frames if prof_frames else gpu_frames
     alg_bytes = float(sum(frame_kernel_bytes(nk, it, kb, fm, nk * 1.05, nd, map_voxels) for nk, it, kb, fm, nd in pf))
@@ -631,7 +636,10 @@ def main():
             "metric": METRIC, "value": val["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * val["seconds"] / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": make_config(args, n_gpus), "arm_note": "liblimu_cuda.so through its C ABI; LIMU_OPT_SPECULATE " + ("off" if args.no_speculate else "on"),
-            "repeats": R, "windows_scans_per_s": val["windows_scans_per_s"], "per_rank": val["per_rank_median_window"], "cpu_cores_per_rank": len(cores),
+            "repeats": R, "windows_scans_per_s": val["windows_scans_per_s"],
+            "per_rank": dict(val["per_rank_median_window"], iterations_per_scan=[round(r_[0], 2) for r_ in rank_work], max_iterations=[int(r_[1]) for r_ in rank_work],
+                             keypoints_per_scan=[round(r_[2], 1) for r_ in rank_work]),
+            "cpu_cores_per_rank": len(cores),
             "mpoints_per_s": val["value"] * n_pts / 1e6,
             "iterations_per_scan": iters_total / K, "scans_at_iteration_cap": int((fr[:, 1] >= args.max_iter).sum()),
             "keypoints_per_scan": float(fr[:, 0].mean()), "downsampled_per_scan": float(fr[:, 4].mean()),

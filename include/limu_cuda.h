@@ -239,8 +239,11 @@ int limu_odom_register_frame_dev(limu_odom *o, const float *xyzt_dev, int64_t n,
  * depend on hints beyond rounding (the twist of a speculated scan is taken by the device's log instead of the host's: ~1e-15); a hint
  * that is not followed by that scan is simply discarded. */
 int limu_odom_hint_next_dev(limu_odom *o, const float *xyzt_dev_next, int64_t n_next);
-/* Handle options. LIMU_OPT_SPECULATE (default 1; the environment variable LIMU_SPECULATE=0 changes the default): see above. */
-enum { LIMU_OPT_SPECULATE = 1 };
+/* Handle options. LIMU_OPT_SPECULATE (default 1; the environment variable LIMU_SPECULATE=0 changes the default): see above.
+ * LIMU_OPT_CLUSTER_LOOP (default 1; LIMU_CLUSTER_LOOP=0): with the reference's registration rules and <= 3840 keypoints the Gauss-Newton
+ * loop of a scan runs on one 16-CTA thread-block cluster (rows exchanged through distributed shared memory, hardware cluster barrier);
+ * 0 = the classic shape (leading CTAs + global-memory barrier), which is also what devices that cannot launch such clusters get. */
+enum { LIMU_OPT_SPECULATE = 1, LIMU_OPT_CLUSTER_LOOP = 2 };
 int limu_odom_set_option(limu_odom *o, int32_t option, int64_t value);
 /* register_frame(Vec3dVector) icp.cpp:58-86 (no deskew). */
 int limu_odom_register_points(limu_odom *o, const double *xyz, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down,

@@ -13,5 +13,6 @@ struct FrameFusion {
     unsigned long long upd_birth_base;
     double *twist_out;         // non-null: leave log(last_pose^-1 * new_pose) here for the NEXT scan's deskew (delta_pose, deskew.cpp:14)
     double last_pose[7];       // poses.back() before this scan
+    int allow_cluster;         // LIMU_OPT_CLUSTER_LOOP: the cluster latency shape may be used (registration.cu, k_frame_cluster)
 };
 }  // namespace limu

@@ -61,7 +61,7 @@ struct limu_odom {
     limu::DevBuf raw, ts, frame, down, src0, src, work, world, partials, d2;
     limu::VoxelizeScratch vx;
     limu::PreScratch pre;                   // limu_odom_register_msg: frame::Lidar::process_frame on the device
-    int64_t nk_hint = 4096, nd_hint = 16384;
+    int64_t nk_hint = 2048, nd_hint = 16384;   // keypoints / downsampled points of the previous scan (launch shapes; the kernels take any count)
     // limu_odom_prefetch: the next scan is uploaded on its own stream while the current one is being registered
     limu::DevBuf pf_buf[2];                 // two slots: the scan about to be registered and the one after it
     cudaStream_t copy_stream = nullptr;
@@ -74,6 +74,7 @@ struct limu_odom {
     // behind this scan's frame kernel, with its deskew twist left on the device by that kernel, so the host round trip of this scan
     // (result copy, wake-up, scalar glue, launch) overlaps it instead of idling the GPU.
     bool speculate = true;
+    bool cluster_loop = true;               // LIMU_OPT_CLUSTER_LOOP: run the Gauss-Newton loop on one 16-CTA cluster (registration.cu, k_frame_cluster)
     const void *hint_ptr = nullptr;         // next scan (device float4 rows), set by the caller before registering the current one
     int64_t hint_n = 0;
     const void *spec_ptr = nullptr;         // scan whose k_voxelize is already in flight / done
@@ -206,6 +207,7 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     const bool speculate = next_ptr && next_n > 0;
     const int next_deskew = (o->cfg.deskew && NP + 1 > 2) ? 1 : 0;   // the gate of icp.cpp:40-46 as the next scan will see it
     fuse.twist_out = nullptr;
+    fuse.allow_cluster = o->cluster_loop ? 1 : 0;
     pose_store(last, fuse.last_pose);
     if (speculate && next_deskew) {
         LIMU_TRY(o->twist_next.reserve(6 * sizeof(double), c->stream));
@@ -325,7 +327,8 @@ int limu_odom_create(limu_ctx *c, const limu_odom_config *cfg, limu_odom **out) 
     limu_odom *o = new limu_odom;
     o->ctx = c;
     o->cfg = *cfg;
-    if (const char *e = getenv("LIMU_SPECULATE")) o->speculate = atoi(e) != 0;   // default of LIMU_OPT_SPECULATE (on)
+    if (const char *e = getenv("LIMU_SPECULATE")) o->speculate = atoi(e) != 0;        // default of LIMU_OPT_SPECULATE (on)
+    if (const char *e = getenv("LIMU_CLUSTER_LOOP")) o->cluster_loop = atoi(e) != 0;   // default of LIMU_OPT_CLUSTER_LOOP (on)
     int64_t capv = cfg->map_capacity_voxels;
     if (capv <= 0) {   // a sensor sees a shell, not a ball: ~ (2 r / v)^2 * 8 voxels is generous for one neighbourhood
         const double side = 2.0 * cfg->max_range / cfg->voxel_size;
@@ -499,6 +502,7 @@ int limu_odom_set_option(limu_odom *o, int32_t option, int64_t value) {
         if (!o->speculate) { o->hint_ptr = nullptr; o->hint_n = 0; }
         return LIMU_OK;
     }
+    if (option == LIMU_OPT_CLUSTER_LOOP) { o->cluster_loop = value != 0; return LIMU_OK; }
     set_error("limu_odom_set_option: unknown option %d", (int)option);
     return LIMU_ERR_INVALID;
 }

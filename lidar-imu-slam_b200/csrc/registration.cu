@@ -938,11 +938,6 @@ static __global__ void k_align_solve(const double *partials, int nblocks, double
 // Per device: 0 = not probed yet, -1 = unavailable (the classic kernel is used), > 0 = clusters of CL_SIZE CTAs that can be co-resident.
 static int g_cluster_state[64] = {};
 static int g_cluster_coop[64] = {};   // 1: launched with the cooperative attribute as well
-static bool cluster_shape_enabled() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("LIMU_GN_CLUSTER"); v = (e && atoi(e) == 0) ? 0 : 1; }
-    return v != 0;
-}
 static int launch_frame_cluster(limu_ctx *c, IcpArgs &A, int cap) {
     const int dev = c->device & 63;
     if (g_cluster_state[dev] < 0) return LIMU_ERR_CUDA;
@@ -1042,7 +1037,7 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
     LIMU_TRY(prof_begin(c, LIMU_STAGE_ICP));
     // pipeline mode with the reference's rules: the cluster latency shape (falls back to the classic kernel where clusters of 16 cannot be launched)
     if (fuse && fuse->iqr_in && fuse->upd_down && icp_mode == 0 && A.nranks == 1 && !est_trace_dev && !ncorr_trace_dev && !hg_trace_dev && m->cap <= 20 &&
-        n_hint <= CL_QPP && cluster_shape_enabled() && launch_frame_cluster(c, A, m->cap) == LIMU_OK) {
+        n_hint <= CL_QPP && fuse->allow_cluster && launch_frame_cluster(c, A, m->cap) == LIMU_OK) {
         LIMU_TRY(prof_end(c, LIMU_STAGE_ICP));
         return LIMU_OK;
     }

@@ -296,52 +296,64 @@ __device__ __forceinline__ void pair_load_candidates(const MapView &m, unsigned 
         cx[k] = ldm(bx + rr); cy[k] = ldm(by + rr); cz[k] = ldm(bz + rr);
     }
 }
+// this lane's share of VoxelBlock::get_closest_point (voxel_block.cpp:87-105): ranks l2, l2+2, ... in ascending order, strict '<'
+template <int ROUNDS>
+__device__ __forceinline__ void pair_scan(const V3 &p, int l2, int count, const double *cx, const double *cy, const double *cz, double &bd2, int &br, double &tx,
+                                          double &ty, double &tz) {
+#pragma unroll
+    for (int k = 0; k < ROUNDS; ++k) {
+        const int r = l2 + 2 * k;
+        const double d = sqnorm3(p.x - cx[k], p.y - cy[k], p.z - cz[k]);
+        if (r < count && d < bd2) { bd2 = d; br = r; tx = cx[k]; ty = cy[k]; tz = cz[k]; }
+    }
+}
 template <int ROUNDS>
 __device__ __forceinline__ void pair_closest(const MapView &m, const V3 &p, int l2, int &count_out, int &own_out, double &d2_out, V3 &t_out, int &rank_out) {
     const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
     const bool inr = key_in_range(kx, ky, kz);
     const unsigned long long key = pack_key(kx, ky, kz);
     const unsigned int h = inr ? slot_of(key, m.shift) : 0u;
-    const ulonglong2 sv = load_slot(m.slots + h);
-    double cx[ROUNDS], cy[ROUNDS], cz[ROUNDS];
-    pair_load_candidates<ROUNDS>(m, h, l2, cx, cy, cz);
-    int slot = -1, count = 0;
+    double bd2 = 1.7976931348623157e308, tx = 0.0, ty = 0.0, tz = 0.0;
+    int br = 0x7FFFFFFF, slot = -1, count = 0;
     own_out = 0;
-    if (inr) {
-        unsigned int s = h;
-        ulonglong2 v = sv;
-        while (v.x != key && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(m.slots + s); }
-        if (v.x == key) { slot = (int)s; count = meta_count(v.y); own_out = 1; }
+    {   // the one round trip of the common case; the prefetched candidates are consumed right here, so that their registers are free
+        // again before the fallback below puts its probes in flight
+        const ulonglong2 sv = load_slot(m.slots + h);
+        double cx[ROUNDS], cy[ROUNDS], cz[ROUNDS];
+        pair_load_candidates<ROUNDS>(m, h, l2, cx, cy, cz);
+        if (inr) {
+            unsigned int s = h;
+            ulonglong2 v = sv;
+            while (v.x != key && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(m.slots + s); }
+            if (v.x == key) { slot = (int)s; count = meta_count(v.y); own_out = 1; }
+        }
+        if (slot >= 0) {
+            if ((unsigned int)slot != h) pair_load_candidates<ROUNDS>(m, (unsigned int)slot, l2, cx, cy, cz);   // displaced by a collision: second trip
+            pair_scan<ROUNDS>(p, l2, count, cx, cy, cz, bd2, br, tx, ty, tz);
+        }
     }
     // fallback (voxel_hash_map.cpp:76-101): the occupied neighbour with the largest (|delta|^2 class, birth); lane l2 probes cells l2, l2+2, ...
     int bd = -1, bslot = -1;
     unsigned long long bmeta = 0ull;
     if (slot < 0) {
-        constexpr int BATCH = ROUNDS <= 5 ? 13 : 7;   // cells per lane and round trip (registers: 16 B per probe in flight)
+        ulonglong2 got[13];
 #pragma unroll
-        for (int u0 = 0; u0 < 13; u0 += BATCH) {
-            ulonglong2 got[BATCH];
+        for (int u = 0; u < 13; ++u) {
+            const int c = l2 + 2 * u;
+            const int x = kx + NB_ALL[c][0], y = ky + NB_ALL[c][1], z = kz + NB_ALL[c][2];
+            got[u] = key_in_range(x, y, z) ? load_slot(m.slots + slot_of(pack_key(x, y, z), m.shift)) : make_ulonglong2(KEY_EMPTY, 0ull);
+        }
 #pragma unroll
-            for (int u = 0; u < BATCH; ++u) {
-                const int c = l2 + 2 * (u0 + u);
-                got[u] = make_ulonglong2(KEY_EMPTY, 0ull);
-                if (u0 + u < 13 && c < 26) {
-                    const int x = kx + NB_ALL[c][0], y = ky + NB_ALL[c][1], z = kz + NB_ALL[c][2];
-                    if (key_in_range(x, y, z)) got[u] = load_slot(m.slots + slot_of(pack_key(x, y, z), m.shift));
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < BATCH; ++u) {
-                const int c = l2 + 2 * (u0 + u);
-                ulonglong2 v = got[u];
-                if (u0 + u < 13 && c < 26 && v.x != KEY_EMPTY) {
-                    const unsigned long long want = pack_key(kx + NB_ALL[c][0], ky + NB_ALL[c][1], kz + NB_ALL[c][2]);
-                    unsigned int s = slot_of(want, m.shift);
-                    while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(m.slots + s); }
-                    if (v.x == want) {
-                        const int d = c < 8 ? 3 : (c < 20 ? 2 : 1);
-                        if (d > bd || (d == bd && v.y > bmeta)) { bd = d; bmeta = v.y; bslot = (int)s; }
-                    }
+        for (int u = 0; u < 13; ++u) {
+            const int c = l2 + 2 * u;
+            ulonglong2 v = got[u];
+            if (v.x != KEY_EMPTY) {
+                const unsigned long long want = pack_key(kx + NB_ALL[c][0], ky + NB_ALL[c][1], kz + NB_ALL[c][2]);
+                unsigned int s = slot_of(want, m.shift);
+                while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(m.slots + s); }
+                if (v.x == want) {
+                    const int d = c < 8 ? 3 : (c < 20 ? 2 : 1);
+                    if (d > bd || (d == bd && v.y > bmeta)) { bd = d; bmeta = v.y; bslot = (int)s; }
                 }
             }
         }
@@ -351,17 +363,11 @@ __device__ __forceinline__ void pair_closest(const MapView &m, const V3 &p, int 
         const unsigned long long om = __shfl_xor_sync(0xFFFFFFFFu, bmeta, 1);
         if (od > bd || (od == bd && om > bmeta)) { bd = od; bmeta = om; bslot = os; }
     }
-    if (slot < 0) { slot = bslot; count = bslot >= 0 ? meta_count(bmeta) : 0; }
-    if (slot >= 0 && (unsigned int)slot != h) pair_load_candidates<ROUNDS>(m, (unsigned int)slot, l2, cx, cy, cz);   // displaced or neighbour voxel: second trip
-    double bd2 = 1.7976931348623157e308, tx = 0.0, ty = 0.0, tz = 0.0;
-    int br = 0x7FFFFFFF;
-    if (slot >= 0) {
-#pragma unroll
-        for (int k = 0; k < ROUNDS; ++k) {
-            const int r = l2 + 2 * k;
-            const double d = sqnorm3(p.x - cx[k], p.y - cy[k], p.z - cz[k]);
-            if (r < count && d < bd2) { bd2 = d; br = r; tx = cx[k]; ty = cy[k]; tz = cz[k]; }
-        }
+    if (slot < 0 && bslot >= 0) {   // neighbour voxel: its candidates are a second trip
+        slot = bslot; count = meta_count(bmeta);
+        double cx[ROUNDS], cy[ROUNDS], cz[ROUNDS];
+        pair_load_candidates<ROUNDS>(m, (unsigned int)slot, l2, cx, cy, cz);
+        pair_scan<ROUNDS>(p, l2, count, cx, cy, cz, bd2, br, tx, ty, tz);
     }
     {
         const double od = __shfl_xor_sync(0xFFFFFFFFu, bd2, 1), ox = __shfl_xor_sync(0xFFFFFFFFu, tx, 1), oy = __shfl_xor_sync(0xFFFFFFFFu, ty, 1),

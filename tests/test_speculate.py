@@ -162,3 +162,54 @@ def test_out_of_range_point_commits_the_frame(ctx, pkg, scans):
         k.close()
         for p in pins:
             p.free()
+
+
+@pytest.mark.parametrize("cap,voxel", [(10, 1.0), (20, 1.0), (3, 1.0), (10, 0.35)])
+def test_cluster_loop_matches_classic_shape(ctx, pkg, cap, voxel):
+    """LIMU_OPT_CLUSTER_LOOP: the Gauss-Newton loop on one 16-CTA cluster (two lanes per query, rows through distributed shared memory,
+    IQR with one grid barrier) against the classic shape (eight lanes per query, global-memory barrier): identical integer results
+    (cloud sizes, iteration counts, map voxels and counts), poses to rounding (the order of the FP64 row sums differs).
+    voxel 0.35 m makes > 3840 keypoints per scan: the multi-pass path of the cluster kernel (working cloud in memory) and, with > 4096
+    IQR candidates, its one-CTA select; the decimated first scan makes the launch hint small."""
+    from importlib import import_module
+    synth = import_module("limu_b200.synth")
+    scene = synth.Scene(seed=5)
+    traj = synth.loop_trajectory(8, radius=30.0, step=0.5)
+    dense = voxel < 1.0
+    seq = [synth.cast_scan(scene, traj[i], traj[i + 1], beams=64 if dense else 32, azimuth_steps=2000 if dense else 900, seed=40 + i) for i in range(7)]
+    if dense:
+        seq[0] = np.ascontiguousarray(seq[0][::16])
+    runs = []
+    for cl in (False, True):
+        k = ctx.KissICP(voxel_size=voxel, cap=cap, deskew=True, icp_max_iteration=80, speculate=False, cluster_loop=cl)
+        rows = []
+        for s_ in seq:
+            d, sr, p = k.register_frame(s_)
+            rows.append((d, sr, p.copy(), k.stats.icp.iterations, k.stats.icp.last_ncorr, k.stats.icp.converged))
+        runs.append((rows, k.local_map().dump()))
+        k.close()
+    (a, da), (b, db) = runs
+    if dense:
+        assert max(len(r[1]) for r in a) > 3840
+    for ra, rb in zip(a, b):
+        assert np.array_equal(ra[0], rb[0]) or np.abs(ra[0] - rb[0]).max() < 1e-9      # deskewed with poses that agree to rounding
+        assert ra[1].shape == rb[1].shape and ra[3] == rb[3] and ra[4] == rb[4] and ra[5] == rb[5]
+        np.testing.assert_allclose(ra[2], rb[2], rtol=0, atol=1e-9)
+    assert np.array_equal(da[0], db[0]) and np.array_equal(da[1], db[1])
+    np.testing.assert_allclose(da[2], db[2], rtol=0, atol=1e-8)
+
+
+def test_cluster_loop_degenerate_inputs(ctx, pkg):
+    """Empty map on the first scan (ICP returns init_guess, registration.cpp:99-100), one-point and empty keypoint clouds."""
+    for cl in (False, True):
+        k = ctx.KissICP(voxel_size=1.0, cap=10, deskew=False, icp_max_iteration=20, speculate=False, cluster_loop=cl)
+        one = np.array([[10.0, 2.0, 1.0, 0.5]], np.float32)
+        d, sr, p = k.register_frame(one)
+        assert len(d) == 1 and len(sr) == 1 and np.array_equal(p, [0, 0, 0, 1, 0, 0, 0])
+        d, sr, p = k.register_frame(one)                       # map now holds that point
+        assert len(d) == 1 and len(sr) == 1 and np.abs(p[4:]).max() < 1e-9
+        two = np.array([[10.0, 2.0, 1.0, 0.5], [30.0, -4.0, 2.0, 0.7]], np.float32)
+        d, sr, p = k.register_frame(two)
+        assert len(d) == 2 and 1 <= len(sr) <= 2
+        assert k.local_map().size()[0] == 2
+        k.close()

@@ -31,4 +31,6 @@ r = np.array(rows)
 names = ["iqr", "icp_loop", "insert_claim", "insert_place", "evict_sweep"]
 print({n: round(float(v), 2) for n, v in zip(names, r.mean(axis=0))}, "total_us", round(float(r.sum(axis=1).mean()), 2), "iters/scan", np.mean(iters),
       "icp_us_per_iter", round(float(r[:, 1].mean() / np.mean(iters)), 2))
-print("solve breakdown (last iteration of the last scan, ns): ldlt", marks[9] - marks[8], "exp", marks[10] - marks[9], "mul", marks[11] - marks[10], "log+norm", marks[12] - marks[11])
+print("classic shape, solve breakdown (last iteration of the last scan, ns, 512 ns ticks): ldlt", marks[9] - marks[8], "exp", marks[10] - marks[9])
+print("cluster shape, last iteration of the last scan (SM cycles, clock64): row reduce + DSMEM push + cluster barrier", marks[7] - marks[6], "fold", marks[8] - marks[7],
+      "ldlt", marks[9] - marks[8], "exp", marks[10] - marks[9])
