@@ -74,7 +74,7 @@ struct limu_odom {
     // behind this scan's frame kernel, with its deskew twist left on the device by that kernel, so the host round trip of this scan
     // (result copy, wake-up, scalar glue, launch) overlaps it instead of idling the GPU.
     bool speculate = true;
-    bool cluster_loop = true;               // LIMU_OPT_CLUSTER_LOOP: run the Gauss-Newton loop on one 16-CTA cluster (registration.cu, k_frame_cluster)
+    bool cluster_loop = false;              // LIMU_OPT_CLUSTER_LOOP: run the Gauss-Newton loop on one 16-CTA cluster (registration.cu, k_frame_cluster); measured slower, opt-in
     const void *hint_ptr = nullptr;         // next scan (device float4 rows), set by the caller before registering the current one
     int64_t hint_n = 0;
     const void *spec_ptr = nullptr;         // scan whose k_voxelize is already in flight / done
@@ -328,7 +328,7 @@ int limu_odom_create(limu_ctx *c, const limu_odom_config *cfg, limu_odom **out) 
     o->ctx = c;
     o->cfg = *cfg;
     if (const char *e = getenv("LIMU_SPECULATE")) o->speculate = atoi(e) != 0;        // default of LIMU_OPT_SPECULATE (on)
-    if (const char *e = getenv("LIMU_CLUSTER_LOOP")) o->cluster_loop = atoi(e) != 0;   // default of LIMU_OPT_CLUSTER_LOOP (on)
+    if (const char *e = getenv("LIMU_CLUSTER_LOOP")) o->cluster_loop = atoi(e) != 0;   // default of LIMU_OPT_CLUSTER_LOOP (off)
     int64_t capv = cfg->map_capacity_voxels;
     if (capv <= 0) {   // a sensor sees a shell, not a ball: ~ (2 r / v)^2 * 8 voxels is generous for one neighbourhood
         const double side = 2.0 * cfg->max_range / cfg->voxel_size;

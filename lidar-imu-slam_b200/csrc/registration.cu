@@ -722,7 +722,9 @@ __device__ __forceinline__ int cluster_iqr_compact(ClusterSmem &sm, const IcpArg
 
 #ifdef LIMU_ICP_PHASE_TIMING
 #define CT_MARK(k) do { if (blockIdx.x == 0 && lane == 0) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
+#define CW_MARK(k, w) do { if (blockIdx.x == 0 && warp == (w) && lane == 0) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
 #else
+#define CW_MARK(k, w) do {} while (0)
 #define CT_MARK(k) do {} while (0)
 #endif
 
@@ -785,6 +787,7 @@ static __global__ void __launch_bounds__(CL_THREADS, 1) k_frame_cluster(const Ic
             const bool no_more = j >= A.max_iter;             // only wait for the tail of iteration j-1
             if (warp > 0) {
                 if (!no_more) {
+                    CW_MARK(11, 1);
                     double acc = 0.0;                         // lane L: running total of sum index L>>1
                     int ncorr = 0, ncand = 0, nmiss = 0;
                     const volatile double *Pv = j == 0 ? sm.Tinit : sm.E;
@@ -822,6 +825,7 @@ static __global__ void __launch_bounds__(CL_THREADS, 1) k_frame_cluster(const Ic
                         ncand += lead ? count : 0;
                         nmiss += (lead && !own) ? 1 : 0;
                     }
+                    CW_MARK(12, 1);
                     ncorr = __reduce_add_sync(0xFFFFFFFFu, ncorr);
                     ncand = __reduce_add_sync(0xFFFFFFFFu, ncand);
                     nmiss = __reduce_add_sync(0xFFFFFFFFu, nmiss);
@@ -830,6 +834,7 @@ static __global__ void __launch_bounds__(CL_THREADS, 1) k_frame_cluster(const Ic
             } else if (j > 0) {
                 // tail of iteration j-1 on the solver warp, overlapped with pass j: T_icp = estimate * T_icp (:122) on lane 0,
                 // |log(estimate)| < eps (:124) on lane 1
+                CW_MARK(13, 0);
                 const Pose est = pose_load(sm.E);
                 if (lane == 0) pose_store(mul(est, pose_load(sm.Ticp)), sm.Ticp);
                 if (lane == 1) {
@@ -837,6 +842,7 @@ static __global__ void __launch_bounds__(CL_THREADS, 1) k_frame_cluster(const Ic
                     se3_log(est, lg);
                     sm.done = norm6(lg) < A.eps;
                 }
+                CW_MARK(14, 0);
             }
             __syncthreads();                                  // S1: partial sums of pass j and the verdict on iteration j-1
             if (j > 0 && sm.done) { converged = 1; break; }   // (the pass just made belongs to an iteration that does not exist)

@@ -33,4 +33,5 @@ print({n: round(float(v), 2) for n, v in zip(names, r.mean(axis=0))}, "total_us"
       "icp_us_per_iter", round(float(r[:, 1].mean() / np.mean(iters)), 2))
 print("classic shape, solve breakdown (last iteration of the last scan, ns, 512 ns ticks): ldlt", marks[9] - marks[8], "exp", marks[10] - marks[9])
 print("cluster shape, last iteration of the last scan (SM cycles, clock64): row reduce + DSMEM push + cluster barrier", marks[7] - marks[6], "fold", marks[8] - marks[7],
-      "ldlt", marks[9] - marks[8], "exp", marks[10] - marks[9])
+      "ldlt", marks[9] - marks[8], "exp", marks[10] - marks[9], "| pass of warp 1", marks[12] - marks[11], "tail of the solver warp", marks[14] - marks[13],
+      "| raw marks 6..14 relative to mark 11:", [int(marks[k] - marks[11]) for k in (6, 7, 8, 9, 10, 11, 12, 13, 14)])
