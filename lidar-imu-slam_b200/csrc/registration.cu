@@ -293,7 +293,7 @@ __device__ __forceinline__ void icp_query_pass(const IcpArgs &A, const volatile 
         if (PLANE) {
             double nrm[3] = {0.0, 0.0, 0.0};
             bool planar = false;
-            if (gate && my_rank >= 0) planar = voxel_normal(A.map, slot, meta_count(load_slot(A.map.slots + slot).y), nrm) != 0;
+            if (gate && my_rank >= 0) planar = voxel_normal(A.map, slot, meta_count(load_slot(slot_at(A.map, (unsigned int)slot)).y), nrm) != 0;
             double c[32];
             contribution_plane(c, s, tg, nrm, A.th, planar, count, on && !own, on);
             acc += warp_reduce_scatter32(c);
@@ -308,13 +308,35 @@ __device__ __forceinline__ void icp_query_pass(const IcpArgs &A, const volatile 
     }
 }
 
-// The same pass in the latency shape: eight lanes per query (four queries per warp), see group8_closest.
-template <bool NN27, bool PLANE>
+// Lane l8 of a query's eight lanes owns sums 2*l8 and 2*l8+1 of the 16 (same expressions, same operation order as contribution()):
+// every lane knows s, t and d2 once the lookup is done, so the eight lanes of a group produce the 16 values without any exchange and
+// each keeps two running FP64 accumulators for the whole pass (SIMT: the redundant weight is free).
+__device__ __forceinline__ void contribution_pair(int l8, const V3 &s, const V3 &t, double d2, double th, bool on, double &c0, double &c1) {
+    const double rx = s.x - t.x, ry = s.y - t.y, rz = s.z - t.z;       // residual = source - target (:48)
+    const double den = th + d2;
+    const double w = on ? (th * th) / (den * den) : 0.0;                // :57-58
+    const double wx = w * s.x, wy = w * s.y, wz = w * s.z;
+    switch (l8) {
+        case 0: c0 = w; c1 = wx; break;
+        case 1: c0 = wy; c1 = wz; break;
+        case 2: c0 = wx * s.x; c1 = wx * s.y; break;
+        case 3: c0 = wx * s.z; c1 = wy * s.y; break;
+        case 4: c0 = wy * s.z; c1 = wz * s.z; break;
+        case 5: c0 = w * rx; c1 = w * ry; break;
+        case 6: c0 = w * rz; c1 = w * (s.y * rz - s.z * ry); break;
+        default: c0 = w * (s.z * rx - s.x * rz); c1 = w * (s.x * ry - s.y * rx); break;
+    }
+}
+
+// One pass over this warp's share of the queries with eight lanes per query (four queries per warp and step), see group8_closest.
+// On return lane L holds the warp total of sum index L>>1 (the layout of warp_reduce_scatter16) in `acc`.
+template <bool NN27, bool PLANE, int ROUNDS>
 __device__ __forceinline__ void icp_query_pass_grouped(const IcpArgs &A, const volatile double *Pv, const double *in, int64_t n, int64_t gbase, int64_t gstride,
                                                        int lane, double &acc, int &ncorr, int &ncand, int &nmiss) {
     const int l8 = lane & 7;
     const unsigned gmask = 0xFFu << (lane & 24);
     const int64_t wfirst = gbase - (lane >> 3);   // first group of this warp: the four groups of a warp iterate together
+    double a0 = 0.0, a1 = 0.0;                    // reference rules: sums 2*l8 and 2*l8+1 over this group's queries
     for (int64_t q0 = wfirst; q0 < n; q0 += gstride) {
         const int64_t q = q0 + (lane >> 3);
         const bool on = q < n;
@@ -325,32 +347,45 @@ __device__ __forceinline__ void icp_query_pass_grouped(const IcpArgs &A, const v
             const Pose P{Pv[0], Pv[1], Pv[2], Pv[3], Pv[4], Pv[5], Pv[6]};
             s = apply(P, V3{in[3 * q], in[3 * q + 1], in[3 * q + 2]});
             if (l8 == 0) { A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z; }
-            if (NN27) group8_closest27(A.map, s, gmask, l8, slot, count, own, d2, my_rank);
-            else group8_closest(A.map, s, gmask, l8, slot, count, own, d2, my_rank);
-            if (my_rank >= 0) {
-                const double *bx = voxel_rows(A.map, (unsigned int)slot);
-                tg = V3{__ldg(bx + my_rank), __ldg(bx + A.map.capp + my_rank), __ldg(bx + 2 * A.map.capp + my_rank)};
+            if (NN27) {
+                group8_closest27(A.map, s, gmask, l8, slot, count, own, d2, my_rank);
+                if (my_rank >= 0) {
+                    const double *bx = voxel_rows(A.map, (unsigned int)slot);
+                    tg = V3{ldm(bx + my_rank), ldm(bx + A.map.capp + my_rank), ldm(bx + 2 * A.map.capp + my_rank)};
+                }
             } else {
-                d2 = sqnorm3(tg.x - s.x, tg.y - s.y, tg.z - s.z);   // nothing found -> (0,0,0), range-tested like a real point
+                group8_closest<ROUNDS>(A.map, s, gmask, l8, slot, count, own, d2, my_rank, tg);
             }
+            if (my_rank < 0) d2 = sqnorm3(tg.x - s.x, tg.y - s.y, tg.z - s.z);   // nothing found -> (0,0,0), range-tested like a real point
         }
         const bool lead = on && l8 == 0;
-        const bool gate = lead && d2 < A.tau_sq;
         if (PLANE) {
+            const bool gate = lead && d2 < A.tau_sq;
             double nrm[3] = {0.0, 0.0, 0.0};
             bool planar = false;   // the group's leading lane fits the plane of the matched voxel (sequential sums: bit-identical to the oracle)
-            if (gate && my_rank >= 0) planar = voxel_normal(A.map, slot, meta_count(load_slot(A.map.slots + slot).y), nrm) != 0;
+            if (gate && my_rank >= 0) planar = voxel_normal(A.map, slot, meta_count(load_slot(slot_at(A.map, (unsigned int)slot)).y), nrm) != 0;
             double c[32];
             contribution_plane(c, s, tg, nrm, A.th, planar, count, lead && !own, lead);
             acc += warp_reduce_scatter32(c);
         } else {
-            double c[16];
-            contribution(c, s, tg, d2, A.th, gate);
-            acc += warp_reduce_scatter16(c);
-            ncorr += gate ? 1 : 0;
+            const bool gate = on && d2 < A.tau_sq;   // known to all eight lanes
+            if (gate) {
+                double c0, c1;
+                contribution_pair(l8, s, tg, d2, A.th, true, c0, c1);
+                a0 += c0; a1 += c1;
+            }
+            ncorr += (gate && l8 == 0) ? 1 : 0;
             ncand += lead ? count : 0;
             nmiss += (lead && !own) ? 1 : 0;
         }
+    }
+    if (!PLANE) {
+        // four groups per warp -> warp totals, then into the reduce-scatter layout the row code expects (lane L: sum L>>1)
+        a0 += __shfl_xor_sync(0xFFFFFFFFu, a0, 8); a1 += __shfl_xor_sync(0xFFFFFFFFu, a1, 8);
+        a0 += __shfl_xor_sync(0xFFFFFFFFu, a0, 16); a1 += __shfl_xor_sync(0xFFFFFFFFu, a1, 16);
+        const int k = lane >> 1;
+        const double v0 = __shfl_sync(0xFFFFFFFFu, a0, k >> 1), v1 = __shfl_sync(0xFFFFFFFFu, a1, k >> 1);
+        acc += (k & 1) ? v1 : v0;
     }
 }
 
@@ -408,11 +443,24 @@ __device__ __forceinline__ void frame_update_epilogue(const IcpArgs &A, GridSync
     }
 }
 
-// SHAPE 0 = latency build (eight lanes per query, a few thousand keypoints: one CTA per SM at most, so the compiler may
-// use up to 255 registers and the serial Gauss-Newton solve stays out of local memory); SHAPE 1 = bandwidth build
-// (one lane per query + cooperative scan, 64 registers -> 4 CTAs/SM for the HBM-bound kernel mode).
+// x = LDLT(H).solve(-g) from the 16 sums (registration.cpp:90), one thread. Kept out of line: its ~90 live registers would otherwise
+// compete with the query pass of the cluster kernel for the 128 registers a 512-thread CTA allows.
+static __device__ __noinline__ void solve_normal_equations(const double *S, double *x_out) {
+    double H[36], g[6], x[6];
+    expand_normal_equations(S, H, g);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g[k] = -g[k];
+    ldlt6_solve(H, g, x);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) x_out[k] = x[k];
+}
+
+// SHAPE 0 = latency build (a few thousand keypoints: one CTA per SM at most, so the compiler may use up to 255 registers and the serial
+// Gauss-Newton solve stays out of local memory); SHAPE 1 = bandwidth build for the HBM-bound kernel mode (millions of queries): 85
+// registers -> 3 CTAs = 96 eight-lane groups per SM, each with one 384/512-byte block in flight (~48 KB per SM, above what the measured
+// HBM latency x bandwidth asks for), the query pass free of spills, the solve out of line.
 template <int SHAPE, bool NN27, bool PLANE>
-static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_persistent(const IcpArgs A) {
+static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 3) k_icp_persistent(const IcpArgs A) {
     constexpr int NSX = PLANE ? NSP : NS;              // doubles per partial row
     constexpr int I_NCORR = PLANE ? 27 : 16;           // where the three counters sit in a row
     __shared__ double red[(ICP_BLOCK / 32) * 32];
@@ -458,8 +506,13 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
         int ncorr = 0, ncand = 0, nmiss = 0;
         const volatile double *Pv = j == 0 ? Tinit : E;   // re-read per batch: keeps 14 registers free across the lookup
         const double *in = j == 0 ? A.points : A.work;
-        if (SHAPE == 0) icp_query_pass_grouped<NN27, PLANE>(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
-        else icp_query_pass<NN27, PLANE>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
+        if (SHAPE == 0 || (!NN27 && !PLANE)) {   // eight lanes per query (both shapes; the opt-in variants of the bandwidth shape keep one lane per query)
+            if (A.map.cap <= 8) icp_query_pass_grouped<NN27, PLANE, 1>(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
+            else if (A.map.cap <= 16) icp_query_pass_grouped<NN27, PLANE, 2>(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
+            else icp_query_pass_grouped<NN27, PLANE, 3>(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
+        } else {
+            icp_query_pass<NN27, PLANE>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
+        }
         PT_MARK(1);
         double *rows = A.partials + (size_t)(j & 1) * A.icp_blocks * NSX;
         if (PLANE) {
@@ -559,14 +612,18 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 4) k_icp_pe
             // while lane 1 takes log(estimate) for the convergence test
             FT_MARK(8);
             if (lane == 0) {
-                double H[36], g[6], x[6];
-                if (PLANE) expand_plane_equations(S, H, g);
-                else expand_normal_equations(S, H, g);
+                if (SHAPE == 1 && !PLANE) {
+                    solve_normal_equations(S, red);               // out of line: the bandwidth build has no registers to spare
+                } else {
+                    double H[36], g[6], x[6];
+                    if (PLANE) expand_plane_equations(S, H, g);
+                    else expand_normal_equations(S, H, g);
 #pragma unroll
-                for (int k = 0; k < 6; ++k) g[k] = -g[k];
-                ldlt6_solve(H, g, x);                             // JTJ.ldlt().solve(-JTr) :90
+                    for (int k = 0; k < 6; ++k) g[k] = -g[k];
+                    ldlt6_solve(H, g, x);                         // JTJ.ldlt().solve(-JTr) :90
 #pragma unroll
-                for (int k = 0; k < 6; ++k) red[k] = x[k];
+                    for (int k = 0; k < 6; ++k) red[k] = x[k];
+                }
                 FT_MARK(9);
             }
             __syncwarp();
@@ -727,18 +784,6 @@ __device__ __forceinline__ int cluster_iqr_compact(ClusterSmem &sm, const IcpArg
 #define CW_MARK(k, w) do {} while (0)
 #define CT_MARK(k) do {} while (0)
 #endif
-
-// x = LDLT(H).solve(-g) from the 16 sums (registration.cpp:90), one thread. Kept out of line: its ~90 live registers would otherwise
-// compete with the query pass of the cluster kernel for the 128 registers a 512-thread CTA allows.
-static __device__ __noinline__ void solve_normal_equations(const double *S, double *x_out) {
-    double H[36], g[6], x[6];
-    expand_normal_equations(S, H, g);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) g[k] = -g[k];
-    ldlt6_solve(H, g, x);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) x_out[k] = x[k];
-}
 
 template <int ROUNDS>   // candidate ranks per lane of a query pair: max_points_per_voxel <= 2 * ROUNDS
 static __global__ void __launch_bounds__(CL_THREADS, 1) k_frame_cluster(const IcpArgs A) {
@@ -1003,7 +1048,7 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
     }
     const bool grouped = n_hint <= 16384 && m->cap <= 64;   // latency shape: eight lanes per query, one CTA per SM
     const int64_t want = std::max<int64_t>(1, div_up(std::max<int64_t>(n_hint, 1) * (grouped ? 8 : 1), ICP_BLOCK));
-    int grid = (int)std::min<int64_t>(want, (int64_t)c->sm_count * (grouped ? 1 : std::min(g_icp_blocks_per_sm, 4)));
+    int grid = (int)std::min<int64_t>(want, (int64_t)c->sm_count * (grouped ? 1 : std::min(g_icp_blocks_per_sm, 3)));
     grid = (int)std::min<int64_t>(grid, (int64_t)partial_rows);
     const int icp_blocks = grid;   // the Gauss-Newton loop is latency bound at keypoint counts: it runs on the leading CTAs only
     if (fuse && fuse->upd_down) grid = std::max(grid, c->sm_count);   // the insert and the eviction sweep want one CTA per SM
@@ -1059,7 +1104,7 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
     return LIMU_OK;
 }
 
-int icp_partial_rows(limu_ctx *c) { return c->sm_count * 4; }
+int icp_partial_rows(limu_ctx *c) { return c->sm_count * 4; }   // >= the largest grid of any shape
 
 #ifdef LIMU_ICP_PHASE_TIMING
 extern "C" int limu_debug_frame_marks(double out[16]) {
@@ -1071,7 +1116,7 @@ extern "C" int limu_debug_frame_marks(double out[16]) {
 #endif
 
 // ---- un-fused baseline for the sharded loop: step kernel -> fold kernel -> ncclAllReduce -> solve kernel, host in the loop ----
-static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_step(const IcpArgs A, const double *state /* E at +24 */, int first, double *rows) {
+static __global__ void __launch_bounds__(ICP_BLOCK, 3) k_icp_step(const IcpArgs A, const double *state /* E at +24 */, int first, double *rows) {
     __shared__ double red[(ICP_BLOCK / 32) * 32];
     __shared__ double Pose7[7];
     const int64_t n = A.n_max;
@@ -1081,7 +1126,10 @@ static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_icp_step(const IcpArgs 
     double acc = 0.0;
     int ncorr = 0, ncand = 0, nmiss = 0;
     const int64_t wbase = ((int64_t)blockIdx.x * (ICP_BLOCK / 32) + warp) * 32, wstride = (int64_t)A.icp_blocks * ICP_BLOCK;
-    icp_query_pass<false, false>(A, Pose7, first ? A.points : A.work, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
+    const double *in = first ? A.points : A.work;
+    if (A.map.cap <= 8) icp_query_pass_grouped<false, false, 1>(A, Pose7, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
+    else if (A.map.cap <= 16) icp_query_pass_grouped<false, false, 2>(A, Pose7, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
+    else icp_query_pass_grouped<false, false, 3>(A, Pose7, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
     ncorr = __reduce_add_sync(0xFFFFFFFFu, ncorr);
     ncand = __reduce_add_sync(0xFFFFFFFFu, ncand);
     nmiss = __reduce_add_sync(0xFFFFFFFFu, nmiss);

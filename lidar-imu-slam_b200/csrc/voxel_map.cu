@@ -12,9 +12,9 @@ namespace limu {
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-static __global__ void k_map_clear(Slot *slots, int64_t C) {
+static __global__ void k_map_clear(MapView m, int64_t C) {
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < C; s += (int64_t)gridDim.x * blockDim.x)
-        slots[s] = Slot{KEY_EMPTY, META_NONE};
+        *slot_at(m, (unsigned int)s) = Slot{KEY_EMPTY, META_NONE};
 }
 
 static __global__ void __launch_bounds__(256) k_insert_claim(MapView m, const double *__restrict__ xyz, int64_t n_max, const int *n_dev,
@@ -47,45 +47,53 @@ static __global__ void __launch_bounds__(256) k_remove_far(MapView m, const doub
 static __global__ void __launch_bounds__(256) k_rehash(MapView old, int64_t oldC, MapView nw, unsigned long long *new_counters) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= oldC) return;
-    const unsigned long long key = old.slots[s].key;
+    const unsigned long long key = slot_at(old, (unsigned int)s)->key;
     if (key >= KEY_TOMB) return;
     unsigned int t = slot_of(key, nw.shift);
     for (;;) {
-        const unsigned long long cur = atomicCAS(&nw.slots[t].key, KEY_EMPTY, key);
+        const unsigned long long cur = atomicCAS(&slot_at(nw, t)->key, KEY_EMPTY, key);
         if (cur == KEY_EMPTY) break;
         t = (t + 1) & nw.mask;
     }
     nw.live[atomicAdd(&new_counters[3], 1ull)] = t;   // the rebuilt list holds live voxels only
-    const unsigned long long meta = old.slots[s].meta;
+    const unsigned long long meta = slot_at(old, (unsigned int)s)->meta;
     const int count = meta_count(meta);
-    nw.slots[t].meta = meta;
+    slot_at(nw, t)->meta = meta;
     const double *src = voxel_rows(old, (unsigned int)s);
     double *dst = voxel_rows(nw, t);
     for (int r = 0; r < count; ++r) { dst[r] = src[r]; dst[nw.capp + r] = src[old.capp + r]; dst[2 * nw.capp + r] = src[2 * old.capp + r]; }
 }
 
-static __global__ void k_sum_counts(const Slot *slots, int64_t C, unsigned long long *out /* [0]=voxels [1]=points */) {
+// Both walk the dense live list (counters[3] entries; erased voxels read KEY_TOMB) instead of the C block headers.
+static __global__ void k_sum_counts(MapView m, const unsigned long long *counters, unsigned long long *out /* [0]=voxels [1]=points */) {
+    const int64_t used = (int64_t)counters[3];
     unsigned long long v = 0, p = 0;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < C; s += (int64_t)gridDim.x * blockDim.x) {
-        if (slots[s].key < KEY_TOMB) { ++v; p += (unsigned long long)meta_count(slots[s].meta); }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < used; i += (int64_t)gridDim.x * blockDim.x) {
+        const Slot *sl = slot_at(m, m.live[i]);
+        if (sl->key < KEY_TOMB) { ++v; p += (unsigned long long)meta_count(sl->meta); }
     }
     for (int o = 16; o > 0; o >>= 1) { v += __shfl_down_sync(0xFFFFFFFFu, v, o); p += __shfl_down_sync(0xFFFFFFFFu, p, o); }
     if ((threadIdx.x & 31) == 0 && (v | p)) { atomicAdd(&out[0], v); atomicAdd(&out[1], p); }
 }
 
 // Live slots -> (birth, slot) pairs, unordered; the host sorts by birth to recover creation order.
-static __global__ void k_collect_live(const Slot *slots, int64_t C, unsigned long long *pairs, unsigned long long *n_out) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = s < C && slots[s].key < KEY_TOMB;
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, live);
-    unsigned long long base = 0;
-    const int lane = threadIdx.x & 31;
-    if (lane == 0 && bal) base = atomicAdd(n_out, (unsigned long long)__popc(bal));
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (live) {
-        const unsigned long long j = base + __popc(bal & ((1u << lane) - 1u));
-        pairs[2 * j] = meta_birth(slots[s].meta);
-        pairs[2 * j + 1] = (unsigned long long)s;
+static __global__ void k_collect_live(MapView m, const unsigned long long *counters, unsigned long long *pairs, unsigned long long *n_out) {
+    const int64_t used = (int64_t)counters[3];
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < used; i0 += (int64_t)gridDim.x * blockDim.x) {   // whole warps stay converged for the ballot
+        const int64_t i = i0 + threadIdx.x;
+        unsigned int s = 0;
+        bool live = false;
+        if (i < used) { s = m.live[i]; live = slot_at(m, s)->key < KEY_TOMB; }
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, live);
+        unsigned long long base = 0;
+        const int lane = threadIdx.x & 31;
+        if (lane == 0 && bal) base = atomicAdd(n_out, (unsigned long long)__popc(bal));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (live) {
+            const unsigned long long j = base + __popc(bal & ((1u << lane) - 1u));
+            pairs[2 * j] = meta_birth(slot_at(m, s)->meta);
+            pairs[2 * j + 1] = (unsigned long long)s;
+        }
     }
 }
 
@@ -94,9 +102,9 @@ static __global__ void k_gather_voxels(MapView m, const unsigned int *order, int
     if (j >= nv) return;
     const unsigned int s = order[j];
     int x, y, z;
-    unpack_key(m.slots[s].key, x, y, z);
+    unpack_key(slot_at(m, s)->key, x, y, z);
     keys[3 * j] = x; keys[3 * j + 1] = y; keys[3 * j + 2] = z;
-    const int c = meta_count(m.slots[s].meta);
+    const int c = meta_count(slot_at(m, s)->meta);
     counts[j] = c;
     const double *b = voxel_rows(m, s);
     for (int r = 0; r < c; ++r) {   // back to array-of-structs for the host
@@ -117,7 +125,7 @@ static __global__ void __launch_bounds__(256) k_closest(MapView m, const double 
     if (out_xyz) { out_xyz[3 * i] = r.x; out_xyz[3 * i + 1] = r.y; out_xyz[3 * i + 2] = r.z; }
     if (out_key) {
         int x = INT32_MIN, y = INT32_MIN, z = INT32_MIN;
-        if (r.slot >= 0 && r.rank >= 0) unpack_key(m.slots[r.slot].key, x, y, z);
+        if (r.slot >= 0 && r.rank >= 0) unpack_key(slot_at(m, (unsigned int)r.slot)->key, x, y, z);
         out_key[3 * i] = x; out_key[3 * i + 1] = y; out_key[3 * i + 2] = z;
     }
     if (out_rank) out_rank[i] = r.rank;
@@ -148,14 +156,13 @@ int transform_device(limu_ctx *c, const double *pose_dev, const double *in, doub
 
 int map_alloc(limu_map *m, int64_t C) {
     limu_ctx *c = m->ctx;
-    m->slots.release(); m->pts.release(); m->pend.release(); m->live.release();
-    LIMU_TRY(m->slots.reserve((size_t)C * sizeof(Slot)));
+    m->blk.release(); m->pend.release(); m->live.release();
+    LIMU_TRY(m->blk.reserve((size_t)C * limu::block_stride(m->cap) * 8));
     LIMU_TRY(m->live.reserve((size_t)C * 4));
-    LIMU_TRY(m->pts.reserve((size_t)C * limu::block_stride(m->cap) * 8));
     LIMU_TRY(m->pend.reserve((size_t)C * m->cap * 4));
     m->capacity = C;
     const int blocks = std::min<int64_t>(div_up(C, 256), (int64_t)c->sm_count * 32);
-    k_map_clear<<<blocks, 256, 0, c->stream>>>(m->slots.as<Slot>(), C);
+    k_map_clear<<<blocks, 256, 0, c->stream>>>(m->view(), C);
     LIMU_LAUNCHED();
     LIMU_CUDA_TRY(cudaMemsetAsync(m->pend.p, 0xFF, (size_t)C * m->cap * 4, c->stream));
     LIMU_TRY(m->counters.reserve(8 * sizeof(unsigned long long)));
@@ -168,8 +175,7 @@ int map_alloc(limu_map *m, int64_t C) {
 
 limu::MapView limu_map::view() const {
     limu::MapView v;
-    v.slots = slots.as<limu::Slot>();
-    v.pts = pts.as<double>();
+    v.blk = blk.as<double>();
     v.pend = pend.as<unsigned int>();
     v.live = live.as<unsigned int>();
     v.mask = (unsigned int)(capacity - 1);
@@ -205,11 +211,11 @@ int map_maybe_grow(limu_map *m, int64_t incoming) {
     limu_ctx *c = m->ctx;
     const int64_t newC = std::max<int64_t>(next_pow2((live + incoming) * 4), 1024);
     limu_map old = *m;  // shallow: keeps the old buffers alive
-    m->slots = DevBuf(); m->pts = DevBuf(); m->pend = DevBuf(); m->live = DevBuf(); m->counters = DevBuf();
+    m->blk = DevBuf(); m->pend = DevBuf(); m->live = DevBuf(); m->counters = DevBuf();
     int st = map_alloc(m, newC);
     if (st != LIMU_OK) {
-        m->slots.release(); m->pts.release(); m->pend.release(); m->live.release(); m->counters.release();
-        m->slots = old.slots; m->pts = old.pts; m->pend = old.pend; m->live = old.live; m->counters = old.counters;
+        m->blk.release(); m->pend.release(); m->live.release(); m->counters.release();
+        m->blk = old.blk; m->pend = old.pend; m->live = old.live; m->counters = old.counters;
         m->capacity = old.capacity;
         set_error("voxel map cannot grow to %lld slots", (long long)newC);
         return LIMU_ERR_MAP_FULL;
@@ -220,7 +226,7 @@ int map_maybe_grow(limu_map *m, int64_t incoming) {
     h[0] = (unsigned long long)live; h[1] = 0; h[2] = 0;   // [3] (used slots = length of the live list) was counted by k_rehash itself
     LIMU_CUDA_TRY(cudaMemcpyAsync(m->counters.p, h, 3 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
     LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    old.slots.release(); old.pts.release(); old.pend.release(); old.live.release(); old.counters.release();
+    old.blk.release(); old.pend.release(); old.live.release(); old.counters.release();
     old.pslot = DevBuf(); old.world = DevBuf();  // still owned by *m
     m->used_upper = live;
     return LIMU_OK;
@@ -290,7 +296,7 @@ void limu_map_destroy(limu_map *m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
-    m->slots.release(); m->pts.release(); m->pend.release(); m->live.release(); m->counters.release();
+    m->blk.release(); m->pend.release(); m->live.release(); m->counters.release();
     m->pslot.release(); m->world.release();
     delete m;
 }
@@ -300,7 +306,7 @@ int limu_map_clear(limu_map *m) {
     LIMU_TRY(bind(m->ctx));
     limu_ctx *c = m->ctx;
     const int blocks = std::min<int64_t>(div_up(m->capacity, 256), (int64_t)c->sm_count * 32);
-    k_map_clear<<<blocks, 256, 0, c->stream>>>(m->slots.as<Slot>(), m->capacity);
+    k_map_clear<<<blocks, 256, 0, c->stream>>>(m->view(), m->capacity);
     LIMU_LAUNCHED();
     LIMU_CUDA_TRY(cudaMemsetAsync(m->pend.p, 0xFF, (size_t)m->capacity * m->cap * 4, c->stream));
     LIMU_CUDA_TRY(cudaMemsetAsync(m->counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
@@ -314,8 +320,8 @@ int limu_map_size(limu_map *m, int64_t *n_voxels, int64_t *n_points) {
     limu_ctx *c = m->ctx;
     unsigned long long *d = m->counters.as<unsigned long long>() + 4;
     LIMU_CUDA_TRY(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), c->stream));
-    const int blocks = std::min<int64_t>(div_up(m->capacity, 256), (int64_t)c->sm_count * 8);
-    k_sum_counts<<<blocks, 256, 0, c->stream>>>(m->slots.as<Slot>(), m->capacity, d);
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(div_up(std::max<int64_t>(m->used_upper, 1), 256), (int64_t)c->sm_count * 8));
+    k_sum_counts<<<blocks, 256, 0, c->stream>>>(m->view(), m->counters.as<unsigned long long>(), d);
     LIMU_LAUNCHED();
     unsigned long long *h = static_cast<unsigned long long *>(c->h_pinned);
     LIMU_CUDA_TRY(cudaMemcpyAsync(h, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
@@ -463,8 +469,8 @@ int limu_map_dump(limu_map *m, int32_t *keys, int32_t *counts, double *pts, int6
     LIMU_TRY(c->tmp0.reserve((size_t)nv * 16 + 16, c->stream));
     unsigned long long *cnt = m->counters.as<unsigned long long>() + 6;
     LIMU_CUDA_TRY(cudaMemsetAsync(cnt, 0, 8, c->stream));
-    k_collect_live<<<div_up(m->capacity, 256), 256, 0, c->stream>>>(m->slots.as<Slot>(), m->capacity,
-                                                                   c->tmp0.as<unsigned long long>(), cnt);
+    k_collect_live<<<(int)std::max<int64_t>(1, std::min<int64_t>(div_up(std::max<int64_t>(m->used_upper, 1), 256), (int64_t)c->sm_count * 8)), 256, 0, c->stream>>>(
+        m->view(), m->counters.as<unsigned long long>(), c->tmp0.as<unsigned long long>(), cnt);
     LIMU_LAUNCHED();
     std::vector<unsigned long long> pairs((size_t)nv * 2);
     LIMU_CUDA_TRY(cudaMemcpyAsync(pairs.data(), c->tmp0.p, (size_t)nv * 16, cudaMemcpyDeviceToHost, c->stream));

@@ -4,19 +4,19 @@
 // voxel_hash_map.hpp:14-48, voxel_block.hpp:13-56): tsl::robin_map<Voxel, VoxelBlock> whose blocks hold
 // one heap node per point becomes ONE open-addressing table in HBM:
 //
-//   slots[C]        16 B  {u64 packed (i,j,k) key, u64 meta = birth << 13 | count}   C = power of two, load <= 0.5
-//                          birth = creation sequence of the voxel (= the reference container's address order,
-//                          used only by the 27-cell fallback tie-break, voxel_hash_map.cpp:81-101)
-//   pts[C*stride]   24 B  per point, slot-indexed, structure-of-arrays INSIDE a voxel: voxel s owns three rows
-//                          x[capp] y[capp] z[capp] at pts + s*3*capp (capp = cap rounded up to 4 doubles = one 32 B
-//                          sector), so eight lanes reading ranks r..r+7 of one row fetch 64 contiguous bytes
+//   blk[C*stride]   one 128-byte-aligned BLOCK per table slot, header first:
+//                          {u64 packed (i,j,k) key, u64 meta = birth << 13 | count}, then three rows x[capp] y[capp] z[capp]
+//                          (structure-of-arrays INSIDE a voxel, capp = cap rounded up to 4), padded to a multiple of 128 B
+//                          (cap 10 -> 384 B, cap 20 -> 512 B). C = power of two, load <= 0.5. birth = creation sequence of the
+//                          voxel (= the reference container's address order, used only by the 27-cell fallback tie-break,
+//                          voxel_hash_map.cpp:81-101). Key, count and points of a voxel are ONE contiguous object: a hit costs
+//                          one DRAM page / one L2 round trip, and the candidates can be requested together with the header.
 //   pend[C*cap]      4 B  per point slot: insert scratch (sorted pending input indices), all-ones at rest
 //   live[C]          4 B  dense list of the slots that ever became a voxel since the last rebuild (append order; an
 //                          erased voxel leaves its entry behind and its slot reads KEY_TOMB): the eviction sweep
 //                          walks this list (V entries) instead of the C table slots. Length = counters[3].
 //
-// One 16-byte load answers "is this my voxel, how many points does it hold, and how old is it"; the points
-// of a voxel are contiguous (capp*24 B), so a query touches 1 + 3*ceil(8*count/32) sectors.
+// One 16-byte load answers "is this my voxel, how many points does it hold, and how old is it"; the points follow in the same block.
 #pragma once
 #include "common.cuh"
 
@@ -38,21 +38,21 @@ __host__ __device__ __forceinline__ int meta_count(unsigned long long meta) { re
 __host__ __device__ __forceinline__ unsigned long long meta_birth(unsigned long long meta) { return meta >> META_COUNT_BITS; }
 
 struct MapView {
-    Slot *slots;
-    double *pts;
+    double *blk;         // C blocks of `stride` doubles: 2 header words (Slot) + 3 rows of capp doubles + padding
     unsigned int *pend;
     unsigned int *live;  // dense list of used slots (live + erased), counters[3] entries
     unsigned int mask;   // C - 1
     int shift;           // 64 - log2(C)
     int cap;
     int capp;            // cap rounded up to a multiple of 4: row length of the per-voxel SoA block
-    int stride;          // doubles per voxel block: 3*capp rounded up to 16 (= one 128 B L2 line), so a block never straddles an extra line
+    int stride;          // doubles per block: 2 + 3*capp rounded up to 16 (= 128 B)
     double vox;
 };
 __host__ __device__ __forceinline__ int cap_padded(int cap) { return (cap + 3) & ~3; }
-__host__ __device__ __forceinline__ int block_stride(int cap) { return (3 * cap_padded(cap) + 15) & ~15; }
-// row pointers of voxel `slot`: x = base, y = base + capp, z = base + 2*capp
-__device__ __forceinline__ double *voxel_rows(const MapView &m, unsigned int slot) { return m.pts + (size_t)slot * (size_t)m.stride; }
+__host__ __device__ __forceinline__ int block_stride(int cap) { return (2 + 3 * cap_padded(cap) + 15) & ~15; }
+// header of table slot `slot`, and the row pointers of its voxel: x = base, y = base + capp, z = base + 2*capp
+__host__ __device__ __forceinline__ Slot *slot_at(const MapView &m, unsigned int slot) { return reinterpret_cast<Slot *>(m.blk + (size_t)slot * (size_t)m.stride); }
+__device__ __forceinline__ double *voxel_rows(const MapView &m, unsigned int slot) { return m.blk + (size_t)slot * (size_t)m.stride + 2; }
 
 // utils::get_vox_index, calculation_helpers.cpp:142-147: IEEE double division, truncation toward zero.
 __device__ __forceinline__ int vox_index(double p, double v) { return __double2int_rz(p / v); }
@@ -85,7 +85,7 @@ __device__ __forceinline__ double ldm(const double *p) { return *p; }
 __device__ __forceinline__ int map_find(const MapView &m, unsigned long long key, int *count) {
     unsigned int s = slot_of(key, m.shift);
     for (;;) {
-        const ulonglong2 v = load_slot(m.slots + s);
+        const ulonglong2 v = load_slot(slot_at(m, s));
         if (v.x == key) { *count = meta_count(v.y); return (int)s; }
         if (v.x == KEY_EMPTY) return -1;
         s = (s + 1) & m.mask;
@@ -148,14 +148,14 @@ __device__ __forceinline__ int map_locate(const MapView &m, const V3 &p, int *co
         ulonglong2 got[4];                                                                                  \
         _Pragma("unroll") for (int c = 0; c < 4; ++c) {                                                     \
             const int x = kx + TABLE[FIRST + c][0], y = ky + TABLE[FIRST + c][1], z = kz + TABLE[FIRST + c][2]; \
-            got[c] = key_in_range(x, y, z) ? load_slot(m.slots + slot_of(pack_key(x, y, z), m.shift)) : make_ulonglong2(KEY_EMPTY, 0ull); \
+            got[c] = key_in_range(x, y, z) ? load_slot(slot_at(m, slot_of(pack_key(x, y, z), m.shift))) : make_ulonglong2(KEY_EMPTY, 0ull); \
         }                                                                                                   \
         _Pragma("unroll") for (int c = 0; c < 4; ++c) {                                                     \
             ulonglong2 v = got[c];                                                                          \
             if (v.x != KEY_EMPTY) {                                                                         \
                 const unsigned long long want = pack_key(kx + TABLE[FIRST + c][0], ky + TABLE[FIRST + c][1], kz + TABLE[FIRST + c][2]); \
                 unsigned int s = slot_of(want, m.shift);                                                    \
-                while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(m.slots + s); } \
+                while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(slot_at(m, s)); } \
                 if (v.x == want && (best_slot < 0 || v.y > best_meta)) { best_meta = v.y; best_slot = (int)s; } \
             }                                                                                               \
         }                                                                                                   \
@@ -199,22 +199,60 @@ __device__ constexpr signed char NB_ALL[26][3] = {
     {-1, -1, 0}, {-1, 1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 0, -1}, {-1, 0, 1}, {1, 0, -1}, {1, 0, 1}, {0, -1, -1}, {0, -1, 1}, {0, 1, -1}, {0, 1, 1},
     {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
 
-// Group-cooperative lookup for the latency-bound shape (a few thousand queries): EIGHT lanes serve one query.
-// All lanes probe the query's own voxel (same address -> one broadcast load); on a miss lane l probes neighbours
-// l, l+8, l+16, l+24 of the 26 at once (one L2 round trip instead of up to seven dependent ones) and a 3-step butterfly
-// picks the lexicographic maximum of (|delta|^2, birth) = the reference's max-heap top (voxel_hash_map.cpp:81-101);
-// then the lanes read candidate ranks l, l+8, ... of the chosen voxel and a second butterfly picks the lexicographic
-// minimum of (d^2, rank) = "first minimum wins" (voxel_block.cpp:87-105). Every lane of the group returns the result.
-__device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, unsigned gmask, int l8, int &slot_out, int &count_out, int &own_out,
-                                               double &d2_out, int &rank_out) {
-    const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
-    int slot = -1, count = 0;
-    own_out = 0;
-    if (key_in_range(kx, ky, kz)) {
-        slot = map_find(m, pack_key(kx, ky, kz), &count);
-        if (slot >= 0) own_out = 1;
+// Group-cooperative lookup: EIGHT lanes serve one query (both shapes of the fused registration kernel: a few thousand keypoints per
+// iteration, latency bound -- and millions of queries against a map far larger than L2, bandwidth bound).
+// The common case -- the query's own voxel exists and sits in its home slot -- is ONE round trip: the block header (key, count, birth:
+// the same address for all eight lanes, one broadcast load) and this lane's candidate ranks l8, l8+8, ... of the same block are requested
+// together, before the key comparison can say whether they will be used; header and points are one contiguous object. A displaced voxel
+// costs dependent probes; an absent one the 26-cell fallback: lane l probes neighbours l, l+8, l+16, l+24 at once and a 3-step butterfly
+// picks the lexicographic maximum of (|delta|^2, birth) = the reference's max-heap top (voxel_hash_map.cpp:81-101). A second butterfly
+// picks the lexicographic minimum of (d^2, rank) = "first minimum wins" (voxel_block.cpp:87-105) and the winning lane hands its point
+// to the group by shuffle. Every lane of the group returns the result. ROUNDS*8 >= cap keeps the whole scan in registers.
+template <int ROUNDS>
+__device__ __forceinline__ void group8_load(const MapView &m, unsigned int slot, int l8, double *cx, double *cy, double *cz) {
+    const double *bx = voxel_rows(m, slot), *by = bx + m.capp, *bz = by + m.capp;
+#pragma unroll
+    for (int k = 0; k < ROUNDS; ++k) {   // ranks beyond the row re-read rank l8 & 3 (always inside the block) and are ignored by the scan
+        const int r = l8 + 8 * k, rr = r < m.capp ? r : (l8 & 3);
+        cx[k] = ldm(bx + rr); cy[k] = ldm(by + rr); cz[k] = ldm(bz + rr);
     }
-    if (slot < 0) {
+}
+template <int ROUNDS>
+__device__ __forceinline__ void group8_scan(const V3 &p, int l8, int count, const double *cx, const double *cy, const double *cz, double &bd2, int &br, double &tx,
+                                            double &ty, double &tz) {
+#pragma unroll
+    for (int k = 0; k < ROUNDS; ++k) {
+        const int r = l8 + 8 * k;
+        const double d = sqnorm3(p.x - cx[k], p.y - cy[k], p.z - cz[k]);
+        if (r < count && d < bd2) { bd2 = d; br = r; tx = cx[k]; ty = cy[k]; tz = cz[k]; }
+    }
+}
+template <int ROUNDS>
+__device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, unsigned gmask, int l8, int &slot_out, int &count_out, int &own_out,
+                                               double &d2_out, int &rank_out, V3 &t_out) {
+    const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
+    const bool inr = key_in_range(kx, ky, kz);
+    const unsigned long long key = pack_key(kx, ky, kz);
+    const unsigned int h = inr ? slot_of(key, m.shift) : 0u;
+    double bd2 = 1.7976931348623157e308, tx = 0.0, ty = 0.0, tz = 0.0;
+    int br = 0x7FFFFFFF, slot = -1, count = 0;
+    own_out = 0;
+    {   // the one round trip of the common case; the prefetched candidates are consumed here, before the fallback needs registers
+        const ulonglong2 sv = load_slot(slot_at(m, h));
+        double cx[ROUNDS], cy[ROUNDS], cz[ROUNDS];
+        group8_load<ROUNDS>(m, h, l8, cx, cy, cz);
+        if (inr) {
+            unsigned int s = h;
+            ulonglong2 v = sv;
+            while (v.x != key && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(slot_at(m, s)); }
+            if (v.x == key) { slot = (int)s; count = meta_count(v.y); own_out = 1; }
+        }
+        if (slot >= 0) {
+            if ((unsigned int)slot != h) group8_load<ROUNDS>(m, (unsigned int)slot, l8, cx, cy, cz);   // displaced by a collision: second trip
+            group8_scan<ROUNDS>(p, l8, count, cx, cy, cz, bd2, br, tx, ty, tz);
+        }
+    }
+    if (slot < 0) {   // group-uniform: all eight lanes saw the same header
         int bd = -1, bslot = -1;
         unsigned long long bmeta = 0ull;
         ulonglong2 got[4];
@@ -224,7 +262,7 @@ __device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, un
             got[u] = make_ulonglong2(KEY_EMPTY, 0ull);
             if (c < 26) {
                 const int x = kx + NB_ALL[c][0], y = ky + NB_ALL[c][1], z = kz + NB_ALL[c][2];
-                if (key_in_range(x, y, z)) got[u] = load_slot(m.slots + slot_of(pack_key(x, y, z), m.shift));
+                if (key_in_range(x, y, z)) got[u] = load_slot(slot_at(m, slot_of(pack_key(x, y, z), m.shift)));
             }
         }
 #pragma unroll
@@ -234,7 +272,7 @@ __device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, un
             if (c < 26 && v.x != KEY_EMPTY) {
                 const unsigned long long want = pack_key(kx + NB_ALL[c][0], ky + NB_ALL[c][1], kz + NB_ALL[c][2]);
                 unsigned int s = slot_of(want, m.shift);
-                while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(m.slots + s); }
+                while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(slot_at(m, s)); }
                 if (v.x == want) {
                     const int d = c < 8 ? 3 : (c < 20 ? 2 : 1);
                     if (d > bd || (d == bd && v.y > bmeta)) { bd = d; bmeta = v.y; bslot = (int)s; }
@@ -247,28 +285,19 @@ __device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, un
             const unsigned long long om = __shfl_xor_sync(gmask, bmeta, o);
             if (od > bd || (od == bd && om > bmeta)) { bd = od; bmeta = om; bslot = os; }
         }
-        slot = bslot;
-        count = bslot >= 0 ? meta_count(bmeta) : 0;
+        if (bslot >= 0) {   // neighbour voxel: its candidates are a second trip
+            slot = bslot; count = meta_count(bmeta);
+            double cx[ROUNDS], cy[ROUNDS], cz[ROUNDS];
+            group8_load<ROUNDS>(m, (unsigned int)slot, l8, cx, cy, cz);
+            group8_scan<ROUNDS>(p, l8, count, cx, cy, cz, bd2, br, tx, ty, tz);
+        }
     }
-    double bd2 = 1.7976931348623157e308;
-    int br = 0x7FFFFFFF;
-    if (slot >= 0) {
+    if (slot >= 0 && count > 8 * ROUNDS) {   // max_points_per_voxel beyond the register-resident part (cap > 24)
         const double *bx = voxel_rows(m, (unsigned int)slot), *by = bx + m.capp, *bz = by + m.capp;
-        double x[2], y[2], z[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {   // ranks l8 and l8+8 in one go (covers cap <= 16); out-of-range ranks re-read rank l8
-            const int r = l8 + 8 * k, rr = r < count ? r : l8;
-            x[k] = ldm(bx + rr); y[k] = ldm(by + rr); z[k] = ldm(bz + rr);
-        }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int r = l8 + 8 * k;
-            const double d = sqnorm3(p.x - x[k], p.y - y[k], p.z - z[k]);
-            if (r < count && d < bd2) { bd2 = d; br = r; }
-        }
-        for (int r = l8 + 16; r < count; r += 8) {
-            const double d = sqnorm3(p.x - ldm(bx + r), p.y - ldm(by + r), p.z - ldm(bz + r));
-            if (d < bd2) { bd2 = d; br = r; }
+        for (int r = l8 + 8 * ROUNDS; r < count; r += 8) {
+            const double x = ldm(bx + r), y = ldm(by + r), z = ldm(bz + r);
+            const double d = sqnorm3(p.x - x, p.y - y, p.z - z);
+            if (d < bd2) { bd2 = d; br = r; tx = x; ty = y; tz = z; }
         }
     }
 #pragma unroll
@@ -277,7 +306,12 @@ __device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, un
         const int orr = __shfl_xor_sync(gmask, br, o);
         if (od < bd2 || (od == bd2 && orr < br)) { bd2 = od; br = orr; }
     }
+    {   // the winner's point: lane (rank & 7) of the group holds it
+        const int src = (br == 0x7FFFFFFF ? 0 : (br & 7));
+        tx = __shfl_sync(gmask, tx, src, 8); ty = __shfl_sync(gmask, ty, src, 8); tz = __shfl_sync(gmask, tz, src, 8);
+    }
     slot_out = slot; count_out = count; d2_out = bd2; rank_out = br == 0x7FFFFFFF ? -1 : br;
+    t_out = br == 0x7FFFFFFF ? V3{0.0, 0.0, 0.0} : V3{tx, ty, tz};   // nothing found -> (0,0,0)
 }
 
 // Pair-cooperative lookup for the cluster latency shape (registration.cu, k_frame_cluster): TWO lanes serve one query, so that one
@@ -318,13 +352,13 @@ __device__ __forceinline__ void pair_closest(const MapView &m, const V3 &p, int 
     own_out = 0;
     {   // the one round trip of the common case; the prefetched candidates are consumed right here, so that their registers are free
         // again before the fallback below puts its probes in flight
-        const ulonglong2 sv = load_slot(m.slots + h);
+        const ulonglong2 sv = load_slot(slot_at(m, h));
         double cx[ROUNDS], cy[ROUNDS], cz[ROUNDS];
         pair_load_candidates<ROUNDS>(m, h, l2, cx, cy, cz);
         if (inr) {
             unsigned int s = h;
             ulonglong2 v = sv;
-            while (v.x != key && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(m.slots + s); }
+            while (v.x != key && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(slot_at(m, s)); }
             if (v.x == key) { slot = (int)s; count = meta_count(v.y); own_out = 1; }
         }
         if (slot >= 0) {
@@ -341,7 +375,7 @@ __device__ __forceinline__ void pair_closest(const MapView &m, const V3 &p, int 
         for (int u = 0; u < 13; ++u) {
             const int c = l2 + 2 * u;
             const int x = kx + NB_ALL[c][0], y = ky + NB_ALL[c][1], z = kz + NB_ALL[c][2];
-            got[u] = key_in_range(x, y, z) ? load_slot(m.slots + slot_of(pack_key(x, y, z), m.shift)) : make_ulonglong2(KEY_EMPTY, 0ull);
+            got[u] = key_in_range(x, y, z) ? load_slot(slot_at(m, slot_of(pack_key(x, y, z), m.shift))) : make_ulonglong2(KEY_EMPTY, 0ull);
         }
 #pragma unroll
         for (int u = 0; u < 13; ++u) {
@@ -350,7 +384,7 @@ __device__ __forceinline__ void pair_closest(const MapView &m, const V3 &p, int 
             if (v.x != KEY_EMPTY) {
                 const unsigned long long want = pack_key(kx + NB_ALL[c][0], ky + NB_ALL[c][1], kz + NB_ALL[c][2]);
                 unsigned int s = slot_of(want, m.shift);
-                while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(m.slots + s); }
+                while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(slot_at(m, s)); }
                 if (v.x == want) {
                     const int d = c < 8 ? 3 : (c < 20 ? 2 : 1);
                     if (d > bd || (d == bd && v.y > bmeta)) { bd = d; bmeta = v.y; bslot = (int)s; }
@@ -395,7 +429,7 @@ __device__ __forceinline__ Nearest map_closest27(const MapView &m, const V3 &p) 
 #pragma unroll
         for (int c = 0; c < 9; ++c) {   // nine home-slot loads in flight
             const int x = kx + dx, y = ky + (c / 3 - 1), z = kz + (c % 3 - 1);
-            got[c] = key_in_range(x, y, z) ? load_slot(m.slots + slot_of(pack_key(x, y, z), m.shift)) : make_ulonglong2(KEY_EMPTY, 0ull);
+            got[c] = key_in_range(x, y, z) ? load_slot(slot_at(m, slot_of(pack_key(x, y, z), m.shift))) : make_ulonglong2(KEY_EMPTY, 0ull);
         }
 #pragma unroll
         for (int c = 0; c < 9; ++c) {
@@ -403,7 +437,7 @@ __device__ __forceinline__ Nearest map_closest27(const MapView &m, const V3 &p) 
             if (v.x == KEY_EMPTY) continue;
             const unsigned long long want = pack_key(kx + dx, ky + (c / 3 - 1), kz + (c % 3 - 1));
             unsigned int s = slot_of(want, m.shift);
-            while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(m.slots + s); }
+            while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(slot_at(m, s)); }
             if (v.x != want) continue;
             if (dx == 0 && c == 4) r.own = 1;
             const int count = meta_count(v.y);
@@ -431,7 +465,7 @@ __device__ __forceinline__ void group8_closest27(const MapView &m, const V3 &p, 
         got[u] = make_ulonglong2(KEY_EMPTY, 0ull);
         if (c < 27) {
             const int x = kx + (c / 9 - 1), y = ky + ((c / 3) % 3 - 1), z = kz + (c % 3 - 1);
-            if (key_in_range(x, y, z)) got[u] = load_slot(m.slots + slot_of(pack_key(x, y, z), m.shift));
+            if (key_in_range(x, y, z)) got[u] = load_slot(slot_at(m, slot_of(pack_key(x, y, z), m.shift)));
         }
     }
     double bd2 = 1.7976931348623157e308;
@@ -443,7 +477,7 @@ __device__ __forceinline__ void group8_closest27(const MapView &m, const V3 &p, 
         if (c < 27 && v.x != KEY_EMPTY) {
             const unsigned long long want = pack_key(kx + (c / 9 - 1), ky + ((c / 3) % 3 - 1), kz + (c % 3 - 1));
             unsigned int s = slot_of(want, m.shift);
-            while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(m.slots + s); }
+            while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(slot_at(m, s)); }
             if (v.x == want) {
                 if (c == 13) own = 1;
                 const int count = meta_count(v.y);
@@ -537,9 +571,9 @@ __device__ __forceinline__ unsigned int insert_claim_one(const MapView &m, const
     const unsigned long long key = pack_key(kx, ky, kz);
     unsigned int s = slot_of(key, m.shift);
     for (unsigned int probes = 0; probes <= m.mask; ++probes) {
-        unsigned long long cur = __ldcg(&m.slots[s].key);
+        unsigned long long cur = __ldcg(&slot_at(m, (unsigned int)s)->key);
         if (cur == KEY_EMPTY) {
-            cur = atomicCAS(&m.slots[s].key, KEY_EMPTY, key);
+            cur = atomicCAS(&slot_at(m, (unsigned int)s)->key, KEY_EMPTY, key);
             if (cur == KEY_EMPTY) { *claimed = true; cur = key; }
         }
         if (cur == key) { slot = s; break; }
@@ -547,7 +581,7 @@ __device__ __forceinline__ unsigned int insert_claim_one(const MapView &m, const
     }
     if (slot == PEND_NONE) { st->table_full = 1; return slot; }
     const unsigned long long mine = (birth_base + (unsigned long long)i) << META_COUNT_BITS;
-    const unsigned long long old = atomicMin(&m.slots[slot].meta, mine);
+    const unsigned long long old = atomicMin(&slot_at(m, (unsigned int)slot)->meta, mine);
     const int count = meta_count(old < mine ? old : mine);   // only pass 2 changes counts
     unsigned int x = i;
     unsigned int *list = m.pend + (size_t)slot * m.cap;
@@ -582,7 +616,7 @@ __device__ __forceinline__ void insert_place_one(const MapView &m, const V3 &p, 
             double *d = voxel_rows(m, slot);
             d[r] = p.x; d[m.capp + r] = p.y; d[2 * m.capp + r] = p.z;
             list[r] = PEND_NONE;
-            atomicAdd(&m.slots[slot].meta, 1ull);
+            atomicAdd(&slot_at(m, (unsigned int)slot)->meta, 1ull);
             break;
         }
     }
@@ -591,7 +625,7 @@ __device__ __forceinline__ void insert_place_one(const MapView &m, const V3 &p, 
 // distance^2 to the origin voxel exceeds max_distance^2 (units as written, :148,:160) drop their points farther than
 // max_distance metres from origin, order preserved (voxel_block.cpp:107-118); empty voxels are erased (tombstoned).
 __device__ __forceinline__ void remove_far_one(const MapView &m, int64_t s, double ox, double oy, double oz, double max_distance, unsigned long long *counters) {
-    const unsigned long long key = m.slots[s].key;
+    const unsigned long long key = slot_at(m, (unsigned int)s)->key;
     if (key >= KEY_TOMB) return;
     const double max_sq = max_distance * max_distance;
     int x, y, z;
@@ -600,7 +634,7 @@ __device__ __forceinline__ void remove_far_one(const MapView &m, int64_t s, doub
     const long long d2 = dx * dx + dy * dy + dz * dz;
     if (!((double)d2 > max_sq)) return;
     double *px = voxel_rows(m, (unsigned int)s), *py = px + m.capp, *pz = py + m.capp;
-    const unsigned long long meta = m.slots[s].meta;
+    const unsigned long long meta = slot_at(m, (unsigned int)s)->meta;
     const int count = meta_count(meta);
     int w = 0;
     for (int r = 0; r < count; ++r) {
@@ -610,10 +644,10 @@ __device__ __forceinline__ void remove_far_one(const MapView &m, int64_t s, doub
             ++w;
         }
     }
-    if (w != count) m.slots[s].meta = (meta & ~META_COUNT_MASK) | (unsigned long long)w;
+    if (w != count) slot_at(m, (unsigned int)s)->meta = (meta & ~META_COUNT_MASK) | (unsigned long long)w;
     if (w == 0) {
-        m.slots[s].key = KEY_TOMB;
-        m.slots[s].meta = META_NONE;
+        slot_at(m, (unsigned int)s)->key = KEY_TOMB;
+        slot_at(m, (unsigned int)s)->meta = META_NONE;
         atomicAdd(&counters[0], ~0ull);  // --live
         atomicAdd(&counters[1], 1ull);   // ++tombstones
     }
@@ -627,7 +661,7 @@ struct limu_map {
     double vox_size = 1.0, max_distance = 100.0;
     int cap = 10;
     int64_t capacity = 0;          // C (slots), power of two
-    limu::DevBuf slots, pts, pend, live;
+    limu::DevBuf blk, pend, live;
     limu::DevBuf counters;         // device: [0] n_live voxels, [1] n_tomb, [2] n_points, [3] n_used (live + tomb)
     uint64_t birth_base = 0;       // creation sequence offset of the next insert batch
     int64_t used_upper = 0;        // host upper bound on live + tomb slots
