@@ -24,6 +24,9 @@
 namespace limu {
 
 constexpr int ICP_BLOCK = 256;
+#ifndef LIMU_BW_CTAS
+#define LIMU_BW_CTAS 3   // CTAs per SM of the bandwidth shape (register cap 65536 / (256 * LIMU_BW_CTAS))
+#endif
 constexpr int NS = 20;   // 16 sums + ncorr + ncand + nmiss + pad
 constexpr int NSP = 32;  // opt-in point-to-plane variant: 21 (upper triangle of H) + 6 (g) + ncorr + ncand + nmiss + 2 pad
 constexpr int NS_MAX = 32;
@@ -389,14 +392,71 @@ __device__ __forceinline__ void icp_query_pass_grouped(const IcpArgs &A, const v
     }
 }
 
+// The bandwidth shape's pass (kernel mode: millions of queries against a map far larger than L2). Everything that is per-query scalar work
+// -- transform, the three FP64 index divisions, key packing and hashing, and later residual, weight and the 16 products -- runs with ONE
+// lane per query, i.e. one warp instruction serves 32 queries (eight lanes per query for ALL of it made the pass FP64-issue bound:
+// 805 us instead of 630 us per iteration at 4 M queries). Only the memory part is cooperative: in step t the eight lanes of a group
+// take over the query of the group's lane t, fetch the voxel block -- header and candidates in ONE round trip -- scan it and hand the
+// winner back to lane t (group8_closest_at).
+template <int ROUNDS>
+__device__ __forceinline__ void icp_query_pass_coop(const IcpArgs &A, const volatile double *Pv, const double *in, int64_t n, int64_t wbase, int64_t wstride,
+                                                    int lane, double &acc, int &ncorr, int &ncand, int &nmiss) {
+    const int l8 = lane & 7;
+    const unsigned gmask = 0xFFu << (lane & 24);
+    for (int64_t base = wbase; base < n; base += wstride) {
+        const int64_t q = base + lane;
+        const bool on = q < n;
+        V3 s{0.0, 0.0, 0.0};
+        int kx = 0, ky = 0, kz = 0, inr = 0;
+        unsigned long long key = 0ull;
+        unsigned int h = 0u;
+        if (on) {
+            const Pose P{Pv[0], Pv[1], Pv[2], Pv[3], Pv[4], Pv[5], Pv[6]};
+            s = apply(P, V3{in[3 * q], in[3 * q + 1], in[3 * q + 2]});
+            A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z;
+            kx = vox_index(s.x, A.map.vox); ky = vox_index(s.y, A.map.vox); kz = vox_index(s.z, A.map.vox);
+            inr = key_in_range(kx, ky, kz) ? 1 : 0;
+            key = pack_key(kx, ky, kz);
+            h = inr ? slot_of(key, A.map.shift) : 0u;
+        }
+        double my_d2 = 0.0;
+        int my_rank = -1, my_count = 0, my_own = 1;
+        V3 tg{0.0, 0.0, 0.0};
+#pragma unroll 1
+        for (int t = 0; t < 8; ++t) {
+            const V3 qp{__shfl_sync(0xFFFFFFFFu, s.x, t, 8), __shfl_sync(0xFFFFFFFFu, s.y, t, 8), __shfl_sync(0xFFFFFFFFu, s.z, t, 8)};
+            const int qx = __shfl_sync(0xFFFFFFFFu, kx, t, 8), qy = __shfl_sync(0xFFFFFFFFu, ky, t, 8), qz = __shfl_sync(0xFFFFFFFFu, kz, t, 8);
+            const int qin = __shfl_sync(0xFFFFFFFFu, inr, t, 8);
+            const unsigned long long qkey = __shfl_sync(0xFFFFFFFFu, key, t, 8);
+            const unsigned int qh = __shfl_sync(0xFFFFFFFFu, h, t, 8);
+            int slot, count, own, rank;
+            double d2;
+            V3 tt;
+            group8_closest_at<ROUNDS>(A.map, qp, qx, qy, qz, qin != 0, qkey, qh, gmask, l8, slot, count, own, d2, rank, tt);
+            if (l8 == t) { my_d2 = d2; my_rank = rank; my_count = count; my_own = own; tg = tt; }
+        }
+        const double d2 = my_rank >= 0 ? my_d2 : sqnorm3(tg.x - s.x, tg.y - s.y, tg.z - s.z);   // nothing found -> (0,0,0), range-tested like a real point
+        const bool gate = on && d2 < A.tau_sq;
+        double c[16];
+        contribution(c, s, tg, d2, A.th, gate);
+        acc += warp_reduce_scatter16(c);
+        ncorr += gate ? 1 : 0;
+        ncand += on ? my_count : 0;
+        nmiss += (on && !my_own) ? 1 : 0;
+    }
+}
+
 #ifdef LIMU_ICP_PHASE_TIMING
 // developer build only (tools/icp_phase_timing.py, tools/frame_phase_timing.py): %globaltimer stamps of CTA 0 / thread 0
 __device__ unsigned long long g_frame_marks[16];
-#define FT_MARK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_frame_marks[k] = _t; } } while (0)
-#define PT_MARK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && A.hg_trace) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); A.hg_trace[42 * (size_t)j + (k)] = (double)_t; } } while (0)
+#define FT_MARK(k) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && ((k) >= 8 || threadIdx.x == 0)) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_frame_marks[k] = _t; } } while (0)
+// SM cycle counter of CTA 0 (one SM: the marks of different warps are comparable): any lane 0 / lane 0 of warp w
+#define CT_MARK(k) do { if (blockIdx.x == 0 && lane == 0) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
+#define CW_MARK(k, w) do { if (blockIdx.x == 0 && warp == (w) && lane == 0) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
 #else
-#define PT_MARK(k) do {} while (0)
 #define FT_MARK(k) do {} while (0)
+#define CW_MARK(k, w) do {} while (0)
+#define CT_MARK(k) do {} while (0)
 #endif
 
 // local_map.update(down_sampled, new_pose) (icp.cpp:81; voxel_hash_map.cpp:138-144) inside a frame kernel: transform + capped ordered insert
@@ -460,12 +520,12 @@ static __device__ __noinline__ void solve_normal_equations(const double *S, doub
 // registers -> 3 CTAs = 96 eight-lane groups per SM, each with one 384/512-byte block in flight (~48 KB per SM, above what the measured
 // HBM latency x bandwidth asks for), the query pass free of spills, the solve out of line.
 template <int SHAPE, bool NN27, bool PLANE>
-static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 3) k_icp_persistent(const IcpArgs A) {
+static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTAS) k_icp_persistent(const IcpArgs A) {
     constexpr int NSX = PLANE ? NSP : NS;              // doubles per partial row
     constexpr int I_NCORR = PLANE ? 27 : 16;           // where the three counters sit in a row
     __shared__ double red[(ICP_BLOCK / 32) * 32];
     __shared__ double S[NSX];
-    __shared__ double E[7], Tinit[7], Ticp[7];
+    __shared__ double E[7], Tinit[7], Ticp[7], xs[8];
     __shared__ int done;
     __shared__ int comm_dead;
     __shared__ IqrSmem iqr_sm;
@@ -497,52 +557,81 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 3) k_icp_pe
     if (threadIdx.x < NSX) S[threadIdx.x] = 0.0;
     if (threadIdx.x == 0) comm_dead = 0;
     __syncthreads();
-    const int64_t wbase = ((int64_t)blockIdx.x * (ICP_BLOCK / 32) + warp) * 32, wstride = (int64_t)A.icp_blocks * ICP_BLOCK;
+    // Warps 0..QW-1 own the queries; the last warp is the SOLVER warp: it has no queries, solves the normal equations once the rows
+    // are folded, publishes the estimate -- and then finishes T_icp, log(estimate) and the convergence test WHILE the query warps are
+    // already in the next pass (the ~2 us of SE3 product + log leave the critical path of the iteration; a pass made after the
+    // converging iteration is simply dropped).
+    constexpr int QW = ICP_BLOCK / 32 - 1;
+    const int64_t wbase = ((int64_t)blockIdx.x * QW + warp) * 32, wstride = (int64_t)A.icp_blocks * QW * 32;
     int j = 0;
     int converged = 0;
-    while (run_icp && icp_member) {
-        PT_MARK(0);
-        double acc = 0.0;            // lane L: running total of sum index L>>1
-        int ncorr = 0, ncand = 0, nmiss = 0;
-        const volatile double *Pv = j == 0 ? Tinit : E;   // re-read per batch: keeps 14 registers free across the lookup
-        const double *in = j == 0 ? A.points : A.work;
-        if (SHAPE == 0 || (!NN27 && !PLANE)) {   // eight lanes per query (both shapes; the opt-in variants of the bandwidth shape keep one lane per query)
-            if (A.map.cap <= 8) icp_query_pass_grouped<NN27, PLANE, 1>(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
-            else if (A.map.cap <= 16) icp_query_pass_grouped<NN27, PLANE, 2>(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
-            else icp_query_pass_grouped<NN27, PLANE, 3>(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
-        } else {
-            icp_query_pass<NN27, PLANE>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
-        }
-        PT_MARK(1);
-        double *rows = A.partials + (size_t)(j & 1) * A.icp_blocks * NSX;
-        if (PLANE) {
-            // CTA row: lane L of every warp holds sum L (27 sums + 3 counters + 2 zeros)
-            red[warp * 32 + lane] = acc;
-            __syncthreads();
-            if (threadIdx.x < NSX) {
-                double v = 0.0;
-#pragma unroll
-                for (int w = 0; w < ICP_BLOCK / 32; ++w) v += red[w * 32 + threadIdx.x];
-                rows[(size_t)blockIdx.x * NSX + threadIdx.x] = v;
+    if (run_icp && icp_member) for (;;) {
+        const bool no_more = j >= A.max_iter;   // nothing left to do but wait for the verdict on iteration j-1
+        if (warp < QW) {
+            if (!no_more) {
+                CW_MARK(6, 0);
+                double acc = 0.0;            // lane L: running total of sum index L>>1
+                int ncorr = 0, ncand = 0, nmiss = 0;
+                const volatile double *Pv = j == 0 ? Tinit : E;   // re-read per batch: keeps 14 registers free across the lookup
+                const double *in = j == 0 ? A.points : A.work;
+                if (SHAPE == 1 && !NN27 && !PLANE) {     // bandwidth shape: one lane per query, eight lanes per voxel block
+                    if (A.map.cap <= 8) icp_query_pass_coop<1>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
+                    else if (A.map.cap <= 16) icp_query_pass_coop<2>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
+                    else icp_query_pass_coop<3>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
+                } else if (SHAPE == 0) {                 // latency shape: eight lanes per query
+                    if (A.map.cap <= 8) icp_query_pass_grouped<NN27, PLANE, 1>(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
+                    else if (A.map.cap <= 16) icp_query_pass_grouped<NN27, PLANE, 2>(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
+                    else icp_query_pass_grouped<NN27, PLANE, 3>(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
+                } else {
+                    icp_query_pass<NN27, PLANE>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
+                }
+                CW_MARK(7, 0);
+                if (PLANE) {
+                    red[warp * 32 + lane] = acc;   // lane L of every warp holds sum L (27 sums + 3 counters + 2 zeros)
+                } else {                           // 16 sums (even lanes hold them) + 3 counters
+                    ncorr = __reduce_add_sync(0xFFFFFFFFu, ncorr);
+                    ncand = __reduce_add_sync(0xFFFFFFFFu, ncand);
+                    nmiss = __reduce_add_sync(0xFFFFFFFFu, nmiss);
+                    red[warp * 32 + lane] = (lane & 1) ? (lane == 1 ? (double)ncorr : lane == 3 ? (double)ncand : lane == 5 ? (double)nmiss : 0.0) : acc;
+                }
             }
-        } else {
-        // CTA row: 16 sums (even lanes hold them) + 3 counters
-        ncorr = __reduce_add_sync(0xFFFFFFFFu, ncorr);
-        ncand = __reduce_add_sync(0xFFFFFFFFu, ncand);
-        nmiss = __reduce_add_sync(0xFFFFFFFFu, nmiss);
-        red[warp * 32 + lane] = (lane & 1) ? (lane == 1 ? (double)ncorr : lane == 3 ? (double)ncand : lane == 5 ? (double)nmiss : 0.0) : acc;
-        __syncthreads();
-        if (threadIdx.x < NS) {
-            const int src_lane = threadIdx.x < 16 ? 2 * threadIdx.x : 2 * (threadIdx.x - 16) + 1;
+        } else if (j > 0) {
+            // tail of iteration j-1, overlapped with pass j: T_icp = estimate * T_icp (:122) on lane 0, |log(estimate)| < eps (:124) on lane 1
+            const Pose est = pose_load(E);
+            if (lane == 0) pose_store(mul(est, pose_load(Ticp)), Ticp);
+            if (lane == 1) {
+                double lg[6];
+                se3_log(est, lg);
+                done = norm6(lg) < A.eps;
+            }
+            if (blockIdx.x == 0 && lane == 2) {   // traces of iteration j-1 (S still holds its sums)
+                if (A.est_trace) pose_store(est, A.est_trace + 7 * (size_t)(j - 1));
+                if (A.ncorr_trace) A.ncorr_trace[j - 1] = (long long)S[I_NCORR];
+                if (A.hg_trace) {
+                    double H[36], g[6];
+                    if (PLANE) expand_plane_equations(S, H, g);
+                    else expand_normal_equations(S, H, g);
+                    double *o = A.hg_trace + 42 * (size_t)(j - 1);
+                    for (int k = 0; k < 36; ++k) o[k] = H[k];
+                    for (int k = 0; k < 6; ++k) o[36 + k] = g[k];
+                }
+            }
+            CW_MARK(14, QW);
+        }
+        __syncthreads();   // S1: CTA partial sums of pass j, and the verdict on iteration j-1
+        CW_MARK(11, 0);
+        if (j > 0 && done) { converged = 1; break; }   // (the pass just made belongs to an iteration that does not exist)
+        if (no_more) break;
+        double *rows = A.partials + (size_t)(j & 1) * A.icp_blocks * NSX;
+        if (threadIdx.x < NSX) {   // CTA row, fixed order over the query warps
+            const int src_lane = PLANE ? (int)threadIdx.x : (threadIdx.x < 16 ? 2 * (int)threadIdx.x : 2 * ((int)threadIdx.x - 16) + 1);
             double v = 0.0;
 #pragma unroll
-            for (int w = 0; w < ICP_BLOCK / 32; ++w) v += red[w * 32 + src_lane];
-            rows[(size_t)blockIdx.x * NS + threadIdx.x] = v;
+            for (int w = 0; w < QW; ++w) v += red[w * 32 + src_lane];
+            rows[(size_t)blockIdx.x * NSX + threadIdx.x] = v;
         }
-        }
-        PT_MARK(2);
         gs_icp.sync();
-        PT_MARK(3);
+        CW_MARK(12, 0);
         // fold the per-CTA rows in a fixed order: lane = column, warp g sums rows g, g+8, ... (four independent
         // accumulators keep the L2 loads in flight), then one thread per column adds the 8 warp partials.
         {
@@ -606,14 +695,12 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 3) k_icp_pe
             }
             __syncthreads();
         }
-        PT_MARK(4);
-        if (warp == 0) {
-            // normal equations -> twist -> estimate (lane 0, all in registers in the latency build), then T_icp on lane 0
-            // while lane 1 takes log(estimate) for the convergence test
-            FT_MARK(8);
+        if (warp == QW) {
+            // normal equations -> twist -> estimate: the critical path of the iteration
+            CW_MARK(8, QW);
             if (lane == 0) {
                 if (SHAPE == 1 && !PLANE) {
-                    solve_normal_equations(S, red);               // out of line: the bandwidth build has no registers to spare
+                    solve_normal_equations(S, xs);                // out of line: the bandwidth build has no registers to spare
                 } else {
                     double H[36], g[6], x[6];
                     if (PLANE) expand_plane_equations(S, H, g);
@@ -622,44 +709,20 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : 3) k_icp_pe
                     for (int k = 0; k < 6; ++k) g[k] = -g[k];
                     ldlt6_solve(H, g, x);                         // JTJ.ldlt().solve(-JTr) :90
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) red[k] = x[k];
+                    for (int k = 0; k < 6; ++k) xs[k] = x[k];
                 }
-                FT_MARK(9);
+                CW_MARK(9, QW);
             }
             __syncwarp();
             // estimate = SE3::exp(x) (vector6d_to_mat4d :91): rotation half on lane 0, translation half on lane 1
-            if (lane == 0) { double th_; se3_exp_rotation(red, E, &th_); }
-            if (lane == 1) se3_exp_translation(red, E + 4);
+            if (lane == 0) { double th_; se3_exp_rotation(xs, E, &th_); }
+            if (lane == 1) se3_exp_translation(xs, E + 4);
             __syncwarp();
-            FT_MARK(10);
-            const Pose est = pose_load(E);
-            if (lane == 0) pose_store(mul(est, pose_load(Ticp)), Ticp);   // T_icp = estimate * T_icp :122
-            if (lane == 1) {
-                double lg[6];
-                se3_log(est, lg);
-                done = norm6(lg) < A.eps;                          // :124
-            }
-            FT_MARK(12);
-            if (blockIdx.x == 0 && lane == 2) {
-                if (A.est_trace) pose_store(est, A.est_trace + 7 * (size_t)j);
-                if (A.ncorr_trace) A.ncorr_trace[j] = (long long)S[I_NCORR];
-#ifndef LIMU_ICP_PHASE_TIMING
-                if (A.hg_trace) {
-                    double H[36], g[6];
-                    if (PLANE) expand_plane_equations(S, H, g);
-                    else expand_normal_equations(S, H, g);
-                    double *o = A.hg_trace + 42 * (size_t)j;
-                    for (int k = 0; k < 36; ++k) o[k] = H[k];
-                    for (int k = 0; k < 6; ++k) o[36 + k] = g[k];
-                }
-#endif
-            }
+            CW_MARK(10, QW);
         }
-        __syncthreads();
-        PT_MARK(5);
+        __syncthreads();   // S2: the estimate is visible to the query warps
+        CW_MARK(15, 0);
         ++j;
-        if (done) { converged = 1; break; }
-        if (j >= A.max_iter) break;
     }
     FT_MARK(2);
     // new_pose = T_icp * init_guess (:129); with an empty map the loop did not run and this is init_guess itself (:99-100)
@@ -777,13 +840,6 @@ __device__ __forceinline__ int cluster_iqr_compact(ClusterSmem &sm, const IcpArg
     return sm.total;
 }
 
-#ifdef LIMU_ICP_PHASE_TIMING
-#define CT_MARK(k) do { if (blockIdx.x == 0 && lane == 0) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
-#define CW_MARK(k, w) do { if (blockIdx.x == 0 && warp == (w) && lane == 0) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
-#else
-#define CW_MARK(k, w) do {} while (0)
-#define CT_MARK(k) do {} while (0)
-#endif
 
 template <int ROUNDS>   // candidate ranks per lane of a query pair: max_points_per_voxel <= 2 * ROUNDS
 static __global__ void __launch_bounds__(CL_THREADS, 1) k_frame_cluster(const IcpArgs A) {
@@ -1047,8 +1103,10 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
         g_icp_blocks_per_sm = std::max(1, b);
     }
     const bool grouped = n_hint <= 16384 && m->cap <= 64;   // latency shape: eight lanes per query, one CTA per SM
-    const int64_t want = std::max<int64_t>(1, div_up(std::max<int64_t>(n_hint, 1) * (grouped ? 8 : 1), ICP_BLOCK));
-    int grid = (int)std::min<int64_t>(want, (int64_t)c->sm_count * (grouped ? 1 : std::min(g_icp_blocks_per_sm, 3)));
+    // queries per CTA: 7 query warps (the eighth warp is the solver warp); eight lanes per query in the latency shape, one in the bandwidth shape
+    const bool lanes8 = grouped;
+    const int64_t want = std::max<int64_t>(1, div_up(std::max<int64_t>(n_hint, 1) * (lanes8 ? 8 : 1), ICP_BLOCK - 32));
+    int grid = (int)std::min<int64_t>(want, (int64_t)c->sm_count * (grouped ? 1 : std::min(g_icp_blocks_per_sm, LIMU_BW_CTAS)));
     grid = (int)std::min<int64_t>(grid, (int64_t)partial_rows);
     const int icp_blocks = grid;   // the Gauss-Newton loop is latency bound at keypoint counts: it runs on the leading CTAs only
     if (fuse && fuse->upd_down) grid = std::max(grid, c->sm_count);   // the insert and the eviction sweep want one CTA per SM
@@ -1116,7 +1174,7 @@ extern "C" int limu_debug_frame_marks(double out[16]) {
 #endif
 
 // ---- un-fused baseline for the sharded loop: step kernel -> fold kernel -> ncclAllReduce -> solve kernel, host in the loop ----
-static __global__ void __launch_bounds__(ICP_BLOCK, 3) k_icp_step(const IcpArgs A, const double *state /* E at +24 */, int first, double *rows) {
+static __global__ void __launch_bounds__(ICP_BLOCK, LIMU_BW_CTAS) k_icp_step(const IcpArgs A, const double *state /* E at +24 */, int first, double *rows) {
     __shared__ double red[(ICP_BLOCK / 32) * 32];
     __shared__ double Pose7[7];
     const int64_t n = A.n_max;
@@ -1127,9 +1185,9 @@ static __global__ void __launch_bounds__(ICP_BLOCK, 3) k_icp_step(const IcpArgs 
     int ncorr = 0, ncand = 0, nmiss = 0;
     const int64_t wbase = ((int64_t)blockIdx.x * (ICP_BLOCK / 32) + warp) * 32, wstride = (int64_t)A.icp_blocks * ICP_BLOCK;
     const double *in = first ? A.points : A.work;
-    if (A.map.cap <= 8) icp_query_pass_grouped<false, false, 1>(A, Pose7, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
-    else if (A.map.cap <= 16) icp_query_pass_grouped<false, false, 2>(A, Pose7, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
-    else icp_query_pass_grouped<false, false, 3>(A, Pose7, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
+    if (A.map.cap <= 8) icp_query_pass_coop<1>(A, Pose7, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
+    else if (A.map.cap <= 16) icp_query_pass_coop<2>(A, Pose7, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
+    else icp_query_pass_coop<3>(A, Pose7, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
     ncorr = __reduce_add_sync(0xFFFFFFFFu, ncorr);
     ncand = __reduce_add_sync(0xFFFFFFFFu, ncand);
     nmiss = __reduce_add_sync(0xFFFFFFFFu, nmiss);

@@ -114,8 +114,15 @@ LIMU_HD void se3_exp_rotation(const double *a, double *q /* x y z w */, double *
     } else {
         theta = sqrt(theta_sq);
         const double half = 0.5 * theta;
+#ifdef __CUDA_ARCH__
+        double sh, ch;   // one argument reduction for both (this sits on the critical path of every Gauss-Newton iteration)
+        sincos(half, &sh, &ch);
+        imag = sh / theta;
+        real = ch;
+#else
         imag = sin(half) / theta;
         real = cos(half);
+#endif
     }
     q[3] = real; q[0] = imag * om[0]; q[1] = imag * om[1]; q[2] = imag * om[2];
     *theta_out = theta;
@@ -132,7 +139,13 @@ LIMU_HD void se3_exp_translation(const double *a, double *t) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) V[i] = ((i % 4 == 0) ? 1.0 : 0.0) + 0.5 * Om[i];
     } else {
-        const double c1 = (1.0 - cos(theta)) / tsq, c2 = (theta - sin(theta)) / (tsq * theta);
+#ifdef __CUDA_ARCH__
+        double st, ct;
+        sincos(theta, &st, &ct);
+#else
+        const double st = sin(theta), ct = cos(theta);
+#endif
+        const double c1 = (1.0 - ct) / tsq, c2 = (theta - st) / (tsq * theta);
 #pragma unroll
         for (int i = 0; i < 9; ++i) V[i] = (((i % 4 == 0) ? 1.0 : 0.0) + c1 * Om[i]) + c2 * Om2[i];
     }
@@ -244,7 +257,11 @@ LIMU_HD void ldlt6_solve(const double *Ain, const double *b, double *x) {
             const double akk = a[k][k];
             const bool valid = fabs(akk) > 0.0;
             if (k == 0 && !valid) zero = true;
+#ifdef __CUDA_ARCH__
+            inv[k] = fabs(akk) > 2.2250738585072014e-308 ? __drcp_rn(akk) : 0.0;   // correctly rounded reciprocal == 1.0 / akk, without the division subroutine
+#else
             inv[k] = fabs(akk) > 2.2250738585072014e-308 ? 1.0 / akk : 0.0;   // pseudo-inverse of D (LDLT.h:590-596)
+#endif
             if (valid) {
 #pragma unroll
                 for (int r = k + 1; r < 6; ++r) a[r][k] *= inv[k];

@@ -227,70 +227,78 @@ __device__ __forceinline__ void group8_scan(const V3 &p, int l8, int count, cons
         if (r < count && d < bd2) { bd2 = d; br = r; tx = cx[k]; ty = cy[k]; tz = cz[k]; }
     }
 }
+// The rare part of the lookup, kept out of line so that its registers (four 16-byte probes in flight per lane) do not weigh on the hot
+// path: the home slot `h` holds ANOTHER voxel (collision: probe on) or nothing. If the query's own voxel is not in the table, fall back
+// to the 26 neighbours: lane l probes cells l, l+8, l+16, l+24 at once and a 3-step butterfly picks the lexicographic maximum of
+// (|delta|^2, birth) = the reference's max-heap top (voxel_hash_map.cpp:81-101). Group-uniform; returns the slot (or -1).
+struct MapProbe { double *blk; unsigned int mask; int shift, stride; };   // what probing needs of a MapView, passed BY VALUE (a reference to the
+                                                                          // kernel's parameter block would force a local copy of all of it)
+static __device__ __noinline__ int group8_resolve_rare(MapProbe mp, int kx, int ky, int kz, bool inr, unsigned long long key, unsigned int h, ulonglong2 sv,
+                                                      unsigned gmask, int l8, int *count_out, int *own_out) {
+    MapView m;
+    m.blk = mp.blk; m.mask = mp.mask; m.shift = mp.shift; m.stride = mp.stride;
+    *own_out = 0;
+    *count_out = 0;
+    if (inr) {
+        unsigned int s = h;
+        ulonglong2 v = sv;
+        while (v.x != key && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(slot_at(m, s)); }
+        if (v.x == key) { *count_out = meta_count(v.y); *own_out = 1; return (int)s; }
+    }
+    int bd = -1, bslot = -1;
+    unsigned long long bmeta = 0ull;
+    ulonglong2 got[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int c = l8 + 8 * u;
+        got[u] = make_ulonglong2(KEY_EMPTY, 0ull);
+        if (c < 26) {
+            const int x = kx + NB_ALL[c][0], y = ky + NB_ALL[c][1], z = kz + NB_ALL[c][2];
+            if (key_in_range(x, y, z)) got[u] = load_slot(slot_at(m, slot_of(pack_key(x, y, z), m.shift)));
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int c = l8 + 8 * u;
+        ulonglong2 v = got[u];
+        if (c < 26 && v.x != KEY_EMPTY) {
+            const unsigned long long want = pack_key(kx + NB_ALL[c][0], ky + NB_ALL[c][1], kz + NB_ALL[c][2]);
+            unsigned int s = slot_of(want, m.shift);
+            while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(slot_at(m, s)); }
+            if (v.x == want) {
+                const int d = c < 8 ? 3 : (c < 20 ? 2 : 1);
+                if (d > bd || (d == bd && v.y > bmeta)) { bd = d; bmeta = v.y; bslot = (int)s; }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        const int od = __shfl_xor_sync(gmask, bd, o), os = __shfl_xor_sync(gmask, bslot, o);
+        const unsigned long long om = __shfl_xor_sync(gmask, bmeta, o);
+        if (od > bd || (od == bd && om > bmeta)) { bd = od; bmeta = om; bslot = os; }
+    }
+    if (bslot >= 0) *count_out = meta_count(bmeta);
+    return bslot;
+}
+
+// Core: the query's voxel index (kx, ky, kz), whether it is inside the packed key range (inr), its packed key and home slot h are given
+// (the bandwidth shape computes them with ONE lane per query and hands them to the group by shuffle).
 template <int ROUNDS>
-__device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, unsigned gmask, int l8, int &slot_out, int &count_out, int &own_out,
-                                               double &d2_out, int &rank_out, V3 &t_out) {
-    const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
-    const bool inr = key_in_range(kx, ky, kz);
-    const unsigned long long key = pack_key(kx, ky, kz);
-    const unsigned int h = inr ? slot_of(key, m.shift) : 0u;
+__device__ __forceinline__ void group8_closest_at(const MapView &m, const V3 &p, int kx, int ky, int kz, bool inr, unsigned long long key, unsigned int h,
+                                                  unsigned gmask, int l8, int &slot_out, int &count_out, int &own_out, double &d2_out, int &rank_out, V3 &t_out) {
     double bd2 = 1.7976931348623157e308, tx = 0.0, ty = 0.0, tz = 0.0;
-    int br = 0x7FFFFFFF, slot = -1, count = 0;
-    own_out = 0;
-    {   // the one round trip of the common case; the prefetched candidates are consumed here, before the fallback needs registers
+    int br = 0x7FFFFFFF, slot, count, own;
+    {   // the one round trip of the common case: header and this lane's candidate ranks of the home block, requested together
         const ulonglong2 sv = load_slot(slot_at(m, h));
         double cx[ROUNDS], cy[ROUNDS], cz[ROUNDS];
         group8_load<ROUNDS>(m, h, l8, cx, cy, cz);
-        if (inr) {
-            unsigned int s = h;
-            ulonglong2 v = sv;
-            while (v.x != key && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(slot_at(m, s)); }
-            if (v.x == key) { slot = (int)s; count = meta_count(v.y); own_out = 1; }
+        if (inr && sv.x == key) {
+            slot = (int)h; count = meta_count(sv.y); own = 1;
+        } else {   // group-uniform: all eight lanes saw the same header
+            slot = group8_resolve_rare(MapProbe{m.blk, m.mask, m.shift, m.stride}, kx, ky, kz, inr, key, h, sv, gmask, l8, &count, &own);
+            if (slot >= 0) group8_load<ROUNDS>(m, (unsigned int)slot, l8, cx, cy, cz);   // displaced or neighbour voxel: its candidates are a second trip
         }
-        if (slot >= 0) {
-            if ((unsigned int)slot != h) group8_load<ROUNDS>(m, (unsigned int)slot, l8, cx, cy, cz);   // displaced by a collision: second trip
-            group8_scan<ROUNDS>(p, l8, count, cx, cy, cz, bd2, br, tx, ty, tz);
-        }
-    }
-    if (slot < 0) {   // group-uniform: all eight lanes saw the same header
-        int bd = -1, bslot = -1;
-        unsigned long long bmeta = 0ull;
-        ulonglong2 got[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int c = l8 + 8 * u;
-            got[u] = make_ulonglong2(KEY_EMPTY, 0ull);
-            if (c < 26) {
-                const int x = kx + NB_ALL[c][0], y = ky + NB_ALL[c][1], z = kz + NB_ALL[c][2];
-                if (key_in_range(x, y, z)) got[u] = load_slot(slot_at(m, slot_of(pack_key(x, y, z), m.shift)));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int c = l8 + 8 * u;
-            ulonglong2 v = got[u];
-            if (c < 26 && v.x != KEY_EMPTY) {
-                const unsigned long long want = pack_key(kx + NB_ALL[c][0], ky + NB_ALL[c][1], kz + NB_ALL[c][2]);
-                unsigned int s = slot_of(want, m.shift);
-                while (v.x != want && v.x != KEY_EMPTY) { s = (s + 1) & m.mask; v = load_slot(slot_at(m, s)); }
-                if (v.x == want) {
-                    const int d = c < 8 ? 3 : (c < 20 ? 2 : 1);
-                    if (d > bd || (d == bd && v.y > bmeta)) { bd = d; bmeta = v.y; bslot = (int)s; }
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            const int od = __shfl_xor_sync(gmask, bd, o), os = __shfl_xor_sync(gmask, bslot, o);
-            const unsigned long long om = __shfl_xor_sync(gmask, bmeta, o);
-            if (od > bd || (od == bd && om > bmeta)) { bd = od; bmeta = om; bslot = os; }
-        }
-        if (bslot >= 0) {   // neighbour voxel: its candidates are a second trip
-            slot = bslot; count = meta_count(bmeta);
-            double cx[ROUNDS], cy[ROUNDS], cz[ROUNDS];
-            group8_load<ROUNDS>(m, (unsigned int)slot, l8, cx, cy, cz);
-            group8_scan<ROUNDS>(p, l8, count, cx, cy, cz, bd2, br, tx, ty, tz);
-        }
+        if (slot >= 0) group8_scan<ROUNDS>(p, l8, count, cx, cy, cz, bd2, br, tx, ty, tz);
     }
     if (slot >= 0 && count > 8 * ROUNDS) {   // max_points_per_voxel beyond the register-resident part (cap > 24)
         const double *bx = voxel_rows(m, (unsigned int)slot), *by = bx + m.capp, *bz = by + m.capp;
@@ -310,8 +318,16 @@ __device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, un
         const int src = (br == 0x7FFFFFFF ? 0 : (br & 7));
         tx = __shfl_sync(gmask, tx, src, 8); ty = __shfl_sync(gmask, ty, src, 8); tz = __shfl_sync(gmask, tz, src, 8);
     }
-    slot_out = slot; count_out = count; d2_out = bd2; rank_out = br == 0x7FFFFFFF ? -1 : br;
+    slot_out = slot; count_out = count; own_out = own; d2_out = bd2; rank_out = br == 0x7FFFFFFF ? -1 : br;
     t_out = br == 0x7FFFFFFF ? V3{0.0, 0.0, 0.0} : V3{tx, ty, tz};   // nothing found -> (0,0,0)
+}
+template <int ROUNDS>
+__device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, unsigned gmask, int l8, int &slot_out, int &count_out, int &own_out,
+                                               double &d2_out, int &rank_out, V3 &t_out) {
+    const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
+    const bool inr = key_in_range(kx, ky, kz);
+    const unsigned long long key = pack_key(kx, ky, kz);
+    group8_closest_at<ROUNDS>(m, p, kx, ky, kz, inr, key, inr ? slot_of(key, m.shift) : 0u, gmask, l8, slot_out, count_out, own_out, d2_out, rank_out, t_out);
 }
 
 // Pair-cooperative lookup for the cluster latency shape (registration.cu, k_frame_cluster): TWO lanes serve one query, so that one

@@ -31,7 +31,10 @@ r = np.array(rows)
 names = ["iqr", "icp_loop", "insert_claim", "insert_place", "evict_sweep"]
 print({n: round(float(v), 2) for n, v in zip(names, r.mean(axis=0))}, "total_us", round(float(r.sum(axis=1).mean()), 2), "iters/scan", np.mean(iters),
       "icp_us_per_iter", round(float(r[:, 1].mean() / np.mean(iters)), 2))
-print("classic shape, solve breakdown (last iteration of the last scan, ns, 512 ns ticks): ldlt", marks[9] - marks[8], "exp", marks[10] - marks[9])
-print("cluster shape, last iteration of the last scan (SM cycles, clock64): row reduce + DSMEM push + cluster barrier", marks[7] - marks[6], "fold", marks[8] - marks[7],
-      "ldlt", marks[9] - marks[8], "exp", marks[10] - marks[9], "| pass of warp 1", marks[12] - marks[11], "tail of the solver warp", marks[14] - marks[13],
-      "| raw marks 6..14 relative to mark 11:", [int(marks[k] - marks[11]) for k in (6, 7, 8, 9, 10, 11, 12, 13, 14)])
+cyc = lambda a, b: int(marks[b] - marks[a])
+if os.environ.get("LIMU_CLUSTER_LOOP", "0") not in ("", "0"):
+    print("cluster shape, last iteration of the last scan (SM cycles of CTA 0): row reduce + DSMEM push + cluster barrier", cyc(6, 7), "fold", cyc(7, 8), "ldlt", cyc(8, 9), "exp", cyc(9, 10),
+          "| pass of warp 1", cyc(11, 12), "tail of the solver warp", cyc(13, 14))
+else:
+    print("classic shape, last full iteration of the last scan (SM cycles of CTA 0, 1965 MHz): pass of warp 0", cyc(6, 7), "| S1 -> grid barrier done", cyc(11, 12), "| fold", cyc(12, 8),
+          "| ldlt", cyc(8, 9), "| exp", cyc(9, 10), "| S2", cyc(10, 15), "| tail of the solver warp (overlaps the next pass) ends", cyc(15, 14), "cycles after S2")
