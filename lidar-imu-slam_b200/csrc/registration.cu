@@ -52,6 +52,7 @@ struct IcpArgs {
     unsigned int *barrier;      // zeroed before launch
     double *out;                // [0..6] pose, [7] iterations, [8] converged, [9] ncorr, [10] ncand, [11] nmiss, [12] n
     int grouped;                // 1: eight lanes per query (latency shape: a few thousand keypoints)
+    int stage_doubles;          // > 0: the launch carries dynamic shared memory for the staged pass of the bandwidth shape
     int coop_scan;              // 1: sub-warp cooperative candidate scan (bandwidth shape); 0: one lane per query (latency shape)
     // point-sharded multi-GPU: every rank owns a contiguous shard of the queries and a full replica of
     // the map; per iteration the ranks exchange their NS-double row through peer-mapped mailboxes (NVLink stores).
@@ -446,6 +447,104 @@ __device__ __forceinline__ void icp_query_pass_coop(const IcpArgs &A, const vola
     }
 }
 
+// ---- staged pass of the bandwidth shape ------------------------------------------------------------------------------------------------
+// What bounds kernel mode is memory-level parallelism: a warp that waits for the ~1 us of an HBM round trip with four voxel blocks in
+// flight (registers hold the candidates) leaves the SM with ~50 KB in flight at best, and every displaced voxel adds a dependent trip.
+// Here the voxel blocks go from HBM to SHARED memory with cp.async (LDGSTS, 16 bytes per lane: ONE warp instruction moves one whole
+// 384/512-byte block, header included, no registers involved), eight blocks per commit group, double-buffered per warp: while the warp
+// scans one group of eight blocks out of shared memory, the next eight (4 KB) are in flight.
+//   1. one lane per query: transform, voxel index, hash, and map_locate (header loads, probing, 26-cell fallback) -- 32 queries per
+//      warp instruction, 32 independent chains in flight;
+//   2. four sub-batches of eight blocks: stage -> wait -> the eight lanes of a group scan the block of their lane t from shared memory
+//      (ranks l8, l8+8, ...), butterfly for the lexicographic minimum of (d^2, rank), winner's point by shuffle;
+//   3. one lane per query again: residual, weight, the 16 products, one reduce-scatter per 32 queries.
+constexpr int STAGE_MAX_STRIDE = 64;                        // doubles per block this path handles (max_points_per_voxel <= 20)
+constexpr int STAGE_SLOT = STAGE_MAX_STRIDE + 2;            // + 16 bytes: the four groups of a warp read different banks
+constexpr int STAGE_WARP_DOUBLES = 2 * 8 * STAGE_SLOT;      // two buffers of eight blocks per query warp (8448 bytes)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void stage_sub_batch(const IcpArgs &A, double *stage, int b, int slot, int lane) {
+    double *buf = stage + (b & 1) * 8 * STAGE_SLOT;
+    const int chunks = A.map.stride >> 1;                   // 16-byte chunks per block
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {                           // block i of the sub-batch belongs to lane 8*(i/2) + 2b + (i&1): group i/2, step 2b + (i&1)
+        const int sl = __shfl_sync(0xFFFFFFFFu, slot, 8 * (i >> 1) + 2 * b + (i & 1));
+        if (sl >= 0 && lane < chunks) cp_async16(buf + i * STAGE_SLOT + 2 * lane, A.map.blk + (size_t)sl * (size_t)A.map.stride + 2 * lane);
+    }
+    cp_async_commit();
+}
+
+__device__ __forceinline__ void icp_query_pass_staged(const IcpArgs &A, const volatile double *Pv, const double *in, int64_t n, int64_t wbase, int64_t wstride,
+                                                      int lane, double *stage, double &acc, int &ncorr, int &ncand, int &nmiss) {
+    const int l8 = lane & 7, g = lane >> 3, capp = A.map.capp;
+    const unsigned gmask = 0xFFu << (lane & 24);
+    for (int64_t base = wbase; base < n; base += wstride) {
+        const int64_t q = base + lane;
+        const bool on = q < n;
+        V3 s{0.0, 0.0, 0.0};
+        int slot = -1, count = 0, own = 1;
+        if (on) {
+            const Pose P{Pv[0], Pv[1], Pv[2], Pv[3], Pv[4], Pv[5], Pv[6]};
+            s = apply(P, V3{in[3 * q], in[3 * q + 1], in[3 * q + 2]});
+            A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z;
+            slot = map_locate(A.map, s, &count, &own);      // which voxel answers (own, else farthest/latest of the 27)
+        }
+        __syncwarp();
+        stage_sub_batch(A, stage, 0, slot, lane);
+        stage_sub_batch(A, stage, 1, slot, lane);
+        double my_d2 = 0.0;
+        int my_rank = -1;
+        V3 tg{0.0, 0.0, 0.0};
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (b < 3) cp_async_wait<1>(); else cp_async_wait<0>();   // sub-batch b has landed (one younger group may still be in flight)
+            __syncwarp();
+            const double *buf = stage + (b & 1) * 8 * STAGE_SLOT;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int t = 2 * b + u;                    // the group serves the query of its lane t
+                const double qx = __shfl_sync(0xFFFFFFFFu, s.x, t, 8), qy = __shfl_sync(0xFFFFFFFFu, s.y, t, 8), qz = __shfl_sync(0xFFFFFFFFu, s.z, t, 8);
+                const int qslot = __shfl_sync(0xFFFFFFFFu, slot, t, 8), qcount = __shfl_sync(0xFFFFFFFFu, count, t, 8);
+                const double *bx = buf + (g * 2 + u) * STAGE_SLOT + 2, *by = bx + capp, *bz = by + capp;
+                double bd2 = 1.7976931348623157e308, tx = 0.0, ty = 0.0, tz = 0.0;
+                int br = 0x7FFFFFFF;
+                if (qslot >= 0) {
+                    for (int r = l8; r < qcount; r += 8) {  // VoxelBlock::get_closest_point (voxel_block.cpp:87-105): ascending ranks, strict '<'
+                        const double x = bx[r], y = by[r], z = bz[r];
+                        const double d = sqnorm3(qx - x, qy - y, qz - z);
+                        if (d < bd2) { bd2 = d; br = r; tx = x; ty = y; tz = z; }
+                    }
+                }
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {
+                    const double od = __shfl_xor_sync(gmask, bd2, o);
+                    const int orr = __shfl_xor_sync(gmask, br, o);
+                    if (od < bd2 || (od == bd2 && orr < br)) { bd2 = od; br = orr; }
+                }
+                const int src = br == 0x7FFFFFFF ? 0 : (br & 7);   // the winner's point sits in lane (rank & 7) of the group
+                tx = __shfl_sync(gmask, tx, src, 8); ty = __shfl_sync(gmask, ty, src, 8); tz = __shfl_sync(gmask, tz, src, 8);
+                if (l8 == t && br != 0x7FFFFFFF) { my_d2 = bd2; my_rank = br; tg = V3{tx, ty, tz}; }
+            }
+            __syncwarp();                                   // everybody is done with this buffer: refill it
+            if (b + 2 < 4) stage_sub_batch(A, stage, b + 2, slot, lane);
+        }
+        const double d2 = my_rank >= 0 ? my_d2 : sqnorm3(tg.x - s.x, tg.y - s.y, tg.z - s.z);   // nothing found -> (0,0,0), range-tested like a real point
+        const bool gate = on && d2 < A.tau_sq;
+        double c[16];
+        contribution(c, s, tg, d2, A.th, gate);
+        acc += warp_reduce_scatter16(c);
+        ncorr += gate ? 1 : 0;
+        ncand += on ? count : 0;
+        nmiss += (on && !own) ? 1 : 0;
+    }
+}
+
 #ifdef LIMU_ICP_PHASE_TIMING
 // developer build only (tools/icp_phase_timing.py, tools/frame_phase_timing.py): %globaltimer stamps of CTA 0 / thread 0
 __device__ unsigned long long g_frame_marks[16];
@@ -574,7 +673,10 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
                 int ncorr = 0, ncand = 0, nmiss = 0;
                 const volatile double *Pv = j == 0 ? Tinit : E;   // re-read per batch: keeps 14 registers free across the lookup
                 const double *in = j == 0 ? A.points : A.work;
-                if (SHAPE == 1 && !NN27 && !PLANE) {     // bandwidth shape: one lane per query, eight lanes per voxel block
+                if (SHAPE == 1 && !NN27 && !PLANE && A.stage_doubles > 0) {   // bandwidth shape: voxel blocks staged through shared memory
+                    extern __shared__ __align__(16) double stage_smem[];
+                    icp_query_pass_staged(A, Pv, in, n, wbase, wstride, lane, stage_smem + (size_t)warp * STAGE_WARP_DOUBLES, acc, ncorr, ncand, nmiss);
+                } else if (SHAPE == 1 && !NN27 && !PLANE) {     // ... or, for blocks too large to stage, fetched by eight lanes into registers
                     if (A.map.cap <= 8) icp_query_pass_coop<1>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
                     else if (A.map.cap <= 16) icp_query_pass_coop<2>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
                     else icp_query_pass_coop<3>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
@@ -1097,12 +1199,20 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
                double *est_trace_dev, long long *ncorr_trace_dev, double *hg_trace_dev, int max_iter_all_ranks, const FrameFusion *fuse, int icp_mode) {
     limu_ctx *c = m->ctx;
     const bool nn27 = (icp_mode & LIMU_ICP_NN27) != 0, plane = (icp_mode & LIMU_ICP_PLANE) != 0;
-    if (g_icp_blocks_per_sm == 0) {
+    const bool grouped = n_hint <= 16384 && m->cap <= 64;   // latency shape: eight lanes per query, one CTA per SM
+    // bandwidth shape with the reference's rules: voxel blocks are staged through dynamic shared memory (two buffers of eight blocks per query warp)
+    const size_t stage_bytes = (!grouped && !nn27 && !plane && block_stride(m->cap) <= STAGE_MAX_STRIDE) ? (size_t)(ICP_BLOCK / 32 - 1) * STAGE_WARP_DOUBLES * sizeof(double) : 0;
+    static bool stage_attr_set[64] = {};
+    if (stage_bytes && !stage_attr_set[c->device & 63]) {
+        LIMU_CUDA_TRY(cudaFuncSetAttribute(k_icp_persistent<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+        stage_attr_set[c->device & 63] = true;
+    }
+    if (!grouped) {
         int b = 0;
-        LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_icp_persistent<1, false, false>, ICP_BLOCK, 0));
+        LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, nn27 || plane ? (const void *)k_icp_persistent<1, true, true> : (const void *)k_icp_persistent<1, false, false>,
+                                                                    ICP_BLOCK, stage_bytes));
         g_icp_blocks_per_sm = std::max(1, b);
     }
-    const bool grouped = n_hint <= 16384 && m->cap <= 64;   // latency shape: eight lanes per query, one CTA per SM
     // queries per CTA: 7 query warps (the eighth warp is the solver warp); eight lanes per query in the latency shape, one in the bandwidth shape
     const bool lanes8 = grouped;
     const int64_t want = std::max<int64_t>(1, div_up(std::max<int64_t>(n_hint, 1) * (lanes8 ? 8 : 1), ICP_BLOCK - 32));
@@ -1126,6 +1236,7 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
     A.est_trace = est_trace_dev; A.ncorr_trace = ncorr_trace_dev; A.hg_trace = hg_trace_dev;
     A.coop_scan = n_hint >= 32768 ? 1 : 0;
     A.grouped = grouped ? 1 : 0;
+    A.stage_doubles = (int)(stage_bytes / sizeof(double));
     A.nranks = 1; A.rank = 0;
     A.status = c->d_status;
     if (max_iter_all_ranks >= 0 && c->comm && c->comm->nranks > 1) {   // point-sharded call: fused peer exchange
@@ -1156,7 +1267,7 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
                                 {{(const void *)k_icp_persistent<1, false, false>, (const void *)k_icp_persistent<1, false, true>},
                                  {(const void *)k_icp_persistent<1, true, false>, (const void *)k_icp_persistent<1, true, true>}}};
     const void *fn = fns[grouped ? 0 : 1][nn27 ? 1 : 0][plane ? 1 : 0];
-    LIMU_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(ICP_BLOCK), args, 0, c->stream));
+    LIMU_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(ICP_BLOCK), args, stage_bytes, c->stream));
     LIMU_LAUNCHED();
     LIMU_TRY(prof_end(c, LIMU_STAGE_ICP));
     return LIMU_OK;
