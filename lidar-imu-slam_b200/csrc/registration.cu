@@ -25,7 +25,7 @@ namespace limu {
 
 constexpr int ICP_BLOCK = 256;
 #ifndef LIMU_BW_CTAS
-#define LIMU_BW_CTAS 3   // CTAs per SM of the bandwidth shape (register cap 65536 / (256 * LIMU_BW_CTAS))
+#define LIMU_BW_CTAS 2   // CTAs per SM of the bandwidth shape (register cap 65536 / (256 * LIMU_BW_CTAS)); measured 2 > 3 > 4 (profiles/r2f_*)
 #endif
 constexpr int NS = 20;   // 16 sums + ncorr + ncand + nmiss + pad
 constexpr int NSP = 32;  // opt-in point-to-plane variant: 21 (upper triangle of H) + 6 (g) + ncorr + ncand + nmiss + 2 pad
@@ -415,7 +415,7 @@ __device__ __forceinline__ void icp_query_pass_coop(const IcpArgs &A, const vola
             const Pose P{Pv[0], Pv[1], Pv[2], Pv[3], Pv[4], Pv[5], Pv[6]};
             s = apply(P, V3{in[3 * q], in[3 * q + 1], in[3 * q + 2]});
             A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z;
-            kx = vox_index(s.x, A.map.vox); ky = vox_index(s.y, A.map.vox); kz = vox_index(s.z, A.map.vox);
+            kx = vox_index(A.map, s.x); ky = vox_index(A.map, s.y); kz = vox_index(A.map, s.z);
             inr = key_in_range(kx, ky, kz) ? 1 : 0;
             key = pack_key(kx, ky, kz);
             h = inr ? slot_of(key, A.map.shift) : 0u;
@@ -480,24 +480,48 @@ __device__ __forceinline__ void stage_sub_batch(const IcpArgs &A, double *stage,
     cp_async_commit();
 }
 
+// one lane per query: running source point and the voxel that answers it
+struct StagedQuery {
+    V3 s;
+    int slot, count, own, on;
+};
+__device__ __forceinline__ V3 staged_load_raw(const double *in, int64_t base, int lane, int64_t n) {
+    const int64_t q = base + lane;
+    return q < n ? V3{in[3 * q], in[3 * q + 1], in[3 * q + 2]} : V3{0.0, 0.0, 0.0};
+}
+__device__ __forceinline__ StagedQuery staged_prepare(const IcpArgs &A, const Pose &P, const V3 &raw, int64_t base, int lane, int64_t n) {
+    StagedQuery c;
+    const int64_t q = base + lane;
+    c.on = q < n ? 1 : 0;
+    c.s = V3{0.0, 0.0, 0.0};
+    c.slot = -1; c.count = 0; c.own = 1;
+    if (c.on) {
+        // j == 0: source = init_guess * points (:102-103); later: source <- estimate * source (:119), applied lazily at this visit
+        c.s = apply(P, raw);
+        A.work[3 * q] = c.s.x; A.work[3 * q + 1] = c.s.y; A.work[3 * q + 2] = c.s.z;
+        c.slot = map_locate(A.map, c.s, &c.count, &c.own);   // which voxel answers (own, else farthest/latest of the 27)
+    }
+    return c;
+}
+
+// Software pipeline over the batches of 32 queries a warp visits: while the eight-block groups of batch k are in flight / being scanned,
+// the warp already transforms and locates batch k+1 (its header loads overlap the copies) and has the raw points of batch k+2 on the way,
+// so a batch costs about ONE memory round trip instead of four dependent ones (raw point -> header -> blocks -> next batch).
 __device__ __forceinline__ void icp_query_pass_staged(const IcpArgs &A, const volatile double *Pv, const double *in, int64_t n, int64_t wbase, int64_t wstride,
                                                       int lane, double *stage, double &acc, int &ncorr, int &ncand, int &nmiss) {
     const int l8 = lane & 7, g = lane >> 3, capp = A.map.capp;
     const unsigned gmask = 0xFFu << (lane & 24);
+    if (wbase >= n) return;   // warp-uniform
+    const Pose P{Pv[0], Pv[1], Pv[2], Pv[3], Pv[4], Pv[5], Pv[6]};
+    StagedQuery cur = staged_prepare(A, P, staged_load_raw(in, wbase, lane, n), wbase, lane, n);
+    V3 raw_next = staged_load_raw(in, wbase + wstride, lane, n);
     for (int64_t base = wbase; base < n; base += wstride) {
-        const int64_t q = base + lane;
-        const bool on = q < n;
-        V3 s{0.0, 0.0, 0.0};
-        int slot = -1, count = 0, own = 1;
-        if (on) {
-            const Pose P{Pv[0], Pv[1], Pv[2], Pv[3], Pv[4], Pv[5], Pv[6]};
-            s = apply(P, V3{in[3 * q], in[3 * q + 1], in[3 * q + 2]});
-            A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z;
-            slot = map_locate(A.map, s, &count, &own);      // which voxel answers (own, else farthest/latest of the 27)
-        }
         __syncwarp();
-        stage_sub_batch(A, stage, 0, slot, lane);
-        stage_sub_batch(A, stage, 1, slot, lane);
+        stage_sub_batch(A, stage, 0, cur.slot, lane);
+        stage_sub_batch(A, stage, 1, cur.slot, lane);
+        const V3 raw_after = staged_load_raw(in, base + 2 * wstride, lane, n);
+        const StagedQuery nxt = staged_prepare(A, P, raw_next, base + wstride, lane, n);   // all lanes off when base + wstride >= n
+        raw_next = raw_after;
         double my_d2 = 0.0;
         int my_rank = -1;
         V3 tg{0.0, 0.0, 0.0};
@@ -509,8 +533,8 @@ __device__ __forceinline__ void icp_query_pass_staged(const IcpArgs &A, const vo
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int t = 2 * b + u;                    // the group serves the query of its lane t
-                const double qx = __shfl_sync(0xFFFFFFFFu, s.x, t, 8), qy = __shfl_sync(0xFFFFFFFFu, s.y, t, 8), qz = __shfl_sync(0xFFFFFFFFu, s.z, t, 8);
-                const int qslot = __shfl_sync(0xFFFFFFFFu, slot, t, 8), qcount = __shfl_sync(0xFFFFFFFFu, count, t, 8);
+                const double qx = __shfl_sync(0xFFFFFFFFu, cur.s.x, t, 8), qy = __shfl_sync(0xFFFFFFFFu, cur.s.y, t, 8), qz = __shfl_sync(0xFFFFFFFFu, cur.s.z, t, 8);
+                const int qslot = __shfl_sync(0xFFFFFFFFu, cur.slot, t, 8), qcount = __shfl_sync(0xFFFFFFFFu, cur.count, t, 8);
                 const double *bx = buf + (g * 2 + u) * STAGE_SLOT + 2, *by = bx + capp, *bz = by + capp;
                 double bd2 = 1.7976931348623157e308, tx = 0.0, ty = 0.0, tz = 0.0;
                 int br = 0x7FFFFFFF;
@@ -532,16 +556,17 @@ __device__ __forceinline__ void icp_query_pass_staged(const IcpArgs &A, const vo
                 if (l8 == t && br != 0x7FFFFFFF) { my_d2 = bd2; my_rank = br; tg = V3{tx, ty, tz}; }
             }
             __syncwarp();                                   // everybody is done with this buffer: refill it
-            if (b + 2 < 4) stage_sub_batch(A, stage, b + 2, slot, lane);
+            if (b + 2 < 4) stage_sub_batch(A, stage, b + 2, cur.slot, lane);
         }
-        const double d2 = my_rank >= 0 ? my_d2 : sqnorm3(tg.x - s.x, tg.y - s.y, tg.z - s.z);   // nothing found -> (0,0,0), range-tested like a real point
-        const bool gate = on && d2 < A.tau_sq;
+        const double d2 = my_rank >= 0 ? my_d2 : sqnorm3(tg.x - cur.s.x, tg.y - cur.s.y, tg.z - cur.s.z);   // nothing found -> (0,0,0), range-tested like a real point
+        const bool gate = cur.on && d2 < A.tau_sq;
         double c[16];
-        contribution(c, s, tg, d2, A.th, gate);
+        contribution(c, cur.s, tg, d2, A.th, gate);
         acc += warp_reduce_scatter16(c);
         ncorr += gate ? 1 : 0;
-        ncand += on ? count : 0;
-        nmiss += (on && !own) ? 1 : 0;
+        ncand += cur.on ? cur.count : 0;
+        nmiss += (cur.on && !cur.own) ? 1 : 0;
+        cur = nxt;
     }
 }
 
@@ -615,9 +640,8 @@ static __device__ __noinline__ void solve_normal_equations(const double *S, doub
 }
 
 // SHAPE 0 = latency build (a few thousand keypoints: one CTA per SM at most, so the compiler may use up to 255 registers and the serial
-// Gauss-Newton solve stays out of local memory); SHAPE 1 = bandwidth build for the HBM-bound kernel mode (millions of queries): 85
-// registers -> 3 CTAs = 96 eight-lane groups per SM, each with one 384/512-byte block in flight (~48 KB per SM, above what the measured
-// HBM latency x bandwidth asks for), the query pass free of spills, the solve out of line.
+// Gauss-Newton solve stays out of local memory); SHAPE 1 = bandwidth build for kernel mode (millions of queries against a map far larger
+// than L2): LIMU_BW_CTAS CTAs per SM, voxel blocks staged through shared memory (icp_query_pass_staged), the solve out of line.
 template <int SHAPE, bool NN27, bool PLANE>
 static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTAS) k_icp_persistent(const IcpArgs A) {
     constexpr int NSX = PLANE ? NSP : NS;              // doubles per partial row

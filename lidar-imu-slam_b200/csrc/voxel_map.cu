@@ -1,6 +1,8 @@
 // voxel_map.cu -- GPU-resident voxel hash map: build, capped ordered insertion, eviction, queries, dump.
 // Replaces lidar::VoxelHashMap / lidar::VoxelBlock (L/src/sensors/lidar/helpers/voxel_hash_map.cpp,
 // voxel_block.cpp). Layout and lookup rules: voxel_map.cuh.
+#include <math.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -186,6 +188,10 @@ limu::MapView limu_map::view() const {
     v.capp = limu::cap_padded(cap);
     v.stride = limu::block_stride(cap);
     v.vox = vox_size;
+    {   // power of two? (mantissa exactly 0.5)
+        int e = 0;
+        v.inv_vox = (vox_size > 0.0 && frexp(vox_size, &e) == 0.5) ? 1.0 / vox_size : 0.0;
+    }
     return v;
 }
 

@@ -47,6 +47,7 @@ struct MapView {
     int capp;            // cap rounded up to a multiple of 4: row length of the per-voxel SoA block
     int stride;          // doubles per block: 2 + 3*capp rounded up to 16 (= 128 B)
     double vox;
+    double inv_vox;      // 1/vox when vox is a power of two (then p * inv_vox == p / vox bit for bit and the FP64 division subroutine is avoided), else 0
 };
 __host__ __device__ __forceinline__ int cap_padded(int cap) { return (cap + 3) & ~3; }
 __host__ __device__ __forceinline__ int block_stride(int cap) { return (2 + 3 * cap_padded(cap) + 15) & ~15; }
@@ -56,6 +57,7 @@ __device__ __forceinline__ double *voxel_rows(const MapView &m, unsigned int slo
 
 // utils::get_vox_index, calculation_helpers.cpp:142-147: IEEE double division, truncation toward zero.
 __device__ __forceinline__ int vox_index(double p, double v) { return __double2int_rz(p / v); }
+__device__ __forceinline__ int vox_index(const MapView &m, double p) { return __double2int_rz(m.inv_vox != 0.0 ? p * m.inv_vox : p / m.vox); }
 
 __device__ __forceinline__ bool key_in_range(int x, int y, int z) {
     return (unsigned)(x + KEY_BIAS - 1) < (unsigned)(2 * KEY_BIAS - 1) && (unsigned)(y + KEY_BIAS - 1) < (unsigned)(2 * KEY_BIAS - 1) &&
@@ -129,7 +131,7 @@ __device__ __forceinline__ void block_closest(const MapView &m, int slot, int co
 // Step 1 of the lookup: WHICH voxel answers the query (rules (a)/(b) below). Returns its slot (or -1), its count,
 // and whether it is the query's own voxel.
 __device__ __forceinline__ int map_locate(const MapView &m, const V3 &p, int *count_out, int *own_out) {
-    const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
+    const int kx = vox_index(m, p.x), ky = vox_index(m, p.y), kz = vox_index(m, p.z);
     *own_out = 0;
     *count_out = 0;
     if (key_in_range(kx, ky, kz)) {
@@ -324,7 +326,7 @@ __device__ __forceinline__ void group8_closest_at(const MapView &m, const V3 &p,
 template <int ROUNDS>
 __device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, unsigned gmask, int l8, int &slot_out, int &count_out, int &own_out,
                                                double &d2_out, int &rank_out, V3 &t_out) {
-    const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
+    const int kx = vox_index(m, p.x), ky = vox_index(m, p.y), kz = vox_index(m, p.z);
     const bool inr = key_in_range(kx, ky, kz);
     const unsigned long long key = pack_key(kx, ky, kz);
     group8_closest_at<ROUNDS>(m, p, kx, ky, kz, inr, key, inr ? slot_of(key, m.shift) : 0u, gmask, l8, slot_out, count_out, own_out, d2_out, rank_out, t_out);
@@ -359,7 +361,7 @@ __device__ __forceinline__ void pair_scan(const V3 &p, int l2, int count, const 
 }
 template <int ROUNDS>
 __device__ __forceinline__ void pair_closest(const MapView &m, const V3 &p, int l2, int &count_out, int &own_out, double &d2_out, V3 &t_out, int &rank_out) {
-    const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
+    const int kx = vox_index(m, p.x), ky = vox_index(m, p.y), kz = vox_index(m, p.z);
     const bool inr = key_in_range(kx, ky, kz);
     const unsigned long long key = pack_key(kx, ky, kz);
     const unsigned int h = inr ? slot_of(key, m.shift) : 0u;
@@ -438,7 +440,7 @@ __device__ __forceinline__ void pair_closest(const MapView &m, const V3 &p, int 
 __device__ __forceinline__ Nearest map_closest27(const MapView &m, const V3 &p) {
     Nearest r;
     r.x = r.y = r.z = 0.0; r.rank = -1; r.ncand = 0; r.slot = -1; r.own = 0;
-    const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
+    const int kx = vox_index(m, p.x), ky = vox_index(m, p.y), kz = vox_index(m, p.z);
     double best = 1.7976931348623157e308;
     for (int dx = -1; dx <= 1; ++dx) {
         ulonglong2 got[9];
@@ -473,7 +475,7 @@ __device__ __forceinline__ Nearest map_closest27(const MapView &m, const V3 &p) 
 // points of the cells it found, and a 3-step butterfly takes the lexicographic minimum of (d^2, cell, rank).
 __device__ __forceinline__ void group8_closest27(const MapView &m, const V3 &p, unsigned gmask, int l8, int &slot_out, int &count_out, int &own_out,
                                                  double &d2_out, int &rank_out) {
-    const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
+    const int kx = vox_index(m, p.x), ky = vox_index(m, p.y), kz = vox_index(m, p.z);
     ulonglong2 got[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -581,7 +583,7 @@ __device__ __forceinline__ int voxel_normal(const MapView &m, int slot, int c, d
 //     (cap - count) smallest input indices in ascending order -- exactly the points a serial "append until full" loop
 //     (voxel_block.cpp:68-73) would have kept. Returns the slot (PEND_NONE on failure).
 __device__ __forceinline__ unsigned int insert_claim_one(const MapView &m, const V3 &p, unsigned int i, unsigned long long birth_base, DevStatus *st, bool *claimed) {
-    const int kx = vox_index(p.x, m.vox), ky = vox_index(p.y, m.vox), kz = vox_index(p.z, m.vox);
+    const int kx = vox_index(m, p.x), ky = vox_index(m, p.y), kz = vox_index(m, p.z);
     unsigned int slot = PEND_NONE;
     if (!key_in_range(kx, ky, kz) || p.x != p.x || p.y != p.y || p.z != p.z) { st->key_range = 1; return slot; }   // NaN -> INT_MIN in the reference
     const unsigned long long key = pack_key(kx, ky, kz);
@@ -646,7 +648,7 @@ __device__ __forceinline__ void remove_far_one(const MapView &m, int64_t s, doub
     const double max_sq = max_distance * max_distance;
     int x, y, z;
     unpack_key(key, x, y, z);
-    const long long dx = x - vox_index(ox, m.vox), dy = y - vox_index(oy, m.vox), dz = z - vox_index(oz, m.vox);
+    const long long dx = x - vox_index(m, ox), dy = y - vox_index(m, oy), dz = z - vox_index(m, oz);
     const long long d2 = dx * dx + dy * dy + dz * dz;
     if (!((double)d2 > max_sq)) return;
     double *px = voxel_rows(m, (unsigned int)s), *py = px + m.capp, *pz = py + m.capp;
