@@ -455,8 +455,8 @@ __device__ __forceinline__ void icp_query_pass_coop(const IcpArgs &A, const vola
 // scans one group of eight blocks out of shared memory, the next eight (4 KB) are in flight.
 //   1. one lane per query: transform, voxel index, hash, and map_locate (header loads, probing, 26-cell fallback) -- 32 queries per
 //      warp instruction, 32 independent chains in flight;
-//   2. four sub-batches of eight blocks: stage -> wait -> the eight lanes of a group scan the block of their lane t from shared memory
-//      (ranks l8, l8+8, ...), butterfly for the lexicographic minimum of (d^2, rank), winner's point by shuffle;
+//   2. four steps of eight blocks: stage -> wait -> the four lanes of a quad scan the block of their lane t from shared memory
+//      (ranks l4, l4+4, ...), butterfly for the lexicographic minimum of (d^2, rank), winner's point by shuffle;
 //   3. one lane per query again: residual, weight, the 16 products, one reduce-scatter per 32 queries.
 constexpr int STAGE_MAX_STRIDE = 64;                        // doubles per block this path handles (max_points_per_voxel <= 20)
 constexpr int STAGE_SLOT = STAGE_MAX_STRIDE + 2;            // + 16 bytes: the four groups of a warp read different banks
@@ -469,13 +469,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ void stage_sub_batch(const IcpArgs &A, double *stage, int b, int slot, int lane) {
-    double *buf = stage + (b & 1) * 8 * STAGE_SLOT;
+// Step t of a batch: the eight quads of a warp serve the queries of lanes 4i + t (i = quad). Their eight blocks are one commit group.
+__device__ __forceinline__ void stage_step(const IcpArgs &A, double *stage, int t, const double *blk_ptr, int lane) {
+    double *buf = stage + (t & 1) * 8 * STAGE_SLOT;
     const int chunks = A.map.stride >> 1;                   // 16-byte chunks per block
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {                           // block i of the sub-batch belongs to lane 8*(i/2) + 2b + (i&1): group i/2, step 2b + (i&1)
-        const int sl = __shfl_sync(0xFFFFFFFFu, slot, 8 * (i >> 1) + 2 * b + (i & 1));
-        if (sl >= 0 && lane < chunks) cp_async16(buf + i * STAGE_SLOT + 2 * lane, A.map.blk + (size_t)sl * (size_t)A.map.stride + 2 * lane);
+    for (int i = 0; i < 8; ++i) {
+        const unsigned long long p = __shfl_sync(0xFFFFFFFFu, (unsigned long long)blk_ptr, 4 * i + t);
+        if (p && lane < chunks) cp_async16(buf + i * STAGE_SLOT + 2 * lane, reinterpret_cast<const double *>(p) + 2 * lane);
     }
     cp_async_commit();
 }
@@ -505,20 +506,23 @@ __device__ __forceinline__ StagedQuery staged_prepare(const IcpArgs &A, const Po
 }
 
 // Software pipeline over the batches of 32 queries a warp visits: while the eight-block groups of batch k are in flight / being scanned,
-// the warp already transforms and locates batch k+1 (its header loads overlap the copies) and has the raw points of batch k+2 on the way,
-// so a batch costs about ONE memory round trip instead of four dependent ones (raw point -> header -> blocks -> next batch).
+// the warp already transforms and locates batch k+1 (its header loads overlap the copies) and has the raw points of batch k+2 on the way.
+// FOUR lanes scan a block (quad q = lane / 4 serves the query of its lane t in step t = 0..3): measured, the pass is bound by issued
+// instructions, not by HBM (a cap-10 map with half the bytes took the same time), and four steps of eight quads cost about half the
+// shuffles, butterflies and loop overhead of eight steps of four octets for the same k-bar distance evaluations.
 __device__ __forceinline__ void icp_query_pass_staged(const IcpArgs &A, const volatile double *Pv, const double *in, int64_t n, int64_t wbase, int64_t wstride,
                                                       int lane, double *stage, double &acc, int &ncorr, int &ncand, int &nmiss) {
-    const int l8 = lane & 7, g = lane >> 3, capp = A.map.capp;
-    const unsigned gmask = 0xFFu << (lane & 24);
+    const int l4 = lane & 3, quad = lane >> 2, capp = A.map.capp;
+    const unsigned qmask = 0xFu << (lane & 28);
     if (wbase >= n) return;   // warp-uniform
     const Pose P{Pv[0], Pv[1], Pv[2], Pv[3], Pv[4], Pv[5], Pv[6]};
     StagedQuery cur = staged_prepare(A, P, staged_load_raw(in, wbase, lane, n), wbase, lane, n);
     V3 raw_next = staged_load_raw(in, wbase + wstride, lane, n);
     for (int64_t base = wbase; base < n; base += wstride) {
+        const double *blk_ptr = cur.slot >= 0 ? A.map.blk + (size_t)cur.slot * (size_t)A.map.stride : nullptr;
         __syncwarp();
-        stage_sub_batch(A, stage, 0, cur.slot, lane);
-        stage_sub_batch(A, stage, 1, cur.slot, lane);
+        stage_step(A, stage, 0, blk_ptr, lane);
+        stage_step(A, stage, 1, blk_ptr, lane);
         const V3 raw_after = staged_load_raw(in, base + 2 * wstride, lane, n);
         const StagedQuery nxt = staged_prepare(A, P, raw_next, base + wstride, lane, n);   // all lanes off when base + wstride >= n
         raw_next = raw_after;
@@ -526,37 +530,32 @@ __device__ __forceinline__ void icp_query_pass_staged(const IcpArgs &A, const vo
         int my_rank = -1;
         V3 tg{0.0, 0.0, 0.0};
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            if (b < 3) cp_async_wait<1>(); else cp_async_wait<0>();   // sub-batch b has landed (one younger group may still be in flight)
+        for (int t = 0; t < 4; ++t) {
+            if (t < 3) cp_async_wait<1>(); else cp_async_wait<0>();   // the blocks of step t have landed (one younger group may still be in flight)
             __syncwarp();
-            const double *buf = stage + (b & 1) * 8 * STAGE_SLOT;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int t = 2 * b + u;                    // the group serves the query of its lane t
-                const double qx = __shfl_sync(0xFFFFFFFFu, cur.s.x, t, 8), qy = __shfl_sync(0xFFFFFFFFu, cur.s.y, t, 8), qz = __shfl_sync(0xFFFFFFFFu, cur.s.z, t, 8);
-                const int qslot = __shfl_sync(0xFFFFFFFFu, cur.slot, t, 8), qcount = __shfl_sync(0xFFFFFFFFu, cur.count, t, 8);
-                const double *bx = buf + (g * 2 + u) * STAGE_SLOT + 2, *by = bx + capp, *bz = by + capp;
-                double bd2 = 1.7976931348623157e308, tx = 0.0, ty = 0.0, tz = 0.0;
-                int br = 0x7FFFFFFF;
-                if (qslot >= 0) {
-                    for (int r = l8; r < qcount; r += 8) {  // VoxelBlock::get_closest_point (voxel_block.cpp:87-105): ascending ranks, strict '<'
-                        const double x = bx[r], y = by[r], z = bz[r];
-                        const double d = sqnorm3(qx - x, qy - y, qz - z);
-                        if (d < bd2) { bd2 = d; br = r; tx = x; ty = y; tz = z; }
-                    }
+            const double qx = __shfl_sync(0xFFFFFFFFu, cur.s.x, t, 4), qy = __shfl_sync(0xFFFFFFFFu, cur.s.y, t, 4), qz = __shfl_sync(0xFFFFFFFFu, cur.s.z, t, 4);
+            const int qslot = __shfl_sync(0xFFFFFFFFu, cur.slot, t, 4), qcount = __shfl_sync(0xFFFFFFFFu, cur.count, t, 4);
+            const double *bx = stage + ((t & 1) * 8 + quad) * STAGE_SLOT + 2, *by = bx + capp, *bz = by + capp;
+            double bd2 = 1.7976931348623157e308, tx = 0.0, ty = 0.0, tz = 0.0;
+            int br = 0x7FFFFFFF;
+            if (qslot >= 0) {
+                for (int r = l4; r < qcount; r += 4) {      // VoxelBlock::get_closest_point (voxel_block.cpp:87-105): ascending ranks, strict '<'
+                    const double x = bx[r], y = by[r], z = bz[r];
+                    const double d = sqnorm3(qx - x, qy - y, qz - z);
+                    if (d < bd2) { bd2 = d; br = r; tx = x; ty = y; tz = z; }
                 }
-#pragma unroll
-                for (int o = 4; o > 0; o >>= 1) {
-                    const double od = __shfl_xor_sync(gmask, bd2, o);
-                    const int orr = __shfl_xor_sync(gmask, br, o);
-                    if (od < bd2 || (od == bd2 && orr < br)) { bd2 = od; br = orr; }
-                }
-                const int src = br == 0x7FFFFFFF ? 0 : (br & 7);   // the winner's point sits in lane (rank & 7) of the group
-                tx = __shfl_sync(gmask, tx, src, 8); ty = __shfl_sync(gmask, ty, src, 8); tz = __shfl_sync(gmask, tz, src, 8);
-                if (l8 == t && br != 0x7FFFFFFF) { my_d2 = bd2; my_rank = br; tg = V3{tx, ty, tz}; }
             }
+#pragma unroll
+            for (int o = 2; o > 0; o >>= 1) {               // lexicographic minimum of (d^2, rank) = "first minimum wins"
+                const double od = __shfl_xor_sync(qmask, bd2, o);
+                const int orr = __shfl_xor_sync(qmask, br, o);
+                if (od < bd2 || (od == bd2 && orr < br)) { bd2 = od; br = orr; }
+            }
+            const int src = br == 0x7FFFFFFF ? 0 : (br & 3);   // the winner's point sits in lane (rank & 3) of the quad
+            tx = __shfl_sync(qmask, tx, src, 4); ty = __shfl_sync(qmask, ty, src, 4); tz = __shfl_sync(qmask, tz, src, 4);
+            if (l4 == t && br != 0x7FFFFFFF) { my_d2 = bd2; my_rank = br; tg = V3{tx, ty, tz}; }
             __syncwarp();                                   // everybody is done with this buffer: refill it
-            if (b + 2 < 4) stage_sub_batch(A, stage, b + 2, cur.slot, lane);
+            if (t + 2 < 4) stage_step(A, stage, t + 2, blk_ptr, lane);
         }
         const double d2 = my_rank >= 0 ? my_d2 : sqnorm3(tg.x - cur.s.x, tg.y - cur.s.y, tg.z - cur.s.z);   // nothing found -> (0,0,0), range-tested like a real point
         const bool gate = cur.on && d2 < A.tau_sq;
