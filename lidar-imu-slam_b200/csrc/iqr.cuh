@@ -104,7 +104,8 @@ __device__ __forceinline__ void iqr_block(IqrSmem &sm, const double *__restrict_
 constexpr int IQR_GRID_MAX = 4096;
 
 template <int BLOCK>
-__device__ __forceinline__ void iqr_grid_select(double *sd2 /* shared, IQR_GRID_MAX */, const double *__restrict__ xyz, int n, double *sel /* global, 4 */) {
+__device__ __forceinline__ void iqr_grid_select(double *sd2 /* shared, IQR_GRID_MAX */, const double *__restrict__ xyz, int n, double *sel /* global, 4 */,
+                                                int nblocks = 0 /* CTAs 0..nblocks-1 share the ranking (0: the whole grid) */) {
     for (int i = threadIdx.x; i < n; i += BLOCK) {
         const double x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
         sd2[i] = x * x + y * y + z * z;   // icp.cpp:97-100
@@ -114,7 +115,7 @@ __device__ __forceinline__ void iqr_grid_select(double *sd2 /* shared, IQR_GRID_
     const int lo = (m % 2 == 0) ? m / 2 - 1 : m / 2, hi = m / 2;   // median(): common.hpp:22-38
     const int r0 = lo, r1 = hi, r2 = lo + u0, r3 = hi + u0;
     const int lane = threadIdx.x & 31;
-    const int gwarp = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5), nwarps = gridDim.x * (BLOCK / 32);
+    const int gwarp = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5), nwarps = (nblocks > 0 ? nblocks : (int)gridDim.x) * (BLOCK / 32);
     for (int i = gwarp; i < n; i += nwarps) {   // warp-uniform trip count
         const double d = sd2[i];
         int c = 0;
@@ -158,6 +159,66 @@ __device__ __forceinline__ void iqr_grid_filter(IqrSmem &sm, const double *sd2, 
         __syncthreads();
     }
     if (tid == 0) *out_count = base;
+}
+
+// Tukey bounds from the four order statistics, inlier flags and the order-preserving INDEX list, by one CTA in its own shared memory in a
+// single pass (IQR_GRID_MAX / BLOCK consecutive candidates per thread, one block scan): every CTA that runs the Gauss-Newton loop derives
+// the keypoint list itself, so nobody waits for CTA 0 to compact it (icp.cpp:103-121; same bounds and comparisons as iqr_grid_filter).
+// write_out: also store the keypoints and their count to global memory (what the host reads back). Returns the keypoint count.
+template <int BLOCK>
+__device__ __forceinline__ int iqr_local_compact(int *ws /* shared, 32 */, int *total /* shared */, const double *sd2, const double *__restrict__ xyz, int n0,
+                                                 const double *sel, unsigned short *qidx /* shared, IQR_GRID_MAX */, double *__restrict__ out, int *out_count,
+                                                 bool write_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = n0 / 2;
+    const double v0 = __ldcg(sel), v1 = __ldcg(sel + 1), v2 = __ldcg(sel + 2), v3 = __ldcg(sel + 3);
+    const double q1 = (m % 2 == 0) ? (v0 + v1) / 2.0 : v1;
+    const double q3 = (m % 2 == 0) ? (v2 + v3) / 2.0 : v3;
+    const double iqr = q3 - q1;
+    const double low = q1 - 1.25 * iqr, high = q3 + 1.25 * iqr;   // icp.cpp:104-105
+    constexpr int PER = IQR_GRID_MAX / BLOCK;
+    unsigned int f = 0;
+    int cnt = 0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int i = tid * PER + u;
+        const double d = i < n0 ? sd2[i] : 0.0;
+        const bool in = i < n0 && d >= low && d <= high;          // icp.cpp:117
+        f |= (in ? 1u : 0u) << u;
+        cnt += in ? 1 : 0;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int v = lane < BLOCK / 32 ? ws[lane] : 0;
+        int wi = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += t; }
+        ws[lane] = wi - v;
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    int pos = ws[warp] + incl - cnt;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        if (f & (1u << u)) {
+            const int i = tid * PER + u;
+            qidx[pos] = (unsigned short)i;
+            if (write_out) {
+                out[3 * (size_t)pos] = xyz[3 * (size_t)i];
+                out[3 * (size_t)pos + 1] = xyz[3 * (size_t)i + 1];
+                out[3 * (size_t)pos + 2] = xyz[3 * (size_t)i + 2];
+            }
+            ++pos;
+        }
+    }
+    const int n = *total;
+    if (write_out && tid == 0) *out_count = n;
+    __syncthreads();
+    return n;
 }
 
 }  // namespace limu

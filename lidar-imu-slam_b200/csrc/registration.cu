@@ -335,8 +335,8 @@ __device__ __forceinline__ void contribution_pair(int l8, const V3 &s, const V3 
 // One pass over this warp's share of the queries with eight lanes per query (four queries per warp and step), see group8_closest.
 // On return lane L holds the warp total of sum index L>>1 (the layout of warp_reduce_scatter16) in `acc`.
 template <bool NN27, bool PLANE, int ROUNDS>
-__device__ __forceinline__ void icp_query_pass_grouped(const IcpArgs &A, const volatile double *Pv, const double *in, int64_t n, int64_t gbase, int64_t gstride,
-                                                       int lane, double &acc, int &ncorr, int &ncand, int &nmiss) {
+__device__ __forceinline__ void icp_query_pass_grouped(const IcpArgs &A, const volatile double *Pv, const double *in, const unsigned short *qidx, int64_t n, int64_t gbase,
+                                                       int64_t gstride, int lane, double &acc, int &ncorr, int &ncand, int &nmiss) {
     const int l8 = lane & 7;
     const unsigned gmask = 0xFFu << (lane & 24);
     const int64_t wfirst = gbase - (lane >> 3);   // first group of this warp: the four groups of a warp iterate together
@@ -349,7 +349,8 @@ __device__ __forceinline__ void icp_query_pass_grouped(const IcpArgs &A, const v
         double d2 = 0.0;
         if (on) {
             const Pose P{Pv[0], Pv[1], Pv[2], Pv[3], Pv[4], Pv[5], Pv[6]};
-            s = apply(P, V3{in[3 * q], in[3 * q + 1], in[3 * q + 2]});
+            const size_t qi = qidx ? (size_t)qidx[q] : (size_t)q;   // first iteration of a fused frame: keypoint q is IQR candidate qidx[q]
+            s = apply(P, V3{in[3 * qi], in[3 * qi + 1], in[3 * qi + 2]});
             if (l8 == 0) { A.work[3 * q] = s.x; A.work[3 * q + 1] = s.y; A.work[3 * q + 2] = s.z; }
             if (NN27) {
                 group8_closest27(A.map, s, gmask, l8, slot, count, own, d2, my_rank);
@@ -656,24 +657,28 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
     const bool icp_member = (int)blockIdx.x < A.icp_blocks;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FT_MARK(0);
-    if (A.iqr_in) {   // KissICP::iqr_processing (icp.cpp:88-124, :133) on CTA 0, then publish the keypoints to the grid
-        // Latency shape: the filter is spread over the whole grid (iqr.cuh: every CTA ranks its share of the ~2.3 k squared ranges by
-        // counting, CTA 0 compacts) -- 25 -> 15 us per scan. The bandwidth shape keeps the one-CTA select (and its 4 CTAs/SM of shared memory).
+    __shared__ unsigned short qidx_s[SHAPE == 0 ? IQR_GRID_MAX : 1];
+    int n_keypoints = -1;   // >= 0: the keypoints are IQR candidates qidx_s[0 .. n_keypoints) (known to the CTAs of the Gauss-Newton loop)
+    if (A.iqr_in) {   // KissICP::iqr_processing (icp.cpp:88-124, :133)
+        // Latency shape: only the CTAs that will run the Gauss-Newton loop take part. They rank their share of the ~2.5 k squared ranges by
+        // counting and meet at THEIR barrier (the leading CTAs of a launch start first; the whole-grid barrier also waits for the last CTA to
+        // be scheduled); then each of them derives bounds, flags and the keypoint index list in its own shared memory, so nobody waits for
+        // CTA 0 to compact (CTA 0 also writes the keypoints out for the host). The bandwidth shape keeps the one-CTA select.
         __shared__ double iqr_sd2[SHAPE == 0 ? IQR_GRID_MAX : 1];
         const int n0 = __ldcg(A.iqr_n);
         if (SHAPE == 0 && n0 > 1 && n0 <= IQR_GRID_MAX) {   // uniform across the grid
-            iqr_grid_select<ICP_BLOCK>(iqr_sd2, A.iqr_in, n0, A.iqr_d2);
-            gs.sync();
-            if (blockIdx.x == 0) iqr_grid_filter<ICP_BLOCK>(iqr_sm, iqr_sd2, A.iqr_in, n0, A.iqr_d2, A.iqr_out, A.iqr_count, nullptr);
-            gs.sync();
-        } else
-        {
+            if (icp_member) {
+                iqr_grid_select<ICP_BLOCK>(iqr_sd2, A.iqr_in, n0, A.iqr_d2, A.icp_blocks);
+                gs_icp.sync();
+                n_keypoints = iqr_local_compact<ICP_BLOCK>(iqr_sm.ws, &iqr_sm.total, iqr_sd2, A.iqr_in, n0, A.iqr_d2, qidx_s, A.iqr_out, A.iqr_count, blockIdx.x == 0);
+            }
+        } else {
             if (blockIdx.x == 0) iqr_block<ICP_BLOCK>(iqr_sm, A.iqr_in, *A.iqr_n, A.iqr_d2, A.iqr_out, A.iqr_count, nullptr);
             gs.sync();
         }
     }
     FT_MARK(1);
-    const int64_t n = A.n_dev ? (int64_t)__ldcg(A.n_dev) : A.n_max;
+    const int64_t n = n_keypoints >= 0 ? (int64_t)n_keypoints : (A.n_dev ? (int64_t)__ldcg(A.n_dev) : A.n_max);
     const bool run_icp = !(__ldcg(A.map_counters) == 0ull || A.max_iter <= 0);   // ICP :99-100: empty map -> init_guess
     if (threadIdx.x < 7) { Tinit[threadIdx.x] = A.init_pose[threadIdx.x]; Ticp[threadIdx.x] = threadIdx.x == 3 ? 1.0 : 0.0; }
     if (threadIdx.x < NSX) S[threadIdx.x] = 0.0;
@@ -695,7 +700,8 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
                 double acc = 0.0;            // lane L: running total of sum index L>>1
                 int ncorr = 0, ncand = 0, nmiss = 0;
                 const volatile double *Pv = j == 0 ? Tinit : E;   // re-read per batch: keeps 14 registers free across the lookup
-                const double *in = j == 0 ? A.points : A.work;
+                const double *in = j == 0 ? (n_keypoints >= 0 ? A.iqr_in : A.points) : A.work;
+                const unsigned short *qi0 = (j == 0 && n_keypoints >= 0) ? qidx_s : nullptr;
                 if (SHAPE == 1 && !NN27 && !PLANE && A.stage_doubles > 0) {   // bandwidth shape: voxel blocks staged through shared memory
                     extern __shared__ __align__(16) double stage_smem[];
                     icp_query_pass_staged(A, Pv, in, n, wbase, wstride, lane, stage_smem + (size_t)warp * STAGE_WARP_DOUBLES, acc, ncorr, ncand, nmiss);
@@ -704,9 +710,9 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
                     else if (A.map.cap <= 16) icp_query_pass_coop<2>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
                     else icp_query_pass_coop<3>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
                 } else if (SHAPE == 0) {                 // latency shape: eight lanes per query
-                    if (A.map.cap <= 8) icp_query_pass_grouped<NN27, PLANE, 1>(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
-                    else if (A.map.cap <= 16) icp_query_pass_grouped<NN27, PLANE, 2>(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
-                    else icp_query_pass_grouped<NN27, PLANE, 3>(A, Pv, in, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
+                    if (A.map.cap <= 8) icp_query_pass_grouped<NN27, PLANE, 1>(A, Pv, in, qi0, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
+                    else if (A.map.cap <= 16) icp_query_pass_grouped<NN27, PLANE, 2>(A, Pv, in, qi0, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
+                    else icp_query_pass_grouped<NN27, PLANE, 3>(A, Pv, in, qi0, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
                 } else {
                     icp_query_pass<NN27, PLANE>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
                 }
@@ -911,61 +917,6 @@ __device__ __forceinline__ void dsmem_store_f64(const double *local_smem, unsign
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
 }
 
-// Tukey bounds from the four order statistics, inlier flags and the order-preserving index list, by one CTA in its shared memory
-// (icp.cpp:103-121; same bounds and comparisons as iqr_grid_filter). Returns the keypoint count.
-__device__ __forceinline__ int cluster_iqr_compact(ClusterSmem &sm, const IcpArgs &A, int n0, bool write_out) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m = n0 / 2;
-    const double v0 = __ldcg(A.iqr_d2), v1 = __ldcg(A.iqr_d2 + 1), v2 = __ldcg(A.iqr_d2 + 2), v3 = __ldcg(A.iqr_d2 + 3);
-    const double q1 = (m % 2 == 0) ? (v0 + v1) / 2.0 : v1;
-    const double q3 = (m % 2 == 0) ? (v2 + v3) / 2.0 : v3;
-    const double iqr = q3 - q1;
-    const double low = q1 - 1.25 * iqr, high = q3 + 1.25 * iqr;   // icp.cpp:104-105
-    constexpr int PER = IQR_GRID_MAX / CL_THREADS;               // 8 consecutive candidates per thread
-    unsigned int f = 0;
-    int cnt = 0;
-#pragma unroll
-    for (int u = 0; u < PER; ++u) {
-        const int i = tid * PER + u;
-        const double d = i < n0 ? sm.sd2[i] : 0.0;
-        const bool in = i < n0 && d >= low && d <= high;         // icp.cpp:117
-        f |= (in ? 1u : 0u) << u;
-        cnt += in ? 1 : 0;
-    }
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
-    if (lane == 31) sm.ws[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        const int v = lane < CL_THREADS / 32 ? sm.ws[lane] : 0;
-        int wi = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += t; }
-        sm.ws[lane] = wi - v;
-        if (lane == 31) sm.total = wi;
-    }
-    __syncthreads();
-    int pos = sm.ws[warp] + incl - cnt;
-#pragma unroll
-    for (int u = 0; u < PER; ++u) {
-        if (f & (1u << u)) {
-            const int i = tid * PER + u;
-            sm.qidx[pos] = (unsigned short)i;
-            if (write_out) {
-                A.iqr_out[3 * (size_t)pos] = A.iqr_in[3 * (size_t)i];
-                A.iqr_out[3 * (size_t)pos + 1] = A.iqr_in[3 * (size_t)i + 1];
-                A.iqr_out[3 * (size_t)pos + 2] = A.iqr_in[3 * (size_t)i + 2];
-            }
-            ++pos;
-        }
-    }
-    if (write_out && tid == 0) *A.iqr_count = sm.total;
-    __syncthreads();
-    return sm.total;
-}
-
-
 template <int ROUNDS>   // candidate ranks per lane of a query pair: max_points_per_voxel <= 2 * ROUNDS
 static __global__ void __launch_bounds__(CL_THREADS, 1) k_frame_cluster(const IcpArgs A) {
     extern __shared__ __align__(16) unsigned char cl_raw[];
@@ -982,7 +933,7 @@ static __global__ void __launch_bounds__(CL_THREADS, 1) k_frame_cluster(const Ic
     if (small && n0 > 1) {
         iqr_grid_select<CL_THREADS>(sm.sd2, A.iqr_in, n0, A.iqr_d2);
         gs.sync();
-        if (loop_cta) n = cluster_iqr_compact(sm, A, n0, blockIdx.x == 0);
+        if (loop_cta) n = iqr_local_compact<CL_THREADS>(sm.ws, &sm.total, sm.sd2, A.iqr_in, n0, A.iqr_d2, sm.qidx, A.iqr_out, A.iqr_count, blockIdx.x == 0);
     } else if (small) {                        // 0 or 1 candidate: outlier::IQR keeps a single value (common.hpp:49-52)
         if (threadIdx.x == 0) {
             sm.qidx[0] = 0;
