@@ -1,5 +1,6 @@
 // frame_fusion.cuh -- what the odometry pipeline asks the persistent registration kernel to do around the ICP loop.
 #pragma once
+#include "common.cuh"
 namespace limu {
 struct FrameFusion {
     const double *iqr_in;      // src0 after the two downsampling stages (nullptr: no IQR prologue)
@@ -13,6 +14,7 @@ struct FrameFusion {
     unsigned long long upd_birth_base;
     double *twist_out;         // non-null: leave log(last_pose^-1 * new_pose) here for the NEXT scan's deskew (delta_pose, deskew.cpp:14)
     double last_pose[7];       // poses.back() before this scan
+    DevStatus *status;         // the frame kernel's status word (per odometry handle); nullptr = the context's
     int allow_cluster;         // LIMU_OPT_CLUSTER_LOOP: the cluster latency shape may be used (registration.cu, k_frame_cluster)
 };
 }  // namespace limu

@@ -58,7 +58,8 @@ struct limu_odom {
     int num_samples = 0;
     limu::Pose model_deviation = limu::pose_identity();
     // device buffers
-    limu::DevBuf raw, ts, frame, down, src0, src, work, world, partials, d2;
+    limu::DevBuf raw, ts, frame, down, src0, src, work, world, partials, d2, res;
+    int vox_word = 0;                       // which of its two status words the last k_voxelize of this handle reports into
     limu::VoxelizeScratch vx;
     limu::PreScratch pre;                   // limu_odom_register_msg: frame::Lidar::process_frame on the device
     int64_t nk_hint = 2048, nd_hint = 16384;   // keypoints / downsampled points of the previous scan (launch shapes; the kernels take any count)
@@ -173,18 +174,25 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     LIMU_TRY(o->world.reserve(nb, c->stream));
     const int rows = icp_partial_rows(c);
     LIMU_TRY(o->partials.reserve((size_t)2 * rows * 32 * 8 + 256, c->stream));   // 32 doubles per row covers both residual variants
-    // [0]=n_down [1]=n_src0 [2]=n_keypoints, [4..7] = the status word of THIS scan's k_voxelize (its own word, so that a speculative
-    // launch is never blamed on the scan before it)
-    int *cnt = reinterpret_cast<int *>(c->d_small.as<double>() + 32);
+    // Per-HANDLE result block in device memory (two handles of one context may interleave their scans, and a speculative launch of one
+    // must not land in the other's counts): 16 ints -- [0]=n_down [1]=n_src0 [2]=n_keypoints, [4..7] / [8..11] = the two status words
+    // k_voxelize alternates between (its own words, so that a speculative launch is never blamed on the scan before it), [12..15] = the
+    // frame kernel's status word -- then pose + loop statistics (13 doubles). ONE copy per scan.
+    if (!o->res.p) {
+        LIMU_TRY(o->res.reserve(32 * sizeof(double)));
+        LIMU_CUDA_TRY(cudaMemsetAsync(o->res.p, 0, o->res.bytes, c->stream));
+    }
+    int *cnt = o->res.as<int>();
     DevStatus *vox_status = reinterpret_cast<DevStatus *>(cnt + 4);
-    double *out13 = c->d_small.as<double>() + 40;
+    DevStatus *frame_status = reinterpret_cast<DevStatus *>(cnt + 12);
+    double *out13 = o->res.as<double>() + 8;
     const double v = o->cfg.voxel_size;
 
     // deskew_scan + voxelize's two downsampling stages (icp.cpp:36-47, :126-131): one cooperative launch
     if (!spec_hit) {
         LIMU_TRY(prof_begin(c, LIMU_STAGE_DOWNSAMPLE));
         LIMU_TRY(voxelize_device(c, o->vx, raw_dev, mode, stride, ts_dev, deskewed, twist, n, v, o->frame.as<double>(), down_mine.as<double>(), o->src0.as<double>(), cnt + 0,
-                                 nullptr, vox_status));
+                                 nullptr, vox_status, &o->vox_word));
         LIMU_TRY(prof_end(c, LIMU_STAGE_DOWNSAMPLE));
     }
     // host scalar glue (icp.cpp:66-71)
@@ -208,6 +216,7 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     const int next_deskew = (o->cfg.deskew && NP + 1 > 2) ? 1 : 0;   // the gate of icp.cpp:40-46 as the next scan will see it
     fuse.twist_out = nullptr;
     fuse.allow_cluster = o->cluster_loop ? 1 : 0;
+    fuse.status = frame_status;
     pose_store(last, fuse.last_pose);
     if (speculate && next_deskew) {
         LIMU_TRY(o->twist_next.reserve(6 * sizeof(double), c->stream));
@@ -221,8 +230,8 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
 
     // the one synchronisation of the scan
     double *h = static_cast<double *>(c->h_pinned) + 32;
-    // counts + k_voxelize status [32..39], pose + loop statistics [40..52] and the context's status word [53..54] in ONE copy
-    LIMU_CUDA_TRY(cudaMemcpyAsync(h, c->d_small.as<double>() + 32, (8 + 13 + 2) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    const int my_vox_word = o->vox_word;   // the status word of THIS scan's k_voxelize (a speculative launch below moves on to the other one)
+    LIMU_CUDA_TRY(cudaMemcpyAsync(h, o->res.p, (8 + 13) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     // device time of the speculative launch that prepared THIS scan (recorded one call ago into the event pair `spec_par`): read after this
     // scan's sync, when it is certainly complete; the launch made below uses the other pair
     const int acct = o->spec_timed ? o->spec_par : -1;
@@ -240,7 +249,7 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
         const int par = o->spec_par ^ 1;
         if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->spec_ev[par][0], c->stream));
         LIMU_TRY(voxelize_device(c, o->vx, next_ptr, 0, 0, nullptr, next_deskew, nullptr, next_n, v, o->frame.as<double>(), down_other.as<double>(),
-                                 o->src0.as<double>(), cnt + 0, next_deskew ? o->twist_next.as<double>() : nullptr, vox_status));
+                                 o->src0.as<double>(), cnt + 0, next_deskew ? o->twist_next.as<double>() : nullptr, vox_status, &o->vox_word));
         if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->spec_ev[par][1], c->stream)); o->spec_timed = true; o->spec_par = par; }
         LIMU_CUDA_TRY(cudaEventRecord(o->spec_launched, c->stream));
         o->spec_ptr = next_ptr; o->spec_n = next_n; o->spec_deskewed = next_deskew; o->spec_slot = next_slot;
@@ -294,12 +303,16 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
         stats->icp.mean_candidates = nk > 0 ? ho[10] / (double)nk : 0.0;
         stats->icp.miss_fraction = nk > 0 ? ho[11] / (double)nk : 0.0;
     }
-    {   // device status of this scan: its own k_voxelize word (counts area) and the context's word (frame kernel: insert)
+    {   // device status of this scan: its own k_voxelize word and the frame kernel's word (insert)
         DevStatus st, sv;
-        memcpy(&st, h + 21, sizeof st);
-        memcpy(&sv, hc + 4, sizeof sv);
+        memcpy(&st, hc + 12, sizeof st);
+        memcpy(&sv, hc + 4 + 4 * my_vox_word, sizeof sv);
+        if (st.key_range | st.table_full | st.pad[0]) LIMU_CUDA_TRY(cudaMemsetAsync(frame_status, 0, sizeof(DevStatus), c->stream));   // (the next frame kernel is launched after this)
         st.key_range |= sv.key_range; st.table_full |= sv.table_full;
-        LIMU_TRY(status_to_error(c, st));   // the frame IS registered (see above); the caller learns that points were left out
+        DevStatus none = {0, 0, {0, 0}};
+        (void)none;
+        if (st.key_range) { set_error("voxel index outside the packed key range (|index| >= 2^20) or NaN coordinate: the frame was registered without those points"); return LIMU_ERR_KEY_RANGE; }
+        if (st.table_full) { set_error("voxel hash table full"); return LIMU_ERR_MAP_FULL; }
     }
     return LIMU_OK;
 }
@@ -346,7 +359,7 @@ void limu_odom_destroy(limu_odom *o) {
     cudaStreamSynchronize(o->ctx->stream);
     limu_map_destroy(o->map);
     if (o->copy_stream) { cudaStreamSynchronize(o->copy_stream); cudaStreamDestroy(o->copy_stream); cudaEventDestroy(o->pf_done[0]); cudaEventDestroy(o->pf_done[1]); }
-    DevBuf *bufs[] = {&o->pf_buf[0], &o->pf_buf[1], &o->d2, &o->raw, &o->ts, &o->frame, &o->down, &o->src0, &o->src, &o->work, &o->world, &o->partials};
+    DevBuf *bufs[] = {&o->res, &o->pf_buf[0], &o->pf_buf[1], &o->d2, &o->raw, &o->ts, &o->frame, &o->down, &o->src0, &o->src, &o->work, &o->world, &o->partials};
     for (auto *b : bufs) b->release();
     o->vx.release();
     o->pre.release();

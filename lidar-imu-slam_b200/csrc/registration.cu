@@ -1223,6 +1223,7 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
         A.iqr_in = fuse->iqr_in; A.iqr_n = fuse->iqr_n; A.iqr_d2 = fuse->iqr_d2; A.iqr_out = fuse->iqr_out; A.iqr_count = fuse->iqr_count;
         A.upd_down = fuse->upd_down; A.upd_n = fuse->upd_n; A.upd_world = fuse->upd_world; A.upd_pslot = fuse->upd_pslot;
         A.upd_counters = m->counters.as<unsigned long long>(); A.upd_birth_base = fuse->upd_birth_base;
+        if (fuse->status) A.status = fuse->status;
         A.upd_capacity = (long long)m->capacity; A.upd_max_distance = m->max_distance;
         A.twist_out = fuse->twist_out;
         for (int k = 0; k < 7; ++k) A.last_pose[k] = fuse->last_pose[k];

@@ -3,9 +3,12 @@
 //
 // The stand-alone stages (ops.cu) cost 13 launches + 2 memsets per scan, each a few microseconds of work on 128k points;
 // here the phases are separated by grid barriers instead of kernel boundaries:
-//   P0 clear both scan-local tables            P3 ordered scatter of stage-1 winners -> down[], stage-2 claim
-//   P1 deskew/widen -> frame[], stage-1 claim  P4 stage-2 winner flags, per-tile counts
+//   P1 deskew/widen -> frame[], stage-1 claim  P4 stage-2 winner flags, per-tile counts (+ un-claim the stage-1 table)
 //   P2 stage-1 winner flags, per-tile counts   P5 ordered scatter of stage-2 winners -> src0[]
+//   P3 ordered scatter of stage-1 winners -> down[], stage-2 claim
+// The scan-local hash tables are left CLEAN instead of being cleared at the start (6 MB of stores and a grid barrier per scan): every
+// claimed slot is remembered per point, so the stage-1 table is un-claimed in P4 (nobody reads it after P3) and the stage-2 table of
+// this launch is un-claimed by the NEXT launch, which works on the other of two stage-2 tables.
 // "First point per voxel wins, output in first-occurrence order" (icp.cpp:13-27 + the oracle's ordered map) becomes:
 // atomicMin of the input index per voxel, then a stable compaction over 256-point tiles.
 #include <algorithm>
@@ -30,13 +33,16 @@ struct VoxelizeArgs {
     double *frame, *down, *src0;
     unsigned long long *keys1, *keys2;
     unsigned int *min1, *min2, *pslot1, *pslot2;
+    unsigned long long *keys2_prev;   // the stage-2 table (and claimed slots) of the previous launch: un-claimed here
+    unsigned int *min2_prev, *pslot2_prev;
+    int *nd_prev, *nd_this;           // how many stage-2 claims the previous launch made / this launch makes
     unsigned int mask1, mask2;
     int shift1, shift2;
     int *tile1, *tile2;
     int *counts;                // [0] n_down, [1] n_src0
     unsigned int *barrier;      // [0] grid barrier, [1] exit counter; zero at rest (the last CTA out re-arms them, no memset per launch)
     DevStatus *st;
-    int clear_status;           // 1: `st` is this launch's own status word (odometry.cu) and starts out clean
+    DevStatus *st_next;         // non-null: the status word of the NEXT launch of this pipeline (two words alternate); zeroed late in this launch
 };
 
 __device__ __forceinline__ unsigned int claim_min(unsigned long long *keys, unsigned int *minidx, unsigned int mask, int shift, const V3 &p, double vs,
@@ -82,14 +88,14 @@ static __global__ void __launch_bounds__(VX_BLOCK, 4) k_voxelize(const VoxelizeA
     const int64_t n = A.n;
     const int64_t gtid = (int64_t)blockIdx.x * VX_BLOCK + threadIdx.x, gthreads = (int64_t)gridDim.x * VX_BLOCK;
     const int ntiles = (int)((n + VX_BLOCK - 1) / VX_BLOCK);
-    // P0: clear the scan-local tables (all-ones = empty key / no index)
+    // un-claim what the previous launch left in ITS stage-2 table (this launch uses the other one): no barrier needed
     {
-        const int64_t w1 = (int64_t)A.mask1 + 1, w2 = (int64_t)A.mask2 + 1;
-        for (int64_t i = gtid; i < w1; i += gthreads) { A.keys1[i] = KEY_EMPTY; A.min1[i] = PEND_NONE; }
-        for (int64_t i = gtid; i < w2; i += gthreads) { A.keys2[i] = KEY_EMPTY; A.min2[i] = PEND_NONE; }
-        if (gtid == 0 && A.clear_status) *A.st = DevStatus{0, 0, {0, 0}};
+        const int ndp = __ldcg(A.nd_prev);
+        for (int64_t j = gtid; j < ndp; j += gthreads) {
+            const unsigned int sl = __ldcg(A.pslot2_prev + j);
+            if (sl != PEND_NONE) { A.keys2_prev[sl] = KEY_EMPTY; A.min2_prev[sl] = PEND_NONE; }
+        }
     }
-    gs.sync();
     // P1: frame[i] = deskewed / widened point (icp.cpp:36-47, deskew.cpp:18-26); stage-1 claim at 0.5 v
     {
         double tw[6];
@@ -151,11 +157,17 @@ static __global__ void __launch_bounds__(VX_BLOCK, 4) k_voxelize(const VoxelizeA
             A.down[3 * (size_t)j] = p.x; A.down[3 * (size_t)j + 1] = p.y; A.down[3 * (size_t)j + 2] = p.z;
             A.pslot2[j] = claim_min(A.keys2, A.min2, A.mask2, A.shift2, p, A.vs2, (unsigned int)j, A.st);
         }
-        if (tile == ntiles - 1 && threadIdx.x == 0) A.counts[0] = base + total;
+        if (tile == ntiles - 1 && threadIdx.x == 0) { A.counts[0] = base + total; *A.nd_this = base + total; }
         __syncthreads();
     }
-    if (ntiles == 0 && gtid == 0) A.counts[0] = 0;
+    if (ntiles == 0 && gtid == 0) { A.counts[0] = 0; *A.nd_this = 0; }
     gs.sync();
+    if (gtid == 0 && A.st_next) *A.st_next = DevStatus{0, 0, {0, 0}};   // (its last reader, the result copy of the previous scan, is long done)
+    // the stage-1 table was last read in P3: un-claim it for the next launch
+    for (int64_t i = gtid; i < n; i += gthreads) {
+        const unsigned int sl = A.pslot1[i];
+        if (sl != PEND_NONE) { A.keys1[sl] = KEY_EMPTY; A.min1[sl] = PEND_NONE; }
+    }
     // P4 / P5: the same flag -> count -> scatter over down[] for stage 2
     const int nd = __ldcg(A.counts);
     const int ntiles2 = (nd + VX_BLOCK - 1) / VX_BLOCK;
@@ -196,10 +208,11 @@ static int64_t pow2_slots(int64_t n) { int64_t p = 1024; while (p < 2 * n) p <<=
 
 // Enqueue the fused kernel. raw/ts/twist are device pointers; outputs: frame (n x 3), down, src0, counts[0..1].
 int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int mode, int stride, const double *ts_dev, int deskew, const double *twist_host,
-                    int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev, const double *twist_dev, DevStatus *own_status) {
+                    int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev, const double *twist_dev, DevStatus *own_status, int *status_used) {
     if (n <= 0) {
         LIMU_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int), c->stream));
-        if (own_status) LIMU_CUDA_TRY(cudaMemsetAsync(own_status, 0, sizeof(DevStatus), c->stream));
+        if (own_status) LIMU_CUDA_TRY(cudaMemsetAsync(own_status, 0, 2 * sizeof(DevStatus), c->stream));
+        if (status_used) *status_used = 0;
         return LIMU_OK;
     }
     if (g_vx_blocks_per_sm == 0) {
@@ -211,30 +224,59 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     int lg = 0;
     while ((int64_t(1) << lg) < C1) ++lg;
     const int ntiles = div_up(n, VX_BLOCK);
-    LIMU_TRY(sc.table.reserve((size_t)(C1 + C2) * 12, c->stream));
-    LIMU_TRY(sc.pslot.reserve((size_t)n * 8, c->stream));
-    {   // [16 ints: barrier words | tile counts]; a fresh allocation is zeroed once, afterwards the kernel keeps the barrier words at zero
-        const void *before = sc.tiles.p;
+    {   // three tables [u64 key x cap | u32 min-index x cap] at offsets fixed by the ALLOCATED capacity (claimed slots are remembered as indices), all-ones
+        // = clean at rest. Whenever one of the buffers is re-allocated the memory of what the previous launch claimed is gone: start over clean.
+        bool reset = false;
+        if (C1 > sc.cap_slots) {
+            int64_t cap = sc.cap_slots ? sc.cap_slots : 1024;
+            while (cap < C1) cap <<= 1;
+            LIMU_TRY(sc.table.reserve((size_t)cap * 12 * 3, c->stream));
+            sc.cap_slots = cap;
+            reset = true;
+        }
+        const void *before = sc.pslot.p;
+        LIMU_TRY(sc.pslot.reserve((size_t)n * 4 * 3, c->stream));   // pslot1 | pslot2 of the two parities
+        if (sc.pslot.p != before) reset = true;
+        sc.pslot_n = (int64_t)(sc.pslot.bytes / 12);
+        // [16 ints: barrier words 0-1, stage-2 claim counts of the two parities 4-5 | tile counts]; the kernel keeps the barrier words at zero
+        before = sc.tiles.p;
         LIMU_TRY(sc.tiles.reserve((size_t)ntiles * 8 + 128, c->stream));
-        if (sc.tiles.p != before) LIMU_CUDA_TRY(cudaMemsetAsync(sc.tiles.p, 0, sc.tiles.bytes, c->stream));
+        if (sc.tiles.p != before) reset = true;
+        if (reset) {
+            LIMU_CUDA_TRY(cudaMemsetAsync(sc.table.p, 0xFF, (size_t)sc.cap_slots * 12 * 3, c->stream));
+            LIMU_CUDA_TRY(cudaMemsetAsync(sc.tiles.p, 0, sc.tiles.bytes, c->stream));
+        }
     }
+    const int par = sc.parity;
+    sc.parity ^= 1;
     VoxelizeArgs A;
     A.raw = raw_dev; A.ts = ts_dev; A.mode = mode; A.stride = stride; A.deskew = deskew; A.n = n;
     for (int k = 0; k < 6; ++k) A.twist[k] = (deskew && twist_host) ? twist_host[k] : 0.0;
     A.twist_dev = deskew ? twist_dev : nullptr;
     A.vs1 = v * 0.5; A.vs2 = v * 1.5;
     A.frame = frame_dev; A.down = down_dev; A.src0 = src0_dev;
-    A.keys1 = sc.table.as<unsigned long long>();
-    A.keys2 = A.keys1 + C1;
-    A.min1 = reinterpret_cast<unsigned int *>(A.keys2 + C2);
-    A.min2 = A.min1 + C1;
+    {
+        unsigned char *base = sc.table.as<unsigned char>();
+        const size_t tb = (size_t)sc.cap_slots * 12;   // bytes per table
+        auto keys_of = [&](int t) { return reinterpret_cast<unsigned long long *>(base + tb * t); };
+        auto min_of = [&](int t) { return reinterpret_cast<unsigned int *>(base + tb * t + (size_t)sc.cap_slots * 8); };
+        A.keys1 = keys_of(0); A.min1 = min_of(0);
+        A.keys2 = keys_of(1 + par); A.min2 = min_of(1 + par);
+        A.keys2_prev = keys_of(1 + (par ^ 1)); A.min2_prev = min_of(1 + (par ^ 1));
+    }
     A.mask1 = (unsigned int)(C1 - 1); A.mask2 = (unsigned int)(C2 - 1); A.shift1 = A.shift2 = 64 - lg;
-    A.pslot1 = sc.pslot.as<unsigned int>(); A.pslot2 = A.pslot1 + n;
+    A.pslot1 = sc.pslot.as<unsigned int>();
+    A.pslot2 = A.pslot1 + sc.pslot_n * (1 + par);
+    A.pslot2_prev = A.pslot1 + sc.pslot_n * (1 + (par ^ 1));
     A.barrier = sc.tiles.as<unsigned int>();
+    A.nd_this = sc.tiles.as<int>() + 4 + par;
+    A.nd_prev = sc.tiles.as<int>() + 4 + (par ^ 1);
     A.tile1 = sc.tiles.as<int>() + 16; A.tile2 = A.tile1 + ntiles;
     A.counts = counts_dev;
-    A.st = own_status ? own_status : c->d_status;
-    A.clear_status = own_status ? 1 : 0;
+    // own_status: two DevStatus words; this launch uses word `par`, the next launch of this scratch the other one
+    A.st = own_status ? own_status + par : c->d_status;
+    A.st_next = own_status ? own_status + (par ^ 1) : nullptr;
+    if (status_used) *status_used = par;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->sm_count * g_vx_blocks_per_sm);
     void *args[] = {&A};
     LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize, dim3(grid), dim3(VX_BLOCK), args, 0, c->stream));
