@@ -116,19 +116,27 @@ __device__ __forceinline__ void iqr_grid_select(double *sd2 /* shared, IQR_GRID_
     const int r0 = lo, r1 = hi, r2 = lo + u0, r3 = hi + u0;
     const int lane = threadIdx.x & 31;
     const int gwarp = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5), nwarps = (nblocks > 0 ? nblocks : (int)gridDim.x) * (BLOCK / 32);
-    for (int i = gwarp; i < n; i += nwarps) {   // warp-uniform trip count
-        const double d = sd2[i];
-        int c = 0;
+    // A warp ranks FOUR candidates at a time: one shared-memory load per comparison partner feeds four comparisons (the one-candidate
+    // loop spent ~1.6 us per candidate on the latency of its 81 dependent load/compare rounds).
+    for (int i0 = gwarp * 4; i0 < n; i0 += nwarps * 4) {   // warp-uniform trip count
+        double d[4];
+        int c[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { d[k] = sd2[i0 + k < n ? i0 + k : n - 1]; c[k] = 0; }
         for (int j = lane; j < n; j += 32) {
             const double e = sd2[j];
-            c += (e < d || (e == d && j < i)) ? 1 : 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) c[k] += (e < d[k] || (e == d[k] && j < i0 + k)) ? 1 : 0;
         }
-        c = __reduce_add_sync(0xFFFFFFFFu, c);
-        if (lane == 0) {
-            if (c == r0) sel[0] = d;
-            if (c == r1) sel[1] = d;
-            if (c == r2) sel[2] = d;
-            if (c == r3) sel[3] = d;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = __reduce_add_sync(0xFFFFFFFFu, c[k]);
+            if (lane == 0 && i0 + k < n) {
+                if (r == r0) sel[0] = d[k];
+                if (r == r1) sel[1] = d[k];
+                if (r == r2) sel[2] = d[k];
+                if (r == r3) sel[3] = d[k];
+            }
         }
     }
 }
@@ -177,10 +185,12 @@ __device__ __forceinline__ int iqr_local_compact(int *ws /* shared, 32 */, int *
     const double iqr = q3 - q1;
     const double low = q1 - 1.25 * iqr, high = q3 + 1.25 * iqr;   // icp.cpp:104-105
     constexpr int PER = IQR_GRID_MAX / BLOCK;
+    static_assert((PER & (PER - 1)) == 0, "candidates per thread must be a power of two");
     unsigned int f = 0;
     int cnt = 0;
 #pragma unroll
-    for (int u = 0; u < PER; ++u) {
+    for (int v = 0; v < PER; ++v) {
+        const int u = (v + tid) & (PER - 1);                       // rotated visiting order: the lanes of a warp read different banks
         const int i = tid * PER + u;
         const double d = i < n0 ? sd2[i] : 0.0;
         const bool in = i < n0 && d >= low && d <= high;          // icp.cpp:117

@@ -575,8 +575,9 @@ __device__ __forceinline__ void icp_query_pass_staged(const IcpArgs &A, const vo
 __device__ unsigned long long g_frame_marks[16];
 #define FT_MARK(k) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && ((k) >= 8 || threadIdx.x == 0)) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_frame_marks[k] = _t; } } while (0)
 // SM cycle counter of CTA 0 (one SM: the marks of different warps are comparable): any lane 0 / lane 0 of warp w
-#define CT_MARK(k) do { if (blockIdx.x == 0 && lane == 0) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
-#define CW_MARK(k, w) do { if (blockIdx.x == 0 && warp == (w) && lane == 0) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
+// (stamped in iteration 2 of the Gauss-Newton loop; marks 13 / 14 = the tail of iteration 2, which runs during loop round 3)
+#define CT_MARK(k) do { if (blockIdx.x == 0 && lane == 0 && j == (((k) == 13 || (k) == 14) ? 3 : 2)) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
+#define CW_MARK(k, w) do { if (blockIdx.x == 0 && warp == (w) && lane == 0 && j == (((k) == 13 || (k) == 14) ? 3 : 2)) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
 #else
 #define FT_MARK(k) do {} while (0)
 #define CW_MARK(k, w) do {} while (0)
@@ -763,22 +764,22 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
         }
         gs_icp.sync();
         CW_MARK(12, 0);
-        // fold the per-CTA rows in a fixed order: lane = column, warp g sums rows g, g+8, ... (four independent
-        // accumulators keep the L2 loads in flight), then one thread per column adds the 8 warp partials.
+        // fold the per-CTA rows in a fixed order: lane = column, warp g sums rows g, g+8, ...; up to 16 rows per warp are requested at
+        // once (ONE L2 round trip for the latency shape's <= 128 rows), then one thread per column adds the 8 warp partials.
         {
-            double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-            if (lane < NSX) {
-                const int G = ICP_BLOCK / 32;
-                int b = warp;
-                for (; b + 3 * G < A.icp_blocks; b += 4 * G) {
-                    v0 += __ldcg(rows + (size_t)b * NSX + lane);
-                    v1 += __ldcg(rows + (size_t)(b + G) * NSX + lane);
-                    v2 += __ldcg(rows + (size_t)(b + 2 * G) * NSX + lane);
-                    v3 += __ldcg(rows + (size_t)(b + 3 * G) * NSX + lane);
+            double acc = 0.0;
+            constexpr int G = ICP_BLOCK / 32;
+            for (int b0 = warp; b0 < A.icp_blocks; b0 += 16 * G) {   // CTA-uniform trip count
+                double v[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int b = b0 + k * G;
+                    v[k] = (lane < NSX && b < A.icp_blocks) ? __ldcg(rows + (size_t)b * NSX + lane) : 0.0;
                 }
-                for (; b < A.icp_blocks; b += G) v0 += __ldcg(rows + (size_t)b * NSX + lane);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) acc += v[k];
             }
-            red[warp * 32 + lane] = (v0 + v1) + (v2 + v3);
+            red[warp * 32 + lane] = acc;
             __syncthreads();
             if (threadIdx.x < NSX) {
                 double v = 0.0;

@@ -33,8 +33,9 @@ print({n: round(float(v), 2) for n, v in zip(names, r.mean(axis=0))}, "total_us"
       "icp_us_per_iter", round(float(r[:, 1].mean() / np.mean(iters)), 2))
 cyc = lambda a, b: int(marks[b] - marks[a])
 if os.environ.get("LIMU_CLUSTER_LOOP", "0") not in ("", "0"):
-    print("cluster shape, last iteration of the last scan (SM cycles of CTA 0): row reduce + DSMEM push + cluster barrier", cyc(6, 7), "fold", cyc(7, 8), "ldlt", cyc(8, 9), "exp", cyc(9, 10),
+    print("cluster shape, iteration 2 of the last scan (SM cycles of CTA 0): row reduce + DSMEM push + cluster barrier", cyc(6, 7), "fold", cyc(7, 8), "ldlt", cyc(8, 9), "exp", cyc(9, 10),
           "| pass of warp 1", cyc(11, 12), "tail of the solver warp", cyc(13, 14))
 else:
-    print("classic shape, last full iteration of the last scan (SM cycles of CTA 0, 1965 MHz): pass of warp 0", cyc(6, 7), "| S1 -> grid barrier done", cyc(11, 12), "| fold", cyc(12, 8),
-          "| ldlt", cyc(8, 9), "| exp", cyc(9, 10), "| S2", cyc(10, 15), "| tail of the solver warp (overlaps the next pass) ends", cyc(15, 14), "cycles after S2")
+    print("classic shape, iteration 2 of the last scan (SM cycles of CTA 0, 1965 MHz): pass of warp 0", cyc(6, 7), "| pass end -> S1", cyc(7, 11), "| CTA row + grid barrier", cyc(11, 12),
+          "| fold", cyc(12, 8), "| ldlt", cyc(8, 9), "| exp", cyc(9, 10), "| -> S2", cyc(10, 15), "| whole round (pass start -> S2)", cyc(6, 15),
+          "| tail of the solver warp ends", cyc(15, 14), "cycles after S2")
