@@ -142,7 +142,7 @@ void limu_ctx_destroy(limu_ctx *c) {
     limu_comm_destroy(c);
     release_ctx_scratch(c);
     release_pre_scratch(c);
-    limu::DevBuf *bufs[] = {&c->in0, &c->in1, &c->out0, &c->out1, &c->out2, &c->tmp0, &c->tmp1, &c->tmp2, &c->tmp3, &c->tmp4, &c->tmp5, &c->d_small};
+    limu::DevBuf *bufs[] = {&c->in0, &c->in1, &c->out0, &c->out1, &c->out2, &c->tmp0, &c->tmp1, &c->tmp2, &c->tmp3, &c->tmp4, &c->tmp5, &c->ll_rows, &c->d_small};
     for (auto *b : bufs) b->release();
     for (int s = 0; s < LIMU_NUM_STAGES; ++s) for (int k = 0; k < 2; ++k) if (c->ev[s][k]) cudaEventDestroy(c->ev[s][k]);
     cudaFreeHost(c->h_status);

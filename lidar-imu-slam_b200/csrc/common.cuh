@@ -91,10 +91,12 @@ struct limu_ctx {
     limu::DevStatus *h_status = nullptr;   // pinned host mirror
     // scratch pools reused by the stateless entry points and the pipeline
     limu::DevBuf in0, in1, out0, out1, out2, tmp0, tmp1, tmp2, tmp3, tmp4, tmp5;
+    limu::DevBuf ll_rows;      // per-CTA rows of the stand-alone ICP entry points (stamped words, see registration.cu)
     void *h_pinned = nullptr;  // small pinned staging area for scalars / poses / counts
     size_t h_pinned_bytes = 0;
     limu::DevBuf d_small;      // small device staging area (poses, counts, partial sums)
     limu_comm *comm = nullptr;
+    unsigned int ll_seq = 1;   // stamp counter of the row exchange in the registration kernels (31 bits, advances with every launch)
     // optional per-stage event timing (limu_ctx_set_profiling)
     bool profiling = false;
     cudaEvent_t ev[LIMU_NUM_STAGES][2] = {};

@@ -173,7 +173,11 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     LIMU_TRY(o->work.reserve(nb, c->stream));
     LIMU_TRY(o->world.reserve(nb, c->stream));
     const int rows = icp_partial_rows(c);
-    LIMU_TRY(o->partials.reserve((size_t)2 * rows * 32 * 8 + 256, c->stream));   // 32 doubles per row covers both residual variants
+    {   // per-CTA rows of the Gauss-Newton loop: 32 (value, stamp) word pairs per row cover both residual variants; never anything that looks like a stamp in a fresh buffer
+        const void *before = o->partials.p;
+        LIMU_TRY(o->partials.reserve((size_t)2 * rows * 32 * 16 + 256, c->stream));
+        if (o->partials.p != before) LIMU_CUDA_TRY(cudaMemsetAsync(o->partials.p, 0, o->partials.bytes, c->stream));
+    }
     // Per-HANDLE result block in device memory (two handles of one context may interleave their scans, and a speculative launch of one
     // must not land in the other's counts): 16 ints -- [0]=n_down [1]=n_src0 [2]=n_keypoints, [4..7] / [8..11] = the two status words
     // k_voxelize alternates between (its own words, so that a speculative launch is never blamed on the scan before it), [12..15] = the

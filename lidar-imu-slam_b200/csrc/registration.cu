@@ -48,7 +48,8 @@ struct IcpArgs {
     double th;                  // kernel (registration.cpp:57-58)
     int max_iter;
     double eps;
-    double *partials;           // [2][gridDim][NS]
+    double *partials;           // [2][icp_blocks][NSX] (value, stamp) word pairs: the per-CTA rows of an iteration, self-validating (see ll_* below)
+    unsigned int ll_stamp_base; // stamps of this launch are 0x80000000 | ((ll_stamp_base + iteration) & 0x7FFFFFFF): never 0, never reused soon
     unsigned int *barrier;      // zeroed before launch
     double *out;                // [0..6] pose, [7] iterations, [8] converged, [9] ncorr, [10] ncand, [11] nmiss, [12] n
     int grouped;                // 1: eight lanes per query (latency shape: a few thousand keypoints)
@@ -572,14 +573,16 @@ __device__ __forceinline__ void icp_query_pass_staged(const IcpArgs &A, const vo
 
 #ifdef LIMU_ICP_PHASE_TIMING
 // developer build only (tools/icp_phase_timing.py, tools/frame_phase_timing.py): %globaltimer stamps of CTA 0 / thread 0
-__device__ unsigned long long g_frame_marks[16];
+__device__ unsigned long long g_frame_marks[24];
 #define FT_MARK(k) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && ((k) >= 8 || threadIdx.x == 0)) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_frame_marks[k] = _t; } } while (0)
 // SM cycle counter of CTA 0 (one SM: the marks of different warps are comparable): any lane 0 / lane 0 of warp w
+#define IQ_MARK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
 // (stamped in iteration 2 of the Gauss-Newton loop; marks 13 / 14 = the tail of iteration 2, which runs during loop round 3)
 #define CT_MARK(k) do { if (blockIdx.x == 0 && lane == 0 && j == (((k) == 13 || (k) == 14) ? 3 : 2)) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
 #define CW_MARK(k, w) do { if (blockIdx.x == 0 && warp == (w) && lane == 0 && j == (((k) == 13 || (k) == 14) ? 3 : 2)) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
 #else
 #define FT_MARK(k) do {} while (0)
+#define IQ_MARK(k) do {} while (0)
 #define CW_MARK(k, w) do {} while (0)
 #define CT_MARK(k) do {} while (0)
 #endif
@@ -640,6 +643,24 @@ static __device__ __noinline__ void solve_normal_equations(const double *S, doub
     for (int k = 0; k < 6; ++k) x_out[k] = x[k];
 }
 
+// ---- row exchange without a barrier ("LL" protocol) ---------------------------------------------------------------------------------------
+// Every CTA of the loop needs every CTA's row of sums. A global-memory barrier + fold cost ~3.5 us per iteration (atomic arrive, release
+// fence, acquire polling, then the loads). Instead each 8-byte word a CTA publishes carries its own validity: a double travels as two
+// words {low 32 bits | stamp}, {high 32 bits | stamp} (aligned 8-byte accesses are single-copy atomic), written with one 16-byte store;
+// readers request all the rows they fold at once and simply re-request the words whose stamp is not this iteration's yet. No fence, no
+// atomic, no separate arrival: store -> L2 -> load. Two buffers alternate by iteration parity (a CTA can only be one iteration ahead
+// of the slowest: it needs everybody's row j+1 before it can write row j+2).
+__device__ __forceinline__ void ll_store(unsigned long long *slot /* 16-byte aligned pair */, double v, unsigned int stamp) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v), st = (unsigned long long)stamp << 32;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"((bits & 0xFFFFFFFFull) | st), "l"((bits >> 32) | st) : "memory");
+}
+__device__ __forceinline__ bool ll_load(const unsigned long long *slot, unsigned int stamp, double &v) {
+    unsigned long long lo, hi;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(slot) : "memory");
+    v = __longlong_as_double((long long)((lo & 0xFFFFFFFFull) | (hi << 32)));
+    return (unsigned int)(lo >> 32) == stamp && (unsigned int)(hi >> 32) == stamp;
+}
+
 // SHAPE 0 = latency build (a few thousand keypoints: one CTA per SM at most, so the compiler may use up to 255 registers and the serial
 // Gauss-Newton solve stays out of local memory); SHAPE 1 = bandwidth build for kernel mode (millions of queries against a map far larger
 // than L2): LIMU_BW_CTAS CTAs per SM, voxel blocks staged through shared memory (icp_query_pass_staged), the solve out of line.
@@ -669,9 +690,13 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
         const int n0 = __ldcg(A.iqr_n);
         if (SHAPE == 0 && n0 > 1 && n0 <= IQR_GRID_MAX) {   // uniform across the grid
             if (icp_member) {
+                IQ_MARK(16);
                 iqr_grid_select<ICP_BLOCK>(iqr_sd2, A.iqr_in, n0, A.iqr_d2, A.icp_blocks);
+                IQ_MARK(17);
                 gs_icp.sync();
+                IQ_MARK(18);
                 n_keypoints = iqr_local_compact<ICP_BLOCK>(iqr_sm.ws, &iqr_sm.total, iqr_sd2, A.iqr_in, n0, A.iqr_d2, qidx_s, A.iqr_out, A.iqr_count, blockIdx.x == 0);
+                IQ_MARK(19);
             }
         } else {
             if (blockIdx.x == 0) iqr_block<ICP_BLOCK>(iqr_sm, A.iqr_in, *A.iqr_n, A.iqr_d2, A.iqr_out, A.iqr_count, nullptr);
@@ -754,27 +779,40 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
         CW_MARK(11, 0);
         if (j > 0 && done) { converged = 1; break; }   // (the pass just made belongs to an iteration that does not exist)
         if (no_more) break;
-        double *rows = A.partials + (size_t)(j & 1) * A.icp_blocks * NSX;
-        if (threadIdx.x < NSX) {   // CTA row, fixed order over the query warps
+        const unsigned int stamp = 0x80000000u | ((A.ll_stamp_base + (unsigned int)j) & 0x7FFFFFFFu);
+        unsigned long long *rows = reinterpret_cast<unsigned long long *>(A.partials) + (size_t)(j & 1) * A.icp_blocks * (2 * NSX);
+        if (threadIdx.x < NSX) {   // CTA row, fixed order over the query warps; published word by word with its stamp
             const int src_lane = PLANE ? (int)threadIdx.x : (threadIdx.x < 16 ? 2 * (int)threadIdx.x : 2 * ((int)threadIdx.x - 16) + 1);
             double v = 0.0;
 #pragma unroll
             for (int w = 0; w < QW; ++w) v += red[w * 32 + src_lane];
-            rows[(size_t)blockIdx.x * NSX + threadIdx.x] = v;
+            ll_store(rows + ((size_t)blockIdx.x * NSX + threadIdx.x) * 2, v, stamp);
         }
-        gs_icp.sync();
+        __syncthreads();           // (red is reused below)
         CW_MARK(12, 0);
-        // fold the per-CTA rows in a fixed order: lane = column, warp g sums rows g, g+8, ...; up to 16 rows per warp are requested at
-        // once (ONE L2 round trip for the latency shape's <= 128 rows), then one thread per column adds the 8 warp partials.
+        // fold the rows in a fixed order: lane = column, warp g sums rows g, g+8, ...; up to 16 rows per warp are requested at once and
+        // re-requested until their stamp says they are this iteration's, then one thread per column adds the 8 warp partials.
         {
             double acc = 0.0;
             constexpr int G = ICP_BLOCK / 32;
             for (int b0 = warp; b0 < A.icp_blocks; b0 += 16 * G) {   // CTA-uniform trip count
                 double v[16];
+                unsigned int pending = 0u;
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
-                    const int b = b0 + k * G;
-                    v[k] = (lane < NSX && b < A.icp_blocks) ? __ldcg(rows + (size_t)b * NSX + lane) : 0.0;
+                    v[k] = 0.0;
+                    if (lane < NSX && b0 + k * G < A.icp_blocks) pending |= 1u << k;
+                }
+                unsigned int spins = 0u;
+                while (pending) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        if (pending & (1u << k)) {
+                            double x;
+                            if (ll_load(rows + ((size_t)(b0 + k * G) * NSX + lane) * 2, stamp, x)) { v[k] = x; pending &= ~(1u << k); }
+                        }
+                    }
+                    if (++spins > (1u << 24)) __trap();   // a CTA of the loop never published its row: fail loudly instead of hanging the device
                 }
 #pragma unroll
                 for (int k = 0; k < 16; ++k) acc += v[k];
@@ -1203,6 +1241,8 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
     for (int k = 0; k < 7; ++k) A.init_pose[k] = init_pose_host[k];
     A.tau_sq = tau * tau; A.th = th; A.max_iter = max_iter; A.eps = eps;
     A.partials = partials_dev; A.out = out13_dev;
+    A.ll_stamp_base = c->ll_seq;
+    c->ll_seq = (c->ll_seq + (unsigned int)std::max(max_iter, 0) + 2u) & 0x7FFFFFFFu;
     // grid barrier + exit counter live in the context's zero-initialised small area; the last CTA out re-arms them
     A.barrier = reinterpret_cast<unsigned int *>(c->d_small.as<double>() + 56);
     A.exit_count = A.barrier + 1;
@@ -1252,10 +1292,10 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
 int icp_partial_rows(limu_ctx *c) { return c->sm_count * 4; }   // >= the largest grid of any shape
 
 #ifdef LIMU_ICP_PHASE_TIMING
-extern "C" int limu_debug_frame_marks(double out[16]) {
-    unsigned long long h[16];
+extern "C" int limu_debug_frame_marks(double out[24]) {
+    unsigned long long h[24];
     if (cudaMemcpyFromSymbol(h, g_frame_marks, sizeof h) != cudaSuccess) return -1;
-    for (int k = 0; k < 16; ++k) out[k] = (double)h[k];
+    for (int k = 0; k < 24; ++k) out[k] = (double)h[k];
     return 0;
 }
 #endif
@@ -1362,11 +1402,15 @@ static int icp_common(limu_map *m, const double *points_dev, int64_t n, const do
     limu_ctx *c = m->ctx;
     const int rows = icp_partial_rows(c);
     LIMU_TRY(c->tmp4.reserve((size_t)std::max<int64_t>(n, 1) * 24, c->stream));                 // working cloud
-    LIMU_TRY(c->tmp5.reserve((size_t)2 * rows * NS_MAX * 8 + 256, c->stream));                 // partial rows
+    {   // partial rows: (value, stamp) word pairs; a fresh allocation must not hold anything that looks like a stamp
+        const void *before = c->ll_rows.p;
+        LIMU_TRY(c->ll_rows.reserve((size_t)2 * rows * NS_MAX * 16 + 256, c->stream));
+        if (c->ll_rows.p != before) LIMU_CUDA_TRY(cudaMemsetAsync(c->ll_rows.p, 0, c->ll_rows.bytes, c->stream));
+    }
     const bool tr = est_trace || ncorr_trace || hg_trace;
     const size_t it = (size_t)std::max(max_iter, 1);
     if (tr) LIMU_TRY(c->tmp3.reserve(it * (7 + 1 + 42) * 8, c->stream));
-    double *partials = c->tmp5.as<double>();
+    double *partials = c->ll_rows.as<double>();
     double *out13 = c->d_small.as<double>() + 16;
     double *d_est = tr ? c->tmp3.as<double>() : nullptr;
     long long *d_nc = tr ? reinterpret_cast<long long *>(d_est + it * 7) : nullptr;

@@ -19,7 +19,7 @@ K = 40
 traj = synth.loop_trajectory(K + 1, radius=30.0, step=1.0)
 scans = [synth.pad_scan(synth.cast_scan(scene, traj[i], traj[i + 1], seed=42 * 100003 + i, device="cuda"), 128000, seed=i) for i in range(K)]
 odo = ctx.KissICP(voxel_size=1.0, cap=10, deskew=True, icp_max_iteration=500)
-marks = np.zeros(16)
+marks = np.zeros(24)
 rows, iters = [], []
 for i, s in enumerate(scans):
     odo.register_frame(s, want_clouds=False)
@@ -39,3 +39,4 @@ else:
     print("classic shape, iteration 2 of the last scan (SM cycles of CTA 0, 1965 MHz): pass of warp 0", cyc(6, 7), "| pass end -> S1", cyc(7, 11), "| CTA row + grid barrier", cyc(11, 12),
           "| fold", cyc(12, 8), "| ldlt", cyc(8, 9), "| exp", cyc(9, 10), "| -> S2", cyc(10, 15), "| whole round (pass start -> S2)", cyc(6, 15),
           "| tail of the solver warp ends", cyc(15, 14), "cycles after S2")
+print("IQR phase of the last scan (SM cycles of CTA 0): squared ranges + ranking", cyc(16, 17), "| barrier of the loop CTAs", cyc(17, 18), "| local compaction (+ keypoints written out)", cyc(18, 19))
