@@ -172,11 +172,10 @@ __device__ __forceinline__ void iqr_grid_filter(IqrSmem &sm, const double *sd2, 
 // Tukey bounds from the four order statistics, inlier flags and the order-preserving INDEX list, by one CTA in its own shared memory in a
 // single pass (IQR_GRID_MAX / BLOCK consecutive candidates per thread, one block scan): every CTA that runs the Gauss-Newton loop derives
 // the keypoint list itself, so nobody waits for CTA 0 to compact it (icp.cpp:103-121; same bounds and comparisons as iqr_grid_filter).
-// write_out: also store the keypoints and their count to global memory (what the host reads back). Returns the keypoint count.
+// Returns the keypoint count.
 template <int BLOCK>
-__device__ __forceinline__ int iqr_local_compact(int *ws /* shared, 32 */, int *total /* shared */, const double *sd2, const double *__restrict__ xyz, int n0,
-                                                 const double *sel, unsigned short *qidx /* shared, IQR_GRID_MAX */, double *__restrict__ out, int *out_count,
-                                                 bool write_out) {
+__device__ __forceinline__ int iqr_local_compact(int *ws /* shared, 32 */, int *total /* shared */, const double *sd2, int n0, const double *sel,
+                                                 unsigned short *qidx /* shared, IQR_GRID_MAX */) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = n0 / 2;
     const double v0 = __ldcg(sel), v1 = __ldcg(sel + 1), v2 = __ldcg(sel + 2), v3 = __ldcg(sel + 3);
@@ -217,18 +216,24 @@ __device__ __forceinline__ int iqr_local_compact(int *ws /* shared, 32 */, int *
         if (f & (1u << u)) {
             const int i = tid * PER + u;
             qidx[pos] = (unsigned short)i;
-            if (write_out) {
-                out[3 * (size_t)pos] = xyz[3 * (size_t)i];
-                out[3 * (size_t)pos + 1] = xyz[3 * (size_t)i + 1];
-                out[3 * (size_t)pos + 2] = xyz[3 * (size_t)i + 2];
-            }
             ++pos;
         }
     }
     const int n = *total;
-    if (write_out && tid == 0) *out_count = n;
     __syncthreads();
     return n;
+}
+
+// The keypoint cloud and its count for the host, written by ONE CTA from its index list -- after the Gauss-Newton loop, off everybody's
+// critical path (inside the compaction, 16 dependent load -> store rounds of CTA 0 held up the first row exchange of every scan by ~10 us).
+template <int BLOCK>
+__device__ __forceinline__ void iqr_write_out(const unsigned short *qidx, const double *__restrict__ xyz, int n, double *__restrict__ out, int *out_count) {
+    for (int p = threadIdx.x; p < n; p += BLOCK) {
+        const size_t i = qidx[p];
+        const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        out[3 * (size_t)p] = x; out[3 * (size_t)p + 1] = y; out[3 * (size_t)p + 2] = z;
+    }
+    if (threadIdx.x == 0) *out_count = n;
 }
 
 }  // namespace limu

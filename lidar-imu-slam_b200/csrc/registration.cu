@@ -695,7 +695,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
                 IQ_MARK(17);
                 gs_icp.sync();
                 IQ_MARK(18);
-                n_keypoints = iqr_local_compact<ICP_BLOCK>(iqr_sm.ws, &iqr_sm.total, iqr_sd2, A.iqr_in, n0, A.iqr_d2, qidx_s, A.iqr_out, A.iqr_count, blockIdx.x == 0);
+                n_keypoints = iqr_local_compact<ICP_BLOCK>(iqr_sm.ws, &iqr_sm.total, iqr_sd2, n0, A.iqr_d2, qidx_s);
                 IQ_MARK(19);
             }
         } else {
@@ -895,6 +895,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
         ++j;
     }
     FT_MARK(2);
+    if (blockIdx.x == 0 && n_keypoints >= 0) iqr_write_out<ICP_BLOCK>(qidx_s, A.iqr_in, n_keypoints, A.iqr_out, A.iqr_count);   // keypoints for the host
     // new_pose = T_icp * init_guess (:129); with an empty map the loop did not run and this is init_guess itself (:99-100)
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const Pose np = run_icp ? mul(pose_load(Ticp), pose_load(Tinit)) : pose_load(Tinit);
@@ -969,10 +970,11 @@ static __global__ void __launch_bounds__(CL_THREADS, 1) k_frame_cluster(const Ic
     const int n0 = __ldcg(A.iqr_n);
     const bool small = n0 <= IQR_GRID_MAX;     // uniform across the grid
     int n = 0;                                 // keypoints (known to the loop CTAs)
+    bool compacted_here = false;               // the keypoints are IQR candidates sm.qidx[0 .. n)
     if (small && n0 > 1) {
         iqr_grid_select<CL_THREADS>(sm.sd2, A.iqr_in, n0, A.iqr_d2);
         gs.sync();
-        if (loop_cta) n = iqr_local_compact<CL_THREADS>(sm.ws, &sm.total, sm.sd2, A.iqr_in, n0, A.iqr_d2, sm.qidx, A.iqr_out, A.iqr_count, blockIdx.x == 0);
+        if (loop_cta) { n = iqr_local_compact<CL_THREADS>(sm.ws, &sm.total, sm.sd2, n0, A.iqr_d2, sm.qidx); compacted_here = true; }
     } else if (small) {                        // 0 or 1 candidate: outlier::IQR keeps a single value (common.hpp:49-52)
         if (threadIdx.x == 0) {
             sm.qidx[0] = 0;
@@ -1100,6 +1102,7 @@ static __global__ void __launch_bounds__(CL_THREADS, 1) k_frame_cluster(const Ic
         }
     }
     FT_MARK(2);
+    if (blockIdx.x == 0 && compacted_here) iqr_write_out<CL_THREADS>(sm.qidx, A.iqr_in, n, A.iqr_out, A.iqr_count);   // keypoints for the host
     // new_pose = T_icp * init_guess (:129); with an empty map the loop did not run and this is init_guess itself (:99-100)
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const Pose np = run_icp ? mul(pose_load(sm.Ticp), pose_load(sm.Tinit)) : pose_load(sm.Tinit);

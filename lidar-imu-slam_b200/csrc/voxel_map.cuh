@@ -235,10 +235,22 @@ __device__ __forceinline__ void group8_scan(const V3 &p, int l8, int count, cons
 // (|delta|^2, birth) = the reference's max-heap top (voxel_hash_map.cpp:81-101). Group-uniform; returns the slot (or -1).
 struct MapProbe { double *blk; unsigned int mask; int shift, stride; };   // what probing needs of a MapView, passed BY VALUE (a reference to the
                                                                           // kernel's parameter block would force a local copy of all of it)
-static __device__ __noinline__ int group8_resolve_rare(MapProbe mp, int kx, int ky, int kz, bool inr, unsigned long long key, unsigned int h, ulonglong2 sv,
-                                                      unsigned gmask, int l8, int *count_out, int *own_out) {
-    MapView m;
-    m.blk = mp.blk; m.mask = mp.mask; m.shift = mp.shift; m.stride = mp.stride;
+// the home slots of this lane's four neighbour cells l8, l8+8, l8+16, l8+24 of the 26 (issued together: one round trip)
+__device__ __forceinline__ void group8_probe_neighbours(const MapView &m, int kx, int ky, int kz, int l8, ulonglong2 *got) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int c = l8 + 8 * u;
+        got[u] = make_ulonglong2(KEY_EMPTY, 0ull);
+        if (c < 26) {
+            const int x = kx + NB_ALL[c][0], y = ky + NB_ALL[c][1], z = kz + NB_ALL[c][2];
+            if (key_in_range(x, y, z)) got[u] = load_slot(slot_at(m, slot_of(pack_key(x, y, z), m.shift)));
+        }
+    }
+}
+// The rare part: the home slot `h` holds ANOTHER voxel (collision: probe on) or nothing; if the query's own voxel is not in the table, the
+// fallback over the neighbour probes `got`. Group-uniform; returns the slot (or -1).
+__device__ __forceinline__ int group8_resolve_core(const MapView &m, int kx, int ky, int kz, bool inr, unsigned long long key, unsigned int h, ulonglong2 sv,
+                                                   const ulonglong2 *got, unsigned gmask, int l8, int *count_out, int *own_out) {
     *own_out = 0;
     *count_out = 0;
     if (inr) {
@@ -249,16 +261,6 @@ static __device__ __noinline__ int group8_resolve_rare(MapProbe mp, int kx, int 
     }
     int bd = -1, bslot = -1;
     unsigned long long bmeta = 0ull;
-    ulonglong2 got[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const int c = l8 + 8 * u;
-        got[u] = make_ulonglong2(KEY_EMPTY, 0ull);
-        if (c < 26) {
-            const int x = kx + NB_ALL[c][0], y = ky + NB_ALL[c][1], z = kz + NB_ALL[c][2];
-            if (key_in_range(x, y, z)) got[u] = load_slot(slot_at(m, slot_of(pack_key(x, y, z), m.shift)));
-        }
-    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const int c = l8 + 8 * u;
@@ -282,10 +284,21 @@ static __device__ __noinline__ int group8_resolve_rare(MapProbe mp, int kx, int 
     if (bslot >= 0) *count_out = meta_count(bmeta);
     return bslot;
 }
+// ... kept out of line where registers are scarce (bandwidth shape: the four 16-byte probes in flight per lane must not weigh on the hot path)
+static __device__ __noinline__ int group8_resolve_rare(MapProbe mp, int kx, int ky, int kz, bool inr, unsigned long long key, unsigned int h, ulonglong2 sv,
+                                                      unsigned gmask, int l8, int *count_out, int *own_out) {
+    MapView m;
+    m.blk = mp.blk; m.mask = mp.mask; m.shift = mp.shift; m.stride = mp.stride;
+    ulonglong2 got[4];
+    group8_probe_neighbours(m, kx, ky, kz, l8, got);
+    return group8_resolve_core(m, kx, ky, kz, inr, key, h, sv, got, gmask, l8, count_out, own_out);
+}
 
 // Core: the query's voxel index (kx, ky, kz), whether it is inside the packed key range (inr), its packed key and home slot h are given
 // (the bandwidth shape computes them with ONE lane per query and hands them to the group by shuffle).
-template <int ROUNDS>
+// PREFETCH_NB (latency shape, registers to spare): the 26 neighbour probes are requested together with the home block, so an absent voxel
+// costs two round trips (probes, then the neighbour's candidates) instead of three -- the slowest query of an iteration sets its pace.
+template <int ROUNDS, bool PREFETCH_NB = false>
 __device__ __forceinline__ void group8_closest_at(const MapView &m, const V3 &p, int kx, int ky, int kz, bool inr, unsigned long long key, unsigned int h,
                                                   unsigned gmask, int l8, int &slot_out, int &count_out, int &own_out, double &d2_out, int &rank_out, V3 &t_out) {
     double bd2 = 1.7976931348623157e308, tx = 0.0, ty = 0.0, tz = 0.0;
@@ -294,8 +307,13 @@ __device__ __forceinline__ void group8_closest_at(const MapView &m, const V3 &p,
         const ulonglong2 sv = load_slot(slot_at(m, h));
         double cx[ROUNDS], cy[ROUNDS], cz[ROUNDS];
         group8_load<ROUNDS>(m, h, l8, cx, cy, cz);
+        ulonglong2 got[PREFETCH_NB ? 4 : 1];
+        if (PREFETCH_NB) group8_probe_neighbours(m, kx, ky, kz, l8, got);
         if (inr && sv.x == key) {
             slot = (int)h; count = meta_count(sv.y); own = 1;
+        } else if (PREFETCH_NB) {
+            slot = group8_resolve_core(m, kx, ky, kz, inr, key, h, sv, got, gmask, l8, &count, &own);
+            if (slot >= 0) group8_load<ROUNDS>(m, (unsigned int)slot, l8, cx, cy, cz);
         } else {   // group-uniform: all eight lanes saw the same header
             slot = group8_resolve_rare(MapProbe{m.blk, m.mask, m.shift, m.stride}, kx, ky, kz, inr, key, h, sv, gmask, l8, &count, &own);
             if (slot >= 0) group8_load<ROUNDS>(m, (unsigned int)slot, l8, cx, cy, cz);   // displaced or neighbour voxel: its candidates are a second trip
@@ -329,7 +347,7 @@ __device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, un
     const int kx = vox_index(m, p.x), ky = vox_index(m, p.y), kz = vox_index(m, p.z);
     const bool inr = key_in_range(kx, ky, kz);
     const unsigned long long key = pack_key(kx, ky, kz);
-    group8_closest_at<ROUNDS>(m, p, kx, ky, kz, inr, key, inr ? slot_of(key, m.shift) : 0u, gmask, l8, slot_out, count_out, own_out, d2_out, rank_out, t_out);
+    group8_closest_at<ROUNDS, true>(m, p, kx, ky, kz, inr, key, inr ? slot_of(key, m.shift) : 0u, gmask, l8, slot_out, count_out, own_out, d2_out, rank_out, t_out);
 }
 
 // Pair-cooperative lookup for the cluster latency shape (registration.cu, k_frame_cluster): TWO lanes serve one query, so that one
