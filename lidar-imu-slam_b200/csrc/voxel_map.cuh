@@ -347,7 +347,9 @@ __device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, un
     const int kx = vox_index(m, p.x), ky = vox_index(m, p.y), kz = vox_index(m, p.z);
     const bool inr = key_in_range(kx, ky, kz);
     const unsigned long long key = pack_key(kx, ky, kz);
-    group8_closest_at<ROUNDS, true>(m, p, kx, ky, kz, inr, key, inr ? slot_of(key, m.shift) : 0u, gmask, l8, slot_out, count_out, own_out, d2_out, rank_out, t_out);
+    // (PREFETCH_NB was measured in the pipeline's latency shape: the absent-voxel path got shorter, but the four extra probes and their key
+    //  arithmetic on EVERY query cost more than they saved -- 9.2 vs 8.7 us per iteration -- so it stays off)
+    group8_closest_at<ROUNDS, false>(m, p, kx, ky, kz, inr, key, inr ? slot_of(key, m.shift) : 0u, gmask, l8, slot_out, count_out, own_out, d2_out, rank_out, t_out);
 }
 
 // Pair-cooperative lookup for the cluster latency shape (registration.cu, k_frame_cluster): TWO lanes serve one query, so that one
