@@ -298,6 +298,40 @@ int limu_odom_register_msg(limu_odom *o, const void *data, int64_t n, const limu
                            int32_t scan_count, int32_t max_segments, double *poses_out, int64_t *seg_sizes, double *seg_time, int32_t *n_segments,
                            limu_frame_stats *stats);
 
+/* ---- kalman::EKF predict / update, L/src/kalman/ekf.cpp -------------------------------------------------
+ * HOST code inside the library (the north star keeps the small state solve on the host): the reference's error-state-free quaternion EKF --
+ * 30 inner states + a trail of `lidar_pose_trail` poses of 7 -- restated without Eigen. The reference constructs this filter and never
+ * steps it at runtime; parity is pinned against the compiled original (oracle/ref_ekf_driver.cpp). State layout, ekf.hpp:32-44: POS 0,
+ * VEL 3, ORI 6 (w x y z), BGA 10, BAA 13, BAT 16, GRAV 19, POS_IMU_LIDAR 22, ROT_IMU_LIDAR 25 (x y z w as Eigen stores it), SFT 29,
+ * trail poses from 30. Matrices are row-major, dim = 30 + 7 * lidar_pose_trail. */
+typedef struct limu_ekf_params {   /* kalman::EKF_PARAMETERS, ekf.hpp:62-86 */
+    int32_t lidar_pose_trail, reserved0;
+    double noise_scale, init_pos_noise, init_vel_noise, init_ori_noise, init_bga_noise, init_baa_noise, init_bat_noise;
+    double acc_process_noise, gyro_process_noise, acc_process_noise_rev, gyro_process_noise_rev;
+    double init_lidar_imu_time_noise, init_pos_trail_noise, init_ori_trail_noise, visualZuptR;
+} limu_ekf_params;
+typedef struct limu_ekf limu_ekf;
+void limu_ekf_default_params(limu_ekf_params *p);
+int limu_ekf_create(const limu_ekf_params *p, limu_ekf **out);       /* EKF::EKF :63-190 */
+void limu_ekf_destroy(limu_ekf *e);
+int limu_ekf_state_dim(limu_ekf *e, int32_t *dim);
+int limu_ekf_get_state(limu_ekf *e, double *m /* dim */, double *P /* dim x dim */, double *current_time); /* any pointer may be NULL */
+int limu_ekf_set_state(limu_ekf *e, const double *m, const double *P);
+/* initialize_imu_global_orientation :194-211 as evidently intended (the original has undefined behaviour: four coefficients into a Vector3d) */
+int limu_ekf_initialize_orientation(limu_ekf *e, const double xa[3], const double calc_grav[3]);
+/* predict :214-290: state propagation with gyro xg / accelerometer xa at time t, Jacobians, covariance */
+int limu_ekf_predict(limu_ekf *e, double t, const double xg[3], const double xa[3], const double calc_grav[3], const double trans_lidar_imu[3],
+                     const double rot_lidar_imu[9]);
+int limu_ekf_normalize_quaternions(limu_ekf *e, int only_current);   /* :619-636 */
+int limu_ekf_zero_velocity_update(limu_ekf *e, double r);            /* zero_vel_update :657-678 */
+int limu_ekf_augment_pose_trail(limu_ekf *e);                        /* update_visual_pose_aug :700-734 */
+int limu_ekf_undo_augmentation(limu_ekf *e);                         /* update_undo_augmentation :736-756 */
+int limu_ekf_update_and_propagate(limu_ekf *e);                      /* :680-698 */
+/* The registration result as a measurement of the filter -- what the reference's design promised and its code never wired:
+ * pose {qx,qy,qz,qw, tx,ty,tz} (limu_odom_register_*) observes POS and ORI directly, R = diag(pos_sigma^2 x3, ori_sigma^2 x4) * noise_scale.
+ * No counterpart in the reference (parity unpinned). */
+int limu_ekf_update_lidar_pose(limu_ekf *e, const double pose[7], double pos_sigma, double ori_sigma);
+
 /* ---- host-side SE(3) helpers (the same restatement of Sophus 1.22.10 the device code uses) ------ */
 void limu_se3_exp(const double x[6], double pose_out[7]);
 void limu_se3_log(const double pose[7], double x_out[6]);

@@ -77,6 +77,14 @@ class ImuState(C.Structure):
                 ("tracker_pos", C.c_double * 3), ("tracker_quat", C.c_double * 4)]
 
 
+class EkfParams(C.Structure):
+    """limu_ekf_params == kalman::EKF_PARAMETERS (ekf.hpp:62-86)."""
+    _fields_ = [("lidar_pose_trail", C.c_int32), ("reserved0", C.c_int32)] + [(n, C.c_double) for n in (
+        "noise_scale", "init_pos_noise", "init_vel_noise", "init_ori_noise", "init_bga_noise", "init_baa_noise", "init_bat_noise",
+        "acc_process_noise", "gyro_process_noise", "acc_process_noise_rev", "gyro_process_noise_rev",
+        "init_lidar_imu_time_noise", "init_pos_trail_noise", "init_ori_trail_noise", "visualZuptR")]
+
+
 def imu_forward_pass(state: ImuState, imu, lidar_beg_time, last_point_curvature_ms):
     """IMU forward pass of EKF::motion_compensation_with_imu (ekf.cpp:292-418), host code. imu: [k,7] rows {t, gyr xyz, acc xyz}, row 0 = the last
     sample of the previous window. Returns (table [M,22], rot_end [9], pos_lidar_end [3]); `state` is updated in place."""
@@ -186,6 +194,11 @@ def lib():
             "limu_odom_register_msg": [_vp, _vp, C.c_int64, C.POINTER(CloudFields), C.POINTER(LidarConfig), C.c_double, C.c_int32, C.c_int32, _dp, _lp, _dp,
                                        C.POINTER(C.c_int32), C.POINTER(FrameStats)],
             "limu_imu_forward_pass": [C.POINTER(ImuState), _vp, C.c_int32, C.c_double, C.c_double, _vp, C.c_int32, C.POINTER(C.c_int32), _dp, _dp],
+            "limu_ekf_default_params": [C.POINTER(EkfParams)], "limu_ekf_create": [C.POINTER(EkfParams), C.POINTER(_vp)], "limu_ekf_destroy": [_vp],
+            "limu_ekf_state_dim": [_vp, C.POINTER(C.c_int32)], "limu_ekf_get_state": [_vp, _dp, _dp, _dp], "limu_ekf_set_state": [_vp, _dp, _dp],
+            "limu_ekf_initialize_orientation": [_vp, _dp, _dp], "limu_ekf_predict": [_vp, C.c_double, _dp, _dp, _dp, _dp, _dp],
+            "limu_ekf_normalize_quaternions": [_vp, C.c_int], "limu_ekf_zero_velocity_update": [_vp, C.c_double], "limu_ekf_augment_pose_trail": [_vp],
+            "limu_ekf_undo_augmentation": [_vp], "limu_ekf_update_and_propagate": [_vp], "limu_ekf_update_lidar_pose": [_vp, _dp, C.c_double, C.c_double],
             "limu_se3_exp": [_dp, _dp], "limu_se3_log": [_dp, _dp], "limu_se3_mul": [_dp, _dp, _dp], "limu_se3_inverse": [_dp, _dp],
         }
         for name, args in sig.items():
@@ -696,3 +709,65 @@ class KissICP:
         out = np.empty(7)
         _chk(lib().limu_odom_prediction(self.h, _d(out)))
         return out
+
+
+class Ekf:
+    """kalman::EKF predict / update (L/src/kalman/ekf.cpp), host code inside the library (SURVEY section 8f N4)."""
+
+    def __init__(self, **params):
+        p = EkfParams()
+        lib().limu_ekf_default_params(C.byref(p))
+        for k, v in params.items():
+            setattr(p, k, v)
+        self.params = p
+        self.h = _vp()
+        _chk(lib().limu_ekf_create(C.byref(p), C.byref(self.h)))
+        d = C.c_int32(0)
+        _chk(lib().limu_ekf_state_dim(self.h, C.byref(d)))
+        self.dim = d.value
+
+    def close(self):
+        if self.h:
+            lib().limu_ekf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def state(self):
+        """(m [dim], P [dim, dim], current_time)."""
+        m, P, t = np.empty(self.dim), np.empty((self.dim, self.dim)), np.empty(1)
+        _chk(lib().limu_ekf_get_state(self.h, _d(m), _d(P), _d(t)))
+        return m, P, float(t[0])
+
+    def set_state(self, m=None, P=None):
+        _chk(lib().limu_ekf_set_state(self.h, _d(np.ascontiguousarray(m, np.float64)) if m is not None else None,
+                                      _d(np.ascontiguousarray(P, np.float64)) if P is not None else None))
+
+    def initialize_orientation(self, xa, calc_grav):
+        _chk(lib().limu_ekf_initialize_orientation(self.h, _d(np.ascontiguousarray(xa, np.float64)), _d(np.ascontiguousarray(calc_grav, np.float64))))
+
+    def predict(self, t, xg, xa, calc_grav, trans_lidar_imu, rot_lidar_imu):
+        a = [np.ascontiguousarray(x, np.float64) for x in (xg, xa, calc_grav, trans_lidar_imu, np.asarray(rot_lidar_imu, np.float64).reshape(9))]
+        _chk(lib().limu_ekf_predict(self.h, float(t), *[_d(x) for x in a]))
+
+    def normalize_quaternions(self, only_current=False):
+        _chk(lib().limu_ekf_normalize_quaternions(self.h, int(only_current)))
+
+    def zero_velocity_update(self, r):
+        _chk(lib().limu_ekf_zero_velocity_update(self.h, float(r)))
+
+    def augment_pose_trail(self):
+        _chk(lib().limu_ekf_augment_pose_trail(self.h))
+
+    def undo_augmentation(self):
+        _chk(lib().limu_ekf_undo_augmentation(self.h))
+
+    def update_and_propagate(self):
+        _chk(lib().limu_ekf_update_and_propagate(self.h))
+
+    def update_lidar_pose(self, pose7, pos_sigma, ori_sigma):
+        _chk(lib().limu_ekf_update_lidar_pose(self.h, _d(_pose(pose7)), float(pos_sigma), float(ori_sigma)))

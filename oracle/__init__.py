@@ -505,3 +505,60 @@ def load_port() -> _Api:
         build_port()
         _cache["port"] = _Api(C.CDLL(PORT_SO), "lo_", "port")
     return _cache["port"]
+
+
+class RefEkf:
+    """The reference's own kalman::EKF (compiled, oracle/ref_ekf_driver.cpp) behind the same calls as limu_b200.Ekf."""
+
+    ORDER = ("lidar_pose_trail", "noise_scale", "init_pos_noise", "init_vel_noise", "init_ori_noise", "init_bga_noise", "init_baa_noise", "init_bat_noise",
+             "acc_process_noise", "gyro_process_noise", "acc_process_noise_rev", "gyro_process_noise_rev", "init_lidar_imu_time_noise",
+             "init_pos_trail_noise", "init_ori_trail_noise", "visualZuptR")
+    DEFAULTS = dict(lidar_pose_trail=20, noise_scale=1.0, init_pos_noise=1e-3, init_vel_noise=1e-3, init_ori_noise=1e-3, init_bga_noise=1e-3, init_baa_noise=1e-3,
+                    init_bat_noise=1e-3, acc_process_noise=0.03, gyro_process_noise=0.00017, acc_process_noise_rev=0.03, gyro_process_noise_rev=0.00017,
+                    init_lidar_imu_time_noise=1e-3, init_pos_trail_noise=1e-3, init_ori_trail_noise=1e-3, visualZuptR=1e-3)
+
+    def __init__(self, **params):
+        self.lib = load_ref().lib
+        L = self.lib
+        L.ref_ekf_create.restype = C.c_void_p
+        L.ref_ekf_create.argtypes = [C.POINTER(C.c_double)]
+        L.ref_ekf_dim.restype = C.c_long
+        for name, args in (("ref_ekf_destroy", [C.c_void_p]), ("ref_ekf_dim", [C.c_void_p]), ("ref_ekf_get", [C.c_void_p] + [C.POINTER(C.c_double)] * 3),
+                           ("ref_ekf_set", [C.c_void_p] + [C.POINTER(C.c_double)] * 2), ("ref_ekf_predict", [C.c_void_p, C.c_double] + [C.POINTER(C.c_double)] * 5),
+                           ("ref_ekf_normalize", [C.c_void_p, C.c_int]), ("ref_ekf_zero_vel_update", [C.c_void_p, C.c_double]), ("ref_ekf_augment", [C.c_void_p]),
+                           ("ref_ekf_undo_augmentation", [C.c_void_p])):
+            getattr(L, name).argtypes = args
+        p = dict(self.DEFAULTS)
+        p.update(params)
+        arr = np.array([float(p[k]) for k in self.ORDER])
+        self.h = L.ref_ekf_create(_d(arr))
+        self.dim = int(L.ref_ekf_dim(self.h))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_ekf_destroy(self.h)
+            self.h = None
+
+    def state(self):
+        m, P, t = np.empty(self.dim), np.empty((self.dim, self.dim)), np.empty(1)
+        self.lib.ref_ekf_get(self.h, _d(m), _d(P), _d(t))
+        return m, P, float(t[0])
+
+    def set_state(self, m=None, P=None):
+        self.lib.ref_ekf_set(self.h, _d(np.ascontiguousarray(m, np.float64)) if m is not None else None, _d(np.ascontiguousarray(P, np.float64)) if P is not None else None)
+
+    def predict(self, t, xg, xa, calc_grav, trans_lidar_imu, rot_lidar_imu):
+        a = [np.ascontiguousarray(x, np.float64) for x in (xg, xa, calc_grav, trans_lidar_imu, np.asarray(rot_lidar_imu, np.float64).reshape(9))]
+        self.lib.ref_ekf_predict(self.h, float(t), *[_d(x) for x in a])
+
+    def normalize_quaternions(self, only_current=False):
+        self.lib.ref_ekf_normalize(self.h, int(only_current))
+
+    def zero_velocity_update(self, r):
+        self.lib.ref_ekf_zero_vel_update(self.h, float(r))
+
+    def augment_pose_trail(self):
+        self.lib.ref_ekf_augment(self.h)
+
+    def undo_augmentation(self):
+        self.lib.ref_ekf_undo_augmentation(self.h)

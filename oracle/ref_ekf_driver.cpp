@@ -131,4 +131,53 @@ long ref_imu_deskew(const float *xyz, const float *curv_ms, long n, const double
     return M;
 }
 
+// ---- kalman::EKF predict / update: a long-lived reference object behind a C handle -------------------------------
+// params: {lidar_pose_trail, noise_scale, init_pos, init_vel, init_ori, init_bga, init_baa, init_bat, acc_noise, gyro_noise, acc_rev, gyro_rev,
+//          init_lidar_imu_time, init_pos_trail, init_ori_trail, visualZuptR} as 16 doubles.
+void *ref_ekf_create(const double *prm16) {
+    auto prm = std::make_shared<kalman::EKF_PARAMETERS>();
+    std::memset(prm.get(), 0, sizeof(kalman::EKF_PARAMETERS));
+    prm->lidar_pose_trail = static_cast<int>(prm16[0]);
+    prm->noise_scale = prm16[1];
+    prm->init_pos_noise = prm16[2]; prm->init_vel_noise = prm16[3]; prm->init_ori_noise = prm16[4];
+    prm->init_bga_noise = prm16[5]; prm->init_baa_noise = prm16[6]; prm->init_bat_noise = prm16[7];
+    prm->acc_process_noise = prm16[8]; prm->gyro_process_noise = prm16[9]; prm->acc_process_noise_rev = prm16[10]; prm->gyro_process_noise_rev = prm16[11];
+    prm->init_lidar_imu_time_noise = prm16[12]; prm->init_pos_trail_noise = prm16[13]; prm->init_ori_trail_noise = prm16[14]; prm->visualZuptR = prm16[15];
+    return new kalman::EKF(prm);
+}
+void ref_ekf_destroy(void *h) { delete static_cast<kalman::EKF *>(h); }
+long ref_ekf_dim(void *h) { return static_cast<kalman::EKF *>(h)->state_dim; }
+void ref_ekf_get(void *h, double *m, double *P /* row-major */, double *time) {
+    auto &e = *static_cast<kalman::EKF *>(h);
+    const int n = e.state_dim;
+    for (int i = 0; i < n; ++i) m[i] = e.m(i);
+    for (int r = 0; r < n; ++r) for (int c = 0; c < n; ++c) P[(size_t)r * n + c] = e.P(r, c);
+    if (time) *time = e.get_current_time();
+}
+void ref_ekf_set(void *h, const double *m, const double *P) {
+    auto &e = *static_cast<kalman::EKF *>(h);
+    const int n = e.state_dim;
+    if (m) for (int i = 0; i < n; ++i) e.m(i) = m[i];
+    if (P) for (int r = 0; r < n; ++r) for (int c = 0; c < n; ++c) e.P(r, c) = P[(size_t)r * n + c];
+}
+void ref_ekf_predict(void *h, double t, const double *xg, const double *xa, const double *grav, const double *trans, const double *rot9 /* row-major */) {
+    auto &e = *static_cast<kalman::EKF *>(h);
+    Eigen::Matrix3d R;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R(r, c) = rot9[3 * r + c];
+    e.predict(t, Eigen::Vector3d(xg[0], xg[1], xg[2]), Eigen::Vector3d(xa[0], xa[1], xa[2]), Eigen::Vector3d(grav[0], grav[1], grav[2]),
+              Eigen::Vector3d(trans[0], trans[1], trans[2]), R);
+}
+void ref_ekf_normalize(void *h, int only_current) { static_cast<kalman::EKF *>(h)->normalize_quaternions(only_current != 0); }
+void ref_ekf_zero_vel_update(void *h, double r) {
+    auto &e = *static_cast<kalman::EKF *>(h);
+    e.zero_vel_update(e.m, e.K, e.P, e.HP, e.invS, e.H, e.R, r);
+}
+void ref_ekf_augment(void *h) { static_cast<kalman::EKF *>(h)->update_visual_pose_aug(); }
+// update_undo_augmentation pops augment_times unconditionally (undefined on the empty vector the reference's own bookkeeping leaves): give it an entry to pop
+void ref_ekf_undo_augmentation(void *h) {
+    auto &e = *static_cast<kalman::EKF *>(h);
+    if (e.augment_times.empty()) { e.augment_times.push_back(0.0); e.augment_count++; }
+    e.update_undo_augmentation();
+}
+
 }  // extern "C"

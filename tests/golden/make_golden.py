@@ -209,10 +209,31 @@ def frame_fixtures(ref):
     return out
 
 
+def ekf_fixtures():
+    """kalman::EKF (ekf.cpp) stepped by oracle/ref_ekf_driver.cpp through the script of tests/test_ekf.py (trail 5 keeps the file small):
+    the state and covariance after every augmentation / zero-velocity update / undo, after the last predict, and after a few early predicts."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import test_ekf as T
+    seed, trail, noise_scale = 11, 5, 1.5
+    steps = T.script(np.random.default_rng(seed))
+    f = oracle.RefEkf(lidar_pose_trail=trail, noise_scale=noise_scale)
+    m0, P0, _ = f.state()
+    m0[3:6] = [0.8, -0.3, 0.05]
+    q = np.array([0.98, 0.05, -0.12, 0.1]); m0[6:10] = q / np.linalg.norm(q)
+    m0[10:13] = [1e-3, -2e-3, 5e-4]; m0[13:16] = [0.02, -0.01, 0.03]; m0[16:19] = [1.01, 0.99, 1.02]; m0[19:22] = T.GRAV
+    P0[6:10, 6:10] = np.diag([1e-6, 1e-6, 1e-6, 0.0]) * noise_scale ** 2
+    f.set_state(m0, P0)
+    states = T.run_script(f, steps, T.GRAV, T.TRANS, T.ROT)
+    idx = [i for i, s_ in enumerate(steps) if s_[0] in ("augment", "zupt", "undo")] + [1, 2, 7, len(steps) - 1]
+    idx = sorted(set(idx))
+    return {"seed": seed, "trail": trail, "noise_scale": noise_scale, "m0": m0, "P0": P0, "idx": np.array(idx), "m": np.array([states[i][0] for i in idx]),
+            "P": np.array([states[i][1] for i in idx])}
+
+
 if __name__ == "__main__":
     oracle.build_ref()
     ref = oracle.load_ref()
-    which = sys.argv[1:] or ["hash_map", "path", "frame"]
+    which = sys.argv[1:] or ["hash_map", "path", "frame", "ekf"]
     made = []
     if "hash_map" in which:
         np.savez_compressed(os.path.join(HERE, "fixtures_hash_map_test.npz"), **hash_map_test_fixtures(ref))
@@ -223,5 +244,8 @@ if __name__ == "__main__":
     if "frame" in which:
         np.savez_compressed(os.path.join(HERE, "fixtures_frame.npz"), **frame_fixtures(ref))
         made.append("fixtures_frame.npz")
+    if "ekf" in which:
+        np.savez_compressed(os.path.join(HERE, "fixtures_ekf.npz"), **ekf_fixtures())
+        made.append("fixtures_ekf.npz")
     for f in made:
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

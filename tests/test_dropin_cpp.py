@@ -129,3 +129,29 @@ def test_cpp_consumer_matches_oracle(tmp_path, port, rng):
     assert np.array_equal(o[j + 4], [s["time"] for s in seg])
     assert np.array_equal(o[j + 5].reshape(-1, 5), np.concatenate([s["points"] for s in seg]).astype(np.float64))
     assert np.array_equal(o[j + 6], np.concatenate([s["ts"] for s in seg]))
+
+
+def test_dropin_ekf_cpp_consumer_matches_python_binding():
+    """include/limu_dropin/limu/kalman/ekf.hpp (kalman::EKF on the C ABI) from a real C++ program, against the same script through ctypes.
+    Host code: no GPU needed."""
+    exe = os.path.join(ROOT, "tests", "cpp", "build", "ekf_test")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/build/ekf_test not built (needs vendored Eigen at build time)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    got = np.array([float(x) for x in out.stdout.split()])
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    e = pkg.Ekf(lidar_pose_trail=3)
+    grav, trans = np.array([0, 0, -9.81]), np.array([0.05, -0.02, 0.1])
+    rot = np.array([[0.0, -1, 0], [1, 0, 0], [0, 0, 1]])
+    e.initialize_orientation(np.array([0.3, -0.2, 9.7]), grav)
+    for i in range(20):
+        e.predict(100.0 + 0.005 * i, np.array([0.02, -0.01, 0.2 + 0.001 * i]), np.array([0.3, 0.1 * i, 9.81]), grav, trans, rot)
+    e.normalize_quaternions(True)
+    e.update_and_propagate()
+    e.update_lidar_pose(np.array([0.0, 0.0, 0.1, 0.99498743710662, 0.4, -0.1, 0.05]), 0.05, 0.01)
+    m, P, t = e.state()
+    want = np.concatenate([m, [np.trace(P), t, np.linalg.norm(m[3:6])]])
+    assert got.shape == want.shape and np.abs(got - want).max() < 1e-12
+    e.close()
