@@ -596,6 +596,15 @@ __device__ __forceinline__ void frame_update_epilogue(const IcpArgs &A, GridSync
     if (threadIdx.x < 7) E[threadIdx.x] = __ldcg(A.out + threadIdx.x);
     __syncthreads();
     const Pose np = pose_load(E);
+    // The next scan deskews with delta_pose(poses[N-2], poses[N-1]) = log(last^-1 * new) (deskew.cpp:14): left on the device for a speculative
+    // k_voxelize. One thread of the LAST CTA takes it (inverse, product, log: ~3 us of scalar code) while the grid inserts -- on CTA 0's
+    // thread 0, in front of the barrier above, it held up every CTA.
+    if (A.twist_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == BLOCK - 1) {
+        double tw[6];
+        se3_log(mul(inverse(Pose{A.last_pose[0], A.last_pose[1], A.last_pose[2], A.last_pose[3], A.last_pose[4], A.last_pose[5], A.last_pose[6]}), np), tw);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) A.twist_out[k] = tw[k];
+    }
     const int64_t nd = (int64_t)__ldcg(A.upd_n);
     const int64_t gtid = (int64_t)blockIdx.x * BLOCK + threadIdx.x, gthreads = (int64_t)gridDim.x * BLOCK;
     for (int64_t base = (int64_t)blockIdx.x * BLOCK; base < nd; base += gthreads) {   // whole warps stay converged for the ballot
@@ -900,12 +909,6 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const Pose np = run_icp ? mul(pose_load(Ticp), pose_load(Tinit)) : pose_load(Tinit);
         pose_store(np, A.out);
-        if (A.twist_out) {   // the next scan deskews with delta_pose(poses[N-2], poses[N-1]) = log(last^-1 * new): leave it on the device
-            double tw[6];
-            se3_log(mul(inverse(Pose{A.last_pose[0], A.last_pose[1], A.last_pose[2], A.last_pose[3], A.last_pose[4], A.last_pose[5], A.last_pose[6]}), np), tw);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) A.twist_out[k] = tw[k];
-        }
         A.out[7] = (double)j; A.out[8] = (double)converged; A.out[9] = S[I_NCORR]; A.out[10] = S[I_NCORR + 1]; A.out[11] = S[I_NCORR + 2]; A.out[12] = (double)n;
     }
     if (A.upd_down) frame_update_epilogue<ICP_BLOCK>(A, gs, E);
@@ -1107,12 +1110,6 @@ static __global__ void __launch_bounds__(CL_THREADS, 1) k_frame_cluster(const Ic
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const Pose np = run_icp ? mul(pose_load(sm.Ticp), pose_load(sm.Tinit)) : pose_load(sm.Tinit);
         pose_store(np, A.out);
-        if (A.twist_out) {   // the next scan deskews with delta_pose(poses[N-2], poses[N-1]) = log(last^-1 * new): leave it on the device
-            double tw[6];
-            se3_log(mul(inverse(Pose{A.last_pose[0], A.last_pose[1], A.last_pose[2], A.last_pose[3], A.last_pose[4], A.last_pose[5], A.last_pose[6]}), np), tw);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) A.twist_out[k] = tw[k];
-        }
         A.out[7] = (double)j; A.out[8] = (double)converged; A.out[9] = sm.S[16]; A.out[10] = sm.S[17]; A.out[11] = sm.S[18]; A.out[12] = (double)n;
     }
     if (A.upd_down) frame_update_epilogue<CL_THREADS>(A, gs, sm.E);

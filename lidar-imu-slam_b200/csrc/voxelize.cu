@@ -10,7 +10,7 @@
 // claimed slot is remembered per point, so the stage-1 table is un-claimed in P4 (nobody reads it after P3) and the stage-2 table of
 // this launch is un-claimed by the NEXT launch, which works on the other of two stage-2 tables.
 // "First point per voxel wins, output in first-occurrence order" (icp.cpp:13-27 + the oracle's ordered map) becomes:
-// atomicMin of the input index per voxel, then a stable compaction over 256-point tiles.
+// atomicMin of the input index per voxel, then a stable compaction over VX_BLOCK-point tiles.
 #include <algorithm>
 
 #include "compact.cuh"
@@ -20,7 +20,10 @@
 
 namespace limu {
 
-constexpr int VX_BLOCK = 256;
+#ifndef LIMU_VX_BLOCK
+#define LIMU_VX_BLOCK 1024   // one fat CTA per SM: a grid barrier is paid per ARRIVING CTA (atomics on one word serialise at ~4 ns each: 592 CTAs of 256 -> 148 of 1024)
+#endif
+constexpr int VX_BLOCK = LIMU_VX_BLOCK;
 
 struct VoxelizeArgs {
     const void *raw;            // mode 0: float4 {x,y,z,t}; mode 1: records `stride` bytes apart + ts; mode 2: double xyz (already a frame)
@@ -81,7 +84,7 @@ __device__ __forceinline__ int tile_base(const int *counts, int tile, int *ws /*
     return v;
 }
 
-static __global__ void __launch_bounds__(VX_BLOCK, 4) k_voxelize(const VoxelizeArgs A) {
+static __global__ void __launch_bounds__(VX_BLOCK, 1024 / VX_BLOCK) k_voxelize(const VoxelizeArgs A) {
     __shared__ int ws[32];
     __shared__ int total;
     GridSync gs{A.barrier, 0u, gridDim.x};
@@ -218,7 +221,7 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     if (g_vx_blocks_per_sm == 0) {
         int b = 0;
         LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_voxelize, VX_BLOCK, 0));
-        g_vx_blocks_per_sm = std::max(1, std::min(b, 4));
+        g_vx_blocks_per_sm = std::max(1, std::min(b, 1024 / VX_BLOCK));
     }
     const int64_t C1 = pow2_slots(n), C2 = pow2_slots(n);
     int lg = 0;
