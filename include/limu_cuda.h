@@ -233,11 +233,16 @@ int limu_odom_register_cloud(limu_odom *o, const void *points, int32_t stride_by
                              double *down_xyz, int64_t *n_down, double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats);
 int limu_odom_register_frame_dev(limu_odom *o, const float *xyzt_dev, int64_t n, double pose_out[7], limu_frame_stats *stats);
 /* Replay hint: the scan that will be registered AFTER the next limu_odom_register_frame_dev call already sits in device memory at
- * xyzt_dev_next (and stays untouched until it has been registered). With LIMU_OPT_SPECULATE on (the default) that scan's deskew +
- * downsampling launch is enqueued right behind the current scan's registration (the deskew twist stays on the device), so the host
- * round trip between two scans overlaps GPU work; limu_odom_prefetch gives the host-pointer entry the same treatment. Poses do not
- * depend on hints beyond rounding (the twist of a speculated scan is taken by the device's log instead of the host's: ~1e-15); a hint
- * that is not followed by that scan is simply discarded. */
+ * xyzt_dev_next (and stays untouched until it has been registered); limu_odom_prefetch gives the host-pointer entry the same treatment.
+ * With LIMU_OPT_SPECULATE on (the default) the packed-float4 entry points then PIPELINE consecutive scans (csrc/odometry.cu):
+ *   - the hinted scan's deskew + downsampling kernel is released the moment the current scan's Gauss-Newton loop has produced its pose
+ *     (its deskew twist stays on the device) and runs beside the current scan's map update;
+ *   - the hinted scan's IQR + Gauss-Newton loop is launched before the current call returns -- it only reads the map; the hinted scan's
+ *     map update is launched only when the caller registers that scan. A hint that is not followed is simply dropped.
+ * What the caller sees: a call returns as soon as its pose and clouds are there, while the map update of its scan may still be running --
+ * every later call on the handle or its map is ordered behind it; an error of that update (a voxel index out of range after the transform
+ * into the world frame) is returned by the NEXT call on the handle, or by limu_odom_flush. Poses do not depend on hints beyond rounding
+ * (the twist of a scan prepared ahead is taken by the device's log instead of the host's: ~1e-15). */
 int limu_odom_hint_next_dev(limu_odom *o, const float *xyzt_dev_next, int64_t n_next);
 /* Handle options. LIMU_OPT_SPECULATE (default 1; the environment variable LIMU_SPECULATE=0 changes the default): see above.
  * LIMU_OPT_CLUSTER_LOOP (default 0; LIMU_CLUSTER_LOOP=1): with the reference's registration rules the Gauss-Newton loop of a scan runs on
@@ -246,6 +251,9 @@ int limu_odom_hint_next_dev(limu_odom *o, const float *xyzt_dev_next, int64_t n_
  * to 1.2 us, but 16 SMs issue the ~2.4 k lookups of an iteration 3.5x slower than 72 SMs do), so it is an opt-in experiment. */
 enum { LIMU_OPT_SPECULATE = 1, LIMU_OPT_CLUSTER_LOOP = 2 };
 int limu_odom_set_option(limu_odom *o, int32_t option, int64_t value);
+/* Wait for everything the handle has in flight (a map update, kernels launched ahead for a hinted scan) and return the status of a map
+ * update that no call has reported yet. Not needed for correctness of later calls; useful before timing or tearing down. */
+int limu_odom_flush(limu_odom *o);
 /* register_frame(Vec3dVector) icp.cpp:58-86 (no deskew). */
 int limu_odom_register_points(limu_odom *o, const double *xyz, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down,
                               double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats);

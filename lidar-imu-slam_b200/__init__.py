@@ -184,6 +184,7 @@ def lib():
             "limu_odom_prefetch": [_vp, _fp, C.c_int64],
             "limu_odom_hint_next_dev": [_vp, _vp, C.c_int64],
             "limu_odom_set_option": [_vp, C.c_int32, C.c_int64],
+            "limu_odom_flush": [_vp],
             "limu_odom_register_points": [_vp, _dp, C.c_int64, _dp, _dp, _lp, _dp, _lp, C.POINTER(FrameStats)],
             "limu_odom_num_poses": [_vp, _lp], "limu_odom_pose": [_vp, C.c_int64, _dp],
             "limu_odom_adaptive_threshold": [_vp, _dp], "limu_odom_prediction": [_vp, _dp], "limu_odom_has_moved": [_vp, C.POINTER(C.c_int)],
@@ -591,8 +592,12 @@ class KissICP:
             _chk(lib().limu_odom_set_option(self.h, 2, int(bool(cluster_loop))))   # LIMU_OPT_CLUSTER_LOOP
 
     def set_speculate(self, on: bool):
-        """LIMU_OPT_SPECULATE: enqueue the next scan's deskew + downsampling behind this scan's registration (see limu_cuda.h)."""
+        """LIMU_OPT_SPECULATE: pipeline consecutive scans when the next one is known (hint_next_dev / prefetch; see limu_cuda.h)."""
         _chk(lib().limu_odom_set_option(self.h, 1, int(bool(on))))
+
+    def flush(self):
+        """Wait for what the handle has in flight; raises what a deferred map update had to report."""
+        _chk(lib().limu_odom_flush(self.h))
 
     def close(self):
         if self.h:

@@ -48,6 +48,19 @@ static double rotation_angle(const Pose &T) {
 }
 }  // namespace limu
 
+// Device result block of one handle (per HANDLE: two handles of one context may interleave their scans). 28 ints, then 13 doubles:
+//   [0] n_down, [1] n_src0 of the scans with parity 0     [20] [21] the same for parity 1 (consecutive scans alternate: in the pipelined
+//   [2] n_keypoints (written by the loop kernel)                    path the next scan's k_voxelize runs while this scan's update reads its count)
+//   [3] the loop flag: sequence number of the last Gauss-Newton loop whose pose and deskew twist are in memory (k_gate waits for it)
+//   [4..7] / [24..27] status word of the map update of a parity-0 / parity-1 scan
+//   [8..19] three status words k_voxelize rotates through
+//   doubles 14..26: pose + loop statistics (out13).     ONE copy of RES_DOUBLES per scan.
+namespace {
+constexpr int RES_CNT1 = 20, RES_FLAG = 3, RES_UPD_ST0 = 4, RES_UPD_ST1 = 24, RES_VOX_ST = 8, RES_OUT = 14, RES_DOUBLES = 27;
+inline int *res_counts(int *cnt, int par) { return cnt + (par ? RES_CNT1 : 0); }
+inline limu::DevStatus *res_update_status(int *cnt, int par) { return reinterpret_cast<limu::DevStatus *>(cnt + (par ? RES_UPD_ST1 : RES_UPD_ST0)); }
+}  // namespace
+
 struct limu_odom {
     limu_ctx *ctx = nullptr;
     limu_odom_config cfg;
@@ -57,9 +70,10 @@ struct limu_odom {
     double model_error_sq = 0.0;
     int num_samples = 0;
     limu::Pose model_deviation = limu::pose_identity();
-    // device buffers
-    limu::DevBuf raw, ts, frame, down, src0, src, work, world, partials, d2, res;
-    int vox_word = 0;                       // which of its two status words the last k_voxelize of this handle reports into
+    // device buffers. down / src0 / src exist twice: consecutive scans alternate (`par`), so that the next scan's kernels and this scan's
+    // cloud copies never touch the same buffer.
+    limu::DevBuf raw, ts, frame, down[2], src0[2], src[2], work, world, partials, d2, res;
+    int par = 0;                            // parity of the scan registered last
     limu::VoxelizeScratch vx;
     limu::PreScratch pre;                   // limu_odom_register_msg: frame::Lidar::process_frame on the device
     int64_t nk_hint = 2048, nd_hint = 16384;   // keypoints / downsampled points of the previous scan (launch shapes; the kernels take any count)
@@ -70,29 +84,43 @@ struct limu_odom {
     const void *pf_host[2] = {nullptr, nullptr};
     int64_t pf_n[2] = {-1, -1};
     uint64_t pf_seq[2] = {0, 0}, pf_counter = 0;   // order in which the pending uploads were requested
-    // Speculative voxelize (LIMU_OPT_SPECULATE, on by default): when the library knows which scan comes next (a device-pointer hint from
-    // limu_odom_hint_next_dev, or the scan limu_odom_prefetch is uploading) that scan's deskew + downsampling launch is enqueued right
-    // behind this scan's frame kernel, with its deskew twist left on the device by that kernel, so the host round trip of this scan
-    // (result copy, wake-up, scalar glue, launch) overlaps it instead of idling the GPU.
+    cudaEvent_t clouds_done = nullptr;
+    bool cluster_loop = false;              // LIMU_OPT_CLUSTER_LOOP: run the Gauss-Newton loop on one 16-CTA cluster (registration.cu, k_frame_cluster); measured slower, opt-in; plain path only
+    // ---- pipelined path (LIMU_OPT_SPECULATE, on by default; packed float4 scans) -------------------------------------------------------
+    // When the library knows which scan comes next (a device-pointer hint from limu_odom_hint_next_dev, or the scan limu_odom_prefetch is
+    // uploading) the work of consecutive scans overlaps on the device and with the host:
+    //   main stream   [loop X] [update X] [loop X+1] [update X+1] ...      loop   = IQR + Gauss-Newton loop (reads the map, writes a pose)
+    //   vox stream        [gate|vox X+1]     [gate|vox X+2]                update = local_map.update: insert + eviction
+    //   * vox X+1 needs pose X for its deskew twist and nothing else: a one-thread gate kernel releases it the moment loop X has published
+    //     pose and twist, so it runs beside update X instead of behind it;
+    //   * loop X+1 is launched at the END of call X -- before the caller has asked for scan X+1 -- because it only reads the map: if the
+    //     caller then registers something else its result is dropped. The map update of a scan is launched only once that scan has been
+    //     registered by the caller. So a call finds its pose computed (or in flight), and the GPU never waits for the host round trip.
+    // Consequences for the caller: a call returns while the map update of its scan may still run (everything else on the handle or its map
+    // is stream-ordered behind it); an error of that update (voxel index out of range AFTER the transform into the world) is reported
+    // by the next call on the handle or by limu_odom_flush.
     bool speculate = true;
-    bool cluster_loop = false;              // LIMU_OPT_CLUSTER_LOOP: run the Gauss-Newton loop on one 16-CTA cluster (registration.cu, k_frame_cluster); measured slower, opt-in
     const void *hint_ptr = nullptr;         // next scan (device float4 rows), set by the caller before registering the current one
     int64_t hint_n = 0;
-    const void *spec_ptr = nullptr;         // scan whose k_voxelize is already in flight / done
-    int64_t spec_n = 0;
-    int spec_deskewed = 0;
-    int spec_slot = -1;                     // prefetch slot the speculative launch reads (-1: a caller-owned device buffer)
-    limu::DevBuf twist_next;                // 6 doubles written by the frame kernel
-    cudaEvent_t frame_done = nullptr;       // recorded after the result copy of the current scan
-    cudaEvent_t spec_launched = nullptr;    // recorded right behind the speculative launch (completes when that kernel has finished)
-    cudaEvent_t spec_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // device time of the speculative launch (two pairs, alternating), folded into LIMU_STAGE_DOWNSAMPLE one call later
-    bool spec_timed = false;
-    int spec_par = 0;
-    // This scan's clouds leave on the copy stream while the speculative launch runs, so `down` is double-buffered (the launch writes the
-    // buffer this scan does not use); `src` is only rewritten by the NEXT frame kernel, which is launched after the clouds have arrived.
-    limu::DevBuf down_alt;
-    int down_cur = 0;
-    cudaEvent_t clouds_done = nullptr;
+    cudaStream_t vox_stream = nullptr;
+    cudaEvent_t vox_done[2] = {nullptr, nullptr}, loop_done[2] = {nullptr, nullptr};
+    cudaEvent_t pev_vox[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, pev_upd[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // profiling: device time of gated / deferred launches
+    bool pev_vox_used[2] = {false, false}, pev_upd_used[2] = {false, false};
+    double *h_res[2] = {nullptr, nullptr};  // pinned: the result block of a scan of either parity
+    unsigned int loop_seq = 0;              // sequence number of the last loop launch of this handle
+    limu::DevBuf twist_next;                // 6 doubles written by the loop kernel
+    int pending_update_par = -1;            // parity of a map update whose status word has not been read yet
+    struct Ahead {                          // what is in flight for the scan the caller said comes next
+        const void *ptr = nullptr;
+        int64_t n = 0;
+        int deskewed = 0, slot = -1, par = 0, vox_word = 0;
+        bool vox = false, loop = false;
+        double sigma = 0.0;                 // what the loop was launched with
+        limu::Pose init = limu::pose_identity();
+        uint64_t map_mutations = 0;         // the map's mutation count when the loop was launched (the caller may touch the map between calls)
+        double stash_model_error_sq = 0.0;  // AdaptiveThreshold state before the glue of that launch: restored if the launch is not used
+        int stash_num_samples = 0;
+    } ahead;
 };
 
 using namespace limu;
@@ -126,50 +154,101 @@ static int odom_side_stream(limu_odom *o) {
         LIMU_CUDA_TRY(cudaStreamCreateWithFlags(&o->copy_stream, cudaStreamNonBlocking));
         for (int sl = 0; sl < 2; ++sl) LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->pf_done[sl], cudaEventDisableTiming));
     }
+    if (!o->clouds_done) LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->clouds_done, cudaEventDisableTiming));
     return LIMU_OK;
 }
 
-// Everything after the scan is in device memory.
+static int odom_res_block(limu_odom *o) {
+    if (!o->res.p) {
+        LIMU_TRY(o->res.reserve(48 * sizeof(double)));
+        LIMU_CUDA_TRY(cudaMemsetAsync(o->res.p, 0, o->res.bytes, o->ctx->stream));
+    }
+    return LIMU_OK;
+}
+
+// Forget what is in flight for a scan that will not be registered (or not as it was prepared). The kernels themselves are harmless -- they
+// write buffers of the other parity and scratch -- but the next launches must be ordered behind them, and the threshold model must not keep
+// a sample that was added for a registration that did not happen (get_adaptive_threshold accumulates on every call, threshold.cpp:16-28).
+static int odom_drop_ahead(limu_odom *o, bool keep_voxelize) {
+    limu_odom::Ahead &ah = o->ahead;
+    if (ah.loop) { o->model_error_sq = ah.stash_model_error_sq; o->num_samples = ah.stash_num_samples; ah.loop = false; }
+    if (!keep_voxelize && ah.vox) {
+        LIMU_CUDA_TRY(cudaStreamWaitEvent(o->ctx->stream, o->vox_done[ah.par], 0));   // (its gate waits for a loop that was launched before it)
+        ah.vox = false; ah.ptr = nullptr; ah.slot = -1;
+    }
+    return LIMU_OK;
+}
+
+// Status word of a map update that was launched by an earlier call and is complete by now (stream order): report and clear it.
+static int odom_deferred_status(limu_odom *o, const int *host_res) {
+    if (o->pending_update_par < 0) return LIMU_OK;
+    const int p = o->pending_update_par;
+    o->pending_update_par = -1;
+    DevStatus st;
+    memcpy(&st, host_res + (p ? RES_UPD_ST1 : RES_UPD_ST0), sizeof st);
+    if (!(st.key_range | st.table_full)) return LIMU_OK;
+    LIMU_CUDA_TRY(cudaMemsetAsync(res_update_status(o->res.as<int>(), p), 0, sizeof(DevStatus), o->ctx->stream));
+    if (st.key_range) { set_error("map update of the PREVIOUS frame: voxel index outside the packed key range (|index| >= 2^20); the frame was inserted without those points"); return LIMU_ERR_KEY_RANGE; }
+    set_error("map update of the previous frame: voxel hash table full");
+    return LIMU_ERR_MAP_FULL;
+}
+
+static int odom_report(limu_odom *o, const int *hc, int vox_word, int upd_par, bool spec_hit, int64_t n, int deskewed, double sigma, limu_frame_stats *stats) {
+    const double *ho = reinterpret_cast<const double *>(hc) + RES_OUT;
+    const int64_t nk = hc[2];
+    if (stats) {
+        stats->n_points = n; stats->n_down = res_counts(const_cast<int *>(hc), o->par)[0]; stats->n_keypoints = nk; stats->sigma = sigma; stats->deskewed = deskewed;
+        stats->reserved0 = spec_hit ? 1 : 0;
+        stats->icp.iterations = (int)ho[7]; stats->icp.converged = (int)ho[8]; stats->icp.last_ncorr = (int64_t)ho[9];
+        stats->icp.mean_candidates = nk > 0 ? ho[10] / (double)nk : 0.0;
+        stats->icp.miss_fraction = nk > 0 ? ho[11] / (double)nk : 0.0;
+    }
+    // device status of this scan: its own k_voxelize word and (plain path) the frame kernel's word
+    DevStatus st = {0, 0, {0, 0}}, sv;
+    if (upd_par >= 0) memcpy(&st, hc + (upd_par ? RES_UPD_ST1 : RES_UPD_ST0), sizeof st);
+    memcpy(&sv, hc + RES_VOX_ST + 4 * vox_word, sizeof sv);
+    if (st.key_range | st.table_full | st.pad[0]) LIMU_CUDA_TRY(cudaMemsetAsync(res_update_status(o->res.as<int>(), upd_par), 0, sizeof(DevStatus), o->ctx->stream));   // (the next frame kernel is launched after this)
+    st.key_range |= sv.key_range; st.table_full |= sv.table_full;
+    if (st.key_range) { set_error("voxel index outside the packed key range (|index| >= 2^20) or NaN coordinate: the frame was registered without those points"); return LIMU_ERR_KEY_RANGE; }
+    if (st.table_full) { set_error("voxel hash table full"); return LIMU_ERR_MAP_FULL; }
+    return LIMU_OK;
+}
+
+// Copy this scan's clouds to the caller. `side`: the main stream is busy with later work, use the copy stream (what the copies read is complete).
+static int odom_copy_clouds(limu_odom *o, bool side, int par, int64_t nd, int64_t nk, double *down_xyz, double *keypoints_xyz) {
+    limu_ctx *c = o->ctx;
+    if (!((down_xyz && nd > 0) || (keypoints_xyz && nk > 0))) return LIMU_OK;
+    cudaStream_t s = c->stream;
+    if (side) { LIMU_TRY(odom_side_stream(o)); s = o->copy_stream; }
+    if (down_xyz && nd > 0) LIMU_CUDA_TRY(cudaMemcpyAsync(down_xyz, o->down[par].p, (size_t)nd * 24, cudaMemcpyDeviceToHost, s));
+    if (keypoints_xyz && nk > 0) LIMU_CUDA_TRY(cudaMemcpyAsync(keypoints_xyz, o->src[par].p, (size_t)nk * 24, cudaMemcpyDeviceToHost, s));
+    if (side) {
+        LIMU_CUDA_TRY(cudaEventRecord(o->clouds_done, s));
+        LIMU_CUDA_TRY(cudaEventSynchronize(o->clouds_done));
+    } else {
+        LIMU_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return LIMU_OK;
+}
+
+// Plain path: everything of one scan enqueued on the context's stream, one synchronisation, nothing left in flight.
 // Input already in device memory. mode 0: float4 {x,y,z,t}; 1: records `stride` bytes apart + FP64 timestamps; 2: double xyz.
 static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int stride, const double *ts_dev, int64_t n, double pose_out[7], double *down_xyz,
                                 int64_t *n_down, double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
     limu_ctx *c = o->ctx;
+    LIMU_TRY(odom_drop_ahead(o, false));
+    o->hint_ptr = nullptr; o->hint_n = 0;
     // deskew gate (icp.cpp:40-46): config.deskew && poses.size() > 2; twist = delta_pose(poses[N-2], poses[N-1]) (deskew.cpp:14)
     const size_t NP = o->poses.size();
     const int deskewed = (mode != 2 && o->cfg.deskew && NP > 2) ? 1 : 0;
     double twist[6] = {0, 0, 0, 0, 0, 0};
     if (deskewed) se3_log(mul(inverse(o->poses[NP - 2]), o->poses[NP - 1]), twist);
-    // was this scan's k_voxelize already enqueued behind the previous scan? Its outputs live in frame / src0 / the other `down` buffer:
-    // growing those buffers for a larger hinted scan must then keep their contents.
-    const bool spec_hit = mode == 0 && n > 0 && o->spec_ptr && raw_dev == o->spec_ptr && n == o->spec_n && o->spec_deskewed == deskewed;
-    if (o->spec_ptr && !spec_hit && o->spec_slot >= 0 && o->pf_buf[o->spec_slot].p == o->spec_ptr) {
-        // the caller registered something else than the scan it had prefetched: that upload is stale, do not speculate on it again
-        o->pf_host[o->spec_slot] = nullptr; o->pf_n[o->spec_slot] = -1;
-    }
-    o->spec_ptr = nullptr; o->spec_slot = -1;
-    if (spec_hit) o->down_cur ^= 1;   // the speculative launch wrote the other `down` buffer
-    // the scan after this one, if the caller told us where it is: a device-pointer hint, or the OLDEST upload limu_odom_prefetch has pending
-    const void *next_ptr = nullptr;
-    int64_t next_n = 0;
-    int next_slot = -1;
-    cudaEvent_t next_ready = nullptr;
-    if (o->speculate && mode == 0) {
-        if (o->hint_ptr) { next_ptr = o->hint_ptr; next_n = o->hint_n; }
-        else {
-            for (int sl = 0; sl < 2; ++sl)
-                if (o->pf_host[sl] && o->pf_n[sl] > 0 && (next_slot < 0 || o->pf_seq[sl] < o->pf_seq[next_slot])) next_slot = sl;
-            if (next_slot >= 0) { next_ptr = o->pf_buf[next_slot].p; next_n = o->pf_n[next_slot]; next_ready = o->pf_done[next_slot]; }
-        }
-    }
-    o->hint_ptr = nullptr; o->hint_n = 0;   // a hint is good for one call only
-    const size_t nb = (size_t)std::max<int64_t>(std::max<int64_t>(n, next_n), 1) * 24;
-    const bool keep = spec_hit;
-    if (o->speculate || o->down_cur) LIMU_TRY(o->down_alt.reserve(nb, c->stream, keep));
-    limu::DevBuf &down_mine = o->down_cur ? o->down_alt : o->down, &down_other = o->down_cur ? o->down : o->down_alt;
-    LIMU_TRY(o->frame.reserve(nb, c->stream, keep));
-    LIMU_TRY(o->down.reserve(nb, c->stream, keep));
-    LIMU_TRY(o->src0.reserve(nb, c->stream, keep));
-    LIMU_TRY(o->src.reserve(nb, c->stream));
+    const int par = o->par ^ 1;
+    const size_t nb = (size_t)std::max<int64_t>(n, 1) * 24;
+    LIMU_TRY(o->frame.reserve(nb, c->stream));
+    LIMU_TRY(o->down[par].reserve(nb, c->stream));
+    LIMU_TRY(o->src0[par].reserve(nb, c->stream));
+    LIMU_TRY(o->src[par].reserve(nb, c->stream));
     LIMU_TRY(o->work.reserve(nb, c->stream));
     LIMU_TRY(o->world.reserve(nb, c->stream));
     const int rows = icp_partial_rows(c);
@@ -178,27 +257,19 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
         LIMU_TRY(o->partials.reserve((size_t)2 * rows * 32 * 16 + 256, c->stream));
         if (o->partials.p != before) LIMU_CUDA_TRY(cudaMemsetAsync(o->partials.p, 0, o->partials.bytes, c->stream));
     }
-    // Per-HANDLE result block in device memory (two handles of one context may interleave their scans, and a speculative launch of one
-    // must not land in the other's counts): 16 ints -- [0]=n_down [1]=n_src0 [2]=n_keypoints, [4..7] / [8..11] = the two status words
-    // k_voxelize alternates between (its own words, so that a speculative launch is never blamed on the scan before it), [12..15] = the
-    // frame kernel's status word -- then pose + loop statistics (13 doubles). ONE copy per scan.
-    if (!o->res.p) {
-        LIMU_TRY(o->res.reserve(32 * sizeof(double)));
-        LIMU_CUDA_TRY(cudaMemsetAsync(o->res.p, 0, o->res.bytes, c->stream));
-    }
+    LIMU_TRY(odom_res_block(o));
     int *cnt = o->res.as<int>();
-    DevStatus *vox_status = reinterpret_cast<DevStatus *>(cnt + 4);
-    DevStatus *frame_status = reinterpret_cast<DevStatus *>(cnt + 12);
-    double *out13 = o->res.as<double>() + 8;
+    int *counts = res_counts(cnt, par);
+    DevStatus *vox_status = reinterpret_cast<DevStatus *>(cnt + RES_VOX_ST);
+    double *out13 = o->res.as<double>() + RES_OUT;
     const double v = o->cfg.voxel_size;
 
     // deskew_scan + voxelize's two downsampling stages (icp.cpp:36-47, :126-131): one cooperative launch
-    if (!spec_hit) {
-        LIMU_TRY(prof_begin(c, LIMU_STAGE_DOWNSAMPLE));
-        LIMU_TRY(voxelize_device(c, o->vx, raw_dev, mode, stride, ts_dev, deskewed, twist, n, v, o->frame.as<double>(), down_mine.as<double>(), o->src0.as<double>(), cnt + 0,
-                                 nullptr, vox_status, &o->vox_word));
-        LIMU_TRY(prof_end(c, LIMU_STAGE_DOWNSAMPLE));
-    }
+    int vox_word = 0;
+    LIMU_TRY(prof_begin(c, LIMU_STAGE_DOWNSAMPLE));
+    LIMU_TRY(voxelize_device(c, o->vx, raw_dev, mode, stride, ts_dev, deskewed, twist, n, v, o->frame.as<double>(), o->down[par].as<double>(), o->src0[par].as<double>(), counts,
+                             nullptr, vox_status, &vox_word));
+    LIMU_TRY(prof_end(c, LIMU_STAGE_DOWNSAMPLE));
     // host scalar glue (icp.cpp:66-71)
     const double sigma = odom_adaptive_threshold(o);
     const Pose pred = odom_prediction(o);
@@ -213,64 +284,27 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     LIMU_TRY(o->map->pslot.reserve((size_t)std::max<int64_t>(n, 1) * 4, c->stream));
     LIMU_TRY(o->d2.reserve((size_t)std::max<int64_t>(n, 1) * 8, c->stream));
     FrameFusion fuse;
-    fuse.iqr_in = o->src0.as<double>(); fuse.iqr_n = cnt + 1; fuse.iqr_d2 = o->d2.as<double>(); fuse.iqr_out = o->src.as<double>(); fuse.iqr_count = cnt + 2;
-    fuse.upd_down = down_mine.as<double>(); fuse.upd_n = cnt + 0; fuse.upd_world = o->world.as<double>(); fuse.upd_pslot = o->map->pslot.as<unsigned int>();
+    memset(&fuse, 0, sizeof fuse);
+    fuse.iqr_in = o->src0[par].as<double>(); fuse.iqr_n = counts + 1; fuse.iqr_d2 = o->d2.as<double>(); fuse.iqr_out = o->src[par].as<double>(); fuse.iqr_count = cnt + 2;
+    fuse.upd_down = o->down[par].as<double>(); fuse.upd_n = counts + 0; fuse.upd_world = o->world.as<double>(); fuse.upd_pslot = o->map->pslot.as<unsigned int>();
     fuse.upd_birth_base = o->map->birth_base;
-    const bool speculate = next_ptr && next_n > 0;
-    const int next_deskew = (o->cfg.deskew && NP + 1 > 2) ? 1 : 0;   // the gate of icp.cpp:40-46 as the next scan will see it
-    fuse.twist_out = nullptr;
     fuse.allow_cluster = o->cluster_loop ? 1 : 0;
-    fuse.status = frame_status;
+    fuse.status = res_update_status(cnt, par);
     pose_store(last, fuse.last_pose);
-    if (speculate && next_deskew) {
-        LIMU_TRY(o->twist_next.reserve(6 * sizeof(double), c->stream));
-        fuse.twist_out = o->twist_next.as<double>();
-    }
     const int64_t upper_before = o->map->used_upper;
-    LIMU_TRY(icp_device(o->map, o->src.as<double>(), o->work.as<double>(), n, cnt + 2, init7, 3.0 * sigma, sigma / 3.0, o->cfg.icp_max_iteration,
+    LIMU_TRY(icp_device(o->map, o->src[par].as<double>(), o->work.as<double>(), n, cnt + 2, init7, 3.0 * sigma, sigma / 3.0, o->cfg.icp_max_iteration,
                         o->cfg.estimation_threshold, o->partials.as<double>(), (size_t)rows, out13, o->nk_hint, nullptr, nullptr, nullptr, -1, &fuse, o->cfg.icp_mode));
     o->map->birth_base += (uint64_t)n;
     o->map->used_upper = upper_before + std::max<int64_t>(n, 0);   // safe bound until the exact count arrives (at most one new voxel per point)
 
     // the one synchronisation of the scan
     double *h = static_cast<double *>(c->h_pinned) + 32;
-    const int my_vox_word = o->vox_word;   // the status word of THIS scan's k_voxelize (a speculative launch below moves on to the other one)
-    LIMU_CUDA_TRY(cudaMemcpyAsync(h, o->res.p, (8 + 13) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    // device time of the speculative launch that prepared THIS scan (recorded one call ago into the event pair `spec_par`): read after this
-    // scan's sync, when it is certainly complete; the launch made below uses the other pair
-    const int acct = o->spec_timed ? o->spec_par : -1;
-    o->spec_timed = false;
-    if (speculate) {
-        if (!o->frame_done) {
-            LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->frame_done, cudaEventDisableTiming));
-            LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->spec_launched, cudaEventDisableTiming));
-            for (int k = 0; k < 4; ++k) LIMU_CUDA_TRY(cudaEventCreate(&o->spec_ev[k >> 1][k & 1]));
-        }
-        LIMU_CUDA_TRY(cudaEventRecord(o->frame_done, c->stream));
-        // stream order: frame kernel (writes twist_next) -> result copy -> [upload of the next scan done] -> k_voxelize of the next scan
-        // (reads twist_next; overwrites frame, src0, the counts and its status word -- dead for this scan -- and the OTHER `down` buffer)
-        if (next_ready) LIMU_CUDA_TRY(cudaStreamWaitEvent(c->stream, next_ready, 0));
-        const int par = o->spec_par ^ 1;
-        if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->spec_ev[par][0], c->stream));
-        LIMU_TRY(voxelize_device(c, o->vx, next_ptr, 0, 0, nullptr, next_deskew, nullptr, next_n, v, o->frame.as<double>(), down_other.as<double>(),
-                                 o->src0.as<double>(), cnt + 0, next_deskew ? o->twist_next.as<double>() : nullptr, vox_status, &o->vox_word));
-        if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->spec_ev[par][1], c->stream)); o->spec_timed = true; o->spec_par = par; }
-        LIMU_CUDA_TRY(cudaEventRecord(o->spec_launched, c->stream));
-        o->spec_ptr = next_ptr; o->spec_n = next_n; o->spec_deskewed = next_deskew; o->spec_slot = next_slot;
-        LIMU_CUDA_TRY(cudaEventSynchronize(o->frame_done));   // wakes up when the frame kernel and the copy are done; k_voxelize keeps running
-    } else {
-        LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    }
-    if (acct >= 0 && c->profiling) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, o->spec_ev[acct][0], o->spec_ev[acct][1]) == cudaSuccess) c->stage_ms[LIMU_STAGE_DOWNSAMPLE] += (double)ms;
-        else (void)cudaGetLastError();
-    }
+    LIMU_CUDA_TRY(cudaMemcpyAsync(h, o->res.p, RES_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
     LIMU_TRY(prof_collect(c));
     const int *hc = reinterpret_cast<const int *>(h);
-    const int64_t nd = hc[0], nk = hc[2];
-    const double *ho = h + 8;
-    const Pose new_pose = pose_load(ho);
+    const int64_t nd = res_counts(const_cast<int *>(hc), par)[0], nk = hc[2];
+    const Pose new_pose = pose_load(h + RES_OUT);
     // Commit the whole frame -- map bookkeeping, pose history, threshold state -- BEFORE looking at the device status: the frame kernel
     // has already inserted this scan into the map (points with out-of-range voxel indices were left out by both downsampling and the
     // insert), so an error return must not leave a map that holds a scan without a pose.
@@ -279,46 +313,218 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     o->nd_hint = std::max<int64_t>(nd, 256);
     o->model_deviation = mul(inverse(init), new_pose);   // icp.cpp:78-79
     o->poses.push_back(new_pose);                        // :82
+    o->par = par;
     if (pose_out) pose_store(new_pose, pose_out);
     if (n_down) *n_down = nd;
     if (n_keypoints) *n_keypoints = nk;
-    bool copied = false;
-    cudaStream_t cloud_stream = c->stream;
-    if (speculate && ((down_xyz && nd > 0) || (keypoints_xyz && nk > 0))) {
-        // the main stream is busy with the next scan's k_voxelize: this scan's clouds leave on the copy stream (everything they read was
-        // complete at frame_done, and nothing in flight writes it)
-        LIMU_TRY(odom_side_stream(o));
-        if (!o->clouds_done) LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->clouds_done, cudaEventDisableTiming));
-        cloud_stream = o->copy_stream;
+    LIMU_TRY(odom_copy_clouds(o, false, par, nd, nk, down_xyz, keypoints_xyz));
+    const int deferred = odom_deferred_status(o, hc);   // (an update of the pipelined path that nobody has asked about yet)
+    LIMU_TRY(odom_report(o, hc, vox_word, par, false, n, deskewed, sigma, stats));
+    return deferred;
+}
+
+static int odom_pipe_init(limu_odom *o) {
+    if (o->vox_stream) return LIMU_OK;
+    LIMU_CUDA_TRY(cudaStreamCreateWithFlags(&o->vox_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->vox_done[k], cudaEventDisableTiming));
+        LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->loop_done[k], cudaEventDisableTiming));
+        LIMU_CUDA_TRY(cudaEventCreate(&o->pev_vox[k][0]));
+        LIMU_CUDA_TRY(cudaEventCreate(&o->pev_vox[k][1]));
+        LIMU_CUDA_TRY(cudaEventCreate(&o->pev_upd[k][0]));
+        LIMU_CUDA_TRY(cudaEventCreate(&o->pev_upd[k][1]));
+        LIMU_CUDA_TRY(cudaMallocHost(&o->h_res[k], 32 * sizeof(double)));
     }
-    if (down_xyz && nd > 0) { LIMU_CUDA_TRY(cudaMemcpyAsync(down_xyz, down_mine.p, (size_t)nd * 24, cudaMemcpyDeviceToHost, cloud_stream)); copied = true; }
-    if (keypoints_xyz && nk > 0) { LIMU_CUDA_TRY(cudaMemcpyAsync(keypoints_xyz, o->src.p, (size_t)nk * 24, cudaMemcpyDeviceToHost, cloud_stream)); copied = true; }
-    if (copied) {
-        if (cloud_stream != c->stream) {
-            LIMU_CUDA_TRY(cudaEventRecord(o->clouds_done, cloud_stream));
-            LIMU_CUDA_TRY(cudaEventSynchronize(o->clouds_done));
-        } else {
-            LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return odom_side_stream(o);
+}
+
+// The IQR + Gauss-Newton half of a frame as a launch of its own (no map update): result block -> h_res[par], loop_done[par] recorded behind it.
+static int odom_launch_loop(limu_odom *o, int par, int64_t n, const Pose &init, const Pose &last, double sigma, bool wait_vox) {
+    limu_ctx *c = o->ctx;
+    const size_t nb = (size_t)std::max<int64_t>(n, 1) * 24;
+    LIMU_TRY(o->src[par].reserve(nb, c->stream));
+    LIMU_TRY(o->work.reserve(nb, c->stream));
+    LIMU_TRY(o->d2.reserve((size_t)std::max<int64_t>(n, 1) * 8, c->stream));
+    LIMU_TRY(o->twist_next.reserve(6 * sizeof(double), c->stream));
+    const int rows = icp_partial_rows(c);
+    {
+        const void *before = o->partials.p;
+        LIMU_TRY(o->partials.reserve((size_t)2 * rows * 32 * 16 + 256, c->stream));
+        if (o->partials.p != before) LIMU_CUDA_TRY(cudaMemsetAsync(o->partials.p, 0, o->partials.bytes, c->stream));
+    }
+    int *cnt = o->res.as<int>();
+    int *counts = res_counts(cnt, par);
+    FrameFusion fuse;
+    memset(&fuse, 0, sizeof fuse);
+    fuse.iqr_in = o->src0[par].as<double>(); fuse.iqr_n = counts + 1; fuse.iqr_d2 = o->d2.as<double>(); fuse.iqr_out = o->src[par].as<double>(); fuse.iqr_count = cnt + 2;
+    fuse.twist_out = o->twist_next.as<double>();
+    fuse.loop_flag = reinterpret_cast<unsigned int *>(cnt + RES_FLAG);
+    fuse.loop_seq = ++o->loop_seq;
+    pose_store(last, fuse.last_pose);
+    double init7[7];
+    pose_store(init, init7);
+    if (wait_vox) LIMU_CUDA_TRY(cudaStreamWaitEvent(c->stream, o->vox_done[par], 0));
+    LIMU_TRY(icp_device(o->map, o->src[par].as<double>(), o->work.as<double>(), n, cnt + 2, init7, 3.0 * sigma, sigma / 3.0, o->cfg.icp_max_iteration,
+                        o->cfg.estimation_threshold, o->partials.as<double>(), (size_t)rows, o->res.as<double>() + RES_OUT, o->nk_hint, nullptr, nullptr, nullptr, -1, &fuse,
+                        o->cfg.icp_mode));
+    LIMU_CUDA_TRY(cudaMemcpyAsync(o->h_res[par], o->res.p, RES_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LIMU_CUDA_TRY(cudaEventRecord(o->loop_done[par], c->stream));
+    return LIMU_OK;
+}
+
+// Pipelined path (see limu_odom): packed float4 scan in device memory.
+static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down, double *keypoints_xyz,
+                                   int64_t *n_keypoints, limu_frame_stats *stats) {
+    limu_ctx *c = o->ctx;
+    LIMU_TRY(odom_pipe_init(o));
+    LIMU_TRY(odom_res_block(o));
+    limu_odom::Ahead &ah = o->ahead;
+    const size_t NP = o->poses.size();
+    const int deskewed = (o->cfg.deskew && NP > 2) ? 1 : 0;   // deskew gate (icp.cpp:40-46)
+    const int par = o->par ^ 1;
+    const bool hit_vox = ah.vox && n > 0 && raw_dev == ah.ptr && n == ah.n && ah.deskewed == deskewed && ah.par == par;
+    const bool hit_loop = hit_vox && ah.loop && ah.map_mutations == o->map->mutations;
+    if (ah.vox && !hit_vox && ah.slot >= 0 && o->pf_buf[ah.slot].p == ah.ptr) {
+        // the caller registered something else than the scan it had prefetched: that upload is stale, do not prepare it again
+        o->pf_host[ah.slot] = nullptr; o->pf_n[ah.slot] = -1;
+    }
+    // the scan after this one, if the caller told us where it is: a device-pointer hint, or the OLDEST upload limu_odom_prefetch has pending
+    const void *next_ptr = nullptr;
+    int64_t next_n = 0;
+    int next_slot = -1;
+    cudaEvent_t next_ready = nullptr;
+    if (o->hint_ptr) { next_ptr = o->hint_ptr; next_n = o->hint_n; }
+    else {
+        for (int sl = 0; sl < 2; ++sl)
+            if (o->pf_host[sl] && o->pf_n[sl] > 0 && o->pf_buf[sl].p != raw_dev && (next_slot < 0 || o->pf_seq[sl] < o->pf_seq[next_slot])) next_slot = sl;
+        if (next_slot >= 0) { next_ptr = o->pf_buf[next_slot].p; next_n = o->pf_n[next_slot]; next_ready = o->pf_done[next_slot]; }
+    }
+    o->hint_ptr = nullptr; o->hint_n = 0;   // a hint is good for one call only
+    int *cnt = o->res.as<int>();
+    DevStatus *vox_status = reinterpret_cast<DevStatus *>(cnt + RES_VOX_ST);
+    const double v = o->cfg.voxel_size;
+    const Pose last = o->poses.empty() ? pose_identity() : o->poses.back();
+
+    // 1. this scan's k_voxelize, unless it ran ahead
+    int vox_word = ah.vox_word;
+    if (!hit_vox) {
+        LIMU_TRY(odom_drop_ahead(o, false));
+        double twist[6] = {0, 0, 0, 0, 0, 0};
+        if (deskewed) se3_log(mul(inverse(o->poses[NP - 2]), o->poses[NP - 1]), twist);
+        const size_t nb = (size_t)std::max<int64_t>(n, 1) * 24;
+        LIMU_TRY(o->frame.reserve(nb, c->stream));
+        LIMU_TRY(o->down[par].reserve(nb, c->stream));
+        LIMU_TRY(o->src0[par].reserve(nb, c->stream));
+        LIMU_TRY(prof_begin(c, LIMU_STAGE_DOWNSAMPLE));
+        LIMU_TRY(voxelize_device(c, o->vx, raw_dev, 0, 0, nullptr, deskewed, twist, n, v, o->frame.as<double>(), o->down[par].as<double>(), o->src0[par].as<double>(),
+                                 res_counts(cnt, par), nullptr, vox_status, &vox_word));
+        LIMU_TRY(prof_end(c, LIMU_STAGE_DOWNSAMPLE));
+    }
+    // 2. its loop, unless that ran ahead too (with exactly the glue this call would compute)
+    double sigma;
+    Pose init;
+    if (hit_loop) {
+        sigma = ah.sigma; init = ah.init;
+        ah.loop = false;   // consumed: the threshold sample it added stays
+    } else {
+        LIMU_TRY(odom_drop_ahead(o, true));
+        sigma = odom_adaptive_threshold(o);              // host scalar glue (icp.cpp:66-71)
+        init = mul(last, odom_prediction(o));
+        LIMU_TRY(odom_launch_loop(o, par, n, init, last, sigma, hit_vox));
+    }
+    const unsigned int my_seq = o->loop_seq;
+    ah.vox = false; ah.ptr = nullptr; ah.slot = -1;
+    // 3. its map update: the caller has registered this scan, so it goes in right behind the loop (local_map.update, icp.cpp:81)
+    LIMU_TRY(map_maybe_grow(o->map, n));
+    LIMU_TRY(o->map->pslot.reserve((size_t)std::max<int64_t>(n, 1) * 4, c->stream));
+    LIMU_TRY(o->world.reserve((size_t)std::max<int64_t>(n, 1) * 24, c->stream));
+    {
+        FrameFusion fuse;
+        memset(&fuse, 0, sizeof fuse);
+        fuse.upd_down = o->down[par].as<double>(); fuse.upd_n = res_counts(cnt, par); fuse.upd_world = o->world.as<double>(); fuse.upd_pslot = o->map->pslot.as<unsigned int>();
+        fuse.upd_birth_base = o->map->birth_base;
+        fuse.status = res_update_status(cnt, par);
+        if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->pev_upd[par][0], c->stream));
+        LIMU_TRY(frame_update_device(o->map, fuse, o->res.as<double>() + RES_OUT));
+        if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->pev_upd[par][1], c->stream)); o->pev_upd_used[par] = true; }
+    }
+    const int64_t upper_before = o->map->used_upper;
+    o->map->birth_base += (uint64_t)n;
+    o->map->used_upper = upper_before + std::max<int64_t>(n, 0);   // safe bound until the exact count arrives (at most one new voxel per point)
+    // 4. the next scan's k_voxelize on its own stream, released by this scan's loop (its deskew twist is log(last^-1 * new), deskew.cpp:14)
+    const int npar = par ^ 1;
+    const int next_deskew = (o->cfg.deskew && NP + 1 > 2) ? 1 : 0;   // the gate of icp.cpp:40-46 as the next scan will see it
+    if (next_ptr && next_n > 0) {
+        const size_t nb = (size_t)next_n * 24;
+        LIMU_TRY(o->frame.reserve(nb, o->vox_stream));
+        LIMU_TRY(o->down[npar].reserve(nb, o->vox_stream));
+        LIMU_TRY(o->src0[npar].reserve(nb, o->vox_stream));
+        if (next_ready) LIMU_CUDA_TRY(cudaStreamWaitEvent(o->vox_stream, next_ready, 0));
+        LIMU_TRY(gate_device(o->vox_stream, reinterpret_cast<unsigned int *>(cnt + RES_FLAG), my_seq));
+        int w = 0;
+        if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->pev_vox[npar][0], o->vox_stream));   // (behind the gate: the kernel's own time)
+        LIMU_TRY(voxelize_device(c, o->vx, next_ptr, 0, 0, nullptr, next_deskew, nullptr, next_n, v, o->frame.as<double>(), o->down[npar].as<double>(), o->src0[npar].as<double>(),
+                                 res_counts(cnt, npar), next_deskew ? o->twist_next.as<double>() : nullptr, vox_status, &w, o->vox_stream, true));
+        if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->pev_vox[npar][1], o->vox_stream)); o->pev_vox_used[npar] = true; }
+        LIMU_CUDA_TRY(cudaEventRecord(o->vox_done[npar], o->vox_stream));
+        ah.vox = true; ah.ptr = next_ptr; ah.n = next_n; ah.deskewed = next_deskew; ah.slot = next_slot; ah.par = npar; ah.vox_word = w;
+    }
+    // 5. the one wait of the call: this scan's pose
+    LIMU_CUDA_TRY(cudaEventSynchronize(o->loop_done[par]));
+    LIMU_TRY(prof_collect(c));
+    if (c->profiling) {
+        float ms = 0.f;
+        if (o->pev_vox_used[par]) {   // the gated launch that prepared THIS scan
+            if (hit_vox && cudaEventElapsedTime(&ms, o->pev_vox[par][0], o->pev_vox[par][1]) == cudaSuccess) c->stage_ms[LIMU_STAGE_DOWNSAMPLE] += (double)ms; else (void)cudaGetLastError();
+            o->pev_vox_used[par] = false;
+        }
+        if (o->pev_upd_used[npar]) {   // the previous scan's map update (in front of this scan's loop on the main stream)
+            if (cudaEventElapsedTime(&ms, o->pev_upd[npar][0], o->pev_upd[npar][1]) == cudaSuccess) c->stage_ms[LIMU_STAGE_MAP_UPDATE] += (double)ms; else (void)cudaGetLastError();
+            o->pev_upd_used[npar] = false;
         }
     }
-    if (stats) {
-        stats->n_points = n; stats->n_down = nd; stats->n_keypoints = nk; stats->sigma = sigma; stats->deskewed = deskewed; stats->reserved0 = spec_hit ? 1 : 0;
-        stats->icp.iterations = (int)ho[7]; stats->icp.converged = (int)ho[8]; stats->icp.last_ncorr = (int64_t)ho[9];
-        stats->icp.mean_candidates = nk > 0 ? ho[10] / (double)nk : 0.0;
-        stats->icp.miss_fraction = nk > 0 ? ho[11] / (double)nk : 0.0;
+    const double *h = o->h_res[par];
+    const int *hc = reinterpret_cast<const int *>(h);
+    const int64_t nd = res_counts(const_cast<int *>(hc), par)[0], nk = hc[2];
+    const Pose new_pose = pose_load(h + RES_OUT);
+    // commit the frame (map bookkeeping, pose history, threshold state) before looking at any status
+    o->map->used_upper = upper_before + nd;   // exact: at most one new voxel per inserted point
+    o->nk_hint = std::max<int64_t>(nk, 256);
+    o->nd_hint = std::max<int64_t>(nd, 256);
+    o->model_deviation = mul(inverse(init), new_pose);   // icp.cpp:78-79
+    o->poses.push_back(new_pose);                        // :82
+    o->par = par;
+    if (pose_out) pose_store(new_pose, pose_out);
+    if (n_down) *n_down = nd;
+    if (n_keypoints) *n_keypoints = nk;
+    const int deferred = odom_deferred_status(o, hc);   // the previous scan's map update ran in front of this scan's loop
+    o->pending_update_par = par;
+    // 6. the next scan's loop, ahead of the caller asking for it: it only reads the map (behind this scan's update in stream order)
+    if (ah.vox) {
+        ah.stash_model_error_sq = o->model_error_sq; ah.stash_num_samples = o->num_samples;
+        ah.sigma = odom_adaptive_threshold(o);
+        ah.init = mul(new_pose, odom_prediction(o));
+        ah.map_mutations = o->map->mutations;
+        ah.loop = true;
+        const int st = odom_launch_loop(o, npar, ah.n, ah.init, new_pose, ah.sigma, true);
+        if (st != LIMU_OK) { (void)odom_drop_ahead(o, true); return st; }
     }
-    {   // device status of this scan: its own k_voxelize word and the frame kernel's word (insert)
-        DevStatus st, sv;
-        memcpy(&st, hc + 12, sizeof st);
-        memcpy(&sv, hc + 4 + 4 * my_vox_word, sizeof sv);
-        if (st.key_range | st.table_full | st.pad[0]) LIMU_CUDA_TRY(cudaMemsetAsync(frame_status, 0, sizeof(DevStatus), c->stream));   // (the next frame kernel is launched after this)
-        st.key_range |= sv.key_range; st.table_full |= sv.table_full;
-        DevStatus none = {0, 0, {0, 0}};
-        (void)none;
-        if (st.key_range) { set_error("voxel index outside the packed key range (|index| >= 2^20) or NaN coordinate: the frame was registered without those points"); return LIMU_ERR_KEY_RANGE; }
-        if (st.table_full) { set_error("voxel hash table full"); return LIMU_ERR_MAP_FULL; }
-    }
-    return LIMU_OK;
+    // 7. this scan's clouds (complete since its loop ended; the main stream is busy with later work)
+    LIMU_TRY(odom_copy_clouds(o, true, par, nd, nk, down_xyz, keypoints_xyz));
+    LIMU_TRY(odom_report(o, hc, vox_word, -1, hit_vox, n, deskewed, sigma, stats));
+    return deferred;
+}
+
+// Wait for everything the handle has in flight and report what a deferred map update had to say.
+static int odom_flush(limu_odom *o) {
+    limu_ctx *c = o->ctx;
+    LIMU_TRY(odom_drop_ahead(o, false));
+    LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (o->pending_update_par < 0 || !o->res.p) return LIMU_OK;
+    double *h = static_cast<double *>(c->h_pinned) + 32;
+    LIMU_CUDA_TRY(cudaMemcpyAsync(h, o->res.p, RES_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return odom_deferred_status(o, reinterpret_cast<const int *>(h));
 }
 
 extern "C" {
@@ -360,16 +566,23 @@ int limu_odom_create(limu_ctx *c, const limu_odom_config *cfg, limu_odom **out) 
 void limu_odom_destroy(limu_odom *o) {
     if (!o) return;
     cudaSetDevice(o->ctx->device);
+    if (o->vox_stream) cudaStreamSynchronize(o->vox_stream);
     cudaStreamSynchronize(o->ctx->stream);
     limu_map_destroy(o->map);
     if (o->copy_stream) { cudaStreamSynchronize(o->copy_stream); cudaStreamDestroy(o->copy_stream); cudaEventDestroy(o->pf_done[0]); cudaEventDestroy(o->pf_done[1]); }
-    DevBuf *bufs[] = {&o->res, &o->pf_buf[0], &o->pf_buf[1], &o->d2, &o->raw, &o->ts, &o->frame, &o->down, &o->src0, &o->src, &o->work, &o->world, &o->partials};
+    DevBuf *bufs[] = {&o->res, &o->pf_buf[0], &o->pf_buf[1], &o->d2, &o->raw, &o->ts, &o->frame, &o->down[0], &o->down[1], &o->src0[0], &o->src0[1], &o->src[0], &o->src[1],
+                      &o->work, &o->world, &o->partials, &o->twist_next};
     for (auto *b : bufs) b->release();
     o->vx.release();
     o->pre.release();
-    o->twist_next.release();
-    o->down_alt.release();
-    if (o->frame_done) { cudaEventDestroy(o->frame_done); cudaEventDestroy(o->spec_launched); for (int k = 0; k < 4; ++k) cudaEventDestroy(o->spec_ev[k >> 1][k & 1]); }
+    if (o->vox_stream) {
+        cudaStreamDestroy(o->vox_stream);
+        for (int k = 0; k < 2; ++k) {
+            cudaEventDestroy(o->vox_done[k]); cudaEventDestroy(o->loop_done[k]);
+            cudaEventDestroy(o->pev_vox[k][0]); cudaEventDestroy(o->pev_vox[k][1]); cudaEventDestroy(o->pev_upd[k][0]); cudaEventDestroy(o->pev_upd[k][1]);
+            cudaFreeHost(o->h_res[k]);
+        }
+    }
     if (o->clouds_done) cudaEventDestroy(o->clouds_done);
     delete o;
 }
@@ -380,19 +593,22 @@ int limu_odom_register_frame(limu_odom *o, const float *xyzt, int64_t n, double 
     LIMU_TRY(bind(o->ctx));
     int hit = -1;
     for (int s = 0; s < 2; ++s) if (n > 0 && o->pf_host[s] == xyzt && o->pf_n[s] == n) hit = s;
-    if (hit >= 0 && o->spec_ptr && o->spec_ptr == o->pf_buf[hit].p && o->spec_n == n) {
-        // uploaded ahead of time AND already through k_voxelize (enqueued behind the previous scan): register it where it lies
+    const void *dev = nullptr;
+    if (hit >= 0 && o->speculate && o->ahead.vox && o->ahead.ptr == o->pf_buf[hit].p && o->ahead.n == n) {
+        // uploaded ahead of time AND already through k_voxelize (released by the previous scan's loop): register it where it lies
         o->pf_host[hit] = nullptr; o->pf_n[hit] = -1;
-        return odom_register_device(o, o->pf_buf[hit].p, 0, 0, nullptr, n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
-    }
-    if (hit >= 0) {   // uploaded ahead of time by limu_odom_prefetch
+        dev = o->pf_buf[hit].p;
+    } else if (hit >= 0) {   // uploaded ahead of time by limu_odom_prefetch
         LIMU_CUDA_TRY(cudaStreamWaitEvent(o->ctx->stream, o->pf_done[hit], 0));
         std::swap(o->raw, o->pf_buf[hit]);
         o->pf_host[hit] = nullptr; o->pf_n[hit] = -1;
+        dev = o->raw.p;
     } else {
         LIMU_TRY(stage_in(o->ctx, o->raw, xyzt, (size_t)n * 16));
+        dev = o->raw.p;
     }
-    return odom_register_device(o, o->raw.p, 0, 0, nullptr, n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+    if (o->speculate) return odom_register_pipelined(o, dev, n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+    return odom_register_device(o, dev, 0, 0, nullptr, n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
 }
 
 int limu_odom_prefetch(limu_odom *o, const float *xyzt, int64_t n) {
@@ -403,11 +619,11 @@ int limu_odom_prefetch(limu_odom *o, const float *xyzt, int64_t n) {
     for (int s = 0; s < 2; ++s) if (o->pf_host[s] == xyzt && o->pf_n[s] == n) return LIMU_OK;   // already in flight
     // a free slot, else the OLDEST pending upload is given up (its scan was evidently never registered)
     int s = o->pf_host[0] == nullptr ? 0 : (o->pf_host[1] == nullptr ? 1 : (o->pf_seq[0] < o->pf_seq[1] ? 0 : 1));
-    if (o->spec_ptr && o->pf_buf[s].p == o->spec_ptr) {
-        // the speculative k_voxelize of the scan in this slot may still be reading it on the main stream: let it finish, and forget the
-        // speculation (the slot is about to hold a different scan, possibly of the same size)
-        LIMU_CUDA_TRY(cudaEventSynchronize(o->spec_launched));
-        o->spec_ptr = nullptr; o->spec_slot = -1;
+    if (o->ahead.vox && o->pf_buf[s].p == o->ahead.ptr) {
+        // the k_voxelize that ran ahead on the scan in this slot may still be reading it: let it finish, and forget what was prepared (the
+        // slot is about to hold a different scan, possibly of the same size)
+        LIMU_CUDA_TRY(cudaEventSynchronize(o->vox_done[o->ahead.par]));
+        LIMU_TRY(odom_drop_ahead(o, false));
     }
     o->pf_host[s] = nullptr; o->pf_n[s] = -1;
     if (o->pf_buf[s].bytes < (size_t)n * 16) {   // growing may free a buffer the copy stream still writes: drain it first
@@ -432,6 +648,7 @@ int limu_odom_register_cloud(limu_odom *o, const void *points, int32_t stride_by
 int limu_odom_register_frame_dev(limu_odom *o, const float *xyzt_dev, int64_t n, double pose_out[7], limu_frame_stats *stats) {
     LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyzt_dev), "limu_odom_register_frame_dev: bad arguments");
     LIMU_TRY(bind(o->ctx));
+    if (o->speculate) return odom_register_pipelined(o, xyzt_dev, n, pose_out, nullptr, nullptr, nullptr, nullptr, stats);
     return odom_register_device(o, xyzt_dev, 0, 0, nullptr, n, pose_out, nullptr, nullptr, nullptr, nullptr, stats);
 }
 
@@ -492,6 +709,9 @@ int limu_odom_pose(limu_odom *o, int64_t i, double pose_out[7]) {
 }
 int limu_odom_adaptive_threshold(limu_odom *o, double *sigma) {
     LIMU_REQUIRE(o && sigma, "limu_odom_adaptive_threshold: null argument");
+    // get_adaptive_threshold() adds a sample on every call (threshold.cpp:16-28): a loop that ran ahead did so with a threshold that does
+    // not contain this one, and is dropped
+    if (o->ahead.loop) { LIMU_TRY(bind(o->ctx)); LIMU_TRY(odom_drop_ahead(o, true)); }
     *sigma = odom_adaptive_threshold(o);
     return LIMU_OK;
 }
@@ -511,17 +731,21 @@ int limu_odom_set_option(limu_odom *o, int32_t option, int64_t value) {
     LIMU_REQUIRE(o, "limu_odom_set_option: null handle");
     if (option == LIMU_OPT_SPECULATE) {
         LIMU_TRY(bind(o->ctx));
-        if (!value && o->spec_ptr) {   // a launch is in flight for a scan that will now be voxelized again: let it finish first
-            LIMU_CUDA_TRY(cudaStreamSynchronize(o->ctx->stream));
-            o->spec_ptr = nullptr; o->spec_slot = -1;
-        }
+        int st = LIMU_OK;
+        if (!value && o->speculate) st = odom_flush(o);   // nothing stays in flight on the plain path
         o->speculate = value != 0;
         if (!o->speculate) { o->hint_ptr = nullptr; o->hint_n = 0; }
-        return LIMU_OK;
+        return st;
     }
     if (option == LIMU_OPT_CLUSTER_LOOP) { o->cluster_loop = value != 0; return LIMU_OK; }
     set_error("limu_odom_set_option: unknown option %d", (int)option);
     return LIMU_ERR_INVALID;
+}
+
+int limu_odom_flush(limu_odom *o) {
+    LIMU_REQUIRE(o, "limu_odom_flush: null handle");
+    LIMU_TRY(bind(o->ctx));
+    return odom_flush(o);
 }
 
 }  // extern "C"

@@ -22,17 +22,21 @@ struct VoxelizeScratch {
     DevBuf table, pslot, tiles;
     int64_t cap_slots = 0, pslot_n = 0;   // allocated slots per table / entries per pslot array
     int parity = 0;                       // which of the two stage-2 tables the NEXT launch uses
-    void release() { table.release(); pslot.release(); tiles.release(); cap_slots = pslot_n = 0; parity = 0; }
+    int st_word = 0;                      // which of the owner's three status words the NEXT launch reports into
+    void release() { table.release(); pslot.release(); tiles.release(); cap_slots = pslot_n = 0; parity = 0; st_word = 0; }
 };
 // KissICP::deskew_scan + the two voxel_downsample stages of KissICP::voxelize in one cooperative launch.
 // mode 0: raw = float4 {x,y,z,t}; 1: records `stride` bytes apart + FP64 ts; 2: double xyz (register_frame(Vec3dVector)).
 // twist_dev (speculative launches, odometry.cu): read the deskew twist from device memory instead of twist_host.
-// own_status: TWO status words private to the pipeline that owns `sc` (zero at first use): consecutive launches alternate between them and each
-// launch zeroes the other one late, so a word is clean when its launch starts without a memset per scan; *status_used = which word this launch
+// own_status: THREE status words private to the pipeline that owns `sc` (zero at first use): consecutive launches rotate through them and each
+// launch zeroes the next one late, so a word is clean when its launch starts without a memset per scan; *status_used = which word this launch
 // reports into. nullptr = the context's shared word.
+// stream: where to enqueue (nullptr = the context's); beside: half-size CTAs, one per SM, so that the launch fits next to another kernel's CTA.
 int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int mode, int stride, const double *ts_dev, int deskew, const double *twist_host,
                     int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev, const double *twist_dev = nullptr,
-                    DevStatus *own_status = nullptr, int *status_used = nullptr);
+                    DevStatus *own_status = nullptr, int *status_used = nullptr, cudaStream_t stream = nullptr, bool beside = false);
+// One-thread kernel on stream s that returns once *flag has reached seq (voxelize.cu).
+int gate_device(cudaStream_t s, const unsigned int *flag, unsigned int seq);
 
 // deskew.cpp:10-28. twist_dev: 6 doubles (device). out: n x 3 doubles.
 int deskew_device(limu_ctx *c, const float *xyzt_dev, int64_t n, const double *twist_dev, double *out_dev);

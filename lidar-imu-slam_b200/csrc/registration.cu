@@ -84,6 +84,8 @@ struct IcpArgs {
     int icp_blocks;
     double *twist_out;          // see FrameFusion
     double last_pose[7];
+    unsigned int *loop_flag;    // non-null: set to loop_seq (release, GPU scope) once pose and twist_out of this launch are in memory
+    unsigned int loop_seq;
     double *est_trace;          // optional [max_iter][7]
     long long *ncorr_trace;     // optional [max_iter]
     double *hg_trace;           // optional [max_iter][42]
@@ -590,21 +592,30 @@ __device__ unsigned long long g_frame_marks[24];
 // local_map.update(down_sampled, new_pose) (icp.cpp:81; voxel_hash_map.cpp:138-144) inside a frame kernel: transform + capped ordered insert
 // (two passes separated by a grid barrier) + eviction around the new position. Every CTA of the grid takes part (those that sat out the
 // Gauss-Newton loop join here); everybody reads the new pose that CTA 0 published in A.out. E: 7 doubles of shared memory.
-template <int BLOCK>
-__device__ __forceinline__ void frame_update_epilogue(const IcpArgs &A, GridSync &gs, double *E) {
-    gs.sync();
-    if (threadIdx.x < 7) E[threadIdx.x] = __ldcg(A.out + threadIdx.x);
-    __syncthreads();
-    const Pose np = pose_load(E);
-    // The next scan deskews with delta_pose(poses[N-2], poses[N-1]) = log(last^-1 * new) (deskew.cpp:14): left on the device for a speculative
-    // k_voxelize. One thread of the LAST CTA takes it (inverse, product, log: ~3 us of scalar code) while the grid inserts -- on CTA 0's
-    // thread 0, in front of the barrier above, it held up every CTA.
-    if (A.twist_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == BLOCK - 1) {
+// The next scan deskews with delta_pose(poses[N-2], poses[N-1]) = log(last^-1 * new) (deskew.cpp:14): left on the device for a k_voxelize
+// that is already enqueued, then the flag its gate kernel waits for (voxelize.cu, k_gate). One thread (~3 us of scalar code).
+__device__ __forceinline__ void publish_twist(const IcpArgs &A, const Pose &np) {
+    if (A.twist_out) {
         double tw[6];
         se3_log(mul(inverse(Pose{A.last_pose[0], A.last_pose[1], A.last_pose[2], A.last_pose[3], A.last_pose[4], A.last_pose[5], A.last_pose[6]}), np), tw);
 #pragma unroll
         for (int k = 0; k < 6; ++k) A.twist_out[k] = tw[k];
     }
+    if (A.loop_flag) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.loop_flag), "r"(A.loop_seq) : "memory");
+    }
+}
+
+template <int BLOCK, bool FUSED = true>
+__device__ __forceinline__ void frame_update_epilogue(const IcpArgs &A, GridSync &gs, double *E) {
+    if (FUSED) gs.sync();   // (a launch of its own starts behind the kernel that wrote the pose)
+    if (threadIdx.x < 7) E[threadIdx.x] = __ldcg(A.out + threadIdx.x);
+    __syncthreads();
+    const Pose np = pose_load(E);
+    // Fused launch: one thread of the LAST CTA publishes the twist while the grid inserts -- on CTA 0's thread 0, in front of the barrier
+    // above, it held up every CTA.
+    if (FUSED && blockIdx.x == gridDim.x - 1 && threadIdx.x == BLOCK - 1) publish_twist(A, np);
     const int64_t nd = (int64_t)__ldcg(A.upd_n);
     const int64_t gtid = (int64_t)blockIdx.x * BLOCK + threadIdx.x, gthreads = (int64_t)gridDim.x * BLOCK;
     for (int64_t base = (int64_t)blockIdx.x * BLOCK; base < nd; base += gthreads) {   // whole warps stay converged for the ballot
@@ -904,13 +915,15 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
         ++j;
     }
     FT_MARK(2);
-    if (blockIdx.x == 0 && n_keypoints >= 0) iqr_write_out<ICP_BLOCK>(qidx_s, A.iqr_in, n_keypoints, A.iqr_out, A.iqr_count);   // keypoints for the host
-    // new_pose = T_icp * init_guess (:129); with an empty map the loop did not run and this is init_guess itself (:99-100)
+    // new_pose = T_icp * init_guess (:129); with an empty map the loop did not run and this is init_guess itself (:99-100). A launch without
+    // the map-update epilogue (pipelined odometry) publishes the next scan's deskew twist here: the next scan's k_voxelize starts on it.
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const Pose np = run_icp ? mul(pose_load(Ticp), pose_load(Tinit)) : pose_load(Tinit);
         pose_store(np, A.out);
         A.out[7] = (double)j; A.out[8] = (double)converged; A.out[9] = S[I_NCORR]; A.out[10] = S[I_NCORR + 1]; A.out[11] = S[I_NCORR + 2]; A.out[12] = (double)n;
+        if (!A.upd_down) publish_twist(A, np);
     }
+    if (blockIdx.x == 0 && n_keypoints >= 0) iqr_write_out<ICP_BLOCK>(qidx_s, A.iqr_in, n_keypoints, A.iqr_out, A.iqr_count);   // keypoints for the host
     if (A.upd_down) frame_update_epilogue<ICP_BLOCK>(A, gs, E);
     FT_MARK(5);
     // the last CTA out re-arms the barrier for the next launch
@@ -919,6 +932,38 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
         __threadfence();
         if (atomicAdd(A.exit_count, 1u) == gridDim.x - 1) { *A.barrier = 0u; *A.barrier_icp = 0u; *A.exit_count = 0u; __threadfence(); }
     }
+}
+
+// local_map.update(down_sampled, new_pose) as a launch of its own (pipelined odometry: the Gauss-Newton loop of a scan is launched before the
+// caller has confirmed that scan, its map update only afterwards). Two CTAs' worth of registers at most, so that it fits beside the next
+// scan's k_voxelize.
+static __global__ void __launch_bounds__(ICP_BLOCK, 2) k_frame_update(const IcpArgs A) {
+    __shared__ double E[7];
+    GridSync gs{A.barrier, 0u, gridDim.x};
+    frame_update_epilogue<ICP_BLOCK, false>(A, gs, E);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(A.exit_count, 1u) == gridDim.x - 1) { *A.barrier = 0u; *A.exit_count = 0u; __threadfence(); }
+    }
+}
+
+int frame_update_device(limu_map *m, const FrameFusion &fuse, const double *pose_dev) {
+    limu_ctx *c = m->ctx;
+    IcpArgs A;
+    memset(&A, 0, sizeof A);
+    A.map = m->view();
+    A.out = const_cast<double *>(pose_dev);
+    A.barrier = reinterpret_cast<unsigned int *>(c->d_small.as<double>() + 56);
+    A.exit_count = A.barrier + 1;
+    A.upd_down = fuse.upd_down; A.upd_n = fuse.upd_n; A.upd_world = fuse.upd_world; A.upd_pslot = fuse.upd_pslot;
+    A.upd_counters = m->counters.as<unsigned long long>(); A.upd_birth_base = fuse.upd_birth_base;
+    A.status = fuse.status ? fuse.status : c->d_status;
+    A.upd_capacity = (long long)m->capacity; A.upd_max_distance = m->max_distance;
+    void *args[] = {&A};
+    LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_frame_update, dim3(c->sm_count), dim3(ICP_BLOCK), args, 0, c->stream));
+    LIMU_LAUNCHED();
+    return LIMU_OK;
 }
 
 // ============================================================================================================================
@@ -1267,6 +1312,7 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
         if (fuse->status) A.status = fuse->status;
         A.upd_capacity = (long long)m->capacity; A.upd_max_distance = m->max_distance;
         A.twist_out = fuse->twist_out;
+        A.loop_flag = fuse->loop_flag; A.loop_seq = fuse->loop_seq;
         for (int k = 0; k < 7; ++k) A.last_pose[k] = fuse->last_pose[k];
     }
     void *args[] = {&A};

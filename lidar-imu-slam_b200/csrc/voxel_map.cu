@@ -252,6 +252,7 @@ int map_insert_device(limu_map *m, const double *xyz_dev, int64_t n, const int *
     LIMU_LAUNCHED();
     m->birth_base += (uint64_t)n;
     m->used_upper += n;
+    ++m->mutations;
     return LIMU_OK;
 }
 
@@ -260,6 +261,7 @@ int map_remove_far_device(limu_map *m, const double *origin_dev3) {
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(div_up(std::max<int64_t>(m->used_upper, 1), 256), (int64_t)c->sm_count * 8));
     k_remove_far<<<blocks, 256, 0, c->stream>>>(m->view(), origin_dev3, m->max_distance, m->counters.as<unsigned long long>());
     LIMU_LAUNCHED();
+    ++m->mutations;
     return LIMU_OK;
 }
 
@@ -317,6 +319,7 @@ int limu_map_clear(limu_map *m) {
     LIMU_CUDA_TRY(cudaMemsetAsync(m->pend.p, 0xFF, (size_t)m->capacity * m->cap * 4, c->stream));
     LIMU_CUDA_TRY(cudaMemsetAsync(m->counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
     m->used_upper = 0;
+    ++m->mutations;
     return LIMU_OK;
 }
 

@@ -703,6 +703,7 @@ struct limu_map {
     limu::DevBuf counters;         // device: [0] n_live voxels, [1] n_tomb, [2] n_points, [3] n_used (live + tomb)
     uint64_t birth_base = 0;       // creation sequence offset of the next insert batch
     int64_t used_upper = 0;        // host upper bound on live + tomb slots
+    uint64_t mutations = 0;        // bumped by every entry point of the C ABI that changes the map's contents (odometry.cu: a loop that ran ahead on an older map is dropped)
     limu::DevBuf pslot;            // per-point slot scratch of the current insert batch
     limu::DevBuf world;            // transformed copy for update(points, pose)
     limu::MapView view() const;

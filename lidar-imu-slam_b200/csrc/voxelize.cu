@@ -24,6 +24,9 @@ namespace limu {
 #define LIMU_VX_BLOCK 1024   // one fat CTA per SM: a grid barrier is paid per ARRIVING CTA (atomics on one word serialise at ~4 ns each: 592 CTAs of 256 -> 148 of 1024)
 #endif
 constexpr int VX_BLOCK = LIMU_VX_BLOCK;
+// The pipelined odometry path (odometry.cu) runs the NEXT scan's launch beside the current scan's map update: 1024 threads x 64 registers
+// are a whole register file, so that launch uses half-size CTAs (one per SM) and leaves room for the update kernel's CTA.
+constexpr int VX_BLOCK_BESIDE = 512;
 
 struct VoxelizeArgs {
     const void *raw;            // mode 0: float4 {x,y,z,t}; mode 1: records `stride` bytes apart + ts; mode 2: double xyz (already a frame)
@@ -69,6 +72,7 @@ __device__ __forceinline__ unsigned int claim_min(unsigned long long *keys, unsi
 }
 
 // exclusive prefix of tile counts: sum of counts[0..tile) computed by the whole CTA
+template <int VX_BLOCK>
 __device__ __forceinline__ int tile_base(const int *counts, int tile, int *ws /* 32 ints */) {
     int part = 0;
     for (int b = threadIdx.x; b < tile; b += VX_BLOCK) part += __ldcg(counts + b);
@@ -84,6 +88,7 @@ __device__ __forceinline__ int tile_base(const int *counts, int tile, int *ws /*
     return v;
 }
 
+template <int VX_BLOCK>
 static __global__ void __launch_bounds__(VX_BLOCK, 1024 / VX_BLOCK) k_voxelize(const VoxelizeArgs A) {
     __shared__ int ws[32];
     __shared__ int total;
@@ -137,7 +142,7 @@ static __global__ void __launch_bounds__(VX_BLOCK, 1024 / VX_BLOCK) k_voxelize(c
         }
     }
     gs.sync();
-    // P2: a point survives stage 1 iff it holds its voxel's smallest input index; count survivors per 256-point tile
+    // P2: a point survives stage 1 iff it holds its voxel's smallest input index; count survivors per VX_BLOCK-point tile
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t i = (int64_t)tile * VX_BLOCK + threadIdx.x;
         int f = 0;
@@ -149,7 +154,7 @@ static __global__ void __launch_bounds__(VX_BLOCK, 1024 / VX_BLOCK) k_voxelize(c
     gs.sync();
     // P3: ordered scatter -> down[]; each winner immediately claims its 1.5 v voxel with its OUTPUT index
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int base = tile_base(A.tile1, tile, ws);
+        const int base = tile_base<VX_BLOCK>(A.tile1, tile, ws);
         const int64_t i = (int64_t)tile * VX_BLOCK + threadIdx.x;
         int f = 0;
         if (i < n) { const unsigned int s = A.pslot1[i]; f = s != PEND_NONE && __ldcg(A.min1 + s) == (unsigned int)i; }
@@ -184,7 +189,7 @@ static __global__ void __launch_bounds__(VX_BLOCK, 1024 / VX_BLOCK) k_voxelize(c
     }
     gs.sync();
     for (int tile = blockIdx.x; tile < ntiles2; tile += gridDim.x) {
-        const int base = tile_base(A.tile2, tile, ws);
+        const int base = tile_base<VX_BLOCK>(A.tile2, tile, ws);
         const int j = tile * VX_BLOCK + threadIdx.x;
         int f = 0;
         if (j < nd) { const unsigned int s = __ldcg(A.pslot2 + j); f = s != PEND_NONE && __ldcg(A.min2 + s) == (unsigned int)j; }
@@ -205,49 +210,79 @@ static __global__ void __launch_bounds__(VX_BLOCK, 1024 / VX_BLOCK) k_voxelize(c
     }
 }
 
+// One thread that waits until a frame kernel launched EARLIER on another stream has published the pose of its scan (the flag carries that
+// launch's sequence number): the stream it sits in -- the next scan's k_voxelize behind it -- is released the moment the Gauss-Newton loop is
+// over instead of when that kernel and the map update behind it have finished. A single thread holds no resource anybody waits for, so the
+// wait cannot deadlock; after 5 s (the awaited kernel is gone) it gives up and lets the error surface on the host.
+static __global__ void k_gate(const unsigned int *flag, unsigned int seq) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned int v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - seq) >= 0) break;
+        __nanosleep(64);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 5000000000ull) break;
+    }
+}
+int gate_device(cudaStream_t s, const unsigned int *flag, unsigned int seq) {
+    k_gate<<<1, 1, 0, s>>>(flag, seq);
+    LIMU_LAUNCHED();
+    return LIMU_OK;
+}
+
 static int g_vx_blocks_per_sm = 0;
 
 static int64_t pow2_slots(int64_t n) { int64_t p = 1024; while (p < 2 * n) p <<= 1; return p; }
 
 // Enqueue the fused kernel. raw/ts/twist are device pointers; outputs: frame (n x 3), down, src0, counts[0..1].
 int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int mode, int stride, const double *ts_dev, int deskew, const double *twist_host,
-                    int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev, const double *twist_dev, DevStatus *own_status, int *status_used) {
+                    int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev, const double *twist_dev, DevStatus *own_status, int *status_used,
+                    cudaStream_t stream, bool beside) {
+    if (!stream) stream = c->stream;
     if (n <= 0) {
-        LIMU_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int), c->stream));
-        if (own_status) LIMU_CUDA_TRY(cudaMemsetAsync(own_status, 0, 2 * sizeof(DevStatus), c->stream));
-        if (status_used) *status_used = 0;
+        LIMU_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int), stream));
+        if (own_status) {   // the word this (empty) launch reports into must read clean; the rotation moves on as for any launch
+            const int w = sc.st_word;
+            sc.st_word = (w + 1) % 3;
+            LIMU_CUDA_TRY(cudaMemsetAsync(own_status + w, 0, sizeof(DevStatus), stream));
+            LIMU_CUDA_TRY(cudaMemsetAsync(own_status + sc.st_word, 0, sizeof(DevStatus), stream));
+            if (status_used) *status_used = w;
+        } else if (status_used) *status_used = 0;
         return LIMU_OK;
     }
     if (g_vx_blocks_per_sm == 0) {
         int b = 0;
-        LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_voxelize, VX_BLOCK, 0));
+        LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_voxelize<VX_BLOCK>, VX_BLOCK, 0));
         g_vx_blocks_per_sm = std::max(1, std::min(b, 1024 / VX_BLOCK));
     }
+    const int block = beside ? VX_BLOCK_BESIDE : VX_BLOCK;
     const int64_t C1 = pow2_slots(n), C2 = pow2_slots(n);
     int lg = 0;
     while ((int64_t(1) << lg) < C1) ++lg;
-    const int ntiles = div_up(n, VX_BLOCK);
+    const int ntiles = div_up(n, block);
     {   // three tables [u64 key x cap | u32 min-index x cap] at offsets fixed by the ALLOCATED capacity (claimed slots are remembered as indices), all-ones
         // = clean at rest. Whenever one of the buffers is re-allocated the memory of what the previous launch claimed is gone: start over clean.
         bool reset = false;
         if (C1 > sc.cap_slots) {
             int64_t cap = sc.cap_slots ? sc.cap_slots : 1024;
             while (cap < C1) cap <<= 1;
-            LIMU_TRY(sc.table.reserve((size_t)cap * 12 * 3, c->stream));
+            LIMU_TRY(sc.table.reserve((size_t)cap * 12 * 3, stream));
             sc.cap_slots = cap;
             reset = true;
         }
         const void *before = sc.pslot.p;
-        LIMU_TRY(sc.pslot.reserve((size_t)n * 4 * 3, c->stream));   // pslot1 | pslot2 of the two parities
+        LIMU_TRY(sc.pslot.reserve((size_t)n * 4 * 3, stream));   // pslot1 | pslot2 of the two parities
         if (sc.pslot.p != before) reset = true;
         sc.pslot_n = (int64_t)(sc.pslot.bytes / 12);
         // [16 ints: barrier words 0-1, stage-2 claim counts of the two parities 4-5 | tile counts]; the kernel keeps the barrier words at zero
         before = sc.tiles.p;
-        LIMU_TRY(sc.tiles.reserve((size_t)ntiles * 8 + 128, c->stream));
+        LIMU_TRY(sc.tiles.reserve((size_t)div_up(n, VX_BLOCK_BESIDE) * 8 + 128, stream));   // (sized for the smaller of the two tile sizes)
         if (sc.tiles.p != before) reset = true;
         if (reset) {
-            LIMU_CUDA_TRY(cudaMemsetAsync(sc.table.p, 0xFF, (size_t)sc.cap_slots * 12 * 3, c->stream));
-            LIMU_CUDA_TRY(cudaMemsetAsync(sc.tiles.p, 0, sc.tiles.bytes, c->stream));
+            LIMU_CUDA_TRY(cudaMemsetAsync(sc.table.p, 0xFF, (size_t)sc.cap_slots * 12 * 3, stream));
+            LIMU_CUDA_TRY(cudaMemsetAsync(sc.tiles.p, 0, sc.tiles.bytes, stream));
         }
     }
     const int par = sc.parity;
@@ -276,13 +311,17 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     A.nd_prev = sc.tiles.as<int>() + 4 + (par ^ 1);
     A.tile1 = sc.tiles.as<int>() + 16; A.tile2 = A.tile1 + ntiles;
     A.counts = counts_dev;
-    // own_status: two DevStatus words; this launch uses word `par`, the next launch of this scratch the other one
-    A.st = own_status ? own_status + par : c->d_status;
-    A.st_next = own_status ? own_status + (par ^ 1) : nullptr;
-    if (status_used) *status_used = par;
-    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->sm_count * g_vx_blocks_per_sm);
+    // own_status: three DevStatus words in rotation; this launch reports into word w and zeroes word w+1 (the next launch's) late. Three, not
+    // two: in the pipelined path launch k+1 runs before the result copy of scan k has read launch k's word.
+    const int w = sc.st_word;
+    if (own_status) sc.st_word = (w + 1) % 3;
+    A.st = own_status ? own_status + w : c->d_status;
+    A.st_next = own_status ? own_status + sc.st_word : nullptr;
+    if (status_used) *status_used = w;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->sm_count * (beside ? 1 : g_vx_blocks_per_sm));
     void *args[] = {&A};
-    LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize, dim3(grid), dim3(VX_BLOCK), args, 0, c->stream));
+    if (beside) LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize<VX_BLOCK_BESIDE>, dim3(grid), dim3(VX_BLOCK_BESIDE), args, 0, stream));
+    else LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize<VX_BLOCK>, dim3(grid), dim3(VX_BLOCK), args, 0, stream));
     LIMU_LAUNCHED();
     return LIMU_OK;
 }
