@@ -23,6 +23,7 @@ struct VoxelizeScratch {
     int64_t cap_slots = 0, pslot_n = 0;   // allocated slots per table / entries per pslot array
     int parity = 0;                       // which of the two stage-2 tables the NEXT launch uses
     int st_word = 0;                      // which of the owner's three status words the NEXT launch reports into
+    unsigned int epoch = 0;               // launch counter: validates the per-tile count words
     void release() { table.release(); pslot.release(); tiles.release(); cap_slots = pslot_n = 0; parity = 0; st_word = 0; }
 };
 // KissICP::deskew_scan + the two voxel_downsample stages of KissICP::voxelize in one cooperative launch.

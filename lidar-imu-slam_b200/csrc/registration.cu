@@ -575,18 +575,20 @@ __device__ __forceinline__ void icp_query_pass_staged(const IcpArgs &A, const vo
 
 #ifdef LIMU_ICP_PHASE_TIMING
 // developer build only (tools/icp_phase_timing.py, tools/frame_phase_timing.py): %globaltimer stamps of CTA 0 / thread 0
-__device__ unsigned long long g_frame_marks[24];
+__device__ unsigned long long g_frame_marks[72];   // [24 + j]: clock of CTA 0 / warp 0 at the start of round j of the Gauss-Newton loop (j < 48)
 #define FT_MARK(k) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && ((k) >= 8 || threadIdx.x == 0)) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_frame_marks[k] = _t; } } while (0)
 // SM cycle counter of CTA 0 (one SM: the marks of different warps are comparable): any lane 0 / lane 0 of warp w
 #define IQ_MARK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
 // (stamped in iteration 2 of the Gauss-Newton loop; marks 13 / 14 = the tail of iteration 2, which runs during loop round 3)
 #define CT_MARK(k) do { if (blockIdx.x == 0 && lane == 0 && j == (((k) == 13 || (k) == 14) ? 3 : 2)) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
 #define CW_MARK(k, w) do { if (blockIdx.x == 0 && warp == (w) && lane == 0 && j == (((k) == 13 || (k) == 14) ? 3 : 2)) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
+#define ROUND_MARK() do { if (blockIdx.x == 0 && threadIdx.x == 0 && j < 48) g_frame_marks[24 + j] = (unsigned long long)clock64(); } while (0)
 #else
 #define FT_MARK(k) do {} while (0)
 #define IQ_MARK(k) do {} while (0)
 #define CW_MARK(k, w) do {} while (0)
 #define CT_MARK(k) do {} while (0)
+#define ROUND_MARK() do {} while (0)
 #endif
 
 // local_map.update(down_sampled, new_pose) (icp.cpp:81; voxel_hash_map.cpp:138-144) inside a frame kernel: transform + capped ordered insert
@@ -740,6 +742,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
     int converged = 0;
     if (run_icp && icp_member) for (;;) {
         const bool no_more = j >= A.max_iter;   // nothing left to do but wait for the verdict on iteration j-1
+        ROUND_MARK();
         if (warp < QW) {
             if (!no_more) {
                 CW_MARK(6, 0);
@@ -774,6 +777,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
             }
         } else if (j > 0) {
             // tail of iteration j-1, overlapped with pass j: T_icp = estimate * T_icp (:122) on lane 0, |log(estimate)| < eps (:124) on lane 1
+            CW_MARK(13, QW);
             const Pose est = pose_load(E);
             if (lane == 0) pose_store(mul(est, pose_load(Ticp)), Ticp);
             if (lane == 1) {
@@ -1338,10 +1342,10 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
 int icp_partial_rows(limu_ctx *c) { return c->sm_count * 4; }   // >= the largest grid of any shape
 
 #ifdef LIMU_ICP_PHASE_TIMING
-extern "C" int limu_debug_frame_marks(double out[24]) {
-    unsigned long long h[24];
+extern "C" int limu_debug_frame_marks(double out[72]) {
+    unsigned long long h[72];
     if (cudaMemcpyFromSymbol(h, g_frame_marks, sizeof h) != cudaSuccess) return -1;
-    for (int k = 0; k < 24; ++k) out[k] = (double)h[k];
+    for (int k = 0; k < 72; ++k) out[k] = (double)h[k];
     return 0;
 }
 #endif

@@ -3,9 +3,12 @@
 //
 // The stand-alone stages (ops.cu) cost 13 launches + 2 memsets per scan, each a few microseconds of work on 128k points;
 // here the phases are separated by grid barriers instead of kernel boundaries:
-//   P1 deskew/widen -> frame[], stage-1 claim  P4 stage-2 winner flags, per-tile counts (+ un-claim the stage-1 table)
-//   P2 stage-1 winner flags, per-tile counts   P5 ordered scatter of stage-2 winners -> src0[]
-//   P3 ordered scatter of stage-1 winners -> down[], stage-2 claim
+//   P1 deskew/widen -> frame[], stage-1 claim
+//   P2 stage-1 winner flags, per-tile counts, ordered scatter of the winners -> down[], stage-2 claim
+//   P3 (un-claim the stage-1 table) stage-2 winner flags, per-tile counts, ordered scatter -> src0[]
+// Inside P2 / P3 a tile does not wait at a grid barrier for the counts of the tiles before it: every count is published as ONE 8-byte word
+// {launch epoch | count}, and a tile simply re-reads the words of its predecessors until they carry this launch's epoch (tiles are handed
+// out in increasing order and all CTAs are co-resident, so every predecessor is finished or in progress). Two grid barriers per scan, not four.
 // The scan-local hash tables are left CLEAN instead of being cleared at the start (6 MB of stores and a grid barrier per scan): every
 // claimed slot is remembered per point, so the stage-1 table is un-claimed in P4 (nobody reads it after P3) and the stage-2 table of
 // this launch is un-claimed by the NEXT launch, which works on the other of two stage-2 tables.
@@ -44,7 +47,8 @@ struct VoxelizeArgs {
     int *nd_prev, *nd_this;           // how many stage-2 claims the previous launch made / this launch makes
     unsigned int mask1, mask2;
     int shift1, shift2;
-    int *tile1, *tile2;
+    unsigned long long *tile1, *tile2;   // per-tile survivor counts of the two stages: {epoch << 32 | count}
+    unsigned int epoch;                  // of this launch (never 0; the words are zero after a reset)
     int *counts;                // [0] n_down, [1] n_src0
     unsigned int *barrier;      // [0] grid barrier, [1] exit counter; zero at rest (the last CTA out re-arms them, no memset per launch)
     DevStatus *st;
@@ -71,11 +75,17 @@ __device__ __forceinline__ unsigned int claim_min(unsigned long long *keys, unsi
     return PEND_NONE;
 }
 
-// exclusive prefix of tile counts: sum of counts[0..tile) computed by the whole CTA
+// exclusive prefix of tile counts: sum of counts[0..tile) computed by the whole CTA; a word is re-read until it is this launch's
 template <int VX_BLOCK>
-__device__ __forceinline__ int tile_base(const int *counts, int tile, int *ws /* 32 ints */) {
+__device__ __forceinline__ int tile_base(const unsigned long long *words, int tile, unsigned int epoch, int *ws /* 32 ints */) {
     int part = 0;
-    for (int b = threadIdx.x; b < tile; b += VX_BLOCK) part += __ldcg(counts + b);
+    for (int b = threadIdx.x; b < tile; b += VX_BLOCK) {
+        unsigned long long w;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(words + b) : "memory");
+        } while ((unsigned int)(w >> 32) != epoch);
+        part += (int)(unsigned int)w;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xFFFFFFFFu, part, o);
     __syncthreads();
@@ -87,6 +97,16 @@ __device__ __forceinline__ int tile_base(const int *counts, int tile, int *ws /*
     __syncthreads();
     return v;
 }
+__device__ __forceinline__ void tile_publish(unsigned long long *word, unsigned int epoch, int count) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(word), "l"(((unsigned long long)epoch << 32) | (unsigned int)count) : "memory");
+}
+
+#ifdef LIMU_ICP_PHASE_TIMING
+__device__ unsigned long long g_vox_marks[8];   // globaltimer of thread 0 of CTA 0: start, after each of the two grid barriers, end
+#define VX_MARK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_vox_marks[k] = _t; } } while (0)
+#else
+#define VX_MARK(k) do {} while (0)
+#endif
 
 template <int VX_BLOCK>
 static __global__ void __launch_bounds__(VX_BLOCK, 1024 / VX_BLOCK) k_voxelize(const VoxelizeArgs A) {
@@ -96,6 +116,7 @@ static __global__ void __launch_bounds__(VX_BLOCK, 1024 / VX_BLOCK) k_voxelize(c
     const int64_t n = A.n;
     const int64_t gtid = (int64_t)blockIdx.x * VX_BLOCK + threadIdx.x, gthreads = (int64_t)gridDim.x * VX_BLOCK;
     const int ntiles = (int)((n + VX_BLOCK - 1) / VX_BLOCK);
+    VX_MARK(0);
     // un-claim what the previous launch left in ITS stage-2 table (this launch uses the other one): no barrier needed
     {
         const int ndp = __ldcg(A.nd_prev);
@@ -142,23 +163,16 @@ static __global__ void __launch_bounds__(VX_BLOCK, 1024 / VX_BLOCK) k_voxelize(c
         }
     }
     gs.sync();
-    // P2: a point survives stage 1 iff it holds its voxel's smallest input index; count survivors per VX_BLOCK-point tile
+    VX_MARK(1);
+    // P2: a point survives stage 1 iff it holds its voxel's smallest input index. Per VX_BLOCK-point tile: flags, count (published),
+    // ordered scatter -> down[]; each winner immediately claims its 1.5 v voxel with its OUTPUT index
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t i = (int64_t)tile * VX_BLOCK + threadIdx.x;
-        int f = 0;
-        if (i < n) { const unsigned int s = A.pslot1[i]; f = s != PEND_NONE && __ldcg(A.min1 + s) == (unsigned int)i; }
-        block_exclusive_scan_flag(f, &total, ws);
-        if (threadIdx.x == 0) A.tile1[tile] = total;
-        __syncthreads();
-    }
-    gs.sync();
-    // P3: ordered scatter -> down[]; each winner immediately claims its 1.5 v voxel with its OUTPUT index
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int base = tile_base<VX_BLOCK>(A.tile1, tile, ws);
         const int64_t i = (int64_t)tile * VX_BLOCK + threadIdx.x;
         int f = 0;
         if (i < n) { const unsigned int s = A.pslot1[i]; f = s != PEND_NONE && __ldcg(A.min1 + s) == (unsigned int)i; }
         const int r = block_exclusive_scan_flag(f, &total, ws);
+        if (threadIdx.x == 0) tile_publish(A.tile1 + tile, A.epoch, total);
+        const int base = tile_base<VX_BLOCK>(A.tile1, tile, A.epoch, ws);
         if (f) {
             const int j = base + r;
             const V3 p{A.frame[3 * i], A.frame[3 * i + 1], A.frame[3 * i + 2]};
@@ -170,30 +184,23 @@ static __global__ void __launch_bounds__(VX_BLOCK, 1024 / VX_BLOCK) k_voxelize(c
     }
     if (ntiles == 0 && gtid == 0) { A.counts[0] = 0; *A.nd_this = 0; }
     gs.sync();
+    VX_MARK(2);
     if (gtid == 0 && A.st_next) *A.st_next = DevStatus{0, 0, {0, 0}};   // (its last reader, the result copy of the previous scan, is long done)
-    // the stage-1 table was last read in P3: un-claim it for the next launch
+    // the stage-1 table was last read in P2: un-claim it for the next launch
     for (int64_t i = gtid; i < n; i += gthreads) {
         const unsigned int sl = A.pslot1[i];
         if (sl != PEND_NONE) { A.keys1[sl] = KEY_EMPTY; A.min1[sl] = PEND_NONE; }
     }
-    // P4 / P5: the same flag -> count -> scatter over down[] for stage 2
+    // P3: the same flag -> count -> scatter over down[] for stage 2
     const int nd = __ldcg(A.counts);
     const int ntiles2 = (nd + VX_BLOCK - 1) / VX_BLOCK;
     for (int tile = blockIdx.x; tile < ntiles2; tile += gridDim.x) {
         const int j = tile * VX_BLOCK + threadIdx.x;
         int f = 0;
         if (j < nd) { const unsigned int s = __ldcg(A.pslot2 + j); f = s != PEND_NONE && __ldcg(A.min2 + s) == (unsigned int)j; }
-        block_exclusive_scan_flag(f, &total, ws);
-        if (threadIdx.x == 0) A.tile2[tile] = total;
-        __syncthreads();
-    }
-    gs.sync();
-    for (int tile = blockIdx.x; tile < ntiles2; tile += gridDim.x) {
-        const int base = tile_base<VX_BLOCK>(A.tile2, tile, ws);
-        const int j = tile * VX_BLOCK + threadIdx.x;
-        int f = 0;
-        if (j < nd) { const unsigned int s = __ldcg(A.pslot2 + j); f = s != PEND_NONE && __ldcg(A.min2 + s) == (unsigned int)j; }
         const int r = block_exclusive_scan_flag(f, &total, ws);
+        if (threadIdx.x == 0) tile_publish(A.tile2 + tile, A.epoch, total);
+        const int base = tile_base<VX_BLOCK>(A.tile2, tile, A.epoch, ws);
         if (f) {
             const size_t k = (size_t)(base + r);
             A.src0[3 * k] = __ldcg(A.down + 3 * (size_t)j); A.src0[3 * k + 1] = __ldcg(A.down + 3 * (size_t)j + 1); A.src0[3 * k + 2] = __ldcg(A.down + 3 * (size_t)j + 2);
@@ -204,6 +211,7 @@ static __global__ void __launch_bounds__(VX_BLOCK, 1024 / VX_BLOCK) k_voxelize(c
     if (ntiles2 == 0 && gtid == 0) A.counts[1] = 0;
     // every CTA has left the last barrier before it gets here, so the last one out can re-arm it for the next launch
     __syncthreads();
+    VX_MARK(3);
     if (threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(A.barrier + 1, 1u) == gridDim.x - 1) { A.barrier[0] = 0u; A.barrier[1] = 0u; __threadfence(); }
@@ -231,6 +239,15 @@ int gate_device(cudaStream_t s, const unsigned int *flag, unsigned int seq) {
     LIMU_LAUNCHED();
     return LIMU_OK;
 }
+
+#ifdef LIMU_ICP_PHASE_TIMING
+extern "C" int limu_debug_vox_marks(double out[8]) {
+    unsigned long long h[8];
+    if (cudaMemcpyFromSymbol(h, g_vox_marks, sizeof h) != cudaSuccess) return -1;
+    for (int k = 0; k < 8; ++k) out[k] = (double)h[k];
+    return 0;
+}
+#endif
 
 static int g_vx_blocks_per_sm = 0;
 
@@ -276,9 +293,10 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
         LIMU_TRY(sc.pslot.reserve((size_t)n * 4 * 3, stream));   // pslot1 | pslot2 of the two parities
         if (sc.pslot.p != before) reset = true;
         sc.pslot_n = (int64_t)(sc.pslot.bytes / 12);
-        // [16 ints: barrier words 0-1, stage-2 claim counts of the two parities 4-5 | tile counts]; the kernel keeps the barrier words at zero
+        // [16 ints: barrier words 0-1, stage-2 claim counts of the two parities 4-5 | per-tile count words of the two stages]; the kernel keeps
+        // the barrier words at zero, and a count word is only believed when it carries the epoch of the launch that reads it
         before = sc.tiles.p;
-        LIMU_TRY(sc.tiles.reserve((size_t)div_up(n, VX_BLOCK_BESIDE) * 8 + 128, stream));   // (sized for the smaller of the two tile sizes)
+        LIMU_TRY(sc.tiles.reserve((size_t)div_up(n, VX_BLOCK_BESIDE) * 16 + 128, stream));   // (sized for the smaller of the two tile sizes)
         if (sc.tiles.p != before) reset = true;
         if (reset) {
             LIMU_CUDA_TRY(cudaMemsetAsync(sc.table.p, 0xFF, (size_t)sc.cap_slots * 12 * 3, stream));
@@ -309,7 +327,9 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     A.barrier = sc.tiles.as<unsigned int>();
     A.nd_this = sc.tiles.as<int>() + 4 + par;
     A.nd_prev = sc.tiles.as<int>() + 4 + (par ^ 1);
-    A.tile1 = sc.tiles.as<int>() + 16; A.tile2 = A.tile1 + ntiles;
+    A.tile1 = reinterpret_cast<unsigned long long *>(sc.tiles.as<int>() + 16); A.tile2 = A.tile1 + ntiles;
+    if (++sc.epoch == 0u) sc.epoch = 1u;
+    A.epoch = sc.epoch;
     A.counts = counts_dev;
     // own_status: three DevStatus words in rotation; this launch reports into word w and zeroes word w+1 (the next launch's) late. Three, not
     // two: in the pipelined path launch k+1 runs before the result copy of scan k has read launch k's word.

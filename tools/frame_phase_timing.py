@@ -19,14 +19,21 @@ K = 40
 traj = synth.loop_trajectory(K + 1, radius=30.0, step=1.0)
 scans = [synth.pad_scan(synth.cast_scan(scene, traj[i], traj[i + 1], seed=42 * 100003 + i, device="cuda"), 128000, seed=i) for i in range(K)]
 odo = ctx.KissICP(voxel_size=1.0, cap=10, deskew=True, icp_max_iteration=500)
-marks = np.zeros(24)
-rows, iters = [], []
+marks = np.zeros(72)
+vmarks = np.zeros(8)
+have_vox = hasattr(pkg.lib(), "limu_debug_vox_marks")
+rows, iters, rounds, vrows = [], [], [], []
 for i, s in enumerate(scans):
     odo.register_frame(s, want_clouds=False)
     pkg.lib().limu_debug_frame_marks(marks.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
     if i >= 5:
         rows.append(np.diff(marks[:6]) / 1e3)
         iters.append(odo.stats.icp.iterations)
+        nr = min(odo.stats.icp.iterations + 1, 47)          # rounds = iterations + the round that notices convergence
+        rounds.append(np.diff(marks[24:24 + nr + 1])[:12] / 1.965e3 if nr >= 12 else np.pad(np.diff(marks[24:24 + nr]) / 1.965e3, (0, 12 - (nr - 1)), constant_values=np.nan)[:12])
+        if have_vox:
+            pkg.lib().limu_debug_vox_marks(vmarks.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+            vrows.append(np.diff(vmarks[:4]) / 1e3)
 r = np.array(rows)
 names = ["iqr", "icp_loop", "insert_claim", "insert_place", "evict_sweep"]
 print({n: round(float(v), 2) for n, v in zip(names, r.mean(axis=0))}, "total_us", round(float(r.sum(axis=1).mean()), 2), "iters/scan", np.mean(iters),
@@ -38,5 +45,8 @@ if os.environ.get("LIMU_CLUSTER_LOOP", "0") not in ("", "0"):
 else:
     print("classic shape, iteration 2 of the last scan (SM cycles of CTA 0, 1965 MHz): pass of warp 0", cyc(6, 7), "| pass end -> S1", cyc(7, 11), "| CTA row + grid barrier", cyc(11, 12),
           "| fold", cyc(12, 8), "| ldlt", cyc(8, 9), "| exp", cyc(9, 10), "| -> S2", cyc(10, 15), "| whole round (pass start -> S2)", cyc(6, 15),
-          "| tail of the solver warp ends", cyc(15, 14), "cycles after S2")
+          "| tail of the solver warp (its own clock)", cyc(13, 14))
+print("rounds of the Gauss-Newton loop (us, CTA 0, mean over scans; nan = fewer rounds):", [round(float(x), 2) for x in np.nanmean(np.array(rounds), axis=0)])
+if vrows:
+    print("k_voxelize phases (us; plain launch, 1024-thread CTAs): P1 deskew + claim | P2 flags, counts, scatter, claim 2 | P3 un-claim, flags, counts, scatter:", [round(float(x), 2) for x in np.mean(np.array(vrows), axis=0)], "total", round(float(np.sum(np.mean(np.array(vrows), axis=0))), 2))
 print("IQR phase of the last scan (SM cycles of CTA 0): squared ranges + ranking", cyc(16, 17), "| barrier of the loop CTAs", cyc(17, 18), "| local compaction (+ keypoints written out)", cyc(18, 19))
