@@ -14,7 +14,8 @@ struct FrameFusion {
     unsigned long long upd_birth_base;
     double *twist_out;         // non-null: leave log(last_pose^-1 * new_pose) here for the NEXT scan's deskew (delta_pose, deskew.cpp:14)
     double last_pose[7];       // poses.back() before this scan
-    unsigned int *loop_flag;   // non-null: the kernel stores loop_seq here once pose and twist are in memory (what k_gate waits for)
+    unsigned int *loop_flag;   // non-null: the kernel stores loop_seq here as soon as its Gauss-Newton loop is over (what k_gate waits for) ...
+    unsigned int *twist_flag;  // ... and here once twist_out is in memory
     unsigned int loop_seq;
     DevStatus *status;         // the frame kernel's status word (per odometry handle); nullptr = the context's
     int allow_cluster;         // LIMU_OPT_CLUSTER_LOOP: the cluster latency shape may be used (registration.cu, k_frame_cluster)

@@ -51,12 +51,12 @@ static double rotation_angle(const Pose &T) {
 // Device result block of one handle (per HANDLE: two handles of one context may interleave their scans). 28 ints, then 13 doubles:
 //   [0] n_down, [1] n_src0 of the scans with parity 0     [20] [21] the same for parity 1 (consecutive scans alternate: in the pipelined
 //   [2] n_keypoints (written by the loop kernel)                    path the next scan's k_voxelize runs while this scan's update reads its count)
-//   [3] the loop flag: sequence number of the last Gauss-Newton loop whose pose and deskew twist are in memory (k_gate waits for it)
+//   [3] the loop flag: sequence number of the last Gauss-Newton loop that is over (k_gate waits for it); [22] the same once its deskew twist is in memory
 //   [4..7] / [24..27] status word of the map update of a parity-0 / parity-1 scan
 //   [8..19] three status words k_voxelize rotates through
 //   doubles 14..26: pose + loop statistics (out13).     ONE copy of RES_DOUBLES per scan.
 namespace {
-constexpr int RES_CNT1 = 20, RES_FLAG = 3, RES_UPD_ST0 = 4, RES_UPD_ST1 = 24, RES_VOX_ST = 8, RES_OUT = 14, RES_DOUBLES = 27;
+constexpr int RES_CNT1 = 20, RES_FLAG = 3, RES_TWIST_FLAG = 22, RES_UPD_ST0 = 4, RES_UPD_ST1 = 24, RES_VOX_ST = 8, RES_OUT = 14, RES_DOUBLES = 27;
 inline int *res_counts(int *cnt, int par) { return cnt + (par ? RES_CNT1 : 0); }
 inline limu::DevStatus *res_update_status(int *cnt, int par) { return reinterpret_cast<limu::DevStatus *>(cnt + (par ? RES_UPD_ST1 : RES_UPD_ST0)); }
 }  // namespace
@@ -359,6 +359,7 @@ static int odom_launch_loop(limu_odom *o, int par, int64_t n, const Pose &init, 
     fuse.iqr_in = o->src0[par].as<double>(); fuse.iqr_n = counts + 1; fuse.iqr_d2 = o->d2.as<double>(); fuse.iqr_out = o->src[par].as<double>(); fuse.iqr_count = cnt + 2;
     fuse.twist_out = o->twist_next.as<double>();
     fuse.loop_flag = reinterpret_cast<unsigned int *>(cnt + RES_FLAG);
+    fuse.twist_flag = reinterpret_cast<unsigned int *>(cnt + RES_TWIST_FLAG);
     fuse.loop_seq = ++o->loop_seq;
     pose_store(last, fuse.last_pose);
     double init7[7];
@@ -464,7 +465,8 @@ static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n,
         int w = 0;
         if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->pev_vox[npar][0], o->vox_stream));   // (behind the gate: the kernel's own time)
         LIMU_TRY(voxelize_device(c, o->vx, next_ptr, 0, 0, nullptr, next_deskew, nullptr, next_n, v, o->frame.as<double>(), o->down[npar].as<double>(), o->src0[npar].as<double>(),
-                                 res_counts(cnt, npar), next_deskew ? o->twist_next.as<double>() : nullptr, vox_status, &w, o->vox_stream, true));
+                                 res_counts(cnt, npar), next_deskew ? o->twist_next.as<double>() : nullptr, vox_status, &w, o->vox_stream, true,
+                                 reinterpret_cast<unsigned int *>(cnt + RES_TWIST_FLAG), my_seq));
         if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->pev_vox[npar][1], o->vox_stream)); o->pev_vox_used[npar] = true; }
         LIMU_CUDA_TRY(cudaEventRecord(o->vox_done[npar], o->vox_stream));
         ah.vox = true; ah.ptr = next_ptr; ah.n = next_n; ah.deskewed = next_deskew; ah.slot = next_slot; ah.par = npar; ah.vox_word = w;

@@ -84,7 +84,8 @@ struct IcpArgs {
     int icp_blocks;
     double *twist_out;          // see FrameFusion
     double last_pose[7];
-    unsigned int *loop_flag;    // non-null: set to loop_seq (release, GPU scope) once pose and twist_out of this launch are in memory
+    unsigned int *loop_flag;    // non-null: set to loop_seq the moment the Gauss-Newton loop of this launch is over (what k_gate waits for) ...
+    unsigned int *twist_flag;   // ... and this one (release, GPU scope) once twist_out is in memory, a few microseconds later
     unsigned int loop_seq;
     double *est_trace;          // optional [max_iter][7]
     long long *ncorr_trace;     // optional [max_iter]
@@ -595,7 +596,7 @@ __device__ unsigned long long g_frame_marks[72];   // [24 + j]: clock of CTA 0 /
 // (two passes separated by a grid barrier) + eviction around the new position. Every CTA of the grid takes part (those that sat out the
 // Gauss-Newton loop join here); everybody reads the new pose that CTA 0 published in A.out. E: 7 doubles of shared memory.
 // The next scan deskews with delta_pose(poses[N-2], poses[N-1]) = log(last^-1 * new) (deskew.cpp:14): left on the device for a k_voxelize
-// that is already enqueued, then the flag its gate kernel waits for (voxelize.cu, k_gate). One thread (~3 us of scalar code).
+// that is already enqueued (it waits for twist_flag in front of its first phase). One thread (~3 us of scalar code).
 __device__ __forceinline__ void publish_twist(const IcpArgs &A, const Pose &np) {
     if (A.twist_out) {
         double tw[6];
@@ -603,9 +604,9 @@ __device__ __forceinline__ void publish_twist(const IcpArgs &A, const Pose &np) 
 #pragma unroll
         for (int k = 0; k < 6; ++k) A.twist_out[k] = tw[k];
     }
-    if (A.loop_flag) {
+    if (A.twist_flag) {
         __threadfence();
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.loop_flag), "r"(A.loop_seq) : "memory");
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.twist_flag), "r"(A.loop_seq) : "memory");
     }
 }
 
@@ -694,6 +695,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
     __shared__ double S[NSX];
     __shared__ double E[7], Tinit[7], Ticp[7], xs[8];
     __shared__ int done;
+    __shared__ int verdict;   // on the iteration just solved: 1 converged, 0 not, 2 too close to call from the twist itself (see below)
     __shared__ int comm_dead;
     __shared__ IqrSmem iqr_sm;
     GridSync gs{A.barrier, 0u, gridDim.x};
@@ -730,7 +732,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
     const bool run_icp = !(__ldcg(A.map_counters) == 0ull || A.max_iter <= 0);   // ICP :99-100: empty map -> init_guess
     if (threadIdx.x < 7) { Tinit[threadIdx.x] = A.init_pose[threadIdx.x]; Ticp[threadIdx.x] = threadIdx.x == 3 ? 1.0 : 0.0; }
     if (threadIdx.x < NSX) S[threadIdx.x] = 0.0;
-    if (threadIdx.x == 0) comm_dead = 0;
+    if (threadIdx.x == 0) { comm_dead = 0; verdict = 0; done = 0; }
     __syncthreads();
     // Warps 0..QW-1 own the queries; the last warp is the SOLVER warp: it has no queries, solves the normal equations once the rows
     // are folded, publishes the estimate -- and then finishes T_icp, log(estimate) and the convergence test WHILE the query warps are
@@ -780,7 +782,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
             CW_MARK(13, QW);
             const Pose est = pose_load(E);
             if (lane == 0) pose_store(mul(est, pose_load(Ticp)), Ticp);
-            if (lane == 1) {
+            if (lane == 1 && verdict == 2) {
                 double lg[6];
                 se3_log(est, lg);
                 done = norm6(lg) < A.eps;
@@ -801,7 +803,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
         }
         __syncthreads();   // S1: CTA partial sums of pass j, and the verdict on iteration j-1
         CW_MARK(11, 0);
-        if (j > 0 && done) { converged = 1; break; }   // (the pass just made belongs to an iteration that does not exist)
+        if (j > 0 && verdict == 2 && done) { converged = 1; break; }   // (the pass just made belongs to an iteration that does not exist)
         if (no_more) break;
         const unsigned int stamp = 0x80000000u | ((A.ll_stamp_base + (unsigned int)j) & 0x7FFFFFFFu);
         unsigned long long *rows = reinterpret_cast<unsigned long long *>(A.partials) + (size_t)(j & 1) * A.icp_blocks * (2 * NSX);
@@ -911,17 +913,47 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
             // estimate = SE3::exp(x) (vector6d_to_mat4d :91): rotation half on lane 0, translation half on lane 1
             if (lane == 0) { double th_; se3_exp_rotation(xs, E, &th_); }
             if (lane == 1) se3_exp_translation(xs, E + 4);
+            // Convergence, |log(estimate)| < eps (:124), from the twist itself: log(exp(x)) is x up to rounding (rotation below pi), so
+            // unless |x| lies within 1e-6 eps of eps -- or the rotation is large -- the verdict is known NOW and the loop need not make
+            // one more pass just to learn that it was over. Too close to call: the tail takes the logarithm, as the reference does.
+            if (lane == 2) {
+                const double nx = norm6(xs), nw = sqrt(xs[3] * xs[3] + xs[4] * xs[4] + xs[5] * xs[5]);
+                verdict = !(nw < 3.0) ? 2 : (nx < A.eps * (1.0 - 1e-6) ? 1 : (nx > A.eps * (1.0 + 1e-6) ? 0 : 2));
+            }
             __syncwarp();
             CW_MARK(10, QW);
         }
         __syncthreads();   // S2: the estimate is visible to the query warps
         CW_MARK(15, 0);
         ++j;
+        if (verdict == 1) {   // iteration j-1 converged: finish its bookkeeping (the tail above, without a pass beside it) and leave
+            if (warp == QW) {
+                const Pose est = pose_load(E);
+                if (lane == 0) pose_store(mul(est, pose_load(Ticp)), Ticp);
+                if (blockIdx.x == 0 && lane == 2) {
+                    if (A.est_trace) pose_store(est, A.est_trace + 7 * (size_t)(j - 1));
+                    if (A.ncorr_trace) A.ncorr_trace[j - 1] = (long long)S[I_NCORR];
+                    if (A.hg_trace) {
+                        double H[36], g[6];
+                        if (PLANE) expand_plane_equations(S, H, g);
+                        else expand_normal_equations(S, H, g);
+                        double *o = A.hg_trace + 42 * (size_t)(j - 1);
+                        for (int k = 0; k < 36; ++k) o[k] = H[k];
+                        for (int k = 0; k < 6; ++k) o[36 + k] = g[k];
+                    }
+                }
+            }
+            converged = 1;
+            __syncthreads();
+            break;
+        }
     }
     FT_MARK(2);
     // new_pose = T_icp * init_guess (:129); with an empty map the loop did not run and this is init_guess itself (:99-100). A launch without
     // the map-update epilogue (pipelined odometry) publishes the next scan's deskew twist here: the next scan's k_voxelize starts on it.
     if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // release the next scan's k_voxelize now: its launch latency covers the few microseconds until the twist is there
+        if (!A.upd_down && A.loop_flag) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(A.loop_flag), "r"(A.loop_seq) : "memory");
         const Pose np = run_icp ? mul(pose_load(Ticp), pose_load(Tinit)) : pose_load(Tinit);
         pose_store(np, A.out);
         A.out[7] = (double)j; A.out[8] = (double)converged; A.out[9] = S[I_NCORR]; A.out[10] = S[I_NCORR + 1]; A.out[11] = S[I_NCORR + 2]; A.out[12] = (double)n;
@@ -1316,7 +1348,7 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
         if (fuse->status) A.status = fuse->status;
         A.upd_capacity = (long long)m->capacity; A.upd_max_distance = m->max_distance;
         A.twist_out = fuse->twist_out;
-        A.loop_flag = fuse->loop_flag; A.loop_seq = fuse->loop_seq;
+        A.loop_flag = fuse->loop_flag; A.twist_flag = fuse->twist_flag; A.loop_seq = fuse->loop_seq;
         for (int k = 0; k < 7; ++k) A.last_pose[k] = fuse->last_pose[k];
     }
     void *args[] = {&A};

@@ -30,13 +30,17 @@ constexpr int VX_BLOCK = LIMU_VX_BLOCK;
 // The pipelined odometry path (odometry.cu) runs the NEXT scan's launch beside the current scan's map update: 1024 threads x 64 registers
 // are a whole register file, so that launch uses half-size CTAs (one per SM) and leaves room for the update kernel's CTA.
 constexpr int VX_BLOCK_BESIDE = 512;
+constexpr int VX_TILE = 1024;            // points per tile in both shapes (1024 x 1 and 512 x 2)
+static_assert(VX_BLOCK == VX_TILE, "the full-size launch handles one point per thread");
 
 struct VoxelizeArgs {
     const void *raw;            // mode 0: float4 {x,y,z,t}; mode 1: records `stride` bytes apart + ts; mode 2: double xyz (already a frame)
     const double *ts;
     int mode, stride, deskew;
     double twist[6];            // by value, read when deskew != 0
-    const double *twist_dev;    // non-null: the twist was left in device memory by the previous scan's frame kernel (speculative launch)
+    const double *twist_dev;    // non-null: the twist is left in device memory by the previous scan's loop kernel
+    const unsigned int *twist_flag;   // non-null: ... and is only there once this word has reached twist_seq
+    unsigned int twist_seq;
     int64_t n;
     double vs1, vs2;            // 0.5 v and 1.5 v (icp.cpp:129-130)
     double *frame, *down, *src0;
@@ -55,31 +59,70 @@ struct VoxelizeArgs {
     DevStatus *st_next;         // non-null: the status word of the NEXT launch of this pipeline (two words alternate); zeroed late in this launch
 };
 
-__device__ __forceinline__ unsigned int claim_min(unsigned long long *keys, unsigned int *minidx, unsigned int mask, int shift, const V3 &p, double vs,
-                                                  unsigned int index, DevStatus *st) {
-    const int kx = vox_index(p.x, vs), ky = vox_index(p.y, vs), kz = vox_index(p.z, vs);
-    // NaN: the reference's (int) cast gives INT_MIN on x86-64 (cvttsd2si), far outside the packed range; cvt.rzi gives 0
-    if (!key_in_range(kx, ky, kz) || p.x != p.x || p.y != p.y || p.z != p.z) { st->key_range = 1; return PEND_NONE; }
-    const unsigned long long key = pack_key(kx, ky, kz);
-    unsigned int s = slot_of(key, shift);
-    for (unsigned int probes = 0; probes <= mask; ++probes) {
-        unsigned long long cur = __ldcg(&keys[s]);
-        if (cur == KEY_EMPTY) {
-            cur = atomicCAS(&keys[s], KEY_EMPTY, key);
-            if (cur == KEY_EMPTY) cur = key;
+// Claim the voxel of p in a scan-local table and note `index` as a candidate for its first point (atomicMin). Split in two so that a thread
+// with several points has all their first probes in flight together: claim_issue sends ONE compare-and-swap per point (it both finds and
+// claims: the slot is the voxel's if it was empty or already held the key), claim_finish looks at the answer and walks on in the rare case
+// of a collision.
+struct Claim {
+    unsigned long long key, cur;
+    unsigned int s;
+    bool valid;
+};
+__device__ __forceinline__ Claim claim_issue(unsigned long long *keys, int shift, const V3 &p, double vs, bool active, DevStatus *st) {
+    Claim c;
+    c.valid = false; c.key = KEY_EMPTY; c.cur = KEY_EMPTY; c.s = 0u;
+    if (active) {
+        const int kx = vox_index(p.x, vs), ky = vox_index(p.y, vs), kz = vox_index(p.z, vs);
+        // NaN: the reference's (int) cast gives INT_MIN on x86-64 (cvttsd2si), far outside the packed range; cvt.rzi gives 0
+        if (!key_in_range(kx, ky, kz) || p.x != p.x || p.y != p.y || p.z != p.z) st->key_range = 1;
+        else {
+            c.valid = true;
+            c.key = pack_key(kx, ky, kz);
+            c.s = slot_of(c.key, shift);
+            c.cur = atomicCAS(&keys[c.s], KEY_EMPTY, c.key);
         }
-        if (cur == key) { atomicMin(&minidx[s], index); return s; }
+    }
+    return c;
+}
+__device__ __forceinline__ unsigned int claim_finish(const Claim &c, unsigned long long *keys, unsigned int *minidx, unsigned int mask, unsigned int index, DevStatus *st) {
+    if (!c.valid) return PEND_NONE;
+    unsigned int s = c.s;
+    unsigned long long cur = c.cur;
+    for (unsigned int probes = 0; probes <= mask; ++probes) {
+        if (cur == KEY_EMPTY || cur == c.key) { atomicMin(&minidx[s], index); return s; }
         s = (s + 1) & mask;
+        cur = atomicCAS(&keys[s], KEY_EMPTY, c.key);
     }
     st->table_full = 1;
     return PEND_NONE;
 }
 
+// exclusive prefix of small per-thread counts over the CTA (thread order); *total = their sum
+__device__ __forceinline__ int block_exclusive_scan_count(int c, int *total, int *warp_sums /* 32 ints shared */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        const int v = lane < nw ? warp_sums[lane] : 0;
+        int wi = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += t; }
+        warp_sums[lane] = wi - v;
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    return warp_sums[warp] + incl - c;
+}
+
 // exclusive prefix of tile counts: sum of counts[0..tile) computed by the whole CTA; a word is re-read until it is this launch's
-template <int VX_BLOCK>
+template <int BLOCK>
 __device__ __forceinline__ int tile_base(const unsigned long long *words, int tile, unsigned int epoch, int *ws /* 32 ints */) {
     int part = 0;
-    for (int b = threadIdx.x; b < tile; b += VX_BLOCK) {
+    for (int b = threadIdx.x; b < tile; b += BLOCK) {
         unsigned long long w;
         do {
             asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(words + b) : "memory");
@@ -93,7 +136,7 @@ __device__ __forceinline__ int tile_base(const unsigned long long *words, int ti
     __syncthreads();
     int v = 0;
 #pragma unroll
-    for (int w = 0; w < VX_BLOCK / 32; ++w) v += ws[w];
+    for (int w = 0; w < BLOCK / 32; ++w) v += ws[w];
     __syncthreads();
     return v;
 }
@@ -108,14 +151,17 @@ __device__ unsigned long long g_vox_marks[8];   // globaltimer of thread 0 of CT
 #define VX_MARK(k) do {} while (0)
 #endif
 
-template <int VX_BLOCK>
-static __global__ void __launch_bounds__(VX_BLOCK, 1024 / VX_BLOCK) k_voxelize(const VoxelizeArgs A) {
+// BLOCK threads handle tiles of VX_TILE = BLOCK * ITEMS consecutive points, ITEMS per thread: the full-size launch is 1024 x 1, the launch
+// that runs beside the map update 512 x 2 -- half the registers per SM, the same tiles, and a thread's two claims in flight together.
+template <int BLOCK, int ITEMS>
+static __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_voxelize(const VoxelizeArgs A) {
+    constexpr int TILE = BLOCK * ITEMS;
     __shared__ int ws[32];
     __shared__ int total;
     GridSync gs{A.barrier, 0u, gridDim.x};
     const int64_t n = A.n;
-    const int64_t gtid = (int64_t)blockIdx.x * VX_BLOCK + threadIdx.x, gthreads = (int64_t)gridDim.x * VX_BLOCK;
-    const int ntiles = (int)((n + VX_BLOCK - 1) / VX_BLOCK);
+    const int64_t gtid = (int64_t)blockIdx.x * BLOCK + threadIdx.x, gthreads = (int64_t)gridDim.x * BLOCK;
+    const int ntiles = (int)((n + TILE - 1) / TILE);
     VX_MARK(0);
     // un-claim what the previous launch left in ITS stage-2 table (this launch uses the other one): no barrier needed
     {
@@ -132,53 +178,97 @@ static __global__ void __launch_bounds__(VX_BLOCK, 1024 / VX_BLOCK) k_voxelize(c
 #pragma unroll
             for (int k = 0; k < 6; ++k) tw[k] = A.twist[k];
             if (A.twist_dev) {
+                if (A.twist_flag) {   // the twist is still being computed by the loop kernel that released this launch (a few microseconds at most)
+                    if (threadIdx.x == 0) {
+                        unsigned long long t0, t1;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                        for (;;) {
+                            unsigned int v;
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(A.twist_flag) : "memory");
+                            if ((int)(v - A.twist_seq) >= 0) break;
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                            if (t1 - t0 > 5000000000ull) break;   // (that kernel died: the host will see its error)
+                        }
+                    }
+                    __syncthreads();
+                }
 #pragma unroll
                 for (int k = 0; k < 6; ++k) tw[k] = __ldcg(A.twist_dev + k);
             }
         }
-        for (int64_t i = gtid; i < n; i += gthreads) {
-            V3 p;
-            double t = 0.0;
-            if (A.mode == 0) {
-                const float4 q = __ldg(reinterpret_cast<const float4 *>(A.raw) + i);
-                p = V3{(double)q.x, (double)q.y, (double)q.z};
-                t = (double)q.w;
-            } else if (A.mode == 1) {
-                const float *q = reinterpret_cast<const float *>(static_cast<const unsigned char *>(A.raw) + (size_t)i * A.stride);
-                p = V3{(double)q[0], (double)q[1], (double)q[2]};
-                if (A.deskew) t = A.ts[i];
-            } else {
-                const double *q = static_cast<const double *>(A.raw) + 3 * i;
-                p = V3{q[0], q[1], q[2]};
-            }
-            if (A.deskew) {
-                const double s = t - 0.5;   // mid_pose_timestamp, deskew.hpp:12
-                double st[6];
+        for (int64_t i0 = gtid; i0 < n; i0 += (int64_t)ITEMS * gthreads) {
+            V3 p[ITEMS];
+            Claim c[ITEMS];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) st[k] = s * tw[k];
-                p = apply(se3_exp(st), p);
+            for (int u = 0; u < ITEMS; ++u) {
+                const int64_t i = i0 + (int64_t)u * gthreads;
+                const bool on = i < n;
+                double t = 0.0;
+                p[u] = V3{0.0, 0.0, 0.0};
+                if (on) {
+                    if (A.mode == 0) {
+                        const float4 q = __ldg(reinterpret_cast<const float4 *>(A.raw) + i);
+                        p[u] = V3{(double)q.x, (double)q.y, (double)q.z};
+                        t = (double)q.w;
+                    } else if (A.mode == 1) {
+                        const float *q = reinterpret_cast<const float *>(static_cast<const unsigned char *>(A.raw) + (size_t)i * A.stride);
+                        p[u] = V3{(double)q[0], (double)q[1], (double)q[2]};
+                        if (A.deskew) t = A.ts[i];
+                    } else {
+                        const double *q = static_cast<const double *>(A.raw) + 3 * i;
+                        p[u] = V3{q[0], q[1], q[2]};
+                    }
+                    if (A.deskew) {
+                        const double s = t - 0.5;   // mid_pose_timestamp, deskew.hpp:12
+                        double st[6];
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) st[k] = s * tw[k];
+                        p[u] = apply(se3_exp(st), p[u]);
+                    }
+                    A.frame[3 * i] = p[u].x; A.frame[3 * i + 1] = p[u].y; A.frame[3 * i + 2] = p[u].z;
+                }
+                c[u] = claim_issue(A.keys1, A.shift1, p[u], A.vs1, on, A.st);
             }
-            A.frame[3 * i] = p.x; A.frame[3 * i + 1] = p.y; A.frame[3 * i + 2] = p.z;
-            A.pslot1[i] = claim_min(A.keys1, A.min1, A.mask1, A.shift1, p, A.vs1, (unsigned int)i, A.st);
+#pragma unroll
+            for (int u = 0; u < ITEMS; ++u) {
+                const int64_t i = i0 + (int64_t)u * gthreads;
+                if (i < n) A.pslot1[i] = claim_finish(c[u], A.keys1, A.min1, A.mask1, (unsigned int)i, A.st);
+            }
         }
     }
     gs.sync();
     VX_MARK(1);
-    // P2: a point survives stage 1 iff it holds its voxel's smallest input index. Per VX_BLOCK-point tile: flags, count (published),
-    // ordered scatter -> down[]; each winner immediately claims its 1.5 v voxel with its OUTPUT index
+    // P2: a point survives stage 1 iff it holds its voxel's smallest input index. Per tile: flags, count (published), ordered scatter
+    // -> down[]; each winner immediately claims its 1.5 v voxel with its OUTPUT index. A thread owns ITEMS consecutive points of the tile.
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t i = (int64_t)tile * VX_BLOCK + threadIdx.x;
-        int f = 0;
-        if (i < n) { const unsigned int s = A.pslot1[i]; f = s != PEND_NONE && __ldcg(A.min1 + s) == (unsigned int)i; }
-        const int r = block_exclusive_scan_flag(f, &total, ws);
-        if (threadIdx.x == 0) tile_publish(A.tile1 + tile, A.epoch, total);
-        const int base = tile_base<VX_BLOCK>(A.tile1, tile, A.epoch, ws);
-        if (f) {
-            const int j = base + r;
-            const V3 p{A.frame[3 * i], A.frame[3 * i + 1], A.frame[3 * i + 2]};
-            A.down[3 * (size_t)j] = p.x; A.down[3 * (size_t)j + 1] = p.y; A.down[3 * (size_t)j + 2] = p.z;
-            A.pslot2[j] = claim_min(A.keys2, A.min2, A.mask2, A.shift2, p, A.vs2, (unsigned int)j, A.st);
+        const int64_t e0 = (int64_t)tile * TILE + (int64_t)threadIdx.x * ITEMS;
+        int f[ITEMS], cnt = 0;
+#pragma unroll
+        for (int u = 0; u < ITEMS; ++u) {
+            const int64_t i = e0 + u;
+            f[u] = 0;
+            if (i < n) { const unsigned int s = A.pslot1[i]; f[u] = s != PEND_NONE && __ldcg(A.min1 + s) == (unsigned int)i; }
+            cnt += f[u];
         }
+        const int r = block_exclusive_scan_count(cnt, &total, ws);
+        if (threadIdx.x == 0) tile_publish(A.tile1 + tile, A.epoch, total);
+        const int base = tile_base<BLOCK>(A.tile1, tile, A.epoch, ws);
+        V3 p[ITEMS];
+        Claim c[ITEMS];
+        int j = base + r;
+#pragma unroll
+        for (int u = 0; u < ITEMS; ++u) {
+            const int64_t i = e0 + u;
+            p[u] = V3{0.0, 0.0, 0.0};
+            if (f[u]) {
+                p[u] = V3{A.frame[3 * i], A.frame[3 * i + 1], A.frame[3 * i + 2]};
+                A.down[3 * (size_t)(j + (u ? f[0] : 0))] = p[u].x; A.down[3 * (size_t)(j + (u ? f[0] : 0)) + 1] = p[u].y; A.down[3 * (size_t)(j + (u ? f[0] : 0)) + 2] = p[u].z;
+            }
+            c[u] = claim_issue(A.keys2, A.shift2, p[u], A.vs2, f[u] != 0, A.st);
+        }
+#pragma unroll
+        for (int u = 0; u < ITEMS; ++u)
+            if (f[u]) { const int jj = j + (u ? f[0] : 0); A.pslot2[jj] = claim_finish(c[u], A.keys2, A.min2, A.mask2, (unsigned int)jj, A.st); }
         if (tile == ntiles - 1 && threadIdx.x == 0) { A.counts[0] = base + total; *A.nd_this = base + total; }
         __syncthreads();
     }
@@ -193,18 +283,26 @@ static __global__ void __launch_bounds__(VX_BLOCK, 1024 / VX_BLOCK) k_voxelize(c
     }
     // P3: the same flag -> count -> scatter over down[] for stage 2
     const int nd = __ldcg(A.counts);
-    const int ntiles2 = (nd + VX_BLOCK - 1) / VX_BLOCK;
+    const int ntiles2 = (nd + TILE - 1) / TILE;
     for (int tile = blockIdx.x; tile < ntiles2; tile += gridDim.x) {
-        const int j = tile * VX_BLOCK + threadIdx.x;
-        int f = 0;
-        if (j < nd) { const unsigned int s = __ldcg(A.pslot2 + j); f = s != PEND_NONE && __ldcg(A.min2 + s) == (unsigned int)j; }
-        const int r = block_exclusive_scan_flag(f, &total, ws);
-        if (threadIdx.x == 0) tile_publish(A.tile2 + tile, A.epoch, total);
-        const int base = tile_base<VX_BLOCK>(A.tile2, tile, A.epoch, ws);
-        if (f) {
-            const size_t k = (size_t)(base + r);
-            A.src0[3 * k] = __ldcg(A.down + 3 * (size_t)j); A.src0[3 * k + 1] = __ldcg(A.down + 3 * (size_t)j + 1); A.src0[3 * k + 2] = __ldcg(A.down + 3 * (size_t)j + 2);
+        const int e0 = tile * TILE + (int)threadIdx.x * ITEMS;
+        int f[ITEMS], cnt = 0;
+#pragma unroll
+        for (int u = 0; u < ITEMS; ++u) {
+            const int j = e0 + u;
+            f[u] = 0;
+            if (j < nd) { const unsigned int s = __ldcg(A.pslot2 + j); f[u] = s != PEND_NONE && __ldcg(A.min2 + s) == (unsigned int)j; }
+            cnt += f[u];
         }
+        const int r = block_exclusive_scan_count(cnt, &total, ws);
+        if (threadIdx.x == 0) tile_publish(A.tile2 + tile, A.epoch, total);
+        const int base = tile_base<BLOCK>(A.tile2, tile, A.epoch, ws);
+#pragma unroll
+        for (int u = 0; u < ITEMS; ++u)
+            if (f[u]) {
+                const size_t k = (size_t)(base + r + (u ? f[0] : 0)), j = (size_t)(e0 + u);
+                A.src0[3 * k] = __ldcg(A.down + 3 * j); A.src0[3 * k + 1] = __ldcg(A.down + 3 * j + 1); A.src0[3 * k + 2] = __ldcg(A.down + 3 * j + 2);
+            }
         if (tile == ntiles2 - 1 && threadIdx.x == 0) A.counts[1] = base + total;
         __syncthreads();
     }
@@ -256,7 +354,7 @@ static int64_t pow2_slots(int64_t n) { int64_t p = 1024; while (p < 2 * n) p <<=
 // Enqueue the fused kernel. raw/ts/twist are device pointers; outputs: frame (n x 3), down, src0, counts[0..1].
 int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int mode, int stride, const double *ts_dev, int deskew, const double *twist_host,
                     int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev, const double *twist_dev, DevStatus *own_status, int *status_used,
-                    cudaStream_t stream, bool beside) {
+                    cudaStream_t stream, bool beside, const unsigned int *twist_flag, unsigned int twist_seq) {
     if (!stream) stream = c->stream;
     if (n <= 0) {
         LIMU_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int), stream));
@@ -271,14 +369,13 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     }
     if (g_vx_blocks_per_sm == 0) {
         int b = 0;
-        LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_voxelize<VX_BLOCK>, VX_BLOCK, 0));
+        LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_voxelize<VX_BLOCK, 1>, VX_BLOCK, 0));
         g_vx_blocks_per_sm = std::max(1, std::min(b, 1024 / VX_BLOCK));
     }
-    const int block = beside ? VX_BLOCK_BESIDE : VX_BLOCK;
     const int64_t C1 = pow2_slots(n), C2 = pow2_slots(n);
     int lg = 0;
     while ((int64_t(1) << lg) < C1) ++lg;
-    const int ntiles = div_up(n, block);
+    const int ntiles = div_up(n, VX_TILE);
     {   // three tables [u64 key x cap | u32 min-index x cap] at offsets fixed by the ALLOCATED capacity (claimed slots are remembered as indices), all-ones
         // = clean at rest. Whenever one of the buffers is re-allocated the memory of what the previous launch claimed is gone: start over clean.
         bool reset = false;
@@ -296,7 +393,7 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
         // [16 ints: barrier words 0-1, stage-2 claim counts of the two parities 4-5 | per-tile count words of the two stages]; the kernel keeps
         // the barrier words at zero, and a count word is only believed when it carries the epoch of the launch that reads it
         before = sc.tiles.p;
-        LIMU_TRY(sc.tiles.reserve((size_t)div_up(n, VX_BLOCK_BESIDE) * 16 + 128, stream));   // (sized for the smaller of the two tile sizes)
+        LIMU_TRY(sc.tiles.reserve((size_t)ntiles * 16 + 128, stream));
         if (sc.tiles.p != before) reset = true;
         if (reset) {
             LIMU_CUDA_TRY(cudaMemsetAsync(sc.table.p, 0xFF, (size_t)sc.cap_slots * 12 * 3, stream));
@@ -309,6 +406,7 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     A.raw = raw_dev; A.ts = ts_dev; A.mode = mode; A.stride = stride; A.deskew = deskew; A.n = n;
     for (int k = 0; k < 6; ++k) A.twist[k] = (deskew && twist_host) ? twist_host[k] : 0.0;
     A.twist_dev = deskew ? twist_dev : nullptr;
+    A.twist_flag = (deskew && twist_dev) ? twist_flag : nullptr; A.twist_seq = twist_seq;
     A.vs1 = v * 0.5; A.vs2 = v * 1.5;
     A.frame = frame_dev; A.down = down_dev; A.src0 = src0_dev;
     {
@@ -340,8 +438,8 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     if (status_used) *status_used = w;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->sm_count * (beside ? 1 : g_vx_blocks_per_sm));
     void *args[] = {&A};
-    if (beside) LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize<VX_BLOCK_BESIDE>, dim3(grid), dim3(VX_BLOCK_BESIDE), args, 0, stream));
-    else LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize<VX_BLOCK>, dim3(grid), dim3(VX_BLOCK), args, 0, stream));
+    if (beside) LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize<VX_BLOCK_BESIDE, VX_TILE / VX_BLOCK_BESIDE>, dim3(grid), dim3(VX_BLOCK_BESIDE), args, 0, stream));
+    else LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize<VX_BLOCK, 1>, dim3(grid), dim3(VX_BLOCK), args, 0, stream));
     LIMU_LAUNCHED();
     return LIMU_OK;
 }

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# GPU call Q (one B200): k_voxelize with two grid barriers (self-validating tile counts) on the pipelined path. GPU suite, bench, phase timing.
+# GPU call Q/R (one B200): pipelined path; k_voxelize variants; GPU suite, bench, phase timing.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 T="${1:-q}"
