@@ -11,6 +11,30 @@
 #include "../../include/limu_cuda.h"
 #include "se3.cuh"
 
+// Instrumented build only (make phase): every translation unit with kernels worth tracing keeps a ring of (id << 56 | globaltimer) records,
+// appended by thread 0 of CTA 0, and exports a getter; tools/frame_phase_timing.py merges the rings into one timeline.
+#ifdef LIMU_ICP_PHASE_TIMING
+#define LIMU_TRACE_RING(getter)                                                                         \
+    static __device__ unsigned long long g_trace[2048];                                                 \
+    static __device__ unsigned int g_trace_n;                                                           \
+    extern "C" int getter(unsigned long long *out /* 2048 */, unsigned int *n) {                        \
+        if (cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 2048) != cudaSuccess) return -1; \
+        if (cudaMemcpyFromSymbol(n, g_trace_n, sizeof(unsigned int)) != cudaSuccess) return -1;         \
+        return 0;                                                                                       \
+    }
+#define LIMU_TRACE(id)                                                                                  \
+    do {                                                                                                \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                                                      \
+            unsigned long long _t;                                                                      \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                      \
+            g_trace[atomicAdd(&g_trace_n, 1u) & 2047u] = ((unsigned long long)(id) << 56) | (_t & 0x00FFFFFFFFFFFFFFull); \
+        }                                                                                               \
+    } while (0)
+#else
+#define LIMU_TRACE_RING(getter)
+#define LIMU_TRACE(id) do {} while (0)
+#endif
+
 namespace limu {
 
 void set_error(const char *fmt, ...);

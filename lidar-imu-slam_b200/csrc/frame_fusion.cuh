@@ -17,6 +17,9 @@ struct FrameFusion {
     unsigned int *loop_flag;   // non-null: the kernel stores loop_seq here as soon as its Gauss-Newton loop is over (what k_gate waits for) ...
     unsigned int *twist_flag;  // ... and here once twist_out is in memory
     unsigned int loop_seq;
+    double *host_res;          // non-null (launches without the map update only): pinned host copy of res_block[0 .. res_doubles), word 31 <- loop_seq when it is complete
+    const double *res_block;
+    int res_doubles;
     DevStatus *status;         // the frame kernel's status word (per odometry handle); nullptr = the context's
     int allow_cluster;         // LIMU_OPT_CLUSTER_LOOP: the cluster latency shape may be used (registration.cu, k_frame_cluster)
 };

@@ -108,6 +108,7 @@ struct limu_odom {
     bool pev_vox_used[2] = {false, false}, pev_upd_used[2] = {false, false};
     double *h_res[2] = {nullptr, nullptr};  // pinned: the result block of a scan of either parity
     unsigned int loop_seq = 0;              // sequence number of the last loop launch of this handle
+    unsigned int loop_seq_of[2] = {0, 0};   // ... and of the last launch for either parity (what the host waits for in h_res[par][31])
     limu::DevBuf twist_next;                // 6 doubles written by the loop kernel
     int pending_update_par = -1;            // parity of a map update whose status word has not been read yet
     struct Ahead {                          // what is in flight for the scan the caller said comes next
@@ -334,6 +335,7 @@ static int odom_pipe_init(limu_odom *o) {
         LIMU_CUDA_TRY(cudaEventCreate(&o->pev_upd[k][0]));
         LIMU_CUDA_TRY(cudaEventCreate(&o->pev_upd[k][1]));
         LIMU_CUDA_TRY(cudaMallocHost(&o->h_res[k], 32 * sizeof(double)));
+        memset(o->h_res[k], 0, 32 * sizeof(double));
     }
     return odom_side_stream(o);
 }
@@ -360,6 +362,7 @@ static int odom_launch_loop(limu_odom *o, int par, int64_t n, const Pose &init, 
     fuse.twist_out = o->twist_next.as<double>();
     fuse.loop_flag = reinterpret_cast<unsigned int *>(cnt + RES_FLAG);
     fuse.twist_flag = reinterpret_cast<unsigned int *>(cnt + RES_TWIST_FLAG);
+    fuse.host_res = o->h_res[par]; fuse.res_block = o->res.as<double>(); fuse.res_doubles = RES_DOUBLES;
     fuse.loop_seq = ++o->loop_seq;
     pose_store(last, fuse.last_pose);
     double init7[7];
@@ -368,8 +371,29 @@ static int odom_launch_loop(limu_odom *o, int par, int64_t n, const Pose &init, 
     LIMU_TRY(icp_device(o->map, o->src[par].as<double>(), o->work.as<double>(), n, cnt + 2, init7, 3.0 * sigma, sigma / 3.0, o->cfg.icp_max_iteration,
                         o->cfg.estimation_threshold, o->partials.as<double>(), (size_t)rows, o->res.as<double>() + RES_OUT, o->nk_hint, nullptr, nullptr, nullptr, -1, &fuse,
                         o->cfg.icp_mode));
-    LIMU_CUDA_TRY(cudaMemcpyAsync(o->h_res[par], o->res.p, RES_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    // (no result copy in the stream: the kernel itself leaves the result block in pinned host memory, so the map update behind it starts at once)
     LIMU_CUDA_TRY(cudaEventRecord(o->loop_done[par], c->stream));
+    o->loop_seq_of[par] = o->loop_seq;
+    return LIMU_OK;
+}
+
+// Wait until the loop launched for parity `par` has left its result block in h_res[par] (it stores its sequence number behind the data).
+static int odom_wait_loop(limu_odom *o, int par) {
+    const volatile unsigned long long *flag = reinterpret_cast<const volatile unsigned long long *>(o->h_res[par]) + 31;
+    const unsigned long long want = o->loop_seq_of[par];
+    for (unsigned int spins = 1;; ++spins) {
+        if (*flag == want) break;
+        if ((spins & 0x3FFFu) == 0u) {   // now and then: is the kernel still alive?
+            const cudaError_t e = cudaEventQuery(o->loop_done[par]);
+            if (e == cudaSuccess) {
+                if (*flag == want) break;
+                set_error("registration kernel finished without publishing its result");
+                return LIMU_ERR_CUDA;
+            }
+            if (e != cudaErrorNotReady) { set_error("registration kernel failed: %s", cudaGetErrorString(e)); return LIMU_ERR_CUDA; }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
     return LIMU_OK;
 }
 
@@ -472,7 +496,8 @@ static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n,
         ah.vox = true; ah.ptr = next_ptr; ah.n = next_n; ah.deskewed = next_deskew; ah.slot = next_slot; ah.par = npar; ah.vox_word = w;
     }
     // 5. the one wait of the call: this scan's pose
-    LIMU_CUDA_TRY(cudaEventSynchronize(o->loop_done[par]));
+    LIMU_TRY(odom_wait_loop(o, par));
+    if (c->profiling) LIMU_CUDA_TRY(cudaEventSynchronize(o->loop_done[par]));   // (the stage events sit behind the kernel in the stream)
     LIMU_TRY(prof_collect(c));
     if (c->profiling) {
         float ms = 0.f;

@@ -34,6 +34,7 @@ constexpr int MBOX_MAX_RANKS = 8, MBOX_ROW = 24, MBOX_RING = 4;   // mailbox row
 
 }  // namespace limu
 #include "frame_fusion.cuh"
+LIMU_TRACE_RING(limu_debug_trace_reg)
 namespace limu {
 
 struct IcpArgs {
@@ -87,6 +88,9 @@ struct IcpArgs {
     unsigned int *loop_flag;    // non-null: set to loop_seq the moment the Gauss-Newton loop of this launch is over (what k_gate waits for) ...
     unsigned int *twist_flag;   // ... and this one (release, GPU scope) once twist_out is in memory, a few microseconds later
     unsigned int loop_seq;
+    double *host_res;           // non-null: pinned host memory; CTA 0 copies the handle's result block (res_block, res_doubles) there when the
+    const double *res_block;    // launch is over and then stores loop_seq into word 31 (system scope): the host reads its pose without a copy
+    int res_doubles;            // engine round trip in the stream, and the next kernel of the stream starts right behind this one
     double *est_trace;          // optional [max_iter][7]
     long long *ncorr_trace;     // optional [max_iter]
     double *hg_trace;           // optional [max_iter][42]
@@ -634,10 +638,12 @@ __device__ __forceinline__ void frame_update_epilogue(const IcpArgs &A, GridSync
     }
     gs.sync();
     FT_MARK(3);
+    LIMU_TRACE(21);
     for (int64_t i = gtid; i < nd; i += gthreads)
         insert_place_one(A.map, V3{A.upd_world[3 * i], A.upd_world[3 * i + 1], A.upd_world[3 * i + 2]}, (unsigned int)i, __ldcg(A.upd_pslot + i));
     gs.sync();
     FT_MARK(4);
+    LIMU_TRACE(22);
     // eviction (remove_points_from_far, voxel_hash_map.cpp:146-171) over the dense list of voxels (V entries, 4 B + one 16 B slot each)
     // instead of the C table slots: a scan that evicts nothing used to read the whole 16 MB slot array.
     const int64_t used = (int64_t)__ldcg(A.upd_counters + 3);
@@ -703,6 +709,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
     const bool icp_member = (int)blockIdx.x < A.icp_blocks;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FT_MARK(0);
+    LIMU_TRACE(1);
     __shared__ unsigned short qidx_s[SHAPE == 0 ? IQR_GRID_MAX : 1];
     int n_keypoints = -1;   // >= 0: the keypoints are IQR candidates qidx_s[0 .. n_keypoints) (known to the CTAs of the Gauss-Newton loop)
     if (A.iqr_in) {   // KissICP::iqr_processing (icp.cpp:88-124, :133)
@@ -728,6 +735,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
         }
     }
     FT_MARK(1);
+    LIMU_TRACE(2);
     const int64_t n = n_keypoints >= 0 ? (int64_t)n_keypoints : (A.n_dev ? (int64_t)__ldcg(A.n_dev) : A.n_max);
     const bool run_icp = !(__ldcg(A.map_counters) == 0ull || A.max_iter <= 0);   // ICP :99-100: empty map -> init_guess
     if (threadIdx.x < 7) { Tinit[threadIdx.x] = A.init_pose[threadIdx.x]; Ticp[threadIdx.x] = threadIdx.x == 3 ? 1.0 : 0.0; }
@@ -949,6 +957,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
         }
     }
     FT_MARK(2);
+    LIMU_TRACE(3);
     // new_pose = T_icp * init_guess (:129); with an empty map the loop did not run and this is init_guess itself (:99-100). A launch without
     // the map-update epilogue (pipelined odometry) publishes the next scan's deskew twist here: the next scan's k_voxelize starts on it.
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -960,8 +969,16 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
         if (!A.upd_down) publish_twist(A, np);
     }
     if (blockIdx.x == 0 && n_keypoints >= 0) iqr_write_out<ICP_BLOCK>(qidx_s, A.iqr_in, n_keypoints, A.iqr_out, A.iqr_count);   // keypoints for the host
+    if (A.host_res && blockIdx.x == 0) {
+        __syncthreads();   // (pose, statistics and the keypoint count were written by threads of this CTA)
+        if ((int)threadIdx.x < A.res_doubles) A.host_res[threadIdx.x] = __ldcg(A.res_block + threadIdx.x);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long *>(A.host_res) + 31), "l"((unsigned long long)A.loop_seq) : "memory");
+    }
     if (A.upd_down) frame_update_epilogue<ICP_BLOCK>(A, gs, E);
     FT_MARK(5);
+    LIMU_TRACE(4);
     // the last CTA out re-arms the barrier for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -976,8 +993,10 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
 static __global__ void __launch_bounds__(ICP_BLOCK, 2) k_frame_update(const IcpArgs A) {
     __shared__ double E[7];
     GridSync gs{A.barrier, 0u, gridDim.x};
+    LIMU_TRACE(20);
     frame_update_epilogue<ICP_BLOCK, false>(A, gs, E);
     __syncthreads();
+    LIMU_TRACE(23);
     if (threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(A.exit_count, 1u) == gridDim.x - 1) { *A.barrier = 0u; *A.exit_count = 0u; __threadfence(); }
@@ -1349,6 +1368,7 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
         A.upd_capacity = (long long)m->capacity; A.upd_max_distance = m->max_distance;
         A.twist_out = fuse->twist_out;
         A.loop_flag = fuse->loop_flag; A.twist_flag = fuse->twist_flag; A.loop_seq = fuse->loop_seq;
+        A.host_res = fuse->host_res; A.res_block = fuse->res_block; A.res_doubles = fuse->res_doubles;
         for (int k = 0; k < 7; ++k) A.last_pose[k] = fuse->last_pose[k];
     }
     void *args[] = {&A};

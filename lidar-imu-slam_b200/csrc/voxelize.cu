@@ -21,6 +21,8 @@
 #include "ops.cuh"
 #include "voxel_map.cuh"
 
+LIMU_TRACE_RING(limu_debug_trace_vox)
+
 namespace limu {
 
 #ifndef LIMU_VX_BLOCK
@@ -163,6 +165,7 @@ static __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_voxelize(const V
     const int64_t gtid = (int64_t)blockIdx.x * BLOCK + threadIdx.x, gthreads = (int64_t)gridDim.x * BLOCK;
     const int ntiles = (int)((n + TILE - 1) / TILE);
     VX_MARK(0);
+    LIMU_TRACE(10);
     // un-claim what the previous launch left in ITS stage-2 table (this launch uses the other one): no barrier needed
     {
         const int ndp = __ldcg(A.nd_prev);
@@ -238,6 +241,7 @@ static __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_voxelize(const V
     }
     gs.sync();
     VX_MARK(1);
+    LIMU_TRACE(11);
     // P2: a point survives stage 1 iff it holds its voxel's smallest input index. Per tile: flags, count (published), ordered scatter
     // -> down[]; each winner immediately claims its 1.5 v voxel with its OUTPUT index. A thread owns ITEMS consecutive points of the tile.
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -275,6 +279,7 @@ static __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_voxelize(const V
     if (ntiles == 0 && gtid == 0) { A.counts[0] = 0; *A.nd_this = 0; }
     gs.sync();
     VX_MARK(2);
+    LIMU_TRACE(12);
     if (gtid == 0 && A.st_next) *A.st_next = DevStatus{0, 0, {0, 0}};   // (its last reader, the result copy of the previous scan, is long done)
     // the stage-1 table was last read in P2: un-claim it for the next launch
     for (int64_t i = gtid; i < n; i += gthreads) {
@@ -310,6 +315,7 @@ static __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_voxelize(const V
     // every CTA has left the last barrier before it gets here, so the last one out can re-arm it for the next launch
     __syncthreads();
     VX_MARK(3);
+    LIMU_TRACE(13);
     if (threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(A.barrier + 1, 1u) == gridDim.x - 1) { A.barrier[0] = 0u; A.barrier[1] = 0u; __threadfence(); }
@@ -327,10 +333,10 @@ static __global__ void k_gate(const unsigned int *flag, unsigned int seq) {
         unsigned int v;
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if ((int)(v - seq) >= 0) break;
-        __nanosleep(64);
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));   // (no __nanosleep: its granularity is microseconds, and one thread polling costs nothing)
         if (t1 - t0 > 5000000000ull) break;
     }
+    LIMU_TRACE(30);
 }
 int gate_device(cudaStream_t s, const unsigned int *flag, unsigned int seq) {
     k_gate<<<1, 1, 0, s>>>(flag, seq);

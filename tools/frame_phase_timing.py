@@ -29,8 +29,9 @@ for i, s in enumerate(scans):
     if i >= 5:
         rows.append(np.diff(marks[:6]) / 1e3)
         iters.append(odo.stats.icp.iterations)
-        nr = min(odo.stats.icp.iterations + 1, 47)          # rounds = iterations + the round that notices convergence
-        rounds.append(np.diff(marks[24:24 + nr + 1])[:12] / 1.965e3 if nr >= 12 else np.pad(np.diff(marks[24:24 + nr]) / 1.965e3, (0, 12 - (nr - 1)), constant_values=np.nan)[:12])
+        nr = min(odo.stats.icp.iterations, 47)              # round j starts at marks[24 + j]; the last one has no successor
+        d = np.diff(marks[24:24 + nr]) / 1.965e3
+        rounds.append(np.pad(d, (0, max(0, 12 - len(d))), constant_values=np.nan)[:12])
         if have_vox:
             pkg.lib().limu_debug_vox_marks(vmarks.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
             vrows.append(np.diff(vmarks[:4]) / 1e3)
@@ -50,3 +51,40 @@ print("rounds of the Gauss-Newton loop (us, CTA 0, mean over scans; nan = fewer 
 if vrows:
     print("k_voxelize phases (us; plain launch, 1024-thread CTAs): P1 deskew + claim | P2 flags, counts, scatter, claim 2 | P3 un-claim, flags, counts, scatter:", [round(float(x), 2) for x in np.mean(np.array(vrows), axis=0)], "total", round(float(np.sum(np.mean(np.array(vrows), axis=0))), 2))
 print("IQR phase of the last scan (SM cycles of CTA 0): squared ranges + ranking", cyc(16, 17), "| barrier of the loop CTAs", cyc(17, 18), "| local compaction (+ keypoints written out)", cyc(18, 19))
+
+# ---- timeline of the pipelined path (hinted device replay): one ring of (id, globaltimer) records per translation unit, merged here
+if hasattr(pkg.lib(), "limu_debug_trace_reg"):
+    import torch
+    odo.close()
+    dev = [torch.from_numpy(s).cuda() if isinstance(s, np.ndarray) else s for s in scans]
+    torch.cuda.synchronize()
+    odo = ctx.KissICP(voxel_size=1.0, cap=10, deskew=True, icp_max_iteration=500, speculate=True)
+    for i, s in enumerate(dev):
+        if i + 1 < len(dev):
+            odo.hint_next_dev(dev[i + 1].data_ptr(), dev[i + 1].shape[0])
+        odo.register_frame_dev(s.data_ptr(), s.shape[0])
+    odo.flush()
+    names = {1: "loop kernel starts", 2: "IQR done", 3: "loop over (gate flag)", 4: "loop kernel ends", 10: "voxelize starts", 11: "voxelize P1 done", 12: "voxelize P2 done",
+             13: "voxelize ends", 20: "update starts", 21: "update: claim done", 22: "update: place done", 23: "update ends", 30: "gate exits"}
+    ev = []
+    for fn in ("limu_debug_trace_reg", "limu_debug_trace_vox"):
+        buf = np.zeros(2048, np.uint64)
+        cnt = ctypes.c_uint(0)
+        getattr(pkg.lib(), fn)(buf.ctypes.data_as(ctypes.POINTER(ctypes.c_ulonglong)), ctypes.byref(cnt))
+        k = min(cnt.value, 2048)
+        for w in buf[:k]:
+            ev.append((int(w) & ((1 << 56) - 1), int(w) >> 56))
+    ev.sort()
+    starts = [i for i, e in enumerate(ev) if e[1] == 1]
+    if len(starts) >= 8:
+        # steady state: average the offsets of every record relative to the loop start of ITS scan, over the last scans
+        rel = {}
+        periods = []
+        for a, b in zip(starts[-12:-1], starts[-11:]):
+            t0 = ev[a][0]
+            periods.append((ev[b][0] - t0) / 1e3)
+            for t, idn in ev[a:b]:
+                rel.setdefault(idn, []).append((t - t0) / 1e3)
+        print("pipelined path, hinted device replay: period between loop starts %.1f us (last 11 scans: %s)" % (np.mean(periods), [round(p, 1) for p in periods]))
+        for idn, v in sorted(rel.items(), key=lambda kv: np.mean(kv[1])):
+            print("  +%7.2f us  %s" % (np.mean(v), names.get(idn, str(idn))))
