@@ -227,13 +227,22 @@ __device__ __forceinline__ int iqr_local_compact(int *ws /* shared, 32 */, int *
 // The keypoint cloud and its count for the host, written by ONE CTA from its index list -- after the Gauss-Newton loop, off everybody's
 // critical path (inside the compaction, 16 dependent load -> store rounds of CTA 0 held up the first row exchange of every scan by ~10 us).
 template <int BLOCK>
-__device__ __forceinline__ void iqr_write_out(const unsigned short *qidx, const double *__restrict__ xyz, int n, double *__restrict__ out, int *out_count) {
-    for (int p = threadIdx.x; p < n; p += BLOCK) {
-        const size_t i = qidx[p];
-        const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
-        out[3 * (size_t)p] = x; out[3 * (size_t)p + 1] = y; out[3 * (size_t)p + 2] = z;
+__device__ __forceinline__ void iqr_write_out(const unsigned short *qidx, const double *__restrict__ xyz, int n, double *__restrict__ out, int *out_count, int tid) {
+    // tid in [0, BLOCK): the caller may leave some of the CTA's threads out. Four points per round, their loads in flight together.
+    for (int p0 = tid; p0 < n; p0 += 4 * BLOCK) {
+        double v[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = p0 + u * BLOCK;
+            if (p < n) { const size_t i = qidx[p]; v[u][0] = xyz[3 * i]; v[u][1] = xyz[3 * i + 1]; v[u][2] = xyz[3 * i + 2]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = p0 + u * BLOCK;
+            if (p < n) { out[3 * (size_t)p] = v[u][0]; out[3 * (size_t)p + 1] = v[u][1]; out[3 * (size_t)p + 2] = v[u][2]; }
+        }
     }
-    if (threadIdx.x == 0) *out_count = n;
+    if (tid == 0) *out_count = n;
 }
 
 }  // namespace limu

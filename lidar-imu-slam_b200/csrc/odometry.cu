@@ -56,7 +56,7 @@ static double rotation_angle(const Pose &T) {
 //   [8..19] three status words k_voxelize rotates through
 //   doubles 14..26: pose + loop statistics (out13).     ONE copy of RES_DOUBLES per scan.
 namespace {
-constexpr int RES_CNT1 = 20, RES_FLAG = 3, RES_TWIST_FLAG = 22, RES_UPD_ST0 = 4, RES_UPD_ST1 = 24, RES_VOX_ST = 8, RES_OUT = 14, RES_DOUBLES = 27;
+constexpr int RES_CNT1 = 20, RES_FLAG = 3, RES_TWIST_FLAG = 22, RES_BARRIER = 64 /* 8 words, zero at rest: grid barriers of the pipelined kernels */, RES_UPD_ST0 = 4, RES_UPD_ST1 = 24, RES_VOX_ST = 8, RES_OUT = 14, RES_DOUBLES = 27;
 inline int *res_counts(int *cnt, int par) { return cnt + (par ? RES_CNT1 : 0); }
 inline limu::DevStatus *res_update_status(int *cnt, int par) { return reinterpret_cast<limu::DevStatus *>(cnt + (par ? RES_UPD_ST1 : RES_UPD_ST0)); }
 }  // namespace
@@ -89,24 +89,28 @@ struct limu_odom {
     // ---- pipelined path (LIMU_OPT_SPECULATE, on by default; packed float4 scans) -------------------------------------------------------
     // When the library knows which scan comes next (a device-pointer hint from limu_odom_hint_next_dev, or the scan limu_odom_prefetch is
     // uploading) the work of consecutive scans overlaps on the device and with the host:
-    //   main stream   [loop X] [update X] [loop X+1] [update X+1] ...      loop   = IQR + Gauss-Newton loop (reads the map, writes a pose)
-    //   vox stream        [gate|vox X+1]     [gate|vox X+2]                update = local_map.update: insert + eviction
-    //   * vox X+1 needs pose X for its deskew twist and nothing else: a one-thread gate kernel releases it the moment loop X has published
-    //     pose and twist, so it runs beside update X instead of behind it;
+    //   pipe stream     [loop X] [vox X+1] [loop X+1] [vox X+2] ...     loop   = IQR + Gauss-Newton loop (reads the map, writes a pose)
+    //   context stream     [gate|update X]    [gate|update X+1]         update = local_map.update: insert + eviction
+    //   * the critical chain -- loop X, deskew + downsampling of scan X+1 (its deskew twist is log(pose X-1^-1 pose X), left on the device
+    //     by loop X), loop X+1 -- is one in-order stream without events or host round trips in it;
+    //   * the map update of scan X runs BESIDE vox X+1 on the context's stream: a one-thread gate kernel releases it the moment loop X
+    //     is over (loop X+1 waits for its event, normally long complete);
     //   * loop X+1 is launched at the END of call X -- before the caller has asked for scan X+1 -- because it only reads the map: if the
     //     caller then registers something else its result is dropped. The map update of a scan is launched only once that scan has been
-    //     registered by the caller. So a call finds its pose computed (or in flight), and the GPU never waits for the host round trip.
+    //     registered by the caller. So a call finds its pose computed (or in flight), and the GPU never waits for the host round trip;
+    //   * the loop kernel leaves its result block in pinned host memory itself (no copy engine in the chain); the host polls for it.
     // Consequences for the caller: a call returns while the map update of its scan may still run (everything else on the handle or its map
-    // is stream-ordered behind it); an error of that update (voxel index out of range AFTER the transform into the world) is reported
-    // by the next call on the handle or by limu_odom_flush.
+    // goes to the context's stream behind it); an error of that update (voxel index out of range AFTER the transform into the world) is
+    // reported by the next call on the handle or by limu_odom_flush.
     bool speculate = true;
     const void *hint_ptr = nullptr;         // next scan (device float4 rows), set by the caller before registering the current one
     int64_t hint_n = 0;
-    cudaStream_t vox_stream = nullptr;
-    cudaEvent_t vox_done[2] = {nullptr, nullptr}, loop_done[2] = {nullptr, nullptr};
-    cudaEvent_t pev_vox[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, pev_upd[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // profiling: device time of gated / deferred launches
+    cudaStream_t pipe_stream = nullptr;
+    cudaEvent_t loop_done[2] = {nullptr, nullptr}, upd_done[2] = {nullptr, nullptr}, pipe_tail = nullptr, input_ready = nullptr;
+    bool upd_recorded[2] = {false, false};
+    cudaEvent_t pev_vox[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, pev_upd[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // profiling: device time of launches collected one call later
     bool pev_vox_used[2] = {false, false}, pev_upd_used[2] = {false, false};
-    double *h_res[2] = {nullptr, nullptr};  // pinned: the result block of a scan of either parity
+    double *h_res[2] = {nullptr, nullptr};  // pinned: the result block of a scan of either parity (256 bytes; word 30 checksum, word 31 sequence number)
     unsigned int loop_seq = 0;              // sequence number of the last loop launch of this handle
     unsigned int loop_seq_of[2] = {0, 0};   // ... and of the last launch for either parity (what the host waits for in h_res[par][31])
     limu::DevBuf twist_next;                // 6 doubles written by the loop kernel
@@ -168,14 +172,16 @@ static int odom_res_block(limu_odom *o) {
 }
 
 // Forget what is in flight for a scan that will not be registered (or not as it was prepared). The kernels themselves are harmless -- they
-// write buffers of the other parity and scratch -- but the next launches must be ordered behind them, and the threshold model must not keep
-// a sample that was added for a registration that did not happen (get_adaptive_threshold accumulates on every call, threshold.cpp:16-28).
-static int odom_drop_ahead(limu_odom *o, bool keep_voxelize) {
+// write buffers of the other parity and scratch -- but the threshold model must not keep a sample that was added for a registration that
+// did not happen (get_adaptive_threshold accumulates on every call, threshold.cpp:16-28). to_context_stream: what follows goes to the
+// context's stream (plain path), which therefore waits for whatever the pipe stream still has to do.
+static int odom_drop_ahead(limu_odom *o, bool keep_voxelize, bool to_context_stream = false) {
     limu_odom::Ahead &ah = o->ahead;
     if (ah.loop) { o->model_error_sq = ah.stash_model_error_sq; o->num_samples = ah.stash_num_samples; ah.loop = false; }
-    if (!keep_voxelize && ah.vox) {
-        LIMU_CUDA_TRY(cudaStreamWaitEvent(o->ctx->stream, o->vox_done[ah.par], 0));   // (its gate waits for a loop that was launched before it)
-        ah.vox = false; ah.ptr = nullptr; ah.slot = -1;
+    if (!keep_voxelize && ah.vox) { ah.vox = false; ah.ptr = nullptr; ah.slot = -1; }
+    if (to_context_stream && o->pipe_stream) {
+        LIMU_CUDA_TRY(cudaEventRecord(o->pipe_tail, o->pipe_stream));
+        LIMU_CUDA_TRY(cudaStreamWaitEvent(o->ctx->stream, o->pipe_tail, 0));
     }
     return LIMU_OK;
 }
@@ -237,7 +243,7 @@ static int odom_copy_clouds(limu_odom *o, bool side, int par, int64_t nd, int64_
 static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int stride, const double *ts_dev, int64_t n, double pose_out[7], double *down_xyz,
                                 int64_t *n_down, double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
     limu_ctx *c = o->ctx;
-    LIMU_TRY(odom_drop_ahead(o, false));
+    LIMU_TRY(odom_drop_ahead(o, false, true));
     o->hint_ptr = nullptr; o->hint_n = 0;
     // deskew gate (icp.cpp:40-46): config.deskew && poses.size() > 2; twist = delta_pose(poses[N-2], poses[N-1]) (deskew.cpp:14)
     const size_t NP = o->poses.size();
@@ -298,10 +304,11 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
     o->map->birth_base += (uint64_t)n;
     o->map->used_upper = upper_before + std::max<int64_t>(n, 0);   // safe bound until the exact count arrives (at most one new voxel per point)
 
-    // the one synchronisation of the scan
+    // the one synchronisation of the scan (nothing is left in flight: a later call on the pipelined path need not wait for anything)
     double *h = static_cast<double *>(c->h_pinned) + 32;
     LIMU_CUDA_TRY(cudaMemcpyAsync(h, o->res.p, RES_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    o->upd_recorded[0] = o->upd_recorded[1] = false;
     LIMU_TRY(prof_collect(c));
     const int *hc = reinterpret_cast<const int *>(h);
     const int64_t nd = res_counts(const_cast<int *>(hc), par)[0], nk = hc[2];
@@ -325,11 +332,15 @@ static int odom_register_device(limu_odom *o, const void *raw_dev, int mode, int
 }
 
 static int odom_pipe_init(limu_odom *o) {
-    if (o->vox_stream) return LIMU_OK;
-    LIMU_CUDA_TRY(cudaStreamCreateWithFlags(&o->vox_stream, cudaStreamNonBlocking));
+    if (o->pipe_stream) return LIMU_OK;
+    LIMU_TRY(odom_res_block(o));
+    LIMU_CUDA_TRY(cudaStreamSynchronize(o->ctx->stream));   // (the result block is zeroed before the pipe stream sees it)
+    LIMU_CUDA_TRY(cudaStreamCreateWithFlags(&o->pipe_stream, cudaStreamNonBlocking));
+    LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->pipe_tail, cudaEventDisableTiming));
+    LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->input_ready, cudaEventDisableTiming));
     for (int k = 0; k < 2; ++k) {
-        LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->vox_done[k], cudaEventDisableTiming));
         LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->loop_done[k], cudaEventDisableTiming));
+        LIMU_CUDA_TRY(cudaEventCreateWithFlags(&o->upd_done[k], cudaEventDisableTiming));
         LIMU_CUDA_TRY(cudaEventCreate(&o->pev_vox[k][0]));
         LIMU_CUDA_TRY(cudaEventCreate(&o->pev_vox[k][1]));
         LIMU_CUDA_TRY(cudaEventCreate(&o->pev_upd[k][0]));
@@ -340,19 +351,21 @@ static int odom_pipe_init(limu_odom *o) {
     return odom_side_stream(o);
 }
 
-// The IQR + Gauss-Newton half of a frame as a launch of its own (no map update): result block -> h_res[par], loop_done[par] recorded behind it.
-static int odom_launch_loop(limu_odom *o, int par, int64_t n, const Pose &init, const Pose &last, double sigma, bool wait_vox) {
+// The IQR + Gauss-Newton half of a frame as a launch of its own on the pipe stream (no map update). It waits for the map update of the
+// previous scan (context stream); its result block goes to h_res[par] (pinned), loop_done[par] is recorded behind it.
+static int odom_launch_loop(limu_odom *o, int par, int64_t n, const Pose &init, const Pose &last, double sigma) {
     limu_ctx *c = o->ctx;
+    cudaStream_t ps = o->pipe_stream;
     const size_t nb = (size_t)std::max<int64_t>(n, 1) * 24;
-    LIMU_TRY(o->src[par].reserve(nb, c->stream));
-    LIMU_TRY(o->work.reserve(nb, c->stream));
-    LIMU_TRY(o->d2.reserve((size_t)std::max<int64_t>(n, 1) * 8, c->stream));
-    LIMU_TRY(o->twist_next.reserve(6 * sizeof(double), c->stream));
+    LIMU_TRY(o->src[par].reserve(nb, ps));
+    LIMU_TRY(o->work.reserve(nb, ps));
+    LIMU_TRY(o->d2.reserve((size_t)std::max<int64_t>(n, 1) * 8, ps));
+    LIMU_TRY(o->twist_next.reserve(6 * sizeof(double), ps));
     const int rows = icp_partial_rows(c);
     {
         const void *before = o->partials.p;
-        LIMU_TRY(o->partials.reserve((size_t)2 * rows * 32 * 16 + 256, c->stream));
-        if (o->partials.p != before) LIMU_CUDA_TRY(cudaMemsetAsync(o->partials.p, 0, o->partials.bytes, c->stream));
+        LIMU_TRY(o->partials.reserve((size_t)2 * rows * 32 * 16 + 256, ps));
+        if (o->partials.p != before) LIMU_CUDA_TRY(cudaMemsetAsync(o->partials.p, 0, o->partials.bytes, ps));
     }
     int *cnt = o->res.as<int>();
     int *counts = res_counts(cnt, par);
@@ -361,52 +374,58 @@ static int odom_launch_loop(limu_odom *o, int par, int64_t n, const Pose &init, 
     fuse.iqr_in = o->src0[par].as<double>(); fuse.iqr_n = counts + 1; fuse.iqr_d2 = o->d2.as<double>(); fuse.iqr_out = o->src[par].as<double>(); fuse.iqr_count = cnt + 2;
     fuse.twist_out = o->twist_next.as<double>();
     fuse.loop_flag = reinterpret_cast<unsigned int *>(cnt + RES_FLAG);
-    fuse.twist_flag = reinterpret_cast<unsigned int *>(cnt + RES_TWIST_FLAG);
-    fuse.host_res = o->h_res[par]; fuse.res_block = o->res.as<double>(); fuse.res_doubles = RES_DOUBLES;
     fuse.loop_seq = ++o->loop_seq;
+    fuse.host_res = o->h_res[par]; fuse.res_block = o->res.as<double>(); fuse.res_doubles = RES_DOUBLES;
+    fuse.stream = ps;
+    fuse.barrier = reinterpret_cast<unsigned int *>(cnt + RES_BARRIER);
     pose_store(last, fuse.last_pose);
     double init7[7];
     pose_store(init, init7);
-    if (wait_vox) LIMU_CUDA_TRY(cudaStreamWaitEvent(c->stream, o->vox_done[par], 0));
+    if (o->upd_recorded[par ^ 1]) LIMU_CUDA_TRY(cudaStreamWaitEvent(ps, o->upd_done[par ^ 1], 0));
     LIMU_TRY(icp_device(o->map, o->src[par].as<double>(), o->work.as<double>(), n, cnt + 2, init7, 3.0 * sigma, sigma / 3.0, o->cfg.icp_max_iteration,
                         o->cfg.estimation_threshold, o->partials.as<double>(), (size_t)rows, o->res.as<double>() + RES_OUT, o->nk_hint, nullptr, nullptr, nullptr, -1, &fuse,
                         o->cfg.icp_mode));
-    // (no result copy in the stream: the kernel itself leaves the result block in pinned host memory, so the map update behind it starts at once)
-    LIMU_CUDA_TRY(cudaEventRecord(o->loop_done[par], c->stream));
+    LIMU_CUDA_TRY(cudaEventRecord(o->loop_done[par], ps));
+    o->map->readers_done = o->loop_done[par];   // (entry points that change the map from the context's stream wait for this reader)
     o->loop_seq_of[par] = o->loop_seq;
     return LIMU_OK;
 }
 
-// Wait until the loop launched for parity `par` has left its result block in h_res[par] (it stores its sequence number behind the data).
-static int odom_wait_loop(limu_odom *o, int par) {
-    const volatile unsigned long long *flag = reinterpret_cast<const volatile unsigned long long *>(o->h_res[par]) + 31;
+// Wait until the loop launched for parity `par` has left its result block in h_res[par]: word 31 carries its sequence number, word 30 the
+// XOR of the other words (the kernel stores the block without a system-scope fence, so a torn read is possible -- and read again).
+static int odom_wait_loop(limu_odom *o, int par, unsigned long long out[32]) {
+    const volatile unsigned long long *src = reinterpret_cast<const volatile unsigned long long *>(o->h_res[par]);
     const unsigned long long want = o->loop_seq_of[par];
     for (unsigned int spins = 1;; ++spins) {
-        if (*flag == want) break;
+        if (src[31] == want) {
+            unsigned long long x = 0ull;
+            for (int k = 0; k < 32; ++k) { out[k] = src[k]; if (k != 30) x ^= out[k]; }
+            if (out[31] == want && x == out[30]) return LIMU_OK;
+        }
         if ((spins & 0x3FFFu) == 0u) {   // now and then: is the kernel still alive?
             const cudaError_t e = cudaEventQuery(o->loop_done[par]);
             if (e == cudaSuccess) {
-                if (*flag == want) break;
+                unsigned long long x = 0ull;
+                for (int k = 0; k < 32; ++k) { out[k] = src[k]; if (k != 30) x ^= out[k]; }
+                if (out[31] == want && x == out[30]) return LIMU_OK;
                 set_error("registration kernel finished without publishing its result");
                 return LIMU_ERR_CUDA;
             }
             if (e != cudaErrorNotReady) { set_error("registration kernel failed: %s", cudaGetErrorString(e)); return LIMU_ERR_CUDA; }
         }
     }
-    std::atomic_thread_fence(std::memory_order_acquire);
-    return LIMU_OK;
 }
 
-// Pipelined path (see limu_odom): packed float4 scan in device memory.
-static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down, double *keypoints_xyz,
-                                   int64_t *n_keypoints, limu_frame_stats *stats) {
+// Pipelined path (see limu_odom): packed float4 scan in device memory. input_ready: event behind the scan's upload (nullptr: it is there).
+static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n, cudaEvent_t input_ready, double pose_out[7], double *down_xyz, int64_t *n_down,
+                                   double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
     limu_ctx *c = o->ctx;
     LIMU_TRY(odom_pipe_init(o));
-    LIMU_TRY(odom_res_block(o));
+    cudaStream_t ps = o->pipe_stream;
     limu_odom::Ahead &ah = o->ahead;
     const size_t NP = o->poses.size();
     const int deskewed = (o->cfg.deskew && NP > 2) ? 1 : 0;   // deskew gate (icp.cpp:40-46)
-    const int par = o->par ^ 1;
+    const int par = o->par ^ 1, npar = par ^ 1;
     const bool hit_vox = ah.vox && n > 0 && raw_dev == ah.ptr && n == ah.n && ah.deskewed == deskewed && ah.par == par;
     const bool hit_loop = hit_vox && ah.loop && ah.map_mutations == o->map->mutations;
     if (ah.vox && !hit_vox && ah.slot >= 0 && o->pf_buf[ah.slot].p == ah.ptr) {
@@ -430,20 +449,21 @@ static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n,
     const double v = o->cfg.voxel_size;
     const Pose last = o->poses.empty() ? pose_identity() : o->poses.back();
 
-    // 1. this scan's k_voxelize, unless it ran ahead
+    // 1. this scan's k_voxelize, unless it ran ahead (pipe stream: behind whatever was prepared for a scan that did not come)
     int vox_word = ah.vox_word;
     if (!hit_vox) {
         LIMU_TRY(odom_drop_ahead(o, false));
         double twist[6] = {0, 0, 0, 0, 0, 0};
         if (deskewed) se3_log(mul(inverse(o->poses[NP - 2]), o->poses[NP - 1]), twist);
         const size_t nb = (size_t)std::max<int64_t>(n, 1) * 24;
-        LIMU_TRY(o->frame.reserve(nb, c->stream));
-        LIMU_TRY(o->down[par].reserve(nb, c->stream));
-        LIMU_TRY(o->src0[par].reserve(nb, c->stream));
-        LIMU_TRY(prof_begin(c, LIMU_STAGE_DOWNSAMPLE));
+        LIMU_TRY(o->frame.reserve(nb, ps));
+        LIMU_TRY(o->down[par].reserve(nb, ps));
+        LIMU_TRY(o->src0[par].reserve(nb, ps));
+        if (input_ready) LIMU_CUDA_TRY(cudaStreamWaitEvent(ps, input_ready, 0));
+        if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->pev_vox[par][0], ps));
         LIMU_TRY(voxelize_device(c, o->vx, raw_dev, 0, 0, nullptr, deskewed, twist, n, v, o->frame.as<double>(), o->down[par].as<double>(), o->src0[par].as<double>(),
-                                 res_counts(cnt, par), nullptr, vox_status, &vox_word));
-        LIMU_TRY(prof_end(c, LIMU_STAGE_DOWNSAMPLE));
+                                 res_counts(cnt, par), nullptr, vox_status, &vox_word, ps, false));
+        if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->pev_vox[par][1], ps)); o->pev_vox_used[par] = true; }
     }
     // 2. its loop, unless that ran ahead too (with exactly the glue this call would compute)
     double sigma;
@@ -455,11 +475,12 @@ static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n,
         LIMU_TRY(odom_drop_ahead(o, true));
         sigma = odom_adaptive_threshold(o);              // host scalar glue (icp.cpp:66-71)
         init = mul(last, odom_prediction(o));
-        LIMU_TRY(odom_launch_loop(o, par, n, init, last, sigma, hit_vox));
+        LIMU_TRY(odom_launch_loop(o, par, n, init, last, sigma));
     }
-    const unsigned int my_seq = o->loop_seq;
+    const unsigned int my_seq = o->loop_seq_of[par];
     ah.vox = false; ah.ptr = nullptr; ah.slot = -1;
-    // 3. its map update: the caller has registered this scan, so it goes in right behind the loop (local_map.update, icp.cpp:81)
+    // 3. its map update on the context's stream: the caller has registered this scan (local_map.update, icp.cpp:81). A gate kernel holds it
+    //    until the loop is over.
     LIMU_TRY(map_maybe_grow(o->map, n));
     LIMU_TRY(o->map->pslot.reserve((size_t)std::max<int64_t>(n, 1) * 4, c->stream));
     LIMU_TRY(o->world.reserve((size_t)std::max<int64_t>(n, 1) * 24, c->stream));
@@ -469,49 +490,51 @@ static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n,
         fuse.upd_down = o->down[par].as<double>(); fuse.upd_n = res_counts(cnt, par); fuse.upd_world = o->world.as<double>(); fuse.upd_pslot = o->map->pslot.as<unsigned int>();
         fuse.upd_birth_base = o->map->birth_base;
         fuse.status = res_update_status(cnt, par);
+        fuse.barrier = reinterpret_cast<unsigned int *>(cnt + RES_BARRIER);
+        LIMU_TRY(gate_device(c->stream, reinterpret_cast<unsigned int *>(cnt + RES_FLAG), my_seq));
         if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->pev_upd[par][0], c->stream));
         LIMU_TRY(frame_update_device(o->map, fuse, o->res.as<double>() + RES_OUT));
         if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->pev_upd[par][1], c->stream)); o->pev_upd_used[par] = true; }
+        LIMU_CUDA_TRY(cudaEventRecord(o->upd_done[par], c->stream));
+        o->upd_recorded[par] = true;
     }
     const int64_t upper_before = o->map->used_upper;
     o->map->birth_base += (uint64_t)n;
     o->map->used_upper = upper_before + std::max<int64_t>(n, 0);   // safe bound until the exact count arrives (at most one new voxel per point)
-    // 4. the next scan's k_voxelize on its own stream, released by this scan's loop (its deskew twist is log(last^-1 * new), deskew.cpp:14)
-    const int npar = par ^ 1;
+    // 4. the next scan's k_voxelize right behind this scan's loop in the pipe stream (its deskew twist, log(last^-1 * new) (deskew.cpp:14),
+    //    is left on the device by that loop); half-size CTAs: it runs beside the map update
     const int next_deskew = (o->cfg.deskew && NP + 1 > 2) ? 1 : 0;   // the gate of icp.cpp:40-46 as the next scan will see it
     if (next_ptr && next_n > 0) {
         const size_t nb = (size_t)next_n * 24;
-        LIMU_TRY(o->frame.reserve(nb, o->vox_stream));
-        LIMU_TRY(o->down[npar].reserve(nb, o->vox_stream));
-        LIMU_TRY(o->src0[npar].reserve(nb, o->vox_stream));
-        if (next_ready) LIMU_CUDA_TRY(cudaStreamWaitEvent(o->vox_stream, next_ready, 0));
-        LIMU_TRY(gate_device(o->vox_stream, reinterpret_cast<unsigned int *>(cnt + RES_FLAG), my_seq));
+        LIMU_TRY(o->frame.reserve(nb, ps));
+        LIMU_TRY(o->down[npar].reserve(nb, ps));
+        LIMU_TRY(o->src0[npar].reserve(nb, ps));
+        if (next_ready) LIMU_CUDA_TRY(cudaStreamWaitEvent(ps, next_ready, 0));
         int w = 0;
-        if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->pev_vox[npar][0], o->vox_stream));   // (behind the gate: the kernel's own time)
+        if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->pev_vox[npar][0], ps));
         LIMU_TRY(voxelize_device(c, o->vx, next_ptr, 0, 0, nullptr, next_deskew, nullptr, next_n, v, o->frame.as<double>(), o->down[npar].as<double>(), o->src0[npar].as<double>(),
-                                 res_counts(cnt, npar), next_deskew ? o->twist_next.as<double>() : nullptr, vox_status, &w, o->vox_stream, true,
-                                 reinterpret_cast<unsigned int *>(cnt + RES_TWIST_FLAG), my_seq));
-        if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->pev_vox[npar][1], o->vox_stream)); o->pev_vox_used[npar] = true; }
-        LIMU_CUDA_TRY(cudaEventRecord(o->vox_done[npar], o->vox_stream));
+                                 res_counts(cnt, npar), next_deskew ? o->twist_next.as<double>() : nullptr, vox_status, &w, ps, true));
+        if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->pev_vox[npar][1], ps)); o->pev_vox_used[npar] = true; }
         ah.vox = true; ah.ptr = next_ptr; ah.n = next_n; ah.deskewed = next_deskew; ah.slot = next_slot; ah.par = npar; ah.vox_word = w;
     }
     // 5. the one wait of the call: this scan's pose
-    LIMU_TRY(odom_wait_loop(o, par));
-    if (c->profiling) LIMU_CUDA_TRY(cudaEventSynchronize(o->loop_done[par]));   // (the stage events sit behind the kernel in the stream)
-    LIMU_TRY(prof_collect(c));
+    unsigned long long hw[32];
+    LIMU_TRY(odom_wait_loop(o, par, hw));
     if (c->profiling) {
+        LIMU_CUDA_TRY(cudaEventSynchronize(o->loop_done[par]));   // (the stage events sit behind the kernel in the stream)
+        LIMU_TRY(prof_collect(c));
         float ms = 0.f;
-        if (o->pev_vox_used[par]) {   // the gated launch that prepared THIS scan
-            if (hit_vox && cudaEventElapsedTime(&ms, o->pev_vox[par][0], o->pev_vox[par][1]) == cudaSuccess) c->stage_ms[LIMU_STAGE_DOWNSAMPLE] += (double)ms; else (void)cudaGetLastError();
+        if (o->pev_vox_used[par]) {   // this scan's k_voxelize
+            if (cudaEventElapsedTime(&ms, o->pev_vox[par][0], o->pev_vox[par][1]) == cudaSuccess) c->stage_ms[LIMU_STAGE_DOWNSAMPLE] += (double)ms; else (void)cudaGetLastError();
             o->pev_vox_used[par] = false;
         }
-        if (o->pev_upd_used[npar]) {   // the previous scan's map update (in front of this scan's loop on the main stream)
+        if (o->pev_upd_used[npar]) {   // the previous scan's map update (this scan's loop waited for it)
             if (cudaEventElapsedTime(&ms, o->pev_upd[npar][0], o->pev_upd[npar][1]) == cudaSuccess) c->stage_ms[LIMU_STAGE_MAP_UPDATE] += (double)ms; else (void)cudaGetLastError();
             o->pev_upd_used[npar] = false;
         }
     }
-    const double *h = o->h_res[par];
-    const int *hc = reinterpret_cast<const int *>(h);
+    const double *h = reinterpret_cast<const double *>(hw);
+    const int *hc = reinterpret_cast<const int *>(hw);
     const int64_t nd = res_counts(const_cast<int *>(hc), par)[0], nk = hc[2];
     const Pose new_pose = pose_load(h + RES_OUT);
     // commit the frame (map bookkeeping, pose history, threshold state) before looking at any status
@@ -526,17 +549,17 @@ static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n,
     if (n_keypoints) *n_keypoints = nk;
     const int deferred = odom_deferred_status(o, hc);   // the previous scan's map update ran in front of this scan's loop
     o->pending_update_par = par;
-    // 6. the next scan's loop, ahead of the caller asking for it: it only reads the map (behind this scan's update in stream order)
+    // 6. the next scan's loop, ahead of the caller asking for it: it only reads the map (it waits for this scan's update)
     if (ah.vox) {
         ah.stash_model_error_sq = o->model_error_sq; ah.stash_num_samples = o->num_samples;
         ah.sigma = odom_adaptive_threshold(o);
         ah.init = mul(new_pose, odom_prediction(o));
         ah.map_mutations = o->map->mutations;
         ah.loop = true;
-        const int st = odom_launch_loop(o, npar, ah.n, ah.init, new_pose, ah.sigma, true);
+        const int st = odom_launch_loop(o, npar, ah.n, ah.init, new_pose, ah.sigma);
         if (st != LIMU_OK) { (void)odom_drop_ahead(o, true); return st; }
     }
-    // 7. this scan's clouds (complete since its loop ended; the main stream is busy with later work)
+    // 7. this scan's clouds (complete since its loop ended; both streams are busy with later work)
     LIMU_TRY(odom_copy_clouds(o, true, par, nd, nk, down_xyz, keypoints_xyz));
     LIMU_TRY(odom_report(o, hc, vox_word, -1, hit_vox, n, deskewed, sigma, stats));
     return deferred;
@@ -545,7 +568,7 @@ static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n,
 // Wait for everything the handle has in flight and report what a deferred map update had to say.
 static int odom_flush(limu_odom *o) {
     limu_ctx *c = o->ctx;
-    LIMU_TRY(odom_drop_ahead(o, false));
+    LIMU_TRY(odom_drop_ahead(o, false, true));
     LIMU_CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (o->pending_update_par < 0 || !o->res.p) return LIMU_OK;
     double *h = static_cast<double *>(c->h_pinned) + 32;
@@ -593,8 +616,9 @@ int limu_odom_create(limu_ctx *c, const limu_odom_config *cfg, limu_odom **out) 
 void limu_odom_destroy(limu_odom *o) {
     if (!o) return;
     cudaSetDevice(o->ctx->device);
-    if (o->vox_stream) cudaStreamSynchronize(o->vox_stream);
+    if (o->pipe_stream) cudaStreamSynchronize(o->pipe_stream);
     cudaStreamSynchronize(o->ctx->stream);
+    o->map->readers_done = nullptr;
     limu_map_destroy(o->map);
     if (o->copy_stream) { cudaStreamSynchronize(o->copy_stream); cudaStreamDestroy(o->copy_stream); cudaEventDestroy(o->pf_done[0]); cudaEventDestroy(o->pf_done[1]); }
     DevBuf *bufs[] = {&o->res, &o->pf_buf[0], &o->pf_buf[1], &o->d2, &o->raw, &o->ts, &o->frame, &o->down[0], &o->down[1], &o->src0[0], &o->src0[1], &o->src[0], &o->src[1],
@@ -602,10 +626,11 @@ void limu_odom_destroy(limu_odom *o) {
     for (auto *b : bufs) b->release();
     o->vx.release();
     o->pre.release();
-    if (o->vox_stream) {
-        cudaStreamDestroy(o->vox_stream);
+    if (o->pipe_stream) {
+        cudaStreamDestroy(o->pipe_stream);
+        cudaEventDestroy(o->pipe_tail); cudaEventDestroy(o->input_ready);
         for (int k = 0; k < 2; ++k) {
-            cudaEventDestroy(o->vox_done[k]); cudaEventDestroy(o->loop_done[k]);
+            cudaEventDestroy(o->loop_done[k]); cudaEventDestroy(o->upd_done[k]);
             cudaEventDestroy(o->pev_vox[k][0]); cudaEventDestroy(o->pev_vox[k][1]); cudaEventDestroy(o->pev_upd[k][0]); cudaEventDestroy(o->pev_upd[k][1]);
             cudaFreeHost(o->h_res[k]);
         }
@@ -621,20 +646,26 @@ int limu_odom_register_frame(limu_odom *o, const float *xyzt, int64_t n, double 
     int hit = -1;
     for (int s = 0; s < 2; ++s) if (n > 0 && o->pf_host[s] == xyzt && o->pf_n[s] == n) hit = s;
     const void *dev = nullptr;
+    cudaEvent_t ready = nullptr;   // what the scan's first kernel has to wait for when it is not launched on the context's stream
     if (hit >= 0 && o->speculate && o->ahead.vox && o->ahead.ptr == o->pf_buf[hit].p && o->ahead.n == n) {
-        // uploaded ahead of time AND already through k_voxelize (released by the previous scan's loop): register it where it lies
+        // uploaded ahead of time AND already through k_voxelize (behind the previous scan's loop): register it where it lies
         o->pf_host[hit] = nullptr; o->pf_n[hit] = -1;
         dev = o->pf_buf[hit].p;
     } else if (hit >= 0) {   // uploaded ahead of time by limu_odom_prefetch
         LIMU_CUDA_TRY(cudaStreamWaitEvent(o->ctx->stream, o->pf_done[hit], 0));
+        if (o->pipe_stream) LIMU_CUDA_TRY(cudaStreamSynchronize(o->pipe_stream));   // (rare: the buffers change hands while a kernel prepared for another scan may read one)
         std::swap(o->raw, o->pf_buf[hit]);
         o->pf_host[hit] = nullptr; o->pf_n[hit] = -1;
         dev = o->raw.p;
+        ready = o->pf_done[hit];
     } else {
+        if (o->speculate) LIMU_TRY(odom_pipe_init(o));
+        if (o->pipe_stream) LIMU_CUDA_TRY(cudaStreamSynchronize(o->pipe_stream));   // (o->raw may still be read by a kernel of the previous scan on the pipe stream)
         LIMU_TRY(stage_in(o->ctx, o->raw, xyzt, (size_t)n * 16));
         dev = o->raw.p;
+        if (o->speculate) { LIMU_CUDA_TRY(cudaEventRecord(o->input_ready, o->ctx->stream)); ready = o->input_ready; }
     }
-    if (o->speculate) return odom_register_pipelined(o, dev, n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+    if (o->speculate) return odom_register_pipelined(o, dev, n, ready, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
     return odom_register_device(o, dev, 0, 0, nullptr, n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
 }
 
@@ -649,7 +680,7 @@ int limu_odom_prefetch(limu_odom *o, const float *xyzt, int64_t n) {
     if (o->ahead.vox && o->pf_buf[s].p == o->ahead.ptr) {
         // the k_voxelize that ran ahead on the scan in this slot may still be reading it: let it finish, and forget what was prepared (the
         // slot is about to hold a different scan, possibly of the same size)
-        LIMU_CUDA_TRY(cudaEventSynchronize(o->vox_done[o->ahead.par]));
+        LIMU_CUDA_TRY(cudaStreamSynchronize(o->pipe_stream));
         LIMU_TRY(odom_drop_ahead(o, false));
     }
     o->pf_host[s] = nullptr; o->pf_n[s] = -1;
@@ -675,7 +706,7 @@ int limu_odom_register_cloud(limu_odom *o, const void *points, int32_t stride_by
 int limu_odom_register_frame_dev(limu_odom *o, const float *xyzt_dev, int64_t n, double pose_out[7], limu_frame_stats *stats) {
     LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyzt_dev), "limu_odom_register_frame_dev: bad arguments");
     LIMU_TRY(bind(o->ctx));
-    if (o->speculate) return odom_register_pipelined(o, xyzt_dev, n, pose_out, nullptr, nullptr, nullptr, nullptr, stats);
+    if (o->speculate) return odom_register_pipelined(o, xyzt_dev, n, nullptr, pose_out, nullptr, nullptr, nullptr, nullptr, stats);
     return odom_register_device(o, xyzt_dev, 0, 0, nullptr, n, pose_out, nullptr, nullptr, nullptr, nullptr, stats);
 }
 

@@ -958,23 +958,40 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
     }
     FT_MARK(2);
     LIMU_TRACE(3);
-    // new_pose = T_icp * init_guess (:129); with an empty map the loop did not run and this is init_guess itself (:99-100). A launch without
-    // the map-update epilogue (pipelined odometry) publishes the next scan's deskew twist here: the next scan's k_voxelize starts on it.
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        // release the next scan's k_voxelize now: its launch latency covers the few microseconds until the twist is there
-        if (!A.upd_down && A.loop_flag) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(A.loop_flag), "r"(A.loop_seq) : "memory");
-        const Pose np = run_icp ? mul(pose_load(Ticp), pose_load(Tinit)) : pose_load(Tinit);
-        pose_store(np, A.out);
-        A.out[7] = (double)j; A.out[8] = (double)converged; A.out[9] = S[I_NCORR]; A.out[10] = S[I_NCORR + 1]; A.out[11] = S[I_NCORR + 2]; A.out[12] = (double)n;
-        if (!A.upd_down) publish_twist(A, np);
-    }
-    if (blockIdx.x == 0 && n_keypoints >= 0) iqr_write_out<ICP_BLOCK>(qidx_s, A.iqr_in, n_keypoints, A.iqr_out, A.iqr_count);   // keypoints for the host
-    if (A.host_res && blockIdx.x == 0) {
-        __syncthreads();   // (pose, statistics and the keypoint count were written by threads of this CTA)
-        if ((int)threadIdx.x < A.res_doubles) A.host_res[threadIdx.x] = __ldcg(A.res_block + threadIdx.x);
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long *>(A.host_res) + 31), "l"((unsigned long long)A.loop_seq) : "memory");
+    // new_pose = T_icp * init_guess (:129); with an empty map the loop did not run and this is init_guess itself (:99-100). What follows is
+    // CTA 0's: in a launch without the map-update epilogue (pipelined odometry) the next scan's k_voxelize sits behind this kernel in the
+    // stream, so its tail is kept short: thread 0 takes pose and deskew twist while warps 1.. write the keypoints out, then warp 0 leaves
+    // the result block in pinned host memory.
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            // (the map update of this scan, on another stream, is released by this flag: the loop's reads of the map are over)
+            if (!A.upd_down && A.loop_flag) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.loop_flag), "r"(A.loop_seq) : "memory");
+            const Pose np = run_icp ? mul(pose_load(Ticp), pose_load(Tinit)) : pose_load(Tinit);
+            pose_store(np, A.out);
+            A.out[7] = (double)j; A.out[8] = (double)converged; A.out[9] = S[I_NCORR]; A.out[10] = S[I_NCORR + 1]; A.out[11] = S[I_NCORR + 2]; A.out[12] = (double)n;
+            if (!A.upd_down) publish_twist(A, np);
+        }
+        if (n_keypoints >= 0) {   // keypoints for the host
+            if (A.host_res) { if (threadIdx.x >= 32) iqr_write_out<ICP_BLOCK - 32>(qidx_s, A.iqr_in, n_keypoints, A.iqr_out, A.iqr_count, (int)threadIdx.x - 32); }
+            else iqr_write_out<ICP_BLOCK>(qidx_s, A.iqr_in, n_keypoints, A.iqr_out, A.iqr_count, (int)threadIdx.x);
+        }
+        if (A.host_res) {
+            // Result block -> pinned host memory as ONE 256-byte store of warp 0: words 0..29 data, 30 = XOR of the others, 31 = this launch's
+            // sequence number. No system-scope fence (several microseconds over PCIe): the host accepts the block when the sequence number
+            // is the one it waits for AND the checksum holds, so a torn read is simply read again.
+            __threadfence();   // (the keypoints are in L2 before the host can start a copy of them)
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                unsigned long long w = 0ull;
+                if ((int)threadIdx.x < A.res_doubles && threadIdx.x < 30) w = (unsigned long long)__double_as_longlong(__ldcg(A.res_block + threadIdx.x));
+                if (threadIdx.x == 31) w = (unsigned long long)A.loop_seq;
+                unsigned long long x = threadIdx.x == 30 ? 0ull : w;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x ^= __shfl_xor_sync(0xFFFFFFFFu, x, o);
+                if (threadIdx.x == 30) w = x;
+                reinterpret_cast<volatile unsigned long long *>(A.host_res)[threadIdx.x] = w;
+            }
+        }
     }
     if (A.upd_down) frame_update_epilogue<ICP_BLOCK>(A, gs, E);
     FT_MARK(5);
@@ -1009,7 +1026,7 @@ int frame_update_device(limu_map *m, const FrameFusion &fuse, const double *pose
     memset(&A, 0, sizeof A);
     A.map = m->view();
     A.out = const_cast<double *>(pose_dev);
-    A.barrier = reinterpret_cast<unsigned int *>(c->d_small.as<double>() + 56);
+    A.barrier = fuse.barrier ? fuse.barrier + 4 : reinterpret_cast<unsigned int *>(c->d_small.as<double>() + 56);   // (its own words: another handle's loop may be running)
     A.exit_count = A.barrier + 1;
     A.upd_down = fuse.upd_down; A.upd_n = fuse.upd_n; A.upd_world = fuse.upd_world; A.upd_pslot = fuse.upd_pslot;
     A.upd_counters = m->counters.as<unsigned long long>(); A.upd_birth_base = fuse.upd_birth_base;
@@ -1205,7 +1222,7 @@ static __global__ void __launch_bounds__(CL_THREADS, 1) k_frame_cluster(const Ic
         }
     }
     FT_MARK(2);
-    if (blockIdx.x == 0 && compacted_here) iqr_write_out<CL_THREADS>(sm.qidx, A.iqr_in, n, A.iqr_out, A.iqr_count);   // keypoints for the host
+    if (blockIdx.x == 0 && compacted_here) iqr_write_out<CL_THREADS>(sm.qidx, A.iqr_in, n, A.iqr_out, A.iqr_count, (int)threadIdx.x);   // keypoints for the host
     // new_pose = T_icp * init_guess (:129); with an empty map the loop did not run and this is init_guess itself (:99-100)
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const Pose np = run_icp ? mul(pose_load(sm.Ticp), pose_load(sm.Tinit)) : pose_load(sm.Tinit);
@@ -1344,7 +1361,7 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
     A.ll_stamp_base = c->ll_seq;
     c->ll_seq = (c->ll_seq + (unsigned int)std::max(max_iter, 0) + 2u) & 0x7FFFFFFFu;
     // grid barrier + exit counter live in the context's zero-initialised small area; the last CTA out re-arms them
-    A.barrier = reinterpret_cast<unsigned int *>(c->d_small.as<double>() + 56);
+    A.barrier = (fuse && fuse->barrier) ? fuse->barrier : reinterpret_cast<unsigned int *>(c->d_small.as<double>() + 56);
     A.exit_count = A.barrier + 1;
     A.barrier_icp = A.barrier + 2;
     A.icp_blocks = icp_blocks;
@@ -1372,7 +1389,8 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
         for (int k = 0; k < 7; ++k) A.last_pose[k] = fuse->last_pose[k];
     }
     void *args[] = {&A};
-    LIMU_TRY(prof_begin(c, LIMU_STAGE_ICP));
+    cudaStream_t stream = (fuse && fuse->stream) ? fuse->stream : c->stream;
+    if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(c->ev[LIMU_STAGE_ICP][0], stream)); c->ev_used[LIMU_STAGE_ICP] = true; }
     // pipeline mode with the reference's rules: the cluster latency shape (falls back to the classic kernel where clusters of 16 cannot be launched)
     if (fuse && fuse->iqr_in && fuse->upd_down && icp_mode == 0 && A.nranks == 1 && !est_trace_dev && !ncorr_trace_dev && !hg_trace_dev && m->cap <= 20 &&
         n_hint <= CL_QPP && fuse->allow_cluster && launch_frame_cluster(c, A, m->cap) == LIMU_OK) {
@@ -1385,9 +1403,9 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
                                 {{(const void *)k_icp_persistent<1, false, false>, (const void *)k_icp_persistent<1, false, true>},
                                  {(const void *)k_icp_persistent<1, true, false>, (const void *)k_icp_persistent<1, true, true>}}};
     const void *fn = fns[grouped ? 0 : 1][nn27 ? 1 : 0][plane ? 1 : 0];
-    LIMU_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(ICP_BLOCK), args, stage_bytes, c->stream));
+    LIMU_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(ICP_BLOCK), args, stage_bytes, stream));
     LIMU_LAUNCHED();
-    LIMU_TRY(prof_end(c, LIMU_STAGE_ICP));
+    if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(c->ev[LIMU_STAGE_ICP][1], stream));
     return LIMU_OK;
 }
 

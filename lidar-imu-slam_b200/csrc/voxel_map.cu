@@ -214,6 +214,7 @@ int map_maybe_grow(limu_map *m, int64_t incoming) {
     const int64_t live = (int64_t)cnt[0], used = (int64_t)cnt[3];
     m->used_upper = used;
     if ((used + incoming) * 2 <= m->capacity) return LIMU_OK;
+    LIMU_TRY(map_wait_readers(m));   // (the old table is freed below)
     limu_ctx *c = m->ctx;
     const int64_t newC = std::max<int64_t>(next_pow2((live + incoming) * 4), 1024);
     limu_map old = *m;  // shallow: keeps the old buffers alive
@@ -241,6 +242,7 @@ int map_maybe_grow(limu_map *m, int64_t incoming) {
 int map_insert_device(limu_map *m, const double *xyz_dev, int64_t n, const int *n_dev) {
     if (n <= 0) return LIMU_OK;
     limu_ctx *c = m->ctx;
+    LIMU_TRY(map_wait_readers(m));
     LIMU_TRY(map_maybe_grow(m, n));
     LIMU_TRY(m->pslot.reserve((size_t)n * 4, c->stream));
     const MapView v = m->view();
@@ -258,6 +260,7 @@ int map_insert_device(limu_map *m, const double *xyz_dev, int64_t n, const int *
 
 int map_remove_far_device(limu_map *m, const double *origin_dev3) {
     limu_ctx *c = m->ctx;
+    LIMU_TRY(map_wait_readers(m));
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(div_up(std::max<int64_t>(m->used_upper, 1), 256), (int64_t)c->sm_count * 8));
     k_remove_far<<<blocks, 256, 0, c->stream>>>(m->view(), origin_dev3, m->max_distance, m->counters.as<unsigned long long>());
     LIMU_LAUNCHED();
@@ -313,6 +316,7 @@ int limu_map_clear(limu_map *m) {
     LIMU_REQUIRE(m, "limu_map_clear: null map");
     LIMU_TRY(bind(m->ctx));
     limu_ctx *c = m->ctx;
+    LIMU_TRY(map_wait_readers(m));
     const int blocks = std::min<int64_t>(div_up(m->capacity, 256), (int64_t)c->sm_count * 32);
     k_map_clear<<<blocks, 256, 0, c->stream>>>(m->view(), m->capacity);
     LIMU_LAUNCHED();

@@ -703,6 +703,7 @@ struct limu_map {
     limu::DevBuf counters;         // device: [0] n_live voxels, [1] n_tomb, [2] n_points, [3] n_used (live + tomb)
     uint64_t birth_base = 0;       // creation sequence offset of the next insert batch
     int64_t used_upper = 0;        // host upper bound on live + tomb slots
+    cudaEvent_t readers_done = nullptr;   // set by an odometry handle that reads this map from another stream: entry points that change the map wait for it (not owned)
     uint64_t mutations = 0;        // bumped by every entry point of the C ABI that changes the map's contents (odometry.cu: a loop that ran ahead on an older map is dropped)
     limu::DevBuf pslot;            // per-point slot scratch of the current insert batch
     limu::DevBuf world;            // transformed copy for update(points, pose)
@@ -714,4 +715,8 @@ int map_alloc(limu_map *m, int64_t capacity_slots);
 int map_insert_device(limu_map *m, const double *xyz_dev, int64_t n, const int *n_dev /* optional device count */);
 int map_remove_far_device(limu_map *m, const double *origin_dev3);
 int map_maybe_grow(limu_map *m, int64_t incoming);
+inline int map_wait_readers(limu_map *m) {
+    if (m->readers_done) LIMU_CUDA_TRY(cudaStreamWaitEvent(m->ctx->stream, m->readers_done, 0));
+    return LIMU_OK;
+}
 }  // namespace limu

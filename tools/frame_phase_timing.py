@@ -65,7 +65,7 @@ if hasattr(pkg.lib(), "limu_debug_trace_reg"):
         odo.register_frame_dev(s.data_ptr(), s.shape[0])
     odo.flush()
     names = {1: "loop kernel starts", 2: "IQR done", 3: "loop over (gate flag)", 4: "loop kernel ends", 10: "voxelize starts", 11: "voxelize P1 done", 12: "voxelize P2 done",
-             13: "voxelize ends", 20: "update starts", 21: "update: claim done", 22: "update: place done", 23: "update ends", 30: "gate exits"}
+             13: "voxelize ends", 20: "update starts", 21: "update: claim done", 22: "update: place done", 23: "update ends", 30: "gate exits (update released)"}
     ev = []
     for fn in ("limu_debug_trace_reg", "limu_debug_trace_vox"):
         buf = np.zeros(2048, np.uint64)
