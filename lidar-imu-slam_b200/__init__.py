@@ -710,6 +710,12 @@ class KissICP:
         _chk(lib().limu_odom_has_moved(self.h, C.byref(e)))
         return bool(e.value)
 
+    def get_adaptive_threshold(self):
+        """KissICP::get_adaptive_threshold (icp.cpp:138-144) -- with the reference's side effect: every call adds a sample to the model."""
+        out = C.c_double(0.0)
+        _chk(lib().limu_odom_adaptive_threshold(self.h, C.byref(out)))
+        return out.value
+
     def get_prediction_model(self):
         out = np.empty(7)
         _chk(lib().limu_odom_prediction(self.h, _d(out)))

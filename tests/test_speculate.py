@@ -164,6 +164,79 @@ def test_out_of_range_point_commits_the_frame(ctx, pkg, scans):
             p.free()
 
 
+def test_caller_touches_handle_and_map_between_pipelined_calls(ctx, pkg, scans):
+    """The pipelined path launches the NEXT scan's Gauss-Newton loop before the caller asks for that scan. Whatever the caller does in between
+    that the loop's inputs depend on -- get_adaptive_threshold (adds a sample to the threshold model, threshold.cpp:16-28), inserting into or
+    pruning the local map -- must give what the plain path gives for the same sequence of calls: the loop that ran ahead is dropped."""
+    import torch
+    rng = np.random.default_rng(5)
+    extra = [rng.uniform(-20, 20, size=(500, 3)) for _ in scans]
+
+    def run(spec):
+        staged = [torch.from_numpy(s).cuda() for s in scans]
+        torch.cuda.synchronize()
+        k = ctx.KissICP(deskew=True, icp_max_iteration=60, speculate=spec)
+        out = []
+        for i, t in enumerate(staged):
+            if spec and i + 1 < len(staged):
+                k.hint_next_dev(staged[i + 1].data_ptr(), len(scans[i + 1]))
+            p = k.register_frame_dev(t.data_ptr(), len(scans[i]))
+            row = [p.copy(), k.stats.icp.iterations, k.stats.n_keypoints]
+            if i in (3, 6):
+                row.append(k.get_adaptive_threshold())            # (a) the getter with its side effect
+            if i == 4:
+                k.local_map().insert_points(extra[i])             # (b) the caller adds points to the map
+            if i == 7:
+                k.local_map().remove_points_from_far(p[4:7] + np.array([60.0, 0.0, 0.0]))   # (c) ... and prunes it around another origin
+            if i == 5:
+                assert k.local_map().size()[0] > 0                # (d) a read of the map is ordered behind the update in flight
+            out.append(row)
+        k.flush()
+        dump = k.local_map().dump()
+        k.close()
+        return out, dump
+
+    (a, da), (b, db) = run(False), run(True)
+    for ra, rb in zip(a, b):
+        assert ra[1] == rb[1] and ra[2] == rb[2]
+        np.testing.assert_allclose(ra[0], rb[0], rtol=0, atol=1e-9)
+        if len(ra) > 3:
+            assert abs(ra[3] - rb[3]) < 1e-9
+    assert np.array_equal(da[0], db[0]) and np.array_equal(da[1], db[1])
+    np.testing.assert_allclose(da[2], db[2], rtol=0, atol=1e-9)
+
+
+def test_flush_and_plain_calls_between_pipelined_calls(ctx, pkg, scans):
+    """register_cloud / register_points go down the plain path: switching back and forth drops what was prepared and keeps the order of map updates."""
+    import torch
+    seq = scans[:8]
+
+    def run(spec):
+        staged = [torch.from_numpy(s).cuda() for s in seq]
+        torch.cuda.synchronize()
+        k = ctx.KissICP(deskew=True, icp_max_iteration=60, speculate=spec)
+        poses = []
+        for i, t in enumerate(staged):
+            if i in (2, 5):     # the same scan through the reference's own layout (float32 xyz records + float64 timestamps), plain path
+                rec = np.ascontiguousarray(seq[i][:, :3])
+                _, _, p = k.register_cloud(rec, 12, seq[i][:, 3].astype(np.float64))
+            else:
+                if spec and i + 1 < len(staged):
+                    k.hint_next_dev(staged[i + 1].data_ptr(), len(seq[i + 1]))   # (before i = 1 and 4: a hint that the plain call then ignores)
+                p = k.register_frame_dev(t.data_ptr(), len(seq[i]))
+            poses.append(p.copy())
+            if i == 3:
+                k.flush()
+        dump = k.local_map().dump()
+        k.close()
+        return poses, dump
+
+    (a, da), (b, db) = run(False), run(True)
+    for pa, pb in zip(a, b):
+        np.testing.assert_allclose(pa, pb, rtol=0, atol=1e-9)
+    assert np.array_equal(da[0], db[0]) and np.array_equal(da[1], db[1])
+
+
 @pytest.mark.parametrize("cap,voxel", [(10, 1.0), (20, 1.0), (3, 1.0), (10, 0.35)])
 def test_cluster_loop_matches_classic_shape(ctx, pkg, cap, voxel):
     """LIMU_OPT_CLUSTER_LOOP: the Gauss-Newton loop on one 16-CTA cluster (two lanes per query, rows through distributed shared memory,
