@@ -344,7 +344,7 @@ __device__ __forceinline__ void contribution_pair(int l8, const V3 &s, const V3 
 // On return lane L holds the warp total of sum index L>>1 (the layout of warp_reduce_scatter16) in `acc`.
 template <bool NN27, bool PLANE, int ROUNDS>
 __device__ __forceinline__ void icp_query_pass_grouped(const IcpArgs &A, const volatile double *Pv, const double *in, const unsigned short *qidx, int64_t n, int64_t gbase,
-                                                       int64_t gstride, int lane, double &acc, int &ncorr, int &ncand, int &nmiss) {
+                                                       int64_t gstride, int lane, double &acc, int &ncorr, int &ncand, int &nmiss, QueryMemo *memo) {
     const int l8 = lane & 7;
     const unsigned gmask = 0xFFu << (lane & 24);
     const int64_t wfirst = gbase - (lane >> 3);   // first group of this warp: the four groups of a warp iterate together
@@ -367,7 +367,7 @@ __device__ __forceinline__ void icp_query_pass_grouped(const IcpArgs &A, const v
                     tg = V3{ldm(bx + my_rank), ldm(bx + A.map.capp + my_rank), ldm(bx + 2 * A.map.capp + my_rank)};
                 }
             } else {
-                group8_closest<ROUNDS>(A.map, s, gmask, l8, slot, count, own, d2, my_rank, tg);
+                group8_closest<ROUNDS>(A.map, s, gmask, l8, slot, count, own, d2, my_rank, tg, q0 == wfirst ? memo : nullptr);   // (the memo belongs to the first query this group serves in a pass)
             }
             if (my_rank < 0) d2 = sqnorm3(tg.x - s.x, tg.y - s.y, tg.z - s.z);   // nothing found -> (0,0,0), range-tested like a real point
         }
@@ -588,12 +588,21 @@ __device__ unsigned long long g_frame_marks[72];   // [24 + j]: clock of CTA 0 /
 #define CT_MARK(k) do { if (blockIdx.x == 0 && lane == 0 && j == (((k) == 13 || (k) == 14) ? 3 : 2)) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
 #define CW_MARK(k, w) do { if (blockIdx.x == 0 && warp == (w) && lane == 0 && j == (((k) == 13 || (k) == 14) ? 3 : 2)) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
 #define ROUND_MARK() do { if (blockIdx.x == 0 && threadIdx.x == 0 && j < 48) g_frame_marks[24 + j] = (unsigned long long)clock64(); } while (0)
+__device__ unsigned long long g_cta_marks[4][160];   // globaltimer of every CTA of the loop in round 3: [0] round start, [1] S1 (its pass is over), [2] all rows folded, [3] S2
+#define CTA_MARK(k) do { if (threadIdx.x == 0 && j == 3 && blockIdx.x < 160) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_cta_marks[k][blockIdx.x] = _t; } } while (0)
+extern "C" int limu_debug_cta_marks(double out[640]) {
+    unsigned long long h[640];
+    if (cudaMemcpyFromSymbol(h, g_cta_marks, sizeof h) != cudaSuccess) return -1;
+    for (int k = 0; k < 640; ++k) out[k] = (double)h[k];
+    return 0;
+}
 #else
 #define FT_MARK(k) do {} while (0)
 #define IQ_MARK(k) do {} while (0)
 #define CW_MARK(k, w) do {} while (0)
 #define CT_MARK(k) do {} while (0)
 #define ROUND_MARK() do {} while (0)
+#define CTA_MARK(k) do {} while (0)
 #endif
 
 // local_map.update(down_sampled, new_pose) (icp.cpp:81; voxel_hash_map.cpp:138-144) inside a frame kernel: transform + capped ordered insert
@@ -750,9 +759,12 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
     const int64_t wbase = ((int64_t)blockIdx.x * QW + warp) * 32, wstride = (int64_t)A.icp_blocks * QW * 32;
     int j = 0;
     int converged = 0;
+    QueryMemo memo;   // (latency shape, reference rules: what this lane's group found for its query in the previous iteration)
+    memo.own = -1; memo.kx = memo.ky = memo.kz = 0; memo.slot = -1; memo.count = 0;
     if (run_icp && icp_member) for (;;) {
         const bool no_more = j >= A.max_iter;   // nothing left to do but wait for the verdict on iteration j-1
         ROUND_MARK();
+        CTA_MARK(0);
         if (warp < QW) {
             if (!no_more) {
                 CW_MARK(6, 0);
@@ -769,9 +781,9 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
                     else if (A.map.cap <= 16) icp_query_pass_coop<2>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
                     else icp_query_pass_coop<3>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
                 } else if (SHAPE == 0) {                 // latency shape: eight lanes per query
-                    if (A.map.cap <= 8) icp_query_pass_grouped<NN27, PLANE, 1>(A, Pv, in, qi0, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
-                    else if (A.map.cap <= 16) icp_query_pass_grouped<NN27, PLANE, 2>(A, Pv, in, qi0, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
-                    else icp_query_pass_grouped<NN27, PLANE, 3>(A, Pv, in, qi0, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss);
+                    if (A.map.cap <= 8) icp_query_pass_grouped<NN27, PLANE, 1>(A, Pv, in, qi0, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss, &memo);
+                    else if (A.map.cap <= 16) icp_query_pass_grouped<NN27, PLANE, 2>(A, Pv, in, qi0, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss, &memo);
+                    else icp_query_pass_grouped<NN27, PLANE, 3>(A, Pv, in, qi0, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss, &memo);
                 } else {
                     icp_query_pass<NN27, PLANE>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
                 }
@@ -811,6 +823,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
         }
         __syncthreads();   // S1: CTA partial sums of pass j, and the verdict on iteration j-1
         CW_MARK(11, 0);
+        CTA_MARK(1);
         if (j > 0 && verdict == 2 && done) { converged = 1; break; }   // (the pass just made belongs to an iteration that does not exist)
         if (no_more) break;
         const unsigned int stamp = 0x80000000u | ((A.ll_stamp_base + (unsigned int)j) & 0x7FFFFFFFu);
@@ -861,6 +874,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
             }
         }
         __syncthreads();
+        CTA_MARK(2);
         if (!PLANE && A.nranks > 1) {
             // Fused exchange: CTA 0 stores this rank's row into EVERY rank's mailbox (its own included) over NVLink, then a
             // system-scope release of the stamp; every CTA of every rank then waits for all stamps in its LOCAL mailbox and
@@ -933,6 +947,7 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
         }
         __syncthreads();   // S2: the estimate is visible to the query warps
         CW_MARK(15, 0);
+        CTA_MARK(3);
         ++j;
         if (verdict == 1) {   // iteration j-1 converged: finish its bookkeeping (the tail above, without a pass beside it) and leave
             if (warp == QW) {

@@ -50,6 +50,18 @@ else:
 print("rounds of the Gauss-Newton loop (us, CTA 0, mean over scans; nan = fewer rounds):", [round(float(x), 2) for x in np.nanmean(np.array(rounds), axis=0)])
 if vrows:
     print("k_voxelize phases (us; plain launch, 1024-thread CTAs): P1 deskew + claim | P2 flags, counts, scatter, claim 2 | P3 un-claim, flags, counts, scatter:", [round(float(x), 2) for x in np.mean(np.array(vrows), axis=0)], "total", round(float(np.sum(np.mean(np.array(vrows), axis=0))), 2))
+if hasattr(pkg.lib(), "limu_debug_cta_marks"):
+    cm = np.zeros(640)
+    pkg.lib().limu_debug_cta_marks(cm.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    cm = cm.reshape(4, 160)
+    live = cm[0] > cm[0].max() - 1e6          # (marks of CTAs that only took part in an earlier, larger launch are stale)
+    cm = cm[:, live]
+    nb = cm.shape[1]
+    t0 = cm[0, :nb].min()
+    q = lambda a: "min %.2f / median %.2f / max %.2f" % (np.min(a), np.median(a), np.max(a))
+    print("round 3 of the last scan over the %d CTAs of the loop (us after the first CTA started the round): round start %s | pass over (S1) %s | rows folded %s | S2 %s"
+          % (nb, q((cm[0, :nb] - t0) / 1e3), q((cm[1, :nb] - t0) / 1e3), q((cm[2, :nb] - t0) / 1e3), q((cm[3, :nb] - t0) / 1e3)))
+    print("  pass duration per CTA (S1 - round start):", q((cm[1, :nb] - cm[0, :nb]) / 1e3), "| ten slowest CTAs:", np.argsort(cm[1, :nb] - cm[0, :nb])[-10:].tolist())
 print("IQR phase of the last scan (SM cycles of CTA 0): squared ranges + ranking", cyc(16, 17), "| barrier of the loop CTAs", cyc(17, 18), "| local compaction (+ keypoints written out)", cyc(18, 19))
 
 # ---- timeline of the pipelined path (hinted device replay): one ring of (id, globaltimer) records per translation unit, merged here
