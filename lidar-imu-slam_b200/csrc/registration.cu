@@ -588,8 +588,11 @@ __device__ unsigned long long g_frame_marks[72];   // [24 + j]: clock of CTA 0 /
 #define CT_MARK(k) do { if (blockIdx.x == 0 && lane == 0 && j == (((k) == 13 || (k) == 14) ? 3 : 2)) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
 #define CW_MARK(k, w) do { if (blockIdx.x == 0 && warp == (w) && lane == 0 && j == (((k) == 13 || (k) == 14) ? 3 : 2)) g_frame_marks[k] = (unsigned long long)clock64(); } while (0)
 #define ROUND_MARK() do { if (blockIdx.x == 0 && threadIdx.x == 0 && j < 48) g_frame_marks[24 + j] = (unsigned long long)clock64(); } while (0)
+__device__ unsigned int g_warp_pass[160][8];   // SM cycles every warp of the loop spent in its pass of round 3
 __device__ unsigned long long g_cta_marks[4][160];   // globaltimer of every CTA of the loop in round 3: [0] round start, [1] S1 (its pass is over), [2] all rows folded, [3] S2
+#define WARP_PASS(t0) do { if (lane == 0 && j == 3 && blockIdx.x < 160) g_warp_pass[blockIdx.x][warp] = (unsigned int)(clock64() - (t0)); } while (0)
 #define CTA_MARK(k) do { if (threadIdx.x == 0 && j == 3 && blockIdx.x < 160) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_cta_marks[k][blockIdx.x] = _t; } } while (0)
+extern "C" int limu_debug_warp_pass(unsigned int out[1280]) { return cudaMemcpyFromSymbol(out, g_warp_pass, sizeof(unsigned int) * 1280) == cudaSuccess ? 0 : -1; }
 extern "C" int limu_debug_cta_marks(double out[640]) {
     unsigned long long h[640];
     if (cudaMemcpyFromSymbol(h, g_cta_marks, sizeof h) != cudaSuccess) return -1;
@@ -603,6 +606,7 @@ extern "C" int limu_debug_cta_marks(double out[640]) {
 #define CT_MARK(k) do {} while (0)
 #define ROUND_MARK() do {} while (0)
 #define CTA_MARK(k) do {} while (0)
+#define WARP_PASS(t0) do {} while (0)
 #endif
 
 // local_map.update(down_sampled, new_pose) (icp.cpp:81; voxel_hash_map.cpp:138-144) inside a frame kernel: transform + capped ordered insert
@@ -768,6 +772,9 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
         if (warp < QW) {
             if (!no_more) {
                 CW_MARK(6, 0);
+#ifdef LIMU_ICP_PHASE_TIMING
+                const long long wp0 = clock64();
+#endif
                 double acc = 0.0;            // lane L: running total of sum index L>>1
                 int ncorr = 0, ncand = 0, nmiss = 0;
                 const volatile double *Pv = j == 0 ? Tinit : E;   // re-read per batch: keeps 14 registers free across the lookup
@@ -788,6 +795,9 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
                     icp_query_pass<NN27, PLANE>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
                 }
                 CW_MARK(7, 0);
+#ifdef LIMU_ICP_PHASE_TIMING
+                WARP_PASS(wp0);
+#endif
                 if (PLANE) {
                     red[warp * 32 + lane] = acc;   // lane L of every warp holds sum L (27 sums + 3 counters + 2 zeros)
                 } else {                           // 16 sums (even lanes hold them) + 3 counters

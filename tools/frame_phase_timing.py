@@ -54,7 +54,7 @@ if hasattr(pkg.lib(), "limu_debug_cta_marks"):
     cm = np.zeros(640)
     pkg.lib().limu_debug_cta_marks(cm.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
     cm = cm.reshape(4, 160)
-    live = cm[0] > cm[0].max() - 1e6          # (marks of CTAs that only took part in an earlier, larger launch are stale)
+    live = cm[0] > cm[0].max() - 5e4          # (marks of CTAs that only took part in an earlier, larger launch are stale)
     cm = cm[:, live]
     nb = cm.shape[1]
     t0 = cm[0, :nb].min()
@@ -62,6 +62,14 @@ if hasattr(pkg.lib(), "limu_debug_cta_marks"):
     print("round 3 of the last scan over the %d CTAs of the loop (us after the first CTA started the round): round start %s | pass over (S1) %s | rows folded %s | S2 %s"
           % (nb, q((cm[0, :nb] - t0) / 1e3), q((cm[1, :nb] - t0) / 1e3), q((cm[2, :nb] - t0) / 1e3), q((cm[3, :nb] - t0) / 1e3)))
     print("  pass duration per CTA (S1 - round start):", q((cm[1, :nb] - cm[0, :nb]) / 1e3), "| ten slowest CTAs:", np.argsort(cm[1, :nb] - cm[0, :nb])[-10:].tolist())
+if hasattr(pkg.lib(), "limu_debug_warp_pass"):
+    wp = np.zeros(1280, np.uint32)
+    pkg.lib().limu_debug_warp_pass(wp.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)))
+    wp = wp.reshape(160, 8)[:, :7].astype(np.float64) / 1.965e3
+    if hasattr(pkg.lib(), "limu_debug_cta_marks"):
+        wp = wp[:len(live)][live]
+    print("pass of round 3 per warp (us, %d CTAs x 7 query warps): median %.2f | p90 %.2f | p99 %.2f | max %.2f | mean per warp index %s | slowest warp per CTA: median %.2f, max %.2f"
+          % (len(wp), np.median(wp), np.percentile(wp, 90), np.percentile(wp, 99), wp.max(), [round(float(x), 2) for x in wp.mean(axis=0)], np.median(wp.max(axis=1)), wp.max()))
 print("IQR phase of the last scan (SM cycles of CTA 0): squared ranges + ranking", cyc(16, 17), "| barrier of the loop CTAs", cyc(17, 18), "| local compaction (+ keypoints written out)", cyc(18, 19))
 
 # ---- timeline of the pipelined path (hinted device replay): one ring of (id, globaltimer) records per translation unit, merged here
