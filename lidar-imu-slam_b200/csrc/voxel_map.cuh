@@ -304,6 +304,9 @@ static __device__ __noinline__ int group8_resolve_rare(MapProbe mp, int kx, int 
 struct QueryMemo {
     int kx, ky, kz;
     int slot, count, own;   // own < 0: nothing remembered
+#ifdef LIMU_ICP_PHASE_TIMING
+    int dbg;                // instrumented build: bit 0 = the last lookup was not a repeat, bit 1 = it left the common path (displaced / absent voxel)
+#endif
 };
 // memo (optional): a repeat goes straight to the candidates of the remembered block. Repeats and first-time lookups share ONE instruction
 // stream (the remembered slot merely replaces the home slot as the block whose candidates are requested; the header load is predicated
@@ -321,13 +324,20 @@ __device__ __forceinline__ void group8_closest_at(const MapView &m, const V3 &p,
         if (!repeat) sv = load_slot(slot_at(m, h));
         double cx[ROUNDS], cy[ROUNDS], cz[ROUNDS];
         group8_load<ROUNDS>(m, first, l8, cx, cy, cz);
-        ulonglong2 got[PREFETCH_NB ? 4 : 1];
-        if (PREFETCH_NB) group8_probe_neighbours(m, kx, ky, kz, l8, got);
+        // A first-time lookup inside a Gauss-Newton loop (memo given, not a repeat) also requests the 26 neighbour probes now: if the voxel turns
+        // out to be absent the answer is one more trip away instead of two, and such a lookup -- a handful per iteration after the first --
+        // is what the whole iteration waits for. (Probing on EVERY query, PREFETCH_NB, cost more than it saved.)
+        const bool probe_now = PREFETCH_NB || (memo != nullptr && !repeat);
+        ulonglong2 got[4];
+        if (probe_now) group8_probe_neighbours(m, kx, ky, kz, l8, got);
+#ifdef LIMU_ICP_PHASE_TIMING
+        if (memo) memo->dbg = (repeat ? 0 : 1) | ((!repeat && !(inr && sv.x == key)) ? 2 : 0);
+#endif
         if (repeat) {
             slot = memo->slot; count = memo->count; own = memo->own;
         } else if (inr && sv.x == key) {
             slot = (int)h; count = meta_count(sv.y); own = 1;
-        } else if (PREFETCH_NB) {
+        } else if (probe_now) {
             slot = group8_resolve_core(m, kx, ky, kz, inr, key, h, sv, got, gmask, l8, &count, &own);
             if (slot >= 0) group8_load<ROUNDS>(m, (unsigned int)slot, l8, cx, cy, cz);
         } else {   // group-uniform: all eight lanes saw the same header

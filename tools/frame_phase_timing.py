@@ -65,9 +65,14 @@ if hasattr(pkg.lib(), "limu_debug_cta_marks"):
 if hasattr(pkg.lib(), "limu_debug_warp_pass"):
     wp = np.zeros(1280, np.uint32)
     pkg.lib().limu_debug_warp_pass(wp.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)))
-    wp = wp.reshape(160, 8)[:, :7].astype(np.float64) / 1.965e3
+    wflags = (wp.reshape(160, 8)[:, :7] >> 24)
+    wp = (wp.reshape(160, 8)[:, :7] & 0xFFFFFF).astype(np.float64) / 1.965e3
     if hasattr(pkg.lib(), "limu_debug_cta_marks"):
         wp = wp[:len(live)][live]
+        wflags = wflags[:len(live)][live]
+    for name, sel in (("all four lookups repeats", wflags == 0), ("a first-time lookup on the common path", wflags == 1), ("a lookup off the common path", wflags >= 2)):
+        if sel.any():
+            print("    warps with %-40s %4d: median %.2f  max %.2f us" % (name + ":", int(sel.sum()), np.median(wp[sel]), wp[sel].max()))
     print("pass of round 3 per warp (us, %d CTAs x 7 query warps): median %.2f | p90 %.2f | p99 %.2f | max %.2f | mean per warp index %s | slowest warp per CTA: median %.2f, max %.2f"
           % (len(wp), np.median(wp), np.percentile(wp, 90), np.percentile(wp, 99), wp.max(), [round(float(x), 2) for x in wp.mean(axis=0)], np.median(wp.max(axis=1)), wp.max()))
 print("IQR phase of the last scan (SM cycles of CTA 0): squared ranges + ranking", cyc(16, 17), "| barrier of the loop CTAs", cyc(17, 18), "| local compaction (+ keypoints written out)", cyc(18, 19))
