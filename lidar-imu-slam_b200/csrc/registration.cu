@@ -590,7 +590,7 @@ __device__ unsigned long long g_frame_marks[72];   // [24 + j]: clock of CTA 0 /
 #define ROUND_MARK() do { if (blockIdx.x == 0 && threadIdx.x == 0 && j < 48) g_frame_marks[24 + j] = (unsigned long long)clock64(); } while (0)
 __device__ unsigned int g_warp_pass[160][8];   // SM cycles every warp of the loop spent in its pass of round 3
 __device__ unsigned long long g_cta_marks[4][160];   // globaltimer of every CTA of the loop in round 3: [0] round start, [1] S1 (its pass is over), [2] all rows folded, [3] S2
-#define WARP_PASS(t0) do { const unsigned int _f = __reduce_or_sync(0xFFFFFFFFu, (unsigned int)memo.dbg); if (lane == 0 && j == 3 && blockIdx.x < 160) g_warp_pass[blockIdx.x][warp] = ((unsigned int)(clock64() - (t0)) & 0xFFFFFFu) | (_f << 24); } while (0)
+#define WARP_PASS(t0) do { if (lane == 0 && j == 3 && blockIdx.x < 160) g_warp_pass[blockIdx.x][warp] = (unsigned int)(clock64() - (t0)) & 0xFFFFFFu; } while (0)
 #define CTA_MARK(k) do { if (threadIdx.x == 0 && j == 3 && blockIdx.x < 160) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_cta_marks[k][blockIdx.x] = _t; } } while (0)
 extern "C" int limu_debug_warp_pass(unsigned int out[1280]) { return cudaMemcpyFromSymbol(out, g_warp_pass, sizeof(unsigned int) * 1280) == cudaSuccess ? 0 : -1; }
 extern "C" int limu_debug_cta_marks(double out[640]) {
@@ -765,9 +765,6 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
     int converged = 0;
     QueryMemo memo;   // (latency shape, reference rules: what this lane's group found for its query in the previous iteration)
     memo.own = -1; memo.kx = memo.ky = memo.kz = 0; memo.slot = -1; memo.count = 0;
-#ifdef LIMU_ICP_PHASE_TIMING
-    memo.dbg = 0;
-#endif
     if (run_icp && icp_member) for (;;) {
         const bool no_more = j >= A.max_iter;   // nothing left to do but wait for the verdict on iteration j-1
         ROUND_MARK();

@@ -298,53 +298,36 @@ static __device__ __noinline__ int group8_resolve_rare(MapProbe mp, int kx, int 
 // (the bandwidth shape computes them with ONE lane per query and hands them to the group by shuffle).
 // PREFETCH_NB (latency shape, registers to spare): the 26 neighbour probes are requested together with the home block, so an absent voxel
 // costs two round trips (probes, then the neighbour's candidates) instead of three -- the slowest query of an iteration sets its pace.
-// What a group remembers about the query it serves in every iteration of a Gauss-Newton loop: the voxel index it resolved last time and
-// the answer. The map does not change inside a launch and an iteration moves a point by less and less, so from the second iteration on
-// nearly every lookup -- in particular the slow kind, an absent voxel answered by a neighbour after two more round trips -- is a repeat.
-struct QueryMemo {
-    int kx, ky, kz;
-    int slot, count, own;   // own < 0: nothing remembered
-#ifdef LIMU_ICP_PHASE_TIMING
-    int dbg;                // instrumented build: bit 0 = the last lookup was not a repeat, bit 1 = it left the common path (displaced / absent voxel)
-#endif
-};
-// memo (optional): a repeat goes straight to the candidates of the remembered block. Repeats and first-time lookups share ONE instruction
-// stream (the remembered slot merely replaces the home slot as the block whose candidates are requested; the header load is predicated
-// off), so a warp whose four groups are in different situations does not run two paths one after the other.
+// known: the caller has resolved this voxel index before (slot_out / count_out / own_out hold the answer, the map has not changed since):
+// straight to the candidates of that block, one round trip whatever the voxel's situation was.
 template <int ROUNDS, bool PREFETCH_NB = false>
 __device__ __forceinline__ void group8_closest_at(const MapView &m, const V3 &p, int kx, int ky, int kz, bool inr, unsigned long long key, unsigned int h,
                                                   unsigned gmask, int l8, int &slot_out, int &count_out, int &own_out, double &d2_out, int &rank_out, V3 &t_out,
-                                                  QueryMemo *memo = nullptr) {
+                                                  bool known = false) {
     double bd2 = 1.7976931348623157e308, tx = 0.0, ty = 0.0, tz = 0.0;
     int br = 0x7FFFFFFF, slot, count, own;
-    {   // the one round trip of the common case: header and this lane's candidate ranks of the home block, requested together
-        const bool repeat = memo && memo->own >= 0 && memo->kx == kx && memo->ky == ky && memo->kz == kz;   // group-uniform
-        const unsigned int first = (repeat && memo->slot >= 0) ? (unsigned int)memo->slot : h;
-        ulonglong2 sv = make_ulonglong2(KEY_EMPTY, 0ull);
-        if (!repeat) sv = load_slot(slot_at(m, h));
+    if (known) {
+        slot = slot_out; count = count_out; own = own_out;
+        if (slot >= 0) {
+            double cx[ROUNDS], cy[ROUNDS], cz[ROUNDS];
+            group8_load<ROUNDS>(m, (unsigned int)slot, l8, cx, cy, cz);
+            group8_scan<ROUNDS>(p, l8, count, cx, cy, cz, bd2, br, tx, ty, tz);
+        }
+    } else {   // the one round trip of the common case: header and this lane's candidate ranks of the home block, requested together
+        const ulonglong2 sv = load_slot(slot_at(m, h));
         double cx[ROUNDS], cy[ROUNDS], cz[ROUNDS];
-        group8_load<ROUNDS>(m, first, l8, cx, cy, cz);
-        // A first-time lookup inside a Gauss-Newton loop (memo given, not a repeat) also requests the 26 neighbour probes now: if the voxel turns
-        // out to be absent the answer is one more trip away instead of two, and such a lookup -- a handful per iteration after the first --
-        // is what the whole iteration waits for. (Probing on EVERY query, PREFETCH_NB, cost more than it saved.)
-        const bool probe_now = PREFETCH_NB || (memo != nullptr && !repeat);
-        ulonglong2 got[4];
-        if (probe_now) group8_probe_neighbours(m, kx, ky, kz, l8, got);
-#ifdef LIMU_ICP_PHASE_TIMING
-        if (memo) memo->dbg = (repeat ? 0 : 1) | ((!repeat && !(inr && sv.x == key)) ? 2 : 0);
-#endif
-        if (repeat) {
-            slot = memo->slot; count = memo->count; own = memo->own;
-        } else if (inr && sv.x == key) {
+        group8_load<ROUNDS>(m, h, l8, cx, cy, cz);
+        ulonglong2 got[PREFETCH_NB ? 4 : 1];
+        if (PREFETCH_NB) group8_probe_neighbours(m, kx, ky, kz, l8, got);
+        if (inr && sv.x == key) {
             slot = (int)h; count = meta_count(sv.y); own = 1;
-        } else if (probe_now) {
+        } else if (PREFETCH_NB) {
             slot = group8_resolve_core(m, kx, ky, kz, inr, key, h, sv, got, gmask, l8, &count, &own);
             if (slot >= 0) group8_load<ROUNDS>(m, (unsigned int)slot, l8, cx, cy, cz);
         } else {   // group-uniform: all eight lanes saw the same header
             slot = group8_resolve_rare(MapProbe{m.blk, m.mask, m.shift, m.stride}, kx, ky, kz, inr, key, h, sv, gmask, l8, &count, &own);
             if (slot >= 0) group8_load<ROUNDS>(m, (unsigned int)slot, l8, cx, cy, cz);   // displaced or neighbour voxel: its candidates are a second trip
         }
-        if (memo && !repeat) { memo->kx = kx; memo->ky = ky; memo->kz = kz; memo->slot = slot; memo->count = count; memo->own = own; }
         if (slot >= 0) group8_scan<ROUNDS>(p, l8, count, cx, cy, cz, bd2, br, tx, ty, tz);
     }
     if (slot >= 0 && count > 8 * ROUNDS) {   // max_points_per_voxel beyond the register-resident part (cap > 24)
@@ -368,15 +351,31 @@ __device__ __forceinline__ void group8_closest_at(const MapView &m, const V3 &p,
     slot_out = slot; count_out = count; own_out = own; d2_out = bd2; rank_out = br == 0x7FFFFFFF ? -1 : br;
     t_out = br == 0x7FFFFFFF ? V3{0.0, 0.0, 0.0} : V3{tx, ty, tz};   // nothing found -> (0,0,0)
 }
+// What a group remembers about the query it serves in every iteration of a Gauss-Newton loop: the voxel index it resolved last time and
+// the answer. The map does not change inside a launch and an iteration moves a point by less and less, so from the second iteration on
+// nearly every lookup -- in particular the slow kind, an absent voxel answered by a neighbour after two more round trips -- is a repeat.
+// (Measured alternatives, profiles/r2_latency_loop_lookup_variants.json: repeats and first-time lookups in ONE instruction stream, and
+//  neighbour probes requested together with the home block on first-time lookups, both made the rare warp faster -- 3.5 -> 2.9 us --
+//  and every other warp slower -- 1.45 -> 1.7 us; scans/s went down.)
+struct QueryMemo {
+    int kx, ky, kz;
+    int slot, count, own;   // own < 0: nothing remembered
+};
 template <int ROUNDS>
 __device__ __forceinline__ void group8_closest(const MapView &m, const V3 &p, unsigned gmask, int l8, int &slot_out, int &count_out, int &own_out,
                                                double &d2_out, int &rank_out, V3 &t_out, QueryMemo *memo = nullptr) {
     const int kx = vox_index(m, p.x), ky = vox_index(m, p.y), kz = vox_index(m, p.z);
+    if (memo && memo->own >= 0 && memo->kx == kx && memo->ky == ky && memo->kz == kz) {   // group-uniform
+        slot_out = memo->slot; count_out = memo->count; own_out = memo->own;
+        group8_closest_at<ROUNDS, false>(m, p, kx, ky, kz, false, 0ull, 0u, gmask, l8, slot_out, count_out, own_out, d2_out, rank_out, t_out, true);
+        return;
+    }
     const bool inr = key_in_range(kx, ky, kz);
     const unsigned long long key = pack_key(kx, ky, kz);
     // (PREFETCH_NB was measured in the pipeline's latency shape: the absent-voxel path got shorter, but the four extra probes and their key
     //  arithmetic on EVERY query cost more than they saved -- 9.2 vs 8.7 us per iteration -- so it stays off)
-    group8_closest_at<ROUNDS, false>(m, p, kx, ky, kz, inr, key, inr ? slot_of(key, m.shift) : 0u, gmask, l8, slot_out, count_out, own_out, d2_out, rank_out, t_out, memo);
+    group8_closest_at<ROUNDS, false>(m, p, kx, ky, kz, inr, key, inr ? slot_of(key, m.shift) : 0u, gmask, l8, slot_out, count_out, own_out, d2_out, rank_out, t_out);
+    if (memo) { memo->kx = kx; memo->ky = ky; memo->kz = kz; memo->slot = slot_out; memo->count = count_out; memo->own = own_out; }
 }
 
 // Pair-cooperative lookup for the cluster latency shape (registration.cu, k_frame_cluster): TWO lanes serve one query, so that one

@@ -70,7 +70,8 @@ if hasattr(pkg.lib(), "limu_debug_warp_pass"):
     if hasattr(pkg.lib(), "limu_debug_cta_marks"):
         wp = wp[:len(live)][live]
         wflags = wflags[:len(live)][live]
-    for name, sel in (("all four lookups repeats", wflags == 0), ("a first-time lookup on the common path", wflags == 1), ("a lookup off the common path", wflags >= 2)):
+    for name, sel in (("all four lookups repeats", wflags == 0), ("a first-time lookup on the common path", wflags == 1), ("a lookup off the common path", wflags >= 2),
+                      ("  ... a displaced voxel (linear probing)", (wflags & 8) != 0), ("  ... an absent voxel (neighbour fallback)", (wflags & 4) != 0)):
         if sel.any():
             print("    warps with %-40s %4d: median %.2f  max %.2f us" % (name + ":", int(sel.sum()), np.median(wp[sel]), wp[sel].max()))
     print("pass of round 3 per warp (us, %d CTAs x 7 query warps): median %.2f | p90 %.2f | p99 %.2f | max %.2f | mean per warp index %s | slowest warp per CTA: median %.2f, max %.2f"
