@@ -559,7 +559,9 @@ static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n,
         const int st = odom_launch_loop(o, npar, ah.n, ah.init, new_pose, ah.sigma);
         if (st != LIMU_OK) { (void)odom_drop_ahead(o, true); return st; }
     }
-    // 7. this scan's clouds (complete since its loop ended; both streams are busy with later work)
+    // 7. this scan's clouds (both streams are busy with later work). The keypoint cloud is the last thing the loop kernel writes -- after the
+    //    result block this call woke up on -- so a caller who wants it waits for the kernel itself.
+    if (keypoints_xyz && nk > 0) LIMU_CUDA_TRY(cudaEventSynchronize(o->loop_done[par]));
     LIMU_TRY(odom_copy_clouds(o, true, par, nd, nk, down_xyz, keypoints_xyz));
     LIMU_TRY(odom_report(o, hc, vox_word, -1, hit_vox, n, deskewed, sigma, stats));
     return deferred;

@@ -985,37 +985,39 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
     LIMU_TRACE(3);
     // new_pose = T_icp * init_guess (:129); with an empty map the loop did not run and this is init_guess itself (:99-100). What follows is
     // CTA 0's: in a launch without the map-update epilogue (pipelined odometry) the next scan's k_voxelize sits behind this kernel in the
-    // stream, so its tail is kept short: thread 0 takes pose and deskew twist while warps 1.. write the keypoints out, then warp 0 leaves
-    // the result block in pinned host memory.
+    // stream, so its tail is kept short: thread 0 takes the pose, warp 0 leaves the result block in pinned host memory, then thread 0
+    // takes the deskew twist while warps 1.. write the keypoints out.
     if (blockIdx.x == 0) {
         if (threadIdx.x == 0) {
-            // (the map update of this scan, on another stream, is released by this flag: the loop's reads of the map are over)
-            if (!A.upd_down && A.loop_flag) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.loop_flag), "r"(A.loop_seq) : "memory");
             const Pose np = run_icp ? mul(pose_load(Ticp), pose_load(Tinit)) : pose_load(Tinit);
             pose_store(np, A.out);
             A.out[7] = (double)j; A.out[8] = (double)converged; A.out[9] = S[I_NCORR]; A.out[10] = S[I_NCORR + 1]; A.out[11] = S[I_NCORR + 2]; A.out[12] = (double)n;
-            if (!A.upd_down) publish_twist(A, np);
+            if (A.host_res && n_keypoints >= 0) *A.iqr_count = n_keypoints;   // (part of the result block that leaves below; the warps that write the cloud out store it again)
+            if (!A.upd_down && A.loop_flag) {
+                // the map update of this scan, on another stream, is released by this flag: the pose is in memory, the loop's reads of the map are over
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.loop_flag), "r"(A.loop_seq) : "memory");
+            }
         }
+        if (A.host_res && threadIdx.x < 32) {
+            // Result block -> pinned host memory as ONE 256-byte store of warp 0, FIRST (the stores take a microsecond or two to cross PCIe,
+            // and a kernel is not over before they have): words 0..29 data, 30 = XOR of the others, 31 = this launch's sequence number.
+            // No system-scope fence: the host accepts the block when the sequence number is the one it waits for AND the checksum holds,
+            // so a torn read is simply read again. (The keypoint CLOUD is complete when the kernel is: a host that wants it waits for that.)
+            __syncwarp();
+            unsigned long long w = 0ull;
+            if ((int)threadIdx.x < A.res_doubles && threadIdx.x < 30) w = (unsigned long long)__double_as_longlong(__ldcg(A.res_block + threadIdx.x));
+            if (threadIdx.x == 31) w = (unsigned long long)A.loop_seq;
+            unsigned long long x = threadIdx.x == 30 ? 0ull : w;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x ^= __shfl_xor_sync(0xFFFFFFFFu, x, o);
+            if (threadIdx.x == 30) w = x;
+            reinterpret_cast<volatile unsigned long long *>(A.host_res)[threadIdx.x] = w;
+        }
+        if (threadIdx.x == 0 && !A.upd_down) publish_twist(A, pose_load(A.out));   // (~3 us of scalar code beside the cloud being written out)
         if (n_keypoints >= 0) {   // keypoints for the host
             if (A.host_res) { if (threadIdx.x >= 32) iqr_write_out<ICP_BLOCK - 32>(qidx_s, A.iqr_in, n_keypoints, A.iqr_out, A.iqr_count, (int)threadIdx.x - 32); }
             else iqr_write_out<ICP_BLOCK>(qidx_s, A.iqr_in, n_keypoints, A.iqr_out, A.iqr_count, (int)threadIdx.x);
-        }
-        if (A.host_res) {
-            // Result block -> pinned host memory as ONE 256-byte store of warp 0: words 0..29 data, 30 = XOR of the others, 31 = this launch's
-            // sequence number. No system-scope fence (several microseconds over PCIe): the host accepts the block when the sequence number
-            // is the one it waits for AND the checksum holds, so a torn read is simply read again.
-            __threadfence();   // (the keypoints are in L2 before the host can start a copy of them)
-            __syncthreads();
-            if (threadIdx.x < 32) {
-                unsigned long long w = 0ull;
-                if ((int)threadIdx.x < A.res_doubles && threadIdx.x < 30) w = (unsigned long long)__double_as_longlong(__ldcg(A.res_block + threadIdx.x));
-                if (threadIdx.x == 31) w = (unsigned long long)A.loop_seq;
-                unsigned long long x = threadIdx.x == 30 ? 0ull : w;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) x ^= __shfl_xor_sync(0xFFFFFFFFu, x, o);
-                if (threadIdx.x == 30) w = x;
-                reinterpret_cast<volatile unsigned long long *>(A.host_res)[threadIdx.x] = w;
-            }
         }
     }
     if (A.upd_down) frame_update_epilogue<ICP_BLOCK>(A, gs, E);

@@ -14,6 +14,8 @@
 // this launch is un-claimed by the NEXT launch, which works on the other of two stage-2 tables.
 // "First point per voxel wins, output in first-occurrence order" (icp.cpp:13-27 + the oracle's ordered map) becomes:
 // atomicMin of the input index per voxel, then a stable compaction over VX_BLOCK-point tiles.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "compact.cuh"
@@ -156,7 +158,7 @@ __device__ unsigned long long g_vox_marks[8];   // globaltimer of thread 0 of CT
 // BLOCK threads handle tiles of VX_TILE = BLOCK * ITEMS consecutive points, ITEMS per thread: the full-size launch is 1024 x 1, the launch
 // that runs beside the map update 512 x 2 -- half the registers per SM, the same tiles, and a thread's two claims in flight together.
 template <int BLOCK, int ITEMS>
-static __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_voxelize(const VoxelizeArgs A) {
+__device__ __forceinline__ void voxelize_body(const VoxelizeArgs &A) {
     constexpr int TILE = BLOCK * ITEMS;
     __shared__ int ws[32];
     __shared__ int total;
@@ -321,6 +323,11 @@ static __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_voxelize(const V
         if (atomicAdd(A.barrier + 1, 1u) == gridDim.x - 1) { A.barrier[0] = 0u; A.barrier[1] = 0u; __threadfence(); }
     }
 }
+// The three launch shapes: full (alone on the GPU: 1024 threads x 64 registers = a whole register file), half (512 x 2 points) and lean
+// (1024 x 1 at 48 registers, a few spills) -- the latter two leave 16 K registers per SM to the map update's CTA that runs beside them.
+static __global__ void __launch_bounds__(VX_BLOCK, 1) k_voxelize_full(const VoxelizeArgs A) { voxelize_body<VX_BLOCK, 1>(A); }
+static __global__ void __launch_bounds__(VX_BLOCK_BESIDE, 2) k_voxelize_half(const VoxelizeArgs A) { voxelize_body<VX_BLOCK_BESIDE, VX_TILE / VX_BLOCK_BESIDE>(A); }
+static __global__ void __maxnreg__(48) k_voxelize_lean(const VoxelizeArgs A) { voxelize_body<VX_BLOCK, 1>(A); }
 
 // One thread that waits until a frame kernel launched EARLIER on another stream has published the pose of its scan (the flag carries that
 // launch's sequence number): the stream it sits in -- the next scan's k_voxelize behind it -- is released the moment the Gauss-Newton loop is
@@ -377,7 +384,7 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     }
     if (g_vx_blocks_per_sm == 0) {
         int b = 0;
-        LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_voxelize<VX_BLOCK, 1>, VX_BLOCK, 0));
+        LIMU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_voxelize_full, VX_BLOCK, 0));
         g_vx_blocks_per_sm = std::max(1, std::min(b, 1024 / VX_BLOCK));
     }
     const int64_t C1 = pow2_slots(n), C2 = pow2_slots(n);
@@ -446,8 +453,10 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     if (status_used) *status_used = w;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->sm_count * (beside ? 1 : g_vx_blocks_per_sm));
     void *args[] = {&A};
-    if (beside) LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize<VX_BLOCK_BESIDE, VX_TILE / VX_BLOCK_BESIDE>, dim3(grid), dim3(VX_BLOCK_BESIDE), args, 0, stream));
-    else LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize<VX_BLOCK, 1>, dim3(grid), dim3(VX_BLOCK), args, 0, stream));
+    static const int beside_shape = getenv("LIMU_VX_BESIDE") ? atoi(getenv("LIMU_VX_BESIDE")) : 1;   // 1: lean (measured 2.6 % more scans/s than half, profiles/r2_voxelize_beside_ab.json), 0: half
+    if (beside && beside_shape == 1) LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize_lean, dim3(grid), dim3(VX_BLOCK), args, 0, stream));
+    else if (beside) LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize_half, dim3(grid), dim3(VX_BLOCK_BESIDE), args, 0, stream));
+    else LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize_full, dim3(grid), dim3(VX_BLOCK), args, 0, stream));
     LIMU_LAUNCHED();
     return LIMU_OK;
 }
