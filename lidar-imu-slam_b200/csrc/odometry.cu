@@ -509,13 +509,11 @@ static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n,
         LIMU_TRY(o->frame.reserve(nb, ps));
         LIMU_TRY(o->down[npar].reserve(nb, ps));
         LIMU_TRY(o->src0[npar].reserve(nb, ps));
-        if (next_ready && cudaEventQuery(next_ready) == cudaSuccess) next_ready = nullptr;   // (the upload is long over: nothing to wait for in the stream)
-        else (void)cudaGetLastError();
         if (next_ready) LIMU_CUDA_TRY(cudaStreamWaitEvent(ps, next_ready, 0));
         int w = 0;
         if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->pev_vox[npar][0], ps));
         LIMU_TRY(voxelize_device(c, o->vx, next_ptr, 0, 0, nullptr, next_deskew, nullptr, next_n, v, o->frame.as<double>(), o->down[npar].as<double>(), o->src0[npar].as<double>(),
-                                 res_counts(cnt, npar), next_deskew ? o->twist_next.as<double>() : nullptr, vox_status, &w, ps, true, nullptr, 0u, !next_ready));   // (behind an event wait the stream predecessor is not the loop kernel)
+                                 res_counts(cnt, npar), next_deskew ? o->twist_next.as<double>() : nullptr, vox_status, &w, ps, true));
         if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->pev_vox[npar][1], ps)); o->pev_vox_used[npar] = true; }
         ah.vox = true; ah.ptr = next_ptr; ah.n = next_n; ah.deskewed = next_deskew; ah.slot = next_slot; ah.par = npar; ah.vox_word = w;
     }

@@ -983,8 +983,6 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
     }
     FT_MARK(2);
     LIMU_TRACE(3);
-    // (a kernel launched behind this one with programmatic stream serialization -- the next scan's k_voxelize -- may start its own preamble now)
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // new_pose = T_icp * init_guess (:129); with an empty map the loop did not run and this is init_guess itself (:99-100). What follows is
     // CTA 0's: in a launch without the map-update epilogue (pipelined odometry) the next scan's k_voxelize sits behind this kernel in the
     // stream, so its tail is kept short: thread 0 takes the pose, warp 0 leaves the result block in pinned host memory, then thread 0

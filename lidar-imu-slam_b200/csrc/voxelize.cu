@@ -15,7 +15,6 @@
 // "First point per voxel wins, output in first-occurrence order" (icp.cpp:13-27 + the oracle's ordered map) becomes:
 // atomicMin of the input index per voxel, then a stable compaction over VX_BLOCK-point tiles.
 #include <stdlib.h>
-#include <string.h>
 
 #include <algorithm>
 
@@ -177,9 +176,6 @@ __device__ __forceinline__ void voxelize_body(const VoxelizeArgs &A) {
             if (sl != PEND_NONE) { A.keys2_prev[sl] = KEY_EMPTY; A.min2_prev[sl] = PEND_NONE; }
         }
     }
-    // A launch behind the previous scan's loop kernel is made with programmatic stream serialization: it may get here while that kernel's
-    // CTA 0 is still writing its twist and keypoints (the un-claim above touches nothing of it). Everything below needs the kernel to be over.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     // P1: frame[i] = deskewed / widened point (icp.cpp:36-47, deskew.cpp:18-26); stage-1 claim at 0.5 v
     {
         double tw[6];
@@ -373,7 +369,7 @@ static int64_t pow2_slots(int64_t n) { int64_t p = 1024; while (p < 2 * n) p <<=
 // Enqueue the fused kernel. raw/ts/twist are device pointers; outputs: frame (n x 3), down, src0, counts[0..1].
 int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int mode, int stride, const double *ts_dev, int deskew, const double *twist_host,
                     int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev, const double *twist_dev, DevStatus *own_status, int *status_used,
-                    cudaStream_t stream, bool beside, const unsigned int *twist_flag, unsigned int twist_seq, bool early) {
+                    cudaStream_t stream, bool beside, const unsigned int *twist_flag, unsigned int twist_seq) {
     if (!stream) stream = c->stream;
     if (n <= 0) {
         LIMU_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int), stream));
@@ -457,24 +453,6 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     if (status_used) *status_used = w;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->sm_count * (beside ? 1 : g_vx_blocks_per_sm));
     void *args[] = {&A};
-    // early: launched with programmatic stream serialization behind a kernel that releases its dependents before it ends (the loop kernel of
-    // the pipelined path); the kernel waits for that predecessor itself (griddepcontrol.wait). Falls back to a plain launch where the
-    // driver refuses the combination with a cooperative launch.
-    static int pdl_state = getenv("LIMU_NO_PDL") ? -1 : 0;   // 0 untried, 1 works, -1 refused / off
-    if (beside && early && pdl_state >= 0) {
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof cfg);
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(VX_BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
-        cudaLaunchAttribute at[2];
-        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
-        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = 2;
-        const cudaError_t e = cudaLaunchKernelExC(&cfg, (const void *)k_voxelize_lean, args);
-        if (e == cudaSuccess) { pdl_state = 1; LIMU_LAUNCHED(); return LIMU_OK; }
-        (void)cudaGetLastError();
-        if (pdl_state == 1) { set_error("cudaLaunchKernelExC failed: %s", cudaGetErrorString(e)); return LIMU_ERR_CUDA; }
-        pdl_state = -1;
-    }
     static const int beside_shape = getenv("LIMU_VX_BESIDE") ? atoi(getenv("LIMU_VX_BESIDE")) : 1;   // 1: lean (measured 2.6 % more scans/s than half, profiles/r2_voxelize_beside_ab.json), 0: half
     if (beside && beside_shape == 1) LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize_lean, dim3(grid), dim3(VX_BLOCK), args, 0, stream));
     else if (beside) LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize_half, dim3(grid), dim3(VX_BLOCK_BESIDE), args, 0, stream));
