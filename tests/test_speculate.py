@@ -1,6 +1,7 @@
-"""LIMU_OPT_SPECULATE (the next scan's deskew + downsampling launch enqueued behind the current scan's registration) and the error
-behaviour of limu_odom_register_*: results must not depend on hints / prefetches beyond rounding (the twist of a speculated scan is taken
-by the device's log: bar 1e-9, far inside the north-star tolerance of 1e-5 m / 1e-6 rad), whatever the caller does with the slots."""
+"""LIMU_OPT_SPECULATE (the pipelined path: the next scan's deskew + downsampling behind the current scan's Gauss-Newton loop in one stream,
+the map update beside it, the next scan's loop launched ahead of the caller) and the error behaviour of limu_odom_register_*: results must
+not depend on hints / prefetches beyond rounding (the twist of a scan prepared ahead is taken by the device's log: bar 1e-9, far inside the
+north-star tolerance of 1e-5 m / 1e-6 rad), whatever the caller does with the slots, the handle or the map between calls."""
 import numpy as np
 import pytest
 
@@ -235,6 +236,41 @@ def test_flush_and_plain_calls_between_pipelined_calls(ctx, pkg, scans):
     for pa, pb in zip(a, b):
         np.testing.assert_allclose(pa, pb, rtol=0, atol=1e-9)
     assert np.array_equal(da[0], db[0]) and np.array_equal(da[1], db[1])
+
+
+def test_two_pipelined_handles_on_one_context(ctx, pkg, scans):
+    """Two odometry handles of one context, calls interleaved: each has its own pipe stream, result block and barrier words, so their loop
+    kernels may overlap each other and the other handle's map update; results must be those of the handles run alone."""
+    import torch
+    seq_a, seq_b = scans[:9], [np.ascontiguousarray(s[::2]) for s in scans[1:10]]   # (different scans, different sizes)
+    dev_a = [torch.from_numpy(s).cuda() for s in seq_a]
+    dev_b = [torch.from_numpy(s).cuda() for s in seq_b]
+    torch.cuda.synchronize()
+
+    def alone(devs, seq):
+        k = ctx.KissICP(deskew=True, icp_max_iteration=60, speculate=False)
+        out = [(k.register_frame_dev(t.data_ptr(), len(s)).copy(), k.stats.icp.iterations) for t, s in zip(devs, seq)]
+        dump = k.local_map().dump()
+        k.close()
+        return out, dump
+
+    ref_a, ref_b = alone(dev_a, seq_a), alone(dev_b, seq_b)
+    ka = ctx.KissICP(deskew=True, icp_max_iteration=60, speculate=True)
+    kb = ctx.KissICP(deskew=True, icp_max_iteration=60, speculate=True)
+    got_a, got_b = [], []
+    for i in range(len(seq_a)):
+        if i + 1 < len(seq_a):
+            ka.hint_next_dev(dev_a[i + 1].data_ptr(), len(seq_a[i + 1]))
+            kb.hint_next_dev(dev_b[i + 1].data_ptr(), len(seq_b[i + 1]))
+        got_a.append((ka.register_frame_dev(dev_a[i].data_ptr(), len(seq_a[i])).copy(), ka.stats.icp.iterations))
+        got_b.append((kb.register_frame_dev(dev_b[i].data_ptr(), len(seq_b[i])).copy(), kb.stats.icp.iterations))
+    for (got, k), (ref, ref_dump) in (((got_a, ka), ref_a), ((got_b, kb), ref_b)):
+        for (gp, gi), (rp, ri) in zip(got, ref):
+            assert gi == ri
+            np.testing.assert_allclose(gp, rp, rtol=0, atol=1e-9)
+        dump = k.local_map().dump()
+        assert np.array_equal(dump[0], ref_dump[0]) and np.array_equal(dump[1], ref_dump[1])
+        k.close()
 
 
 @pytest.mark.parametrize("cap,voxel", [(10, 1.0), (20, 1.0), (3, 1.0), (10, 0.35)])
