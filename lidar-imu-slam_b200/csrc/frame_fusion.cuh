@@ -14,8 +14,7 @@ struct FrameFusion {
     unsigned long long upd_birth_base;
     double *twist_out;         // non-null: leave log(last_pose^-1 * new_pose) here for the NEXT scan's deskew (delta_pose, deskew.cpp:14)
     double last_pose[7];       // poses.back() before this scan
-    unsigned int *loop_flag;   // non-null: the kernel stores loop_seq here as soon as its Gauss-Newton loop is over (what k_gate waits for) ...
-    unsigned int *twist_flag;  // ... and here once twist_out is in memory
+    unsigned int *loop_flag;   // non-null: the kernel stores loop_seq here once its pose is in memory and its reads of the map are over (what k_gate waits for)
     unsigned int loop_seq;
     double *host_res;          // non-null (launches without the map update only): pinned host copy of res_block[0 .. res_doubles), word 31 <- loop_seq when it is complete
     const double *res_block;

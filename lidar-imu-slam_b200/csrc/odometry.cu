@@ -51,12 +51,12 @@ static double rotation_angle(const Pose &T) {
 // Device result block of one handle (per HANDLE: two handles of one context may interleave their scans). 28 ints, then 13 doubles:
 //   [0] n_down, [1] n_src0 of the scans with parity 0     [20] [21] the same for parity 1 (consecutive scans alternate: in the pipelined
 //   [2] n_keypoints (written by the loop kernel)                    path the next scan's k_voxelize runs while this scan's update reads its count)
-//   [3] the loop flag: sequence number of the last Gauss-Newton loop that is over (k_gate waits for it); [22] the same once its deskew twist is in memory
+//   [3] the loop flag: sequence number of the last Gauss-Newton loop that is over and has its pose in memory (k_gate waits for it)
 //   [4..7] / [24..27] status word of the map update of a parity-0 / parity-1 scan
 //   [8..19] three status words k_voxelize rotates through
 //   doubles 14..26: pose + loop statistics (out13).     ONE copy of RES_DOUBLES per scan.
 namespace {
-constexpr int RES_CNT1 = 20, RES_FLAG = 3, RES_TWIST_FLAG = 22, RES_BARRIER = 64 /* 8 words, zero at rest: grid barriers of the pipelined kernels */, RES_UPD_ST0 = 4, RES_UPD_ST1 = 24, RES_VOX_ST = 8, RES_OUT = 14, RES_DOUBLES = 27;
+constexpr int RES_CNT1 = 20, RES_FLAG = 3, RES_BARRIER = 64 /* 8 words, zero at rest: grid barriers of the pipelined kernels */, RES_UPD_ST0 = 4, RES_UPD_ST1 = 24, RES_VOX_ST = 8, RES_OUT = 14, RES_DOUBLES = 27;
 inline int *res_counts(int *cnt, int par) { return cnt + (par ? RES_CNT1 : 0); }
 inline limu::DevStatus *res_update_status(int *cnt, int par) { return reinterpret_cast<limu::DevStatus *>(cnt + (par ? RES_UPD_ST1 : RES_UPD_ST0)); }
 }  // namespace

@@ -33,11 +33,9 @@ struct VoxelizeScratch {
 // launch zeroes the next one late, so a word is clean when its launch starts without a memset per scan; *status_used = which word this launch
 // reports into. nullptr = the context's shared word.
 // stream: where to enqueue (nullptr = the context's); beside: half-size CTAs, one per SM, so that the launch fits next to another kernel's CTA.
-// twist_flag / twist_seq: the twist at twist_dev is valid once *twist_flag has reached twist_seq (the kernel waits for it before its first phase).
 int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int mode, int stride, const double *ts_dev, int deskew, const double *twist_host,
                     int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev, const double *twist_dev = nullptr,
-                    DevStatus *own_status = nullptr, int *status_used = nullptr, cudaStream_t stream = nullptr, bool beside = false,
-                    const unsigned int *twist_flag = nullptr, unsigned int twist_seq = 0);
+                    DevStatus *own_status = nullptr, int *status_used = nullptr, cudaStream_t stream = nullptr, bool beside = false);
 // One-thread kernel on stream s that returns once *flag has reached seq (voxelize.cu).
 int gate_device(cudaStream_t s, const unsigned int *flag, unsigned int seq);
 

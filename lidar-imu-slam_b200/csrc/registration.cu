@@ -85,8 +85,7 @@ struct IcpArgs {
     int icp_blocks;
     double *twist_out;          // see FrameFusion
     double last_pose[7];
-    unsigned int *loop_flag;    // non-null: set to loop_seq the moment the Gauss-Newton loop of this launch is over (what k_gate waits for) ...
-    unsigned int *twist_flag;   // ... and this one (release, GPU scope) once twist_out is in memory, a few microseconds later
+    unsigned int *loop_flag;    // non-null: set to loop_seq (release, GPU scope) once the pose of this launch is in memory and its reads of the map are over (what k_gate waits for)
     unsigned int loop_seq;
     double *host_res;           // non-null: pinned host memory; CTA 0 copies the handle's result block (res_block, res_doubles) there when the
     const double *res_block;    // launch is over and then stores loop_seq into word 31 (system scope): the host reads its pose without a copy
@@ -613,17 +612,13 @@ extern "C" int limu_debug_cta_marks(double out[640]) {
 // (two passes separated by a grid barrier) + eviction around the new position. Every CTA of the grid takes part (those that sat out the
 // Gauss-Newton loop join here); everybody reads the new pose that CTA 0 published in A.out. E: 7 doubles of shared memory.
 // The next scan deskews with delta_pose(poses[N-2], poses[N-1]) = log(last^-1 * new) (deskew.cpp:14): left on the device for a k_voxelize
-// that is already enqueued (it waits for twist_flag in front of its first phase). One thread (~3 us of scalar code).
+// that sits behind this kernel in the stream. One thread (~3 us of scalar code).
 __device__ __forceinline__ void publish_twist(const IcpArgs &A, const Pose &np) {
     if (A.twist_out) {
         double tw[6];
         se3_log(mul(inverse(Pose{A.last_pose[0], A.last_pose[1], A.last_pose[2], A.last_pose[3], A.last_pose[4], A.last_pose[5], A.last_pose[6]}), np), tw);
 #pragma unroll
         for (int k = 0; k < 6; ++k) A.twist_out[k] = tw[k];
-    }
-    if (A.twist_flag) {
-        __threadfence();
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.twist_flag), "r"(A.loop_seq) : "memory");
     }
 }
 
@@ -1411,7 +1406,7 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
         if (fuse->status) A.status = fuse->status;
         A.upd_capacity = (long long)m->capacity; A.upd_max_distance = m->max_distance;
         A.twist_out = fuse->twist_out;
-        A.loop_flag = fuse->loop_flag; A.twist_flag = fuse->twist_flag; A.loop_seq = fuse->loop_seq;
+        A.loop_flag = fuse->loop_flag; A.loop_seq = fuse->loop_seq;
         A.host_res = fuse->host_res; A.res_block = fuse->res_block; A.res_doubles = fuse->res_doubles;
         for (int k = 0; k < 7; ++k) A.last_pose[k] = fuse->last_pose[k];
     }

@@ -43,8 +43,6 @@ struct VoxelizeArgs {
     int mode, stride, deskew;
     double twist[6];            // by value, read when deskew != 0
     const double *twist_dev;    // non-null: the twist is left in device memory by the previous scan's loop kernel
-    const unsigned int *twist_flag;   // non-null: ... and is only there once this word has reached twist_seq
-    unsigned int twist_seq;
     int64_t n;
     double vs1, vs2;            // 0.5 v and 1.5 v (icp.cpp:129-130)
     double *frame, *down, *src0;
@@ -183,20 +181,6 @@ __device__ __forceinline__ void voxelize_body(const VoxelizeArgs &A) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) tw[k] = A.twist[k];
             if (A.twist_dev) {
-                if (A.twist_flag) {   // the twist is still being computed by the loop kernel that released this launch (a few microseconds at most)
-                    if (threadIdx.x == 0) {
-                        unsigned long long t0, t1;
-                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-                        for (;;) {
-                            unsigned int v;
-                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(A.twist_flag) : "memory");
-                            if ((int)(v - A.twist_seq) >= 0) break;
-                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                            if (t1 - t0 > 5000000000ull) break;   // (that kernel died: the host will see its error)
-                        }
-                    }
-                    __syncthreads();
-                }
 #pragma unroll
                 for (int k = 0; k < 6; ++k) tw[k] = __ldcg(A.twist_dev + k);
             }
@@ -369,7 +353,7 @@ static int64_t pow2_slots(int64_t n) { int64_t p = 1024; while (p < 2 * n) p <<=
 // Enqueue the fused kernel. raw/ts/twist are device pointers; outputs: frame (n x 3), down, src0, counts[0..1].
 int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int mode, int stride, const double *ts_dev, int deskew, const double *twist_host,
                     int64_t n, double v, double *frame_dev, double *down_dev, double *src0_dev, int *counts_dev, const double *twist_dev, DevStatus *own_status, int *status_used,
-                    cudaStream_t stream, bool beside, const unsigned int *twist_flag, unsigned int twist_seq) {
+                    cudaStream_t stream, bool beside) {
     if (!stream) stream = c->stream;
     if (n <= 0) {
         LIMU_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int), stream));
@@ -421,7 +405,6 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     A.raw = raw_dev; A.ts = ts_dev; A.mode = mode; A.stride = stride; A.deskew = deskew; A.n = n;
     for (int k = 0; k < 6; ++k) A.twist[k] = (deskew && twist_host) ? twist_host[k] : 0.0;
     A.twist_dev = deskew ? twist_dev : nullptr;
-    A.twist_flag = (deskew && twist_dev) ? twist_flag : nullptr; A.twist_seq = twist_seq;
     A.vs1 = v * 0.5; A.vs2 = v * 1.5;
     A.frame = frame_dev; A.down = down_dev; A.src0 = src0_dev;
     {
