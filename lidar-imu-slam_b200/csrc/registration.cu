@@ -339,11 +339,12 @@ __device__ __forceinline__ void contribution_pair(int l8, const V3 &s, const V3 
     }
 }
 
+struct PlaneMemo { int slot, planar; double n[3]; };   // slot < 0: nothing remembered
 // One pass over this warp's share of the queries with eight lanes per query (four queries per warp and step), see group8_closest.
 // On return lane L holds the warp total of sum index L>>1 (the layout of warp_reduce_scatter16) in `acc`.
 template <bool NN27, bool PLANE, int ROUNDS>
 __device__ __forceinline__ void icp_query_pass_grouped(const IcpArgs &A, const volatile double *Pv, const double *in, const unsigned short *qidx, int64_t n, int64_t gbase,
-                                                       int64_t gstride, int lane, double &acc, int &ncorr, int &ncand, int &nmiss, QueryMemo *memo) {
+                                                       int64_t gstride, int lane, double &acc, int &ncorr, int &ncand, int &nmiss, QueryMemo *memo, PlaneMemo *pmemo) {
     const int l8 = lane & 7;
     const unsigned gmask = 0xFFu << (lane & 24);
     const int64_t wfirst = gbase - (lane >> 3);   // first group of this warp: the four groups of a warp iterate together
@@ -375,7 +376,16 @@ __device__ __forceinline__ void icp_query_pass_grouped(const IcpArgs &A, const v
             const bool gate = lead && d2 < A.tau_sq;
             double nrm[3] = {0.0, 0.0, 0.0};
             bool planar = false;   // the group's leading lane fits the plane of the matched voxel (sequential sums: bit-identical to the oracle)
-            if (gate && my_rank >= 0) planar = voxel_normal(A.map, slot, meta_count(load_slot(slot_at(A.map, (unsigned int)slot)).y), nrm) != 0;
+            if (gate && my_rank >= 0) {
+                // the plane of a voxel does not change inside a launch: the fit (two passes over the voxel's points + 15 Jacobi rotations,
+                // the longest serial stretch of an iteration) is kept for the voxel this group's first query matched last time
+                if (q0 == wfirst && pmemo->slot == slot) {
+                    planar = pmemo->planar != 0; nrm[0] = pmemo->n[0]; nrm[1] = pmemo->n[1]; nrm[2] = pmemo->n[2];
+                } else {
+                    planar = voxel_normal(A.map, slot, meta_count(load_slot(slot_at(A.map, (unsigned int)slot)).y), nrm) != 0;
+                    if (q0 == wfirst) { pmemo->slot = slot; pmemo->planar = planar ? 1 : 0; pmemo->n[0] = nrm[0]; pmemo->n[1] = nrm[1]; pmemo->n[2] = nrm[2]; }
+                }
+            }
             double c[32];
             contribution_plane(c, s, tg, nrm, A.th, planar, count, lead && !own, lead);
             acc += warp_reduce_scatter32(c);
@@ -758,6 +768,8 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
     const int64_t wbase = ((int64_t)blockIdx.x * QW + warp) * 32, wstride = (int64_t)A.icp_blocks * QW * 32;
     int j = 0;
     int converged = 0;
+    PlaneMemo pmemo;  // (latency shape, point-to-plane variant: the plane fitted to the voxel this lane's query matched in the previous iteration)
+    pmemo.slot = -1; pmemo.planar = 0; pmemo.n[0] = pmemo.n[1] = pmemo.n[2] = 0.0;
     QueryMemo memo;   // (latency shape, reference rules: what this lane's group found for its query in the previous iteration)
     memo.own = -1; memo.kx = memo.ky = memo.kz = 0; memo.slot = -1; memo.count = 0;
     if (run_icp && icp_member) for (;;) {
@@ -783,9 +795,9 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
                     else if (A.map.cap <= 16) icp_query_pass_coop<2>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
                     else icp_query_pass_coop<3>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
                 } else if (SHAPE == 0) {                 // latency shape: eight lanes per query
-                    if (A.map.cap <= 8) icp_query_pass_grouped<NN27, PLANE, 1>(A, Pv, in, qi0, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss, &memo);
-                    else if (A.map.cap <= 16) icp_query_pass_grouped<NN27, PLANE, 2>(A, Pv, in, qi0, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss, &memo);
-                    else icp_query_pass_grouped<NN27, PLANE, 3>(A, Pv, in, qi0, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss, &memo);
+                    if (A.map.cap <= 8) icp_query_pass_grouped<NN27, PLANE, 1>(A, Pv, in, qi0, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss, &memo, &pmemo);
+                    else if (A.map.cap <= 16) icp_query_pass_grouped<NN27, PLANE, 2>(A, Pv, in, qi0, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss, &memo, &pmemo);
+                    else icp_query_pass_grouped<NN27, PLANE, 3>(A, Pv, in, qi0, n, wbase / 8 + (lane >> 3), wstride / 8, lane, acc, ncorr, ncand, nmiss, &memo, &pmemo);
                 } else {
                     icp_query_pass<NN27, PLANE>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
                 }
