@@ -231,10 +231,15 @@ int limu_odom_prefetch(limu_odom *o, const float *xyzt, int64_t n);
 /* register_frame(cloud, timestamps) on the reference's own layout (PCL point records + FP64 timestamps). */
 int limu_odom_register_cloud(limu_odom *o, const void *points, int32_t stride_bytes, const double *timestamps, int64_t n, double pose_out[7],
                              double *down_xyz, int64_t *n_down, double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats);
+/* limu_odom_prefetch for the reference's own layout: start uploading the NEXT cloud (records + FP64 timestamps, ideally pinned) while the
+ * current one is being registered; the following limu_odom_register_cloud call with the same pointers, stride and size finds it on the device
+ * (and, with LIMU_OPT_SPECULATE, already deskewed and downsampled). Both buffers must stay untouched until that call. */
+int limu_odom_prefetch_cloud(limu_odom *o, const void *points, int32_t stride_bytes, const double *timestamps, int64_t n);
 int limu_odom_register_frame_dev(limu_odom *o, const float *xyzt_dev, int64_t n, double pose_out[7], limu_frame_stats *stats);
 /* Replay hint: the scan that will be registered AFTER the next limu_odom_register_frame_dev call already sits in device memory at
  * xyzt_dev_next (and stays untouched until it has been registered); limu_odom_prefetch gives the host-pointer entry the same treatment.
- * With LIMU_OPT_SPECULATE on (the default) the packed-float4 entry points then PIPELINE consecutive scans (csrc/odometry.cu):
+ * With LIMU_OPT_SPECULATE on (the default) limu_odom_register_frame[_dev] and limu_odom_register_cloud then PIPELINE consecutive scans
+ * (csrc/odometry.cu):
  *   - the hinted scan's deskew + downsampling kernel is released the moment the current scan's Gauss-Newton loop has produced its pose
  *     (its deskew twist stays on the device) and runs beside the current scan's map update;
  *   - the hinted scan's IQR + Gauss-Newton loop is launched before the current call returns -- it only reads the map; the hinted scan's

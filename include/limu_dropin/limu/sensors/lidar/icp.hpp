@@ -70,6 +70,14 @@ namespace lidar
             src.resize(static_cast<size_t>(ns));
             return {down, src, limu_dropin::from_pose7(pose)};
         }
+        // Extension (no counterpart in the reference): a caller that already holds the NEXT cloud -- odom_run.cpp pops frames from a buffer --
+        // may announce it, so that its upload (and, by default, its deskew + downsampling) overlaps the registration of the current one.
+        // Both containers must stay untouched until they are passed to register_frame.
+        void prefetch(const utils::PointCloudXYZI &pointcloud, const std::vector<double> &timestamps)
+        {
+            const size_t n = pointcloud.points.size();
+            if (n) limu_dropin::check(limu_odom_prefetch_cloud(h_, &pointcloud.points[0], static_cast<int32_t>(sizeof(pointcloud.points[0])), timestamps.data(), static_cast<int64_t>(n)), "prefetch");
+        }
         // icp.cpp:58-86
         ReturnTuple register_frame(const utils::Vec3dVector &frame)
         {

@@ -182,6 +182,7 @@ def lib():
             "limu_odom_register_frame": [_vp, _fp, C.c_int64, _dp, _dp, _lp, _dp, _lp, C.POINTER(FrameStats)],
             "limu_odom_register_frame_dev": [_vp, _vp, C.c_int64, _dp, C.POINTER(FrameStats)],
             "limu_odom_prefetch": [_vp, _fp, C.c_int64],
+            "limu_odom_prefetch_cloud": [_vp, _vp, C.c_int32, _dp, C.c_int64],
             "limu_odom_hint_next_dev": [_vp, _vp, C.c_int64],
             "limu_odom_set_option": [_vp, C.c_int32, C.c_int64],
             "limu_odom_flush": [_vp],
@@ -643,6 +644,12 @@ class KissICP:
         """Start the H2D copy of the NEXT scan (pinned float32 [n,4]); pass the same array to the next register_frame."""
         assert isinstance(xyzt_f32, np.ndarray) and xyzt_f32.dtype == np.float32 and xyzt_f32.flags.c_contiguous
         _chk(lib().limu_odom_prefetch(self.h, xyzt_f32.ctypes.data_as(_fp), xyzt_f32.size // 4))
+
+    def prefetch_cloud(self, records, stride_bytes, timestamps):
+        """Start the H2D copy of the NEXT cloud (contiguous records + float64 timestamps, ideally pinned); pass the same arrays to the next register_cloud."""
+        assert isinstance(records, np.ndarray) and records.flags.c_contiguous
+        assert isinstance(timestamps, np.ndarray) and timestamps.dtype == np.float64 and timestamps.flags.c_contiguous
+        _chk(lib().limu_odom_prefetch_cloud(self.h, records.ctypes.data_as(_vp), int(stride_bytes), _d(timestamps), len(timestamps)))
 
     def register_cloud(self, records, stride_bytes, timestamps, copy=True):
         """register_frame(cloud, timestamps) on strided point records + float64 timestamps (the reference's layout).

@@ -79,6 +79,8 @@ struct limu_odom {
     int64_t nk_hint = 2048, nd_hint = 16384;   // keypoints / downsampled points of the previous scan (launch shapes; the kernels take any count)
     // limu_odom_prefetch: the next scan is uploaded on its own stream while the current one is being registered
     limu::DevBuf pf_buf[2];                 // two slots: the scan about to be registered and the one after it
+    limu::DevBuf pf_ts[2];                  // ... its FP64 timestamps when the slot holds point records (limu_odom_prefetch_cloud)
+    int pf_stride[2] = {0, 0};              // 0: packed float4 {x,y,z,t}; > 0: records this many bytes apart + pf_ts
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t pf_done[2] = {nullptr, nullptr};
     const void *pf_host[2] = {nullptr, nullptr};
@@ -117,6 +119,8 @@ struct limu_odom {
     int pending_update_par = -1;            // parity of a map update whose status word has not been read yet
     struct Ahead {                          // what is in flight for the scan the caller said comes next
         const void *ptr = nullptr;
+        const double *ts = nullptr;         // FP64 timestamps of a scan given as point records (stride > 0)
+        int stride = 0;
         int64_t n = 0;
         int deskewed = 0, slot = -1, par = 0, vox_word = 0;
         bool vox = false, loop = false;
@@ -416,9 +420,10 @@ static int odom_wait_loop(limu_odom *o, int par, unsigned long long out[32]) {
     }
 }
 
-// Pipelined path (see limu_odom): packed float4 scan in device memory. input_ready: event behind the scan's upload (nullptr: it is there).
-static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n, cudaEvent_t input_ready, double pose_out[7], double *down_xyz, int64_t *n_down,
-                                   double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
+// Pipelined path (see limu_odom): scan in device memory. input_ready: event behind the scan's upload (nullptr: it is there).
+// stride 0: packed float4 {x,y,z,t}; stride > 0: point records that many bytes apart + FP64 timestamps ts_dev (the reference's own layout).
+static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int stride, const double *ts_dev, int64_t n, cudaEvent_t input_ready, double pose_out[7],
+                                   double *down_xyz, int64_t *n_down, double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
     limu_ctx *c = o->ctx;
     LIMU_TRY(odom_pipe_init(o));
     cudaStream_t ps = o->pipe_stream;
@@ -426,7 +431,7 @@ static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n,
     const size_t NP = o->poses.size();
     const int deskewed = (o->cfg.deskew && NP > 2) ? 1 : 0;   // deskew gate (icp.cpp:40-46)
     const int par = o->par ^ 1, npar = par ^ 1;
-    const bool hit_vox = ah.vox && n > 0 && raw_dev == ah.ptr && n == ah.n && ah.deskewed == deskewed && ah.par == par;
+    const bool hit_vox = ah.vox && n > 0 && raw_dev == ah.ptr && n == ah.n && ah.stride == stride && (stride == 0 || ah.ts == ts_dev) && ah.deskewed == deskewed && ah.par == par;
     const bool hit_loop = hit_vox && ah.loop && ah.map_mutations == o->map->mutations;
     if (ah.vox && !hit_vox && ah.slot >= 0 && o->pf_buf[ah.slot].p == ah.ptr) {
         // the caller registered something else than the scan it had prefetched: that upload is stale, do not prepare it again
@@ -434,14 +439,18 @@ static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n,
     }
     // the scan after this one, if the caller told us where it is: a device-pointer hint, or the OLDEST upload limu_odom_prefetch has pending
     const void *next_ptr = nullptr;
+    const double *next_ts = nullptr;
     int64_t next_n = 0;
-    int next_slot = -1;
+    int next_slot = -1, next_stride = 0;
     cudaEvent_t next_ready = nullptr;
     if (o->hint_ptr) { next_ptr = o->hint_ptr; next_n = o->hint_n; }
     else {
         for (int sl = 0; sl < 2; ++sl)
             if (o->pf_host[sl] && o->pf_n[sl] > 0 && o->pf_buf[sl].p != raw_dev && (next_slot < 0 || o->pf_seq[sl] < o->pf_seq[next_slot])) next_slot = sl;
-        if (next_slot >= 0) { next_ptr = o->pf_buf[next_slot].p; next_n = o->pf_n[next_slot]; next_ready = o->pf_done[next_slot]; }
+        if (next_slot >= 0) {
+            next_ptr = o->pf_buf[next_slot].p; next_n = o->pf_n[next_slot]; next_ready = o->pf_done[next_slot];
+            next_stride = o->pf_stride[next_slot]; next_ts = next_stride ? o->pf_ts[next_slot].as<double>() : nullptr;
+        }
     }
     o->hint_ptr = nullptr; o->hint_n = 0;   // a hint is good for one call only
     int *cnt = o->res.as<int>();
@@ -461,7 +470,7 @@ static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n,
         LIMU_TRY(o->src0[par].reserve(nb, ps));
         if (input_ready) LIMU_CUDA_TRY(cudaStreamWaitEvent(ps, input_ready, 0));
         if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->pev_vox[par][0], ps));
-        LIMU_TRY(voxelize_device(c, o->vx, raw_dev, 0, 0, nullptr, deskewed, twist, n, v, o->frame.as<double>(), o->down[par].as<double>(), o->src0[par].as<double>(),
+        LIMU_TRY(voxelize_device(c, o->vx, raw_dev, stride ? 1 : 0, stride, ts_dev, deskewed, twist, n, v, o->frame.as<double>(), o->down[par].as<double>(), o->src0[par].as<double>(),
                                  res_counts(cnt, par), nullptr, vox_status, &vox_word, ps, false));
         if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->pev_vox[par][1], ps)); o->pev_vox_used[par] = true; }
     }
@@ -512,10 +521,10 @@ static int odom_register_pipelined(limu_odom *o, const void *raw_dev, int64_t n,
         if (next_ready) LIMU_CUDA_TRY(cudaStreamWaitEvent(ps, next_ready, 0));
         int w = 0;
         if (c->profiling) LIMU_CUDA_TRY(cudaEventRecord(o->pev_vox[npar][0], ps));
-        LIMU_TRY(voxelize_device(c, o->vx, next_ptr, 0, 0, nullptr, next_deskew, nullptr, next_n, v, o->frame.as<double>(), o->down[npar].as<double>(), o->src0[npar].as<double>(),
+        LIMU_TRY(voxelize_device(c, o->vx, next_ptr, next_stride ? 1 : 0, next_stride, next_ts, next_deskew, nullptr, next_n, v, o->frame.as<double>(), o->down[npar].as<double>(), o->src0[npar].as<double>(),
                                  res_counts(cnt, npar), next_deskew ? o->twist_next.as<double>() : nullptr, vox_status, &w, ps, true));
         if (c->profiling) { LIMU_CUDA_TRY(cudaEventRecord(o->pev_vox[npar][1], ps)); o->pev_vox_used[npar] = true; }
-        ah.vox = true; ah.ptr = next_ptr; ah.n = next_n; ah.deskewed = next_deskew; ah.slot = next_slot; ah.par = npar; ah.vox_word = w;
+        ah.vox = true; ah.ptr = next_ptr; ah.ts = next_ts; ah.stride = next_stride; ah.n = next_n; ah.deskewed = next_deskew; ah.slot = next_slot; ah.par = npar; ah.vox_word = w;
     }
     // 5. the one wait of the call: this scan's pose
     unsigned long long hw[32];
@@ -623,7 +632,7 @@ void limu_odom_destroy(limu_odom *o) {
     o->map->readers_done = nullptr;
     limu_map_destroy(o->map);
     if (o->copy_stream) { cudaStreamSynchronize(o->copy_stream); cudaStreamDestroy(o->copy_stream); cudaEventDestroy(o->pf_done[0]); cudaEventDestroy(o->pf_done[1]); }
-    DevBuf *bufs[] = {&o->res, &o->pf_buf[0], &o->pf_buf[1], &o->d2, &o->raw, &o->ts, &o->frame, &o->down[0], &o->down[1], &o->src0[0], &o->src0[1], &o->src[0], &o->src[1],
+    DevBuf *bufs[] = {&o->res, &o->pf_buf[0], &o->pf_buf[1], &o->pf_ts[0], &o->pf_ts[1], &o->d2, &o->raw, &o->ts, &o->frame, &o->down[0], &o->down[1], &o->src0[0], &o->src0[1], &o->src[0], &o->src[1],
                       &o->work, &o->world, &o->partials, &o->twist_next};
     for (auto *b : bufs) b->release();
     o->vx.release();
@@ -641,43 +650,42 @@ void limu_odom_destroy(limu_odom *o) {
     delete o;
 }
 
-int limu_odom_register_frame(limu_odom *o, const float *xyzt, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down,
-                             double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
-    LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyzt), "limu_odom_register_frame: bad arguments");
-    LIMU_TRY(bind(o->ctx));
+// A scan in host memory -> device memory, on the way noting whether limu_odom_prefetch* has uploaded it (and whether its k_voxelize has
+// even run ahead). stride 0: packed float4; > 0: records + FP64 timestamps. Returns the device pointers and the event to wait for.
+static int odom_host_scan(limu_odom *o, const void *pts, int stride, const double *ts_host, int64_t n, const void **dev, const double **ts_dev, cudaEvent_t *ready) {
+    limu_ctx *c = o->ctx;
+    const size_t bytes = (size_t)n * (stride ? stride : 16);
     int hit = -1;
-    for (int s = 0; s < 2; ++s) if (n > 0 && o->pf_host[s] == xyzt && o->pf_n[s] == n) hit = s;
-    const void *dev = nullptr;
-    cudaEvent_t ready = nullptr;   // what the scan's first kernel has to wait for when it is not launched on the context's stream
-    if (hit >= 0 && o->speculate && o->ahead.vox && o->ahead.ptr == o->pf_buf[hit].p && o->ahead.n == n) {
+    for (int s = 0; s < 2; ++s) if (n > 0 && o->pf_host[s] == pts && o->pf_n[s] == n && o->pf_stride[s] == stride) hit = s;
+    *ready = nullptr;
+    if (hit >= 0 && o->speculate && o->ahead.vox && o->ahead.ptr == o->pf_buf[hit].p && o->ahead.n == n && o->ahead.stride == stride) {
         // uploaded ahead of time AND already through k_voxelize (behind the previous scan's loop): register it where it lies
         o->pf_host[hit] = nullptr; o->pf_n[hit] = -1;
-        dev = o->pf_buf[hit].p;
-    } else if (hit >= 0) {   // uploaded ahead of time by limu_odom_prefetch
-        LIMU_CUDA_TRY(cudaStreamWaitEvent(o->ctx->stream, o->pf_done[hit], 0));
-        if (o->pipe_stream) LIMU_CUDA_TRY(cudaStreamSynchronize(o->pipe_stream));   // (rare: the buffers change hands while a kernel prepared for another scan may read one)
-        std::swap(o->raw, o->pf_buf[hit]);
-        o->pf_host[hit] = nullptr; o->pf_n[hit] = -1;
-        dev = o->raw.p;
-        ready = o->pf_done[hit];
-    } else {
-        if (o->speculate) LIMU_TRY(odom_pipe_init(o));
-        if (o->pipe_stream) LIMU_CUDA_TRY(cudaStreamSynchronize(o->pipe_stream));   // (o->raw may still be read by a kernel of the previous scan on the pipe stream)
-        LIMU_TRY(stage_in(o->ctx, o->raw, xyzt, (size_t)n * 16));
-        dev = o->raw.p;
-        if (o->speculate) { LIMU_CUDA_TRY(cudaEventRecord(o->input_ready, o->ctx->stream)); ready = o->input_ready; }
+        *dev = o->pf_buf[hit].p; *ts_dev = stride ? o->pf_ts[hit].as<double>() : nullptr;
+        return LIMU_OK;
     }
-    if (o->speculate) return odom_register_pipelined(o, dev, n, ready, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
-    return odom_register_device(o, dev, 0, 0, nullptr, n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+    if (o->speculate) LIMU_TRY(odom_pipe_init(o));
+    if (o->pipe_stream) LIMU_CUDA_TRY(cudaStreamSynchronize(o->pipe_stream));   // (o->raw may still be read by a kernel prepared for another scan)
+    if (hit >= 0) {   // uploaded ahead of time: the buffers change hands
+        LIMU_CUDA_TRY(cudaStreamWaitEvent(c->stream, o->pf_done[hit], 0));
+        std::swap(o->raw, o->pf_buf[hit]);
+        if (stride) std::swap(o->ts, o->pf_ts[hit]);
+        o->pf_host[hit] = nullptr; o->pf_n[hit] = -1;
+        *ready = o->pf_done[hit];
+    } else {
+        LIMU_TRY(stage_in(c, o->raw, pts, bytes));
+        if (stride) LIMU_TRY(stage_in(c, o->ts, ts_host, (size_t)n * 8));
+        if (o->speculate) { LIMU_CUDA_TRY(cudaEventRecord(o->input_ready, c->stream)); *ready = o->input_ready; }
+    }
+    *dev = o->raw.p; *ts_dev = stride ? o->ts.as<double>() : nullptr;
+    return LIMU_OK;
 }
 
-int limu_odom_prefetch(limu_odom *o, const float *xyzt, int64_t n) {
-    LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyzt), "limu_odom_prefetch: bad arguments");
-    LIMU_TRY(bind(o->ctx));
+// Start the upload of a scan that will be registered later (two slots; the OLDEST pending upload gives way).
+static int odom_prefetch_scan(limu_odom *o, const void *pts, int stride, const double *ts_host, int64_t n) {
     if (n == 0) return LIMU_OK;
     LIMU_TRY(odom_side_stream(o));
-    for (int s = 0; s < 2; ++s) if (o->pf_host[s] == xyzt && o->pf_n[s] == n) return LIMU_OK;   // already in flight
-    // a free slot, else the OLDEST pending upload is given up (its scan was evidently never registered)
+    for (int s = 0; s < 2; ++s) if (o->pf_host[s] == pts && o->pf_n[s] == n && o->pf_stride[s] == stride) return LIMU_OK;   // already in flight
     int s = o->pf_host[0] == nullptr ? 0 : (o->pf_host[1] == nullptr ? 1 : (o->pf_seq[0] < o->pf_seq[1] ? 0 : 1));
     if (o->ahead.vox && o->pf_buf[s].p == o->ahead.ptr) {
         // the k_voxelize that ran ahead on the scan in this slot may still be reading it: let it finish, and forget what was prepared (the
@@ -686,29 +694,59 @@ int limu_odom_prefetch(limu_odom *o, const float *xyzt, int64_t n) {
         LIMU_TRY(odom_drop_ahead(o, false));
     }
     o->pf_host[s] = nullptr; o->pf_n[s] = -1;
-    if (o->pf_buf[s].bytes < (size_t)n * 16) {   // growing may free a buffer the copy stream still writes: drain it first
+    const size_t bytes = (size_t)n * (stride ? stride : 16);
+    if (o->pf_buf[s].bytes < bytes || (stride && o->pf_ts[s].bytes < (size_t)n * 8)) {   // growing may free a buffer the copy stream still writes: drain it first
         LIMU_CUDA_TRY(cudaStreamSynchronize(o->copy_stream));
-        LIMU_TRY(o->pf_buf[s].reserve((size_t)n * 16, o->copy_stream));
+        LIMU_TRY(o->pf_buf[s].reserve(bytes, o->copy_stream));
+        if (stride) LIMU_TRY(o->pf_ts[s].reserve((size_t)n * 8, o->copy_stream));
     }
-    LIMU_CUDA_TRY(cudaMemcpyAsync(o->pf_buf[s].p, xyzt, (size_t)n * 16, cudaMemcpyHostToDevice, o->copy_stream));
+    LIMU_CUDA_TRY(cudaMemcpyAsync(o->pf_buf[s].p, pts, bytes, cudaMemcpyHostToDevice, o->copy_stream));
+    if (stride) LIMU_CUDA_TRY(cudaMemcpyAsync(o->pf_ts[s].p, ts_host, (size_t)n * 8, cudaMemcpyHostToDevice, o->copy_stream));
     LIMU_CUDA_TRY(cudaEventRecord(o->pf_done[s], o->copy_stream));
-    o->pf_host[s] = xyzt; o->pf_n[s] = n; o->pf_seq[s] = ++o->pf_counter;
+    o->pf_host[s] = pts; o->pf_n[s] = n; o->pf_stride[s] = stride; o->pf_seq[s] = ++o->pf_counter;
     return LIMU_OK;
+}
+
+int limu_odom_register_frame(limu_odom *o, const float *xyzt, int64_t n, double pose_out[7], double *down_xyz, int64_t *n_down,
+                             double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
+    LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyzt), "limu_odom_register_frame: bad arguments");
+    LIMU_TRY(bind(o->ctx));
+    const void *dev = nullptr;
+    const double *ts_dev = nullptr;
+    cudaEvent_t ready = nullptr;   // what the scan's first kernel has to wait for when it is not launched on the context's stream
+    LIMU_TRY(odom_host_scan(o, xyzt, 0, nullptr, n, &dev, &ts_dev, &ready));
+    if (o->speculate) return odom_register_pipelined(o, dev, 0, nullptr, n, ready, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+    return odom_register_device(o, dev, 0, 0, nullptr, n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+}
+
+int limu_odom_prefetch(limu_odom *o, const float *xyzt, int64_t n) {
+    LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyzt), "limu_odom_prefetch: bad arguments");
+    LIMU_TRY(bind(o->ctx));
+    return odom_prefetch_scan(o, xyzt, 0, nullptr, n);
 }
 
 int limu_odom_register_cloud(limu_odom *o, const void *points, int32_t stride_bytes, const double *timestamps, int64_t n, double pose_out[7],
                              double *down_xyz, int64_t *n_down, double *keypoints_xyz, int64_t *n_keypoints, limu_frame_stats *stats) {
     LIMU_REQUIRE(o && n >= 0 && stride_bytes >= 12 && stride_bytes % 4 == 0 && (n == 0 || (points && timestamps)), "limu_odom_register_cloud: bad arguments");
     LIMU_TRY(bind(o->ctx));
-    LIMU_TRY(stage_in(o->ctx, o->raw, points, (size_t)n * stride_bytes));
-    LIMU_TRY(stage_in(o->ctx, o->ts, timestamps, (size_t)n * 8));
-    return odom_register_device(o, o->raw.p, 1, stride_bytes, o->ts.as<double>(), n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+    const void *dev = nullptr;
+    const double *ts_dev = nullptr;
+    cudaEvent_t ready = nullptr;
+    LIMU_TRY(odom_host_scan(o, points, stride_bytes, timestamps, n, &dev, &ts_dev, &ready));
+    if (o->speculate) return odom_register_pipelined(o, dev, stride_bytes, ts_dev, n, ready, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+    return odom_register_device(o, dev, 1, stride_bytes, ts_dev, n, pose_out, down_xyz, n_down, keypoints_xyz, n_keypoints, stats);
+}
+
+int limu_odom_prefetch_cloud(limu_odom *o, const void *points, int32_t stride_bytes, const double *timestamps, int64_t n) {
+    LIMU_REQUIRE(o && n >= 0 && stride_bytes >= 12 && stride_bytes % 4 == 0 && (n == 0 || (points && timestamps)), "limu_odom_prefetch_cloud: bad arguments");
+    LIMU_TRY(bind(o->ctx));
+    return odom_prefetch_scan(o, points, stride_bytes, timestamps, n);
 }
 
 int limu_odom_register_frame_dev(limu_odom *o, const float *xyzt_dev, int64_t n, double pose_out[7], limu_frame_stats *stats) {
     LIMU_REQUIRE(o && n >= 0 && (n == 0 || xyzt_dev), "limu_odom_register_frame_dev: bad arguments");
     LIMU_TRY(bind(o->ctx));
-    if (o->speculate) return odom_register_pipelined(o, xyzt_dev, n, nullptr, pose_out, nullptr, nullptr, nullptr, nullptr, stats);
+    if (o->speculate) return odom_register_pipelined(o, xyzt_dev, 0, nullptr, n, nullptr, pose_out, nullptr, nullptr, nullptr, nullptr, stats);
     return odom_register_device(o, xyzt_dev, 0, 0, nullptr, n, pose_out, nullptr, nullptr, nullptr, nullptr, stats);
 }
 

@@ -238,6 +238,38 @@ def test_flush_and_plain_calls_between_pipelined_calls(ctx, pkg, scans):
     assert np.array_equal(da[0], db[0]) and np.array_equal(da[1], db[1])
 
 
+def test_prefetched_clouds_match_plain(ctx, pkg, scans):
+    """limu_odom_prefetch_cloud + limu_odom_register_cloud (point records + FP64 timestamps, the reference's own layout) through the pipelined
+    path against the plain path; one prefetch is not followed (the caller registers another cloud instead)."""
+    seq = scans[:8]
+    recs, tss = [], []
+    for s_ in seq:
+        r = pkg.PinnedArray((len(s_), 12), np.float32); r.array[...] = 0; r.array[:, :3] = s_[:, :3]
+        t = pkg.PinnedArray((len(s_),), np.float64); t.array[...] = s_[:, 3]
+        recs.append(r); tss.append(t)
+    order = [0, 1, 2, 3, 5, 6, 7]          # cloud 4 is prefetched and then skipped
+
+    def run(spec):
+        k = ctx.KissICP(deskew=True, icp_max_iteration=60, speculate=spec)
+        out, hits = [], 0
+        for j, i in enumerate(order):
+            if spec and i + 1 < len(seq):
+                k.prefetch_cloud(recs[i + 1].array, 48, tss[i + 1].array)
+            d, sr, p = k.register_cloud(recs[i].array, 48, tss[i].array)
+            hits += k.stats.reserved0
+            out.append((d, sr, p.copy(), k.stats.icp.iterations))
+        dump = k.local_map().dump()
+        k.close()
+        return out, dump, hits
+
+    (a, da, _), (b, db, hits) = run(False), run(True)
+    assert hits == len(order) - 2                      # every cloud but the first and the one after the skipped prefetch ran ahead
+    close_enough(b, a)
+    assert np.array_equal(da[0], db[0]) and np.array_equal(da[1], db[1])
+    for x in recs + tss:
+        x.free()
+
+
 def test_two_pipelined_handles_on_one_context(ctx, pkg, scans):
     """Two odometry handles of one context, calls interleaved: each has its own pipe stream, result block and barrier words, so their loop
     kernels may overlap each other and the other handle's map update; results must be those of the handles run alone."""
