@@ -43,6 +43,9 @@ UNIT = "scans/s"
 WORKLOADS = {
     "c2": dict(scene=dict(), elev=(-25.0, 2.0), beams=64, azimuth_steps=2000,
                text="configs[1]: synthetic {beams}-beam LiDAR, {points} pts/scan, loop r=30 m at {step} m/scan, voxel {voxel} m, cap {cap}, deskew on"),
+    "c3": dict(scene=dict(street=True, n_boxes=60, n_cyl=30), elev=(-25.0, 15.0), beams=128, azimuth_steps=4000,
+               text="configs[2]: synthetic {beams}-beam LiDAR in an urban canyon (two facade rows + ground + clutter), {points} pts/scan, loop r=30 m at {step} m/scan, "
+                    "voxel {voxel} m, cap {cap}, deskew on, local map of ~45 M points resident in HBM"),
     "tracking": dict(scene=dict(n_boxes=150, n_cyl=60), elev=(0.5, 30.0), beams=64, azimuth_steps=3000,
                      text="tracking regime: {beams}-beam LiDAR looking up (+0.5..+30 deg, no ground returns), 150 boxes + 60 cylinders, {points} pts/scan, "
                           "loop r=30 m at {step} m/scan, voxel {voxel} m, cap {cap}, deskew on"),
@@ -245,7 +248,7 @@ def cpu_reference_api(icp_mode=0, mt=True):
 def time_cpu(args, scans, warmup, max_steps, budget_s, mt=True, keep=False):
     """The reference's own register_frame on the host cores over a bounded prefix of the same sequence."""
     api, kind = cpu_reference_api(args.icp_mode, mt)
-    k = api.Kiss(voxel_size=args.voxel, max_range=100.0, cap=args.cap, deskew=True, icp_max_iteration=args.max_iter)
+    k = api.Kiss(voxel_size=args.voxel, max_range=getattr(args, "max_range", 100.0), cap=args.cap, deskew=True, icp_max_iteration=args.max_iter)
     if args.icp_mode:
         k.set_mode(args.icp_mode)
     xyz = [np.ascontiguousarray(s[:, :3]) for s in scans]
@@ -297,7 +300,7 @@ def parity_record(args, scans, gpu_poses, gpu_frames, cpu):
         return None
     dp = np.abs(np.asarray(gpu_poses[:n]) - cpu["poses"][:n])
     port = oracle.load_port()
-    k = port.Kiss(voxel_size=args.voxel, max_range=100.0, cap=args.cap, deskew=True, icp_max_iteration=args.max_iter)
+    k = port.Kiss(voxel_size=args.voxel, max_range=getattr(args, "max_range", 100.0), cap=args.cap, deskew=True, icp_max_iteration=args.max_iter)
     its = []
     for i in range(n):
         k.register_cloud(np.ascontiguousarray(scans[i][:, :3]), scans[i][:, 3].astype(np.float64))
@@ -337,16 +340,18 @@ class Bench:
         self.dist.all_gather(out, t)
         return [o.tolist() for o in out]
 
-    def new_odom(self, icp_mode=None, speculate=None):
-        a = self.args
+    def new_odom(self, icp_mode=None, speculate=None, args=None, map_capacity_voxels=0):
+        a = args or self.args
         spec = (not a.no_speculate) if speculate is None else speculate
-        return self.ctx.KissICP(voxel_size=a.voxel, max_range=100.0, cap=a.cap, deskew=True, icp_max_iteration=a.max_iter,
-                                icp_mode=a.icp_mode if icp_mode is None else icp_mode, speculate=spec)
+        return self.ctx.KissICP(voxel_size=a.voxel, max_range=getattr(a, "max_range", 100.0), cap=a.cap, deskew=True, icp_max_iteration=a.max_iter,
+                                icp_mode=a.icp_mode if icp_mode is None else icp_mode, speculate=spec, map_capacity_voxels=map_capacity_voxels)
 
-    def window(self, step, n_warm, n_timed, odom):
+    def window(self, step, n_warm, n_timed, odom, after_warmup=None):
         """W untimed + K timed calls of step(odom, i, last_of_phase). Returns this window's per-rank (time, wall, dev, closing barrier) rows."""
         for i in range(n_warm):
             step(odom, i, i == n_warm - 1)
+        if after_warmup:
+            after_warmup()
         self.barrier()
         e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
         if self.sampler:
@@ -365,14 +370,14 @@ class Bench:
         wall, dev = t1 - t0, e0.elapsed_time(e1) / 1e3
         return self.gather([max(wall, dev), wall, dev, t2 - t1])
 
-    def run_windows(self, make_step, n_warm, n_timed, repeats, icp_mode=None, keep_last=False):
+    def run_windows(self, make_step, n_warm, n_timed, repeats, icp_mode=None, keep_last=False, after_warmup=None):
         """`repeats` windows on fresh handles. Returns (summary, last odom or None)."""
         rows, odom = [], None
         for r in range(repeats):
             if odom is not None:
                 odom.close()
             odom = self.new_odom(icp_mode)
-            rows.append(self.window(make_step(), n_warm, n_timed, odom))
+            rows.append(self.window(make_step(), n_warm, n_timed, odom, after_warmup))
         if not keep_last:
             odom.close()
             odom = None
@@ -433,6 +438,91 @@ def kernel_mode_record(torch, pkg, ctx, queries=(524288, 4194304), voxels=2.5e6,
             "bytes_formula": "SURVEY 8d K4: per query per iteration 24 + 16 + 24*k_bar + f_miss*27*16 B (measured k_bar, f_miss); frac_with_source_writeback adds the 24 B/query source update",
             "timing": "CUDA events on the library stream around limu_icp_dev (one cooperative launch = the whole loop + one 104-byte D2H), median of 5 after 2 warm-ups; queries and map >> L2",
             "cases": out}
+
+
+def c3_record(b, args, device, W3=3, K3=12, R3=3, bg_points=46_000_000):
+    """configs[2] / SURVEY C3 in PIPELINE mode: the whole register_frame path on 512 000-point scans (128 beams x 4000 azimuth steps, urban
+    canyon), voxel 0.5 m, cap 20, against a local map of ~45 M points resident in HBM. The map's bulk is a background slab (800 x 800 x 4
+    voxels at z = 150..152 m, inserted through limu_map_insert_dev BEHIND warm-up scan 0, outside the timed region): it makes the table and
+    the block array large (lookups of the scene's own voxels are scattered over ~4 GB) and is walked by every eviction sweep, but no query
+    comes within 100 m of it, so the poses are those of the same sequence without it -- which is what the CPU arm (the reference's
+    register_frame, no background) checks. max_range (= the map's max_distance) is 1000 m on both arms so the slab is never evicted."""
+    import copy
+    torch, ctx = b.torch, b.ctx
+    a3 = copy.copy(args)
+    a3.points, a3.beams, a3.azimuth_steps, a3.voxel, a3.cap, a3.max_range, a3.icp_mode = 512000, 128, 4000, 0.5, 20, 1000.0, 0
+    n3 = a3.points
+    scans = make_scans(a3, W3 + K3, 42, device, workload="c3")
+    devs = [torch.from_numpy(s).cuda() for s in scans]
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    bg = torch.empty((bg_points, 3), dtype=torch.float64, device="cuda")
+    bg[:, :2] = (torch.rand((bg_points, 2), generator=gen, device="cuda", dtype=torch.float64) - 0.5) * 400.0
+    bg[:, 2] = 150.0 + torch.rand(bg_points, generator=gen, device="cuda", dtype=torch.float64) * 2.0
+    torch.cuda.synchronize()
+
+    def prefill(o):
+        m = o.local_map()
+        for lo in range(0, bg_points, 1 << 20):
+            m.insert_points_dev(bg[lo:lo + (1 << 20)].data_ptr(), min(1 << 20, bg_points - lo))
+
+    def mk(rec):
+        def step(o, i, last):
+            if i > 0 and not last and i + 1 < len(devs):
+                o.hint_next_dev(devs[i + 1].data_ptr(), n3)
+            o.register_frame_dev(devs[i].data_ptr(), n3)
+            st = o.stats
+            rec.append((st.n_keypoints, st.icp.iterations, st.icp.mean_candidates, st.icp.miss_fraction, st.n_down))
+            if i == 0:
+                prefill(o)
+        return step
+
+    rows, frames, odom = [], [], None
+    for r in range(R3):
+        if odom is not None:
+            odom.close()
+        frames = []
+        odom = b.new_odom(args=a3, map_capacity_voxels=3_400_000)
+        rows.append(b.window(mk(frames), W3, K3, odom)[0])
+    poses = odom.poses()
+    nv, npts = odom.local_map().size()
+    odom.close()
+    # stage split (and the k_voxelize roofline at this size) from one more window with the stage events on
+    ctx.set_profiling(True)
+    odom = b.new_odom(args=a3, map_capacity_voxels=3_400_000)
+    pfr = []
+    b.window(mk(pfr), W3, K3, odom, after_warmup=lambda: ctx.set_profiling(True))
+    prof, nfr = ctx.profile()
+    ctx.set_profiling(False)
+    odom.close()
+    del bg
+    torch.cuda.empty_cache()
+    times = sorted(max(rw[0], rw[2]) for rw in rows)
+    sec = times[len(times) // 2]
+    f = np.array(frames[W3:], dtype=np.float64)
+    peak, peak_src = measured_peak()
+    nd, nk = float(f[:, 4].mean()), float(f[:, 0].mean())
+    vox_bytes = 40.0 * n3 + 40.0 * (n3 + nd) + 24.0 * (nd + nk * 1.05)      # SURVEY 8d: K1*N + K2*(N + N_d), K2 = 40 B/point + 24 B/winner
+    vox_ms = prof["downsample"] / max(nfr, 1)
+    loop_bytes = float(np.mean([k4_bytes(x[0], x[1], x[2], x[3]) for x in pfr[W3:]]))
+    loop_ms = prof["icp"] / max(nfr, 1)
+    cpu = time_cpu(a3, scans, W3, K3, min(args.cpu_seconds, 12.0), mt=True, keep=True)
+    return {
+        "workload": workload_text(a3, "c3"), "value": K3 / sec, "unit": UNIT, "mpoints_per_s": K3 / sec * n3 / 1e6, "ms_per_step": 1e3 * sec / K3,
+        "windows_scans_per_s": [round(K3 / t, 1) for t in times], "steps": K3, "warmup": W3,
+        "iterations_per_scan": float(f[:, 1].mean()), "keypoints_per_scan": nk, "downsampled_per_scan": nd, "k_bar": float(f[:, 2].mean()), "f_miss": float(f[:, 3].mean()),
+        "map_voxels": int(nv), "map_points": int(npts), "map_block_bytes": int(nv) * 512,
+        "stage_ms_per_step": {k: v / max(nfr, 1) for k, v in prof.items()},
+        "roofline_k_voxelize": {"bound": "hbm", "achieved": vox_bytes / (vox_ms * 1e-3) / 1e9 if vox_ms > 0 else 0.0, "peak": peak, "unit": "GB/s",
+                                "frac": vox_bytes / (vox_ms * 1e-3) / 1e9 / peak if vox_ms > 0 else 0.0, "algorithmic_bytes_per_launch": vox_bytes,
+                                "avg_launch_ms": vox_ms, "bytes_formula": "SURVEY 8d: K1*N + K2*(N + N_d) = 40 N + 40 (N + N_d) + 24 B per stage winner"},
+        "roofline_loop_kernel": {"bound": "hbm", "achieved": loop_bytes / (loop_ms * 1e-3) / 1e9 if loop_ms > 0 else 0.0, "peak": peak, "unit": "GB/s",
+                                 "frac": loop_bytes / (loop_ms * 1e-3) / 1e9 / peak if loop_ms > 0 else 0.0, "algorithmic_bytes_per_launch": loop_bytes,
+                                 "avg_launch_ms": loop_ms, "note": "pipeline mode: the queries are the ~N_k keypoints, not the 512 k points (kernel mode: roofline_kernel_mode)"},
+        "cpu_baseline": {"value": cpu["done"] / cpu["dt"] if cpu["done"] else None, "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"],
+                         "sample": f"first {cpu['done']} timed scans of the same sequence (no background slab: it cannot be matched)"},
+        "parity": parity_record(a3, scans, poses, frames, cpu),
+        "timing": "windows on fresh handles (background re-inserted each time, behind warm-up scan 0); per window max(host wall, CUDA events); median of the windows",
+    }
 
 
 def sharded_record(b, voxels=2.5e6, fill=20.0, nq=4194304, iters=20, reps=3):
@@ -611,7 +701,8 @@ def main():
     # -- one more window with per-stage event timing switched on (NOT part of `value`): the frame kernel's own duration for the roofline
     ctx.set_profiling(True)
     prof_frames = []
-    b.run_windows(dev_step_factory(dev_scans, prof_frames), W, K, 1)
+    # (the sums restart behind the warm-up scans: a fresh handle's first k_voxelize has its scratch allocated between the two events)
+    b.run_windows(dev_step_factory(dev_scans, prof_frames), W, K, 1, after_warmup=lambda: ctx.set_profiling(True))
     prof, nframes = ctx.profile()
     ctx.set_profiling(False)
     clocks = b.sampler.stop()
@@ -620,8 +711,8 @@ def main():
     fr = np.array(gpu_frames[W:], dtype=np.float64)
     iters_total = float(fr[:, 1].sum())
     rank_work = b.gather([float(fr[:, 1].mean()), float(fr[:, 1].max()), float(fr[:, 0].mean())])   # equal work per GPU? (weak scaling)
-    # bytes per launch over ALL profiled frames (warm-up included: set_profiling covers the whole window)
-    pf = prof_frames if prof_frames else gpu_frames
+    # bytes per launch over the profiled frames (the K timed scans of that window)
+    pf = prof_frames[W:] if prof_frames else gpu_frames[W:]
     # LIMU_OPT_SPECULATE on (pipelined path): the loop kernel carries IQR + Gauss-Newton loop only, the map update is a launch of its own
     pipelined = not args.no_speculate
     if pipelined:
@@ -756,6 +847,10 @@ def main():
     if extras and n_gpus == 1 and rank == 0:
         torch.cuda.empty_cache()
         line["roofline_kernel_mode"] = kernel_mode_record(torch, pkg, ctx)
+        try:
+            line["workload_c3"] = c3_record(b, args, f"cuda:{local_rank}")
+        except Exception as e:   # noqa: BLE001
+            line["workload_c3"] = {"error": repr(e)}
 
     if rank == 0 and n_gpus == 1:
         cpu = time_cpu(args, scans, W, K, args.cpu_seconds, mt=True, keep=True)

@@ -87,6 +87,10 @@ struct DevBuf {
 };
 
 // Device-side status word shared by kernels of one context.
+// SMs a cooperative launch of the pipelined path leaves free for k_gate threads (voxelize.cu) that may be resident while its CTAs are placed (one gate per
+// context stream; a few more for other contexts on the same GPU)
+constexpr int GATE_SLACK_SMS = 4;
+
 struct DevStatus {
     int key_range;    // some voxel index fell outside the packed key range
     int table_full;   // an insert probe ran through the whole table

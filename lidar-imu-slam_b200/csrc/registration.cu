@@ -231,7 +231,7 @@ __device__ __forceinline__ void coop_scan(const MapView &m, const V3 &s, int slo
 #pragma unroll
             for (int k = 0; k < ROUNDS; ++k) {   // out-of-range ranks re-read rank l8 (always inside the block) and are ignored below
                 const int r = l8 + 8 * k, rr = r < qcount ? r : l8;
-                x[k] = __ldg(bx + rr); y[k] = __ldg(by + rr); z[k] = __ldg(bz + rr);
+                x[k] = *(bx + rr); y[k] = *(by + rr); z[k] = *(bz + rr);
             }
 #pragma unroll
             for (int k = 0; k < ROUNDS; ++k) {
@@ -241,7 +241,7 @@ __device__ __forceinline__ void coop_scan(const MapView &m, const V3 &s, int slo
             }
         } else {
             for (int r = l8; r < qcount; r += 8) {
-                const double d = sqnorm3(qx - __ldg(bx + r), qy - __ldg(by + r), qz - __ldg(bz + r));
+                const double d = sqnorm3(qx - *(bx + r), qy - *(by + r), qz - *(bz + r));
                 if (d < bd) { bd = d; br = r; }
             }
         }
@@ -297,7 +297,7 @@ __device__ __forceinline__ void icp_query_pass(const IcpArgs &A, const volatile 
         V3 tg{0.0, 0.0, 0.0};   // nothing found -> (0,0,0), range-tested like a real point (voxel_hash_map.cpp:98-99,118-124)
         if (my_rank >= 0) {
             const double *bx = voxel_rows(A.map, (unsigned int)slot);
-            tg = V3{__ldg(bx + my_rank), __ldg(bx + A.map.capp + my_rank), __ldg(bx + 2 * A.map.capp + my_rank)};
+            tg = V3{*(bx + my_rank), *(bx + A.map.capp + my_rank), *(bx + 2 * A.map.capp + my_rank)};
         }
         const double d2 = my_rank >= 0 ? my_d2 : sqnorm3(tg.x - s.x, tg.y - s.y, tg.z - s.z);   // (found - point).squaredNorm() :120
         const bool gate = on && d2 < A.tau_sq;
@@ -1380,7 +1380,12 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
     // queries per CTA: 7 query warps (the eighth warp is the solver warp); eight lanes per query in the latency shape, one in the bandwidth shape
     const bool lanes8 = grouped;
     const int64_t want = std::max<int64_t>(1, div_up(std::max<int64_t>(n_hint, 1) * (lanes8 ? 8 : 1), ICP_BLOCK - 32));
-    int grid = (int)std::min<int64_t>(want, (int64_t)c->sm_count * (grouped ? 1 : std::min(g_icp_blocks_per_sm, LIMU_BW_CTAS)));
+    // Pipelined path: a k_gate thread may already sit on an SM, waiting for THIS launch, when its CTAs are placed -- and an SM that runs a
+    // kernel without shared memory is not handed a CTA that needs a different shared-memory carve-out until it has drained. A cooperative
+    // grid that needs every SM of the GPU would then wait for the gate and the gate for the grid (until the gate's 5 s give-up; seen with
+    // ~7 k keypoints per scan = 148 CTAs, configs[2]). Such launches leave GATE_SLACK_SMS SMs free.
+    const int sms = (fuse && fuse->loop_flag) ? std::max(1, c->sm_count - GATE_SLACK_SMS) : c->sm_count;
+    int grid = (int)std::min<int64_t>(want, (int64_t)sms * (grouped ? 1 : std::min(g_icp_blocks_per_sm, LIMU_BW_CTAS)));
     grid = (int)std::min<int64_t>(grid, (int64_t)partial_rows);
     const int icp_blocks = grid;   // the Gauss-Newton loop is latency bound at keypoint counts: it runs on the leading CTAs only
     if (fuse && fuse->upd_down) grid = std::max(grid, c->sm_count);   // the insert and the eviction sweep want one CTA per SM

@@ -332,6 +332,11 @@ static __global__ void k_gate(const unsigned int *flag, unsigned int seq) {
     LIMU_TRACE(30);
 }
 int gate_device(cudaStream_t s, const unsigned int *flag, unsigned int seq) {
+    static bool hinted = false;
+    if (!hinted) {   // ask for the largest shared-memory carve-out: the SM the gate sits on can then take CTAs of the kernels it waits for without draining first
+        if (cudaFuncSetAttribute(k_gate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) (void)cudaGetLastError();
+        hinted = true;
+    }
     k_gate<<<1, 1, 0, s>>>(flag, seq);
     LIMU_LAUNCHED();
     return LIMU_OK;
@@ -434,7 +439,9 @@ int voxelize_device(limu_ctx *c, VoxelizeScratch &sc, const void *raw_dev, int m
     A.st = own_status ? own_status + w : c->d_status;
     A.st_next = own_status ? own_status + sc.st_word : nullptr;
     if (status_used) *status_used = w;
-    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->sm_count * (beside ? 1 : g_vx_blocks_per_sm));
+    // beside the map update (pipelined path) the grid leaves GATE_SLACK_SMS SMs free: the NEXT scan's k_gate may become resident before every
+    // CTA of this cooperative launch has been placed, and this launch sits in front of the loop that gate waits for (see icp_device)
+    const int grid = (int)std::min<int64_t>(ntiles, beside ? (int64_t)std::max(1, c->sm_count - GATE_SLACK_SMS) : (int64_t)c->sm_count * g_vx_blocks_per_sm);
     void *args[] = {&A};
     static const int beside_shape = getenv("LIMU_VX_BESIDE") ? atoi(getenv("LIMU_VX_BESIDE")) : 1;   // 1: lean (measured 2.6 % more scans/s than half, profiles/r2_voxelize_beside_ab.json), 0: half
     if (beside && beside_shape == 1) LIMU_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_voxelize_lean, dim3(grid), dim3(VX_BLOCK), args, 0, stream));

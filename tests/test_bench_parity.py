@@ -160,3 +160,63 @@ def test_one_iteration_at_512k_queries_matches_oracle(ctx, pkg, bench):
     os_, ot, oi = om.correspondences(qs, tau, with_index=True)
     assert np.array_equal(gi, oi) and np.array_equal(gs, os_) and np.array_equal(gt, ot)
     gm.close()
+
+
+def test_c3_pipeline_sequence_at_512k_with_resident_background_matches_reference(ctx, pkg, bench):
+    """configs[2] in PIPELINE mode (bench.py's `workload_c3` record): 512 000-point scans (128 x 4000, urban canyon), voxel 0.5 m, cap 20,
+    deskew on, through the pipelined register_frame path while the local map also holds a large background slab (here 6 M points at
+    z = 150..152 m, inserted behind scan 0 through limu_map_insert_dev). No query comes near the slab, so the compiled reference and the C
+    port -- run WITHOUT it -- must give the same n_down / n_keypoints / iterations and poses within the north-star tolerance
+    (icp.cpp:49-86, registration.cpp:94-130, voxel_hash_map.cpp:64-171; max_range = 1000 m on every arm so nothing is evicted)."""
+    import copy
+    import oracle
+    import torch
+    a3 = copy.copy(bench_args(bench))
+    a3.points, a3.beams, a3.azimuth_steps, a3.voxel, a3.cap, a3.max_range = 512000, 128, 4000, 0.5, 20, 1000.0
+    n = 7
+    scans = bench.make_scans(a3, n, 42, "cuda:0", workload="c3")
+    assert all(s.shape == (512000, 4) for s in scans)
+    refs = [("port", oracle.load_port())]
+    if oracle.have_ref():
+        import os
+        refs.append(("ref", oracle.load_ref(mt=os.path.exists(oracle.REF_MT_SO))))
+    cpu = {}
+    for name, api in refs:
+        k = api.Kiss(voxel_size=0.5, max_range=1000.0, cap=20, deskew=True, icp_max_iteration=500)
+        rows = []
+        for s in scans:
+            d, sr, p = k.register_cloud(np.ascontiguousarray(s[:, :3]), s[:, 3].astype(np.float64))
+            rows.append((len(d), len(sr), k.last_iterations(), p.copy()))
+        cpu[name] = rows
+    staged = [torch.from_numpy(s).cuda() for s in scans]
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    nbg = 6_000_000
+    bg = torch.empty((nbg, 3), dtype=torch.float64, device="cuda")
+    bg[:, :2] = (torch.rand((nbg, 2), generator=gen, device="cuda", dtype=torch.float64) - 0.5) * 150.0
+    bg[:, 2] = 150.0 + torch.rand(nbg, generator=gen, device="cuda", dtype=torch.float64) * 2.0
+    torch.cuda.synchronize()
+    for spec in (True, False):
+        g = ctx.KissICP(voxel_size=0.5, max_range=1000.0, cap=20, deskew=True, icp_max_iteration=500, speculate=spec, map_capacity_voxels=600_000)
+        got = []
+        for i, t in enumerate(staged):
+            if spec and i > 0 and i + 1 < len(staged):
+                g.hint_next_dev(staged[i + 1].data_ptr(), 512000)
+            p = g.register_frame_dev(t.data_ptr(), 512000)
+            got.append((g.stats.n_down, g.stats.n_keypoints, g.stats.icp.iterations, p.copy()))
+            if i == 0:
+                m = g.local_map()
+                for lo in range(0, nbg, 1 << 20):
+                    m.insert_points_dev(bg[lo:lo + (1 << 20)].data_ptr(), min(1 << 20, nbg - lo))
+        nv, npts = g.local_map().size()
+        g.close()
+        assert npts > 4_000_000 and nv > 300_000                  # the slab is resident (360 k voxels of it) next to the scene's own voxels
+        gp = np.array([r[3] for r in got])
+        for name, rows in cpu.items():
+            rp = np.array([r[3] for r in rows])
+            assert [r[0] for r in got] == [r[0] for r in rows], f"n_down vs {name}"
+            assert [r[1] for r in got] == [r[1] for r in rows], f"n_keypoints vs {name}"
+            if name == "port":
+                assert [r[2] for r in got] == [r[2] for r in rows], "Gauss-Newton iterations per scan"
+            assert np.abs(gp[:, 4:] - rp[:, 4:]).max() < 1e-5 and np.abs(gp[:, :4] - rp[:, :4]).max() < 1e-6, f"absolute pose vs {name}"
+            du_g, du_r = rel_update(pkg, gp), rel_update(pkg, rp)
+            assert np.abs(du_g[:, 4:] - du_r[:, 4:]).max() < 1e-5 and np.abs(du_g[:, :4] - du_r[:, :4]).max() < 1e-6, f"per-update pose vs {name}"

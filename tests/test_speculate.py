@@ -354,3 +354,35 @@ def test_cluster_loop_degenerate_inputs(ctx, pkg):
         assert len(d) == 2 and 1 <= len(sr) <= 2
         assert k.local_map().size()[0] == 2
         k.close()
+
+
+@pytest.mark.parametrize("voxel,beams,az", [(0.3, 64, 2000), (0.1, 64, 2000)])
+def test_pipelined_matches_plain_when_the_loop_needs_every_sm(ctx, pkg, voxel, beams, az):
+    """Small voxels = many keypoints: at ~5 k keypoints the latency shape of the loop kernel asks for one CTA on EVERY SM, above 16 384 the
+    bandwidth shape for several per SM, and the scan's k_voxelize for one 1024-thread CTA per SM. A cooperative grid that needs the whole GPU
+    must not wait for the SM a k_gate thread of the same pipeline sits on (that was a 5-second stall with a wrong map state behind it at
+    configs[2]'s size): the pipelined path leaves GATE_SLACK_SMS SMs free. Hinted replay against the plain path, timing checked."""
+    import time
+    import torch
+    from importlib import import_module
+    synth = import_module("limu_b200.synth")
+    scene = synth.Scene(seed=5, n_boxes=60, n_cyl=30)
+    traj = synth.loop_trajectory(9, radius=30.0, step=0.5)
+    seq = [synth.cast_scan(scene, traj[i], traj[i + 1], beams=beams, azimuth_steps=az, seed=900 + i, device="cuda:0") for i in range(8)]
+    ref, _ = plain_run(ctx, seq, voxel_size=voxel, cap=20)
+    nk = max(len(r[1]) for r in ref)
+    assert nk > (16384 if voxel < 0.2 else 4200), nk          # the regime this test is about
+    staged = [torch.from_numpy(s).cuda() for s in seq]
+    torch.cuda.synchronize()
+    k = ctx.KissICP(deskew=True, icp_max_iteration=60, speculate=True, voxel_size=voxel, cap=20)
+    worst = 0.0
+    for i, t in enumerate(staged):
+        if i + 1 < len(staged):
+            k.hint_next_dev(staged[i + 1].data_ptr(), len(seq[i + 1]))
+        t0 = time.perf_counter()
+        p = k.register_frame_dev(t.data_ptr(), len(seq[i]))
+        worst = max(worst, time.perf_counter() - t0) if i > 0 else worst
+        np.testing.assert_allclose(p, ref[i][2], rtol=0, atol=1e-9)
+        assert k.stats.icp.iterations == ref[i][3] and k.stats.n_down == len(ref[i][0]) and k.stats.n_keypoints == len(ref[i][1])
+    k.close()
+    assert worst < 1.0, f"a call took {worst:.2f} s: the gate and a full-GPU cooperative launch waited for each other"
