@@ -652,7 +652,7 @@ __device__ __forceinline__ void frame_update_epilogue(const IcpArgs &A, GridSync
             A.upd_world[3 * i] = w.x; A.upd_world[3 * i + 1] = w.y; A.upd_world[3 * i + 2] = w.z;
             A.upd_pslot[i] = slot = insert_claim_one(A.map, w, (unsigned int)i, A.upd_birth_base, A.status, &claimed);
         }
-        insert_account(claimed, slot, A.upd_counters, A.map.live);
+        insert_account(claimed, slot, A.upd_counters, A.map);
     }
     gs.sync();
     FT_MARK(3);
@@ -664,17 +664,20 @@ __device__ __forceinline__ void frame_update_epilogue(const IcpArgs &A, GridSync
     LIMU_TRACE(22);
     // eviction (remove_points_from_far, voxel_hash_map.cpp:146-171) over the dense list of voxels (V entries, 4 B + one 16 B slot each)
     // instead of the C table slots: a scan that evicts nothing used to read the whole 16 MB slot array.
+    // The voxel test needs the key only: the sweep streams the list's key words (coalesced) and touches the block of a far voxel alone --
+    // a map of 2.6 M voxels spread over a 4 GB block array took 110 us per scan to visit header by header.
     const int64_t used = (int64_t)__ldcg(A.upd_counters + 3);
+    const int ovx = vox_index(A.map, np.tx), ovy = vox_index(A.map, np.ty), ovz = vox_index(A.map, np.tz);
     for (int64_t i0 = gtid; i0 < used; i0 += 4 * gthreads) {
-        unsigned int sl[4];
+        unsigned long long key[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int64_t idx = i0 + (int64_t)u * gthreads;
-            sl[u] = idx < used ? __ldcg(A.map.live + idx) : PEND_NONE;
+            key[u] = idx < used ? __ldcg(A.map.live_key + idx) : KEY_TOMB;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            if (sl[u] != PEND_NONE) remove_far_one(A.map, (int64_t)sl[u], np.tx, np.ty, np.tz, A.upd_max_distance, A.upd_counters);
+            remove_far_entry(A.map, i0 + (int64_t)u * gthreads, key[u], ovx, ovy, ovz, np.tx, np.ty, np.tz, A.upd_max_distance, A.upd_counters);
     }
 }
 
@@ -1041,7 +1044,9 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
 // local_map.update(down_sampled, new_pose) as a launch of its own (pipelined odometry: the Gauss-Newton loop of a scan is launched before the
 // caller has confirmed that scan, its map update only afterwards). Two CTAs' worth of registers at most, so that it fits beside the next
 // scan's k_voxelize.
-static __global__ void __launch_bounds__(ICP_BLOCK, 2) k_frame_update(const IcpArgs A) {
+// at most 64 registers (256 threads x 4): the CTA has to fit into the 16 K registers k_voxelize_lean (1024 x 48) leaves on the SM -- at 72 the two kernels took
+// turns on every SM instead of running beside each other (-10 % scans/s)
+static __global__ void __launch_bounds__(ICP_BLOCK, 4) k_frame_update(const IcpArgs A) {
     __shared__ double E[7];
     GridSync gs{A.barrier, 0u, gridDim.x};
     LIMU_TRACE(20);

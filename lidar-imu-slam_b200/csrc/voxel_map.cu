@@ -27,7 +27,7 @@ static __global__ void __launch_bounds__(256) k_insert_claim(MapView m, const do
     bool claimed = false;
     unsigned int slot = PEND_NONE;
     if (i < n) pslot[i] = slot = insert_claim_one(m, V3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, (unsigned int)i, birth_base, st, &claimed);
-    insert_account(claimed, slot, counters, m.live);
+    insert_account(claimed, slot, counters, m);
 }
 
 static __global__ void __launch_bounds__(256) k_insert_place(MapView m, const double *__restrict__ xyz, int64_t n_max, const int *n_dev,
@@ -41,8 +41,10 @@ static __global__ void __launch_bounds__(256) k_insert_place(MapView m, const do
 // Walks the dense live list (one entry per voxel ever created since the last rebuild) instead of the C table slots.
 static __global__ void __launch_bounds__(256) k_remove_far(MapView m, const double *__restrict__ origin, double max_distance, unsigned long long *counters) {
     const int64_t used = (int64_t)counters[3];
+    const double ox = origin[0], oy = origin[1], oz = origin[2];
+    const int ovx = vox_index(m, ox), ovy = vox_index(m, oy), ovz = vox_index(m, oz);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < used; i += (int64_t)gridDim.x * blockDim.x)
-        remove_far_one(m, (int64_t)m.live[i], origin[0], origin[1], origin[2], max_distance, counters);
+        remove_far_entry(m, i, __ldcg(m.live_key + i), ovx, ovy, ovz, ox, oy, oz, max_distance, counters);
 }
 
 // Move every live voxel of `old` into the (cleared) table `nw`.
@@ -57,7 +59,11 @@ static __global__ void __launch_bounds__(256) k_rehash(MapView old, int64_t oldC
         if (cur == KEY_EMPTY) break;
         t = (t + 1) & nw.mask;
     }
-    nw.live[atomicAdd(&new_counters[3], 1ull)] = t;   // the rebuilt list holds live voxels only
+    {
+        const unsigned long long at = atomicAdd(&new_counters[3], 1ull);   // the rebuilt list holds live voxels only
+        nw.live[at] = t;
+        nw.live_key[at] = key;
+    }
     const unsigned long long meta = slot_at(old, (unsigned int)s)->meta;
     const int count = meta_count(meta);
     slot_at(nw, t)->meta = meta;
@@ -160,7 +166,7 @@ int map_alloc(limu_map *m, int64_t C) {
     limu_ctx *c = m->ctx;
     m->blk.release(); m->pend.release(); m->live.release();
     LIMU_TRY(m->blk.reserve((size_t)C * limu::block_stride(m->cap) * 8));
-    LIMU_TRY(m->live.reserve((size_t)C * 4));
+    LIMU_TRY(m->live.reserve((size_t)C * 12));   // C slot indices (4 B) followed by their C keys (8 B)
     LIMU_TRY(m->pend.reserve((size_t)C * m->cap * 4));
     m->capacity = C;
     const int blocks = std::min<int64_t>(div_up(C, 256), (int64_t)c->sm_count * 32);
@@ -180,6 +186,7 @@ limu::MapView limu_map::view() const {
     v.blk = blk.as<double>();
     v.pend = pend.as<unsigned int>();
     v.live = live.as<unsigned int>();
+    v.live_key = reinterpret_cast<unsigned long long *>(v.live + capacity);   // (capacity is a power of two >= 1024: 8-byte aligned)
     v.mask = (unsigned int)(capacity - 1);
     int lg = 0;
     while ((int64_t(1) << lg) < capacity) ++lg;

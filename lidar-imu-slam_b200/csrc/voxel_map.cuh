@@ -41,6 +41,8 @@ struct MapView {
     double *blk;         // C blocks of `stride` doubles: 2 header words (Slot) + 3 rows of capp doubles + padding
     unsigned int *pend;
     unsigned int *live;  // dense list of used slots (live + erased), counters[3] entries
+    unsigned long long *live_key;   // the packed voxel key of live[i] (KEY_TOMB once the voxel has been erased): the eviction sweep streams these 8-byte words
+                                    // instead of one scattered block header per voxel
     unsigned int mask;   // C - 1
     int shift;           // 64 - log2(C)
     int cap;
@@ -658,7 +660,7 @@ __device__ __forceinline__ unsigned int insert_claim_one(const MapView &m, const
 }
 // warp-aggregated occupancy accounting + append of the new voxels' slots to the dense live list (call with the whole
 // warp converged; `slot` is what insert_claim_one returned)
-__device__ __forceinline__ void insert_account(bool claimed, unsigned int slot, unsigned long long *counters, unsigned int *live) {
+__device__ __forceinline__ void insert_account(bool claimed, unsigned int slot, unsigned long long *counters, const MapView &m) {
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, claimed);
     if (!bal) return;   // warp-uniform
     const int lane = threadIdx.x & 31;
@@ -668,7 +670,11 @@ __device__ __forceinline__ void insert_account(bool claimed, unsigned int slot, 
         base = atomicAdd(&counters[3], (unsigned long long)__popc(bal));   // used slots (live + tombstones) = length of the live list
     }
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (claimed) live[base + (unsigned long long)__popc(bal & ((1u << lane) - 1u))] = slot;
+    if (claimed) {
+        const unsigned long long at = base + (unsigned long long)__popc(bal & ((1u << lane) - 1u));
+        m.live[at] = slot;
+        m.live_key[at] = __ldcg(&slot_at(m, slot)->key);   // (this thread's own compare-and-swap put it there)
+    }
 }
 // Pass 2: the point looks for its own index in its voxel's pending list; position r IS its storage rank (the list
 // started at the old count). Winners store their coordinates and clear the entry.
@@ -688,15 +694,20 @@ __device__ __forceinline__ void insert_place_one(const MapView &m, const V3 &p, 
 // remove_points_from_far (voxel_hash_map.cpp:146-171) as it executes under null locks, for slot s: voxels whose INDEX
 // distance^2 to the origin voxel exceeds max_distance^2 (units as written, :148,:160) drop their points farther than
 // max_distance metres from origin, order preserved (voxel_block.cpp:107-118); empty voxels are erased (tombstoned).
-__device__ __forceinline__ void remove_far_one(const MapView &m, int64_t s, double ox, double oy, double oz, double max_distance, unsigned long long *counters) {
-    const unsigned long long key = slot_at(m, (unsigned int)s)->key;
-    if (key >= KEY_TOMB) return;
-    const double max_sq = max_distance * max_distance;
+// the voxel test of :160 on a packed key (origin voxel ovx/ovy/ovz)
+__device__ __forceinline__ bool voxel_is_far(unsigned long long key, int ovx, int ovy, int ovz, double max_sq) {
     int x, y, z;
     unpack_key(key, x, y, z);
-    const long long dx = x - vox_index(m, ox), dy = y - vox_index(m, oy), dz = z - vox_index(m, oz);
+    const long long dx = x - ovx, dy = y - ovy, dz = z - ovz;
     const long long d2 = dx * dx + dy * dy + dz * dz;
-    if (!((double)d2 > max_sq)) return;
+    return (double)d2 > max_sq;
+}
+// returns true when the voxel was erased
+__device__ __forceinline__ bool remove_far_one(const MapView &m, int64_t s, double ox, double oy, double oz, double max_distance, unsigned long long *counters) {
+    const unsigned long long key = slot_at(m, (unsigned int)s)->key;
+    if (key >= KEY_TOMB) return false;
+    const double max_sq = max_distance * max_distance;
+    if (!voxel_is_far(key, vox_index(m, ox), vox_index(m, oy), vox_index(m, oz), max_sq)) return false;
     double *px = voxel_rows(m, (unsigned int)s), *py = px + m.capp, *pz = py + m.capp;
     const unsigned long long meta = slot_at(m, (unsigned int)s)->meta;
     const int count = meta_count(meta);
@@ -714,7 +725,15 @@ __device__ __forceinline__ void remove_far_one(const MapView &m, int64_t s, doub
         slot_at(m, (unsigned int)s)->meta = META_NONE;
         atomicAdd(&counters[0], ~0ull);  // --live
         atomicAdd(&counters[1], 1ull);   // ++tombstones
+        return true;
     }
+    return false;
+}
+// entry i of the dense live list: its key decides (one coalesced 8-byte word); only a far voxel's block is touched
+__device__ __forceinline__ void remove_far_entry(const MapView &m, int64_t i, unsigned long long key, int ovx, int ovy, int ovz, double ox, double oy, double oz,
+                                                 double max_distance, unsigned long long *counters) {
+    if (key >= KEY_TOMB || !voxel_is_far(key, ovx, ovy, ovz, max_distance * max_distance)) return;
+    if (remove_far_one(m, (int64_t)__ldcg(m.live + i), ox, oy, oz, max_distance, counters)) m.live_key[i] = KEY_TOMB;
 }
 
 }  // namespace limu

@@ -112,3 +112,22 @@ def test_config_defaults_are_the_reference_launch_defaults(pkg):
             cfg.initial_threshold, cfg.estimation_threshold) == (1.0, 100.0, 10, 0, 0.1, 500, 0, 2.0, 1e-4)
     lc = pkg.lidar_config()
     assert (lc.min_range, lc.max_range, lc.min_angle, lc.max_angle, lc.frame_rate, lc.num_scan_lines, lc.frame_split_num) == (5.0, 100.0, 0.0, 360.0, 10.0, 16, 1)
+
+
+def test_kernels_that_run_beside_each_other_share_one_register_file(pkg):
+    """Pipelined path: the map update of scan X (k_frame_update, 256 threads) runs BESIDE the next scan's k_voxelize_lean (1024 threads) on
+    the same SMs. Both CTAs must fit into the 65 536 registers of an SM together, or the two kernels take turns (measured: -10 % scans/s when
+    k_frame_update grew from 60 to 72 registers). Read from the ptxas logs the build leaves under lidar-imu-slam_b200/build/."""
+    regs = {}
+    for log in ("registration.ptxas.log", "voxelize.ptxas.log"):
+        path = os.path.join(ROOT, "lidar-imu-slam_b200", "build", log)
+        if not os.path.exists(path):
+            pytest.skip("no ptxas log (library not built here)")
+        text = open(path).read()
+        for m in re.finditer(r"Compiling entry function '(\w+)'.*?Used (\d+) registers", text, re.S):
+            regs[m.group(1)] = int(m.group(2))
+    upd = [v for k, v in regs.items() if "k_frame_update" in k]
+    vox = [v for k, v in regs.items() if "k_voxelize_lean" in k]
+    assert upd and vox, sorted(regs)
+    alloc = lambda r, threads: ((r + 7) // 8 * 8) * threads      # registers are allocated in units of 8 per thread
+    assert alloc(upd[0], 256) + alloc(vox[0], 1024) <= 65536, (upd, vox)

@@ -386,3 +386,47 @@ def test_pipelined_matches_plain_when_the_loop_needs_every_sm(ctx, pkg, voxel, b
         assert k.stats.icp.iterations == ref[i][3] and k.stats.n_down == len(ref[i][0]) and k.stats.n_keypoints == len(ref[i][1])
     k.close()
     assert worst < 1.0, f"a call took {worst:.2f} s: the gate and a full-GPU cooperative launch waited for each other"
+
+
+def test_ragged_sequence_through_the_pipelined_path(ctx, pkg):
+    """Scan sizes that change from call to call -- 1 point to 4 M points, so every per-scan buffer is re-allocated while earlier launches are
+    in flight and the launch shapes change between scans (one tile, many tiles per CTA, latency and bandwidth shape of the loop) -- hinted
+    replay on the pipelined path against the plain path (counts and iterations equal, poses 1e-9) and the C port (north-star tolerance)."""
+    import torch
+    import oracle
+    from importlib import import_module
+    synth = import_module("limu_b200.synth")
+    scene = synth.Scene(seed=9, n_boxes=40, n_cyl=20)
+    sizes = [30000, 120000, 300000, 8000, 4194304, 1000, 1048576, 1, 57, 2, 40000]
+    n_pinned = 7   # a one-point scan makes the normal equations singular: there the compiled reference and its C port already disagree with each
+                   # other (LDLT of a rank-3 matrix), so from that scan on only the pipelined path against the plain path is checked
+    traj = synth.loop_trajectory(len(sizes) + 1, radius=30.0, step=0.4)
+    rng = np.random.default_rng(4)
+    seq = []
+    for i, n in enumerate(sizes):
+        beams, az = (512, 11059) if n > 2_000_000 else (256, 5530) if n > 100_000 else (64, 2000)   # (rays that hit nothing are dropped: cast more than needed)
+        s = synth.cast_scan(scene, traj[i], traj[i + 1], beams=beams, azimuth_steps=az, seed=700 + i, device="cuda:0")
+        assert len(s) >= n, (len(s), n)
+        keep = np.sort(rng.choice(len(s), size=n, replace=False)) if n < len(s) else np.arange(n)
+        seq.append(np.ascontiguousarray(s[keep]))
+    ref, ref_dump = plain_run(ctx, seq, cap=10)
+    port = oracle.load_port()
+    kc = port.Kiss(voxel_size=1.0, max_range=100.0, cap=10, deskew=True, icp_max_iteration=60)
+    staged = [torch.from_numpy(s).cuda() for s in seq]
+    torch.cuda.synchronize()
+    k = ctx.KissICP(deskew=True, icp_max_iteration=60, speculate=True, cap=10)
+    for i, t in enumerate(staged):
+        if i + 1 < len(staged):
+            k.hint_next_dev(staged[i + 1].data_ptr(), len(seq[i + 1]))
+        p = k.register_frame_dev(t.data_ptr(), len(seq[i]))
+        np.testing.assert_allclose(p, ref[i][2], rtol=0, atol=1e-9, err_msg=f"scan {i} ({sizes[i]} points)")
+        assert k.stats.icp.iterations == ref[i][3] and k.stats.n_down == len(ref[i][0]) and k.stats.n_keypoints == len(ref[i][1]), (i, sizes[i])
+        if i >= n_pinned:
+            continue
+        dc, sc, pc = kc.register_cloud(np.ascontiguousarray(seq[i][:, :3]), seq[i][:, 3].astype(np.float64))
+        assert (len(dc), len(sc), kc.last_iterations()) == (k.stats.n_down, k.stats.n_keypoints, k.stats.icp.iterations), (i, sizes[i])
+        assert np.abs(p[4:] - pc[4:]).max() < 1e-5 and np.abs(p[:4] - pc[:4]).max() < 1e-6, (i, sizes[i])
+    dump = k.local_map().dump()
+    assert np.array_equal(dump[0], ref_dump[0]) and np.array_equal(dump[1], ref_dump[1])
+    np.testing.assert_allclose(dump[2], ref_dump[2], rtol=0, atol=1e-9)
+    k.close()
