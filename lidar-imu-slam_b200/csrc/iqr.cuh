@@ -101,14 +101,28 @@ __device__ __forceinline__ void iqr_block(IqrSmem &sm, const double *__restrict_
 // the <= 4 elements whose rank is one of the wanted order statistics publish their value. After one grid barrier CTA 0 derives the
 // Tukey bounds and compacts the inliers from its shared copy. Same values as the select above (an order statistic is an order
 // statistic), so the filtered cloud is bit-identical.
-constexpr int IQR_GRID_MAX = 4096;
+constexpr int IQR_GRID_MAX = 4096;        // capacity of the copy every CTA keeps in STATIC shared memory
+constexpr int IQR_GRID_MAX_DYN = 16384;   // ... in dynamic shared memory, for launches whose hint announces more candidates (8192 or 16384 of them)
 
 template <int BLOCK>
 __device__ __forceinline__ void iqr_grid_select(double *sd2 /* shared, IQR_GRID_MAX */, const double *__restrict__ xyz, int n, double *sel /* global, 4 */,
                                                 int nblocks = 0 /* CTAs 0..nblocks-1 share the ranking (0: the whole grid) */) {
-    for (int i = threadIdx.x; i < n; i += BLOCK) {
-        const double x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
-        sd2[i] = x * x + y * y + z * z;   // icp.cpp:97-100
+    // eight candidates per thread and round, all 24 loads in flight before the first product: one candidate per round cost one L2 round trip
+    // per 256 candidates (5 of the 7 us of this phase at 2.5 k candidates, 15 us at 7.4 k)
+    constexpr int FB = 8;
+    for (int i0 = threadIdx.x; i0 < n; i0 += BLOCK * FB) {
+        double x[FB], y[FB], z[FB];
+#pragma unroll
+        for (int u = 0; u < FB; ++u) {
+            const int i = i0 + u * BLOCK;
+            const size_t k = 3 * (size_t)(i < n ? i : n - 1);
+            x[u] = xyz[k]; y[u] = xyz[k + 1]; z[u] = xyz[k + 2];
+        }
+#pragma unroll
+        for (int u = 0; u < FB; ++u) {
+            const int i = i0 + u * BLOCK;
+            if (i < n) sd2[i] = x[u] * x[u] + y[u] * y[u] + z[u] * z[u];   // icp.cpp:97-100
+        }
     }
     __syncthreads();
     const int half = n / 2, m = half, u0 = half + n % 2;
@@ -123,6 +137,7 @@ __device__ __forceinline__ void iqr_grid_select(double *sd2 /* shared, IQR_GRID_
         int c[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) { d[k] = sd2[i0 + k < n ? i0 + k : n - 1]; c[k] = 0; }
+#pragma unroll 4
         for (int j = lane; j < n; j += 32) {
             const double e = sd2[j];
 #pragma unroll
@@ -173,9 +188,9 @@ __device__ __forceinline__ void iqr_grid_filter(IqrSmem &sm, const double *sd2, 
 // single pass (IQR_GRID_MAX / BLOCK consecutive candidates per thread, one block scan): every CTA that runs the Gauss-Newton loop derives
 // the keypoint list itself, so nobody waits for CTA 0 to compact it (icp.cpp:103-121; same bounds and comparisons as iqr_grid_filter).
 // Returns the keypoint count.
-template <int BLOCK>
+template <int BLOCK, int PER = IQR_GRID_MAX / BLOCK /* candidates per thread: capacity = BLOCK * PER */>
 __device__ __forceinline__ int iqr_local_compact(int *ws /* shared, 32 */, int *total /* shared */, const double *sd2, int n0, const double *sel,
-                                                 unsigned short *qidx /* shared, IQR_GRID_MAX */) {
+                                                 unsigned short *qidx /* shared, BLOCK * PER */) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = n0 / 2;
     const double v0 = __ldcg(sel), v1 = __ldcg(sel + 1), v2 = __ldcg(sel + 2), v3 = __ldcg(sel + 3);
@@ -183,17 +198,17 @@ __device__ __forceinline__ int iqr_local_compact(int *ws /* shared, 32 */, int *
     const double q3 = (m % 2 == 0) ? (v2 + v3) / 2.0 : v3;
     const double iqr = q3 - q1;
     const double low = q1 - 1.25 * iqr, high = q3 + 1.25 * iqr;   // icp.cpp:104-105
-    constexpr int PER = IQR_GRID_MAX / BLOCK;
-    static_assert((PER & (PER - 1)) == 0, "candidates per thread must be a power of two");
-    unsigned int f = 0;
+    static_assert((PER & (PER - 1)) == 0 && PER <= 64, "candidates per thread: a power of two, one flag bit each");
+    unsigned long long f = 0;
     int cnt = 0;
-#pragma unroll
+    constexpr int UNROLL = PER > 16 ? 8 : PER;   // (fully unrolled, the 32 / 64-candidate variants want every register the launch bounds allow)
+#pragma unroll UNROLL
     for (int v = 0; v < PER; ++v) {
         const int u = (v + tid) & (PER - 1);                       // rotated visiting order: the lanes of a warp read different banks
         const int i = tid * PER + u;
         const double d = i < n0 ? sd2[i] : 0.0;
         const bool in = i < n0 && d >= low && d <= high;          // icp.cpp:117
-        f |= (in ? 1u : 0u) << u;
+        f |= (in ? 1ull : 0ull) << u;
         cnt += in ? 1 : 0;
     }
     int incl = cnt;
@@ -211,9 +226,9 @@ __device__ __forceinline__ int iqr_local_compact(int *ws /* shared, 32 */, int *
     }
     __syncthreads();
     int pos = ws[warp] + incl - cnt;
-#pragma unroll
+#pragma unroll UNROLL
     for (int u = 0; u < PER; ++u) {
-        if (f & (1u << u)) {
+        if (f & (1ull << u)) {
             const int i = tid * PER + u;
             qidx[pos] = (unsigned short)i;
             ++pos;

@@ -55,6 +55,8 @@ struct IcpArgs {
     double *out;                // [0..6] pose, [7] iterations, [8] converged, [9] ncorr, [10] ncand, [11] nmiss, [12] n
     int grouped;                // 1: eight lanes per query (latency shape: a few thousand keypoints)
     int stage_doubles;          // > 0: the launch carries dynamic shared memory for the staged pass of the bandwidth shape
+    int iqr_cap;                // latency shape: candidates the grid-wide IQR ranking can hold per CTA: IQR_GRID_MAX (static shared memory), or 8192 / 16384
+                                // (the launch then carries iqr_cap * 10 bytes of dynamic shared memory: squared ranges + index list)
     int coop_scan;              // 1: sub-warp cooperative candidate scan (bandwidth shape); 0: one lane per query (latency shape)
     // point-sharded multi-GPU: every rank owns a contiguous shard of the queries and a full replica of
     // the map; per iteration the ranks exchange their NS-double row through peer-mapped mailboxes (NVLink stores).
@@ -714,6 +716,13 @@ __device__ __forceinline__ bool ll_load(const unsigned long long *slot, unsigned
 // SHAPE 0 = latency build (a few thousand keypoints: one CTA per SM at most, so the compiler may use up to 255 registers and the serial
 // Gauss-Newton solve stays out of local memory); SHAPE 1 = bandwidth build for kernel mode (millions of queries against a map far larger
 // than L2): LIMU_BW_CTAS CTAs per SM, voxel blocks staged through shared memory (icp_query_pass_staged), the solve out of line.
+// the index-list compaction for the larger candidate capacities, out of line: unrolled 32 / 64 times inside the loop kernel it took that kernel
+// from 140 to 255 registers
+static __device__ __noinline__ int iqr_local_compact_dyn(int cap, int *ws, int *total, const double *sd2, int n0, const double *sel, unsigned short *qidx) {
+    if (cap <= 8192) return iqr_local_compact<ICP_BLOCK, 8192 / ICP_BLOCK>(ws, total, sd2, n0, sel, qidx);
+    return iqr_local_compact<ICP_BLOCK, IQR_GRID_MAX_DYN / ICP_BLOCK>(ws, total, sd2, n0, sel, qidx);
+}
+
 template <int SHAPE, bool NN27, bool PLANE>
 static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTAS) k_icp_persistent(const IcpArgs A) {
     constexpr int NSX = PLANE ? NSP : NS;              // doubles per partial row
@@ -731,23 +740,30 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FT_MARK(0);
     LIMU_TRACE(1);
-    __shared__ unsigned short qidx_s[SHAPE == 0 ? IQR_GRID_MAX : 1];
+    __shared__ unsigned short qidx_static[SHAPE == 0 ? IQR_GRID_MAX : 1];
+    extern __shared__ __align__(16) double stage_smem[];
+    // more than IQR_GRID_MAX candidates announced (~7 k at configs[2]): the two lists live in dynamic shared memory -- the one-CTA select
+    // behind a whole-grid barrier that such scans used to fall back to took 61 us per scan
+    const bool iqr_dyn = SHAPE == 0 && A.iqr_cap > IQR_GRID_MAX;
+    unsigned short *qidx_s = iqr_dyn ? reinterpret_cast<unsigned short *>(stage_smem + A.iqr_cap) : qidx_static;
     int n_keypoints = -1;   // >= 0: the keypoints are IQR candidates qidx_s[0 .. n_keypoints) (known to the CTAs of the Gauss-Newton loop)
     if (A.iqr_in) {   // KissICP::iqr_processing (icp.cpp:88-124, :133)
         // Latency shape: only the CTAs that will run the Gauss-Newton loop take part. They rank their share of the ~2.5 k squared ranges by
         // counting and meet at THEIR barrier (the leading CTAs of a launch start first; the whole-grid barrier also waits for the last CTA to
         // be scheduled); then each of them derives bounds, flags and the keypoint index list in its own shared memory, so nobody waits for
         // CTA 0 to compact (CTA 0 also writes the keypoints out for the host). The bandwidth shape keeps the one-CTA select.
-        __shared__ double iqr_sd2[SHAPE == 0 ? IQR_GRID_MAX : 1];
+        __shared__ double iqr_sd2_static[SHAPE == 0 ? IQR_GRID_MAX : 1];
+        double *iqr_sd2 = iqr_dyn ? stage_smem : iqr_sd2_static;
         const int n0 = __ldcg(A.iqr_n);
-        if (SHAPE == 0 && n0 > 1 && n0 <= IQR_GRID_MAX) {   // uniform across the grid
+        if (SHAPE == 0 && n0 > 1 && n0 <= (iqr_dyn ? A.iqr_cap : IQR_GRID_MAX)) {   // uniform across the grid
             if (icp_member) {
                 IQ_MARK(16);
                 iqr_grid_select<ICP_BLOCK>(iqr_sd2, A.iqr_in, n0, A.iqr_d2, A.icp_blocks);
                 IQ_MARK(17);
                 gs_icp.sync();
                 IQ_MARK(18);
-                n_keypoints = iqr_local_compact<ICP_BLOCK>(iqr_sm.ws, &iqr_sm.total, iqr_sd2, n0, A.iqr_d2, qidx_s);
+                if (!iqr_dyn) n_keypoints = iqr_local_compact<ICP_BLOCK>(iqr_sm.ws, &iqr_sm.total, iqr_sd2, n0, A.iqr_d2, qidx_s);
+                else n_keypoints = iqr_local_compact_dyn(A.iqr_cap, iqr_sm.ws, &iqr_sm.total, iqr_sd2, n0, A.iqr_d2, qidx_s);
                 IQ_MARK(19);
             }
         } else {
@@ -791,7 +807,6 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
                 const double *in = j == 0 ? (n_keypoints >= 0 ? A.iqr_in : A.points) : A.work;
                 const unsigned short *qi0 = (j == 0 && n_keypoints >= 0) ? qidx_s : nullptr;
                 if (SHAPE == 1 && !NN27 && !PLANE && A.stage_doubles > 0) {   // bandwidth shape: voxel blocks staged through shared memory
-                    extern __shared__ __align__(16) double stage_smem[];
                     icp_query_pass_staged(A, Pv, in, n, wbase, wstride, lane, stage_smem + (size_t)warp * STAGE_WARP_DOUBLES, acc, ncorr, ncand, nmiss);
                 } else if (SHAPE == 1 && !NN27 && !PLANE) {     // ... or, for blocks too large to stage, fetched by eight lanes into registers
                     if (A.map.cap <= 8) icp_query_pass_coop<1>(A, Pv, in, n, wbase, wstride, lane, acc, ncorr, ncand, nmiss);
@@ -1370,7 +1385,21 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
     const bool nn27 = (icp_mode & LIMU_ICP_NN27) != 0, plane = (icp_mode & LIMU_ICP_PLANE) != 0;
     const bool grouped = n_hint <= 16384 && m->cap <= 64;   // latency shape: eight lanes per query, one CTA per SM
     // bandwidth shape with the reference's rules: voxel blocks are staged through dynamic shared memory (two buffers of eight blocks per query warp)
-    const size_t stage_bytes = (!grouped && !nn27 && !plane && block_stride(m->cap) <= STAGE_MAX_STRIDE) ? (size_t)(ICP_BLOCK / 32 - 1) * STAGE_WARP_DOUBLES * sizeof(double) : 0;
+    size_t stage_bytes = (!grouped && !nn27 && !plane && block_stride(m->cap) <= STAGE_MAX_STRIDE) ? (size_t)(ICP_BLOCK / 32 - 1) * STAGE_WARP_DOUBLES * sizeof(double) : 0;
+    // latency shape with the IQR filter in front: the candidates (a few per cent more than the keypoints the hint counts) are ranked by the whole
+    // grid out of a copy in every CTA's shared memory -- static up to IQR_GRID_MAX of them, dynamic (8192 or 16384) when the hint announces more
+    int iqr_cap = IQR_GRID_MAX;
+    if (grouped && fuse && fuse->iqr_in && n_hint + n_hint / 8 + 64 > IQR_GRID_MAX) {
+        iqr_cap = (n_hint + n_hint / 8 + 64 <= 8192) ? 8192 : IQR_GRID_MAX_DYN;
+        stage_bytes = (size_t)iqr_cap * (sizeof(double) + sizeof(unsigned short));
+        static bool iqr_attr_set = false;
+        if (!iqr_attr_set) {
+            const void *lat[4] = {(const void *)k_icp_persistent<0, false, false>, (const void *)k_icp_persistent<0, false, true>, (const void *)k_icp_persistent<0, true, false>,
+                                  (const void *)k_icp_persistent<0, true, true>};
+            for (const void *f : lat) LIMU_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, IQR_GRID_MAX_DYN * 10));
+            iqr_attr_set = true;
+        }
+    }
     static bool stage_attr_set[64] = {};
     if (stage_bytes && !stage_attr_set[c->device & 63]) {
         LIMU_CUDA_TRY(cudaFuncSetAttribute(k_icp_persistent<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
@@ -1412,7 +1441,8 @@ int icp_device(limu_map *m, const double *points_dev, double *work_dev, int64_t 
     A.est_trace = est_trace_dev; A.ncorr_trace = ncorr_trace_dev; A.hg_trace = hg_trace_dev;
     A.coop_scan = n_hint >= 32768 ? 1 : 0;
     A.grouped = grouped ? 1 : 0;
-    A.stage_doubles = (int)(stage_bytes / sizeof(double));
+    A.stage_doubles = grouped ? 0 : (int)(stage_bytes / sizeof(double));
+    A.iqr_cap = iqr_cap;
     A.nranks = 1; A.rank = 0;
     A.status = c->d_status;
     if (max_iter_all_ranks >= 0 && c->comm && c->comm->nranks > 1) {   // point-sharded call: fused peer exchange

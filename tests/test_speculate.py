@@ -372,6 +372,15 @@ def test_pipelined_matches_plain_when_the_loop_needs_every_sm(ctx, pkg, voxel, b
     ref, _ = plain_run(ctx, seq, voxel_size=voxel, cap=20)
     nk = max(len(r[1]) for r in ref)
     assert nk > (16384 if voxel < 0.2 else 4200), nk          # the regime this test is about
+    # ... which is also where the grid-wide IQR ranking keeps its candidate lists in dynamic shared memory (more than 4096 of them; 16384 at
+    # most, beyond that one CTA selects): the C port pins the filter's output and the poses
+    import oracle
+    kc = oracle.load_port().Kiss(voxel_size=voxel, max_range=100.0, cap=20, deskew=True, icp_max_iteration=60)
+    for i, s in enumerate(seq):
+        dc, sc, pc = kc.register_cloud(np.ascontiguousarray(s[:, :3]), s[:, 3].astype(np.float64))
+        assert (len(dc), len(sc), kc.last_iterations()) == (len(ref[i][0]), len(ref[i][1]), ref[i][3]), i
+        assert np.array_equal(sc, ref[i][1]) or i >= 3          # keypoint cloud bit-exact while the deskew gate is closed (identical inputs)
+        assert np.abs(ref[i][2][4:] - pc[4:]).max() < 1e-5 and np.abs(ref[i][2][:4] - pc[:4]).max() < 1e-6, i
     staged = [torch.from_numpy(s).cuda() for s in seq]
     torch.cuda.synchronize()
     k = ctx.KissICP(deskew=True, icp_max_iteration=60, speculate=True, voxel_size=voxel, cap=20)

@@ -14,19 +14,47 @@ pkg = g.load_package()
 from importlib import import_module
 synth = import_module("limu_b200.synth")
 ctx = pkg.Context(0)
-scene = synth.Scene(seed=42)
-K = 40
-traj = synth.loop_trajectory(K + 1, radius=30.0, step=1.0)
-scans = [synth.pad_scan(synth.cast_scan(scene, traj[i], traj[i + 1], seed=42 * 100003 + i, device="cuda"), 128000, seed=i) for i in range(K)]
-odo = ctx.KissICP(voxel_size=1.0, cap=10, deskew=True, icp_max_iteration=500)
+WL = os.environ.get("LIMU_PT_WORKLOAD", "c2")     # c2: the bench workload; c3: configs[2] in pipeline mode (512 k points/scan, voxel 0.5 m, cap 20)
+if WL == "c3":
+    import copy
+    import bench
+    a3 = copy.copy(bench.parse([]))
+    a3.points, a3.beams, a3.azimuth_steps, a3.voxel, a3.cap, a3.max_range = 512000, 128, 4000, 0.5, 20, 1000.0
+    K = 14
+    scans = bench.make_scans(a3, K, 42, "cuda", workload="c3")
+    KW = dict(voxel_size=0.5, cap=20, max_range=1000.0, map_capacity_voxels=3_400_000 if os.environ.get("LIMU_PT_BG") else 0)
+else:
+    scene = synth.Scene(seed=42)
+    K = 40
+    traj = synth.loop_trajectory(K + 1, radius=30.0, step=1.0)
+    scans = [synth.pad_scan(synth.cast_scan(scene, traj[i], traj[i + 1], seed=42 * 100003 + i, device="cuda"), 128000, seed=i) for i in range(K)]
+    KW = dict(voxel_size=1.0, cap=10)
+odo = ctx.KissICP(deskew=True, icp_max_iteration=500, **KW)
+
+
+def background(o):
+    """configs[2]: the ~45 M-point slab bench.py's workload_c3 keeps resident (LIMU_PT_BG=1)."""
+    import torch
+    n = 46_000_000
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    bg = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+    bg[:, :2] = (torch.rand((n, 2), generator=gen, device="cuda", dtype=torch.float64) - 0.5) * 400.0
+    bg[:, 2] = 150.0 + torch.rand(n, generator=gen, device="cuda", dtype=torch.float64) * 2.0
+    torch.cuda.synchronize()
+    m = o.local_map()
+    for lo in range(0, n, 1 << 20):
+        m.insert_points_dev(bg[lo:lo + (1 << 20)].data_ptr(), min(1 << 20, n - lo))
+    ctx.sync()
 marks = np.zeros(72)
 vmarks = np.zeros(8)
 have_vox = hasattr(pkg.lib(), "limu_debug_vox_marks")
 rows, iters, rounds, vrows = [], [], [], []
 for i, s in enumerate(scans):
     odo.register_frame(s, want_clouds=False)
+    if i == 0 and WL == "c3" and os.environ.get("LIMU_PT_BG"):
+        background(odo)
     pkg.lib().limu_debug_frame_marks(marks.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
-    if i >= 5:
+    if i >= (3 if WL == "c3" else 5):
         rows.append(np.diff(marks[:6]) / 1e3)
         iters.append(odo.stats.icp.iterations)
         nr = min(odo.stats.icp.iterations, 47)              # round j starts at marks[24 + j]; the last one has no successor
@@ -84,11 +112,13 @@ if hasattr(pkg.lib(), "limu_debug_trace_reg"):
     odo.close()
     dev = [torch.from_numpy(s).cuda() if isinstance(s, np.ndarray) else s for s in scans]
     torch.cuda.synchronize()
-    odo = ctx.KissICP(voxel_size=1.0, cap=10, deskew=True, icp_max_iteration=500, speculate=True)
+    odo = ctx.KissICP(deskew=True, icp_max_iteration=500, speculate=True, **KW)
     for i, s in enumerate(dev):
-        if i + 1 < len(dev):
+        if i + 1 < len(dev) and i > 0:
             odo.hint_next_dev(dev[i + 1].data_ptr(), dev[i + 1].shape[0])
         odo.register_frame_dev(s.data_ptr(), s.shape[0])
+        if i == 0 and WL == "c3" and os.environ.get("LIMU_PT_BG"):
+            background(odo)
     odo.flush()
     names = {1: "loop kernel starts", 2: "IQR done", 3: "loop over (gate flag)", 4: "loop kernel ends", 10: "voxelize starts", 11: "voxelize P1 done", 12: "voxelize P2 done",
              13: "voxelize ends", 20: "update starts", 21: "update: claim done", 22: "update: place done", 23: "update ends", 30: "gate exits (update released)"}
