@@ -439,3 +439,49 @@ def test_ragged_sequence_through_the_pipelined_path(ctx, pkg):
     assert np.array_equal(dump[0], ref_dump[0]) and np.array_equal(dump[1], ref_dump[1])
     np.testing.assert_allclose(dump[2], ref_dump[2], rtol=0, atol=1e-9)
     k.close()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_configurations_pipelined_vs_plain_vs_port(ctx, pkg, seed):
+    """Seeded random configurations (voxel size, cap, deskew gate, scan shape, iteration cap, registration variant): hinted replay on the
+    pipelined path against the plain path (1e-9) and against the C port (counts and iterations equal, north-star pose tolerance)."""
+    import torch
+    import oracle
+    from importlib import import_module
+    synth = import_module("limu_b200.synth")
+    rng = np.random.default_rng(1000 + seed)
+    voxel = float(rng.choice([0.25, 0.5, 1.0, 2.0]))
+    cap = int(rng.choice([1, 3, 10, 20]))
+    deskew = bool(rng.integers(0, 2))
+    mode = int(rng.choice([0, 0, 0, 3]))
+    beams = int(rng.choice([8, 16, 32, 64]))
+    az = int(rng.integers(300, 2500))
+    max_iter = int(rng.choice([5, 60, 500]))
+    step = float(rng.choice([0.1, 0.5, 1.0]))
+    scene = synth.Scene(seed=50 + seed, n_boxes=int(rng.integers(10, 80)), n_cyl=int(rng.integers(5, 40)))
+    traj = synth.loop_trajectory(8, radius=30.0, step=step)
+    seq = [synth.cast_scan(scene, traj[i], traj[i + 1], beams=beams, azimuth_steps=az, seed=40 * seed + i, device="cuda:0") for i in range(7)]
+    cfg = dict(voxel_size=voxel, cap=cap, deskew=deskew, icp_max_iteration=max_iter, icp_mode=mode)
+    what = f"seed {seed}: {cfg}, {beams} x {az}, {step} m/scan"
+    k = ctx.KissICP(speculate=False, **cfg)
+    ref = []
+    for s in seq:
+        d, sr, p = k.register_frame(s)
+        ref.append((d, sr, p.copy(), k.stats.icp.iterations))
+    k.close()
+    kc = oracle.load_port().Kiss(voxel_size=voxel, max_range=100.0, cap=cap, deskew=deskew, icp_max_iteration=max_iter)
+    if mode:
+        kc.set_mode(mode)
+    staged = [torch.from_numpy(s).cuda() for s in seq]
+    torch.cuda.synchronize()
+    k = ctx.KissICP(speculate=True, **cfg)
+    for i, t in enumerate(staged):
+        if i + 1 < len(staged):
+            k.hint_next_dev(staged[i + 1].data_ptr(), len(seq[i + 1]))
+        p = k.register_frame_dev(t.data_ptr(), len(seq[i]))
+        np.testing.assert_allclose(p, ref[i][2], rtol=0, atol=1e-9, err_msg=f"{what}, scan {i}")
+        assert (k.stats.icp.iterations, k.stats.n_down, k.stats.n_keypoints) == (ref[i][3], len(ref[i][0]), len(ref[i][1])), (what, i)
+        dc, sc, pc = kc.register_cloud(np.ascontiguousarray(seq[i][:, :3]), seq[i][:, 3].astype(np.float64))
+        assert (len(dc), len(sc), kc.last_iterations()) == (k.stats.n_down, k.stats.n_keypoints, k.stats.icp.iterations), (what, i)
+        assert np.abs(p[4:] - pc[4:]).max() < 1e-5 and np.abs(p[:4] - pc[:4]).max() < 1e-6, (what, i, p, pc)
+    k.close()
