@@ -441,7 +441,17 @@ def test_ragged_sequence_through_the_pipelined_path(ctx, pkg):
     k.close()
 
 
-@pytest.mark.parametrize("seed", range(16))
+def _random_seeds():
+    """16 seeds in the suite; LIMU_RANDOM_SEEDS="lo-hi" widens the campaign (profiles/r2_random_campaign.json: seeds 16..255 on one B200)."""
+    import os
+    spec = os.environ.get("LIMU_RANDOM_SEEDS", "")
+    if "-" in spec:
+        lo, hi = spec.split("-")
+        return range(int(lo), int(hi))
+    return range(16)
+
+
+@pytest.mark.parametrize("seed", _random_seeds())
 def test_random_configurations_pipelined_vs_plain_vs_port(ctx, pkg, seed):
     """Seeded random configurations (voxel size, cap, deskew gate, scan shape, iteration cap, registration variant): hinted replay on the
     pipelined path against the plain path (1e-9) and against the C port (counts and iterations equal, north-star pose tolerance)."""
