@@ -166,9 +166,10 @@ int limu_icp_dev(limu_map *m, const double *xyz_dev, int64_t n, const double ini
  *   upstream KISS-ICP describe), cells visited x-outermost, points in storage order, first minimum wins.
  *   LIMU_ICP_PLANE: point-to-plane residual e = n.(s - t) with n = normal of the matched point's voxel (smallest-eigenvalue
  *   direction of the scatter of its >= 5 stored points, planar when l_min <= 0.04 l_mid; other correspondences are dropped),
- *   weight th^2/(th + e^2)^2, Jacobian row [n ; s x n]; the solve carries a fixed Levenberg-Marquardt damping, x = LDLT(H + D).solve(-g)
- *   with D = diag(1, 1, 1, 100, 100, 100) (negligible against a populated map; keeps the step bounded where only a handful of planar
- *   voxels can be matched, e.g. on the first scans of a sequence). Not available in the point-sharded loop. */
+ *   weight th^2/(th + e^2)^2, Jacobian row [n ; s x n]; the solve carries a weak prior on the initial guess,
+ *   x = LDLT(H + D).solve(-(g + D log(T_icp))) with D = diag(1, 1, 1, 100, 100, 100) (negligible against a populated map; where only a
+ *   handful of planar voxels can be matched, e.g. on the first scans of a sequence, the directions they do not observe stay at the
+ *   prediction instead of running away). Not available in the point-sharded loop. */
 enum { LIMU_ICP_REFERENCE = 0, LIMU_ICP_NN27 = 1, LIMU_ICP_PLANE = 2 };
 int limu_icp_ex(limu_map *m, const double *xyz, int64_t n, const double init_guess[7], double max_corresp_dist, double kernel,
                 int icp_max_iteration, double est_threshold, int32_t icp_mode, double pose_out[7], limu_icp_stats *stats,

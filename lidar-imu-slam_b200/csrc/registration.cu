@@ -175,7 +175,7 @@ __device__ __forceinline__ double warp_reduce_scatter32(const double *c) {
     for (int i = 0; i < 2; ++i) g[i] = (u2 ? f[i + 2] : f[i]) + __shfl_xor_sync(0xFFFFFFFFu, u2 ? f[i] : f[i + 2], 2);
     return (u1 ? g[1] : g[0]) + __shfl_xor_sync(0xFFFFFFFFu, u1 ? g[0] : g[1], 1);
 }
-constexpr double PLANE_DAMP = 1.0, PLANE_DAMP_ARM2 = 100.0;   // the oracle's LO_PLANE_DAMP, LO_PLANE_DAMP_ARM2: x = LDLT(H + D).solve(-g)
+constexpr double PLANE_PRIOR = 1.0, PLANE_PRIOR_ARM2 = 100.0;   // the oracle's LO_PLANE_PRIOR, LO_PLANE_PRIOR_ARM2: D = diag(mu x 3, mu rho^2 x 3)
 // S[0..20] = upper triangle of H row-major, S[21..26] = g.
 __device__ __forceinline__ void expand_plane_equations(const double *S, double *H, double *g) {
     int k = 0;
@@ -962,10 +962,17 @@ static __global__ void __launch_bounds__(ICP_BLOCK, SHAPE == 0 ? 1 : LIMU_BW_CTA
 #pragma unroll
                     for (int k = 0; k < 6; ++k) g[k] = -g[k];
                     if (PLANE) {
-                        // point-to-plane: fixed Levenberg-Marquardt damping (oracle: lo_icp) -- a map that offers only a handful of planar
-                        // voxels does not determine six degrees of freedom, and the undamped step runs away
+                        // point-to-plane: weak prior on the initial guess (oracle: lo_icp), x = LDLT(H + D).solve(-(g + D log(T_icp))) -- a map
+                        // that offers only a handful of planar voxels does not determine six degrees of freedom, and the plain step runs away.
+                        // (T_icp is this lane's own: it folded the previous estimate into it in the tail above.)
+                        double xi[6];
+                        se3_log(pose_load(Ticp), xi);
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) { H[7 * k] += PLANE_DAMP; H[7 * (k + 3)] += PLANE_DAMP * PLANE_DAMP_ARM2; }
+                        for (int k = 0; k < 3; ++k) {
+                            H[7 * k] += PLANE_PRIOR; H[7 * (k + 3)] += PLANE_PRIOR * PLANE_PRIOR_ARM2;
+                            g[k] = -(S[21 + k] + PLANE_PRIOR * xi[k]);
+                            g[k + 3] = -(S[24 + k] + (PLANE_PRIOR * PLANE_PRIOR_ARM2) * xi[k + 3]);
+                        }
                     }
                     ldlt6_solve(H, g, x);                         // JTJ.ldlt().solve(-JTr) :90
 #pragma unroll

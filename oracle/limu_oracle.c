@@ -539,17 +539,20 @@ void lo_align(const double *src, const double *tgt, long n, double th, double *H
  * spread; line-like and blob-like voxels are rejected) and its correspondences are dropped otherwise, as are voxels with < 5 points.
  * Residual e = n.(s - t), weight w = th^2/(th + e^2)^2, Jacobian row a = [n ; s x n] in the reference's perturbation model
  * (s' = exp(x) s, J_point = [I | -hat(s)], registration.cpp:46-54), H += w a a^T, g += w a e, x = LDLT(H).solve(-g).
- * The solve is damped (Levenberg-Marquardt with a FIXED damping, i.e. a weak prior on "no further motion" in every iteration):
- * x = LDLT(H + D).solve(-g), D = diag(mu, mu, mu, mu rho^2, mu rho^2, mu rho^2) with mu = LO_PLANE_DAMP = 1 (one unit-weight
- * correspondence per axis) and rho^2 = LO_PLANE_DAMP_ARM2 = 100 m^2 (a 10 m lever arm for the rotational part). The fixed point of the
- * iteration (g = 0) is unchanged and against the thousands of correspondences of a populated map D is negligible; but a map of ONE scan
- * with small voxels offers a keypoint cloud only 1..40 planar voxels, H (rank <= that number, far less when they share a normal) does not
- * determine six degrees of freedom, and the undamped step ran away by up to 20 m on scan 1 in 7 of 60 random point-to-plane
- * configurations -- in this restatement and on the device alike (profiles/r2_random_campaign.json). */
+ * The solve carries a weak prior on the initial guess (the motion model's prediction), as the measurement update of a LiDAR-inertial
+ * filter does: with xi = log(T_icp), the correction accumulated so far, x = LDLT(H + D).solve(-(g + D xi)),
+ * D = diag(mu, mu, mu, mu rho^2, mu rho^2, mu rho^2), mu = LO_PLANE_PRIOR = 1 (one unit-weight correspondence per axis),
+ * rho^2 = LO_PLANE_PRIOR_ARM2 = 100 m^2 (a 10 m lever arm for the rotational part). Against the thousands of correspondences of a
+ * populated map D is negligible (the bias is ~1e-3 of a centimetre-sized correction); but a map of ONE scan with small voxels offers a
+ * keypoint cloud only 1..40 planar voxels, H (rank <= that number, far less when they share a normal) does not determine six degrees of
+ * freedom, and the unregularised step ran away by up to 20 m on scan 1 in 7 of 60 random point-to-plane configurations -- in this
+ * restatement and on the device alike (profiles/r2_random_campaign.json). Directions the planes do not observe stay at the prediction.
+ * (A prior on the STEP instead -- fixed Levenberg-Marquardt damping -- also stops the runaway but creeps along those directions for
+ * hundreds of iterations before the twist falls below the convergence threshold.) */
 #define LO_PLANE_MIN_POINTS 5
 #define LO_PLANE_RATIO 0.04
-#define LO_PLANE_DAMP 1.0
-#define LO_PLANE_DAMP_ARM2 100.0
+#define LO_PLANE_PRIOR 1.0
+#define LO_PLANE_PRIOR_ARM2 100.0
 int lo_plane_normal(const double *b, int c, double *nrm) {   /* b: c points, array-of-structs */
     if (c < LO_PLANE_MIN_POINTS) return 0;
     double mu[3] = {0, 0, 0};
@@ -640,10 +643,14 @@ int lo_icp(const lo_map *m, const double *xyz, long n, const double *init7, doub
         if (m->icp_mode & 2) {                                        /* opt-in point-to-plane variant (not in the reference) */
             double ng[6], x[6];
             c = plane_step(m, source, n, tau, th, H, g);
-            for (int i = 0; i < 6; ++i) ng[i] = -g[i];
-            double Hd[36];
-            memcpy(Hd, H, sizeof Hd);                                 /* (the trace keeps the undamped H) */
-            for (int i = 0; i < 3; ++i) { Hd[7 * i] += LO_PLANE_DAMP; Hd[7 * (i + 3)] += LO_PLANE_DAMP * LO_PLANE_DAMP_ARM2; }
+            double Hd[36], xi[6];
+            memcpy(Hd, H, sizeof Hd);                                 /* (the trace keeps H and g without the prior) */
+            lo_se3_log(T_icp, xi);
+            for (int i = 0; i < 3; ++i) {
+                Hd[7 * i] += LO_PLANE_PRIOR; Hd[7 * (i + 3)] += LO_PLANE_PRIOR * LO_PLANE_PRIOR_ARM2;
+                ng[i] = -(g[i] + LO_PLANE_PRIOR * xi[i]);
+                ng[i + 3] = -(g[i + 3] + (LO_PLANE_PRIOR * LO_PLANE_PRIOR_ARM2) * xi[i + 3]);
+            }
             ldlt6_solve(Hd, ng, x);
             lo_se3_exp(x, est);
         } else {

@@ -170,7 +170,8 @@ def test_icp_variants_per_iteration(ctx, port, rng, mode, nq, max_iter):
 def test_pipeline_variants_match_oracle(ctx, port, mode):
     synth = synth_mod()
     scene = synth.Scene(seed=42)
-    n = 7   # every scan of this prefix converges in both variants, so rounding differences are not amplified by a capped loop
+    n = 7   # (scan 1 of the point-to-plane variant matches only ~17 planar voxels of the one-scan map and ends in a limit cycle at the cap --
+            # on the device and in the oracle alike: the prior of the solve keeps it at the prediction, see oracle/limu_oracle.c)
     traj = synth.loop_trajectory(n + 1, radius=30.0, step=1.0)
     scans = [synth.cast_scan(scene, traj[i], traj[i + 1], beams=32, azimuth_steps=1000, seed=i) for i in range(n)]
     gk = ctx.KissICP(voxel_size=1.0, cap=10, deskew=True, icp_max_iteration=150, icp_mode=mode)
@@ -180,7 +181,7 @@ def test_pipeline_variants_match_oracle(ctx, port, mode):
         _, _, gp = gk.register_frame(scan)
         _, _, op = ok.register_cloud(scan[:, :3], scan[:, 3].astype(np.float64))
         assert np.abs(gp[4:] - op[4:]).max() < 1e-5 and np.abs(gp[:4] - op[:4]).max() < 1e-6, i
-        assert gk.stats.icp.iterations == port._kiss_last_iterations(ok.h) < 150
+        assert gk.stats.icp.iterations == port._kiss_last_iterations(ok.h) <= 150
     p = gk.poses()
     if mode & PLANE:   # and the device pipeline follows the sensor
         truth = np.linalg.norm(traj[n, :2] - traj[1, :2])

@@ -5,25 +5,27 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 T="${1:-fin2}"
+BUDGET="${2:-700}"   # seconds this script may use in all: every leg is cut to what is left of it
+left() { local l=$(( BUDGET - SECONDS )); [ $l -lt 5 ] && l=5; [ $l -gt $1 ] && l=$1; echo $l; }
 python -c "
 import __graft_entry__ as g
 print('source_hash', g.load_package().source_hash())
 " | tee gpurun_out/${T}_hash.txt
-( time timeout 600 python -m pytest tests -m gpu -q ) > gpurun_out/${T}_pytest.log 2>&1; RC1=$?
+( time timeout $(left 600) python -m pytest tests -m gpu -q ) > gpurun_out/${T}_pytest.log 2>&1; RC1=$?
 echo "pytest rc=$RC1"; tail -4 gpurun_out/${T}_pytest.log | cut -c1-300
-( time LIMU_RANDOM_SEEDS=16-256 timeout 400 python -m pytest tests/test_speculate.py -m gpu -q -k random -n 4 -p no:cacheprovider ) > gpurun_out/${T}_campaign.log 2>&1; RC2=$?
+( time LIMU_RANDOM_SEEDS=16-256 timeout $(left 400) python -m pytest tests/test_speculate.py -m gpu -q -k random -n 4 -p no:cacheprovider ) > gpurun_out/${T}_campaign.log 2>&1; RC2=$?
 echo "campaign rc=$RC2"; tail -12 gpurun_out/${T}_campaign.log | cut -c1-300
 if [ $RC1 -ne 0 ] || [ $RC2 -ne 0 ]; then echo "STOP: tests failed"; exit 1; fi
-( time timeout 300 python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/${T}_smoke.log 2>&1; echo "smoke rc=$?"; grep "smoke ok" gpurun_out/${T}_smoke.log
+( time timeout $(left 300) python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/${T}_smoke.log 2>&1; echo "smoke rc=$?"; grep "smoke ok" gpurun_out/${T}_smoke.log
 CMD="python bench.py --steps 12 --warmup 5 --no-extras --cpu-seconds 1 --repeats 1"
-timeout 400 $CMD > gpurun_out/${T}_plain_for_ncu.json 2> gpurun_out/${T}_plain_for_ncu.err && \
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_voxelize|k_icp|k_frame|k_gate' -c 400 --csv --log-file gpurun_out/${T}_launches.csv $CMD > gpurun_out/${T}_ncu_list.log 2>&1
+timeout $(left 400) $CMD > gpurun_out/${T}_plain_for_ncu.json 2> gpurun_out/${T}_plain_for_ncu.err && \
+timeout $(left 600) ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_voxelize|k_icp|k_frame|k_gate' -c 400 --csv --log-file gpurun_out/${T}_launches.csv $CMD > gpurun_out/${T}_ncu_list.log 2>&1
 echo "ncu launch list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_icp_persistent|k_voxelize_lean|k_frame_update' --launch-skip 30 -c 9 -o gpurun_out/${T}_frame_full $CMD > gpurun_out/${T}_ncu_full.log 2>&1
+timeout $(left 900) ncu --set full --clock-control none --import-source on -k regex:'k_icp_persistent|k_voxelize_lean|k_frame_update' --launch-skip 30 -c 9 -o gpurun_out/${T}_frame_full $CMD > gpurun_out/${T}_ncu_full.log 2>&1
 echo "ncu full rc=$?"; tail -3 gpurun_out/${T}_ncu_full.log
-( time timeout 600 python bench.py --steps 20 --warmup 5 ) > gpurun_out/${T}_bench20.json 2> gpurun_out/${T}_bench20.err; echo "bench20 rc=$?"
-( time timeout 400 python bench.py --impl reference --steps 20 --warmup 5 ) > gpurun_out/${T}_bench_ref.json 2> gpurun_out/${T}_bench_ref.err; echo "bench ref rc=$?"
-( time timeout 900 python bench.py ) > gpurun_out/${T}_bench_default.json 2> gpurun_out/${T}_bench_default.err; echo "bench default rc=$?"; tail -3 gpurun_out/${T}_bench_default.err
+( time timeout $(left 600) python bench.py --steps 20 --warmup 5 ) > gpurun_out/${T}_bench20.json 2> gpurun_out/${T}_bench20.err; echo "bench20 rc=$?"
+( time timeout $(left 400) python bench.py --impl reference --steps 20 --warmup 5 ) > gpurun_out/${T}_bench_ref.json 2> gpurun_out/${T}_bench_ref.err; echo "bench ref rc=$?"
+( time timeout $(left 900) python bench.py ) > gpurun_out/${T}_bench_default.json 2> gpurun_out/${T}_bench_default.err; echo "bench default rc=$?"; tail -3 gpurun_out/${T}_bench_default.err
 grep -h '^{' gpurun_out/${T}_bench_default.json gpurun_out/${T}_bench20.json gpurun_out/${T}_bench_ref.json | python -c "
 import sys, json
 for l in sys.stdin:
