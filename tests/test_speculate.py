@@ -495,3 +495,70 @@ def test_random_configurations_pipelined_vs_plain_vs_port(ctx, pkg, seed):
         assert (len(dc), len(sc), kc.last_iterations()) == (k.stats.n_down, k.stats.n_keypoints, k.stats.icp.iterations), (what, i)
         assert np.abs(p[4:] - pc[4:]).max() < 1e-5 and np.abs(p[:4] - pc[:4]).max() < 1e-6, (what, i, p, pc)
     k.close()
+
+
+def _random_seeds_b():
+    """4 seeds in the suite; LIMU_RANDOM_SEEDS_B="lo-hi" widens the campaign (profiles/r2_random_campaign.json)."""
+    import os
+    spec = os.environ.get("LIMU_RANDOM_SEEDS_B", "")
+    if "-" in spec:
+        lo, hi = spec.split("-")
+        return range(int(lo), int(hi))
+    return range(1000, 1004)
+
+
+@pytest.mark.parametrize("seed", _random_seeds_b())
+def test_random_configurations_with_eviction_and_map_growth(ctx, pkg, seed):
+    """Second family of seeded random configurations: a short max_range (the eviction sweep removes voxels on every scan), long steps between
+    scans, and a voxel table that starts small (map_capacity_voxels: the table is re-hashed while the sequence runs). Pipelined path with hints
+    against the plain path (poses 1e-9, final map: same voxels in the same creation order) and against the C port (counts, iterations, poses)."""
+    import torch
+    import oracle
+    from importlib import import_module
+    synth = import_module("limu_b200.synth")
+    rng = np.random.default_rng(seed)
+    voxel = float(rng.choice([0.25, 0.5, 1.0]))
+    cap = int(rng.choice([3, 10, 20]))
+    deskew = bool(rng.integers(0, 2))
+    mode = int(rng.choice([0, 0, 0, 3]))
+    beams = int(rng.choice([16, 32]))
+    az = int(rng.integers(500, 2000))
+    max_iter = int(rng.choice([30, 100]))
+    step = float(rng.choice([1.0, 2.0, 4.0]))
+    max_range = float(rng.choice([15.0, 30.0, 60.0]))
+    capacity = int(rng.choice([0, 512, 4096]))
+    scene = synth.Scene(seed=seed, n_boxes=int(rng.integers(10, 80)), n_cyl=int(rng.integers(5, 40)))
+    n = 10
+    traj = synth.loop_trajectory(n + 1, radius=30.0, step=step)
+    seq = [synth.cast_scan(scene, traj[i], traj[i + 1], beams=beams, azimuth_steps=az, seed=40 * seed + i, device="cuda:0") for i in range(n)]
+    cfg = dict(voxel_size=voxel, max_range=max_range, cap=cap, deskew=deskew, icp_max_iteration=max_iter, icp_mode=mode, map_capacity_voxels=capacity)
+    what = f"seed {seed}: {cfg}, {beams} x {az}, {step} m/scan"
+    k = ctx.KissICP(speculate=False, **cfg)
+    ref = []
+    for s in seq:
+        d, sr, p = k.register_frame(s)
+        ref.append((d, sr, p.copy(), k.stats.icp.iterations))
+    ref_dump = k.local_map().dump()
+    k.close()
+    kc = oracle.load_port().Kiss(voxel_size=voxel, max_range=max_range, cap=cap, deskew=deskew, icp_max_iteration=max_iter)
+    if mode:
+        kc.set_mode(mode)
+    staged = [torch.from_numpy(s).cuda() for s in seq]
+    torch.cuda.synchronize()
+    k = ctx.KissICP(speculate=True, **cfg)
+    for i, t in enumerate(staged):
+        if i + 1 < len(staged):
+            k.hint_next_dev(staged[i + 1].data_ptr(), len(seq[i + 1]))
+        p = k.register_frame_dev(t.data_ptr(), len(seq[i]))
+        np.testing.assert_allclose(p, ref[i][2], rtol=0, atol=1e-9, err_msg=f"{what}, scan {i}")
+        assert (k.stats.icp.iterations, k.stats.n_down, k.stats.n_keypoints) == (ref[i][3], len(ref[i][0]), len(ref[i][1])), (what, i)
+        dc, sc, pc = kc.register_cloud(np.ascontiguousarray(seq[i][:, :3]), seq[i][:, 3].astype(np.float64))
+        assert (len(dc), len(sc), kc.last_iterations()) == (k.stats.n_down, k.stats.n_keypoints, k.stats.icp.iterations), (what, i)
+        assert np.abs(p[4:] - pc[4:]).max() < 1e-5 and np.abs(p[:4] - pc[:4]).max() < 1e-6, (what, i, p, pc)
+    dump = k.local_map().dump()
+    assert np.array_equal(dump[0], ref_dump[0]) and np.array_equal(dump[1], ref_dump[1]), what
+    np.testing.assert_allclose(dump[2], ref_dump[2], rtol=0, atol=1e-9, err_msg=what)
+    pd = kc.map().dump()
+    if mode == 0:   # (poses equal to ~1e-15 under the reference's rules: the port's map holds the same voxels after the last eviction)
+        assert np.array_equal(pd[0], dump[0]) and np.array_equal(pd[1], dump[1]), (what, len(pd[0]), len(dump[0]))
+    k.close()
