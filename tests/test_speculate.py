@@ -562,3 +562,89 @@ def test_random_configurations_with_eviction_and_map_growth(ctx, pkg, seed):
     if mode == 0:   # (poses equal to ~1e-15 under the reference's rules: the port's map holds the same voxels after the last eviction)
         assert np.array_equal(pd[0], dump[0]) and np.array_equal(pd[1], dump[1]), (what, len(pd[0]), len(dump[0]))
     k.close()
+
+
+def _random_seeds_c():
+    """4 seeds in the suite; LIMU_RANDOM_SEEDS_C="lo-hi" widens the campaign (profiles/r2_random_campaign.json)."""
+    import os
+    spec = os.environ.get("LIMU_RANDOM_SEEDS_C", "")
+    if "-" in spec:
+        lo, hi = spec.split("-")
+        return range(int(lo), int(hi))
+    return range(2000, 2004)
+
+
+@pytest.mark.parametrize("seed", _random_seeds_c())
+def test_random_configurations_through_the_host_pointer_entries(ctx, pkg, seed):
+    """Third family: the entries a host application calls -- limu_odom_register_frame (packed x, y, z, t; pinned or pageable memory) with
+    limu_odom_prefetch, or limu_odom_register_cloud (48-byte point records + FP64 stamps) with limu_odom_prefetch_cloud -- on ragged scan
+    sizes, with a prefetch left out now and then. Pipelined against plain (1e-9, same clouds, same final map) and against the C port."""
+    import oracle
+    from importlib import import_module
+    synth = import_module("limu_b200.synth")
+    rng = np.random.default_rng(seed)
+    voxel = float(rng.choice([0.5, 1.0, 2.0]))
+    cap = int(rng.choice([1, 10, 20]))
+    deskew = bool(rng.integers(0, 2))
+    beams = int(rng.choice([8, 16, 32]))
+    az = int(rng.integers(300, 1800))
+    max_iter = int(rng.choice([30, 100]))
+    step = float(rng.choice([0.1, 0.5, 1.0]))
+    cloud_api = bool(rng.integers(0, 2))
+    pinned = bool(rng.integers(0, 2))
+    scene = synth.Scene(seed=seed, n_boxes=int(rng.integers(10, 80)), n_cyl=int(rng.integers(5, 40)))
+    n = 8
+    traj = synth.loop_trajectory(n + 1, radius=30.0, step=step)
+    seq = []
+    for i in range(n):
+        s = synth.cast_scan(scene, traj[i], traj[i + 1], beams=beams, azimuth_steps=az, seed=40 * seed + i, device="cuda:0")
+        seq.append(np.ascontiguousarray(s[: max(1, int(len(s) * rng.uniform(0.4, 1.0)))]))   # ragged sizes
+    skip = set(int(x) for x in np.nonzero(rng.random(n) < 0.2)[0])                           # scans whose prefetch is left out
+    cfg = dict(voxel_size=voxel, cap=cap, deskew=deskew, icp_max_iteration=max_iter)
+    what = f"seed {seed}: {cfg}, {beams} x {az}, {step} m/scan, {'cloud records' if cloud_api else 'packed scans'}, {'pinned' if pinned else 'pageable'}, no prefetch of {sorted(skip)}"
+    bufs = []
+
+    def hold(shape, dtype, fill):
+        if pinned:
+            b = pkg.PinnedArray(shape, dtype)
+            bufs.append(b)
+            b.array[...] = fill
+            return b.array
+        return np.ascontiguousarray(fill, dtype=dtype)
+
+    if cloud_api:
+        recs, tss = [], []
+        for s in seq:
+            r = np.zeros((len(s), 12), np.float32)
+            r[:, :3] = s[:, :3]
+            r[:, 4:] = rng.random((len(s), 8), dtype=np.float32)      # intensity / normal / curvature fields: must be ignored
+            recs.append(hold(r.shape, np.float32, r))
+            tss.append(hold((len(s),), np.float64, s[:, 3].astype(np.float64)))
+    else:
+        packed = [hold(s.shape, np.float32, s) for s in seq]
+
+    def run(spec):
+        k = ctx.KissICP(speculate=spec, **cfg)
+        out = []
+        for i in range(n):
+            if spec and i + 1 < n and (i + 1) not in skip:
+                if cloud_api:
+                    k.prefetch_cloud(recs[i + 1], 48, tss[i + 1])
+                else:
+                    k.prefetch(packed[i + 1])
+            d, sr, p = k.register_cloud(recs[i], 48, tss[i]) if cloud_api else k.register_frame(packed[i])
+            out.append((d, sr, p.copy(), k.stats.icp.iterations))
+        dump = k.local_map().dump()
+        k.close()
+        return out, dump
+
+    (a, da), (b, db) = run(False), run(True)
+    close_enough(b, a)
+    assert np.array_equal(da[0], db[0]) and np.array_equal(da[1], db[1]), what
+    kc = oracle.load_port().Kiss(voxel_size=voxel, max_range=100.0, cap=cap, deskew=deskew, icp_max_iteration=max_iter)
+    for i, s in enumerate(seq):
+        dc, sc, pc = kc.register_cloud(np.ascontiguousarray(s[:, :3]), s[:, 3].astype(np.float64))
+        assert (len(dc), len(sc), kc.last_iterations()) == (len(b[i][0]), len(b[i][1]), b[i][3]), (what, i)
+        assert np.abs(b[i][2][4:] - pc[4:]).max() < 1e-5 and np.abs(b[i][2][:4] - pc[:4]).max() < 1e-6, (what, i)
+    for x in bufs:
+        x.free()
