@@ -306,3 +306,62 @@ def test_prefetch_gives_identical_results(ctx, pkg):
         b.close()
     for p in pinned:
         p.free()
+
+
+def _random_seeds_d():
+    """4 seeds in the suite; LIMU_RANDOM_SEEDS_D="lo-hi" widens the campaign (profiles/r2_random_campaign.json)."""
+    import os
+    spec = os.environ.get("LIMU_RANDOM_SEEDS_D", "")
+    if "-" in spec:
+        lo, hi = spec.split("-")
+        return range(int(lo), int(hi))
+    return range(3000, 3004)
+
+
+@pytest.mark.parametrize("seed", _random_seeds_d())
+def test_random_shapes_per_function_bit_exact(ctx, port, seed):
+    """Seeded random shapes for the per-function entries: cloud sizes from 1 to ~200 000 (log-uniform, so tile and grid boundaries of every
+    size class are hit), voxel sizes down to 0.1 m, clouds with exact duplicates, points ON voxel faces and negative coordinates (the key
+    truncates toward zero), batches inserted into a map that has to grow. Everything integer or selected must equal the C port bit for bit."""
+    rng = np.random.default_rng(seed)
+    n = int(np.exp(rng.uniform(0.0, np.log(200000.0))))
+    voxel = float(rng.choice([0.1, 0.25, 0.3, 0.5, 1.0, 1.5, 2.0]))
+    spread = float(rng.choice([0.5, 3.0, 10.0, 40.0]))
+    cap = int(rng.choice([1, 3, 10, 20]))
+    pts = rng.normal(size=(n, 3)) * spread * np.array([1.0, 1.0, rng.choice([0.1, 1.0])])
+    k = n // 10
+    if k:
+        pts[:k] = pts[rng.integers(0, n, k)]                                       # exact duplicates
+        pts[k:2 * k] = np.round(pts[k:2 * k] / voxel) * voxel                      # on voxel faces / corners
+        pts[2 * k:2 * k + max(1, k // 8)] *= 1e-7                                  # crowd around the origin, both signs
+    what = f"seed {seed}: n {n}, voxel {voxel}, spread {spread}, cap {cap}"
+    assert np.array_equal(ctx.voxel_keys(pts, voxel), port.vox_index(pts, voxel)), what
+    assert np.array_equal(ctx.voxel_downsample(pts, voxel), port.voxel_downsample(pts, voxel)), what
+    assert np.array_equal(ctx.iqr_processing(pts), port.iqr(pts)), what
+    gs, gd = ctx.voxelize(pts, voxel)
+    os_, od = port.voxelize(pts, voxel)
+    assert np.array_equal(gs, os_) and np.array_equal(gd, od), what
+    max_d = float(rng.choice([2.0, 20.0, 100.0])) * max(voxel, 0.5)
+    gm, om = ctx.VoxelHashMap(voxel, max_d, cap, capacity_voxels=int(rng.choice([0, 64, 4096]))), port.Map(voxel, max_d, cap)
+    cuts = sorted(set(int(x) for x in rng.integers(0, n + 1, 3)) | {0, n})
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        gm.insert_points(pts[lo:hi])
+        om.insert(pts[lo:hi])
+    gk, gc, gp = gm.dump()
+    ok, oc, op = om.dump()
+    assert np.array_equal(gk, ok) and np.array_equal(gc, oc) and np.array_equal(gp, op), what
+    q = pts[rng.integers(0, n, min(n, 20000))] + rng.normal(size=(min(n, 20000), 3)) * voxel * 0.7
+    gout, gkey, grank = gm.get_closest_neighbour(q, with_index=True)
+    oout, okey, orank = om.closest(q, with_index=True)
+    assert np.array_equal(gkey, okey) and np.array_equal(grank, orank) and np.array_equal(gout, oout), what
+    tau = float(rng.choice([0.3, 1.0, 2.5])) * voxel
+    gs, gt = gm.get_correspondences(q, tau)
+    os_, ot = om.correspondences(q, tau)[:2]
+    assert np.array_equal(gs, os_) and np.array_equal(gt, ot), what
+    origin = pts[int(rng.integers(0, n))]
+    gm.remove_points_from_far(origin)
+    om.remove_far(origin)
+    gk, gc, gp = gm.dump()
+    ok, oc, op = om.dump()
+    assert np.array_equal(gk, ok) and np.array_equal(gc, oc) and np.array_equal(gp, op), what + " (after the eviction)"
+    gm.close()
