@@ -114,6 +114,32 @@ def test_plane_variant_follows_the_sensor_where_point_to_point_does_not(port):
     assert abs(travelled[NN27 | PLANE] - truth) < 0.05 * truth
 
 
+@pytest.mark.parametrize("seed", [67, 214, 220, 250])
+def test_plane_prior_keeps_a_starved_first_registration_near_the_prediction(port, seed):
+    """Four of the seven random configurations whose first registration ran away (by up to 20 m) before the point-to-plane solve had its prior
+    (profiles/r2_random_campaign.json; same construction as tests/test_speculate.py::test_random_configurations_pipelined_vs_plain_vs_port):
+    the one-scan map offers the keypoints 0..25 planar voxels, so the pose of scan 1 must stay within the distance travelled of the prediction."""
+    synth = synth_mod()
+    rng = np.random.default_rng(1000 + seed)
+    voxel = float(rng.choice([0.25, 0.5, 1.0, 2.0]))
+    cap = int(rng.choice([1, 3, 10, 20]))
+    deskew = bool(rng.integers(0, 2))
+    mode = int(rng.choice([0, 0, 0, 3]))
+    beams = int(rng.choice([8, 16, 32, 64]))
+    az = int(rng.integers(300, 2500))
+    max_iter = int(rng.choice([5, 60, 500]))
+    step = float(rng.choice([0.1, 0.5, 1.0]))
+    assert mode == (NN27 | PLANE)
+    scene = synth.Scene(seed=50 + seed, n_boxes=int(rng.integers(10, 80)), n_cyl=int(rng.integers(5, 40)))
+    traj = synth.loop_trajectory(8, radius=30.0, step=step)
+    k = port.Kiss(voxel_size=voxel, max_range=100.0, cap=cap, deskew=deskew, icp_max_iteration=max_iter)
+    k.set_mode(mode)
+    for i in range(2):
+        s = synth.cast_scan(scene, traj[i], traj[i + 1], beams=beams, azimuth_steps=az, seed=40 * seed + i)
+        _, _, p = k.register_cloud(np.ascontiguousarray(s[:, :3]), s[:, 3].astype(np.float64))
+    assert np.linalg.norm(p[4:]) < 1.5 * step + 0.05 and np.abs(p[:3]).max() < 0.02, (seed, p)   # (without the prior: 0.4 .. 27 m, up to 120 degrees)
+
+
 # ---------------------------------------------------------------------------------------------------------------- GPU
 @pytest.fixture(scope="module")
 def ctx():
