@@ -248,3 +248,50 @@ def test_mt_flavour_matches_serial(ref, ref_mt, rng):
     b = ref_mt.align(sb, tb, 0.5)["pose"]
     np.testing.assert_allclose(b, a, rtol=0, atol=1e-11)    # join order differs from the serial sum
     assert np.array_equal(ref.iqr(world), ref_mt.iqr(world))
+
+
+def _random_seeds_p():
+    """4 seeds in the suite; LIMU_RANDOM_SEEDS_P="lo-hi" widens the campaign (profiles/r2_random_campaign.json)."""
+    import os
+    spec = os.environ.get("LIMU_RANDOM_SEEDS_P", "")
+    if "-" in spec:
+        lo, hi = spec.split("-")
+        return range(int(lo), int(hi))
+    return range(4)
+
+
+@pytest.mark.parametrize("seed", _random_seeds_p())
+def test_random_configurations_port_vs_compiled_reference(ref, port, seed):
+    """The pin of the C restatement widened: seeded random configurations (voxel size, cap, deskew, scan shape, iteration cap, metres per
+    scan, scene -- the generator of the GPU suite's first random family, reference rules only) through the COMPILED reference's
+    register_frame (icp.cpp:49-86) and through the port: same cloud sizes on every scan, bit-equal clouds while the deskew gate is closed,
+    poses to 1e-7 m / 1e-8."""
+    import __graft_entry__ as g
+    g.load_package()
+    from importlib import import_module
+    synth = import_module("limu_b200.synth")
+    rng = np.random.default_rng(1000 + seed)
+    voxel = float(rng.choice([0.25, 0.5, 1.0, 2.0]))
+    cap = int(rng.choice([1, 3, 10, 20]))
+    deskew = bool(rng.integers(0, 2))
+    rng.choice([0, 0, 0, 3])                        # (the GPU family draws a registration variant here; the reference has only its own)
+    beams = int(rng.choice([8, 16, 32, 64]))
+    az = int(rng.integers(300, 2500))
+    max_iter = min(int(rng.choice([5, 60, 500])), 60)   # (the compiled reference needs ~0.1 s per iteration on a large scan)
+    step = float(rng.choice([0.1, 0.5, 1.0]))
+    az = min(az, 40000 // beams)
+    scene = synth.Scene(seed=50 + seed, n_boxes=int(rng.integers(10, 80)), n_cyl=int(rng.integers(5, 40)))
+    traj = synth.loop_trajectory(7, radius=30.0, step=step)
+    kr = ref.Kiss(voxel_size=voxel, max_range=100.0, cap=cap, deskew=deskew, icp_max_iteration=max_iter)
+    kp = port.Kiss(voxel_size=voxel, max_range=100.0, cap=cap, deskew=deskew, icp_max_iteration=max_iter)
+    what = f"seed {seed}: voxel {voxel}, cap {cap}, deskew {deskew}, {beams} x {az}, cap {max_iter} iterations, {step} m/scan"
+    for i in range(6):
+        s = synth.cast_scan(scene, traj[i], traj[i + 1], beams=beams, azimuth_steps=az, seed=40 * seed + i)
+        xyz, ts = np.ascontiguousarray(s[:, :3]), s[:, 3].astype(np.float64)
+        da, sa, pa = kr.register_cloud(xyz, ts)
+        db, sb, pb = kp.register_cloud(xyz, ts)
+        assert da.shape == db.shape and sa.shape == sb.shape, (what, i)
+        if i < 3 or not deskew:
+            assert np.array_equal(da, db) and np.array_equal(sa, sb), (what, i)
+        np.testing.assert_allclose(pb[4:], pa[4:], rtol=0, atol=1e-7, err_msg=f"{what}, scan {i}")
+        np.testing.assert_allclose(pb[:4], pa[:4], rtol=0, atol=1e-8, err_msg=f"{what}, scan {i}")
