@@ -275,3 +275,30 @@ def test_register_msg_matches_oracle_pipeline(ctx, port):
         assert np.abs(poses[0][4:] - pose_o[4:]).max() < 1e-5 and np.abs(poses[0][:4] - pose_o[:4]).max() < 1e-6
         assert stats[0].n_points == sizes[0] and stats[0].icp.iterations == port._kiss_last_iterations(ko.h)
     kg.close()
+
+
+def _random_seeds_e():
+    """4 seeds in the suite; LIMU_RANDOM_SEEDS_E="lo-hi" widens the campaign (profiles/r2_random_campaign.json)."""
+    spec = os.environ.get("LIMU_RANDOM_SEEDS_E", "")
+    if "-" in spec:
+        lo, hi = spec.split("-")
+        return range(int(lo), int(hi))
+    return range(4000, 4004)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", _random_seeds_e())
+def test_cuda_matches_oracle_at_random_shapes(ctx, port, seed):
+    """frame::Lidar::process_frame (frame.cpp:28-193) on the device against the oracle at seeded random shapes: message sizes 1 .. 150 000
+    points (log-uniform), 1 .. 6 frame segments, any scan count (the first 20 messages are not split), distinct stamps or columns that
+    share a firing time."""
+    rng = np.random.default_rng(seed)
+    n = int(np.exp(rng.uniform(0.0, np.log(150000.0))))
+    ties = bool(rng.random() < 0.25)
+    split = 1 if ties else int(rng.integers(1, 7))
+    sc = int(rng.choice([1, 7, 19, 20, 21, 50]))
+    beams = int(rng.choice([16, 32, 64]))
+    data, fields, mt = make_msg(seed, n, beams=beams, kind="ties" if ties else "distinct")
+    cfg = dict(CFG, frame_split_num=split, num_scan_lines=beams)
+    a, b = port.process_frame(data, fields, cfg, mt, sc), ctx.process_frame(data, fields, cfg, mt, sc)
+    assert_segments_equal(a, b)
