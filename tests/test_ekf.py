@@ -173,3 +173,55 @@ def test_update_and_propagate_and_orientation(pkg):
     m2, P2, _ = b.state()
     assert np.abs(m2 - m_exp).max() < 1e-12 and np.abs(P2 - P_exp).max() < 1e-15
     a.close(); b.close()
+
+
+def _random_seeds_k():
+    """4 seeds in the suite; LIMU_RANDOM_SEEDS_K="lo-hi" widens the campaign (profiles/r2_random_campaign.json)."""
+    import os
+    spec = os.environ.get("LIMU_RANDOM_SEEDS_K", "")
+    if "-" in spec:
+        lo, hi = spec.split("-")
+        return range(int(lo), int(hi))
+    return range(5000, 5004)
+
+
+@pytest.mark.parametrize("seed", _random_seeds_k())
+def test_ekf_matches_compiled_reference_on_random_scripts(pkg, seed):
+    """kalman::EKF (ekf.cpp:11-290, 521-764) behind limu_ekf_* against the compiled reference on seeded random scripts: IMU stream length,
+    pose-trail length, noise scale, initial state, extrinsics, and WHERE the quaternion normalisation, the pose-trail augmentation, its
+    undo and the zero-velocity update fall between the predictions. State 1e-11, covariance 1e-12 relative."""
+    import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/liblimu_ref.so not built (needs /root/reference at build time)")
+    rng = np.random.default_rng(seed)
+    trail = int(rng.choice([3, 5, 10, 20]))
+    noise_scale = float(rng.uniform(0.5, 3.0))
+    n_imu = int(rng.integers(30, 110))
+    t, xg, xa = imu_stream(rng, n_imu, t0=float(rng.uniform(0.0, 1e4)), rate=float(rng.choice([100.0, 200.0, 400.0])))
+    steps, augmented = [], 0
+    for i in range(n_imu):
+        steps.append(("predict", t[i], xg[i], xa[i]))
+        r = rng.random()
+        if r < 0.15:
+            steps.append(("normalize", bool(rng.integers(0, 2))))
+        elif r < 0.25:
+            steps.append(("augment",))
+            augmented += 1
+        elif r < 0.30 and augmented:
+            steps.append(("undo",))
+            augmented -= 1
+        elif r < 0.35:
+            steps.append(("zupt", float(10.0 ** rng.uniform(-4, -1))))
+    a = pkg.Ekf(lidar_pose_trail=trail, noise_scale=noise_scale)
+    b = oracle.RefEkf(lidar_pose_trail=trail, noise_scale=noise_scale)
+    m0, P0, _ = a.state()
+    m0[0:3] = rng.normal(size=3) * 5.0
+    m0[3:6] = rng.normal(size=3)
+    q = rng.normal(size=4); q[0] = abs(q[0]) + 0.5; m0[6:10] = q / np.linalg.norm(q)
+    m0[10:13] = rng.normal(size=3) * 2e-3; m0[13:16] = rng.normal(size=3) * 2e-2; m0[16:19] = 1.0 + rng.normal(size=3) * 0.01; m0[19:22] = GRAV
+    P0[6:10, 6:10] = np.diag([1e-6, 1e-6, 1e-6, 0.0]) * noise_scale ** 2
+    a.set_state(m0, P0); b.set_state(m0, P0)
+    trans = rng.normal(size=3) * 0.1
+    rot = [ROT, np.eye(3), np.array([[-1.0, 0.0, 0.0], [0.0, -1.0, 0.0], [0.0, 0.0, 1.0]])][int(rng.integers(0, 3))]
+    compare(run_script(a, steps, GRAV, trans, rot), run_script(b, steps, GRAV, trans, rot), 1e-11)
+    a.close()
