@@ -65,6 +65,35 @@ def test_forward_pass_matches_the_reference_ekf(pkg, ref, port, rng, case):
     assert np.all(np.abs(wb - r["written_back"]) <= ulp) and (wb != r["written_back"]).mean() < 1e-3
 
 
+def _random_seeds_n():
+    """4 seeds in the suite; LIMU_RANDOM_SEEDS_N="lo-hi" widens the campaign (profiles/r2_random_campaign.json)."""
+    import os
+    spec = os.environ.get("LIMU_RANDOM_SEEDS_N", "")
+    if "-" in spec:
+        lo, hi = spec.split("-")
+        return range(int(lo), int(hi))
+    return range(6000, 6004)
+
+
+@pytest.mark.parametrize("seed", _random_seeds_n())
+def test_forward_pass_matches_the_reference_ekf_on_random_windows(pkg, ref, port, seed):
+    """Seeded random IMU windows (2 .. 60 samples at 100 / 200 / 400 Hz, rates up to ~3 rad/s, accelerations up to ~2 g, where the window
+    starts before the scan) through limu_imu_forward_pass and through the compiled reference's own forward pass: pose table, scan-end
+    rotation and lidar position to 1e-11; the per-point loop fed with OUR table writes the reference's floats back (<= 1 ulp)."""
+    r_ = np.random.default_rng(seed)
+    case = dict(k=int(r_.integers(2, 61)), dt=float(r_.choice([0.0025, 0.005, 0.01])), n=int(r_.integers(50, 3000)),
+                gyr=tuple(r_.normal(size=3) * r_.choice([0.05, 0.5, 1.5])), acc=tuple(np.array([0.0, 0.0, 9.81]) + r_.normal(size=3) * r_.choice([0.3, 3.0])),
+                first_offset=-float(r_.uniform(1e-4, 0.03)))
+    r, table, rot_end, ple, st, (xyz, curv, pil) = forward_and_reference(pkg, ref, r_, **case)
+    assert table.shape == r["table"].shape, case
+    np.testing.assert_allclose(table, r["table"], rtol=0, atol=1e-11, err_msg=str(case))
+    np.testing.assert_allclose(rot_end, r["rot_end"], rtol=0, atol=1e-11, err_msg=str(case))
+    np.testing.assert_allclose(ple, r["pos_lidar_end"], rtol=0, atol=1e-11, err_msg=str(case))
+    out, wb = port.deskew_imu(xyz, curv, table, rot_end, ple, pil)
+    ulp = np.spacing(np.abs(r["written_back"]).astype(np.float32))
+    assert np.all(np.abs(wb - r["written_back"]) <= ulp), case
+
+
 @pytest.mark.parametrize("last_end", [50.013, 50.0301, 49.99, 50.0958])   # (with every pair skipped the reference reads uninitialised vectors)
 def test_pairs_older_than_the_previous_scan_end(pkg, ref, rng, last_end):
     """ekf.cpp:322-323 (pairs entirely before the previous scan's end are skipped) and :340-341 (the straddling pair is cut)."""
