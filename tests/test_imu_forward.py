@@ -123,3 +123,21 @@ def test_forward_pass_feeds_the_cuda_deskew(pkg, ref, rng):
     assert np.all(np.abs(wb - r["written_back"]) <= ulp) and (wb != r["written_back"]).mean() < 1e-3
     assert np.array_equal(out, wb.astype(np.float64))
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", _random_seeds_n())
+def test_cuda_deskew_on_random_windows(pkg, ref, seed):
+    """The same random windows through the CUDA per-point loop (limu_deskew_imu, csrc/imu_deskew.cu) fed with OUR forward pass:
+    the reference's written-back floats within 1 ulp."""
+    r_ = np.random.default_rng(seed)
+    case = dict(k=int(r_.integers(2, 61)), dt=float(r_.choice([0.0025, 0.005, 0.01])), n=int(r_.integers(50, 3000)),
+                gyr=tuple(r_.normal(size=3) * r_.choice([0.05, 0.5, 1.5])), acc=tuple(np.array([0.0, 0.0, 9.81]) + r_.normal(size=3) * r_.choice([0.3, 3.0])),
+                first_offset=-float(r_.uniform(1e-4, 0.03)))
+    r, table, rot_end, ple, st, (xyz, curv, pil) = forward_and_reference(pkg, ref, r_, **case)
+    ctx = pkg.Context(0)
+    out, wb = ctx.deskew_imu(np.concatenate([xyz, curv[:, None]], 1).astype(np.float32), table, rot_end, ple, pil)
+    ulp = np.spacing(np.abs(r["written_back"]).astype(np.float32))
+    assert np.all(np.abs(wb - r["written_back"]) <= ulp), case
+    assert np.array_equal(out, wb.astype(np.float64))
+    ctx.close()
